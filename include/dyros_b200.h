@@ -1,0 +1,229 @@
+/* dyros_b200.h -- C ABI of libdyros_b200.so (hand-written sm_100a CUDA behind the Isaac Gym tensor API).
+ *
+ * Drop-in boundary for ONE hot path of kdh0429/IsaacGymDyros: the per-step vectorised environment
+ * behind `python train.py task=DyrosDynamicWalk`.  Paths below are relative to the reference root:
+ *   T  = python/IsaacGymEnvs/isaacgymenvs/tasks/dyros_dynamic_walk.py
+ *   VT = python/IsaacGymEnvs/isaacgymenvs/tasks/base/vec_task.py
+ *   DOCT = docs/_sources/programming/tensors.rst.txt   (Isaac Gym tensor API contract)
+ *
+ * Conventions
+ *   - Every pointer in DyrosSimBuffers / DyrosTaskBuffers is a DEVICE pointer into memory owned by the
+ *     caller (torch allocations); the library keeps the pointers, never frees them, and allocates only
+ *     its own constant model tables at create time (no allocation after dyros_sim_create).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  No call synchronises the
+ *     host; every call is capturable in a CUDA graph.
+ *   - Return value: 0 = ok, non-zero = error; dyros_last_error() gives the message (thread-local).
+ *   - Tensor layouts are the reference's: root (N,13) [pos3, quat xyzw, linvel3, angvel3] DOCT:50-62;
+ *     dof_state (N*nd,2) [pos,vel] DOCT:154-156; net contact force (N*nb,3) DOCT:267-279;
+ *     actuation force (N*nd) DOCT:300-311; reset/progress/timeout/randomize buffers int64 VT:248-255.
+ */
+#ifndef DYROS_B200_H
+#define DYROS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DYROS_ABI_VERSION 1
+#define DYROS_MAX_LINKS 40
+#define DYROS_MAX_BODIES 48
+#define DYROS_LANES 4 /* lanes per env in the physics kernel (branch-parallel recursions) */
+
+typedef struct DyrosSim DyrosSim;   /* replaces the `sim` handle of gym.create_sim (VT:270) */
+typedef struct DyrosTask DyrosTask; /* per-env task state of DyrosDynamicWalk (T:58-195) */
+
+/* Flat model tables (host pointers, float64/int32; see isaacgymdyros_b200/model/tables.py).
+ * Replaces what gym.load_asset + create_actor build inside the closed importer (T:293, T:354). */
+typedef struct {
+  int32_t num_links, num_bodies, num_dofs, num_points, num_cyls, num_solver_links, sched_slots;
+  const int32_t* link_parent; /* [nl] */
+  const int32_t* link_dof;    /* [nl] */
+  const double* link_E;       /* [nl*9] */
+  const double* link_r;       /* [nl*3] */
+  const double* link_axis;    /* [nl*3] */
+  const int32_t* body_link;   /* [nb] */
+  const double* body_pos;     /* [nb*3] */
+  const double* body_rot;     /* [nb*9] */
+  const double* body_inertia; /* [nb*10] */
+  const double* dof_lower;    /* [nd] */
+  const double* dof_upper;    /* [nd] */
+  const double* dof_vel_limit;/* [nd]  dof_prop['velocity'], T:372 */
+  const double* dof_effort;   /* [nd]  MJCF ctrlrange; used only if clamp_effort */
+  const int32_t* pt_link;     /* [np] */
+  const int32_t* pt_body;     /* [np] */
+  const double* pt_pos;       /* [np*3] */
+  const double* pt_radius;    /* [np] */
+  const int32_t* cyl_link;    /* [nc] */
+  const int32_t* cyl_body;    /* [nc] */
+  const double* cyl_center;   /* [nc*3] */
+  const double* cyl_axis;     /* [nc*3] */
+  const double* cyl_size;     /* [nc*2] radius, half height */
+  const int32_t* solver_links;/* [ns] links whose ground contacts are constraint-solved (feet) */
+  const int32_t* sched;       /* [sched_slots*DYROS_LANES] */
+} DyrosModelDesc;
+
+/* gymapi.SimParams / PhysXParams subset that reaches the solver (VT:423-471, DyrosDynamicWalk.yaml:37-56)
+ * plus the named model options of SURVEY D2. */
+typedef struct {
+  int32_t num_envs;
+  int32_t device;
+  double dt;                /* sim.dt = 0.002 (double: derived constants are formed in double as Python does) */
+  int32_t substeps;         /* sim.substeps = 1 (sub-steps inside one gym.simulate) */
+  float gravity[3];
+  float contact_offset;     /* physx.contact_offset 0.002 */
+  float max_depenetration_velocity; /* 10 */
+  int32_t contact_sweeps;   /* PGS sweeps with penetration bias (physx.num_position_iterations scaled) */
+  int32_t contact_final_sweeps; /* sweeps without bias (physx.num_velocity_iterations) */
+  float friction;           /* combined plane/shape friction, terrain_cfg.py:7-8 -> 1.0 */
+  float penalty_stiffness;  /* non-solver-link ground contact (N/m) */
+  float penalty_damping;    /* (N s/m) */
+  float max_angular_velocity; /* AssetOptions.max_angular_velocity T:289 */
+  int32_t clamp_effort;     /* clamp actuation to MJCF ctrlrange (default 0) */
+} DyrosSimDesc;
+
+/* Device buffers behind the gym tensor API (all owned by the caller). */
+typedef struct {
+  float* root_states;        /* (N,13)      acquire_actor_root_state_tensor  T:73 */
+  float* dof_state;          /* (N*nd,2)    acquire_dof_state_tensor         T:74 */
+  float* net_contact_force;  /* (N*nb,3)    acquire_net_contact_force_tensor T:75 */
+  float* rigid_body_state;   /* (N*nb,13)   acquire_rigid_body_state_tensor  T:76 (may be NULL) */
+  float* dof_actuation_force;/* (N*nd)      set_dof_actuation_force_tensor   T:520 */
+  float* rb_force;           /* (N*nb,3)    apply_rigid_body_force_tensors   T:502 (may be NULL) */
+  float* rb_torque;          /* (N*nb,3)    (may be NULL) */
+  float* dof_damping;        /* (N,nd) per-env dof_prop['damping']  T:365 + DR */
+  float* dof_armature;       /* (N,nd) per-env dof_prop['armature'] T:366-371 + DR */
+  float* body_mass_scale;    /* (N,nb) per-env rigid_body_properties.mass scaling (setup-only DR) */
+} DyrosSimBuffers;
+
+/* Per-env task state (names = the reference attributes, T:87-195; internal integers are int32). */
+typedef struct {
+  /* VecTask API buffers (VT:242-255) */
+  float* obs_buf;            /* (N,487) */
+  float* rew_buf;            /* (N) */
+  int64_t* reset_buf;        /* (N) */
+  int64_t* timeout_buf;      /* (N) */
+  int64_t* progress_buf;     /* (N) */
+  int64_t* randomize_buf;    /* (N) */
+  float* stacked_rewards;    /* (N,15) extras["stacked_rewards"] T:415-427 */
+  int64_t* reset_env_ids;    /* (N) compacted ascending ids, T:554 */
+  int32_t* reset_env_ids32;  /* (N) int32 copy, T:737,745 */
+  int32_t* reset_count;      /* (1) */
+  /* task attributes */
+  float* actions;            /* (N,13) */
+  float* actions_pre;        /* (N,13) */
+  float* time;               /* (N) */
+  int32_t* init_mocap_data_idx; /* (N) */
+  int32_t* mocap_data_idx;   /* (N) */
+  float* target_data_qpos;   /* (N,33) */
+  float* target_data_force;  /* (N,2) */
+  float* action_torque;      /* (N,12) */
+  float* action_torque_pre;  /* (N,12) */
+  float* motor_constant_scale; /* (N,12) */
+  float* action_log;         /* (N,6,12) delay ring, linear layout as T:166 */
+  int32_t* delay_idx;        /* (N) delay_idx_tensor[:,1] */
+  int32_t* simul_len;        /* (N) simul_len_tensor[:,1] */
+  float* qpos_noise;         /* (N,33) */
+  float* qvel_noise;         /* (N,33) */
+  float* qpos_pre;           /* (N,33) */
+  float* qpos_bias;          /* (N,12) */
+  float* quat_bias;          /* (N,3) */
+  float* target_vel;         /* (N,2) */
+  float* pre_joint_velocity_states; /* (N,33) */
+  float* contact_forces_pre; /* (N,38,3) */
+  float* total_mass;         /* (N) */
+  float* env_origins;        /* (N,3) */
+  float* epi_len;            /* (N) */
+  float* epi_len_log;        /* (N) */
+  float* contact_reward_sum; /* (N) */
+  float* contact_reward_mean;/* (N) */
+  int32_t* perturbation_count; /* (N) */
+  int32_t* pert_duration;    /* (N) */
+  int32_t* pert_on;          /* (N) 0/1 */
+  int32_t* impulse;          /* (N) */
+  float* magnitude;          /* (N) */
+  float* phase;              /* (N) */
+  int32_t* perturb_timing;   /* (N) */
+  int32_t* perturb_start;    /* (1) sticky curriculum flag, T:489-490 */
+  float* push_force;         /* (N,3) pelvis force for the next substep, forces[:,pelvis,:] T:498-499 */
+  float* obs_history;        /* (N,20,37) ring; slot (head+1+j)%20 = reference history position j */
+  float* action_history;     /* (N,20,13) ring */
+  int32_t* obs_hist_head;    /* (N) newest slot */
+  int32_t* act_hist_head;    /* (N) newest slot */
+  /* shared tables */
+  const float* mocap_data;   /* (3600,36) T:112-113 */
+  const float* obs_mean;     /* (37) */
+  const float* obs_var;      /* (37) */
+} DyrosTaskBuffers;
+
+/* Constants of the task. */
+typedef struct {
+  int32_t skipframe;         /* controlFrequencyInv = 2 */
+  float max_episode_length;  /* 8000.0 */
+  float death_cost;          /* 0.0 */
+  float initial_height;      /* 0.93 */
+  int32_t perturb;           /* env.perturbation */
+  int32_t randomize;         /* task.randomize: re-draw damping/armature on reset (VT:519-733) */
+  float dr_damping_base, dr_damping_lo, dr_damping_hi;  /* 0.1, +U[0,2.9] */
+  float dr_armature_lo, dr_armature_hi;                 /* xU[0.8,1.2] of the base table */
+  const double* dr_armature_base;                       /* [nd] host pointer, T:366-371 */
+  int32_t mocap_rows;        /* 3600 */
+  const float* kp;           /* [33] host, already /9 in float32 (T:58-63) */
+  const float* kv;           /* [33] host, already /3 in float32 (T:65-70) */
+  const float* action_high;  /* [33] host (T:296-301) */
+  const float* initial_dof_pos; /* [33] host (T:95-100) */
+  int32_t left_foot_body, right_foot_body, pelvis_body; /* find_asset_rigid_body_index T:304-306 */
+  uint64_t seed;             /* Philox key (config.yaml:11 seed 42 + rank) */
+} DyrosTaskDesc;
+
+/* Test-mode noise injection: env-indexed draws replacing the Philox streams. Any NULL
+ * member keeps its production stream. */
+typedef struct {
+  const float* qpos_normal;  /* (skipframe,N,33) outputs of torch.normal(0,0.00016/3) T:528 */
+  const float* vel_u;        /* (N,6)  torch.rand T:766 */
+  const float* reset_f;      /* (N,32) [qpos_bias u12, quat_bias u3, ft u2(unused), vel_mag, vel_theta, mocap, motor u12, pad2] */
+  const int64_t* reset_i;    /* (N,2)  [delay, perturb_timing] T:652,665 */
+  const int64_t* pert_i;     /* (N,2)  [impulse, duration] T:440-441 */
+  const float* pert_f;       /* (N,1)  T:443 */
+  const float* dr_u;         /* (N,66) [damping u33, armature u33] */
+} DyrosNoiseInjection;
+
+const char* dyros_last_error(void);
+int dyros_abi_version(void);
+
+/* --- gym level (replaces gym.create_sim / prepare_sim / simulate, VT:270, VT:196, T:525) --- */
+int dyros_sim_create(const DyrosSimDesc* desc, const DyrosModelDesc* model, const DyrosSimBuffers* buf, DyrosSim** out);
+int dyros_sim_destroy(DyrosSim* sim);
+/* gym.simulate: one time step dt (in `substeps` sub-steps) from dof_actuation_force (+ pending rb_force/torque
+ * when apply_wrench != 0, consumed by the first sub-step, DOCT:322-335). */
+int dyros_simulate(DyrosSim* sim, int apply_wrench, void* stream);
+/* gym.refresh_rigid_body_state_tensor: forward kinematics into rigid_body_state (DOCT:193-207). */
+int dyros_refresh_rigid_body_state(DyrosSim* sim, void* stream);
+/* gym.set_dof_state_tensor_indexed / set_actor_root_state_tensor_indexed (T:738,746): buffers are the live state
+ * already (immediate CPU-pipeline semantics); validates the ids and returns. */
+int dyros_set_state_indexed(DyrosSim* sim, const int32_t* env_ids, int count, void* stream);
+
+/* --- task level (bodies of DyrosDynamicWalk methods) --- */
+int dyros_task_create(DyrosSim* sim, const DyrosTaskDesc* desc, const DyrosTaskBuffers* buf, DyrosTask** out);
+int dyros_task_destroy(DyrosTask* task);
+int dyros_task_set_noise_injection(DyrosTask* task, const DyrosNoiseInjection* inj);
+int dyros_task_prologue(DyrosTask* task, const float* actions, void* stream);      /* VT:307 + T:449-502 */
+int dyros_task_substep_torque(DyrosTask* task, void* stream);                      /* T:505-520 -> dof_actuation_force */
+int dyros_task_sensor_noise(DyrosTask* task, int substep, void* stream);           /* T:528-530 */
+int dyros_task_epilogue(DyrosTask* task, void* stream);                            /* T:532-541 + VT:325 + T:544-545 */
+int dyros_task_check_termination(DyrosTask* task, void* stream);                   /* T:581-596 */
+int dyros_task_compute_reward(DyrosTask* task, void* stream);                      /* T:387-428, T:802-947 */
+int dyros_task_compact_resets(DyrosTask* task, void* stream);                      /* T:554 nonzero + curriculum gate sums T:489 */
+int dyros_task_reset_idx(DyrosTask* task, const int64_t* env_ids, int count, void* stream); /* T:598-669; env_ids NULL = use compacted list */
+int dyros_task_compute_observations(DyrosTask* task, void* stream);                /* T:750-796 */
+int dyros_task_late_update(DyrosTask* task, void* stream);                         /* T:560-563 */
+/* Whole VecTask.step (VT:293-344) in the fewest launches; same results as the staged calls. */
+int dyros_task_step(DyrosTask* task, const float* actions, void* stream);
+/* Number of kernel launches dyros_task_step enqueues (for bench.py's gpu_launches). */
+int dyros_task_step_launches(DyrosTask* task);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYROS_B200_H */

@@ -1,0 +1,630 @@
+// K2/K3/K4: the bodies of DyrosDynamicWalk's per-step methods as sm_100a kernels (one warp per env).
+//
+// Compiled with -fmad=false: the reference computes every float32 op separately (CPU torch / op-by-op
+// ATen), and parity is judged at 1e-5 relative with bit-exact masks, so no FMA contraction here.
+// Citations: T = tasks/dyros_dynamic_walk.py, VT = tasks/base/vec_task.py, JU = utils/torch_jit_utils.py,
+// TU = isaacgym/torch_utils.py (all under the reference's python/ tree).
+#include "internal.h"
+
+namespace dyros {
+
+struct TK {
+  TaskParams p;
+  DyrosTaskBuffers b;
+  DyrosSimBuffers s;
+  DyrosNoiseInjection j;
+};
+
+constexpr int kWarpsPerBlock = 4;
+
+// ------------------------------------------------------------------ small math (TU / JU restated)
+// JU:374-395 with x_dot_0 = x_dot_f = 0.0 (T:458-461), reference operation order
+__device__ __forceinline__ float cubic0(float time, float t0, float tf, float x0, float xf) {
+  float e = time - t0;
+  float tt = tf - t0;
+  float tt2 = tt * tt;
+  float tt3 = tt2 * tt;
+  float tx = xf - x0;
+  float c = x0 + 0.0f * e;
+  c = c + ((3.0f * tx) / tt2 - 0.0f / tt - 0.0f / tt) * e * e;
+  c = c + ((-2.0f * tx) / tt3 + 0.0f / tt2) * e * e * e;
+  float xt = (time > tf) ? xf : x0;
+  if (t0 <= time && time <= tf) xt = c;
+  return xt;
+}
+
+// JU:142-160 with a = identity: |vec(a (x) conj(q))| through the TU:20-40 product, then 2*asin(min(.,1))
+__device__ __forceinline__ float quat_err_identity(const float* q) {
+  float x2 = -q[0], y2 = -q[1], z2 = -q[2], w2 = q[3];
+  const float x1 = 0.f, y1 = 0.f, z1 = 0.f, w1 = 1.f;
+  float ww = (z1 + x1) * (x2 + y2);
+  float yy = (w1 - y1) * (w2 + z2);
+  float zz = (w1 + y1) * (w2 - z2);
+  float xx = ww + yy + zz;
+  float qq = 0.5f * (xx + (z1 - x1) * (x2 - y2));
+  float x = qq - xx + (x1 + w1) * (x2 + w2);
+  float y = qq - yy + (w1 - x1) * (y2 + z2);
+  float z = qq - zz + (z1 + y1) * (w2 - x2);
+  float n = sqrtf(x * x + y * y + z * z);
+  return 2.0f * asinf(fminf(n, 1.0f));
+}
+
+// TU:228-273 quat2euler (xyzw) -> component `which` (0:x 1:y 2:z)
+__device__ __forceinline__ float quat2euler_comp(const float* q, int which) {
+  float w = q[3], x = q[0], y = q[1], z = q[2];
+  float m00 = w * w + x * x - y * y - z * z;
+  float m01 = 2.f * x * y - 2.f * w * z;
+  float m10 = 2.f * x * y + 2.f * w * z;
+  float m11 = w * w - x * x + y * y - z * z;
+  float m20 = 2.f * x * z - 2.f * w * y;
+  float m21 = 2.f * y * z + 2.f * w * x;
+  float m22 = w * w - x * x - y * y + z * z;
+  float cy = sqrtf(m00 * m00 + m10 * m10);
+  bool cond = cy > (float)(2.220446049250313e-16 * 4);
+  if (which == 2) return cond ? atan2f(m10, m00) : atan2f(-m01, m11);
+  if (which == 1) return atan2f(-m20, cy);
+  return cond ? atan2f(m21, m22) : 0.0f;
+}
+
+__device__ __forceinline__ bool collision_true(const TK& k, int e, int lane) {
+  // T:590 / T:937: any non-foot body with |F| > 1
+  bool hit = false;
+  for (int b = lane; b < NB; b += kWarp) {
+    if (b == k.p.lfoot || b == k.p.rfoot) continue;
+    const float* f = k.s.net_contact_force + ((size_t)e * NB + b) * 3;
+    float n = sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+    hit |= n > 1.0f;
+  }
+  return __any_sync(kFull, hit);
+}
+
+// ------------------------------------------------------------------ stages (device functions, one warp per env)
+// VT:307 clamp + T:449-468 + push schedule T:489-502, T:438-447
+__device__ void stage_prologue(const TK& k, const float* __restrict__ actions_in, int e, int lane) {
+  const TaskParams& P = k.p;
+  float time = k.b.time[e];
+  int init = k.b.init_mocap_data_idx[e];
+  float local_time = py_fmodf(time, P.period);                                   // T:450
+  float lt_init = py_fmodf(local_time + (float)init * P.cycle_dt, P.period);     // T:451
+  int idx = (int)(((long long)init + (long long)(local_time / P.cycle_dt)) % P.mocap_data_num);  // T:452
+  if (lane == 0) k.b.mocap_data_idx[e] = idx;
+  const float* r0 = k.b.mocap_data + (size_t)idx * 36;
+  const float* r1 = r0 + 36;
+  float t0 = r0[0], tf = r1[0];
+  for (int c = lane; c < 35; c += kWarp) {                                        // T:458-461
+    float v = cubic0(lt_init, t0, tf, r0[1 + c], r1[1 + c]);
+    if (c < ND) k.b.target_data_qpos[(size_t)e * ND + c] = v;
+    else k.b.target_data_force[(size_t)e * 2 + (c - ND)] = v;
+  }
+  if (lane < NA) {
+    float a = actions_in[(size_t)e * NA + lane];
+    a = (a < -1.0f) ? -1.0f : ((a > 1.0f) ? 1.0f : a);                            // VT:307 (NaN passes through)
+    if (lane == NA - 1) a = ((a > 0.0f) ? 1.0f : 0.0f) * a;                       // T:464-465
+    k.b.actions[(size_t)e * NA + lane] = a;
+    int head = (k.b.act_hist_head[e] + 1) % NSLOT;                                // T:466 as a ring push
+    k.b.action_history[((size_t)e * NSLOT + head) * NA + lane] = a;
+    if (lane < 12)                                                                // T:468
+      k.b.action_torque[(size_t)e * 12 + lane] = a * k.b.motor_constant_scale[(size_t)e * 12 + lane] * P.action_high[lane];
+    __syncwarp(0x1fffu);
+    if (lane == 0) k.b.act_hist_head[e] = head;
+  }
+  if (lane == 0) {
+    float fx = 0.f, fy = 0.f;
+    if (*k.b.perturb_start) {                                                     // T:492
+      int on = k.b.pert_on[e], cnt = k.b.perturbation_count[e], dur = k.b.pert_duration[e];
+      float mag = k.b.magnitude[e], ph = k.b.phase[e];
+      if (py_fmodf(k.b.epi_len[e], P.pert_period) == (float)k.b.perturb_timing[e]) {  // T:495
+        int imp;
+        float u;
+        if (k.j.pert_i) {
+          imp = (int)k.j.pert_i[(size_t)e * 2];
+          dur = (int)k.j.pert_i[(size_t)e * 2 + 1];
+          u = k.j.pert_f[e];
+        } else {
+          uint4 r = draw4(P.seed, *P.step_counter, e, kSitePert, 0);
+          int lo = (int)(0.1 / (double)P.dt_policy), hi = (int)(1.0 / (double)P.dt_policy);
+          imp = 50 + (int)(r.x % 200u);                                           // T:440 randint(50,250)
+          dur = lo + (int)(r.y % (uint32_t)(hi - lo));                            // T:441
+          u = u01(r.z);
+        }
+        on = 1;                                                                   // T:439
+        mag = (float)imp / ((float)dur * P.dt_policy);                            // T:442
+        ph = u * 2.0f * 3.14159265358979f;                                        // T:443
+        k.b.impulse[e] = imp;
+        k.b.pert_duration[e] = dur;
+        k.b.magnitude[e] = mag;
+        k.b.phase[e] = ph;
+      }
+      if (on) cnt += 1;                                                           // T:497
+      if (on) {                                                                   // T:498-499
+        fx = mag * cosf(ph);
+        fy = mag * sinf(ph);
+      }
+      if (cnt == dur) {                                                           // T:500-501, T:445-447
+        on = 0;
+        cnt = 0;
+      }
+      k.b.pert_on[e] = on;
+      k.b.perturbation_count[e] = cnt;
+    }
+    k.b.push_force[(size_t)e * 3 + 0] = fx;
+    k.b.push_force[(size_t)e * 3 + 1] = fy;
+    k.b.push_force[(size_t)e * 3 + 2] = 0.f;
+  }
+}
+
+// T:505-520
+__device__ void stage_substep_torque(const TK& k, int e, int lane) {
+  const float* ds = k.s.dof_state + (size_t)e * ND * 2;
+  float* out = k.s.dof_actuation_force + (size_t)e * ND;
+  for (int d = 12 + lane; d < ND; d += kWarp) {                                   // T:506
+    float pos = ds[2 * d], vel = ds[2 * d + 1];
+    out[d] = k.p.kp[d] * (k.b.target_data_qpos[(size_t)e * ND + d] - pos) + k.p.kv[d] * (-vel);
+  }
+  int sl = k.b.simul_len[e] + 1;                                                  // T:513-514
+  sl = sl > LOG_DEPTH ? LOG_DEPTH : (sl < 0 ? 0 : sl);
+  int dl = k.b.delay_idx[e];
+  if (lane < 12) {
+    float* lg = k.b.action_log + (size_t)e * LOG_DEPTH * 12 + lane;
+    float v[LOG_DEPTH];
+#pragma unroll
+    for (int i = 0; i < LOG_DEPTH - 1; ++i) v[i] = lg[(i + 1) * 12];              // T:511
+    v[LOG_DEPTH - 1] = k.b.action_torque[(size_t)e * 12 + lane];                  // T:512
+#pragma unroll
+    for (int i = 0; i < LOG_DEPTH; ++i) lg[i * 12] = v[i];
+    int pick = (sl > dl) ? dl : (LOG_DEPTH - sl);                                 // T:515-519
+    float r = v[0];
+#pragma unroll
+    for (int i = 1; i < LOG_DEPTH; ++i) r = (pick == i) ? v[i] : r;
+    out[lane] = r;                                                                // T:520
+  }
+  __syncwarp();
+  if (lane == 0) k.b.simul_len[e] = sl;
+}
+
+// T:528-530
+__device__ void stage_sensor_noise(const TK& k, int substep, int e, int lane) {
+  const float* ds = k.s.dof_state + (size_t)e * ND * 2;
+  for (int d = lane; d < ND; d += kWarp) {
+    float n;
+    if (k.j.qpos_normal) {
+      n = k.j.qpos_normal[((size_t)substep * k.p.N + e) * ND + d];
+    } else {
+      uint4 r = draw4(k.p.seed, *k.p.step_counter, e, kSiteQposNoise, substep * 64 + d);
+      n = normal01(r.x, r.y) * k.p.noise_std;
+    }
+    n = (n < -0.00016f) ? -0.00016f : ((n > 0.00016f) ? 0.00016f : n);
+    float qn = ds[2 * d] + n;
+    size_t i = (size_t)e * ND + d;
+    k.b.qvel_noise[i] = (qn - k.b.qpos_pre[i]) / k.p.dt;
+    k.b.qpos_noise[i] = qn;
+    k.b.qpos_pre[i] = qn;
+  }
+}
+
+// T:532-541, VT:325, T:544-545
+__device__ void stage_epilogue(const TK& k, int e, int lane) {
+  if (lane != 0) return;
+  k.b.epi_len[e] = k.b.epi_len[e] + 1.0f;
+  float t = k.b.time[e] + k.p.dt_policy;
+  t = t + k.p.time_gain * k.b.actions[(size_t)e * NA + NA - 1];
+  k.b.time[e] = t;
+  long long pr = k.b.progress_buf[e];
+  k.b.timeout_buf[e] = ((float)pr >= k.p.max_len_m1) ? 1 : 0;
+  k.b.progress_buf[e] = pr + 1;
+  k.b.randomize_buf[e] = k.b.randomize_buf[e] + 1;
+}
+
+// T:581-596 ; returns the reset flag (warp-uniform)
+__device__ int stage_check_termination(const TK& k, int e, int lane) {
+  float qe = quat_err_identity(k.s.root_states + (size_t)e * 13 + 3);
+  int reset = (fabsf(qe) > 0.5f) ? 1 : 0;
+  if ((float)k.b.progress_buf[e] >= k.p.max_len_m1) reset = 1;
+  if (collision_true(k, e, lane)) reset = 1;
+  if (lane == 0) k.b.reset_buf[e] = reset;
+  return reset;
+}
+
+// T:387-428 + T:802-947
+__device__ void stage_compute_reward(const TK& k, int e, int lane) {
+  const float* root = k.s.root_states + (size_t)e * 13;
+  const float* ds = k.s.dof_state + (size_t)e * ND * 2;
+  float s_qpos = 0.f, s_qvel = 0.f, s_qacc = 0.f, s_tq = 0.f, s_tqd = 0.f;
+  for (int d = lane; d < ND; d += kWarp) {
+    float pos = ds[2 * d], vel = ds[2 * d + 1];
+    float a = k.b.target_data_qpos[(size_t)e * ND + d] - pos;
+    float b = 0.0f - vel;
+    float c = vel - k.b.pre_joint_velocity_states[(size_t)e * ND + d];
+    s_qpos += a * a;
+    s_qvel += b * b;
+    s_qacc += c * c;
+  }
+  if (lane < 12) {
+    float a = k.b.actions[(size_t)e * NA + lane], ap = k.b.actions_pre[(size_t)e * NA + lane];
+    float t = a * 333.0f, td = (a - ap) * 333.0f;
+    s_tq = t * t;
+    s_tqd = td * td;
+  }
+  s_qpos = warp_sum(s_qpos);
+  s_qvel = warp_sum(s_qvel);
+  s_qacc = warp_sum(s_qacc);
+  s_tq = warp_sum(s_tq);
+  s_tqd = warp_sum(s_tqd);
+  bool col = collision_true(k, e, lane);
+  if (lane != 0) return;
+  float qe = quat_err_identity(root + 3);
+  float r[14];
+  r[0] = 0.3f * expf(-13.2f * fabsf(qe));                                          // T:835
+  float n;
+  n = sqrtf(s_qpos); r[1] = 0.35f * expf(-2.0f * (n * n));                         // T:837
+  n = sqrtf(s_qvel); r[2] = 0.05f * expf(-0.01f * (n * n));                        // T:839
+  const float* F = k.s.net_contact_force + (size_t)e * NB * 3;
+  const float* Fp = k.b.contact_forces_pre + (size_t)e * NB * 3;
+  const float *lf = F + k.p.lfoot * 3, *rf = F + k.p.rfoot * 3, *lfp = Fp + k.p.lfoot * 3, *rfp = Fp + k.p.rfoot * 3;
+  float dl0 = lf[0] - lfp[0], dl1 = lf[1] - lfp[1], dl2 = lf[2] - lfp[2];
+  float dr0 = rf[0] - rfp[0], dr1 = rf[1] - rfp[1], dr2 = rf[2] - rfp[2];
+  r[9] = 0.2f * expf(-0.01f * (sqrtf(dl0 * dl0 + dl1 * dl1 + dl2 * dl2) + sqrtf(dr0 * dr0 + dr1 * dr1 + dr2 * dr2)));  // T:858
+  r[4] = 0.05f * expf(-0.01f * sqrtf(s_tq));                                        // T:861
+  r[5] = 0.6f * expf(-0.01f * sqrtf(s_tqd));                                        // T:863
+  n = sqrtf(s_qacc); r[7] = 0.05f * expf(-20.0f * (n * n));                        // T:865
+  float vx = k.b.target_vel[(size_t)e * 2] - root[7], vy = k.b.target_vel[(size_t)e * 2 + 1] - root[8];
+  n = sqrtf(vx * vx + vy * vy); r[6] = 0.3f * expf(-3.0f * (n * n));               // T:867
+  bool lc = lf[2] > 1.0f, rc = rf[2] > 1.0f;                                       // T:869-870
+  int idx = k.b.mocap_data_idx[e];
+  bool DSP = ((3300 <= idx) && (idx < 3600)) || (idx < 300) || ((1500 <= idx) && (idx < 2100));
+  bool RSSP = (300 <= idx) && (idx < 1500);
+  bool LSSP = (2100 <= idx) && (idx < 3300);
+  bool sync = (DSP && rc && lc) || (RSSP && rc && !lc) || (LSSP && !rc && lc);     // T:882-889
+  r[8] = sync ? 0.2f : 0.0f;
+  k.b.contact_reward_sum[e] = k.b.contact_reward_sum[e] + r[8];                    // T:891
+  r[10] = 0.0f;                                                                    // T:893
+  float m = k.b.total_mass[e];
+  float thr = (float)(1.4 * 9.81) * m;                                             // T:895
+  bool thres = (lf[2] > thr) || (rf[2] > thr);
+  r[11] = thres ? -0.2f : 0.0f;                                                    // T:898
+  float cl = fmaxf(lf[2] - thr, 0.0f), cr = fmaxf(rf[2] - thr, 0.0f);
+  float pen = 0.1f * expf(-0.007f * (sqrtf(cl * cl) + sqrtf(cr * cr)));            // T:900-901
+  r[3] = thres ? pen : 0.1f;                                                       // T:902
+  float dthr = (float)(0.2 * 9.81) * m / 1.0f;                                     // T:904
+  bool tdiff = (fabsf(lf[2] - lfp[2]) > dthr) || (fabsf(rf[2] - rfp[2]) > dthr);
+  r[12] = tdiff ? -0.05f : 0.0f;                                                   // T:907
+  float ws = m / 104.48f;                                                          // T:917
+  const float* ft = k.b.target_data_force + (size_t)e * 2;
+  r[13] = 0.1f * expf(-0.001f * fabsf(lf[2] + ws * ft[0])) + 0.1f * expf(-0.001f * fabsf(rf[2] + ws * ft[1]));  // T:918-919
+  float total = r[0] + r[1] + r[2] + r[3] + r[4] + r[5] + r[6] + r[7] + r[8] + r[9] + r[10] + r[11] + r[12] + r[13];  // T:932-934
+  if (col) total = k.p.death_cost;                                                 // T:942
+  if (fabsf(qe) > 0.5f) total = k.p.death_cost;                                    // T:943
+  k.b.rew_buf[e] = total;
+  float* st = k.b.stacked_rewards + (size_t)e * 15;
+#pragma unroll
+  for (int i = 0; i < 14; ++i) st[i] = col ? k.p.death_cost : r[i];                // T:945
+  st[14] = (*k.b.perturb_start) ? 1.0f : 0.0f;                                     // T:415
+}
+
+// T:598-669, T:720-748 (+ DR re-draw of damping/armature, VT:519-733 / gymutil.py:584-619)
+__device__ void stage_reset_env(const TK& k, int e, int lane) {
+  const TaskParams& P = k.p;
+  uint64_t step = *P.step_counter;
+  // --- draws (env-indexed). reset_f columns: see DyrosNoiseInjection
+  auto uf = [&](int col) -> float {
+    if (k.j.reset_f) return k.j.reset_f[(size_t)e * 32 + col];
+    uint4 r = draw4(P.seed, step, e, kSiteResetF, col >> 2);
+    uint32_t w = (col & 3) == 0 ? r.x : (col & 3) == 1 ? r.y : (col & 3) == 2 ? r.z : r.w;
+    return u01(w);
+  };
+  for (int d = lane; d < ND; d += kWarp) {
+    size_t i = (size_t)e * ND + d;
+    k.b.qpos_noise[i] = P.init_dof_pos[d];                                         // T:611
+    k.b.qpos_pre[i] = P.init_dof_pos[d];                                           // T:612
+    k.b.qvel_noise[i] = 0.f;                                                       // T:613
+    k.s.dof_state[2 * i] = P.reset_dof_pos[d];                                     // T:742
+    k.s.dof_state[2 * i + 1] = 0.f;                                                // T:743
+    k.b.pre_joint_velocity_states[i] = 0.f;                                        // T:635
+    if (P.randomize) {                                                             // CFG:103-115, always re-drawn on reset
+      float u0, u1;
+      if (k.j.dr_u) {
+        u0 = k.j.dr_u[(size_t)e * 66 + d];
+        u1 = k.j.dr_u[(size_t)e * 66 + 33 + d];
+      } else {
+        uint4 r = draw4(P.seed, step, e, kSiteDR, d);
+        u0 = u01(r.x);
+        u1 = u01(r.y);
+      }
+      k.s.dof_damping[i] = P.dr_damping_base + (P.dr_damping_lo + u0 * (P.dr_damping_hi - P.dr_damping_lo));
+      k.s.dof_armature[i] = P.armature_base[d] * (P.dr_armature_lo + u1 * (P.dr_armature_hi - P.dr_armature_lo));
+    }
+  }
+  if (lane < 12) {
+    k.b.qpos_bias[(size_t)e * 12 + lane] = uf(lane) * 6.28f / 100.f - (float)(3.14 / 100);        // T:615
+    k.b.motor_constant_scale[(size_t)e * 12 + lane] = uf(18 + lane) * 0.4f + 0.8f;                // T:645
+    k.b.action_torque_pre[(size_t)e * 12 + lane] = 0.f;                                            // T:636
+  }
+  if (lane < 3) k.b.quat_bias[(size_t)e * 3 + lane] = uf(12 + lane) * 6.28f / 150.f - (float)(3.14 / 150);  // T:616
+  if (lane < 13) {                                                                 // T:734-735
+    float v = 0.f;
+    if (lane < 3) v = k.b.env_origins[(size_t)e * 3 + lane];
+    if (lane == 2) v = P.initial_height + v;
+    if (lane == 6) v = 1.f;
+    k.s.root_states[(size_t)e * 13 + lane] = v;
+  }
+  for (int i = lane; i < NB * 3; i += kWarp)                                       // T:638
+    k.b.contact_forces_pre[(size_t)e * NB * 3 + i] = k.s.net_contact_force[(size_t)e * NB * 3 + i];
+  for (int i = lane; i < LOG_DEPTH * 12; i += kWarp) k.b.action_log[(size_t)e * LOG_DEPTH * 12 + i] = 0.f;  // T:651
+  for (int i = lane; i < NSLOT * NOBS1; i += kWarp) k.b.obs_history[(size_t)e * NSLOT * NOBS1 + i] = 0.f;   // T:668
+  for (int i = lane; i < NSLOT * NA; i += kWarp) k.b.action_history[(size_t)e * NSLOT * NA + i] = 0.f;       // T:669
+  if (lane == 0) {
+    float vel_mag = uf(15) * 0.8f;                                                 // T:624
+    float vel_theta = uf(16) * 0.0f;                                               // T:625
+    k.b.target_vel[(size_t)e * 2] = vel_mag * cosf(vel_theta);                     // T:626-628
+    k.b.target_vel[(size_t)e * 2 + 1] = vel_mag * sinf(vel_theta);
+    k.b.init_mocap_data_idx[e] = (uf(17) > 0.5f) ? 0 : 1800;                       // T:630-632
+    k.b.time[e] = 0.f;                                                             // T:642
+    k.b.progress_buf[e] = 0;                                                       // T:648
+    k.b.reset_buf[e] = 1;                                                          // T:649
+    int delay, timing;
+    if (k.j.reset_i) {
+      delay = (int)k.j.reset_i[(size_t)e * 2];
+      timing = (int)k.j.reset_i[(size_t)e * 2 + 1];
+    } else {
+      uint4 r = draw4(P.seed, step, e, kSiteResetI, 0);
+      int lo = 1 + (int)(0.002 / (double)P.dt), hi = 1 + (int)(0.01 / (double)P.dt + 0.5);
+      delay = lo + (int)(r.x % (uint32_t)(hi - lo));                               // T:652
+      timing = (int)(r.y % (uint32_t)(int)(8.0 / (double)P.dt_policy));            // T:665
+    }
+    k.b.delay_idx[e] = delay;
+    float el = k.b.epi_len[e];
+    k.b.contact_reward_mean[e] = k.b.contact_reward_sum[e] / el;                   // T:654
+    k.b.contact_reward_sum[e] = 0.f;                                               // T:655
+    k.b.simul_len[e] = 0;                                                          // T:657
+    k.b.epi_len_log[e] = el;                                                       // T:658
+    k.b.epi_len[e] = 0.f;                                                          // T:659
+    k.b.perturbation_count[e] = 0;                                                 // T:663
+    k.b.pert_on[e] = 0;                                                            // T:664
+    k.b.perturb_timing[e] = timing;                                                // T:665
+    if (P.randomize && k.b.randomize_buf[e] >= 1) k.b.randomize_buf[e] = 0;        // VT:540-544 (frequency 1)
+  }
+}
+
+// T:750-796 (history kept as rings, see DyrosTaskBuffers)
+__device__ void stage_compute_observations(const TK& k, int e, int lane) {
+  const TaskParams& P = k.p;
+  const float* root = k.s.root_states + (size_t)e * 13;
+  float time = k.b.time[e];
+  float time2idx = py_fmodf(time, P.period) / P.cycle_dt;                                           // T:762
+  float phase = py_fmodf((float)k.b.init_mocap_data_idx[e] + time2idx, (float)P.mocap_data_num) / (float)P.mocap_data_num;  // T:763
+  float ang = (float)(2 * 3.14159265358979) * phase;
+  int head = (k.b.obs_hist_head[e] + 1) % NSLOT;
+  bool start = k.b.epi_len[e] == 0.0f;                                                              // T:785
+  float* hist = k.b.obs_history + (size_t)e * NSLOT * NOBS1;
+  for (int i = lane; i < NOBS1; i += kWarp) {
+    float v;
+    if (i < 3) v = quat2euler_comp(root + 3, i) + k.b.quat_bias[(size_t)e * 3 + i];                 // T:753-757
+    else if (i < 15) v = k.b.qpos_noise[(size_t)e * ND + (i - 3)] + k.b.qpos_bias[(size_t)e * 12 + (i - 3)];
+    else if (i < 27) v = k.b.qvel_noise[(size_t)e * ND + (i - 15)];
+    else if (i == 27) v = sinf(ang);                                                                // T:764
+    else if (i == 28) v = cosf(ang);                                                                // T:765
+    else if (i < 31) v = k.b.target_vel[(size_t)e * 2 + (i - 29)];
+    else {
+      int c = i - 31;
+      float u;
+      if (k.j.vel_u) u = k.j.vel_u[(size_t)e * 6 + c];
+      else {
+        uint4 r = draw4(P.seed, *P.step_counter, e, kSiteVelNoise, c);
+        u = u01(r.x);
+      }
+      v = root[7 + c] + (u * 0.05f - 0.025f);                                                       // T:766,774
+    }
+    float nv = (v - k.b.obs_mean[i]) / sqrtf(k.b.obs_var[i] + 1e-8f * 1.0f);                        // T:776-777
+    if (start) {
+      for (int sl = 0; sl < NSLOT; ++sl) hist[sl * NOBS1 + i] = nv;                                 // T:786-787
+    } else {
+      hist[head * NOBS1 + i] = nv;                                                                  // T:783
+    }
+  }
+  __syncwarp();
+  if (lane == 0) k.b.obs_hist_head[e] = head;
+  float* ob = k.b.obs_buf + (size_t)e * NOBS;
+  const float* ah = k.b.action_history + (size_t)e * NSLOT * NA;
+  int ahead = k.b.act_hist_head[e];
+  for (int o = lane; o < NOBS; o += kWarp) {
+    float v;
+    if (o < NOBS1 * NHIS) {                                                                         // T:789-791
+      int i = o / NOBS1, j = o - i * NOBS1;
+      int pos = NSKIP * (i + 1) - 1;
+      v = hist[((head + 1 + pos) % NSLOT) * NOBS1 + j];
+    } else {                                                                                        // T:793-796
+      int q = o - NOBS1 * NHIS;
+      int i = q / NA, j = q - i * NA;
+      int pos = NSKIP * (i + 1);
+      v = ah[((ahead + 1 + pos) % NSLOT) * NA + j];
+    }
+    ob[o] = v;
+  }
+}
+
+// T:560-563
+__device__ void stage_late_update(const TK& k, int e, int lane) {
+  const float* ds = k.s.dof_state + (size_t)e * ND * 2;
+  for (int d = lane; d < ND; d += kWarp) k.b.pre_joint_velocity_states[(size_t)e * ND + d] = ds[2 * d + 1];
+  if (lane < 12) k.b.action_torque_pre[(size_t)e * 12 + lane] = k.b.action_torque[(size_t)e * 12 + lane];
+  if (lane < NA) k.b.actions_pre[(size_t)e * NA + lane] = k.b.actions[(size_t)e * NA + lane];
+  for (int i = lane; i < NB * 3; i += kWarp)
+    k.b.contact_forces_pre[(size_t)e * NB * 3 + i] = k.s.net_contact_force[(size_t)e * NB * 3 + i];
+}
+
+// ------------------------------------------------------------------ kernels
+#define ENV_LANE()                                                   \
+  int lane = threadIdx.x & 31;                                       \
+  int e = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);          \
+  if (e >= k.p.N) return;
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_prologue(TK k, const float* __restrict__ actions) {
+  ENV_LANE();
+  stage_prologue(k, actions, e, lane);
+}
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_substep_torque(TK k) {
+  ENV_LANE();
+  stage_substep_torque(k, e, lane);
+}
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_sensor_noise(TK k, int substep) {
+  ENV_LANE();
+  stage_sensor_noise(k, substep, e, lane);
+}
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_epilogue(TK k) {
+  ENV_LANE();
+  stage_epilogue(k, e, lane);
+}
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_check_termination(TK k) {
+  ENV_LANE();
+  stage_check_termination(k, e, lane);
+}
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_compute_reward(TK k) {
+  ENV_LANE();
+  stage_compute_reward(k, e, lane);
+}
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_reset_idx(TK k, const int64_t* __restrict__ ids, int count) {
+  int lane = threadIdx.x & 31;
+  int w = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  int n = count >= 0 ? count : *k.b.reset_count;
+  if (w >= n || w >= k.p.N) return;
+  long long e = ids[w];
+  if (e < 0 || e >= k.p.N) return;
+  stage_reset_env(k, (int)e, lane);
+}
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_compute_observations(TK k) {
+  ENV_LANE();
+  stage_compute_observations(k, e, lane);
+}
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_late_update(TK k) {
+  ENV_LANE();
+  stage_late_update(k, e, lane);
+}
+// post_physics_step in one launch: epilogue, termination, reward, reset, observations, late update.
+// Reward/termination read the pre-reset state, observations the post-reset state.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_post_fused(TK k) {
+  ENV_LANE();
+  stage_epilogue(k, e, lane);
+  __syncwarp();
+  int reset = stage_check_termination(k, e, lane);
+  __syncwarp();
+  stage_compute_reward(k, e, lane);
+  __syncwarp();
+  if (reset) {
+    stage_reset_env(k, e, lane);
+    __syncwarp();
+  }
+  stage_compute_observations(k, e, lane);
+  __syncwarp();
+  stage_late_update(k, e, lane);
+}
+
+// Cross-env pass (one block): (a) reset_buf.nonzero() -> ascending ids by ballot + prefix scan (T:554),
+// (b) the curriculum gate means of T:489, (c) Philox epoch bump.
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads) k_crossenv(TK k, int do_compact, int do_gate, int do_bump) {
+  __shared__ int warp_tot[kScanThreads / 32];
+  __shared__ int base_sh;
+  __shared__ double red[2][kScanThreads / 32];
+  int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  int N = k.p.N;
+  if (do_compact) {
+    if (tid == 0) base_sh = 0;
+    __syncthreads();
+    for (int start = 0; start < N; start += kScanThreads) {
+      int e = start + tid;
+      bool f = (e < N) && (k.b.reset_buf[e] != 0);
+      unsigned bal = __ballot_sync(kFull, f);
+      int rank = __popc(bal & ((1u << lane) - 1u));
+      if (lane == 0) warp_tot[w] = __popc(bal);
+      __syncthreads();
+      if (w == 0) {
+        int v = warp_tot[lane];
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int t = __shfl_up_sync(kFull, inc, o);
+          if (lane >= o) inc += t;
+        }
+        warp_tot[lane] = inc - v;  // exclusive
+        if (lane == 31) red[0][0] = (double)inc;  // chunk total (reuse smem slot)
+      }
+      __syncthreads();
+      int base = base_sh;
+      if (f) {
+        int pos = base + warp_tot[w] + rank;
+        k.b.reset_env_ids[pos] = e;
+        k.b.reset_env_ids32[pos] = e;
+      }
+      __syncthreads();
+      if (tid == 0) base_sh = base + (int)red[0][0];
+      __syncthreads();
+    }
+    if (tid == 0) *k.b.reset_count = base_sh;
+  }
+  if (do_gate && k.p.perturb) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int e = tid; e < N; e += kScanThreads) {
+      s0 += (double)k.b.epi_len_log[e];
+      s1 += (double)k.b.contact_reward_mean[e];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(kFull, s0, o);
+      s1 += __shfl_xor_sync(kFull, s1, o);
+    }
+    __syncthreads();
+    if (lane == 0) {
+      red[0][w] = s0;
+      red[1][w] = s1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double a = 0, b = 0;
+      for (int i = 0; i < kScanThreads / 32; ++i) {
+        a += red[0][i];
+        b += red[1][i];
+      }
+      if ((float)(a / N) > k.p.gate_len && (float)(b / N) > 0.165f) *k.b.perturb_start = 1;  // T:489-490 (sticky)
+    }
+  }
+  if (do_bump && tid == 0) *k.p.step_counter = *k.p.step_counter + 1;
+}
+
+// ------------------------------------------------------------------ launchers
+static inline TK make_tk(Task* t) {
+  TK k;
+  k.p = t->p;
+  k.b = t->b;
+  k.s = t->sim->b;
+  k.j = t->inj;
+  return k;
+}
+static inline int env_grid(int N) { return (N + kWarpsPerBlock - 1) / kWarpsPerBlock; }
+#define LAUNCH_ENV(kern, ...)                                                    \
+  kern<<<env_grid(t->p.N), kWarpsPerBlock * 32, 0, s>>>(make_tk(t), ##__VA_ARGS__); \
+  DY_LAUNCH_CHECK();                                                             \
+  return 0;
+
+int launch_prologue(Task* t, const float* actions, cudaStream_t s) { LAUNCH_ENV(k_prologue, actions) }
+int launch_substep_torque(Task* t, cudaStream_t s) { LAUNCH_ENV(k_substep_torque) }
+int launch_sensor_noise(Task* t, int substep, cudaStream_t s) { LAUNCH_ENV(k_sensor_noise, substep) }
+int launch_epilogue(Task* t, cudaStream_t s) { LAUNCH_ENV(k_epilogue) }
+int launch_check_termination(Task* t, cudaStream_t s) { LAUNCH_ENV(k_check_termination) }
+int launch_compute_reward(Task* t, cudaStream_t s) { LAUNCH_ENV(k_compute_reward) }
+int launch_compute_observations(Task* t, cudaStream_t s) { LAUNCH_ENV(k_compute_observations) }
+int launch_late_update(Task* t, cudaStream_t s) { LAUNCH_ENV(k_late_update) }
+int launch_post_fused(Task* t, cudaStream_t s) { LAUNCH_ENV(k_post_fused) }
+int launch_reset_idx(Task* t, const int64_t* env_ids, int count, cudaStream_t s) {
+  if (count == 0) return 0;
+  const int64_t* ids = env_ids ? env_ids : t->b.reset_env_ids;
+  int n = count >= 0 ? count : t->p.N;
+  k_reset_idx<<<env_grid(n), kWarpsPerBlock * 32, 0, s>>>(make_tk(t), ids, count);
+  DY_LAUNCH_CHECK();
+  return 0;
+}
+int launch_crossenv(Task* t, bool compact, bool gate, bool bump, cudaStream_t s) {
+  k_crossenv<<<1, kScanThreads, 0, s>>>(make_tk(t), compact, gate, bump);
+  DY_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace dyros
