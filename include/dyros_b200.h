@@ -37,7 +37,7 @@ typedef struct DyrosTask DyrosTask; /* per-env task state of DyrosDynamicWalk (T
 /* Flat model tables (host pointers, float64/int32; see isaacgymdyros_b200/model/tables.py).
  * Replaces what gym.load_asset + create_actor build inside the closed importer (T:293, T:354). */
 typedef struct {
-  int32_t num_links, num_bodies, num_dofs, num_points, num_cyls, num_solver_links, sched_slots;
+  int32_t num_links, num_bodies, num_dofs, num_points, num_cyls, sched_slots;
   const int32_t* link_parent; /* [nl] */
   const int32_t* link_dof;    /* [nl] */
   const double* link_E;       /* [nl*9] */
@@ -55,12 +55,12 @@ typedef struct {
   const int32_t* pt_body;     /* [np] */
   const double* pt_pos;       /* [np*3] */
   const double* pt_radius;    /* [np] */
+  const int32_t* pt_solver;   /* [np] 1 = ground contact of this point is constraint-solved (sole corners), 0 = penalty */
   const int32_t* cyl_link;    /* [nc] */
   const int32_t* cyl_body;    /* [nc] */
   const double* cyl_center;   /* [nc*3] */
   const double* cyl_axis;     /* [nc*3] */
   const double* cyl_size;     /* [nc*2] radius, half height */
-  const int32_t* solver_links;/* [ns] links whose ground contacts are constraint-solved (feet) */
   const int32_t* sched;       /* [sched_slots*DYROS_LANES] */
 } DyrosModelDesc;
 
@@ -74,11 +74,12 @@ typedef struct {
   float gravity[3];
   float contact_offset;     /* physx.contact_offset 0.002 */
   float max_depenetration_velocity; /* 10 */
-  int32_t contact_sweeps;   /* PGS sweeps with penetration bias (physx.num_position_iterations scaled) */
-  int32_t contact_final_sweeps; /* sweeps without bias (physx.num_velocity_iterations) */
+  int32_t contact_sweeps;   /* fixed PGS sweeps = physx.num_position_iterations + num_velocity_iterations (4+1) */
+  float contact_erp;        /* fraction of penetration removed per sub-step through the velocity bias */
   float friction;           /* combined plane/shape friction, terrain_cfg.py:7-8 -> 1.0 */
-  float penalty_stiffness;  /* non-solver-link ground contact (N/m) */
+  float penalty_stiffness;  /* ground contact of non-solved points (N/m) */
   float penalty_damping;    /* (N s/m) */
+  float penalty_max_force;  /* clamp of one penalty point's normal force (N) */
   float max_angular_velocity; /* AssetOptions.max_angular_velocity T:289 */
   int32_t clamp_effort;     /* clamp actuation to MJCF ctrlrange (default 0) */
 } DyrosSimDesc;
@@ -218,6 +219,8 @@ int dyros_task_compact_resets(DyrosTask* task, void* stream);                   
 int dyros_task_reset_idx(DyrosTask* task, const int64_t* env_ids, int count, void* stream); /* T:598-669; env_ids NULL = use compacted list */
 int dyros_task_compute_observations(DyrosTask* task, void* stream);                /* T:750-796 */
 int dyros_task_late_update(DyrosTask* task, void* stream);                         /* T:560-563 */
+/* End of a staged step: the cross-env curriculum gate of T:489 (evaluated for the next step) + RNG epoch bump. */
+int dyros_task_end_step(DyrosTask* task, void* stream);
 /* Whole VecTask.step (VT:293-344) in the fewest launches; same results as the staged calls. */
 int dyros_task_step(DyrosTask* task, const float* actions, void* stream);
 /* Number of kernel launches dyros_task_step enqueues (for bench.py's gpu_launches). */

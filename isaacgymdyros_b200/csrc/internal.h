@@ -8,14 +8,23 @@ constexpr int ND = 33, NB = 38, NA = 13, NOBS1 = 37, NHIS = 10, NSKIP = 2, NSLOT
 constexpr int NOBS = (NOBS1 + NA) * (NHIS - 1) + NOBS1;                                           // 487
 constexpr int LOG_DEPTH = 6;                                                                      // T:166
 
-// float32 device copies of the model tables (see model/tables.py for the meaning of each array)
+// float32 device copies of the model tables (see model/tables.py for the meaning of each array) plus
+// tables derived at create time (children lists, per-link candidate ranges, foot chains)
+constexpr int MAX_CHAIN = 8;   // links between the base and a solver (foot) link
+constexpr int MAX_FEET = 2;    // solver links
+constexpr int MAX_SOLVER_PTS = 8;  // candidate solver points per foot
+constexpr int MAX_ACTIVE_PTS = 4;  // active (constraint-solved) points per foot and sub-step
 struct DevModel {
-  int nl, nb, nd, np, nc, ns, T;
+  int nl, nb, nd, np, nc, T;
   const int* link_parent;
   const int* link_dof;
   const float* link_E;
   const float* link_r;
   const float* link_axis;
+  const int* link_child_start;  // [nl+1]
+  const int* link_children;     // [nl-1] ascending link order inside each parent
+  const int* link_body_start;   // [nl+1]
+  const int* link_bodies;       // [nb] bodies grouped by link
   const int* body_link;
   const float* body_pos;
   const float* body_rot;
@@ -24,27 +33,33 @@ struct DevModel {
   const float* dof_upper;
   const float* dof_vel_limit;
   const float* dof_effort;
-  const int* pt_link;
-  const int* pt_body;
-  const float* pt_pos;
-  const float* pt_radius;
-  const int* cyl_link;
+  const int* link_pt_start;     // [nl+1] penalty points grouped by link
+  const int* pt_body;           // [npp]
+  const float* pt_pos;          // [npp*3]
+  const float* pt_radius;       // [npp]
+  const int* link_cyl_start;    // [nl+1]
   const int* cyl_body;
   const float* cyl_center;
   const float* cyl_axis;
   const float* cyl_size;
-  const int* solver_links;
-  const int* sched;
-  const int* link_solver_slot;  // [nl] index into solver_links or -1
+  const int* sched;             // [T*DYROS_LANES]
+  int num_feet;
+  int foot_link[MAX_FEET];
+  int chain_len[MAX_FEET];
+  int chain[MAX_FEET][MAX_CHAIN];      // base child ... foot link
+  int foot_npts[MAX_FEET];
+  int foot_pt_body[MAX_FEET][MAX_SOLVER_PTS];
+  float foot_pt_pos[MAX_FEET][MAX_SOLVER_PTS][3];
+  float foot_pt_radius[MAX_FEET][MAX_SOLVER_PTS];
 };
 
 struct SimParams {
   int N;
-  float dt;
+  float dt;       // dt / substeps: the integration step of one sub-step
   int substeps;
   float g[3];
-  float contact_offset, max_depen_vel, mu, pen_k, pen_c, max_ang_vel;
-  int sweeps, final_sweeps, clamp_effort;
+  float contact_offset, max_depen_vel, erp, mu, pen_k, pen_c, pen_fmax, max_ang_vel;
+  int sweeps, clamp_effort;
 };
 
 // task constants; every derived value is formed in double on the host the way Python forms it, then cast once
@@ -80,6 +95,9 @@ struct Sim {
   DyrosSimBuffers b;
   void* dev_blob = nullptr;  // one allocation holding every model table
   int device = 0;
+  int sm_count = 148;
+  int envs_per_block = 0;    // physics kernel: envs per CTA (DYROS_LANES threads each)
+  size_t phys_smem = 0;      // dynamic shared memory of one physics CTA
 };
 
 struct Task {
@@ -103,8 +121,8 @@ int launch_compute_observations(Task* t, cudaStream_t s);
 int launch_late_update(Task* t, cudaStream_t s);
 int launch_post_fused(Task* t, cudaStream_t s);
 // launchers (physics_kernels.cu)
-int launch_simulate(Sim* sim, int apply_wrench, cudaStream_t s);
-int launch_task_physics(Task* t, cudaStream_t s);  // skipframe x (PD + delay + substep + noise) in one launch
+int physics_configure(Sim* sim);  // chooses envs_per_block / shared memory, sets the kernel attributes
+int launch_simulate(Sim* sim, int apply_wrench, const float* push_force, cudaStream_t s);
 int launch_refresh_rigid_body_state(Sim* sim, cudaStream_t s);
 
 }  // namespace dyros
