@@ -88,6 +88,51 @@ def env_origins(n: int, spacing: float) -> np.ndarray:
     return o
 
 
+def make_model_desc(t: ModelTables, cfg: "CoreConfig"):
+    """ModelTables -> DyrosModelDesc (host arrays are returned too: keep them alive during the create call)."""
+    keep = []
+    f64 = lambda a: keep.append(np.ascontiguousarray(a, dtype=np.float64)) or keep[-1]
+    i32 = lambda a: keep.append(np.ascontiguousarray(a, dtype=np.int32)) or keep[-1]
+    md = native.DyrosModelDesc()
+    md.num_links, md.num_bodies, md.num_dofs = t.num_links, t.num_bodies, t.num_dofs
+    md.num_points, md.num_cyls, md.sched_slots = len(t.pt_link), len(t.cyl_link), t.sched.shape[0]
+    solver_ids = [t.body_names.index(n) for n in cfg.solver_bodies]
+    pt_solver = np.isin(t.pt_body, solver_ids).astype(np.int32)
+    vel_limit = np.full(t.num_dofs, cfg.dof_vel_limit)
+    for name, arr, ct in [("link_parent", i32(t.link_parent), C.c_int32), ("link_dof", i32(t.link_dof), C.c_int32),
+                          ("link_E", f64(t.link_E), C.c_double), ("link_r", f64(t.link_r), C.c_double),
+                          ("link_axis", f64(t.link_axis), C.c_double), ("body_link", i32(t.body_link), C.c_int32),
+                          ("body_pos", f64(t.body_pos), C.c_double), ("body_rot", f64(t.body_rot), C.c_double),
+                          ("body_inertia", f64(t.body_inertia), C.c_double),
+                          ("dof_lower", f64(t.dof_lower), C.c_double), ("dof_upper", f64(t.dof_upper), C.c_double),
+                          ("dof_vel_limit", f64(vel_limit), C.c_double), ("dof_effort", f64(t.dof_effort), C.c_double),
+                          ("pt_link", i32(t.pt_link), C.c_int32), ("pt_body", i32(t.pt_body), C.c_int32),
+                          ("pt_pos", f64(t.pt_pos), C.c_double), ("pt_radius", f64(t.pt_radius), C.c_double),
+                          ("pt_solver", i32(pt_solver), C.c_int32),
+                          ("cyl_link", i32(t.cyl_link), C.c_int32), ("cyl_body", i32(t.cyl_body), C.c_int32),
+                          ("cyl_center", f64(t.cyl_center), C.c_double), ("cyl_axis", f64(t.cyl_axis), C.c_double),
+                          ("cyl_size", f64(t.cyl_size), C.c_double), ("sched", i32(t.sched), C.c_int32)]:
+        setattr(md, name, _np_ptr(arr, ct))
+    return md, keep
+
+
+def make_sim_desc(cfg: "CoreConfig", num_envs: int, device_index: int = 0):
+    sd = native.DyrosSimDesc()
+    sd.num_envs, sd.device = num_envs, device_index
+    sd.dt, sd.substeps = cfg.dt, cfg.substeps
+    sd.gravity = (C.c_float * 3)(*cfg.gravity)
+    sd.contact_offset = cfg.contact_offset
+    sd.max_depenetration_velocity = cfg.max_depenetration_velocity
+    sd.contact_sweeps = cfg.num_position_iterations + cfg.num_velocity_iterations
+    sd.contact_erp = cfg.contact_erp
+    sd.friction = cfg.friction
+    sd.penalty_stiffness, sd.penalty_damping = cfg.penalty_stiffness, cfg.penalty_damping
+    sd.penalty_max_force = cfg.penalty_max_force
+    sd.max_angular_velocity = cfg.max_angular_velocity
+    sd.clamp_effort = int(cfg.clamp_effort)
+    return sd
+
+
 class DyrosCore:
     def __init__(self, num_envs: int, device: str = "cuda:0", cfg: Optional[CoreConfig] = None,
                  tables: Optional[ModelTables] = None, seed: int = 42, rank: int = 0):
@@ -153,43 +198,9 @@ class DyrosCore:
 
     # ------------------------------------------------------------------ native objects
     def _create_sim(self):
-        t, cfg = self.tables, self.cfg
-        keep = self._keep
-        f64 = lambda a: keep.append(np.ascontiguousarray(a, dtype=np.float64)) or keep[-1]
-        i32 = lambda a: keep.append(np.ascontiguousarray(a, dtype=np.int32)) or keep[-1]
-        md = native.DyrosModelDesc()
-        md.num_links, md.num_bodies, md.num_dofs = t.num_links, t.num_bodies, t.num_dofs
-        md.num_points, md.num_cyls, md.sched_slots = len(t.pt_link), len(t.cyl_link), t.sched.shape[0]
-        solver_ids = [t.body_names.index(n) for n in cfg.solver_bodies]
-        pt_solver = np.isin(t.pt_body, solver_ids).astype(np.int32)
-        vel_limit = np.full(t.num_dofs, cfg.dof_vel_limit)
-        for name, arr, ct in [("link_parent", i32(t.link_parent), C.c_int32), ("link_dof", i32(t.link_dof), C.c_int32),
-                              ("link_E", f64(t.link_E), C.c_double), ("link_r", f64(t.link_r), C.c_double),
-                              ("link_axis", f64(t.link_axis), C.c_double), ("body_link", i32(t.body_link), C.c_int32),
-                              ("body_pos", f64(t.body_pos), C.c_double), ("body_rot", f64(t.body_rot), C.c_double),
-                              ("body_inertia", f64(t.body_inertia), C.c_double),
-                              ("dof_lower", f64(t.dof_lower), C.c_double), ("dof_upper", f64(t.dof_upper), C.c_double),
-                              ("dof_vel_limit", f64(vel_limit), C.c_double), ("dof_effort", f64(t.dof_effort), C.c_double),
-                              ("pt_link", i32(t.pt_link), C.c_int32), ("pt_body", i32(t.pt_body), C.c_int32),
-                              ("pt_pos", f64(t.pt_pos), C.c_double), ("pt_radius", f64(t.pt_radius), C.c_double),
-                              ("pt_solver", i32(pt_solver), C.c_int32),
-                              ("cyl_link", i32(t.cyl_link), C.c_int32), ("cyl_body", i32(t.cyl_body), C.c_int32),
-                              ("cyl_center", f64(t.cyl_center), C.c_double), ("cyl_axis", f64(t.cyl_axis), C.c_double),
-                              ("cyl_size", f64(t.cyl_size), C.c_double), ("sched", i32(t.sched), C.c_int32)]:
-            setattr(md, name, _np_ptr(arr, ct))
-        sd = native.DyrosSimDesc()
-        sd.num_envs, sd.device = self.N, self.device.index or 0
-        sd.dt, sd.substeps = cfg.dt, cfg.substeps
-        sd.gravity = (C.c_float * 3)(*cfg.gravity)
-        sd.contact_offset = cfg.contact_offset
-        sd.max_depenetration_velocity = cfg.max_depenetration_velocity
-        sd.contact_sweeps = cfg.num_position_iterations + cfg.num_velocity_iterations
-        sd.contact_erp = cfg.contact_erp
-        sd.friction = cfg.friction
-        sd.penalty_stiffness, sd.penalty_damping = cfg.penalty_stiffness, cfg.penalty_damping
-        sd.penalty_max_force = cfg.penalty_max_force
-        sd.max_angular_velocity = cfg.max_angular_velocity
-        sd.clamp_effort = int(cfg.clamp_effort)
+        md, keep = make_model_desc(self.tables, self.cfg)
+        self._keep.extend(keep)
+        sd = make_sim_desc(self.cfg, self.N, self.device.index or 0)
         sb = native.DyrosSimBuffers()
         for n in native.SIM_BUFFERS:
             setattr(sb, n, self.sim_t[n].data_ptr() if n in self.sim_t else None)

@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 
+#include "host_model.h"
 #include "internal.h"
 
 namespace dyros {
@@ -23,29 +24,6 @@ void set_error(const char* fmt, ...) {
   g_error = buf;
 }
 
-// Host-side builder of one device blob: arrays are appended, then uploaded with a single copy.
-struct Blob {
-  std::vector<unsigned char> host;
-  size_t add(const void* p, size_t bytes) {
-    size_t off = (host.size() + 15) & ~size_t(15);
-    host.resize(off + bytes);
-    if (bytes) memcpy(host.data() + off, p, bytes);
-    return off;
-  }
-  size_t add_f(const double* p, size_t n) {
-    std::vector<float> f(n);
-    for (size_t i = 0; i < n; ++i) f[i] = (float)p[i];
-    return add(f.data(), n * sizeof(float));
-  }
-  size_t add_f32(const float* p, size_t n) { return add(p, n * sizeof(float)); }
-  size_t add_i(const int* p, size_t n) { return add(p, n * sizeof(int)); }
-};
-
-template <class T>
-static const T* at(void* base, size_t off) {
-  return reinterpret_cast<const T*>(static_cast<unsigned char*>(base) + off);
-}
-
 #define REQUIRE(cond, ...)      \
   do {                          \
     if (!(cond)) {              \
@@ -58,175 +36,23 @@ static int build_sim(const DyrosSimDesc* d, const DyrosModelDesc* m, const Dyros
   REQUIRE(d && m && b && out, "dyros_sim_create: null argument");
   REQUIRE(d->num_envs > 0, "dyros_sim_create: num_envs must be positive (got %d)", d->num_envs);
   REQUIRE(d->substeps >= 1 && d->dt > 0, "dyros_sim_create: need dt > 0 and substeps >= 1");
-  REQUIRE(m->num_links >= 1 && m->num_links <= DYROS_MAX_LINKS, "dyros_sim_create: num_links %d outside [1,%d]",
-          m->num_links, DYROS_MAX_LINKS);
-  REQUIRE(m->num_bodies >= m->num_links && m->num_bodies <= DYROS_MAX_BODIES, "dyros_sim_create: num_bodies %d",
-          m->num_bodies);
-  REQUIRE(m->num_dofs == m->num_links - 1, "dyros_sim_create: one revolute DOF per non-base link expected");
-  REQUIRE(m->sched_slots >= 1 && m->sched, "dyros_sim_create: missing branch schedule");
+  REQUIRE(d->contact_sweeps >= 0 && d->contact_sweeps <= 64, "dyros_sim_create: contact_sweeps %d", d->contact_sweeps);
   REQUIRE(b->root_states && b->dof_state && b->net_contact_force && b->dof_actuation_force && b->dof_damping &&
               b->dof_armature && b->body_mass_scale,
           "dyros_sim_create: a required device buffer is NULL");
-  const int nl = m->num_links, nb = m->num_bodies, nd = m->num_dofs, np = m->num_points, nc = m->num_cyls;
-  for (int l = 1; l < nl; ++l) {
-    REQUIRE(m->link_parent[l] >= 0 && m->link_parent[l] < l, "dyros_sim_create: link %d parent %d not topological", l,
-            m->link_parent[l]);
-    REQUIRE(m->link_dof[l] >= 0 && m->link_dof[l] < nd, "dyros_sim_create: link %d dof index %d", l, m->link_dof[l]);
-  }
-  // every link exactly once in the schedule, after its parent
-  {
-    std::vector<int> slot(nl, -1);
-    slot[0] = -1;
-    for (int t = 0; t < m->sched_slots; ++t)
-      for (int g = 0; g < DYROS_LANES; ++g) {
-        int l = m->sched[t * DYROS_LANES + g];
-        if (l < 0) continue;
-        REQUIRE(l >= 1 && l < nl && slot[l] < 0, "dyros_sim_create: bad schedule entry %d", l);
-        int p = m->link_parent[l];
-        REQUIRE(p == 0 || (slot[p] >= 0 && slot[p] < t), "dyros_sim_create: schedule runs link %d before its parent", l);
-        slot[l] = t;
-      }
-    for (int l = 1; l < nl; ++l) REQUIRE(slot[l] >= 0, "dyros_sim_create: link %d missing from the schedule", l);
-  }
-
   Sim* sim = new (std::nothrow) Sim();
   REQUIRE(sim, "out of host memory");
   sim->device = d->device;
-  SimParams& p = sim->p;
-  p.N = d->num_envs;
-  p.substeps = d->substeps;
-  p.dt = (float)(d->dt / (double)d->substeps);
-  for (int i = 0; i < 3; ++i) p.g[i] = d->gravity[i];
-  p.contact_offset = d->contact_offset;
-  p.max_depen_vel = d->max_depenetration_velocity;
-  p.erp = d->contact_erp;
-  p.mu = d->friction;
-  p.pen_k = d->penalty_stiffness;
-  p.pen_c = d->penalty_damping;
-  p.pen_fmax = d->penalty_max_force;
-  p.max_ang_vel = d->max_angular_velocity;
-  p.sweeps = d->contact_sweeps;
-  p.clamp_effort = d->clamp_effort;
+  fill_sim_params(d, sim->p);
   sim->b = *b;
-
-  // ---- derived tables
-  std::vector<int> child_start(nl + 1, 0), children;
-  for (int l = 0; l < nl; ++l) {
-    child_start[l] = (int)children.size();
-    for (int c = 1; c < nl; ++c)
-      if (m->link_parent[c] == l) children.push_back(c);
-  }
-  child_start[nl] = (int)children.size();
-  std::vector<int> body_start(nl + 1, 0), bodies;
-  for (int l = 0; l < nl; ++l) {
-    body_start[l] = (int)bodies.size();
-    for (int bb = 0; bb < nb; ++bb)
-      if (m->body_link[bb] == l) bodies.push_back(bb);
-  }
-  body_start[nl] = (int)bodies.size();
-  REQUIRE((int)bodies.size() == nb, "dyros_sim_create: body_link has entries outside [0,%d)", nl);
-  std::vector<int> pt_start(nl + 1, 0), ppt_body;
-  std::vector<float> ppt_pos, ppt_rad;
-  for (int l = 0; l < nl; ++l) {
-    pt_start[l] = (int)ppt_body.size();
-    for (int i = 0; i < np; ++i)
-      if (m->pt_link[i] == l && !(m->pt_solver && m->pt_solver[i])) {
-        ppt_body.push_back(m->pt_body[i]);
-        for (int k = 0; k < 3; ++k) ppt_pos.push_back((float)m->pt_pos[3 * i + k]);
-        ppt_rad.push_back((float)m->pt_radius[i]);
-      }
-  }
-  pt_start[nl] = (int)ppt_body.size();
-  std::vector<int> cyl_start(nl + 1, 0), ccyl_body;
-  std::vector<float> ccyl_center, ccyl_axis, ccyl_size;
-  for (int l = 0; l < nl; ++l) {
-    cyl_start[l] = (int)ccyl_body.size();
-    for (int i = 0; i < nc; ++i)
-      if (m->cyl_link[i] == l) {
-        ccyl_body.push_back(m->cyl_body[i]);
-        for (int k = 0; k < 3; ++k) ccyl_center.push_back((float)m->cyl_center[3 * i + k]);
-        for (int k = 0; k < 3; ++k) ccyl_axis.push_back((float)m->cyl_axis[3 * i + k]);
-        for (int k = 0; k < 2; ++k) ccyl_size.push_back((float)m->cyl_size[2 * i + k]);
-      }
-  }
-  cyl_start[nl] = (int)ccyl_body.size();
-
-  DevModel& dm = sim->m;
-  memset(&dm, 0, sizeof(dm));
-  dm.nl = nl; dm.nb = nb; dm.nd = nd; dm.np = (int)ppt_body.size(); dm.nc = (int)ccyl_body.size(); dm.T = m->sched_slots;
-  // solver (foot) links, their chains and candidate points, in ascending link order
-  for (int i = 0; i < np; ++i) {
-    if (!(m->pt_solver && m->pt_solver[i])) continue;
-    int l = m->pt_link[i], f = -1;
-    for (int k = 0; k < dm.num_feet; ++k)
-      if (dm.foot_link[k] == l) f = k;
-    if (f < 0) {
-      if (dm.num_feet >= MAX_FEET) {
-        delete sim;
-        set_error("dyros_sim_create: more than %d solver links", MAX_FEET);
-        return 1;
-      }
-      f = dm.num_feet++;
-      dm.foot_link[f] = l;
-    }
-    if (dm.foot_npts[f] >= MAX_SOLVER_PTS) {
-      delete sim;
-      set_error("dyros_sim_create: more than %d solver points on link %d", MAX_SOLVER_PTS, l);
-      return 1;
-    }
-    int k = dm.foot_npts[f]++;
-    dm.foot_pt_body[f][k] = m->pt_body[i];
-    for (int c = 0; c < 3; ++c) dm.foot_pt_pos[f][k][c] = (float)m->pt_pos[3 * i + c];
-    dm.foot_pt_radius[f][k] = (float)m->pt_radius[i];
-  }
-  if (dm.num_feet == 2 && dm.foot_link[0] > dm.foot_link[1]) {
-    std::swap(dm.foot_link[0], dm.foot_link[1]);
-    std::swap(dm.foot_npts[0], dm.foot_npts[1]);
-    for (int k = 0; k < MAX_SOLVER_PTS; ++k) {
-      std::swap(dm.foot_pt_body[0][k], dm.foot_pt_body[1][k]);
-      std::swap(dm.foot_pt_radius[0][k], dm.foot_pt_radius[1][k]);
-      for (int c = 0; c < 3; ++c) std::swap(dm.foot_pt_pos[0][k][c], dm.foot_pt_pos[1][k][c]);
-    }
-  }
-  for (int f = 0; f < dm.num_feet; ++f) {
-    std::vector<int> path;
-    for (int l = dm.foot_link[f]; l > 0; l = m->link_parent[l]) path.push_back(l);
-    if ((int)path.size() > MAX_CHAIN || path.empty()) {
-      delete sim;
-      set_error("dyros_sim_create: solver link %d is %zu joints from the base (max %d)", dm.foot_link[f], path.size(),
-                MAX_CHAIN);
-      return 1;
-    }
-    dm.chain_len[f] = (int)path.size();
-    for (int k = 0; k < (int)path.size(); ++k) dm.chain[f][k] = path[path.size() - 1 - k];
-  }
-  if (dm.num_feet == 2) {  // the two chains must only share the base (block-Jacobi coupling goes through the base)
-    for (int a = 0; a < dm.chain_len[0]; ++a)
-      for (int c = 0; c < dm.chain_len[1]; ++c)
-        if (dm.chain[0][a] == dm.chain[1][c]) {
-          delete sim;
-          set_error("dyros_sim_create: solver links %d and %d share link %d below the base", dm.foot_link[0],
-                    dm.foot_link[1], dm.chain[0][a]);
-          return 1;
-        }
-  }
-
   Blob bl;
-  size_t o_parent = bl.add_i(m->link_parent, nl), o_dof = bl.add_i(m->link_dof, nl);
-  size_t o_E = bl.add_f(m->link_E, nl * 9), o_r = bl.add_f(m->link_r, nl * 3), o_ax = bl.add_f(m->link_axis, nl * 3);
-  size_t o_cs = bl.add_i(child_start.data(), nl + 1), o_ch = bl.add_i(children.data(), children.size());
-  size_t o_bs = bl.add_i(body_start.data(), nl + 1), o_bd = bl.add_i(bodies.data(), nb);
-  size_t o_bl = bl.add_i(m->body_link, nb), o_bp = bl.add_f(m->body_pos, nb * 3), o_br = bl.add_f(m->body_rot, nb * 9);
-  size_t o_bi = bl.add_f(m->body_inertia, nb * 10);
-  size_t o_lo = bl.add_f(m->dof_lower, nd), o_up = bl.add_f(m->dof_upper, nd), o_vl = bl.add_f(m->dof_vel_limit, nd);
-  size_t o_ef = bl.add_f(m->dof_effort, nd);
-  size_t o_ps = bl.add_i(pt_start.data(), nl + 1), o_pb = bl.add_i(ppt_body.data(), ppt_body.size());
-  size_t o_pp = bl.add_f32(ppt_pos.data(), ppt_pos.size()), o_pr = bl.add_f32(ppt_rad.data(), ppt_rad.size());
-  size_t o_ys = bl.add_i(cyl_start.data(), nl + 1), o_yb = bl.add_i(ccyl_body.data(), ccyl_body.size());
-  size_t o_yc = bl.add_f32(ccyl_center.data(), ccyl_center.size()), o_ya = bl.add_f32(ccyl_axis.data(), ccyl_axis.size());
-  size_t o_yz = bl.add_f32(ccyl_size.data(), ccyl_size.size());
-  size_t o_sc = bl.add_i(m->sched, (size_t)m->sched_slots * DYROS_LANES);
-
+  ModelOffsets off;
+  std::string err = build_model_tables(m, bl, sim->m, off);
+  if (!err.empty()) {
+    set_error("dyros_sim_create: %s", err.c_str());
+    delete sim;
+    return 1;
+  }
   cudaError_t e = cudaSetDevice(d->device);
   if (e == cudaSuccess) e = cudaMalloc(&sim->dev_blob, bl.host.size());
   if (e == cudaSuccess) e = cudaMemcpy(sim->dev_blob, bl.host.data(), bl.host.size(), cudaMemcpyHostToDevice);
@@ -236,21 +62,7 @@ static int build_sim(const DyrosSimDesc* d, const DyrosModelDesc* m, const Dyros
     delete sim;
     return 1;
   }
-  void* base = sim->dev_blob;
-  dm.link_parent = at<int>(base, o_parent); dm.link_dof = at<int>(base, o_dof);
-  dm.link_E = at<float>(base, o_E); dm.link_r = at<float>(base, o_r); dm.link_axis = at<float>(base, o_ax);
-  dm.link_child_start = at<int>(base, o_cs); dm.link_children = at<int>(base, o_ch);
-  dm.link_body_start = at<int>(base, o_bs); dm.link_bodies = at<int>(base, o_bd);
-  dm.body_link = at<int>(base, o_bl); dm.body_pos = at<float>(base, o_bp); dm.body_rot = at<float>(base, o_br);
-  dm.body_inertia = at<float>(base, o_bi);
-  dm.dof_lower = at<float>(base, o_lo); dm.dof_upper = at<float>(base, o_up); dm.dof_vel_limit = at<float>(base, o_vl);
-  dm.dof_effort = at<float>(base, o_ef);
-  dm.link_pt_start = at<int>(base, o_ps); dm.pt_body = at<int>(base, o_pb); dm.pt_pos = at<float>(base, o_pp);
-  dm.pt_radius = at<float>(base, o_pr);
-  dm.link_cyl_start = at<int>(base, o_ys); dm.cyl_body = at<int>(base, o_yb); dm.cyl_center = at<float>(base, o_yc);
-  dm.cyl_axis = at<float>(base, o_ya); dm.cyl_size = at<float>(base, o_yz);
-  dm.sched = at<int>(base, o_sc);
-
+  resolve_model(sim->m, off, sim->dev_blob);
   int dev_sms = 0;
   if (cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, d->device) == cudaSuccess && dev_sms > 0)
     sim->sm_count = dev_sms;

@@ -1,0 +1,209 @@
+// Host-only: DyrosModelDesc -> one packed blob of float32/int32 tables + a DevModel whose pointers are resolved
+// against the blob's base address (device memory in capi.cu, host memory in tests/native/hostemu.cpp).
+#pragma once
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+
+namespace dyros {
+
+// Host-side builder of one device blob: arrays are appended, then uploaded with a single copy.
+struct Blob {
+  std::vector<unsigned char> host;
+  size_t add(const void* p, size_t bytes) {
+    size_t off = (host.size() + 15) & ~size_t(15);
+    host.resize(off + bytes);
+    if (bytes) memcpy(host.data() + off, p, bytes);
+    return off;
+  }
+  size_t add_f(const double* p, size_t n) {
+    std::vector<float> f(n);
+    for (size_t i = 0; i < n; ++i) f[i] = (float)p[i];
+    return add(f.data(), n * sizeof(float));
+  }
+  size_t add_f32(const float* p, size_t n) { return add(p, n * sizeof(float)); }
+  size_t add_i(const int* p, size_t n) { return add(p, n * sizeof(int)); }
+};
+
+template <class T>
+static const T* at(void* base, size_t off) {
+  return reinterpret_cast<const T*>(static_cast<unsigned char*>(base) + off);
+}
+
+struct ModelOffsets {
+  size_t parent, dof, E, r, ax, cs, ch, bs, bd, bl, bp, br, bi, lo, up, vl, ef, ps, pb, pp, pr, ys, yb, yc, ya, yz, sc;
+};
+
+// Fills `dm` (counts, foot tables) and appends every table to `bl`. Returns "" or an error message.
+static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevModel& dm, ModelOffsets& o) {
+  char err[256];
+#define MFAIL(...)                        \
+  do {                                    \
+    snprintf(err, sizeof(err), __VA_ARGS__); \
+    return std::string(err);              \
+  } while (0)
+  const int nl = m->num_links, nb = m->num_bodies, nd = m->num_dofs, np = m->num_points, nc = m->num_cyls;
+  if (nl < 1 || nl > DYROS_MAX_LINKS) MFAIL("num_links %d outside [1,%d]", nl, DYROS_MAX_LINKS);
+  if (nb < nl || nb > DYROS_MAX_BODIES) MFAIL("num_bodies %d outside [%d,%d]", nb, nl, DYROS_MAX_BODIES);
+  if (nd != nl - 1) MFAIL("one revolute DOF per non-base link expected (links %d, dofs %d)", nl, nd);
+  if (m->sched_slots < 1 || !m->sched) MFAIL("missing branch schedule");
+  for (int l = 1; l < nl; ++l) {
+    if (m->link_parent[l] < 0 || m->link_parent[l] >= l) MFAIL("link %d parent %d not topological", l, m->link_parent[l]);
+    if (m->link_dof[l] < 0 || m->link_dof[l] >= nd) MFAIL("link %d dof index %d", l, m->link_dof[l]);
+  }
+  {  // every link exactly once in the schedule, after its parent
+    std::vector<int> slot(nl, -1);
+    for (int t = 0; t < m->sched_slots; ++t)
+      for (int g = 0; g < DYROS_LANES; ++g) {
+        int l = m->sched[t * DYROS_LANES + g];
+        if (l < 0) continue;
+        if (l < 1 || l >= nl || slot[l] >= 0) MFAIL("bad schedule entry %d", l);
+        int p = m->link_parent[l];
+        if (!(p == 0 || (slot[p] >= 0 && slot[p] < t))) MFAIL("schedule runs link %d before its parent", l);
+        slot[l] = t;
+      }
+    for (int l = 1; l < nl; ++l)
+      if (slot[l] < 0) MFAIL("link %d missing from the schedule", l);
+  }
+  // ---- derived tables
+  std::vector<int> child_start(nl + 1, 0), children;
+  for (int l = 0; l < nl; ++l) {
+    child_start[l] = (int)children.size();
+    for (int c = 1; c < nl; ++c)
+      if (m->link_parent[c] == l) children.push_back(c);
+  }
+  child_start[nl] = (int)children.size();
+  std::vector<int> body_start(nl + 1, 0), bodies;
+  for (int l = 0; l < nl; ++l) {
+    body_start[l] = (int)bodies.size();
+    for (int bb = 0; bb < nb; ++bb)
+      if (m->body_link[bb] == l) bodies.push_back(bb);
+  }
+  body_start[nl] = (int)bodies.size();
+  if ((int)bodies.size() != nb) MFAIL("body_link has entries outside [0,%d)", nl);
+  std::vector<int> pt_start(nl + 1, 0), ppt_body;
+  std::vector<float> ppt_pos, ppt_rad;
+  for (int l = 0; l < nl; ++l) {
+    pt_start[l] = (int)ppt_body.size();
+    for (int i = 0; i < np; ++i)
+      if (m->pt_link[i] == l && !(m->pt_solver && m->pt_solver[i])) {
+        ppt_body.push_back(m->pt_body[i]);
+        for (int k = 0; k < 3; ++k) ppt_pos.push_back((float)m->pt_pos[3 * i + k]);
+        ppt_rad.push_back((float)m->pt_radius[i]);
+      }
+  }
+  pt_start[nl] = (int)ppt_body.size();
+  std::vector<int> cyl_start(nl + 1, 0), ccyl_body;
+  std::vector<float> ccyl_center, ccyl_axis, ccyl_size;
+  for (int l = 0; l < nl; ++l) {
+    cyl_start[l] = (int)ccyl_body.size();
+    for (int i = 0; i < nc; ++i)
+      if (m->cyl_link[i] == l) {
+        ccyl_body.push_back(m->cyl_body[i]);
+        for (int k = 0; k < 3; ++k) ccyl_center.push_back((float)m->cyl_center[3 * i + k]);
+        for (int k = 0; k < 3; ++k) ccyl_axis.push_back((float)m->cyl_axis[3 * i + k]);
+        for (int k = 0; k < 2; ++k) ccyl_size.push_back((float)m->cyl_size[2 * i + k]);
+      }
+  }
+  cyl_start[nl] = (int)ccyl_body.size();
+
+  memset(&dm, 0, sizeof(dm));
+  dm.nl = nl; dm.nb = nb; dm.nd = nd; dm.np = (int)ppt_body.size(); dm.nc = (int)ccyl_body.size(); dm.T = m->sched_slots;
+  // solver (foot) links, their chains and candidate points, in ascending link order
+  for (int i = 0; i < np; ++i) {
+    if (!(m->pt_solver && m->pt_solver[i])) continue;
+    int l = m->pt_link[i], f = -1;
+    for (int k = 0; k < dm.num_feet; ++k)
+      if (dm.foot_link[k] == l) f = k;
+    if (f < 0) {
+      if (dm.num_feet >= MAX_FEET) MFAIL("more than %d solver links", MAX_FEET);
+      f = dm.num_feet++;
+      dm.foot_link[f] = l;
+    }
+    if (dm.foot_npts[f] >= MAX_SOLVER_PTS) MFAIL("more than %d solver points on link %d", MAX_SOLVER_PTS, l);
+    int k = dm.foot_npts[f]++;
+    dm.foot_pt_body[f][k] = m->pt_body[i];
+    for (int c = 0; c < 3; ++c) dm.foot_pt_pos[f][k][c] = (float)m->pt_pos[3 * i + c];
+    dm.foot_pt_radius[f][k] = (float)m->pt_radius[i];
+  }
+  if (dm.num_feet == 2 && dm.foot_link[0] > dm.foot_link[1]) {
+    std::swap(dm.foot_link[0], dm.foot_link[1]);
+    std::swap(dm.foot_npts[0], dm.foot_npts[1]);
+    for (int k = 0; k < MAX_SOLVER_PTS; ++k) {
+      std::swap(dm.foot_pt_body[0][k], dm.foot_pt_body[1][k]);
+      std::swap(dm.foot_pt_radius[0][k], dm.foot_pt_radius[1][k]);
+      for (int c = 0; c < 3; ++c) std::swap(dm.foot_pt_pos[0][k][c], dm.foot_pt_pos[1][k][c]);
+    }
+  }
+  for (int f = 0; f < dm.num_feet; ++f) {
+    std::vector<int> path;
+    for (int l = dm.foot_link[f]; l > 0; l = m->link_parent[l]) path.push_back(l);
+    if ((int)path.size() > MAX_CHAIN || path.empty()) MFAIL("solver link %d is %zu joints from the base (max %d)", dm.foot_link[f], path.size(),
+                MAX_CHAIN);
+    dm.chain_len[f] = (int)path.size();
+    for (int k = 0; k < (int)path.size(); ++k) dm.chain[f][k] = path[path.size() - 1 - k];
+  }
+  if (dm.num_feet == 2) {  // the two chains must only share the base (block-Jacobi coupling goes through the base)
+    for (int a = 0; a < dm.chain_len[0]; ++a)
+      for (int c = 0; c < dm.chain_len[1]; ++c)
+        if (dm.chain[0][a] == dm.chain[1][c]) MFAIL("solver links %d and %d share link %d below the base", dm.foot_link[0],
+                    dm.foot_link[1], dm.chain[0][a]);
+  }
+
+  o.parent = bl.add_i(m->link_parent, nl); o.dof = bl.add_i(m->link_dof, nl);
+  o.E = bl.add_f(m->link_E, nl * 9); o.r = bl.add_f(m->link_r, nl * 3); o.ax = bl.add_f(m->link_axis, nl * 3);
+  o.cs = bl.add_i(child_start.data(), nl + 1); o.ch = bl.add_i(children.data(), children.size());
+  o.bs = bl.add_i(body_start.data(), nl + 1); o.bd = bl.add_i(bodies.data(), nb);
+  o.bl = bl.add_i(m->body_link, nb); o.bp = bl.add_f(m->body_pos, nb * 3); o.br = bl.add_f(m->body_rot, nb * 9);
+  o.bi = bl.add_f(m->body_inertia, nb * 10);
+  o.lo = bl.add_f(m->dof_lower, nd); o.up = bl.add_f(m->dof_upper, nd); o.vl = bl.add_f(m->dof_vel_limit, nd);
+  o.ef = bl.add_f(m->dof_effort, nd);
+  o.ps = bl.add_i(pt_start.data(), nl + 1); o.pb = bl.add_i(ppt_body.data(), ppt_body.size());
+  o.pp = bl.add_f32(ppt_pos.data(), ppt_pos.size()); o.pr = bl.add_f32(ppt_rad.data(), ppt_rad.size());
+  o.ys = bl.add_i(cyl_start.data(), nl + 1); o.yb = bl.add_i(ccyl_body.data(), ccyl_body.size());
+  o.yc = bl.add_f32(ccyl_center.data(), ccyl_center.size()); o.ya = bl.add_f32(ccyl_axis.data(), ccyl_axis.size());
+  o.yz = bl.add_f32(ccyl_size.data(), ccyl_size.size());
+  o.sc = bl.add_i(m->sched, (size_t)m->sched_slots * DYROS_LANES);
+
+  return std::string();
+#undef MFAIL
+}
+
+static void resolve_model(DevModel& dm, const ModelOffsets& o, void* base) {
+  dm.link_parent = at<int>(base, o.parent); dm.link_dof = at<int>(base, o.dof);
+  dm.link_E = at<float>(base, o.E); dm.link_r = at<float>(base, o.r); dm.link_axis = at<float>(base, o.ax);
+  dm.link_child_start = at<int>(base, o.cs); dm.link_children = at<int>(base, o.ch);
+  dm.link_body_start = at<int>(base, o.bs); dm.link_bodies = at<int>(base, o.bd);
+  dm.body_link = at<int>(base, o.bl); dm.body_pos = at<float>(base, o.bp); dm.body_rot = at<float>(base, o.br);
+  dm.body_inertia = at<float>(base, o.bi);
+  dm.dof_lower = at<float>(base, o.lo); dm.dof_upper = at<float>(base, o.up); dm.dof_vel_limit = at<float>(base, o.vl);
+  dm.dof_effort = at<float>(base, o.ef);
+  dm.link_pt_start = at<int>(base, o.ps); dm.pt_body = at<int>(base, o.pb); dm.pt_pos = at<float>(base, o.pp);
+  dm.pt_radius = at<float>(base, o.pr);
+  dm.link_cyl_start = at<int>(base, o.ys); dm.cyl_body = at<int>(base, o.yb); dm.cyl_center = at<float>(base, o.yc);
+  dm.cyl_axis = at<float>(base, o.ya); dm.cyl_size = at<float>(base, o.yz);
+  dm.sched = at<int>(base, o.sc);
+}
+
+static void fill_sim_params(const DyrosSimDesc* d, SimParams& p) {
+  p.N = d->num_envs;
+  p.substeps = d->substeps;
+  p.dt = (float)(d->dt / (double)d->substeps);
+  for (int i = 0; i < 3; ++i) p.g[i] = d->gravity[i];
+  p.contact_offset = d->contact_offset;
+  p.max_depen_vel = d->max_depenetration_velocity;
+  p.erp = d->contact_erp;
+  p.mu = d->friction;
+  p.pen_k = d->penalty_stiffness;
+  p.pen_c = d->penalty_damping;
+  p.pen_fmax = d->penalty_max_force;
+  p.max_ang_vel = d->max_angular_velocity;
+  p.sweeps = d->contact_sweeps;
+  p.clamp_effort = d->clamp_effort;
+}
+
+}  // namespace dyros

@@ -1,7 +1,125 @@
-// placeholder until the physics kernel lands (next commit): fails loudly
-#include "internal.h"
+// K1: gym.simulate as one kernel launch. DYROS_LANES lanes per env (branch-parallel recursions over the link
+// tree), envs_per_block envs per CTA sized so that one CTA per SM covers N = 4096 on 148 SMs in a single wave;
+// the per-env scratch of physics_core.cuh lives in dynamic shared memory.
+#include "physics_core.cuh"
+
 namespace dyros {
-int physics_configure(Sim*) { return 0; }
-int launch_simulate(Sim*, int, const float*, cudaStream_t) { set_error("physics kernel not built"); return 1; }
-int launch_refresh_rigid_body_state(Sim*, cudaStream_t) { set_error("physics kernel not built"); return 1; }
+
+struct WarpSync {
+  __device__ __forceinline__ void operator()() const { __syncwarp(); }
+};
+
+constexpr int kMaxPhysSmem = 227 * 1024;
+
+__global__ void __launch_bounds__(128) k_simulate(DevModel m, SimParams p, DyrosSimBuffers b, const float* __restrict__ push,
+                                                  int apply_wrench, int epb, int es) {
+  extern __shared__ float smem[];
+  const int le = threadIdx.x / DYROS_LANES, g = threadIdx.x % DYROS_LANES;
+  const int e = blockIdx.x * epb + le;
+  if (le >= epb || e >= p.N) return;  // whole lane groups leave together: every sync is inside one group
+  EnvIO io;
+  io.root = b.root_states + (size_t)e * 13;
+  io.dof_state = b.dof_state + (size_t)e * m.nd * 2;
+  io.tau = b.dof_actuation_force + (size_t)e * m.nd;
+  io.damping = b.dof_damping + (size_t)e * m.nd;
+  io.armature = b.dof_armature + (size_t)e * m.nd;
+  io.mass_scale = b.body_mass_scale + (size_t)e * m.nb;
+  io.contact = b.net_contact_force + (size_t)e * m.nb * 3;
+  io.push = push ? push + (size_t)e * 3 : nullptr;
+  io.rb_force = apply_wrench ? b.rb_force + (size_t)e * m.nb * 3 : nullptr;
+  io.rb_torque = apply_wrench ? b.rb_torque + (size_t)e * m.nb * 3 : nullptr;
+  io.live = true;
+  WarpSync sync;
+  real* sm = smem + (size_t)le * es;
+  for (int s = 0; s < p.substeps; ++s) {
+    env_substep(io, sm, m, p, g, sync);
+    io.push = nullptr;  // applied wrenches act "for the immediate timestep" (gym_py.html apply_rigid_body_force_tensors)
+    io.rb_force = nullptr;
+    io.rb_torque = nullptr;
+  }
 }
+
+int physics_configure(Sim* sim) {
+  const int es = env_scratch_floats(sim->m.nl);
+  const int max_epb = std::min(kMaxPhysSmem / (es * (int)sizeof(float)), 128 / DYROS_LANES);
+  if (max_epb < 1) {
+    set_error("physics_configure: one env needs %d bytes of shared memory", es * (int)sizeof(float));
+    return 1;
+  }
+  int epb = (sim->p.N + sim->sm_count - 1) / sim->sm_count;  // one wave when it fits
+  epb = std::max(epb, 8);
+  epb = std::min(epb, max_epb);
+  sim->envs_per_block = epb;
+  sim->phys_smem = (size_t)epb * es * sizeof(float);
+  DY_CUDA(cudaFuncSetAttribute(k_simulate, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPhysSmem));
+  return 0;
+}
+
+int launch_simulate(Sim* sim, int apply_wrench, const float* push, cudaStream_t s) {
+  const int epb = sim->envs_per_block;
+  const int grid = (sim->p.N + epb - 1) / epb;
+  const int threads = ((epb * DYROS_LANES + 31) / 32) * 32;
+  k_simulate<<<grid, threads, sim->phys_smem, s>>>(sim->m, sim->p, sim->b, push, apply_wrench, epb,
+                                                   env_scratch_floats(sim->m.nl));
+  DY_LAUNCH_CHECK();
+  return 0;
+}
+
+// gym.refresh_rigid_body_state_tensor: forward kinematics of every body (tensors.rst.txt:193-207), one thread per env.
+__global__ void __launch_bounds__(64) k_rigid_body_state(DevModel m, SimParams p, DyrosSimBuffers b) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= p.N) return;
+  M3 Rw[DYROS_MAX_LINKS];
+  V3 pw[DYROS_MAX_LINKS];
+  SV v[DYROS_MAX_LINKS];
+  const float* root = b.root_states + (size_t)e * 13;
+  const float* ds = b.dof_state + (size_t)e * m.nd * 2;
+  Rw[0] = quat_to_mat(root[3], root[4], root[5], root[6]);
+  pw[0] = ld3_f(root);
+  v[0] = SV{mulT(Rw[0], ld3_f(root + 10)), mulT(Rw[0], ld3_f(root + 7))};
+  for (int i = 1; i < m.nl; ++i) {
+    int pr = m.link_parent[i], d = m.link_dof[i];
+    V3 ax = ld3_f(m.link_axis + 3 * i), r = ld3_f(m.link_r + 3 * i);
+    float q = ds[2 * d], qd = ds[2 * d + 1];
+    M3 E = mul(axis_rot_T(ax, sinf(q), cosf(q)), ld_m3_f(m.link_E + 9 * i));
+    v[i] = xform_motion(E, r, v[pr]);
+    v[i].w = v[i].w + qd * ax;
+    Rw[i] = mulABt(Rw[pr], E);
+    pw[i] = pw[pr] + mul(Rw[pr], r);
+  }
+  for (int bb = 0; bb < m.nb; ++bb) {
+    int l = m.body_link[bb];
+    V3 bp = ld3_f(m.body_pos + 3 * bb);
+    M3 Rb = mul(Rw[l], ld_m3_f(m.body_rot + 9 * bb));
+    V3 pos = pw[l] + mul(Rw[l], bp);
+    V3 lin = mul(Rw[l], v[l].v + cross(v[l].w, bp));
+    V3 ang = mul(Rw[l], v[l].w);
+    // rotation -> quaternion xyzw
+    const real* a = Rb.a;
+    real tr = a[0] + a[4] + a[8], qx, qy, qz, qw;
+    if (tr > 0) {
+      real s = sqrtf(tr + 1.f) * 2.f;
+      qw = 0.25f * s; qx = (a[7] - a[5]) / s; qy = (a[2] - a[6]) / s; qz = (a[3] - a[1]) / s;
+    } else if (a[0] > a[4] && a[0] > a[8]) {
+      real s = sqrtf(1.f + a[0] - a[4] - a[8]) * 2.f;
+      qw = (a[7] - a[5]) / s; qx = 0.25f * s; qy = (a[1] + a[3]) / s; qz = (a[2] + a[6]) / s;
+    } else if (a[4] > a[8]) {
+      real s = sqrtf(1.f + a[4] - a[0] - a[8]) * 2.f;
+      qw = (a[2] - a[6]) / s; qx = (a[1] + a[3]) / s; qy = 0.25f * s; qz = (a[5] + a[7]) / s;
+    } else {
+      real s = sqrtf(1.f + a[8] - a[0] - a[4]) * 2.f;
+      qw = (a[3] - a[1]) / s; qx = (a[2] + a[6]) / s; qy = (a[5] + a[7]) / s; qz = 0.25f * s;
+    }
+    float* o = b.rigid_body_state + ((size_t)e * m.nb + bb) * 13;
+    o[0] = pos.x; o[1] = pos.y; o[2] = pos.z; o[3] = qx; o[4] = qy; o[5] = qz; o[6] = qw;
+    o[7] = lin.x; o[8] = lin.y; o[9] = lin.z; o[10] = ang.x; o[11] = ang.y; o[12] = ang.z;
+  }
+}
+
+int launch_refresh_rigid_body_state(Sim* sim, cudaStream_t s) {
+  k_rigid_body_state<<<(sim->p.N + 63) / 64, 64, 0, s>>>(sim->m, sim->p, sim->b);
+  DY_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace dyros

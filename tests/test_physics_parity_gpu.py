@@ -1,0 +1,100 @@
+"""GPU parity of dyros_simulate (CUDA, float32, O(n) recursions, through the C ABI) against the dense fp64 oracle
+on identical states. PhysX itself is absent from the reference checkout (parity with it unpinned, see
+oracle/physics_oracle.py); the per-quantity tolerances below are on single-step state deltas."""
+import numpy as np
+import pytest
+import torch
+
+from isaacgymdyros_b200.core import CoreConfig
+from oracle.physics_oracle import PhysicsOracle
+from tests.golden_util import load_assets
+from tests.physics_util import oracle_params, random_states
+from tests.test_physics_emulation import compare
+
+pytestmark = pytest.mark.gpu
+
+
+def load_sim_state(core, st):
+    dev, N = core.device, core.N
+    T = lambda a: torch.tensor(np.ascontiguousarray(a, dtype=np.float32), device=dev)
+    core.sim_t["root_states"].copy_(T(st["root"]))
+    ds = core.sim_t["dof_state"].view(N, 33, 2)
+    ds[:, :, 0] = T(st["q"])
+    ds[:, :, 1] = T(st["qd"])
+    core.sim_t["dof_actuation_force"].copy_(T(st["tau"]).reshape(-1))
+    core.sim_t["dof_damping"].copy_(T(st["damping"]))
+    core.sim_t["dof_armature"].copy_(T(st["armature"]))
+    core.sim_t["body_mass_scale"].copy_(T(st["mass_scale"]))
+
+
+def read_sim_state(core):
+    N = core.N
+    ds = core.sim_t["dof_state"].view(N, 33, 2)
+    f = lambda t: t.cpu().numpy().astype(np.float64)
+    return f(core.sim_t["root_states"]), f(ds[:, :, 0]), f(ds[:, :, 1]), f(core.sim_t["net_contact_force"].view(N, 38, 3))
+
+
+@pytest.mark.parametrize("kind,N,seed", [("air", 7, 0), ("stand", 64, 1), ("mixed", 300, 2)])
+def test_cuda_simulate_matches_dense_oracle(kind, N, seed):
+    from isaacgymdyros_b200.core import DyrosCore
+    tables = load_assets()[0]
+    cfg = CoreConfig(with_rb_force_tensors=True)
+    o = PhysicsOracle(tables, oracle_params(cfg))
+    rng = np.random.default_rng(seed)
+    st = random_states(N, rng, tables, kind)
+    F, Tq = rng.normal(0, 30, (N, 38, 3)), rng.normal(0, 3, (N, 38, 3))
+    want = o.substep(st["root"], st["q"], st["qd"], st["tau"], st["damping"], st["armature"], st["mass_scale"],
+                     rb_force=F, rb_torque=Tq)
+    core = DyrosCore(N, "cuda:0", cfg)
+    load_sim_state(core, st)
+    core.sim_t["rb_force"].copy_(torch.tensor(F, dtype=torch.float32).reshape(-1, 3))
+    core.sim_t["rb_torque"].copy_(torch.tensor(Tq, dtype=torch.float32).reshape(-1, 3))
+    core.simulate(apply_wrench=True)
+    torch.cuda.synchronize()
+    compare(st, read_sim_state(core), want, ctx=f"{kind}: ")
+    core.close()
+
+
+def test_cuda_standing_carries_weight_on_feet_only():
+    """Physical invariant on the GPU at the full size: 4096 robots held at the reset pose by a stiff PD settle with
+    the ground reaction equal to their weight, on bodies 8 and 16 only."""
+    from isaacgymdyros_b200.core import DyrosCore, INIT_DOF_POS, KP, KV
+    N = 4096
+    core = DyrosCore(N, "cuda:0", CoreConfig())
+    dev = core.device
+    kp, kv = torch.tensor(KP, device=dev), torch.tensor(KV, device=dev)
+    q0 = torch.tensor(INIT_DOF_POS, device=dev)
+    ds = core.sim_t["dof_state"].view(N, 33, 2)
+    for s in range(400):
+        core.sim_t["dof_actuation_force"].copy_((kp * (q0 - ds[:, :, 0]) - kv * ds[:, :, 1]).reshape(-1))
+        core.simulate()
+    torch.cuda.synchronize()
+    cf = core.sim_t["net_contact_force"].view(N, 38, 3)
+    fz = cf[:, :, 2].sum(1)
+    w = 104.48712 * 9.81
+    assert torch.isfinite(core.sim_t["root_states"]).all()
+    assert (fz - w).abs().max().item() < 0.05 * w
+    others = [b for b in range(38) if b not in (8, 16)]
+    assert cf[:, others].abs().max().item() == 0.0
+    assert (core.sim_t["root_states"][:, 2] - 0.93).abs().max().item() < 0.01
+    core.close()
+
+
+def test_cuda_rigid_body_state_matches_oracle():
+    from isaacgymdyros_b200.core import DyrosCore
+    tables = load_assets()[0]
+    cfg = CoreConfig(with_rigid_body_state=True)
+    o = PhysicsOracle(tables, oracle_params(cfg))
+    N = 50
+    st = random_states(N, np.random.default_rng(4), tables, "mixed")
+    core = DyrosCore(N, "cuda:0", cfg)
+    load_sim_state(core, st)
+    core.refresh_rigid_body_state()
+    torch.cuda.synchronize()
+    got = core.sim_t["rigid_body_state"].view(N, 38, 13).cpu().numpy().astype(np.float64)
+    want = o.rigid_body_state(st["root"], st["q"], st["qd"])
+    assert np.abs(got[..., :3] - want[..., :3]).max() < 5e-6
+    sign = np.sign((got[..., 3:7] * want[..., 3:7]).sum(-1, keepdims=True))
+    assert np.abs(got[..., 3:7] * sign - want[..., 3:7]).max() < 5e-6
+    assert np.abs(got[..., 7:] - want[..., 7:]).max() < 2e-5
+    core.close()
