@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the DyrosDynamicWalk hot path (BASELINE.json metric, configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs 4096] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one VecTask.step of every env of the shard: PD/delay + 2 physics sub-steps + sensor noise +
+termination + reward + reset + observations. Envs shard across ranks with no data-path collective
+(weak scaling: 4096 envs per GPU); NCCL is used for the barrier, the max-over-ranks timing and the episode statistics.
+
+Prints ONE JSON line (rank 0). `value` is device-resident throughput with the L2 flushed between timed steps;
+`e2e` goes through DyrosDynamicWalk.step with pinned HOST buffers (actions H2D, obs/reward/reset D2H every step).
+`--impl reference` times the CPU oracle port (oracle/env_oracle.py) on the host cores: the reference's own physics
+is closed-source PhysX whose binaries are absent from the checkout, so the "reference arm" is the port.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/s at 4096 envs/GPU"
+UNIT = "env-steps/s"
+WORKLOAD = "DyrosDynamicWalk 4096 envs/GPU, random actions, physics + PD + obs/reward/reset kernels (BASELINE configs[1])"
+K1_BYTES_PER_ENV_SUBSTEP = 1648      # K1 reads root13+dof66+torque33+ext3+DR104, writes root13+dof66+contact114 (fp32 words)
+ENV_STEP_BYTES = 7044                # SURVEY 8d canonical bytes per env-step
+K1_FLOP_PER_ENV_SUBSTEP = 52500      # DESIGN.md section 6 (FMA = 2 FLOP), this algorithm
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:  # noqa: BLE001
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU oracle port
+def make_cpu_env(n_envs, seed):
+    import numpy as np
+    from oracle.env_oracle import EnvOracle
+    from oracle import task_oracle as O
+    from isaacgymdyros_b200.model.tables import ModelTables
+    assets = os.path.join(ROOT, "isaacgymdyros_b200", "assets")
+    tables = ModelTables.load(os.path.join(assets, "tocabi_tables.npz"))
+    mocap, obs_norm = np.load(os.path.join(assets, "mocap_walk.npy")), np.load(os.path.join(assets, "obs_norm.npy"))
+    rng = np.random.default_rng(seed)
+    env = EnvOracle(n_envs, tables, mocap, obs_norm, rng=rng)
+    return env, rng, O
+
+
+def cpu_worker(args):
+    """Steps a 64-env shard of the workload with the oracle port for up to `steps` steps or `seconds` seconds."""
+    n_envs, steps, warmup, seconds, seed = args
+    try:
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(limits=1)
+    except Exception:  # noqa: BLE001
+        import contextlib
+        ctx = contextlib.nullcontext()
+    with ctx:
+        env, rng, O = make_cpu_env(n_envs, seed)
+        import numpy as np
+        act = lambda: rng.uniform(-1, 1, (n_envs, 13)).astype(np.float32)
+        for _ in range(warmup):
+            env.step(act(), O.draw_noise(n_envs, 2, rng))
+        done, t0 = 0, time.perf_counter()
+        while done < steps and (time.perf_counter() - t0) < seconds:
+            env.step(act(), O.draw_noise(n_envs, 2, rng))
+            done += 1
+        return done, time.perf_counter() - t0
+
+
+def cpu_baseline(seconds):
+    done, el = cpu_worker((64, 10 ** 9, 1, seconds, 42))
+    return {"value": 64 * done / el, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{done} steps of a 64-env shard (BASELINE configs[0] size) with oracle/env_oracle.py "
+                      f"(numpy task restatement + dense fp64 physics), 1 thread, {el:.1f} s; not PhysX"}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    workers = max(1, min(os.cpu_count() or 1, 32))
+    budget = 150.0
+    per_step_guess = 0.2
+    steps = max(1, min(a.steps, int(budget / per_step_guess)))
+    warm = min(a.warmup, 3)
+    with mp.get_context("spawn").Pool(workers) as pool:
+        res = pool.map(cpu_worker, [(64, steps, warm, budget, 42 + i) for i in range(workers)])
+    total = sum(64 * d for d, _ in res)
+    el = max(e for _, e in res)
+    value = total / el
+    steps_done = min(d for d, _ in res)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps_done,
+            "warmup": warm, "ms_per_step": 1e3 * el / max(steps_done, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": a.envs},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+                             "sample": f"{workers} processes x 64-env shards x {steps_done} steps of the oracle port "
+                                       f"(reference PhysX binaries absent: SURVEY fact 2), {el:.1f} s"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from isaacgymdyros_b200 import DyrosDynamicWalk, default_cfg
+    from isaacgymdyros_b200.core import measure_fp32_peak
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = f"cuda:{local}"
+    torch.cuda.set_device(dev)
+    N, K, W = a.envs, a.steps, max(a.warmup, 3)
+    env = DyrosDynamicWalk(default_cfg(N), dev, rank=rank)
+    g = torch.Generator(device=dev)
+    g.manual_seed(42 + rank)  # reference default seed, cfg/config.yaml:11
+    pool = [torch.rand(N, 13, device=dev, generator=g) * 2 - 1 for _ in range(16)]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step(i):
+        env._actions_static.copy_(pool[i % len(pool)])
+        env._graph.replay()
+
+    env.step(pool[0])  # captures the graph
+    for i in range(W):
+        device_step(i)
+    barrier()
+    # ---- (1) device-resident, L2 flushed between timed steps: `value`
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    with ClockSampler(local) as clk:
+        barrier()
+        t_wall0 = time.perf_counter()
+        for i in range(K):
+            flush.fill_(i & 0xFF)
+            ev[i][0].record()
+            device_step(W + i)
+            ev[i][1].record()
+        barrier()
+        t_wall_flush = time.perf_counter() - t_wall0
+        cold_ms = sum(s.elapsed_time(e) for s, e in ev)
+        # ---- (2) back to back (state L2-resident, as in the real rollout loop)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        s0.record()
+        for i in range(K):
+            device_step(W + K + i)
+        s1.record()
+        barrier()
+        warm_ms = s0.elapsed_time(s1)
+        # ---- (3) end to end through the public API with host buffers
+        h_act = [p.cpu().pin_memory() for p in pool]
+        h_obs = torch.empty(N, 487).pin_memory()
+        h_rew = torch.empty(N).pin_memory()
+        h_rst = torch.empty(N, dtype=torch.int64).pin_memory()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(K):
+            obs, rew, rst, _ = env.step(h_act[i % len(h_act)].to(dev, non_blocking=True))
+            h_obs.copy_(obs["obs"], non_blocking=True)
+            h_rew.copy_(rew, non_blocking=True)
+            h_rst.copy_(rst, non_blocking=True)
+        e1.record()
+        barrier()
+        e2e_ms = e0.elapsed_time(e1)
+    clocks = clk.summary()
+    h2d, d2h = N * 13 * 4, N * 487 * 4 + N * 4 + N * 8
+    # ---- (4) the dominant kernel alone (k_simulate), inside real staged steps, L2 flushed before each launch
+    KS = min(K, 50)
+    kev = []
+    core = env.core
+    for i in range(KS):
+        core.prologue(pool[i % len(pool)])
+        for k in range(2):
+            core.substep_torque()
+            flush.fill_(k)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            core.simulate()
+            a1.record()
+            kev.append((a0, a1))
+            core.sensor_noise(k)
+        env.post_physics_step()
+    torch.cuda.synchronize()
+    k1_ms = statistics.mean(s.elapsed_time(e) for s, e in kev)
+    reset_rate = float(env.reset_buf.float().mean().item())
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    cold_ms, warm_ms, e2e_ms, k1_ms = (reduce_max(x) for x in (cold_ms, warm_ms, e2e_ms, k1_ms))
+    # episode statistics across ranks (the only data the env path ever reduces)
+    stats = torch.stack([env.epi_len_log.mean(), env.contact_reward_mean.nan_to_num().mean()]).double()
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        stats /= world
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        fp32_peak = measure_fp32_peak(local)
+        total_envs = N * world
+        value = total_envs * K / (cold_ms * 1e-3)
+        k1_bytes = K1_BYTES_PER_ENV_SUBSTEP * N
+        achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": cold_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": N, "actions": "torch.rand(N,13)*2-1, seed 42",
+                       "domain_randomisation": True, "perturbation": "gated as in the reference (T:489)",
+                       "l2": "flushed between timed steps (256 MiB fill outside the timed intervals)",
+                       "timing": "CUDA events per step on the launch stream, summed; max over ranks",
+                       "launch_geometry": core.launch_info(), "reset_rate_last_step": reset_rate},
+            "clocks": clocks,
+            "e2e": {"value": total_envs * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
+            "gpu_launches": K * core.step_launches(),
+            "value_warm_l2": total_envs * K / (warm_ms * 1e-3), "ms_per_step_warm_l2": warm_ms / K,
+            "roofline": {"bound": "hbm", "kernel": "k_simulate (one physics sub-step of all envs)",
+                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "traffic": None,
+                         "launch_ms": k1_ms, "algorithmic_bytes_per_launch": k1_bytes,
+                         "note": "K1 is FP32-latency bound, not HBM bound (SURVEY 8d): see fp32"},
+            "fp32": {"achieved": K1_FLOP_PER_ENV_SUBSTEP * N / (k1_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": K1_FLOP_PER_ENV_SUBSTEP * N / (k1_ms * 1e-3) / 1e12 / fp32_peak,
+                     "peak_source": "dyros_measure_fp32_peak (FFMA saturation, this run)"},
+            "whole_step_hbm": {"achieved": ENV_STEP_BYTES * N / (cold_ms / K * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"},
+            "episode_stats": {"epi_len_log_mean": float(stats[0]), "contact_reward_mean": float(stats[1])},
+            "wall_s_flush_loop": t_wall_flush,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(a.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

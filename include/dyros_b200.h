@@ -205,6 +205,12 @@ int dyros_refresh_rigid_body_state(DyrosSim* sim, void* stream);
  * already (immediate CPU-pipeline semantics); validates the ids and returns. */
 int dyros_set_state_indexed(DyrosSim* sim, const int32_t* env_ids, int count, void* stream);
 
+/* Measurement aid (no reference counterpart): FFMA-saturation micro-benchmark giving the FP32 roofline denominator
+ * that MEASURED_PEAKS.json lacks. Synchronous; returns TFLOP/s (FMA = 2 FLOP). */
+int dyros_measure_fp32_peak(int device, int iters, double* tflops_out);
+/* Physics launch geometry chosen at create time: envs per CTA, CTAs, threads per CTA, dynamic shared memory bytes. */
+int dyros_sim_launch_info(DyrosSim* sim, int32_t out[4]);
+
 /* --- task level (bodies of DyrosDynamicWalk methods) --- */
 int dyros_task_create(DyrosSim* sim, const DyrosTaskDesc* desc, const DyrosTaskBuffers* buf, DyrosTask** out);
 int dyros_task_destroy(DyrosTask* task);

@@ -133,6 +133,13 @@ def make_sim_desc(cfg: "CoreConfig", num_envs: int, device_index: int = 0):
     return sd
 
 
+def measure_fp32_peak(device_index: int = 0, iters: int = 20000) -> float:
+    """TFLOP/s of an FFMA-saturation kernel on this GPU (the FP32 roofline denominator)."""
+    out = C.c_double()
+    native.check(native.load().dyros_measure_fp32_peak(device_index, iters, C.byref(out)), "dyros_measure_fp32_peak")
+    return out.value
+
+
 class DyrosCore:
     def __init__(self, num_envs: int, device: str = "cuda:0", cfg: Optional[CoreConfig] = None,
                  tables: Optional[ModelTables] = None, seed: int = 42, rank: int = 0):
@@ -287,6 +294,11 @@ class DyrosCore:
 
     def simulate(self, apply_wrench: bool = False):
         native.check(self.lib.dyros_simulate(self.sim_handle, int(apply_wrench), self._stream), "dyros_simulate")
+
+    def launch_info(self) -> dict:
+        out = (C.c_int32 * 4)()
+        native.check(self.lib.dyros_sim_launch_info(self.sim_handle, C.byref(out)), "dyros_sim_launch_info")
+        return {"envs_per_cta": out[0], "ctas": out[1], "threads_per_cta": out[2], "smem_bytes": out[3]}
 
     def refresh_rigid_body_state(self):
         native.check(self.lib.dyros_refresh_rigid_body_state(self.sim_handle, self._stream), "dyros_refresh_rigid_body_state")

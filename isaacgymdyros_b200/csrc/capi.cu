@@ -228,6 +228,26 @@ int dyros_set_state_indexed(DyrosSim* sim, const int32_t* env_ids, int count, vo
   return 0;  // buffers are the live state (immediate CPU-pipeline semantics)
 }
 
+int dyros_measure_fp32_peak(int device, int iters, double* tflops_out) {
+  if (!tflops_out || iters < 1) {
+    set_error("dyros_measure_fp32_peak: bad arguments");
+    return 1;
+  }
+  return measure_fp32_peak(device, iters, tflops_out);
+}
+int dyros_sim_launch_info(DyrosSim* sim, int32_t out[4]) {
+  SIM_OR_FAIL("dyros_sim_launch_info");
+  if (!out) {
+    set_error("dyros_sim_launch_info: out is NULL");
+    return 1;
+  }
+  out[0] = s->envs_per_block;
+  out[1] = (s->p.N + s->envs_per_block - 1) / s->envs_per_block;
+  out[2] = ((s->envs_per_block * DYROS_LANES + 31) / 32) * 32;
+  out[3] = (int32_t)s->phys_smem;
+  return 0;
+}
+
 int dyros_task_create(DyrosSim* sim, const DyrosTaskDesc* desc, const DyrosTaskBuffers* buf, DyrosTask** out) {
   Task* t = nullptr;
   int rc = build_task(reinterpret_cast<Sim*>(sim), desc, buf, &t);

@@ -124,5 +124,6 @@ int launch_post_fused(Task* t, cudaStream_t s);
 int physics_configure(Sim* sim);  // chooses envs_per_block / shared memory, sets the kernel attributes
 int launch_simulate(Sim* sim, int apply_wrench, const float* push_force, cudaStream_t s);
 int launch_refresh_rigid_body_state(Sim* sim, cudaStream_t s);
+int measure_fp32_peak(int device, int iters, double* tflops_out);
 
 }  // namespace dyros

@@ -65,6 +65,46 @@ int launch_simulate(Sim* sim, int apply_wrench, const float* push, cudaStream_t 
   return 0;
 }
 
+// FFMA-saturation micro-benchmark: 8 independent accumulator chains per thread.
+__global__ void __launch_bounds__(512) k_ffma_peak(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+    x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+  }
+  float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 123.456f) out[0] = s;  // never true in practice; keeps the chains alive
+}
+
+int measure_fp32_peak(int device, int iters, double* tflops_out) {
+  DY_CUDA(cudaSetDevice(device));
+  int sms = 0;
+  DY_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  float* out = nullptr;
+  DY_CUDA(cudaMalloc(&out, sizeof(float)));
+  cudaEvent_t e0, e1;
+  DY_CUDA(cudaEventCreate(&e0));
+  DY_CUDA(cudaEventCreate(&e1));
+  const int blocks = sms * 4, threads = 512;
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    DY_CUDA(cudaEventRecord(e0));
+    k_ffma_peak<<<blocks, threads>>>(out, iters, 0.999f, 0.001f);
+    DY_CUDA(cudaEventRecord(e1));
+    DY_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    DY_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    double tf = (double)blocks * threads * 8.0 * iters * 2.0 / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops_out = best;
+  return 0;
+}
+
 // gym.refresh_rigid_body_state_tensor: forward kinematics of every body (tensors.rst.txt:193-207), one thread per env.
 __global__ void __launch_bounds__(64) k_rigid_body_state(DevModel m, SimParams p, DyrosSimBuffers b) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,0 +1,276 @@
+"""DyrosDynamicWalk with the reference's VecTask API, running on the sm_100a kernels.
+
+Mirrors python/IsaacGymEnvs/isaacgymenvs/tasks/dyros_dynamic_walk.py (T) and tasks/base/vec_task.py (VT):
+same constructor signature, `step` / `reset` / `reset_idx` / `reset_done` / `zero_actions`, the properties rl_games
+reads (VT:129-152, utils/rlgames_utils.py:157-186) and the same `extras` keys ("time_outs", "stacked_rewards",
+"reward_names"; T:415-428, VT:336). One `step` is one CUDA-graph replay of dyros_task_step; nothing in it
+synchronises the host.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional
+
+import numpy as np
+import torch
+
+from ..core import CoreConfig, DyrosCore
+from .spaces import Box
+
+REWARD_NAMES = ["mimic_body_orientation_reward", "qpos_regulation", "qvel_regulation", "contact_force_penalty",
+                "torque_regulation", "torque_diff_regulation", "body_vel_reward", "qacc_regulation",
+                "foot_contact_reward", "contact_force_diff_regulation", "double_support_force_diff_regulation",
+                "force_thres_penalty", "force_diff_thres_penalty", "force_ref_reward", "perturbation"]  # T:922-925, T:423
+
+
+def default_cfg(num_envs: int = 4096, randomize: bool = True, perturbation: bool = True) -> Dict[str, Any]:
+    """The values of cfg/task/DyrosDynamicWalk.yaml (+ cfg/config.yaml defaults) as the plain dict VecTask receives."""
+    return {
+        "name": "DyrosDynamicWalk", "physics_engine": "physx",
+        "env": {"numEnvs": num_envs, "envSpacing": 5, "episodeLength": 32, "enableDebugVis": False,
+                "controlFrequencyInv": 2, "clipActions": 1.0, "NumSingleStepObs": 37, "NumAction": 13,
+                "perturbation": perturbation, "NumHis": 10, "NumSkip": 2, "initialHieght": 0.93, "deathCost": 0.0,
+                "terminationHeight": 0.6, "asset": {"assetFileName": "mjcf/dyros_tocabi/xml/dyros_tocabi.xml"}},
+        "sim": {"dt": 0.002, "substeps": 1, "up_axis": "z", "use_gpu_pipeline": True, "gravity": [0.0, 0.0, -9.81],
+                "physx": {"num_threads": 4, "solver_type": 1, "use_gpu": True, "num_position_iterations": 4,
+                          "num_velocity_iterations": 1, "contact_offset": 0.002, "rest_offset": 0.0,
+                          "bounce_threshold_velocity": 0.04, "max_depenetration_velocity": 10.0,
+                          "contact_collection": 1}},
+        "task": {"randomize": randomize, "randomization_params": {
+            "frequency": 1, "actor_params": {"humanoid": {
+                "rigid_body_properties": {"mass": {"range": [0.8, 1.2], "operation": "scaling",
+                                                   "distribution": "uniform", "setup_only": True}},
+                "dof_properties": {"damping": {"range": [0.0, 2.9], "operation": "additive", "distribution": "uniform"},
+                                   "armature": {"range": [0.8, 1.2], "operation": "scaling", "distribution": "uniform"}}}}}},
+    }
+
+
+def core_config_from_cfg(cfg: Dict[str, Any]) -> CoreConfig:
+    env, sim, task = cfg["env"], cfg["sim"], cfg.get("task", {})
+    px = sim.get("physx", {})
+    c = CoreConfig(dt=sim["dt"], substeps=sim.get("substeps", 1), control_freq_inv=env.get("controlFrequencyInv", 1),
+                   episode_length_s=env["episodeLength"], gravity=tuple(sim.get("gravity", (0, 0, -9.81))),
+                   contact_offset=px.get("contact_offset", 0.002),
+                   max_depenetration_velocity=px.get("max_depenetration_velocity", 10.0),
+                   num_position_iterations=px.get("num_position_iterations", 4),
+                   num_velocity_iterations=px.get("num_velocity_iterations", 1),
+                   death_cost=env.get("deathCost", 0.0), initial_height=env.get("initialHieght", 0.93),
+                   env_spacing=env.get("envSpacing", 5), perturb=env.get("perturbation", False),
+                   randomize=task.get("randomize", False))
+    ap = task.get("randomization_params", {}).get("actor_params", {}).get("humanoid", {})
+    dp = ap.get("dof_properties", {})
+    if "damping" in dp:
+        c.dr_damping_range = tuple(dp["damping"]["range"])
+    if "armature" in dp:
+        c.dr_armature_range = tuple(dp["armature"]["range"])
+    rb = ap.get("rigid_body_properties", {})
+    if "mass" in rb:
+        c.dr_mass_range = tuple(rb["mass"]["range"])
+    return c
+
+
+class DyrosDynamicWalk:
+    def __init__(self, cfg: Dict[str, Any], sim_device: str = "cuda:0", graphics_device_id: int = -1,
+                 headless: bool = True, seed: int = 42, rank: int = 0, use_cuda_graph: bool = True):
+        self.cfg = cfg
+        env = cfg["env"]
+        # T:36-44
+        self.num_single_step_obs, self.num_action = env["NumSingleStepObs"], env["NumAction"]
+        self.num_obs_his, self.num_obs_skip = env["NumHis"], env["NumSkip"]
+        env["numObservations"] = (self.num_single_step_obs + self.num_action) * (self.num_obs_his - 1) + self.num_single_step_obs
+        env["numActions"] = self.num_action
+        if (self.num_single_step_obs, self.num_action, self.num_obs_his, self.num_obs_skip) != (37, 13, 10, 2):
+            raise ValueError("the fused observation kernel is specialised to 37/13/10/2 (DyrosDynamicWalk.yaml:15-20)")
+        # VT:50-97 (Env.__init__)
+        dev = sim_device.split(":")
+        if dev[0].lower() not in ("cuda", "gpu"):
+            raise ValueError("sim_device must be a CUDA device: this implementation has no CPU pipeline")
+        self.device_type, self.device_id = "cuda", int(dev[1]) if len(dev) > 1 else 0
+        self.device = f"cuda:{self.device_id}"
+        self.rl_device = cfg.get("rl_device", self.device)
+        self.headless, self.graphics_device_id = headless, graphics_device_id
+        self.num_environments = env["numEnvs"]
+        self.num_agents = env.get("numAgents", 1)
+        self.num_observations, self.num_states, self.num_actions = env["numObservations"], env.get("numStates", 0), env["numActions"]
+        self.control_freq_inv = env.get("controlFrequencyInv", 1)
+        self.obs_space = Box(np.ones(self.num_obs) * -np.inf, np.ones(self.num_obs) * np.inf)
+        self.state_space = Box(np.ones(self.num_states) * -np.inf, np.ones(self.num_states) * np.inf)
+        self.act_space = Box(np.ones(self.num_actions) * -1., np.ones(self.num_actions) * 1.)
+        self.clip_obs = env.get("clipObservations", np.inf)
+        self.clip_actions = env.get("clipActions", np.inf)
+        if self.clip_actions != 1.0:
+            raise ValueError("clipActions is fixed to 1.0 in the prologue kernel (DyrosDynamicWalk.yaml:13)")
+        self.randomize = cfg.get("task", {}).get("randomize", False)
+        self.randomization_params = cfg.get("task", {}).get("randomization_params", {})
+        self.max_episode_length_s = env["episodeLength"]
+        self.death_cost, self.initial_height = env["deathCost"], env["initialHieght"]
+        self.perturb = env["perturbation"]
+        self.core_cfg = core_config_from_cfg(cfg)
+        self.dt, self.skipframe = self.core_cfg.dt, self.control_freq_inv
+        self.dt_policy = self.dt * self.skipframe
+        self.max_episode_length = self.max_episode_length_s / (self.dt * self.skipframe)  # T:35
+        self.core = DyrosCore(self.num_environments, self.device, self.core_cfg, seed=seed, rank=rank)
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(seed + rank)
+        self._bind_buffers()
+        self._initial_randoms()
+        self.extras: Dict[str, Any] = {}
+        self.obs_dict: Dict[str, torch.Tensor] = {}
+        self._actions_static = torch.zeros(self.num_envs, self.num_actions, device=self.device)
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._use_graph = use_cuda_graph
+        self.first_randomization = True
+
+    # ------------------------------------------------------------------ VT:129-152
+    @property
+    def observation_space(self):
+        return self.obs_space
+
+    @property
+    def action_space(self):
+        return self.act_space
+
+    @property
+    def num_envs(self) -> int:
+        return self.num_environments
+
+    @property
+    def num_acts(self) -> int:
+        return self.num_actions
+
+    @property
+    def num_obs(self) -> int:
+        return self.num_observations
+
+    # ------------------------------------------------------------------ buffers (VT:233-256, T:87-195)
+    def _bind_buffers(self):
+        t, s, N = self.core.task_t, self.core.sim_t, self.num_envs
+        self.obs_buf, self.rew_buf, self.reset_buf = t["obs_buf"], t["rew_buf"], t["reset_buf"]
+        self.timeout_buf, self.progress_buf, self.randomize_buf = t["timeout_buf"], t["progress_buf"], t["randomize_buf"]
+        self.states_buf = torch.zeros(N, self.num_states, device=self.device)
+        self.root_states = s["root_states"]
+        self.dof_state = s["dof_state"]
+        self.dof_pos = s["dof_state"].view(N, 33, 2)[..., 0]
+        self.dof_vel = s["dof_state"].view(N, 33, 2)[..., 1]
+        self.contact_forces = s["net_contact_force"].view(N, 38, 3)
+        self.stacked_rewards = t["stacked_rewards"]
+        for k in ("actions", "actions_pre", "time", "target_vel", "motor_constant_scale", "qpos_noise", "qvel_noise",
+                  "qpos_bias", "quat_bias", "epi_len", "epi_len_log", "contact_reward_mean", "total_mass"):
+            setattr(self, k, t[k])
+
+    def _initial_randoms(self):
+        """Per-env draws the reference makes in __init__ (T:129-153, T:175) and the creation pose of episode 0:
+        env origin + U(-1,1) m in x, y (T:350-353)."""
+        t, s, N, g, dev = self.core.task_t, self.core.sim_t, self.num_envs, self.gen, self.device
+        r = lambda *shape: torch.rand(*shape, device=dev, generator=g)
+        t["target_vel"][:, 0] = r(N) * 0.8
+        t["motor_constant_scale"].copy_(r(N, 12) * 0.4 + 0.8)
+        t["qpos_bias"].copy_(r(N, 12) * 6.28 / 100 - 3.14 / 100)
+        t["quat_bias"].copy_(r(N, 3) * 6.28 / 150 - 3.14 / 150)
+        t["pert_duration"].copy_(torch.randint(1, 100, (N,), device=dev, generator=g, dtype=torch.int32))
+        s["root_states"][:, 0:2] = t["env_origins"][:, 0:2] + (r(N, 2) * 2 - 1)
+        if self.randomize:  # first_randomization: every env (VT:536-538); mass is setup_only (CFG:81-88)
+            c = self.core_cfg
+            lo, hi = c.dr_mass_range
+            s["body_mass_scale"].copy_(lo + r(N, 38) * (hi - lo))
+            lo, hi = c.dr_damping_range
+            s["dof_damping"].copy_(c.dof_damping + lo + r(N, 33) * (hi - lo))
+            lo, hi = c.dr_armature_range
+            s["dof_armature"].mul_(lo + r(N, 33) * (hi - lo))
+            masses = torch.tensor(self.core.tables.body_inertia[:, 0], dtype=torch.float32, device=dev)
+            t["total_mass"].copy_((s["body_mass_scale"] * masses).sum(1))  # T:221-225
+
+    # ------------------------------------------------------------------ step / reset (VT:293-374)
+    def step(self, actions: torch.Tensor):
+        """VT:293-344: returns (obs_dict, rew_buf, reset_buf, extras); tensors are the env's own buffers."""
+        self._actions_static.copy_(actions.to(self.device), non_blocking=True)
+        if self._use_graph:
+            if self._graph is None:
+                self._capture()
+            self._graph.replay()
+        else:
+            self.core.step(self._actions_static)
+        self.extras["time_outs"] = self.timeout_buf.to(self.rl_device)
+        self.extras["stacked_rewards"] = self.stacked_rewards
+        self.extras["reward_names"] = REWARD_NAMES
+        self.obs_dict["obs"] = self.obs_buf.to(self.rl_device)  # clipObservations = inf (VT:97-98): clamp is the identity
+        return self.obs_dict, self.rew_buf.to(self.rl_device), self.reset_buf.to(self.rl_device), self.extras
+
+    def _capture(self):
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            self.core.step(self._actions_static)
+        self._graph = g
+
+    def zero_actions(self) -> torch.Tensor:
+        return torch.zeros(self.num_envs, self.num_actions, dtype=torch.float32, device=self.rl_device)
+
+    def reset(self) -> Dict[str, torch.Tensor]:
+        """VT:362-374: returns the observation buffer as is (zeros before the first step); resets nothing."""
+        self.obs_dict["obs"] = self.obs_buf.to(self.rl_device)
+        return self.obs_dict
+
+    def reset_done(self):
+        """VT:376-391."""
+        done = self.reset_buf.nonzero(as_tuple=False).squeeze(-1)
+        if len(done) > 0:
+            self.reset_idx(done)
+        self.obs_dict["obs"] = self.obs_buf.to(self.rl_device)
+        return self.obs_dict, done
+
+    def reset_idx(self, env_ids: torch.Tensor):
+        """T:598-669 for an explicit id list (the per-step path resets inside the fused kernel)."""
+        self.core.reset_idx(env_ids.to(device=self.device, dtype=torch.int64).contiguous())
+
+    def get_state(self):
+        return self.states_buf.to(self.rl_device)
+
+    # staged methods with the reference's names (T:449, T:543, T:581, T:387, T:430)
+    def pre_physics_step(self, actions: torch.Tensor):
+        c = self.core
+        c.prologue(actions.contiguous())
+        for k in range(self.skipframe):
+            c.substep_torque()
+            native_push = k == 0
+            self._simulate_with_push(native_push)
+            c.sensor_noise(k)
+
+    def _simulate_with_push(self, first: bool):
+        import ctypes as C
+        from .. import native
+        c = self.core
+        if first and "rb_force" in c.sim_t:
+            c.sim_t["rb_force"].zero_()
+            c.sim_t["rb_torque"].zero_()
+            c.sim_t["rb_force"].view(self.num_envs, 38, 3)[:, 0, :] = c.task_t["push_force"]
+            c.simulate(apply_wrench=True)
+        elif first:
+            raise native.DyrosError("staged pre_physics_step needs CoreConfig.with_rb_force_tensors (apply_rigid_body_force_tensors path)")
+        else:
+            c.simulate()
+
+    def post_physics_step(self):
+        c = self.core
+        c.epilogue()
+        c.check_termination()
+        c.compute_reward()
+        c.compact_resets()
+        c.reset_idx(None)
+        c.compute_observations()
+        c.late_update()
+        c.end_step()
+
+    def check_termination(self):
+        self.core.check_termination()
+
+    def compute_reward(self):
+        self.core.compute_reward()
+
+    def compute_observations(self):
+        self.core.compute_observations()
+
+    def close(self):
+        self._graph = None
+        self.core.close()

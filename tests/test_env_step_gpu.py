@@ -1,0 +1,137 @@
+"""GPU tests of the whole env step through the public API (fused dyros_task_step / DyrosDynamicWalk.step):
+agreement with the CPU oracle (task restatement + fp64 physics) on injected draws, equivalence of the fused and
+staged call sequences, CUDA-graph replay, and size-independent properties at the full 4096-env size."""
+import numpy as np
+import pytest
+import torch
+
+from isaacgymdyros_b200.core import CoreConfig
+from oracle import task_oracle as O
+from oracle.env_oracle import EnvOracle
+from tests.golden_util import load_assets
+from tests.physics_util import oracle_params
+from tests.test_task_parity_gpu import inject_noise, load_state, make_core, read_state
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fused_step_matches_cpu_oracle_rollout():
+    """6 policy steps from the reset pose: physics + PD + noise + reward + reset + obs against the oracle.
+    Integer outputs exact; float tolerances account for fp32 vs fp64 physics over the rollout."""
+    N = 16
+    tables, mocap, obs_norm = load_assets()
+    cfg = CoreConfig()
+    rng = np.random.default_rng(11)
+    ref = EnvOracle(N, tables, mocap, obs_norm, phys_params=oracle_params(cfg), rng=rng)
+    ref.s["progress_buf"][:4] = 7997  # a few time-outs so that reset_idx runs inside the fused kernel
+    ref.s["epi_len"][:4] = 7997
+    core = make_core(N)
+    load_state(core, ref.s)
+    for t in range(6):
+        noise = O.draw_noise(N, 2, rng)
+        actions = rng.uniform(-1, 1, (N, 13)).astype(np.float32)
+        want_ids = ref.step(actions, noise)
+        inject_noise(core, noise)
+        core.step(torch.tensor(actions, device=core.device))
+        torch.cuda.synchronize()
+        got = read_state(core)
+        n = int(core.task_t["reset_count"].item())
+        assert np.array_equal(core.task_t["reset_env_ids"][:n].cpu().numpy(), want_ids), f"step {t}"
+        for k in ("reset_buf", "timeout_buf", "progress_buf", "mocap_data_idx", "delay_idx", "simul_len"):
+            assert np.array_equal(got[k].reshape(-1), np.asarray(ref.s[k]).reshape(-1)), f"step {t} {k}"
+        for k, tol in (("dof_pos", 2e-5), ("dof_vel", 2e-3), ("root_states", 2e-4), ("rew_buf", 2e-4), ("obs_buf", 5e-3)):
+            err = np.abs(got[k].reshape(ref.s[k].shape) - ref.s[k]).max()
+            assert err < tol, f"step {t}: {k} differs by {err}"
+    core.close()
+
+
+def test_fused_step_equals_staged_sequence_bitwise():
+    """dyros_task_step must give the same bits as the staged calls it fuses (same kernels, same order)."""
+    N = 257
+    rng = np.random.default_rng(3)
+    a, b = make_core(N), make_core(N)
+    tables, mocap, obs_norm = load_assets()
+    s, _c = O.new_state(N, mocap, obs_norm, np.full(N, np.float32(tables.total_mass())), tables.dof_lower,
+                        tables.dof_upper, O.Params(), rng=rng)
+    s["progress_buf"][::5] = 7998
+    load_state(a, s)
+    load_state(b, s)
+    for t in range(4):
+        noise = O.draw_noise(N, 2, rng)
+        actions = torch.tensor(rng.uniform(-1, 1, (N, 13)).astype(np.float32), device=a.device)
+        inject_noise(a, noise)
+        inject_noise(b, noise)
+        a.step(actions)
+        b.prologue(actions)
+        for k in range(2):
+            b.substep_torque()
+            if k == 0:
+                b.sim_t["rb_force"].zero_()
+                b.sim_t["rb_force"].view(N, 38, 3)[:, 0, :] = b.task_t["push_force"]
+                b.simulate(apply_wrench=True)
+            else:
+                b.simulate()
+            b.sensor_noise(k)
+        b.epilogue(); b.check_termination(); b.compute_reward(); b.compact_resets(); b.reset_idx(None)
+        b.compute_observations(); b.late_update(); b.end_step()
+        torch.cuda.synchronize()
+        ga, gb = read_state(a), read_state(b)
+        for k in ga:
+            assert np.array_equal(ga[k], gb[k], equal_nan=True), f"step {t}: {k} differs between fused and staged"
+    a.close(); b.close()
+
+
+def make_core(N, **kw):  # noqa: F811  (rb force tensors needed by the staged push path)
+    from isaacgymdyros_b200.core import DyrosCore
+    return DyrosCore(N, "cuda:0", CoreConfig(with_rb_force_tensors=True, **kw))
+
+
+def test_vectask_api_rollout_properties_full_size():
+    """DyrosDynamicWalk.step at N=4096 with production RNG and CUDA-graph replay: shapes/dtypes of the VecTask API,
+    finite outputs, reset bookkeeping (progress_buf == 0 exactly where reset_buf == 1, compacted ids == nonzero),
+    reward bounds, and that random actions make robots fall and get reset."""
+    from isaacgymdyros_b200 import DyrosDynamicWalk, default_cfg
+    N = 4096
+    env = DyrosDynamicWalk(default_cfg(N), "cuda:0")
+    assert env.num_obs == 487 and env.num_acts == 13 and env.num_envs == N
+    obs0 = env.reset()["obs"]
+    assert obs0.shape == (N, 487) and not obs0.any()
+    g = torch.Generator(device="cuda:0"); g.manual_seed(42)
+    total_resets = 0
+    for t in range(300):
+        obs, rew, rst, extras = env.step(torch.rand(N, 13, device="cuda:0", generator=g) * 2 - 1)
+        if t % 50 == 49 or t == 0:
+            torch.cuda.synchronize()
+            assert obs["obs"].shape == (N, 487) and obs["obs"].dtype == torch.float32
+            assert rew.shape == (N,) and rst.dtype == torch.int64 and extras["time_outs"].dtype == torch.int64
+            assert extras["stacked_rewards"].shape == (N, 15) and len(extras["reward_names"]) == 15
+            assert torch.isfinite(obs["obs"]).all() and torch.isfinite(rew).all()
+            assert torch.isfinite(env.root_states).all() and torch.isfinite(env.dof_state).all()
+            assert ((env.progress_buf == 0) == (rst == 1)).all()
+            n = int(env.core.task_t["reset_count"].item())
+            assert torch.equal(env.core.task_t["reset_env_ids"][:n], rst.nonzero().flatten())
+            assert rew.max().item() <= 2.5 and rew.min().item() >= -0.3
+            assert (env.dof_vel.abs() <= 4.03 + 1e-4).all()
+        total_resets += int(rst.sum().item()) if t % 10 == 9 else 0
+    assert total_resets > 0, "random actions should make some robots fall within 1.2 s"
+    env.close()
+
+
+def test_domain_randomisation_redraw_on_reset_ranges():
+    from isaacgymdyros_b200 import DyrosDynamicWalk, default_cfg
+    from isaacgymdyros_b200.core import ARMATURE
+    N = 512
+    env = DyrosDynamicWalk(default_cfg(N, randomize=True), "cuda:0", use_cuda_graph=False)
+    d0 = env.core.sim_t["dof_damping"].clone()
+    ids = torch.arange(0, N, 2, device="cuda:0")
+    env.reset_idx(ids)
+    torch.cuda.synchronize()
+    d1, a1 = env.core.sim_t["dof_damping"], env.core.sim_t["dof_armature"]
+    assert (d1[1::2] == d0[1::2]).all() and (d1[0::2] != d0[0::2]).float().mean() > 0.99
+    assert d1.min() >= 0.1 - 1e-6 and d1.max() <= 3.0 + 1e-5
+    ratio = a1 / torch.tensor(ARMATURE, device="cuda:0")
+    assert ratio.min() >= 0.8 - 1e-5 and ratio.max() <= 1.2 + 1e-5
+    ms = env.core.sim_t["body_mass_scale"]
+    assert ms.min() >= 0.8 and ms.max() <= 1.2 and ms.std() > 0.05
+    assert torch.allclose(env.total_mass, (ms * torch.tensor(env.core.tables.body_inertia[:, 0], dtype=torch.float32, device="cuda:0")).sum(1), rtol=1e-5)
+    env.close()
