@@ -33,7 +33,7 @@ UNIT = "env-steps/s"
 WORKLOAD = "DyrosDynamicWalk 4096 envs/GPU, random actions, physics + PD + obs/reward/reset kernels (BASELINE configs[1])"
 K1_BYTES_PER_ENV_SUBSTEP = 1648      # K1 reads root13+dof66+torque33+ext3+DR104, writes root13+dof66+contact114 (fp32 words)
 ENV_STEP_BYTES = 7044                # SURVEY 8d canonical bytes per env-step
-K1_FLOP_PER_ENV_SUBSTEP = 52500      # DESIGN.md section 6 (FMA = 2 FLOP), this algorithm
+K1_FLOP_PER_ENV_SUBSTEP = 67000      # DESIGN.md section 6 (FMA = 2 FLOP), this algorithm
 
 
 def parse():
