@@ -31,9 +31,9 @@ sys.path.insert(0, ROOT)
 METRIC = "env-steps/s at 4096 envs/GPU"
 UNIT = "env-steps/s"
 WORKLOAD = "DyrosDynamicWalk 4096 envs/GPU, random actions, physics + PD + obs/reward/reset kernels (BASELINE configs[1])"
-K1_BYTES_PER_ENV_SUBSTEP = 1648      # K1 reads root13+dof66+torque33+ext3+DR104, writes root13+dof66+contact114 (fp32 words)
+K1_BYTES_PER_ENV_STEP = 2 * 1648 + 2 * 1296   # per policy step: 2 x K1 sub-step (412 words) + 2 x (torque/delay ring + sensor noise: 324 words), DESIGN.md section 6
 ENV_STEP_BYTES = 7044                # SURVEY 8d canonical bytes per env-step
-K1_FLOP_PER_ENV_SUBSTEP = 67000      # DESIGN.md section 6 (FMA = 2 FLOP), this algorithm
+K1_FLOP_PER_ENV_STEP = 2 * 62000         # executed FP32 FLOP of 2 sub-steps (ncu r1: ffma*2+fadd+fmul = 62.0e3 per env-sub-step)
 
 
 def parse():
@@ -240,21 +240,19 @@ def run_ours(a):
         e2e_ms = e0.elapsed_time(e1)
     clocks = clk.summary()
     h2d, d2h = N * 13 * 4, N * 487 * 4 + N * 4 + N * 8
-    # ---- (4) the dominant kernel alone (k_simulate), inside real staged steps, L2 flushed before each launch
+    # ---- (4) the dominant kernel alone (k_step_physics = 2 x (torque, physics sub-step, noise) in one launch), inside
+    #          real staged steps, L2 flushed before each launch
     KS = min(K, 50)
     kev = []
     core = env.core
     for i in range(KS):
         core.prologue(pool[i % len(pool)])
-        for k in range(2):
-            core.substep_torque()
-            flush.fill_(k)
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            core.simulate()
-            a1.record()
-            kev.append((a0, a1))
-            core.sensor_noise(k)
+        flush.fill_(i & 0xFF)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        core.task_physics()
+        a1.record()
+        kev.append((a0, a1))
         env.post_physics_step()
     torch.cuda.synchronize()
     k1_ms = statistics.mean(s.elapsed_time(e) for s, e in kev)
@@ -283,7 +281,7 @@ def run_ours(a):
         fp32_peak = measure_fp32_peak(local)
         total_envs = N * world
         value = total_envs * K / (cold_ms * 1e-3)
-        k1_bytes = K1_BYTES_PER_ENV_SUBSTEP * N
+        k1_bytes = K1_BYTES_PER_ENV_STEP * N
         achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -299,13 +297,13 @@ def run_ours(a):
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
             "gpu_launches": K * core.step_launches(),
             "value_warm_l2": total_envs * K / (warm_ms * 1e-3), "ms_per_step_warm_l2": warm_ms / K,
-            "roofline": {"bound": "hbm", "kernel": "k_simulate (one physics sub-step of all envs)",
+            "roofline": {"bound": "hbm", "kernel": "k_step_physics (2 x (PD/delay torque, physics sub-step, sensor noise) of all envs, one launch)",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "traffic": None,
                          "launch_ms": k1_ms, "algorithmic_bytes_per_launch": k1_bytes,
                          "note": "K1 is FP32-latency bound, not HBM bound (SURVEY 8d): see fp32"},
-            "fp32": {"achieved": K1_FLOP_PER_ENV_SUBSTEP * N / (k1_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-                     "frac": K1_FLOP_PER_ENV_SUBSTEP * N / (k1_ms * 1e-3) / 1e12 / fp32_peak,
+            "fp32": {"achieved": K1_FLOP_PER_ENV_STEP * N / (k1_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": K1_FLOP_PER_ENV_STEP * N / (k1_ms * 1e-3) / 1e12 / fp32_peak,
                      "peak_source": "dyros_measure_fp32_peak (FFMA saturation, this run)"},
             "whole_step_hbm": {"achieved": ENV_STEP_BYTES * N / (cold_ms / K * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"},
             "episode_stats": {"epi_len_log_mean": float(stats[0]), "contact_reward_mean": float(stats[1])},

@@ -216,6 +216,8 @@ int dyros_task_create(DyrosSim* sim, const DyrosTaskDesc* desc, const DyrosTaskB
 int dyros_task_destroy(DyrosTask* task);
 int dyros_task_set_noise_injection(DyrosTask* task, const DyrosNoiseInjection* inj);
 int dyros_task_prologue(DyrosTask* task, const float* actions, void* stream);      /* VT:307 + T:449-502 */
+/* T:504-530 in one launch: skipframe x (substep torque, gym.simulate, sensor noise); what dyros_task_step uses. */
+int dyros_task_physics(DyrosTask* task, void* stream);
 int dyros_task_substep_torque(DyrosTask* task, void* stream);                      /* T:505-520 -> dof_actuation_force */
 int dyros_task_sensor_noise(DyrosTask* task, int substep, void* stream);           /* T:528-530 */
 int dyros_task_epilogue(DyrosTask* task, void* stream);                            /* T:532-541 + VT:325 + T:544-545 */

@@ -310,6 +310,9 @@ class DyrosCore:
     def prologue(self, actions):
         native.check(self.lib.dyros_task_prologue(self.task_handle, self._actions_ptr(actions), self._stream), "prologue")
 
+    def task_physics(self):
+        native.check(self.lib.dyros_task_physics(self.task_handle, self._stream), "task_physics")
+
     def substep_torque(self):
         native.check(self.lib.dyros_task_substep_torque(self.task_handle, self._stream), "substep_torque")
 

@@ -280,6 +280,10 @@ int dyros_task_prologue(DyrosTask* task, const float* actions, void* stream) {
   }
   return launch_prologue(t, actions, (cudaStream_t)stream);
 }
+int dyros_task_physics(DyrosTask* task, void* stream) {
+  TASK_OR_FAIL("dyros_task_physics");
+  return launch_task_physics(t, (cudaStream_t)stream);
+}
 int dyros_task_substep_torque(DyrosTask* task, void* stream) {
   TASK_OR_FAIL("dyros_task_substep_torque");
   return launch_substep_torque(t, (cudaStream_t)stream);
@@ -337,18 +341,13 @@ int dyros_task_step(DyrosTask* task, const float* actions, void* stream) {
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (launch_prologue(t, actions, st)) return 1;
-  for (int k = 0; k < t->p.skipframe; ++k) {
-    if (launch_substep_torque(t, st)) return 1;
-    // the pelvis push acts on the first sub-step only: applied once before the loop, T:502 vs T:504
-    if (launch_simulate(t->sim, 0, k == 0 ? t->b.push_force : nullptr, st)) return 1;
-    if (launch_sensor_noise(t, k, st)) return 1;
-  }
+  if (launch_task_physics(t, st)) return 1;
   if (launch_post_fused(t, st)) return 1;
   return launch_crossenv(t, true, true, true, st);
 }
 int dyros_task_step_launches(DyrosTask* task) {
   TASK_OR_FAIL("dyros_task_step_launches");
-  return 1 + 3 * t->p.skipframe + 2;
+  return 4;  // prologue, fused physics, fused post-physics, cross-env
 }
 
 }  // extern "C"

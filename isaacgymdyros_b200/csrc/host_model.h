@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -35,7 +36,7 @@ static const T* at(void* base, size_t off) {
 }
 
 struct ModelOffsets {
-  size_t parent, dof, E, r, ax, cs, ch, bs, bd, bl, bp, br, bi, lo, up, vl, ef, ps, pb, pp, pr, ys, yb, yc, ya, yz, sc;
+  size_t parent, dof, E, r, ax, cs, ch, bs, bd, bl, bp, br, bi, lo, up, vl, ef, ps, pb, pp, pr, ys, yb, yc, ya, yz, sc, rc;
 };
 
 // Fills `dm` (counts, foot tables) and appends every table to `bl`. Returns "" or an error message.
@@ -154,20 +155,45 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
                     dm.foot_link[1], dm.chain[0][a]);
   }
 
+  // per-link bounding radius of the penalty candidates about the link origin (early-out of the contact loops)
+  std::vector<float> reach(nl, 0.f);
+  for (int l = 0; l < nl; ++l) {
+    for (int k = pt_start[l]; k < pt_start[l + 1]; ++k) {
+      float x = ppt_pos[3 * k], y = ppt_pos[3 * k + 1], z = ppt_pos[3 * k + 2];
+      reach[l] = std::max(reach[l], std::sqrt(x * x + y * y + z * z) + ppt_rad[k]);
+    }
+    for (int k = cyl_start[l]; k < cyl_start[l + 1]; ++k) {
+      float x = ccyl_center[3 * k], y = ccyl_center[3 * k + 1], z = ccyl_center[3 * k + 2];
+      reach[l] = std::max(reach[l], std::sqrt(x * x + y * y + z * z) + ccyl_size[2 * k] + ccyl_size[2 * k + 1]);
+    }
+  }
+  // hot tables first: the physics kernel stages the prefix [0, hot_bytes) into shared memory
   o.parent = bl.add_i(m->link_parent, nl); o.dof = bl.add_i(m->link_dof, nl);
   o.E = bl.add_f(m->link_E, nl * 9); o.r = bl.add_f(m->link_r, nl * 3); o.ax = bl.add_f(m->link_axis, nl * 3);
   o.cs = bl.add_i(child_start.data(), nl + 1); o.ch = bl.add_i(children.data(), children.size());
   o.bs = bl.add_i(body_start.data(), nl + 1); o.bd = bl.add_i(bodies.data(), nb);
-  o.bl = bl.add_i(m->body_link, nb); o.bp = bl.add_f(m->body_pos, nb * 3); o.br = bl.add_f(m->body_rot, nb * 9);
   o.bi = bl.add_f(m->body_inertia, nb * 10);
   o.lo = bl.add_f(m->dof_lower, nd); o.up = bl.add_f(m->dof_upper, nd); o.vl = bl.add_f(m->dof_vel_limit, nd);
   o.ef = bl.add_f(m->dof_effort, nd);
-  o.ps = bl.add_i(pt_start.data(), nl + 1); o.pb = bl.add_i(ppt_body.data(), ppt_body.size());
+  o.ps = bl.add_i(pt_start.data(), nl + 1); o.ys = bl.add_i(cyl_start.data(), nl + 1);
+  o.sc = bl.add_i(m->sched, (size_t)m->sched_slots * DYROS_LANES);
+  o.rc = bl.add_f32(reach.data(), nl);
+  dm.hot_bytes = (int)((bl.host.size() + 15) & ~size_t(15));
+  // cold tables (global memory, read only when a link is near the ground or for rigid_body_state)
+  o.bl = bl.add_i(m->body_link, nb); o.bp = bl.add_f(m->body_pos, nb * 3); o.br = bl.add_f(m->body_rot, nb * 9);
+  o.pb = bl.add_i(ppt_body.data(), ppt_body.size());
   o.pp = bl.add_f32(ppt_pos.data(), ppt_pos.size()); o.pr = bl.add_f32(ppt_rad.data(), ppt_rad.size());
-  o.ys = bl.add_i(cyl_start.data(), nl + 1); o.yb = bl.add_i(ccyl_body.data(), ccyl_body.size());
+  o.yb = bl.add_i(ccyl_body.data(), ccyl_body.size());
   o.yc = bl.add_f32(ccyl_center.data(), ccyl_center.size()); o.ya = bl.add_f32(ccyl_axis.data(), ccyl_axis.size());
   o.yz = bl.add_f32(ccyl_size.data(), ccyl_size.size());
-  o.sc = bl.add_i(m->sched, (size_t)m->sched_slots * DYROS_LANES);
+  bl.host.resize((bl.host.size() + 15) & ~size_t(15));
+  // word offsets of the hot tables inside the staged prefix
+  dm.o_parent = (int)(o.parent / 4); dm.o_dof = (int)(o.dof / 4); dm.o_E = (int)(o.E / 4); dm.o_r = (int)(o.r / 4);
+  dm.o_axis = (int)(o.ax / 4); dm.o_child_start = (int)(o.cs / 4); dm.o_children = (int)(o.ch / 4);
+  dm.o_body_start = (int)(o.bs / 4); dm.o_bodies = (int)(o.bd / 4); dm.o_body_inertia = (int)(o.bi / 4);
+  dm.o_lower = (int)(o.lo / 4); dm.o_upper = (int)(o.up / 4); dm.o_vel_limit = (int)(o.vl / 4);
+  dm.o_effort = (int)(o.ef / 4); dm.o_pt_start = (int)(o.ps / 4); dm.o_cyl_start = (int)(o.ys / 4);
+  dm.o_sched = (int)(o.sc / 4); dm.o_reach = (int)(o.rc / 4);
 
   return std::string();
 #undef MFAIL
@@ -187,6 +213,8 @@ static void resolve_model(DevModel& dm, const ModelOffsets& o, void* base) {
   dm.link_cyl_start = at<int>(base, o.ys); dm.cyl_body = at<int>(base, o.yb); dm.cyl_center = at<float>(base, o.yc);
   dm.cyl_axis = at<float>(base, o.ya); dm.cyl_size = at<float>(base, o.yz);
   dm.sched = at<int>(base, o.sc);
+  dm.link_reach = at<float>(base, o.rc);
+  dm.blob = base;
 }
 
 static void fill_sim_params(const DyrosSimDesc* d, SimParams& p) {

@@ -33,6 +33,11 @@ constexpr int X_SIZE = X_ROWS + MAX_FEET * MAX_ACTIVE_PTS * 3 * 7;
 
 HD int env_scratch_floats(int nl) { return nl * LS + X_SIZE; }
 
+// The hot model tables are read from the staged copy `hot` (shared memory on the GPU) through word offsets.
+#define HI(field, idx) (reinterpret_cast<const int*>(hot)[m.o_##field + (idx)])
+#define HF(field, idx) (hot[m.o_##field + (idx)])
+#define HF3(field, idx) ld3_f(hot + m.o_##field + 3 * (idx))
+
 // global-memory views of one env (all device pointers on the GPU, host pointers in the emulation)
 struct EnvIO {
   float* root;             // 13
@@ -68,19 +73,29 @@ HD void penalty_point(const SimParams& p, const M3& Rw, SV v, V3 xs, real depth,
   fext.v = fext.v + fl;
 }
 
-// Inertia parameters, bias force and external wrench of link i (pass 1). Writes A_INERTIA / A_PA.
-HD void link_forces(const EnvIO& io, real* L, const DevModel& m, const SimParams& p, int i, const M3& Rw, V3 pw, SV v) {
+// Link inertia parameters of link i from the per-body mass scales (P0). Writes A_INERTIA.
+HD void link_inertia(const EnvIO& io, real* L, const float* hot, const DevModel& m, int i) {
   real par[10];
 #pragma unroll
   for (int k = 0; k < 10; ++k) par[k] = 0;
+  for (int bi = HI(body_start, i); bi < HI(body_start, i + 1); ++bi) {
+    int b = HI(bodies, bi);
+    real sc = io.mass_scale[b];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) par[k] += sc * HF(body_inertia, b * 10 + k);
+  }
+#pragma unroll
+  for (int k = 0; k < 10; ++k) L[LS_A + A_INERTIA + k] = par[k];
+}
+
+// Bias force and external wrench of link i (pass 1). Reads A_INERTIA, writes A_PA.
+HD void link_forces(const EnvIO& io, real* L, const float* hot, const DevModel& m, const SimParams& p, int i, const M3& Rw,
+                    V3 pw, SV v) {
+  real* A = L + LS_A;
   SV fext = sv_zero();
   V3 nrm = v3(Rw.a[6], Rw.a[7], Rw.a[8]);  // world z in link coordinates
-  for (int bi = m.link_body_start[i]; bi < m.link_body_start[i + 1]; ++bi) {
-    int b = m.link_bodies[bi];
-    real sc = io.mass_scale[b];
-    const float* bp = m.body_inertia + b * 10;
-#pragma unroll
-    for (int k = 0; k < 10; ++k) par[k] += sc * bp[k];
+  for (int bi = HI(body_start, i); bi < HI(body_start, i + 1); ++bi) {
+    int b = HI(bodies, bi);
     if (io.live) {
       io.contact[3 * b] = 0.f;
       io.contact[3 * b + 1] = 0.f;
@@ -94,21 +109,24 @@ HD void link_forces(const EnvIO& io, real* L, const DevModel& m, const SimParams
         F = F + ld3_f(io.rb_force + 3 * b);
         T = ld3_f(io.rb_torque + 3 * b);
       }
-      real mb = sc * bp[0];
+      real sc = io.mass_scale[b];
+      real mb = sc * HF(body_inertia, b * 10);
       real inv = 1 / (mb > (real)1e-30 ? mb : (real)1e-30);
-      V3 com = v3(sc * bp[1] * inv, sc * bp[2] * inv, sc * bp[3] * inv);
+      V3 com = v3(sc * HF(body_inertia, b * 10 + 1) * inv, sc * HF(body_inertia, b * 10 + 2) * inv,
+                  sc * HF(body_inertia, b * 10 + 3) * inv);
       V3 fl = mulT(Rw, F);
       fext.w = fext.w + cross(com, fl) + mulT(Rw, T);
       fext.v = fext.v + fl;
     }
   }
-  for (int k = m.link_pt_start[i]; k < m.link_pt_start[i + 1]; ++k) {
+  const bool near_ground = pw.z < HF(reach, i);  // nothing of this link can reach z = 0 otherwise
+  for (int k = near_ground ? HI(pt_start, i) : 0; k < (near_ground ? HI(pt_start, i + 1) : 0); ++k) {
     V3 x = ld3_f(m.pt_pos + 3 * k);
     real rad = m.pt_radius[k];
     real z = pw.z + dot(nrm, x);
     penalty_point(p, Rw, v, x - rad * nrm, rad - z, io.contact + 3 * m.pt_body[k], io.live, fext);
   }
-  for (int k = m.link_cyl_start[i]; k < m.link_cyl_start[i + 1]; ++k) {
+  for (int k = near_ground ? HI(cyl_start, i) : 0; k < (near_ground ? HI(cyl_start, i + 1) : 0); ++k) {
     V3 c = ld3_f(m.cyl_center + 3 * k), a = ld3_f(m.cyl_axis + 3 * k);
     real rad = m.cyl_size[2 * k], hh = m.cyl_size[2 * k + 1];
     real az = dot(nrm, a);
@@ -120,29 +138,28 @@ HD void link_forces(const EnvIO& io, real* L, const DevModel& m, const SimParams
     real z = pw.z + dot(nrm, rim);
     penalty_point(p, Rw, v, rim, -z, io.contact + 3 * m.cyl_body[k], io.live, fext);
   }
-  ABI I = abi_rigid(par[0], v3(par[1], par[2], par[3]), S3{par[4], par[5], par[6], par[7], par[8], par[9]});
+  ABI I = abi_rigid(A[0], v3(A[1], A[2], A[3]), S3{A[4], A[5], A[6], A[7], A[8], A[9]});
   SV pA = crf(v, mul(I, v)) - fext;
-  real* A = L + LS_A;
-#pragma unroll
-  for (int k = 0; k < 10; ++k) A[A_INERTIA + k] = par[k];
   st6(A + A_PA, pA);
 }
 
 template <class Sync>
-HD void env_substep(const EnvIO& io, real* sm, const DevModel& m, const SimParams& p, int g, Sync& sync) {
+HD void env_substep(const EnvIO& io, real* sm, const float* hot, const DevModel& m, const SimParams& p, int g, Sync& sync) {
   const int nl = m.nl, T = m.T;
   real* X = sm + nl * LS;
   const real dt = p.dt;
 
   // ---- P0: joint inputs -> scratch (lane g takes links g+1, g+1+LANES, ...)
-  for (int i = 1 + g; i < nl; i += DYROS_LANES) {
-    int d = m.link_dof[i];
+  for (int i = g; i < nl; i += DYROS_LANES) {
     real* L = sm + i * LS;
+    link_inertia(io, L, hot, m, i);
+    if (i == 0) continue;
+    int d = HI(dof, i);
     L[LS_E] = io.dof_state[2 * d];
     L[LS_SC + 0] = io.dof_state[2 * d + 1];
     real tq = io.tau[d];
     if (p.clamp_effort) {
-      real lim = m.dof_effort[d];
+      real lim = HF(effort, d);
       tq = tq > lim ? lim : (tq < -lim ? -lim : tq);
     }
     L[LS_SC + 1] = tq;
@@ -159,18 +176,18 @@ HD void env_substep(const EnvIO& io, real* sm, const DevModel& m, const SimParam
     st6(L + LS_V, v0);
     st_m3(L + LS_A + A_POSE, R0);
     st3(L + LS_A + A_POSE + 9, pw);
-    link_forces(io, L, m, p, 0, R0, pw, v0);
+    link_forces(io, L, hot, m, p, 0, R0, pw, v0);
   }
   sync();
   // ---- P2: pass 1, root -> leaves: transforms, velocities, world poses, bias forces
   for (int t = 0; t < T; ++t) {
-    int i = m.sched[t * DYROS_LANES + g];
+    int i = HI(sched, t * DYROS_LANES + g);
     if (i > 0) {
       real* L = sm + i * LS;
-      const real* Lp = sm + m.link_parent[i] * LS;
+      const real* Lp = sm + HI(parent, i) * LS;
       real q = L[LS_E], qd = L[LS_SC];
-      V3 ax = ld3_f(m.link_axis + 3 * i), r = ld3_f(m.link_r + 3 * i);
-      M3 E = mul(axis_rot_T(ax, sin(q), cos(q)), ld_m3_f(m.link_E + 9 * i));
+      V3 ax = HF3(axis, i), r = HF3(r, i);
+      M3 E = mul(axis_rot_T(ax, sin(q), cos(q)), ld_m3_f(hot + m.o_E + 9 * i));
       SV v = xform_motion(E, r, ld6(Lp + LS_V));
       v.w = v.w + qd * ax;
       M3 Rwp = ld_m3(Lp + LS_A + A_POSE);
@@ -185,24 +202,24 @@ HD void env_substep(const EnvIO& io, real* sm, const DevModel& m, const SimParam
           st_m3(X + X_FOOTPOSE + 12 * f, Rw);
           st3(X + X_FOOTPOSE + 12 * f + 9, pw);
         }
-      link_forces(io, L, m, p, i, Rw, pw, v);
+      link_forces(io, L, hot, m, p, i, Rw, pw, v);
     }
     sync();
   }
   // ---- P3: pass 2, leaves -> root: articulated inertias and bias forces
   for (int t = T - 1; t >= 0; --t) {
-    int i = m.sched[t * DYROS_LANES + g];
+    int i = HI(sched, t * DYROS_LANES + g);
     if (i > 0) {
       real* L = sm + i * LS;
       real* A = L + LS_A;
       ABI IA = abi_rigid(A[0], v3(A[1], A[2], A[3]), S3{A[4], A[5], A[6], A[7], A[8], A[9]});
       SV pA = ld6(A + A_PA);
-      for (int ci = m.link_child_start[i]; ci < m.link_child_start[i + 1]; ++ci) {
-        const real* Ac = sm + m.link_children[ci] * LS + LS_A;
+      for (int ci = HI(child_start, i); ci < HI(child_start, i + 1); ++ci) {
+        const real* Ac = sm + HI(children, ci) * LS + LS_A;
         IA = IA + ld_abi(Ac + A_CIA);
         pA = pA + ld6(Ac + A_CPA);
       }
-      V3 ax = ld3_f(m.link_axis + 3 * i), r = ld3_f(m.link_r + 3 * i);
+      V3 ax = HF3(axis, i), r = HF3(r, i);
       M3 E = ld_m3(L + LS_E);
       SV v = ld6(L + LS_V);
       real qd = L[LS_SC], tq = L[LS_SC + 1], damp = L[LS_SC + 2], arm = L[LS_SC + 3];
@@ -229,8 +246,8 @@ HD void env_substep(const EnvIO& io, real* sm, const DevModel& m, const SimParam
     real* A = L + LS_A;
     ABI IA = abi_rigid(A[0], v3(A[1], A[2], A[3]), S3{A[4], A[5], A[6], A[7], A[8], A[9]});
     SV pA = ld6(A + A_PA);
-    for (int ci = m.link_child_start[0]; ci < m.link_child_start[1]; ++ci) {
-      const real* Ac = sm + m.link_children[ci] * LS + LS_A;
+    for (int ci = HI(child_start, 0); ci < HI(child_start, 1); ++ci) {
+      const real* Ac = sm + HI(children, ci) * LS + LS_A;
       IA = IA + ld_abi(Ac + A_CIA);
       pA = pA + ld6(Ac + A_CPA);
     }
@@ -251,11 +268,11 @@ HD void env_substep(const EnvIO& io, real* sm, const DevModel& m, const SimParam
   sync();
   // ---- P5: pass 3, root -> leaves: joint accelerations, predicted joint velocities
   for (int t = 0; t < T; ++t) {
-    int i = m.sched[t * DYROS_LANES + g];
+    int i = HI(sched, t * DYROS_LANES + g);
     if (i > 0) {
       real* L = sm + i * LS;
-      const real* Lp = sm + m.link_parent[i] * LS;
-      V3 ax = ld3_f(m.link_axis + 3 * i), r = ld3_f(m.link_r + 3 * i);
+      const real* Lp = sm + HI(parent, i) * LS;
+      V3 ax = HF3(axis, i), r = HF3(r, i);
       M3 E = ld_m3(L + LS_E);
       SV v = ld6(L + LS_V);
       real qd = L[LS_SC];
@@ -290,7 +307,7 @@ HD void env_substep(const EnvIO& io, real* sm, const DevModel& m, const SimParam
     for (int k = 0; k < m.chain_len[g]; ++k) {
       int j = m.chain[g][k];
       const real* L = sm + j * LS;
-      V3 ax = ld3_f(m.link_axis + 3 * j), r = ld3_f(m.link_r + 3 * j);
+      V3 ax = HF3(axis, j), r = HF3(r, j);
       M3 E = ld_m3(L + LS_E);
       real Dinv = L[LS_SC + 2];
       SV w = Dinv * xform_force_T(E, r, ld6(L + LS_U));
@@ -390,7 +407,7 @@ HD void env_substep(const EnvIO& io, real* sm, const DevModel& m, const SimParam
     for (int k = m.chain_len[g] - 1; k >= 0; --k) {
       int j = m.chain[g][k];
       real* L = sm + j * LS;
-      V3 ax = ld3_f(m.link_axis + 3 * j), r = ld3_f(m.link_r + 3 * j);
+      V3 ax = HF3(axis, j), r = HF3(r, j);
       real sd = dot(ax, pd.w);
       L[LS_SC + 3] = sd;
       pd = xform_force_T(ld_m3(L + LS_E), r, pd - (L[LS_SC + 2] * sd) * ld6(L + LS_U));
@@ -416,22 +433,22 @@ HD void env_substep(const EnvIO& io, real* sm, const DevModel& m, const SimParam
   }
   sync();
   for (int t = 0; t < T; ++t) {
-    int i = m.sched[t * DYROS_LANES + g];
+    int i = HI(sched, t * DYROS_LANES + g);
     if (i > 0) {
       real* L = sm + i * LS;
-      const real* Lp = sm + m.link_parent[i] * LS;
-      int d = m.link_dof[i];
-      V3 ax = ld3_f(m.link_axis + 3 * i), r = ld3_f(m.link_r + 3 * i);
+      const real* Lp = sm + HI(parent, i) * LS;
+      int d = HI(dof, i);
+      V3 ax = HF3(axis, i), r = HF3(r, i);
       SV dv = xform_motion(ld_m3(L + LS_E), r, ld6(Lp + LS_V));
       real dqd = -L[LS_SC + 2] * (dot(ld6(L + LS_U), dv) + L[LS_SC + 3]);
       dv.w = dv.w + dqd * ax;
       st6(L + LS_V, dv);
       // joint velocity cap (dof_prop['velocity'], T:372), explicit Euler on the angle, limit projection
-      real vl = m.dof_vel_limit[d];
+      real vl = HF(vel_limit, d);
       real qdn = L[LS_SC] + dqd;
       qdn = qdn > vl ? vl : (qdn < -vl ? -vl : qdn);
       real qn = io.dof_state[2 * d] + dt * qdn;
-      real lo = m.dof_lower[d], up = m.dof_upper[d];
+      real lo = HF(lower, d), up = HF(upper, d);
       if (qn > up) {
         qn = up;
         qdn = qdn < 0 ? qdn : 0;

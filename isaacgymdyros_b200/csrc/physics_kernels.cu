@@ -2,6 +2,7 @@
 // tree), envs_per_block envs per CTA sized so that one CTA per SM covers N = 4096 on 148 SMs in a single wave;
 // the per-env scratch of physics_core.cuh lives in dynamic shared memory.
 #include "physics_core.cuh"
+#include "task_stages.cuh"
 
 namespace dyros {
 
@@ -13,10 +14,18 @@ constexpr int kMaxPhysSmem = 227 * 1024;
 
 __global__ void __launch_bounds__(128) k_simulate(DevModel m, SimParams p, DyrosSimBuffers b, const float* __restrict__ push,
                                                   int apply_wrench, int epb, int es) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
+  // stage the hot model tables (link tree, inertias, schedule) once per CTA
+  {
+    const float4* src = reinterpret_cast<const float4*>(m.blob);
+    float4* dst = reinterpret_cast<float4*>(smem);
+    for (int i = threadIdx.x; i < m.hot_bytes / 16; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const float* hot = smem;
   const int le = threadIdx.x / DYROS_LANES, g = threadIdx.x % DYROS_LANES;
   const int e = blockIdx.x * epb + le;
-  if (le >= epb || e >= p.N) return;  // whole lane groups leave together: every sync is inside one group
+  if (le >= epb || e >= p.N) return;  // whole lane groups leave together: every later sync is inside one group
   EnvIO io;
   io.root = b.root_states + (size_t)e * 13;
   io.dof_state = b.dof_state + (size_t)e * m.nd * 2;
@@ -30,18 +39,59 @@ __global__ void __launch_bounds__(128) k_simulate(DevModel m, SimParams p, Dyros
   io.rb_torque = apply_wrench ? b.rb_torque + (size_t)e * m.nb * 3 : nullptr;
   io.live = true;
   WarpSync sync;
-  real* sm = smem + (size_t)le * es;
+  real* sm = smem + m.hot_bytes / 4 + (size_t)le * es;
   for (int s = 0; s < p.substeps; ++s) {
-    env_substep(io, sm, m, p, g, sync);
+    env_substep(io, sm, hot, m, p, g, sync);
     io.push = nullptr;  // applied wrenches act "for the immediate timestep" (gym_py.html apply_rigid_body_force_tensors)
     io.rb_force = nullptr;
     io.rb_torque = nullptr;
   }
 }
 
+// The physics part of one policy step in ONE launch: skipframe x (PD + delay torque, gym.simulate, sensor noise),
+// i.e. the loop body of T:504-530 with the three gym calls of T:520-526 folded in.
+__global__ void __launch_bounds__(128) k_step_physics(DevModel m, SimParams p, TK k, int epb, int es) {
+  extern __shared__ __align__(16) float smem[];
+  {
+    const float4* src = reinterpret_cast<const float4*>(m.blob);
+    float4* dst = reinterpret_cast<float4*>(smem);
+    for (int i = threadIdx.x; i < m.hot_bytes / 16; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const float* hot = smem;
+  const int le = threadIdx.x / DYROS_LANES, g = threadIdx.x % DYROS_LANES;
+  const int e = blockIdx.x * epb + le;
+  if (le >= epb || e >= p.N) return;
+  const DyrosSimBuffers& b = k.s;
+  EnvIO io;
+  io.root = b.root_states + (size_t)e * 13;
+  io.dof_state = b.dof_state + (size_t)e * m.nd * 2;
+  io.tau = b.dof_actuation_force + (size_t)e * m.nd;
+  io.damping = b.dof_damping + (size_t)e * m.nd;
+  io.armature = b.dof_armature + (size_t)e * m.nd;
+  io.mass_scale = b.body_mass_scale + (size_t)e * m.nb;
+  io.contact = b.net_contact_force + (size_t)e * m.nb * 3;
+  io.rb_force = nullptr;
+  io.rb_torque = nullptr;
+  io.live = true;
+  WarpSync sync;
+  real* sm = smem + m.hot_bytes / 4 + (size_t)le * es;
+  for (int s = 0; s < k.p.skipframe; ++s) {
+    stage_substep_torque<DYROS_LANES>(k, e, g, sync);
+    sync();
+    io.push = s == 0 ? k.b.push_force + (size_t)e * 3 : nullptr;  // the push acts on the first sub-step only (T:502 vs T:504)
+    for (int ss = 0; ss < p.substeps; ++ss) {
+      env_substep(io, sm, hot, m, p, g, sync);
+      io.push = nullptr;
+    }
+    stage_sensor_noise<DYROS_LANES>(k, s, e, g);
+    sync();
+  }
+}
+
 int physics_configure(Sim* sim) {
   const int es = env_scratch_floats(sim->m.nl);
-  const int max_epb = std::min(kMaxPhysSmem / (es * (int)sizeof(float)), 128 / DYROS_LANES);
+  const int max_epb = std::min((kMaxPhysSmem - sim->m.hot_bytes) / (es * (int)sizeof(float)), 128 / DYROS_LANES);
   if (max_epb < 1) {
     set_error("physics_configure: one env needs %d bytes of shared memory", es * (int)sizeof(float));
     return 1;
@@ -50,8 +100,9 @@ int physics_configure(Sim* sim) {
   epb = std::max(epb, 8);
   epb = std::min(epb, max_epb);
   sim->envs_per_block = epb;
-  sim->phys_smem = (size_t)epb * es * sizeof(float);
+  sim->phys_smem = (size_t)sim->m.hot_bytes + (size_t)epb * es * sizeof(float);
   DY_CUDA(cudaFuncSetAttribute(k_simulate, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPhysSmem));
+  DY_CUDA(cudaFuncSetAttribute(k_step_physics, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPhysSmem));
   return 0;
 }
 
@@ -61,6 +112,21 @@ int launch_simulate(Sim* sim, int apply_wrench, const float* push, cudaStream_t 
   const int threads = ((epb * DYROS_LANES + 31) / 32) * 32;
   k_simulate<<<grid, threads, sim->phys_smem, s>>>(sim->m, sim->p, sim->b, push, apply_wrench, epb,
                                                    env_scratch_floats(sim->m.nl));
+  DY_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_task_physics(Task* t, cudaStream_t s) {
+  Sim* sim = t->sim;
+  const int epb = sim->envs_per_block;
+  const int grid = (sim->p.N + epb - 1) / epb;
+  const int threads = ((epb * DYROS_LANES + 31) / 32) * 32;
+  TK k;
+  k.p = t->p;
+  k.b = t->b;
+  k.s = sim->b;
+  k.j = t->inj;
+  k_step_physics<<<grid, threads, sim->phys_smem, s>>>(sim->m, sim->p, k, epb, env_scratch_floats(sim->m.nl));
   DY_LAUNCH_CHECK();
   return 0;
 }

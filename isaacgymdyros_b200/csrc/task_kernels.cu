@@ -4,16 +4,9 @@
 // ATen), and parity is judged at 1e-5 relative with bit-exact masks, so no FMA contraction here.
 // Citations: T = tasks/dyros_dynamic_walk.py, VT = tasks/base/vec_task.py, JU = utils/torch_jit_utils.py,
 // TU = isaacgym/torch_utils.py (all under the reference's python/ tree).
-#include "internal.h"
+#include "task_stages.cuh"
 
 namespace dyros {
-
-struct TK {
-  TaskParams p;
-  DyrosTaskBuffers b;
-  DyrosSimBuffers s;
-  DyrosNoiseInjection j;
-};
 
 constexpr int kWarpsPerBlock = 4;
 
@@ -153,54 +146,9 @@ __device__ void stage_prologue(const TK& k, const float* __restrict__ actions_in
   }
 }
 
-// T:505-520
-__device__ void stage_substep_torque(const TK& k, int e, int lane) {
-  const float* ds = k.s.dof_state + (size_t)e * ND * 2;
-  float* out = k.s.dof_actuation_force + (size_t)e * ND;
-  for (int d = 12 + lane; d < ND; d += kWarp) {                                   // T:506
-    float pos = ds[2 * d], vel = ds[2 * d + 1];
-    out[d] = k.p.kp[d] * (k.b.target_data_qpos[(size_t)e * ND + d] - pos) + k.p.kv[d] * (-vel);
-  }
-  int sl = k.b.simul_len[e] + 1;                                                  // T:513-514
-  sl = sl > LOG_DEPTH ? LOG_DEPTH : (sl < 0 ? 0 : sl);
-  int dl = k.b.delay_idx[e];
-  if (lane < 12) {
-    float* lg = k.b.action_log + (size_t)e * LOG_DEPTH * 12 + lane;
-    float v[LOG_DEPTH];
-#pragma unroll
-    for (int i = 0; i < LOG_DEPTH - 1; ++i) v[i] = lg[(i + 1) * 12];              // T:511
-    v[LOG_DEPTH - 1] = k.b.action_torque[(size_t)e * 12 + lane];                  // T:512
-#pragma unroll
-    for (int i = 0; i < LOG_DEPTH; ++i) lg[i * 12] = v[i];
-    int pick = (sl > dl) ? dl : (LOG_DEPTH - sl);                                 // T:515-519
-    float r = v[0];
-#pragma unroll
-    for (int i = 1; i < LOG_DEPTH; ++i) r = (pick == i) ? v[i] : r;
-    out[lane] = r;                                                                // T:520
-  }
-  __syncwarp();
-  if (lane == 0) k.b.simul_len[e] = sl;
-}
-
-// T:528-530
-__device__ void stage_sensor_noise(const TK& k, int substep, int e, int lane) {
-  const float* ds = k.s.dof_state + (size_t)e * ND * 2;
-  for (int d = lane; d < ND; d += kWarp) {
-    float n;
-    if (k.j.qpos_normal) {
-      n = k.j.qpos_normal[((size_t)substep * k.p.N + e) * ND + d];
-    } else {
-      uint4 r = draw4(k.p.seed, *k.p.step_counter, e, kSiteQposNoise, substep * 64 + d);
-      n = normal01(r.x, r.y) * k.p.noise_std;
-    }
-    n = (n < -0.00016f) ? -0.00016f : ((n > 0.00016f) ? 0.00016f : n);
-    float qn = ds[2 * d] + n;
-    size_t i = (size_t)e * ND + d;
-    k.b.qvel_noise[i] = (qn - k.b.qpos_pre[i]) / k.p.dt;
-    k.b.qpos_noise[i] = qn;
-    k.b.qpos_pre[i] = qn;
-  }
-}
+struct WarpSyncT {
+  __device__ __forceinline__ void operator()() const { __syncwarp(); }
+};
 
 // T:532-541, VT:325, T:544-545
 __device__ void stage_epilogue(const TK& k, int e, int lane) {
@@ -464,11 +412,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_prologue(TK k, const fl
 }
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_substep_torque(TK k) {
   ENV_LANE();
-  stage_substep_torque(k, e, lane);
+  WarpSyncT sync;
+  stage_substep_torque<32>(k, e, lane, sync);
 }
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_sensor_noise(TK k, int substep) {
   ENV_LANE();
-  stage_sensor_noise(k, substep, e, lane);
+  stage_sensor_noise<32>(k, substep, e, lane);
 }
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_epilogue(TK k) {
   ENV_LANE();

@@ -10,7 +10,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdyros_b200.so")
+LIB_PATH = os.environ.get("DYROS_B200_LIB", os.path.join(_HERE, "libdyros_b200.so"))  # override: A/B builds only
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "dyros_b200.h")
 
 i32, f32, f64, u64 = C.c_int32, C.c_float, C.c_double, C.c_uint64
@@ -102,6 +102,7 @@ SIGNATURES = {
     "dyros_task_destroy": (_INT, [_VP]),
     "dyros_task_set_noise_injection": (_INT, [_VP, C.POINTER(DyrosNoiseInjection)]),
     "dyros_task_prologue": (_INT, [_VP, _VP, _VP]),
+    "dyros_task_physics": (_INT, [_VP, _VP]),
     "dyros_task_substep_torque": (_INT, [_VP, _VP]),
     "dyros_task_sensor_noise": (_INT, [_VP, _INT, _VP]),
     "dyros_task_epilogue": (_INT, [_VP, _VP]),

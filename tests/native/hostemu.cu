@@ -55,7 +55,7 @@ extern "C" int dyros_hostemu_simulate(const DyrosSimDesc* d, const DyrosModelDes
       for (int g = 0; g < DYROS_LANES; ++g)
         th.emplace_back([&, g]() {
           BarrierSync sync{&bar};
-          env_substep(io, scratch.data(), m, p, g, sync);
+          env_substep(io, scratch.data(), reinterpret_cast<const float*>(bl.host.data()), m, p, g, sync);
         });
       for (auto& t : th) t.join();
       io.push = nullptr;
@@ -63,5 +63,15 @@ extern "C" int dyros_hostemu_simulate(const DyrosSimDesc* d, const DyrosModelDes
       io.rb_torque = nullptr;
     }
   }
+  return 0;
+}
+
+extern "C" int dyros_hostemu_layout(const DyrosModelDesc* md, int* hot_bytes, int* env_scratch_bytes) {
+  Blob bl;
+  DevModel m;
+  ModelOffsets off;
+  if (!build_model_tables(md, bl, m, off).empty()) return 1;
+  *hot_bytes = m.hot_bytes;
+  *env_scratch_bytes = env_scratch_floats(m.nl) * (int)sizeof(real);
   return 0;
 }
