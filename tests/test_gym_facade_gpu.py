@@ -1,0 +1,100 @@
+"""The gym-level boundary (gymapi / gymtorch facade) driven the way the reference task drives Isaac Gym
+(tasks/dyros_dynamic_walk.py:199-385 setup, :504-530 physics loop, :720-748 indexed resets)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def build_sim(N):
+    from isaacgymdyros_b200 import gymapi, gymtorch
+    gym = gymapi.acquire_gym()
+    sp = gymapi.SimParams()
+    sp.dt, sp.substeps, sp.up_axis = 0.002, 1, gymapi.UP_AXIS_Z
+    sp.gravity = gymapi.Vec3(0.0, 0.0, -9.81)
+    sp.use_gpu_pipeline = True
+    sp.physx.contact_offset, sp.physx.max_depenetration_velocity = 0.002, 10.0
+    sim = gym.create_sim(0, -1, gymapi.SIM_PHYSX, sp)
+    assert sim is not None
+    pp = gymapi.PlaneParams()
+    pp.normal = gymapi.Vec3(0.0, 0.0, 1.0)
+    gym.add_ground(sim, pp)
+    ao = gymapi.AssetOptions()
+    ao.angular_damping, ao.max_angular_velocity = 0.0, 100.0
+    asset = gym.load_asset(sim, "../assets", "mjcf/dyros_tocabi/xml/dyros_tocabi.xml", ao)
+    assert gym.get_asset_rigid_body_count(asset) == 38 and gym.get_asset_dof_count(asset) == 33
+    assert gym.find_asset_rigid_body_index(asset, "L_Foot_Link") == 8
+    assert gym.find_asset_rigid_body_index(asset, "R_Foot_Link") == 16
+    envs = []
+    for i in range(N):
+        env = gym.create_env(sim, gymapi.Vec3(0, 0, 0), gymapi.Vec3(0, 0, 0), 4)
+        pose = gymapi.Transform(gymapi.Vec3(5.0 * i, 0.0, 0.93), gymapi.Quat(0, 0, 0, 1))
+        h = gym.create_actor(env, asset, pose, "humanoid", i, 0, 0)
+        props = gym.get_actor_dof_properties(env, h)
+        props["damping"] = 0.1
+        props["velocity"] = 4.03
+        props["armature"] = 0.5
+        assert gym.set_actor_dof_properties(env, h, props)
+        envs.append(env)
+    assert gym.prepare_sim(sim)
+    return gym, gymapi, gymtorch, sim, envs
+
+
+def test_gym_tensor_api_loop_matches_core_and_indexed_reset():
+    from isaacgymdyros_b200.core import INIT_DOF_POS
+    N = 6
+    gym, gymapi, gymtorch, sim, envs = build_sim(N)
+    root = gymtorch.wrap_tensor(gym.acquire_actor_root_state_tensor(sim))
+    dof = gymtorch.wrap_tensor(gym.acquire_dof_state_tensor(sim))
+    contact = gymtorch.wrap_tensor(gym.acquire_net_contact_force_tensor(sim))
+    rb = gymtorch.wrap_tensor(gym.acquire_rigid_body_state_tensor(sim))
+    assert root.shape == (N, 13) and dof.shape == (N * 33, 2) and contact.shape == (N * 38, 3) and rb.shape == (N * 38, 13)
+    assert gymtorch.wrap_tensor(gym.acquire_dof_state_tensor(sim)).data_ptr() == dof.data_ptr()
+    assert torch.allclose(root[:, 0].cpu(), torch.arange(N) * 5.0) and (root[:, 2] == 0.93).all()
+    masses = [p.mass for p in gym.get_actor_rigid_body_properties(envs[0], 0)]
+    assert abs(sum(masses) - 104.48712) < 1e-4
+    dof.view(N, 33, 2)[:, :, 0] = torch.tensor(INIT_DOF_POS, device=dof.device)
+    assert gym.set_dof_state_tensor(sim, gymtorch.unwrap_tensor(dof))
+    q0 = dof.view(N, 33, 2)[:, :, 0].clone()
+    kp = torch.full((33,), 2000.0, device=dof.device)
+    for _ in range(150):  # T:504-526 pattern
+        tau = (kp * (q0 - dof.view(N, 33, 2)[:, :, 0]) - 30.0 * dof.view(N, 33, 2)[:, :, 1]).reshape(-1).contiguous()
+        assert gym.set_dof_actuation_force_tensor(sim, gymtorch.unwrap_tensor(tau))
+        gym.simulate(sim)
+        assert gym.refresh_dof_state_tensor(sim)
+    gym.fetch_results(sim, True)
+    assert gym.refresh_net_contact_force_tensor(sim) and gym.refresh_rigid_body_state_tensor(sim)
+    assert gym.get_frame_count(sim) == 150
+    fz = contact.view(N, 38, 3)[:, :, 2].sum(1)
+    assert ((fz - 104.48712 * 9.81).abs() < 0.08 * 104.48712 * 9.81).all()
+    assert torch.allclose(rb.view(N, 38, 13)[:, 0, :3], root[:, :3], atol=1e-6)  # body 0 is the root
+    # a push through apply_rigid_body_force_tensors acts for one step on the pelvis
+    f = torch.zeros(N * 38, 3, device=dof.device)
+    f.view(N, 38, 3)[:, 0, 0] = 2000.0
+    v_before = root[:, 7].clone()
+    assert gym.apply_rigid_body_force_tensors(sim, gymtorch.unwrap_tensor(f), None, gymapi.ENV_SPACE)
+    gym.simulate(sim)
+    dv1 = (root[:, 7] - v_before).clone()
+    v_before = root[:, 7].clone()
+    gym.simulate(sim)
+    dv2 = root[:, 7] - v_before
+    assert (dv1 > 0.01).all() and (dv2.abs() < 0.5 * dv1).all()
+    # indexed reset: full tensors + int32 actor ids (T:737-746)
+    ids = torch.tensor([1, 4], dtype=torch.int32, device=dof.device)
+    root[ids.long(), 2] = 1.5
+    dof.view(N, 33, 2)[ids.long()] = 0.0
+    assert gym.set_actor_root_state_tensor_indexed(sim, gymtorch.unwrap_tensor(root), gymtorch.unwrap_tensor(ids), 2)
+    assert gym.set_dof_state_tensor_indexed(sim, gymtorch.unwrap_tensor(dof), gymtorch.unwrap_tensor(ids), 2)
+    assert not gym.set_dof_state_tensor_indexed(sim, gymtorch.unwrap_tensor(dof), gymtorch.unwrap_tensor(ids.long()), 2)
+    gym.simulate(sim)
+    assert (root[ids.long(), 2] > 1.4).all() and (contact.view(N, 38, 3)[ids.long()] == 0).all()
+    with pytest.raises(Exception):
+        gymtorch.unwrap_tensor(dof.view(N, 33, 2)[:, :, 0])  # non-contiguous (gymtorch.py:98-99)
+    gym.destroy_sim(sim)
+
+
+def test_create_sim_failure_returns_none():
+    from isaacgymdyros_b200 import gymapi
+    gym = gymapi.acquire_gym()
+    assert gym.create_sim(0, -1, gymapi.SIM_FLEX, gymapi.SimParams()) is None  # caller quits (vec_task.py:270-273)
