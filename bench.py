@@ -258,19 +258,10 @@ def run_ours(a):
     k1_ms = statistics.mean(s.elapsed_time(e) for s, e in kev)
     reset_rate = float(env.reset_buf.float().mean().item())
 
-    def reduce_max(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    cold_ms, warm_ms, e2e_ms, k1_ms = (reduce_max(x) for x in (cold_ms, warm_ms, e2e_ms, k1_ms))
+    from isaacgymdyros_b200.sharding import max_over_ranks, reduce_episode_stats
+    cold_ms, warm_ms, e2e_ms, k1_ms = (max_over_ranks(x, dev) for x in (cold_ms, warm_ms, e2e_ms, k1_ms))
     # episode statistics across ranks (the only data the env path ever reduces)
-    stats = torch.stack([env.epi_len_log.mean(), env.contact_reward_mean.nan_to_num().mean()]).double()
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-        stats /= world
+    stats = reduce_episode_stats({"epi_len_log": env.epi_len_log, "contact_reward_mean": env.contact_reward_mean})
     if rank == 0:
         peaks = {}
         try:
@@ -306,7 +297,7 @@ def run_ours(a):
                      "frac": K1_FLOP_PER_ENV_STEP * N / (k1_ms * 1e-3) / 1e12 / fp32_peak,
                      "peak_source": "dyros_measure_fp32_peak (FFMA saturation, this run)"},
             "whole_step_hbm": {"achieved": ENV_STEP_BYTES * N / (cold_ms / K * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"},
-            "episode_stats": {"epi_len_log_mean": float(stats[0]), "contact_reward_mean": float(stats[1])},
+            "episode_stats": stats,
             "wall_s_flush_loop": t_wall_flush,
         }
         if world == 1 and not a.no_cpu_baseline:
