@@ -62,6 +62,8 @@ typedef struct {
   const double* cyl_axis;     /* [nc*3] */
   const double* cyl_size;     /* [nc*2] radius, half height */
   const int32_t* sched;       /* [sched_slots*DYROS_LANES] */
+  const int32_t* link_pos;    /* [nl] scratch-block position of each link (a permutation of 0..nl-1; bank-conflict
+                                 layout, model/tables.py::scratch_positions); NULL = identity */
 } DyrosModelDesc;
 
 /* gymapi.SimParams / PhysXParams subset that reaches the solver (VT:423-471, DyrosDynamicWalk.yaml:37-56)

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import native
-from .model.tables import ModelTables
+from .model.tables import ModelTables, scratch_positions
 
 ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
 ND, NB, NA = 33, 38, 13
@@ -111,7 +111,8 @@ def make_model_desc(t: ModelTables, cfg: "CoreConfig"):
                           ("pt_solver", i32(pt_solver), C.c_int32),
                           ("cyl_link", i32(t.cyl_link), C.c_int32), ("cyl_body", i32(t.cyl_body), C.c_int32),
                           ("cyl_center", f64(t.cyl_center), C.c_double), ("cyl_axis", f64(t.cyl_axis), C.c_double),
-                          ("cyl_size", f64(t.cyl_size), C.c_double), ("sched", i32(t.sched), C.c_int32)]:
+                          ("cyl_size", f64(t.cyl_size), C.c_double), ("sched", i32(t.sched), C.c_int32),
+                          ("link_pos", i32(scratch_positions(t.sched, t.num_links)), C.c_int32)]:
         setattr(md, name, _np_ptr(arr, ct))
     return md, keep
 

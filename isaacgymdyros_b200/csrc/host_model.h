@@ -36,7 +36,7 @@ static const T* at(void* base, size_t off) {
 }
 
 struct ModelOffsets {
-  size_t parent, dof, E, r, ax, cs, ch, bs, bd, bl, bp, br, bi, lo, up, vl, ef, ps, pb, pp, pr, ys, yb, yc, ya, yz, sc, rc;
+  size_t parent, dof, E, r, ax, cs, ch, bs, bd, bl, bp, br, bi, lo, up, vl, ef, ps, pb, pp, pr, ys, yb, yc, ya, yz, sc, rc, po;
 };
 
 // Fills `dm` (counts, foot tables) and appends every table to `bl`. Returns "" or an error message.
@@ -145,6 +145,9 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
     for (int l = dm.foot_link[f]; l > 0; l = m->link_parent[l]) path.push_back(l);
     if ((int)path.size() > MAX_CHAIN || path.empty()) MFAIL("solver link %d is %zu joints from the base (max %d)", dm.foot_link[f], path.size(),
                 MAX_CHAIN);
+    if ((int)path.size() * 2 < MAX_ACTIVE_PTS * 3)
+      MFAIL("solver link %d is only %zu joints from the base; the contact rows are parked in the chain's scratch blocks "
+            "(2 per link, %d needed)", dm.foot_link[f], path.size(), MAX_ACTIVE_PTS * 3);
     dm.chain_len[f] = (int)path.size();
     for (int k = 0; k < (int)path.size(); ++k) dm.chain[f][k] = path[path.size() - 1 - k];
   }
@@ -178,6 +181,15 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
   o.ps = bl.add_i(pt_start.data(), nl + 1); o.ys = bl.add_i(cyl_start.data(), nl + 1);
   o.sc = bl.add_i(m->sched, (size_t)m->sched_slots * DYROS_LANES);
   o.rc = bl.add_f32(reach.data(), nl);
+  std::vector<int> pos(nl);
+  {
+    std::vector<int> seen(nl, 0);
+    for (int l = 0; l < nl; ++l) {
+      pos[l] = m->link_pos ? m->link_pos[l] : l;
+      if (pos[l] < 0 || pos[l] >= nl || seen[pos[l]]++) MFAIL("link_pos is not a permutation of 0..%d", nl - 1);
+    }
+  }
+  o.po = bl.add_i(pos.data(), nl);
   dm.hot_bytes = (int)((bl.host.size() + 15) & ~size_t(15));
   // cold tables (global memory, read only when a link is near the ground or for rigid_body_state)
   o.bl = bl.add_i(m->body_link, nb); o.bp = bl.add_f(m->body_pos, nb * 3); o.br = bl.add_f(m->body_rot, nb * 9);
@@ -193,7 +205,7 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
   dm.o_body_start = (int)(o.bs / 4); dm.o_bodies = (int)(o.bd / 4); dm.o_body_inertia = (int)(o.bi / 4);
   dm.o_lower = (int)(o.lo / 4); dm.o_upper = (int)(o.up / 4); dm.o_vel_limit = (int)(o.vl / 4);
   dm.o_effort = (int)(o.ef / 4); dm.o_pt_start = (int)(o.ps / 4); dm.o_cyl_start = (int)(o.ys / 4);
-  dm.o_sched = (int)(o.sc / 4); dm.o_reach = (int)(o.rc / 4);
+  dm.o_sched = (int)(o.sc / 4); dm.o_reach = (int)(o.rc / 4); dm.o_pos = (int)(o.po / 4);
 
   return std::string();
 #undef MFAIL

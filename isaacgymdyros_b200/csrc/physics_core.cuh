@@ -5,38 +5,46 @@
 // forward dynamics (Featherstone ABA, three passes over a branch-parallel link schedule) with implicit joint
 // damping and rotor inertia, penalty ground contact for all collision primitives except the sole corners,
 // and a fixed-sweep projected Gauss-Seidel solve of the sole-corner contacts in the 6-D space of each foot
-// link using the exact articulated inverse inertia (O(n) recursion down the leg chains). The model and every
+// link using the exact articulated inverse inertia (O(n) recursion up the leg chains). The model and every
 // formula are stated independently (dense, fp64) in oracle/physics_oracle.py; see DESIGN.md section 4.
 //
 // The lanes of an env talk through the env's scratch block `sm` (shared memory on the GPU) and meet at
-// sync() points; the same source is compiled for the host by tests/native/hostemu.cpp (4 threads + a barrier).
+// sync() points; the same source is compiled for the host by tests/native/hostemu.cu (4 threads + a barrier).
 #pragma once
 #include "internal.h"
 #include "phys_math.cuh"
 
 namespace dyros {
 
-// per-link scratch layout (floats)
+// per-link scratch block (floats). Blocks are placed at positions HI(pos, link) so that the links of one schedule
+// slot fall into different shared-memory banks (LS is odd, the env stride is 4 mod 32).
 constexpr int LS_E = 0;    // 9  parent->link rotation (base: base->world rotation)
 constexpr int LS_V = 9;    // 6  link velocity, later the impulse response dv
-constexpr int LS_A = 15;   // 28 pass1: inertia(10) pA(6) world pose(12) | pass2: contribution to parent IA(21) pA(6) | pass3: a'(6)
-constexpr int LS_U = 43;   // 6  U = IA S (base: predicted velocity v0*)
-constexpr int LS_SC = 49;  // 4  [qd -> qd*, tau -> u, damping -> 1/D, armature -> S^T dp]
+constexpr int LS_A = 15;   // 27 pass1: pA(6) world pose(12) | pass2: contribution to parent IA(21) pA(6) |
+                           //    pass3: a'(6); leg-chain links then also hold contact rows (14) and g = S^T G (6)
+constexpr int LS_U = 42;   // 6  U = IA S (base: predicted velocity v0*)
+constexpr int LS_SC = 48;  // 4  [qd -> qd*, tau -> u, damping -> 1/D, armature -> S^T dp]
+constexpr int LS_Q = 52;   // 1  joint angle
 constexpr int LS = 53;
-constexpr int A_INERTIA = 0, A_PA = 10, A_POSE = 16, A_CIA = 0, A_CPA = 21, A_ACC = 0, A_OM0 = 6;
+constexpr int A_PA = 0, A_POSE = 6, A_CIA = 0, A_CPA = 21, A_ACC = 0, A_OM0 = 6, A_ROWS = 6, A_G = 21;
+constexpr int ROWS_PER_LINK = 2;  // contact rows (7 floats each) parked in one leg-chain link's block
 // per-env extra scratch
 constexpr int X_FOOTPOSE = 0;                     // MAX_FEET * 12
 constexpr int X_Z = X_FOOTPOSE + MAX_FEET * 12;   // MAX_FEET * 6  base velocity change caused by a foot's sweep
 constexpr int X_PD = X_Z + MAX_FEET * 6;          // MAX_FEET * 6  impulse arriving at the base from a foot
-constexpr int X_ROWS = X_PD + MAX_FEET * 6;       // MAX_FEET * MAX_ACTIVE_PTS * 3 * 7  (Om J^T (6), 1 / (J Om J^T))
-constexpr int X_SIZE = X_ROWS + MAX_FEET * MAX_ACTIVE_PTS * 3 * 7;
+constexpr int X_MASS = X_PD + MAX_FEET * 6;       // DYROS_MAX_BODIES per-body mass scale
+constexpr int X_SIZE = X_MASS + DYROS_MAX_BODIES;
 
-HD int env_scratch_floats(int nl) { return nl * LS + X_SIZE; }
+HD int env_scratch_floats(int nl) {
+  int n = nl * LS + X_SIZE;
+  return n + ((4 - n % 32) + 32) % 32;  // stride = 4 (mod 32): the 8 envs of a warp start in banks 0, 4, ..., 28
+}
 
 // The hot model tables are read from the staged copy `hot` (shared memory on the GPU) through word offsets.
 #define HI(field, idx) (reinterpret_cast<const int*>(hot)[m.o_##field + (idx)])
 #define HF(field, idx) (hot[m.o_##field + (idx)])
 #define HF3(field, idx) ld3_f(hot + m.o_##field + 3 * (idx))
+#define BLK(link) (sm + HI(pos, link) * LS)
 
 // global-memory views of one env (all device pointers on the GPU, host pointers in the emulation)
 struct EnvIO {
@@ -73,25 +81,23 @@ HD void penalty_point(const SimParams& p, const M3& Rw, SV v, V3 xs, real depth,
   fext.v = fext.v + fl;
 }
 
-// Link inertia parameters of link i from the per-body mass scales (P0). Writes A_INERTIA.
-HD void link_inertia(const EnvIO& io, real* L, const float* hot, const DevModel& m, int i) {
+// Rigid inertia of link i from the hot body table and the env's per-body mass scales (X_MASS).
+HD ABI link_inertia(const real* X, const float* hot, const DevModel& m, int i) {
   real par[10];
 #pragma unroll
   for (int k = 0; k < 10; ++k) par[k] = 0;
   for (int bi = HI(body_start, i); bi < HI(body_start, i + 1); ++bi) {
     int b = HI(bodies, bi);
-    real sc = io.mass_scale[b];
+    real sc = X[X_MASS + b];
 #pragma unroll
     for (int k = 0; k < 10; ++k) par[k] += sc * HF(body_inertia, b * 10 + k);
   }
-#pragma unroll
-  for (int k = 0; k < 10; ++k) L[LS_A + A_INERTIA + k] = par[k];
+  return abi_rigid(par[0], v3(par[1], par[2], par[3]), S3{par[4], par[5], par[6], par[7], par[8], par[9]});
 }
 
-// Bias force and external wrench of link i (pass 1). Reads A_INERTIA, writes A_PA.
-HD void link_forces(const EnvIO& io, real* L, const float* hot, const DevModel& m, const SimParams& p, int i, const M3& Rw,
-                    V3 pw, SV v) {
-  real* A = L + LS_A;
+// Bias force and external wrench of link i (pass 1). Writes A_PA.
+HD void link_forces(const EnvIO& io, real* L, const real* X, const float* hot, const DevModel& m, const SimParams& p, int i,
+                    const M3& Rw, V3 pw, SV v) {
   SV fext = sv_zero();
   V3 nrm = v3(Rw.a[6], Rw.a[7], Rw.a[8]);  // world z in link coordinates
   for (int bi = HI(body_start, i); bi < HI(body_start, i + 1); ++bi) {
@@ -109,7 +115,7 @@ HD void link_forces(const EnvIO& io, real* L, const float* hot, const DevModel& 
         F = F + ld3_f(io.rb_force + 3 * b);
         T = ld3_f(io.rb_torque + 3 * b);
       }
-      real sc = io.mass_scale[b];
+      real sc = X[X_MASS + b];
       real mb = sc * HF(body_inertia, b * 10);
       real inv = 1 / (mb > (real)1e-30 ? mb : (real)1e-30);
       V3 com = v3(sc * HF(body_inertia, b * 10 + 1) * inv, sc * HF(body_inertia, b * 10 + 2) * inv,
@@ -138,9 +144,8 @@ HD void link_forces(const EnvIO& io, real* L, const float* hot, const DevModel& 
     real z = pw.z + dot(nrm, rim);
     penalty_point(p, Rw, v, rim, -z, io.contact + 3 * m.cyl_body[k], io.live, fext);
   }
-  ABI I = abi_rigid(A[0], v3(A[1], A[2], A[3]), S3{A[4], A[5], A[6], A[7], A[8], A[9]});
-  SV pA = crf(v, mul(I, v)) - fext;
-  st6(A + A_PA, pA);
+  SV pA = crf(v, mul(link_inertia(X, hot, m, i), v)) - fext;
+  st6(L + LS_A + A_PA, pA);
 }
 
 template <class Sync>
@@ -149,13 +154,12 @@ HD void env_substep(const EnvIO& io, real* sm, const float* hot, const DevModel&
   real* X = sm + nl * LS;
   const real dt = p.dt;
 
-  // ---- P0: joint inputs -> scratch (lane g takes links g+1, g+1+LANES, ...)
-  for (int i = g; i < nl; i += DYROS_LANES) {
-    real* L = sm + i * LS;
-    link_inertia(io, L, hot, m, i);
-    if (i == 0) continue;
+  // ---- P0: per-env inputs -> scratch (lane g takes links g+1, g+1+LANES, ...)
+  for (int b = g; b < m.nb; b += DYROS_LANES) X[X_MASS + b] = io.mass_scale[b];
+  for (int i = 1 + g; i < nl; i += DYROS_LANES) {
     int d = HI(dof, i);
-    L[LS_E] = io.dof_state[2 * d];
+    real* L = BLK(i);
+    L[LS_Q] = io.dof_state[2 * d];
     L[LS_SC + 0] = io.dof_state[2 * d + 1];
     real tq = io.tau[d];
     if (p.clamp_effort) {
@@ -166,9 +170,10 @@ HD void env_substep(const EnvIO& io, real* sm, const float* hot, const DevModel&
     L[LS_SC + 2] = io.damping[d];
     L[LS_SC + 3] = io.armature[d];
   }
+  sync();
   // ---- P1: base kinematics and forces (lane 0)
   if (g == 0) {
-    real* L = sm;
+    real* L = BLK(0);
     V3 pw = ld3_f(io.root);
     M3 R0 = quat_to_mat(io.root[3], io.root[4], io.root[5], io.root[6]);
     SV v0{mulT(R0, ld3_f(io.root + 10)), mulT(R0, ld3_f(io.root + 7))};
@@ -176,16 +181,16 @@ HD void env_substep(const EnvIO& io, real* sm, const float* hot, const DevModel&
     st6(L + LS_V, v0);
     st_m3(L + LS_A + A_POSE, R0);
     st3(L + LS_A + A_POSE + 9, pw);
-    link_forces(io, L, hot, m, p, 0, R0, pw, v0);
+    link_forces(io, L, X, hot, m, p, 0, R0, pw, v0);
   }
   sync();
   // ---- P2: pass 1, root -> leaves: transforms, velocities, world poses, bias forces
   for (int t = 0; t < T; ++t) {
     int i = HI(sched, t * DYROS_LANES + g);
     if (i > 0) {
-      real* L = sm + i * LS;
-      const real* Lp = sm + HI(parent, i) * LS;
-      real q = L[LS_E], qd = L[LS_SC];
+      real* L = BLK(i);
+      const real* Lp = BLK(HI(parent, i));
+      real q = L[LS_Q], qd = L[LS_SC];
       V3 ax = HF3(axis, i), r = HF3(r, i);
       M3 E = mul(axis_rot_T(ax, sin(q), cos(q)), ld_m3_f(hot + m.o_E + 9 * i));
       SV v = xform_motion(E, r, ld6(Lp + LS_V));
@@ -202,7 +207,7 @@ HD void env_substep(const EnvIO& io, real* sm, const float* hot, const DevModel&
           st_m3(X + X_FOOTPOSE + 12 * f, Rw);
           st3(X + X_FOOTPOSE + 12 * f + 9, pw);
         }
-      link_forces(io, L, hot, m, p, i, Rw, pw, v);
+      link_forces(io, L, X, hot, m, p, i, Rw, pw, v);
     }
     sync();
   }
@@ -210,12 +215,12 @@ HD void env_substep(const EnvIO& io, real* sm, const float* hot, const DevModel&
   for (int t = T - 1; t >= 0; --t) {
     int i = HI(sched, t * DYROS_LANES + g);
     if (i > 0) {
-      real* L = sm + i * LS;
+      real* L = BLK(i);
       real* A = L + LS_A;
-      ABI IA = abi_rigid(A[0], v3(A[1], A[2], A[3]), S3{A[4], A[5], A[6], A[7], A[8], A[9]});
+      ABI IA = link_inertia(X, hot, m, i);
       SV pA = ld6(A + A_PA);
       for (int ci = HI(child_start, i); ci < HI(child_start, i + 1); ++ci) {
-        const real* Ac = sm + HI(children, ci) * LS + LS_A;
+        const real* Ac = BLK(HI(children, ci)) + LS_A;
         IA = IA + ld_abi(Ac + A_CIA);
         pA = pA + ld6(Ac + A_CPA);
       }
@@ -242,12 +247,12 @@ HD void env_substep(const EnvIO& io, real* sm, const float* hot, const DevModel&
   }
   // ---- P4: floating base (lane 0): inverse articulated inertia, base acceleration, predicted base velocity
   if (g == 0) {
-    real* L = sm;
+    real* L = BLK(0);
     real* A = L + LS_A;
-    ABI IA = abi_rigid(A[0], v3(A[1], A[2], A[3]), S3{A[4], A[5], A[6], A[7], A[8], A[9]});
+    ABI IA = link_inertia(X, hot, m, 0);
     SV pA = ld6(A + A_PA);
     for (int ci = HI(child_start, 0); ci < HI(child_start, 1); ++ci) {
-      const real* Ac = sm + HI(children, ci) * LS + LS_A;
+      const real* Ac = BLK(HI(children, ci)) + LS_A;
       IA = IA + ld_abi(Ac + A_CIA);
       pA = pA + ld6(Ac + A_CPA);
     }
@@ -270,8 +275,8 @@ HD void env_substep(const EnvIO& io, real* sm, const float* hot, const DevModel&
   for (int t = 0; t < T; ++t) {
     int i = HI(sched, t * DYROS_LANES + g);
     if (i > 0) {
-      real* L = sm + i * LS;
-      const real* Lp = sm + HI(parent, i) * LS;
+      real* L = BLK(i);
+      const real* Lp = BLK(HI(parent, i));
       V3 ax = HF3(axis, i), r = HF3(r, i);
       M3 E = ld_m3(L + LS_E);
       SV v = ld6(L + LS_V);
@@ -285,11 +290,12 @@ HD void env_substep(const EnvIO& io, real* sm, const float* hot, const DevModel&
     }
     sync();
   }
-  // ---- P6: feet (lane f = foot f): inverse inertia at the foot, coupling to the base, predicted foot velocity,
-  //          active sole points and their constraint rows
+  // ---- P6: feet (lane f = foot f). Down the leg chain: predicted foot velocity. Up the leg chain: G = map foot
+  //          force -> force on the current link; the foot's inverse inertia Om = sum_j g_j g_j^T / D_j + G0^T Om0 G0
+  //          with g_j = S_j^T G_j (kept per chain link for the impulse pass). Then the active sole points and rows.
   const bool foot = g < m.num_feet;
-  ABI Om;               // inverse inertia seen at the foot link
-  SV K[6];              // rows of the map foot force -> base force
+  SV G[6];              // columns: force arriving at the base per unit foot force
+  SV Y[6];              // Om0 G
   SV V = sv_zero();     // foot velocity (foot coordinates)
   SV P = sv_zero();     // accumulated contact impulse on the foot (foot coordinates)
   M3 Rwf;
@@ -297,31 +303,62 @@ HD void env_substep(const EnvIO& io, real* sm, const float* hot, const DevModel&
   real bias[MAX_ACTIVE_PTS], lam[MAX_ACTIVE_PTS][3];
   int pbody[MAX_ACTIVE_PTS];
   int nact = 0;
-  real* rows = X + X_ROWS + (foot ? g : 0) * MAX_ACTIVE_PTS * 21;
   if (foot) {
-    Om = ld_abi(sm + LS_A + A_OM0);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) K[k] = sv_zero();
-    K[0].w.x = 1; K[1].w.y = 1; K[2].w.z = 1; K[3].v.x = 1; K[4].v.y = 1; K[5].v.z = 1;
-    V = ld6(sm + LS_U);
-    for (int k = 0; k < m.chain_len[g]; ++k) {
+    const int len = m.chain_len[g];
+    V = ld6(BLK(0) + LS_U);
+    for (int k = 0; k < len; ++k) {
       int j = m.chain[g][k];
-      const real* L = sm + j * LS;
+      const real* L = BLK(j);
+      V = xform_motion(ld_m3(L + LS_E), HF3(r, j), V);
+      V.w = V.w + L[LS_SC] * HF3(axis, j);
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) G[c] = sv_zero();
+    G[0].w.x = 1; G[1].w.y = 1; G[2].w.z = 1; G[3].v.x = 1; G[4].v.y = 1; G[5].v.z = 1;
+    ABI Om;
+    Om.I = S3{0, 0, 0, 0, 0, 0};
+    Om.M = S3{0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 9; ++c) Om.H.a[c] = 0;
+    for (int k = len - 1; k >= 0; --k) {
+      int j = m.chain[g][k];
+      real* L = BLK(j);
       V3 ax = HF3(axis, j), r = HF3(r, j);
       M3 E = ld_m3(L + LS_E);
       real Dinv = L[LS_SC + 2];
-      SV w = Dinv * xform_force_T(E, r, ld6(L + LS_U));
-      SV y = mul(Om, w);
-      real alpha = dot(w, y);
-      Om = inv_joint_update(inv_to_child(E, r, Om), ax, xform_motion(E, r, y), alpha + Dinv);
+      SV U = ld6(L + LS_U);
+      real gj[6];
 #pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        real kw = dot(K[q], w);
-        K[q] = xform_motion(E, r, K[q]);
-        K[q].w = K[q].w - kw * ax;
-      }
-      V = xform_motion(E, r, V);
-      V.w = V.w + L[LS_SC] * ax;
+      for (int c = 0; c < 6; ++c) gj[c] = dot(ax, G[c].w);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) L[LS_A + A_G + c] = gj[c];
+      // Om += Dinv g g^T  (blocks: angular-angular, angular-linear, linear-linear)
+      Om.I.xx += Dinv * gj[0] * gj[0]; Om.I.yy += Dinv * gj[1] * gj[1]; Om.I.zz += Dinv * gj[2] * gj[2];
+      Om.I.xy += Dinv * gj[0] * gj[1]; Om.I.xz += Dinv * gj[0] * gj[2]; Om.I.yz += Dinv * gj[1] * gj[2];
+      Om.M.xx += Dinv * gj[3] * gj[3]; Om.M.yy += Dinv * gj[4] * gj[4]; Om.M.zz += Dinv * gj[5] * gj[5];
+      Om.M.xy += Dinv * gj[3] * gj[4]; Om.M.xz += Dinv * gj[3] * gj[5]; Om.M.yz += Dinv * gj[4] * gj[5];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) Om.H.a[3 * a + b] += Dinv * gj[a] * gj[3 + b];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) G[c] = xform_force_T(E, r, G[c] - (Dinv * gj[c]) * U);
+    }
+    {
+      ABI Om0 = ld_abi(BLK(0) + LS_A + A_OM0);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) Y[c] = mul(Om0, G[c]);
+      real w[6][6];
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 6; ++b) w[a][b] = dot(G[a], Y[b]);
+      Om.I.xx += w[0][0]; Om.I.yy += w[1][1]; Om.I.zz += w[2][2]; Om.I.xy += w[0][1]; Om.I.xz += w[0][2]; Om.I.yz += w[1][2];
+      Om.M.xx += w[3][3]; Om.M.yy += w[4][4]; Om.M.zz += w[5][5]; Om.M.xy += w[3][4]; Om.M.xz += w[3][5]; Om.M.yz += w[4][5];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) Om.H.a[3 * a + b] += w[a][3 + b];
     }
     Rwf = ld_m3(X + X_FOOTPOSE + 12 * g);
     real pz = X[X_FOOTPOSE + 12 * g + 11];
@@ -352,7 +389,8 @@ HD void env_substep(const EnvIO& io, real* sm, const float* hot, const DevModel&
           V3 dir = d == 0 ? nrm : (d == 1 ? v3(Rwf.a[0], Rwf.a[1], Rwf.a[2]) : v3(Rwf.a[3], Rwf.a[4], Rwf.a[5]));
           SV J{cross(xsk, dir), dir};
           SV cv = mul(Om, J);
-          real* rw = rows + (nact * 3 + d) * 7;
+          int row = nact * 3 + d;  // parked in the block of chain link row / ROWS_PER_LINK
+          real* rw = BLK(m.chain[g][row / ROWS_PER_LINK]) + LS_A + A_ROWS + (row % ROWS_PER_LINK) * 7;
           st6(rw, cv);
           rw[6] = 1 / dot(J, cv);
         }
@@ -372,7 +410,8 @@ HD void env_substep(const EnvIO& io, real* sm, const float* hot, const DevModel&
             V3 dir = d == 0 ? v3(Rwf.a[6], Rwf.a[7], Rwf.a[8])
                             : (d == 1 ? v3(Rwf.a[0], Rwf.a[1], Rwf.a[2]) : v3(Rwf.a[3], Rwf.a[4], Rwf.a[5]));
             SV J{cross(xs[a], dir), dir};
-            const real* rw = rows + (a * 3 + d) * 7;
+            const int row = a * 3 + d;
+            const real* rw = BLK(m.chain[g][row / ROWS_PER_LINK]) + LS_A + A_ROWS + (row % ROWS_PER_LINK) * 7;
             real vrel = dot(J, V);
             real nw;
             if (d == 0) {
@@ -391,28 +430,24 @@ HD void env_substep(const EnvIO& io, real* sm, const float* hot, const DevModel&
         }
       }
       P = P + dP;
-      SV tb{v3(dot(K[0], dP), dot(K[1], dP), dot(K[2], dP)), v3(dot(K[3], dP), dot(K[4], dP), dot(K[5], dP))};
-      st6(X + X_Z + 6 * g, mul(ld_abi(sm + LS_A + A_OM0), tb));
+      // base velocity change caused by this sweep's impulses: Om0 G dP = sum_c dP_c Y_c
+      st6(X + X_Z + 6 * g, dP.w.x * Y[0] + dP.w.y * Y[1] + dP.w.z * Y[2] + dP.v.x * Y[3] + dP.v.y * Y[4] + dP.v.z * Y[5]);
     }
     sync();
     if (foot && m.num_feet == 2) {
-      SV z = ld6(X + X_Z + 6 * (1 - g));
-      V = V + z.w.x * K[0] + z.w.y * K[1] + z.w.z * K[2] + z.v.x * K[3] + z.v.y * K[4] + z.v.z * K[5];
+      SV z = ld6(X + X_Z + 6 * (1 - g));  // response of this foot: G^T z
+      V = V + SV{v3(dot(G[0], z), dot(G[1], z), dot(G[2], z)), v3(dot(G[3], z), dot(G[4], z), dot(G[5], z))};
     }
     sync();
   }
-  // ---- P8: contact impulse -> joint space. Up the leg chains, base response, then down the whole tree.
+  // ---- P8: contact impulse -> joint space: S^T dp on the leg chains, base response, then down the whole tree
   if (foot) {
-    SV pd = (real)-1 * P;
-    for (int k = m.chain_len[g] - 1; k >= 0; --k) {
-      int j = m.chain[g][k];
-      real* L = sm + j * LS;
-      V3 ax = HF3(axis, j), r = HF3(r, j);
-      real sd = dot(ax, pd.w);
-      L[LS_SC + 3] = sd;
-      pd = xform_force_T(ld_m3(L + LS_E), r, pd - (L[LS_SC + 2] * sd) * ld6(L + LS_U));
+    for (int k = 0; k < m.chain_len[g]; ++k) {
+      real* L = BLK(m.chain[g][k]);
+      const real* gj = L + LS_A + A_G;
+      L[LS_SC + 3] = -(gj[0] * P.w.x + gj[1] * P.w.y + gj[2] * P.w.z + gj[3] * P.v.x + gj[4] * P.v.y + gj[5] * P.v.z);
     }
-    st6(X + X_PD + 6 * g, pd);
+    st6(X + X_PD + 6 * g, (real)-1 * (P.w.x * G[0] + P.w.y * G[1] + P.w.z * G[2] + P.v.x * G[3] + P.v.y * G[4] + P.v.z * G[5]));
     if (io.live) {
       real inv_dt = 1 / dt;
 #pragma unroll
@@ -429,14 +464,14 @@ HD void env_substep(const EnvIO& io, real* sm, const float* hot, const DevModel&
   if (g == 0) {
     SV pd = sv_zero();
     for (int f = 0; f < m.num_feet; ++f) pd = pd + ld6(X + X_PD + 6 * f);
-    st6(sm + LS_V, (real)-1 * mul(ld_abi(sm + LS_A + A_OM0), pd));
+    st6(BLK(0) + LS_V, (real)-1 * mul(ld_abi(BLK(0) + LS_A + A_OM0), pd));
   }
   sync();
   for (int t = 0; t < T; ++t) {
     int i = HI(sched, t * DYROS_LANES + g);
     if (i > 0) {
-      real* L = sm + i * LS;
-      const real* Lp = sm + HI(parent, i) * LS;
+      real* L = BLK(i);
+      const real* Lp = BLK(HI(parent, i));
       int d = HI(dof, i);
       V3 ax = HF3(axis, i), r = HF3(r, i);
       SV dv = xform_motion(ld_m3(L + LS_E), r, ld6(Lp + LS_V));
@@ -447,7 +482,7 @@ HD void env_substep(const EnvIO& io, real* sm, const float* hot, const DevModel&
       real vl = HF(vel_limit, d);
       real qdn = L[LS_SC] + dqd;
       qdn = qdn > vl ? vl : (qdn < -vl ? -vl : qdn);
-      real qn = io.dof_state[2 * d] + dt * qdn;
+      real qn = L[LS_Q] + dt * qdn;
       real lo = HF(lower, d), up = HF(upper, d);
       if (qn > up) {
         qn = up;
@@ -465,7 +500,7 @@ HD void env_substep(const EnvIO& io, real* sm, const float* hot, const DevModel&
   }
   // ---- P9: base integration (lane 0)
   if (g == 0) {
-    const real* L = sm;
+    const real* L = BLK(0);
     M3 R0 = ld_m3(L + LS_E);
     SV vb = ld6(L + LS_U) + ld6(L + LS_V);
     vb.v = vb.v + ld3(L + LS_SC);

@@ -135,6 +135,43 @@ def branch_schedule(link_parent: np.ndarray, lanes: int = LANES_PER_ENV) -> np.n
     return np.array(rows, dtype=np.int32)
 
 
+def scratch_positions(sched: np.ndarray, nl: int) -> np.ndarray:
+    """Position of each link's scratch block in the physics kernel's per-env shared-memory area, chosen so that the
+    (up to) four links of every schedule slot sit at positions that differ mod 4. With an odd block size and an env
+    stride of 4 (mod 32) words, the 8 envs x 4 lanes of a warp then hit 32 different banks. Backtracking over the
+    residues; falls back to the identity when no assignment exists."""
+    lanes = sched.shape[1]
+    cap = [len(range(r, nl, 4)) for r in range(4)]
+    slot_of = {int(l): (t, g) for t, row in enumerate(sched) for g, l in enumerate(row) if l > 0}
+    links = [0] + sorted(slot_of, key=lambda l: slot_of[l])
+    res, cnt, used = {}, [0] * 4, [set() for _ in range(sched.shape[0])]
+
+    def rec(k):
+        if k == len(links):
+            return True
+        l = links[k]
+        order = [0, 1, 2, 3] if l == 0 else [slot_of[l][1] % 4] + [r for r in range(4) if r != slot_of[l][1] % 4]
+        for r in order:
+            if cnt[r] >= cap[r] or (l > 0 and r in used[slot_of[l][0]]):
+                continue
+            res[l] = r
+            cnt[r] += 1
+            if l > 0:
+                used[slot_of[l][0]].add(r)
+            if rec(k + 1):
+                return True
+            cnt[r] -= 1
+            if l > 0:
+                used[slot_of[l][0]].discard(r)
+            del res[l]
+        return False
+
+    if lanes > 4 or not rec(0):
+        return np.arange(nl, dtype=np.int32)
+    free = {r: list(range(r, nl, 4)) for r in range(4)}
+    return np.array([free[res[l]].pop(0) for l in range(nl)], dtype=np.int32)
+
+
 def build_tables(model: RobotModel, *, solver_bodies: List[str], vel_limit: float = 4.03,
                  default_damping: float = 0.0, lanes: int = LANES_PER_ENV) -> ModelTables:
     """Flatten `model`. `solver_bodies`: names of the bodies whose ground contact is constraint-solved
