@@ -29,7 +29,7 @@ extern "C" {
 #define DYROS_ABI_VERSION 1
 #define DYROS_MAX_LINKS 40
 #define DYROS_MAX_BODIES 48
-#define DYROS_LANES 4 /* lanes per env in the physics kernel (branch-parallel recursions) */
+#define DYROS_LANES 4 /* roles (warps) per env group in the physics kernel */
 
 typedef struct DyrosSim DyrosSim;   /* replaces the `sim` handle of gym.create_sim (VT:270) */
 typedef struct DyrosTask DyrosTask; /* per-env task state of DyrosDynamicWalk (T:58-195) */
@@ -61,9 +61,8 @@ typedef struct {
   const double* cyl_center;   /* [nc*3] */
   const double* cyl_axis;     /* [nc*3] */
   const double* cyl_size;     /* [nc*2] radius, half height */
-  const int32_t* sched;       /* [sched_slots*DYROS_LANES] */
-  const int32_t* link_pos;    /* [nl] scratch-block position of each link (a permutation of 0..nl-1; bank-conflict
-                                 layout, model/tables.py::scratch_positions); NULL = identity */
+  const int32_t* sched;       /* [sched_slots*DYROS_LANES] role programs: column r = links of role r, ascending, -1 padded
+                                 (model/tables.py::role_programs) */
 } DyrosModelDesc;
 
 /* gymapi.SimParams / PhysXParams subset that reaches the solver (VT:423-471, DyrosDynamicWalk.yaml:37-56)

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import native
-from .model.tables import ModelTables, scratch_positions
+from .model.tables import ModelTables, role_programs
 
 ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
 ND, NB, NA = 33, 38, 13
@@ -95,9 +95,10 @@ def make_model_desc(t: ModelTables, cfg: "CoreConfig"):
     i32 = lambda a: keep.append(np.ascontiguousarray(a, dtype=np.int32)) or keep[-1]
     md = native.DyrosModelDesc()
     md.num_links, md.num_bodies, md.num_dofs = t.num_links, t.num_bodies, t.num_dofs
-    md.num_points, md.num_cyls, md.sched_slots = len(t.pt_link), len(t.cyl_link), t.sched.shape[0]
     solver_ids = [t.body_names.index(n) for n in cfg.solver_bodies]
     pt_solver = np.isin(t.pt_body, solver_ids).astype(np.int32)
+    prog = role_programs(t.link_parent, sorted(set(int(l) for l in t.pt_link[pt_solver > 0])))
+    md.num_points, md.num_cyls, md.sched_slots = len(t.pt_link), len(t.cyl_link), prog.shape[0]
     vel_limit = np.full(t.num_dofs, cfg.dof_vel_limit)
     for name, arr, ct in [("link_parent", i32(t.link_parent), C.c_int32), ("link_dof", i32(t.link_dof), C.c_int32),
                           ("link_E", f64(t.link_E), C.c_double), ("link_r", f64(t.link_r), C.c_double),
@@ -111,8 +112,7 @@ def make_model_desc(t: ModelTables, cfg: "CoreConfig"):
                           ("pt_solver", i32(pt_solver), C.c_int32),
                           ("cyl_link", i32(t.cyl_link), C.c_int32), ("cyl_body", i32(t.cyl_body), C.c_int32),
                           ("cyl_center", f64(t.cyl_center), C.c_double), ("cyl_axis", f64(t.cyl_axis), C.c_double),
-                          ("cyl_size", f64(t.cyl_size), C.c_double), ("sched", i32(t.sched), C.c_int32),
-                          ("link_pos", i32(scratch_positions(t.sched, t.num_links)), C.c_int32)]:
+                          ("cyl_size", f64(t.cyl_size), C.c_double), ("sched", i32(prog), C.c_int32)]:
         setattr(md, name, _np_ptr(arr, ct))
     return md, keep
 

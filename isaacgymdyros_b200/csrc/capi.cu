@@ -243,7 +243,7 @@ int dyros_sim_launch_info(DyrosSim* sim, int32_t out[4]) {
   }
   out[0] = s->envs_per_block;
   out[1] = (s->p.N + s->envs_per_block - 1) / s->envs_per_block;
-  out[2] = ((s->envs_per_block * DYROS_LANES + 31) / 32) * 32;
+  out[2] = DYROS_LANES * 32;
   out[3] = (int32_t)s->phys_smem;
   return 0;
 }

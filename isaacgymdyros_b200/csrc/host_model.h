@@ -36,7 +36,7 @@ static const T* at(void* base, size_t off) {
 }
 
 struct ModelOffsets {
-  size_t parent, dof, E, r, ax, cs, ch, bs, bd, bl, bp, br, bi, lo, up, vl, ef, ps, pb, pp, pr, ys, yb, yc, ya, yz, sc, rc, po;
+  size_t parent, dof, E, r, ax, cs, ch, bs, bd, bl, bp, br, bi, lo, up, vl, ef, ps, pb, pp, pr, ys, yb, yc, ya, yz, sc, rc, ro;
 };
 
 // Fills `dm` (counts, foot tables) and appends every table to `bl`. Returns "" or an error message.
@@ -56,20 +56,24 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
     if (m->link_parent[l] < 0 || m->link_parent[l] >= l) MFAIL("link %d parent %d not topological", l, m->link_parent[l]);
     if (m->link_dof[l] < 0 || m->link_dof[l] >= nd) MFAIL("link %d dof index %d", l, m->link_dof[l]);
   }
-  {  // every link exactly once in the schedule, after its parent
-    std::vector<int> slot(nl, -1);
-    for (int t = 0; t < m->sched_slots; ++t)
-      for (int g = 0; g < DYROS_LANES; ++g) {
-        int l = m->sched[t * DYROS_LANES + g];
-        if (l < 0) continue;
-        if (l < 1 || l >= nl || slot[l] >= 0) MFAIL("bad schedule entry %d", l);
-        int p = m->link_parent[l];
-        if (!(p == 0 || (slot[p] >= 0 && slot[p] < t))) MFAIL("schedule runs link %d before its parent", l);
-        slot[l] = t;
-      }
-    for (int l = 1; l < nl; ++l)
-      if (slot[l] < 0) MFAIL("link %d missing from the schedule", l);
+  // `sched` holds the role programs (model/tables.py::role_programs): column r = links of role r in ascending
+  // (topological) order, every link exactly once.
+  std::vector<int> role_of(nl, -1);
+  int role_len[DYROS_LANES] = {0};
+  for (int g = 0; g < DYROS_LANES; ++g) {
+    int prev = 0;
+    for (int t = 0; t < m->sched_slots; ++t) {
+      int l = m->sched[t * DYROS_LANES + g];
+      if (l < 0) continue;
+      if (l < 1 || l >= nl || role_of[l] >= 0) MFAIL("bad role program entry %d", l);
+      if (l <= prev || role_len[g] != t) MFAIL("role %d is not a dense ascending list at row %d", g, t);
+      prev = l;
+      role_of[l] = g;
+      role_len[g] = t + 1;
+    }
   }
+  for (int l = 1; l < nl; ++l)
+    if (role_of[l] < 0) MFAIL("link %d missing from the role programs", l);
   // ---- derived tables
   std::vector<int> child_start(nl + 1, 0), children;
   for (int l = 0; l < nl; ++l) {
@@ -151,6 +155,25 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
     dm.chain_len[f] = (int)path.size();
     for (int k = 0; k < (int)path.size(); ++k) dm.chain[f][k] = path[path.size() - 1 - k];
   }
+  for (int f = 0; f < dm.num_feet; ++f) {
+    dm.foot_role[f] = role_of[dm.foot_link[f]];
+    for (int k = 0; k < dm.chain_len[f]; ++k)
+      if (role_of[dm.chain[f][k]] != dm.foot_role[f]) MFAIL("leg chain of solver link %d is split between roles", dm.foot_link[f]);
+    for (int f2 = 0; f2 < f; ++f2)
+      if (dm.foot_role[f2] == dm.foot_role[f]) MFAIL("two solver links share role %d", dm.foot_role[f]);
+  }
+  {  // the base is handled by the least loaded role that has no foot
+    int best = -1;
+    for (int g = 0; g < DYROS_LANES; ++g) {
+      bool is_foot = false;
+      for (int f = 0; f < dm.num_feet; ++f) is_foot |= dm.foot_role[f] == g;
+      if (!is_foot && (best < 0 || role_len[g] < role_len[best])) best = g;
+    }
+    if (best < 0) best = 0;
+    dm.base_role = best;
+    role_of[0] = best;
+    for (int g = 0; g < DYROS_LANES; ++g) dm.role_len[g] = role_len[g];
+  }
   if (dm.num_feet == 2) {  // the two chains must only share the base (block-Jacobi coupling goes through the base)
     for (int a = 0; a < dm.chain_len[0]; ++a)
       for (int c = 0; c < dm.chain_len[1]; ++c)
@@ -181,15 +204,7 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
   o.ps = bl.add_i(pt_start.data(), nl + 1); o.ys = bl.add_i(cyl_start.data(), nl + 1);
   o.sc = bl.add_i(m->sched, (size_t)m->sched_slots * DYROS_LANES);
   o.rc = bl.add_f32(reach.data(), nl);
-  std::vector<int> pos(nl);
-  {
-    std::vector<int> seen(nl, 0);
-    for (int l = 0; l < nl; ++l) {
-      pos[l] = m->link_pos ? m->link_pos[l] : l;
-      if (pos[l] < 0 || pos[l] >= nl || seen[pos[l]]++) MFAIL("link_pos is not a permutation of 0..%d", nl - 1);
-    }
-  }
-  o.po = bl.add_i(pos.data(), nl);
+  o.ro = bl.add_i(role_of.data(), nl);
   dm.hot_bytes = (int)((bl.host.size() + 15) & ~size_t(15));
   // cold tables (global memory, read only when a link is near the ground or for rigid_body_state)
   o.bl = bl.add_i(m->body_link, nb); o.bp = bl.add_f(m->body_pos, nb * 3); o.br = bl.add_f(m->body_rot, nb * 9);
@@ -205,7 +220,7 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
   dm.o_body_start = (int)(o.bs / 4); dm.o_bodies = (int)(o.bd / 4); dm.o_body_inertia = (int)(o.bi / 4);
   dm.o_lower = (int)(o.lo / 4); dm.o_upper = (int)(o.up / 4); dm.o_vel_limit = (int)(o.vl / 4);
   dm.o_effort = (int)(o.ef / 4); dm.o_pt_start = (int)(o.ps / 4); dm.o_cyl_start = (int)(o.ys / 4);
-  dm.o_sched = (int)(o.sc / 4); dm.o_reach = (int)(o.rc / 4); dm.o_pos = (int)(o.po / 4);
+  dm.o_sched = (int)(o.sc / 4); dm.o_reach = (int)(o.rc / 4); dm.o_role_of = (int)(o.ro / 4);
 
   return std::string();
 #undef MFAIL

@@ -48,7 +48,8 @@ struct DevModel {
   int hot_bytes;
   // word offsets of the hot tables inside the staged prefix (same order as the pointers above)
   int o_parent, o_dof, o_E, o_r, o_axis, o_child_start, o_children, o_body_start, o_bodies, o_body_inertia, o_lower,
-      o_upper, o_vel_limit, o_effort, o_pt_start, o_cyl_start, o_sched, o_reach, o_pos;
+      o_upper, o_vel_limit, o_effort, o_pt_start, o_cyl_start, o_sched, o_reach, o_role_of;
+  int base_role, foot_role[MAX_FEET], role_len[DYROS_LANES];
   int num_feet;
   int foot_link[MAX_FEET];
   int chain_len[MAX_FEET];

@@ -1,31 +1,74 @@
-// K1: gym.simulate as one kernel launch. DYROS_LANES lanes per env (branch-parallel recursions over the link
-// tree), envs_per_block envs per CTA sized so that one CTA per SM covers N = 4096 on 148 SMs in a single wave;
-// the per-env scratch of physics_core.cuh lives in dynamic shared memory.
-#include "physics_core.cuh"
+// K1: gym.simulate as one kernel launch, warp-specialised: one warp per role (physics_roles.cuh), lane = env, up to 32
+// envs per CTA (28 for N = 4096, so that one CTA per SM covers the shard in a single wave); the per-env scratch
+// blocks, the hot model tables and the dataflow flags live in dynamic shared memory.
+#include "physics_roles.cuh"
 #include "task_stages.cuh"
 
 namespace dyros {
 
-struct WarpSync {
-  __device__ __forceinline__ void operator()() const { __syncwarp(); }
+__device__ __forceinline__ int ld_acquire_shared(const int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_shared(int* p, int v) {
+  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
+// Flags between role warps: the producer's lanes finish their shared-memory writes, lane 0 publishes with release;
+// the consumer's lane 0 spins with acquire, then the warp re-converges.
+struct RoleSync {
+  int lane;
+  __device__ __forceinline__ void signal(int* f, int v) const {
+    __syncwarp();
+    if (lane == 0) st_release_shared(f, v);
+  }
+  __device__ __forceinline__ void wait(const int* f, int v) const {
+    if (lane == 0)
+      while (ld_acquire_shared(f) < v) {
+      }
+    __syncwarp();
+  }
+};
+struct CtaSync {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
 
 constexpr int kMaxPhysSmem = 227 * 1024;
+constexpr int kPhysThreads = DYROS_LANES * 32;
 
-__global__ void __launch_bounds__(128) k_simulate(DevModel m, SimParams p, DyrosSimBuffers b, const float* __restrict__ push,
-                                                  int apply_wrench, int epb, int es) {
-  extern __shared__ __align__(16) float smem[];
-  // stage the hot model tables (link tree, inertias, schedule) once per CTA
+struct PhysCta {
+  const float* hot;
+  int* flags;
+  real* sm;     // this lane's env scratch block
+  int role, lane, e;
+  bool live;
+};
+
+// Common prologue of the physics kernels: stage the hot tables, clear the flags, locate the lane's env.
+__device__ __forceinline__ PhysCta phys_cta_setup(const DevModel& m, const SimParams& p, float* smem, int epb, int es) {
   {
     const float4* src = reinterpret_cast<const float4*>(m.blob);
     float4* dst = reinterpret_cast<float4*>(smem);
     for (int i = threadIdx.x; i < m.hot_bytes / 16; i += blockDim.x) dst[i] = src[i];
   }
+  int* flags = reinterpret_cast<int*>(smem + m.hot_bytes / 4);
+  for (int i = threadIdx.x; i < F_COUNT; i += blockDim.x) flags[i] = 0;
   __syncthreads();
-  const float* hot = smem;
-  const int le = threadIdx.x / DYROS_LANES, g = threadIdx.x % DYROS_LANES;
-  const int e = blockIdx.x * epb + le;
-  if (le >= epb || e >= p.N) return;  // whole lane groups leave together: every later sync is inside one group
+  PhysCta c;
+  c.hot = smem;
+  c.flags = flags;
+  c.role = threadIdx.x >> 5;
+  c.lane = threadIdx.x & 31;
+  const int le = c.lane < epb ? c.lane : epb - 1;  // padding lanes shadow the last env (same values, no global writes)
+  int e = blockIdx.x * epb + le;
+  c.live = c.lane < epb && e < p.N;
+  c.e = e < p.N ? e : p.N - 1;
+  c.sm = smem + m.hot_bytes / 4 + ((F_COUNT + 3) & ~3) + (size_t)le * es;
+  return c;
+}
+
+__device__ __forceinline__ EnvIO env_io(const DevModel& m, const DyrosSimBuffers& b, int e, bool live) {
   EnvIO io;
   io.root = b.root_states + (size_t)e * 13;
   io.dof_state = b.dof_state + (size_t)e * m.nd * 2;
@@ -34,14 +77,27 @@ __global__ void __launch_bounds__(128) k_simulate(DevModel m, SimParams p, Dyros
   io.armature = b.dof_armature + (size_t)e * m.nd;
   io.mass_scale = b.body_mass_scale + (size_t)e * m.nb;
   io.contact = b.net_contact_force + (size_t)e * m.nb * 3;
-  io.push = push ? push + (size_t)e * 3 : nullptr;
-  io.rb_force = apply_wrench ? b.rb_force + (size_t)e * m.nb * 3 : nullptr;
-  io.rb_torque = apply_wrench ? b.rb_torque + (size_t)e * m.nb * 3 : nullptr;
-  io.live = true;
-  WarpSync sync;
-  real* sm = smem + m.hot_bytes / 4 + (size_t)le * es;
+  io.push = nullptr;
+  io.rb_force = nullptr;
+  io.rb_torque = nullptr;
+  io.live = live;
+  return io;
+}
+
+__global__ void __launch_bounds__(kPhysThreads) k_simulate(DevModel m, SimParams p, DyrosSimBuffers b, const float* __restrict__ push,
+                                                           int apply_wrench, int epb, int es) {
+  extern __shared__ __align__(16) float smem[];
+  PhysCta c = phys_cta_setup(m, p, smem, epb, es);
+  EnvIO io = env_io(m, b, c.e, c.live);
+  io.push = push ? push + (size_t)c.e * 3 : nullptr;
+  io.rb_force = apply_wrench ? b.rb_force + (size_t)c.e * m.nb * 3 : nullptr;
+  io.rb_torque = apply_wrench ? b.rb_torque + (size_t)c.e * m.nb * 3 : nullptr;
+  RoleSync sync{c.lane};
   for (int s = 0; s < p.substeps; ++s) {
-    env_substep(io, sm, hot, m, p, g, sync);
+    env_stage_inputs(io, c.sm, c.hot, m, p, c.role, DYROS_LANES);
+    __syncthreads();
+    env_substep_role(io, c.sm, c.flags, s, c.hot, m, p, c.role, sync);
+    __syncthreads();
     io.push = nullptr;  // applied wrenches act "for the immediate timestep" (gym_py.html apply_rigid_body_force_tensors)
     io.rb_force = nullptr;
     io.rb_torque = nullptr;
@@ -50,57 +106,44 @@ __global__ void __launch_bounds__(128) k_simulate(DevModel m, SimParams p, Dyros
 
 // The physics part of one policy step in ONE launch: skipframe x (PD + delay torque, gym.simulate, sensor noise),
 // i.e. the loop body of T:504-530 with the three gym calls of T:520-526 folded in.
-__global__ void __launch_bounds__(128) k_step_physics(DevModel m, SimParams p, TK k, int epb, int es) {
+__global__ void __launch_bounds__(kPhysThreads) k_step_physics(DevModel m, SimParams p, TK k, int epb, int es) {
   extern __shared__ __align__(16) float smem[];
-  {
-    const float4* src = reinterpret_cast<const float4*>(m.blob);
-    float4* dst = reinterpret_cast<float4*>(smem);
-    for (int i = threadIdx.x; i < m.hot_bytes / 16; i += blockDim.x) dst[i] = src[i];
-  }
-  __syncthreads();
-  const float* hot = smem;
-  const int le = threadIdx.x / DYROS_LANES, g = threadIdx.x % DYROS_LANES;
-  const int e = blockIdx.x * epb + le;
-  if (le >= epb || e >= p.N) return;
-  const DyrosSimBuffers& b = k.s;
-  EnvIO io;
-  io.root = b.root_states + (size_t)e * 13;
-  io.dof_state = b.dof_state + (size_t)e * m.nd * 2;
-  io.tau = b.dof_actuation_force + (size_t)e * m.nd;
-  io.damping = b.dof_damping + (size_t)e * m.nd;
-  io.armature = b.dof_armature + (size_t)e * m.nd;
-  io.mass_scale = b.body_mass_scale + (size_t)e * m.nb;
-  io.contact = b.net_contact_force + (size_t)e * m.nb * 3;
-  io.rb_force = nullptr;
-  io.rb_torque = nullptr;
-  io.live = true;
-  WarpSync sync;
-  real* sm = smem + m.hot_bytes / 4 + (size_t)le * es;
+  PhysCta c = phys_cta_setup(m, p, smem, epb, es);
+  EnvIO io = env_io(m, k.s, c.e, c.live);
+  RoleSync sync{c.lane};
+  CtaSync cta;
+  int epoch = 0;
   for (int s = 0; s < k.p.skipframe; ++s) {
-    stage_substep_torque<DYROS_LANES>(k, e, g, sync);
-    sync();
-    io.push = s == 0 ? k.b.push_force + (size_t)e * 3 : nullptr;  // the push acts on the first sub-step only (T:502 vs T:504)
+    stage_substep_torque<DYROS_LANES>(k, c.e, c.role, cta, c.live);
+    __syncthreads();
+    io.push = s == 0 ? k.b.push_force + (size_t)c.e * 3 : nullptr;  // the push acts on the first sub-step only (T:502 vs T:504)
     for (int ss = 0; ss < p.substeps; ++ss) {
-      env_substep(io, sm, hot, m, p, g, sync);
+      env_stage_inputs(io, c.sm, c.hot, m, p, c.role, DYROS_LANES);
+      __syncthreads();
+      env_substep_role(io, c.sm, c.flags, epoch++, c.hot, m, p, c.role, sync);
+      __syncthreads();
       io.push = nullptr;
     }
-    stage_sensor_noise<DYROS_LANES>(k, s, e, g);
-    sync();
+    stage_sensor_noise<DYROS_LANES>(k, s, c.e, c.role, c.live);
+    __syncthreads();
   }
 }
 
+static size_t phys_smem_bytes(const Sim* sim, int epb) {
+  return (size_t)sim->m.hot_bytes + (((F_COUNT + 3) & ~3) + (size_t)epb * env_scratch_floats(sim->m.nl)) * sizeof(float);
+}
+
 int physics_configure(Sim* sim) {
-  const int es = env_scratch_floats(sim->m.nl);
-  const int max_epb = std::min((kMaxPhysSmem - sim->m.hot_bytes) / (es * (int)sizeof(float)), 128 / DYROS_LANES);
-  if (max_epb < 1) {
-    set_error("physics_configure: one env needs %d bytes of shared memory", es * (int)sizeof(float));
-    return 1;
-  }
   int epb = (sim->p.N + sim->sm_count - 1) / sim->sm_count;  // one wave when it fits
   epb = std::max(epb, 8);
-  epb = std::min(epb, max_epb);
+  epb = std::min(epb, 32);
+  while (epb > 1 && phys_smem_bytes(sim, epb) > (size_t)kMaxPhysSmem) --epb;
+  if (phys_smem_bytes(sim, epb) > (size_t)kMaxPhysSmem) {
+    set_error("physics_configure: one env needs %zu bytes of shared memory", phys_smem_bytes(sim, 1));
+    return 1;
+  }
   sim->envs_per_block = epb;
-  sim->phys_smem = (size_t)sim->m.hot_bytes + (size_t)epb * es * sizeof(float);
+  sim->phys_smem = phys_smem_bytes(sim, epb);
   DY_CUDA(cudaFuncSetAttribute(k_simulate, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPhysSmem));
   DY_CUDA(cudaFuncSetAttribute(k_step_physics, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxPhysSmem));
   return 0;
@@ -109,8 +152,7 @@ int physics_configure(Sim* sim) {
 int launch_simulate(Sim* sim, int apply_wrench, const float* push, cudaStream_t s) {
   const int epb = sim->envs_per_block;
   const int grid = (sim->p.N + epb - 1) / epb;
-  const int threads = ((epb * DYROS_LANES + 31) / 32) * 32;
-  k_simulate<<<grid, threads, sim->phys_smem, s>>>(sim->m, sim->p, sim->b, push, apply_wrench, epb,
+  k_simulate<<<grid, kPhysThreads, sim->phys_smem, s>>>(sim->m, sim->p, sim->b, push, apply_wrench, epb,
                                                    env_scratch_floats(sim->m.nl));
   DY_LAUNCH_CHECK();
   return 0;
@@ -120,13 +162,12 @@ int launch_task_physics(Task* t, cudaStream_t s) {
   Sim* sim = t->sim;
   const int epb = sim->envs_per_block;
   const int grid = (sim->p.N + epb - 1) / epb;
-  const int threads = ((epb * DYROS_LANES + 31) / 32) * 32;
   TK k;
   k.p = t->p;
   k.b = t->b;
   k.s = sim->b;
   k.j = t->inj;
-  k_step_physics<<<grid, threads, sim->phys_smem, s>>>(sim->m, sim->p, k, epb, env_scratch_floats(sim->m.nl));
+  k_step_physics<<<grid, kPhysThreads, sim->phys_smem, s>>>(sim->m, sim->p, k, epb, env_scratch_floats(sim->m.nl));
   DY_LAUNCH_CHECK();
   return 0;
 }

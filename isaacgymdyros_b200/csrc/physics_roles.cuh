@@ -1,0 +1,577 @@
+// One sub-step of gym.simulate, written as the program of ONE ROLE acting on ONE env.
+//
+// Replaces the body of `gym.simulate` (reference call site tasks/dyros_dynamic_walk.py:525; the reference's
+// implementation is closed-source PhysX) for a floating-base tree of revolute joints: articulated-body
+// forward dynamics (Featherstone ABA) with implicit joint damping and rotor inertia, penalty ground contact for all
+// collision primitives except the sole corners, and a fixed-sweep projected Gauss-Seidel solve of the sole-corner
+// contacts in the 6-D space of each foot link using the exact articulated inverse inertia (O(n) recursion up the
+// leg chains). The model and every formula are stated independently (dense, fp64) in oracle/physics_oracle.py;
+// see DESIGN.md section 4.
+//
+// Parallel decomposition (GPU): the link tree is cut into DYROS_LANES "roles" (model/tables.py::role_programs: torso
+// + left arm, head + right arm (+ base), left leg, right leg for TOCABI). A CTA holds one warp per role; lane = env,
+// so a warp runs the same link operation on up to 32 envs (no divergence, warp-uniform table reads). Roles exchange
+// per-link results through the env's scratch block in shared memory and order themselves with per-link stage flags
+// (release/acquire on shared memory): a role only ever waits for what it actually consumes, so the legs run their
+// three tree passes and the whole contact stage while the arm roles are still in theirs.
+// The same source is compiled for the host by tests/native/hostemu.cu (one thread per role, atomics for the flags).
+#pragma once
+#include "internal.h"
+#include "phys_math.cuh"
+
+namespace dyros {
+
+// per-link scratch block (floats) of one env
+constexpr int LS_E = 0;    // 9  parent->link rotation (base: base->world rotation)
+constexpr int LS_V = 9;    // 6  link velocity, later the impulse response dv
+constexpr int LS_A = 15;   // 27 pass1: pA(6) world pose(12) | pass2: contribution to parent IA(21) pA(6) |
+                           //    pass3: a'(6); leg-chain links then also hold contact rows (14)
+constexpr int LS_U = 42;   // 6  U = IA S (base: predicted velocity v0*)
+constexpr int LS_SC = 48;  // 4  [qd -> qd*, tau -> u, damping -> 1/D, armature -> S^T dp]
+constexpr int LS_Q = 52;   // 1  joint angle
+constexpr int LS = 53;
+constexpr int A_PA = 0, A_POSE = 6, A_CIA = 0, A_CPA = 21, A_ACC = 0, A_OM0 = 6, A_ROWS = 6;
+constexpr int ROWS_PER_LINK = 2;  // contact rows (7 floats each) parked in one leg-chain link's block
+// per-env extra scratch
+constexpr int X_FOOTPOSE = 0;                        // MAX_FEET * 12
+constexpr int X_Z = X_FOOTPOSE + MAX_FEET * 12;      // 2 (double buffer) * MAX_FEET * 6: base velocity change of a sweep
+constexpr int X_PD = X_Z + 2 * MAX_FEET * 6;         // MAX_FEET * 6  impulse arriving at the base from a foot
+constexpr int X_G = X_PD + MAX_FEET * 6;             // MAX_FEET * MAX_CHAIN * 6  g_j = S_j^T G_j of the leg-chain links
+constexpr int X_MASS = X_G + MAX_FEET * MAX_CHAIN * 6;  // DYROS_MAX_BODIES per-body mass scale
+constexpr int X_SIZE = X_MASS + DYROS_MAX_BODIES;
+
+HD int env_scratch_floats(int nl) {
+  int n = nl * LS + X_SIZE;
+  return n | 1;  // odd stride: the 32 envs of a warp touch 32 different banks for any field
+}
+
+// CTA-wide flags (ints): stage reached by each link, plus the hand-shakes of the contact stage
+constexpr int F_LINK = 0;                         // [DYROS_MAX_LINKS]
+constexpr int F_Z = DYROS_MAX_LINKS;              // [MAX_FEET] sweeps published
+constexpr int F_PD = F_Z + MAX_FEET;              // [MAX_FEET] base impulse published
+constexpr int F_COUNT = F_PD + MAX_FEET;
+constexpr int ST_PASS1 = 1, ST_PASS2 = 2, ST_PASS3 = 3, ST_DOWN = 4, ST_STRIDE = 8;
+
+// The hot model tables are read from the staged copy `hot` (shared memory on the GPU) through word offsets.
+#define HI(field, idx) (reinterpret_cast<const int*>(hot)[m.o_##field + (idx)])
+#define HF(field, idx) (hot[m.o_##field + (idx)])
+#define HF3(field, idx) ld3_f(hot + m.o_##field + 3 * (idx))
+#define BLK(link) (sm + (link) * LS)
+
+// global-memory views of one env (all device pointers on the GPU, host pointers in the emulation)
+struct EnvIO {
+  float* root;             // 13
+  float* dof_state;        // nd*2
+  const float* tau;        // nd
+  const float* damping;    // nd
+  const float* armature;   // nd
+  const float* mass_scale; // nb
+  float* contact;          // nb*3
+  const float* push;       // 3 or NULL
+  const float* rb_force;   // nb*3 or NULL
+  const float* rb_torque;  // nb*3 or NULL
+  bool live;               // false: padding lane, no global writes
+};
+
+// ---- penalty ground contact of one location on a link (oracle: PhysicsOracle._external_wrench.add_point)
+HD void penalty_point(const SimParams& p, const M3& Rw, SV v, V3 xs, real depth, float* cf, bool live, SV& fext) {
+  if (!(depth > 0)) return;
+  V3 vel_w = mul(Rw, v.v + cross(v.w, xs));
+  real fn = p.pen_k * depth - p.pen_c * vel_w.z;
+  fn = fn < 0 ? 0 : (fn > p.pen_fmax ? p.pen_fmax : fn);
+  real speed = sqrt(vel_w.x * vel_w.x + vel_w.y * vel_w.y);
+  real lim = p.mu * fn / (speed > (real)1e-6 ? speed : (real)1e-6);
+  real coef = p.pen_c < lim ? p.pen_c : lim;
+  V3 Fw = v3(-coef * vel_w.x, -coef * vel_w.y, fn);
+  if (live) {
+    cf[0] += (float)Fw.x;
+    cf[1] += (float)Fw.y;
+    cf[2] += (float)Fw.z;
+  }
+  V3 fl = mulT(Rw, Fw);
+  fext.w = fext.w + cross(xs, fl);
+  fext.v = fext.v + fl;
+}
+
+// Rigid inertia of link i from the hot body table and the env's per-body mass scales (X_MASS).
+HD ABI link_inertia(const real* X, const float* hot, const DevModel& m, int i) {
+  real par[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) par[k] = 0;
+  for (int bi = HI(body_start, i); bi < HI(body_start, i + 1); ++bi) {
+    int b = HI(bodies, bi);
+    real sc = X[X_MASS + b];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) par[k] += sc * HF(body_inertia, b * 10 + k);
+  }
+  return abi_rigid(par[0], v3(par[1], par[2], par[3]), S3{par[4], par[5], par[6], par[7], par[8], par[9]});
+}
+
+// Bias force and external wrench of link i (pass 1). Writes A_PA.
+HD void link_forces(const EnvIO& io, real* L, const real* X, const float* hot, const DevModel& m, const SimParams& p, int i,
+                    const M3& Rw, V3 pw, SV v) {
+  SV fext = sv_zero();
+  V3 nrm = v3(Rw.a[6], Rw.a[7], Rw.a[8]);  // world z in link coordinates
+  for (int bi = HI(body_start, i); bi < HI(body_start, i + 1); ++bi) {
+    int b = HI(bodies, bi);
+    if (io.live) {
+      io.contact[3 * b] = 0.f;
+      io.contact[3 * b + 1] = 0.f;
+      io.contact[3 * b + 2] = 0.f;
+    }
+    bool has_push = io.push && b == 0;
+    if (has_push || io.rb_force) {  // world wrench at the body's centre of mass (tensors.rst.txt:322-335)
+      V3 F = v3(0, 0, 0), T = v3(0, 0, 0);
+      if (has_push) F = ld3_f(io.push);
+      if (io.rb_force) {
+        F = F + ld3_f(io.rb_force + 3 * b);
+        T = ld3_f(io.rb_torque + 3 * b);
+      }
+      real sc = X[X_MASS + b];
+      real mb = sc * HF(body_inertia, b * 10);
+      real inv = 1 / (mb > (real)1e-30 ? mb : (real)1e-30);
+      V3 com = v3(sc * HF(body_inertia, b * 10 + 1) * inv, sc * HF(body_inertia, b * 10 + 2) * inv,
+                  sc * HF(body_inertia, b * 10 + 3) * inv);
+      V3 fl = mulT(Rw, F);
+      fext.w = fext.w + cross(com, fl) + mulT(Rw, T);
+      fext.v = fext.v + fl;
+    }
+  }
+  if (pw.z < HF(reach, i)) {  // nothing of this link can reach z = 0 otherwise
+    for (int k = HI(pt_start, i); k < HI(pt_start, i + 1); ++k) {
+      V3 x = ld3_f(m.pt_pos + 3 * k);
+      real rad = m.pt_radius[k];
+      real z = pw.z + dot(nrm, x);
+      penalty_point(p, Rw, v, x - rad * nrm, rad - z, io.contact + 3 * m.pt_body[k], io.live, fext);
+    }
+    for (int k = HI(cyl_start, i); k < HI(cyl_start, i + 1); ++k) {
+      V3 c = ld3_f(m.cyl_center + 3 * k), a = ld3_f(m.cyl_axis + 3 * k);
+      real rad = m.cyl_size[2 * k], hh = m.cyl_size[2 * k + 1];
+      real az = dot(nrm, a);
+      real s = az >= 0 ? (real)-1 : (real)1;
+      V3 d = neg(nrm - az * a);
+      real dn = sqrt(dot(d, d));
+      V3 rim = c + (s * hh) * a;
+      if (dn > (real)1e-6) rim = rim + (rad / dn) * d;
+      real z = pw.z + dot(nrm, rim);
+      penalty_point(p, Rw, v, rim, -z, io.contact + 3 * m.cyl_body[k], io.live, fext);
+    }
+  }
+  SV pA = crf(v, mul(link_inertia(X, hot, m, i), v)) - fext;
+  st6(L + LS_A + A_PA, pA);
+}
+
+// Inputs of one env -> its scratch block: thread `tid` of `nthreads` cooperating threads (P0).
+HD void env_stage_inputs(const EnvIO& io, real* sm, const float* hot, const DevModel& m, const SimParams& p, int tid, int nthreads) {
+  real* X = sm + m.nl * LS;
+  for (int b = tid; b < m.nb; b += nthreads) X[X_MASS + b] = io.mass_scale[b];
+  for (int i = 1 + tid; i < m.nl; i += nthreads) {
+    int d = HI(dof, i);
+    real* L = BLK(i);
+    real tq = io.tau[d];
+    if (p.clamp_effort) {
+      real lim = HF(effort, d);
+      tq = tq > lim ? lim : (tq < -lim ? -lim : tq);
+    }
+    L[LS_Q] = io.dof_state[2 * d];
+    L[LS_SC + 0] = io.dof_state[2 * d + 1];
+    L[LS_SC + 1] = tq;
+    L[LS_SC + 2] = io.damping[d];
+    L[LS_SC + 3] = io.armature[d];
+  }
+}
+
+// One sub-step for role `role` of one env. `flags`: the CTA-wide stage flags; `epoch`: sub-steps done so far in this
+// launch (the flags are monotonic). The env's inputs must have been staged (env_stage_inputs) and made visible.
+template <class Sync>
+HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const float* hot, const DevModel& m,
+                         const SimParams& p, int role, Sync& sync) {
+  const int nl = m.nl;
+  real* X = sm + nl * LS;
+  const real dt = p.dt;
+  const int base = epoch * ST_STRIDE;
+  const int len = m.role_len[role];
+  const bool base_role = role == m.base_role;
+  int* fl = flags + F_LINK;
+
+  // ---- pass 1, root -> leaves: transforms, velocities, world poses, bias forces
+  if (base_role) {
+    real* L = BLK(0);
+    V3 pw = ld3_f(io.root);
+    M3 R0 = quat_to_mat(io.root[3], io.root[4], io.root[5], io.root[6]);
+    SV v0{mulT(R0, ld3_f(io.root + 10)), mulT(R0, ld3_f(io.root + 7))};
+    st_m3(L + LS_E, R0);
+    st6(L + LS_V, v0);
+    st_m3(L + LS_A + A_POSE, R0);
+    st3(L + LS_A + A_POSE + 9, pw);
+    link_forces(io, L, X, hot, m, p, 0, R0, pw, v0);
+    sync.signal(fl + 0, base + ST_PASS1);
+  }
+  for (int k = 0; k < len; ++k) {
+    const int i = HI(sched, k * DYROS_LANES + role);
+    const int par = HI(parent, i);
+    if (HI(role_of, par) != role) sync.wait(fl + par, base + ST_PASS1);
+    real* L = BLK(i);
+    const real* Lp = BLK(par);
+    real q = L[LS_Q], qd = L[LS_SC];
+    V3 ax = HF3(axis, i), r = HF3(r, i);
+    M3 E = mul(axis_rot_T(ax, sin(q), cos(q)), ld_m3_f(hot + m.o_E + 9 * i));
+    SV v = xform_motion(E, r, ld6(Lp + LS_V));
+    v.w = v.w + qd * ax;
+    M3 Rwp = ld_m3(Lp + LS_A + A_POSE);
+    M3 Rw = mulABt(Rwp, E);
+    V3 pw = ld3(Lp + LS_A + A_POSE + 9) + mul(Rwp, r);
+    st_m3(L + LS_E, E);
+    st6(L + LS_V, v);
+    st_m3(L + LS_A + A_POSE, Rw);
+    st3(L + LS_A + A_POSE + 9, pw);
+    for (int f = 0; f < m.num_feet; ++f)
+      if (m.foot_link[f] == i) {
+        st_m3(X + X_FOOTPOSE + 12 * f, Rw);
+        st3(X + X_FOOTPOSE + 12 * f + 9, pw);
+      }
+    link_forces(io, L, X, hot, m, p, i, Rw, pw, v);
+    sync.signal(fl + i, base + ST_PASS1);
+  }
+  // Pass 2 overwrites A (pose) of a link with its contribution to the parent: every child of this role's links that
+  // lives in another role must have read its parent's pose first.
+  for (int k = 0; k < len; ++k) {
+    const int i = HI(sched, k * DYROS_LANES + role);
+    for (int ci = HI(child_start, i); ci < HI(child_start, i + 1); ++ci) {
+      const int c = HI(children, ci);
+      if (HI(role_of, c) != role) sync.wait(fl + c, base + ST_PASS1);
+    }
+  }
+  // ---- pass 2, leaves -> root: articulated inertias and bias forces
+  for (int k = len - 1; k >= 0; --k) {
+    const int i = HI(sched, k * DYROS_LANES + role);
+    real* L = BLK(i);
+    real* A = L + LS_A;
+    ABI IA = link_inertia(X, hot, m, i);
+    SV pA = ld6(A + A_PA);
+    for (int ci = HI(child_start, i); ci < HI(child_start, i + 1); ++ci) {
+      const int c = HI(children, ci);
+      if (HI(role_of, c) != role) sync.wait(fl + c, base + ST_PASS2);
+      const real* Ac = BLK(c) + LS_A;
+      IA = IA + ld_abi(Ac + A_CIA);
+      pA = pA + ld6(Ac + A_CPA);
+    }
+    V3 ax = HF3(axis, i), r = HF3(r, i);
+    M3 E = ld_m3(L + LS_E);
+    SV v = ld6(L + LS_V);
+    real qd = L[LS_SC], tq = L[LS_SC + 1], damp = L[LS_SC + 2], arm = L[LS_SC + 3];
+    SV U{mul(IA.I, ax), mulT(IA.H, ax)};
+    real D = dot(ax, U.w) + arm + dt * damp;
+    real Dinv = 1 / D;
+    real u = tq - damp * qd - dot(ax, pA.w);
+    V3 aq = qd * ax;
+    SV c{cross(v.w, aq), cross(v.v, aq)};
+    ABI Ia = rank1_sub(IA, U, Dinv);
+    SV pa = pA + mul(Ia, c) + (Dinv * u) * U;
+    st_abi(A + A_CIA, abi_to_parent(E, r, Ia));
+    st6(A + A_CPA, xform_force_T(E, r, pa));
+    st6(L + LS_U, U);
+    L[LS_SC + 1] = u;
+    L[LS_SC + 2] = Dinv;
+    L[LS_SC + 3] = 0;
+    sync.signal(fl + i, base + ST_PASS2);
+  }
+  // ---- floating base (base role): inverse articulated inertia, base acceleration, predicted base velocity
+  if (base_role) {
+    real* L = BLK(0);
+    real* A = L + LS_A;
+    ABI IA = link_inertia(X, hot, m, 0);
+    SV pA = ld6(A + A_PA);
+    for (int ci = HI(child_start, 0); ci < HI(child_start, 1); ++ci) {
+      const int c = HI(children, ci);
+      if (HI(role_of, c) != role) sync.wait(fl + c, base + ST_PASS2);
+      const real* Ac = BLK(c) + LS_A;
+      IA = IA + ld_abi(Ac + A_CIA);
+      pA = pA + ld6(Ac + A_CPA);
+    }
+    real f[36];
+    abi_to_full(IA, f);
+    spd6_inverse(f);
+    ABI Om0 = abi_from_full(f);
+    SV a0 = (real)-1 * mul(Om0, pA);  // acceleration relative to the gravity field
+    M3 R0 = ld_m3(L + LS_E);
+    SV v0 = ld6(L + LS_V);
+    st6(A + A_ACC, a0);
+    st_abi(A + A_OM0, Om0);
+    V3 gl = mulT(R0, v3(p.g[0], p.g[1], p.g[2]));
+    SV vs{v0.w + dt * a0.w, v0.v + dt * (a0.v + gl)};
+    st6(L + LS_U, vs);
+    st3(L + LS_SC, dt * cross(v0.w, v0.v));  // rotating-frame term of the world-frame linear velocity update
+    sync.signal(fl + 0, base + ST_PASS2);
+  }
+  // ---- feet, part 1 (needs pass 2 of the own leg chain only): up the chain, G = map foot force -> force on the
+  //      current link; Om = sum_j g_j g_j^T / D_j with g_j = S_j^T G_j (kept per chain link for the impulse pass)
+  int foot = -1;
+  for (int f = 0; f < m.num_feet; ++f)
+    if (m.foot_role[f] == role) foot = f;
+  SV G[6];              // columns: force arriving at the base per unit foot force
+  ABI Om;               // inverse inertia seen at the foot link
+  if (foot >= 0) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) G[c] = sv_zero();
+    G[0].w.x = 1; G[1].w.y = 1; G[2].w.z = 1; G[3].v.x = 1; G[4].v.y = 1; G[5].v.z = 1;
+    Om.I = S3{0, 0, 0, 0, 0, 0};
+    Om.M = S3{0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 9; ++c) Om.H.a[c] = 0;
+    for (int k = m.chain_len[foot] - 1; k >= 0; --k) {
+      int j = m.chain[foot][k];
+      real* L = BLK(j);
+      V3 ax = HF3(axis, j), r = HF3(r, j);
+      M3 E = ld_m3(L + LS_E);
+      real Dinv = L[LS_SC + 2];
+      SV U = ld6(L + LS_U);
+      real gj[6];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) gj[c] = dot(ax, G[c].w);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) X[X_G + (foot * MAX_CHAIN + k) * 6 + c] = gj[c];  // (the base may still be reading A of chain[0])
+      Om.I.xx += Dinv * gj[0] * gj[0]; Om.I.yy += Dinv * gj[1] * gj[1]; Om.I.zz += Dinv * gj[2] * gj[2];
+      Om.I.xy += Dinv * gj[0] * gj[1]; Om.I.xz += Dinv * gj[0] * gj[2]; Om.I.yz += Dinv * gj[1] * gj[2];
+      Om.M.xx += Dinv * gj[3] * gj[3]; Om.M.yy += Dinv * gj[4] * gj[4]; Om.M.zz += Dinv * gj[5] * gj[5];
+      Om.M.xy += Dinv * gj[3] * gj[4]; Om.M.xz += Dinv * gj[3] * gj[5]; Om.M.yz += Dinv * gj[4] * gj[5];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) Om.H.a[3 * a + b] += Dinv * gj[a] * gj[3 + b];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) G[c] = xform_force_T(E, r, G[c] - (Dinv * gj[c]) * U);
+    }
+  }
+  // ---- pass 3, root -> leaves: joint accelerations, predicted joint velocities
+  for (int k = 0; k < len; ++k) {
+    const int i = HI(sched, k * DYROS_LANES + role);
+    const int par = HI(parent, i);
+    if (par == 0) {
+      if (!base_role) sync.wait(fl + 0, base + ST_PASS2);
+    } else if (HI(role_of, par) != role) {
+      sync.wait(fl + par, base + ST_PASS3);
+    }
+    real* L = BLK(i);
+    const real* Lp = BLK(par);
+    V3 ax = HF3(axis, i), r = HF3(r, i);
+    M3 E = ld_m3(L + LS_E);
+    SV v = ld6(L + LS_V);
+    real qd = L[LS_SC];
+    V3 aq = qd * ax;
+    SV a = xform_motion(E, r, ld6(Lp + LS_A + A_ACC)) + SV{cross(v.w, aq), cross(v.v, aq)};
+    real qdd = L[LS_SC + 2] * (L[LS_SC + 1] - dot(ld6(L + LS_U), a));
+    a.w = a.w + qdd * ax;
+    st6(L + LS_A + A_ACC, a);
+    L[LS_SC] = qd + dt * qdd;
+    sync.signal(fl + i, base + ST_PASS3);
+  }
+  // ---- feet, part 2: predicted foot velocity, Om += G^T Om0 G, active sole points and their rows, the sweeps
+  if (foot >= 0) {
+    const int g = foot;
+    const int clen = m.chain_len[g];
+    SV Y[6];              // Om0 G
+    SV V = ld6(BLK(0) + LS_U);  // base role published v0* with ST_PASS2 (waited for in pass 3)
+    SV P = sv_zero();     // accumulated contact impulse on the foot (foot coordinates)
+    for (int k = 0; k < clen; ++k) {
+      int j = m.chain[g][k];
+      const real* L = BLK(j);
+      V = xform_motion(ld_m3(L + LS_E), HF3(r, j), V);
+      V.w = V.w + L[LS_SC] * HF3(axis, j);
+    }
+    {
+      ABI Om0 = ld_abi(BLK(0) + LS_A + A_OM0);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) Y[c] = mul(Om0, G[c]);
+      real w[6][6];
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 6; ++b) w[a][b] = dot(G[a], Y[b]);
+      Om.I.xx += w[0][0]; Om.I.yy += w[1][1]; Om.I.zz += w[2][2]; Om.I.xy += w[0][1]; Om.I.xz += w[0][2]; Om.I.yz += w[1][2];
+      Om.M.xx += w[3][3]; Om.M.yy += w[4][4]; Om.M.zz += w[5][5]; Om.M.xy += w[3][4]; Om.M.xz += w[3][5]; Om.M.yz += w[4][5];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) Om.H.a[3 * a + b] += w[a][3 + b];
+    }
+    M3 Rwf = ld_m3(X + X_FOOTPOSE + 12 * g);
+    real pz = X[X_FOOTPOSE + 12 * g + 11];
+    V3 nrm = v3(Rwf.a[6], Rwf.a[7], Rwf.a[8]);
+    V3 xs[MAX_ACTIVE_PTS];
+    real bias[MAX_ACTIVE_PTS], lam[MAX_ACTIVE_PTS][3];
+    int pbody[MAX_ACTIVE_PTS];
+    int nact = 0;
+#pragma unroll
+    for (int a = 0; a < MAX_ACTIVE_PTS; ++a) {
+      xs[a] = v3(0, 0, 0);
+      bias[a] = 0;
+      pbody[a] = 0;
+      lam[a][0] = lam[a][1] = lam[a][2] = 0;
+    }
+    for (int k = 0; k < m.foot_npts[g]; ++k) {
+      V3 x = v3(m.foot_pt_pos[g][k][0], m.foot_pt_pos[g][k][1], m.foot_pt_pos[g][k][2]);
+      real rad = m.foot_pt_radius[g][k];
+      real phi = pz + dot(nrm, x) - rad;
+      if (phi < p.contact_offset && nact < MAX_ACTIVE_PTS) {
+        real b = phi >= 0 ? -phi / dt : fmin_r(-p.erp * phi / dt, p.max_depen_vel);
+        V3 xsk = x - rad * nrm;
+#pragma unroll
+        for (int a = 0; a < MAX_ACTIVE_PTS; ++a)
+          if (a == nact) {
+            xs[a] = xsk;
+            bias[a] = b;
+            pbody[a] = m.foot_pt_body[g][k];
+          }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          V3 dir = d == 0 ? nrm : (d == 1 ? v3(Rwf.a[0], Rwf.a[1], Rwf.a[2]) : v3(Rwf.a[3], Rwf.a[4], Rwf.a[5]));
+          SV J{cross(xsk, dir), dir};
+          SV cv = mul(Om, J);
+          int row = nact * 3 + d;  // parked in the block of chain link row / ROWS_PER_LINK
+          real* rw = BLK(m.chain[g][row / ROWS_PER_LINK]) + LS_A + A_ROWS + (row % ROWS_PER_LINK) * 7;
+          st6(rw, cv);
+          rw[6] = 1 / dot(J, cv);
+        }
+        ++nact;
+      }
+    }
+    // fixed number of sweeps; Gauss-Seidel inside a foot, Jacobi between the feet (coupled through the base)
+    for (int s = 0; s < p.sweeps; ++s) {
+      SV dP = sv_zero();
+#pragma unroll
+      for (int a = 0; a < MAX_ACTIVE_PTS; ++a) {
+        if (a < nact) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            V3 dir = d == 0 ? v3(Rwf.a[6], Rwf.a[7], Rwf.a[8])
+                            : (d == 1 ? v3(Rwf.a[0], Rwf.a[1], Rwf.a[2]) : v3(Rwf.a[3], Rwf.a[4], Rwf.a[5]));
+            SV J{cross(xs[a], dir), dir};
+            const int row = a * 3 + d;
+            const real* rw = BLK(m.chain[g][row / ROWS_PER_LINK]) + LS_A + A_ROWS + (row % ROWS_PER_LINK) * 7;
+            real vrel = dot(J, V);
+            real nw;
+            if (d == 0) {
+              nw = lam[a][0] + (bias[a] - vrel) * rw[6];
+              nw = nw > 0 ? nw : 0;
+            } else {
+              real lim = p.mu * lam[a][0];
+              nw = lam[a][d] - vrel * rw[6];
+              nw = nw > lim ? lim : (nw < -lim ? -lim : nw);
+            }
+            real delta = nw - lam[a][d];
+            lam[a][d] = nw;
+            V = V + delta * ld6(rw);
+            dP = dP + delta * J;
+          }
+        }
+      }
+      P = P + dP;
+      if (m.num_feet == 2) {
+        // base velocity change caused by this sweep's impulses: Om0 G dP = sum_c dP_c Y_c (double-buffered by sweep parity)
+        const int seq = epoch * 64 + s + 1;
+        st6(X + X_Z + ((s & 1) * MAX_FEET + g) * 6,
+            dP.w.x * Y[0] + dP.w.y * Y[1] + dP.w.z * Y[2] + dP.v.x * Y[3] + dP.v.y * Y[4] + dP.v.z * Y[5]);
+        sync.signal(flags + F_Z + g, seq);
+        sync.wait(flags + F_Z + (1 - g), seq);
+        SV z = ld6(X + X_Z + ((s & 1) * MAX_FEET + (1 - g)) * 6);  // response of this foot: G^T z
+        V = V + SV{v3(dot(G[0], z), dot(G[1], z), dot(G[2], z)), v3(dot(G[3], z), dot(G[4], z), dot(G[5], z))};
+      }
+    }
+    // contact impulse -> joint space: S^T dp on the leg chain, impulse arriving at the base
+    for (int k = 0; k < clen; ++k) {
+      real* L = BLK(m.chain[g][k]);
+      const real* gj = X + X_G + (g * MAX_CHAIN + k) * 6;
+      L[LS_SC + 3] = -(gj[0] * P.w.x + gj[1] * P.w.y + gj[2] * P.w.z + gj[3] * P.v.x + gj[4] * P.v.y + gj[5] * P.v.z);
+    }
+    st6(X + X_PD + 6 * g, (real)-1 * (P.w.x * G[0] + P.w.y * G[1] + P.w.z * G[2] + P.v.x * G[3] + P.v.y * G[4] + P.v.z * G[5]));
+    sync.signal(flags + F_PD + g, epoch + 1);
+    if (io.live) {
+      real inv_dt = 1 / dt;
+#pragma unroll
+      for (int a = 0; a < MAX_ACTIVE_PTS; ++a)
+        if (a < nact) {  // world force over this sub-step: (t1, t2, n) = world (x, y, z)
+          float* cf = io.contact + 3 * pbody[a];
+          cf[0] += (float)(lam[a][1] * inv_dt);
+          cf[1] += (float)(lam[a][2] * inv_dt);
+          cf[2] += (float)(lam[a][0] * inv_dt);
+        }
+    }
+  }
+  // ---- base response to the contact impulses (base role)
+  if (base_role) {
+    SV pd = sv_zero();
+    for (int f = 0; f < m.num_feet; ++f) {
+      sync.wait(flags + F_PD + f, epoch + 1);
+      pd = pd + ld6(X + X_PD + 6 * f);
+    }
+    st6(BLK(0) + LS_V, (real)-1 * mul(ld_abi(BLK(0) + LS_A + A_OM0), pd));
+    sync.signal(fl + 0, base + ST_DOWN);
+  }
+  // ---- down the tree: joint velocity changes, speed cap, integration, limit projection
+  for (int k = 0; k < len; ++k) {
+    const int i = HI(sched, k * DYROS_LANES + role);
+    const int par = HI(parent, i);
+    if (par == 0) {
+      if (!base_role) sync.wait(fl + 0, base + ST_DOWN);
+    } else if (HI(role_of, par) != role) {
+      sync.wait(fl + par, base + ST_DOWN);
+    }
+    real* L = BLK(i);
+    const real* Lp = BLK(par);
+    int d = HI(dof, i);
+    V3 ax = HF3(axis, i), r = HF3(r, i);
+    SV dv = xform_motion(ld_m3(L + LS_E), r, ld6(Lp + LS_V));
+    real dqd = -L[LS_SC + 2] * (dot(ld6(L + LS_U), dv) + L[LS_SC + 3]);
+    dv.w = dv.w + dqd * ax;
+    st6(L + LS_V, dv);
+    sync.signal(fl + i, base + ST_DOWN);
+    // joint velocity cap (dof_prop['velocity'], T:372), explicit Euler on the angle, limit projection
+    real vl = HF(vel_limit, d);
+    real qdn = L[LS_SC] + dqd;
+    qdn = qdn > vl ? vl : (qdn < -vl ? -vl : qdn);
+    real qn = L[LS_Q] + dt * qdn;
+    real lo = HF(lower, d), up = HF(upper, d);
+    if (qn > up) {
+      qn = up;
+      qdn = qdn < 0 ? qdn : 0;
+    } else if (qn < lo) {
+      qn = lo;
+      qdn = qdn > 0 ? qdn : 0;
+    }
+    if (io.live) {
+      io.dof_state[2 * d] = (float)qn;
+      io.dof_state[2 * d + 1] = (float)qdn;
+    }
+  }
+  // ---- base integration (base role)
+  if (base_role) {
+    const real* L = BLK(0);
+    M3 R0 = ld_m3(L + LS_E);
+    SV vb = ld6(L + LS_U) + ld6(L + LS_V);
+    vb.v = vb.v + ld3(L + LS_SC);
+    V3 ww = mul(R0, vb.w), vw = mul(R0, vb.v);
+    real wn = sqrt(dot(ww, ww));
+    if (wn > p.max_ang_vel) ww = (p.max_ang_vel / wn) * ww;
+    if (io.live) {
+      real qx = io.root[3], qy = io.root[4], qz = io.root[5], qw = io.root[6];
+      real h = (real)0.5 * dt;
+      real nx = qx + h * (ww.x * qw + ww.y * qz - ww.z * qy);
+      real ny = qy + h * (-ww.x * qz + ww.y * qw + ww.z * qx);
+      real nz = qz + h * (ww.x * qy - ww.y * qx + ww.z * qw);
+      real nw = qw + h * (-ww.x * qx - ww.y * qy - ww.z * qz);
+      real inv = 1 / sqrt(nx * nx + ny * ny + nz * nz + nw * nw);
+      io.root[0] = (float)(io.root[0] + dt * vw.x);
+      io.root[1] = (float)(io.root[1] + dt * vw.y);
+      io.root[2] = (float)(io.root[2] + dt * vw.z);
+      io.root[3] = (float)(nx * inv);
+      io.root[4] = (float)(ny * inv);
+      io.root[5] = (float)(nz * inv);
+      io.root[6] = (float)(nw * inv);
+      io.root[7] = (float)vw.x; io.root[8] = (float)vw.y; io.root[9] = (float)vw.z;
+      io.root[10] = (float)ww.x; io.root[11] = (float)ww.y; io.root[12] = (float)ww.z;
+    }
+  }
+}
+
+}  // namespace dyros

@@ -17,13 +17,27 @@ struct TK {
 // T:505-520: upper-body PD, actuation-delay ring, the 33 torques of set_dof_actuation_force_tensor.
 // LANES lanes of one env cooperate; `lane` in [0, LANES). Ends with the lanes in sync.
 template <int LANES, class Sync>
-__device__ __forceinline__ void stage_substep_torque(const TK& k, int e, int lane, Sync& sync) {
+__device__ __forceinline__ void stage_substep_torque(const TK& k, int e, int lane, Sync& sync, bool live = true) {
   const float* ds = k.s.dof_state + (size_t)e * ND * 2;
   float* out = k.s.dof_actuation_force + (size_t)e * ND;
-  for (int d = 12 + lane; d < ND; d += LANES) {                                   // T:506
-    float pos = ds[2 * d], vel = ds[2 * d + 1];
-    out[d] = __fadd_rn(__fmul_rn(k.p.kp[d], __fsub_rn(k.b.target_data_qpos[(size_t)e * ND + d], pos)),
-                       __fmul_rn(k.p.kv[d], -vel));
+  {  // T:506; loads of all iterations are issued before the first use (trip count is a compile-time constant)
+    constexpr int IT = (ND - 12 + LANES - 1) / LANES;
+    float pos[IT], vel[IT], tgt[IT], kp[IT], kv[IT];
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      int d = 12 + lane + it * LANES;
+      int dc = d < ND ? d : ND - 1;
+      pos[it] = ds[2 * dc];
+      vel[it] = ds[2 * dc + 1];
+      tgt[it] = k.b.target_data_qpos[(size_t)e * ND + dc];
+      kp[it] = k.p.kp[dc];
+      kv[it] = k.p.kv[dc];
+    }
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+      int d = 12 + lane + it * LANES;
+      if (d < ND && live) out[d] = __fadd_rn(__fmul_rn(kp[it], __fsub_rn(tgt[it], pos[it])), __fmul_rn(kv[it], -vel[it]));
+    }
   }
   int sl = k.b.simul_len[e] + 1;                                                  // T:513-514
   sl = sl > LOG_DEPTH ? LOG_DEPTH : (sl < 0 ? 0 : sl);
@@ -35,35 +49,50 @@ __device__ __forceinline__ void stage_substep_torque(const TK& k, int e, int lan
     for (int i = 0; i < LOG_DEPTH - 1; ++i) v[i] = lg[(i + 1) * 12];              // T:511
     v[LOG_DEPTH - 1] = k.b.action_torque[(size_t)e * 12 + j];                     // T:512
 #pragma unroll
-    for (int i = 0; i < LOG_DEPTH; ++i) lg[i * 12] = v[i];
+    for (int i = 0; i < LOG_DEPTH; ++i)
+      if (live) lg[i * 12] = v[i];
     int pick = (sl > dl) ? dl : (LOG_DEPTH - sl);                                 // T:515-519
     float r = v[0];
 #pragma unroll
     for (int i = 1; i < LOG_DEPTH; ++i) r = (pick == i) ? v[i] : r;
-    out[j] = r;                                                                   // T:520
+    if (live) out[j] = r;                                                         // T:520
   }
   sync();
-  if (lane == 0) k.b.simul_len[e] = sl;
+  if (lane == 0 && live) k.b.simul_len[e] = sl;
 }
 
 // T:528-530
 template <int LANES>
-__device__ __forceinline__ void stage_sensor_noise(const TK& k, int substep, int e, int lane) {
+__device__ __forceinline__ void stage_sensor_noise(const TK& k, int substep, int e, int lane, bool live = true) {
   const float* ds = k.s.dof_state + (size_t)e * ND * 2;
-  for (int d = lane; d < ND; d += LANES) {
-    float n;
-    if (k.j.qpos_normal) {
-      n = k.j.qpos_normal[((size_t)substep * k.p.N + e) * ND + d];
-    } else {
-      uint4 r = draw4(k.p.seed, *k.p.step_counter, e, kSiteQposNoise, substep * 64 + d);
-      n = __fmul_rn(normal01(r.x, r.y), k.p.noise_std);
+  constexpr int IT = (ND + LANES - 1) / LANES;
+  float pos[IT], pre[IT], nz[IT];
+  const bool inject = k.j.qpos_normal != nullptr;
+  const uint64_t epoch = inject ? 0 : *k.p.step_counter;
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {  // all loads first
+    int d = lane + it * LANES;
+    int dc = d < ND ? d : ND - 1;
+    pos[it] = ds[2 * dc];
+    pre[it] = k.b.qpos_pre[(size_t)e * ND + dc];
+    nz[it] = inject ? k.j.qpos_normal[((size_t)substep * k.p.N + e) * ND + dc] : 0.f;
+  }
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    int d = lane + it * LANES;
+    if (d < ND && live) {
+      float n = nz[it];
+      if (!inject) {
+        uint4 r = draw4(k.p.seed, epoch, e, kSiteQposNoise, substep * 64 + d);
+        n = __fmul_rn(normal01(r.x, r.y), k.p.noise_std);
+      }
+      n = (n < -0.00016f) ? -0.00016f : ((n > 0.00016f) ? 0.00016f : n);
+      float qn = __fadd_rn(pos[it], n);
+      size_t i = (size_t)e * ND + d;
+      k.b.qvel_noise[i] = __fdiv_rn(__fsub_rn(qn, pre[it]), k.p.dt);
+      k.b.qpos_noise[i] = qn;
+      k.b.qpos_pre[i] = qn;
     }
-    n = (n < -0.00016f) ? -0.00016f : ((n > 0.00016f) ? 0.00016f : n);
-    float qn = __fadd_rn(ds[2 * d], n);
-    size_t i = (size_t)e * ND + d;
-    k.b.qvel_noise[i] = __fdiv_rn(__fsub_rn(qn, k.b.qpos_pre[i]), k.p.dt);
-    k.b.qpos_noise[i] = qn;
-    k.b.qpos_pre[i] = qn;
   }
 }
 

@@ -135,41 +135,55 @@ def branch_schedule(link_parent: np.ndarray, lanes: int = LANES_PER_ENV) -> np.n
     return np.array(rows, dtype=np.int32)
 
 
-def scratch_positions(sched: np.ndarray, nl: int) -> np.ndarray:
-    """Position of each link's scratch block in the physics kernel's per-env shared-memory area, chosen so that the
-    (up to) four links of every schedule slot sit at positions that differ mod 4. With an odd block size and an env
-    stride of 4 (mod 32) words, the 8 envs x 4 lanes of a warp then hit 32 different banks. Backtracking over the
-    residues; falls back to the identity when no assignment exists."""
-    lanes = sched.shape[1]
-    cap = [len(range(r, nl, 4)) for r in range(4)]
-    slot_of = {int(l): (t, g) for t, row in enumerate(sched) for g, l in enumerate(row) if l > 0}
-    links = [0] + sorted(slot_of, key=lambda l: slot_of[l])
-    res, cnt, used = {}, [0] * 4, [set() for _ in range(sched.shape[0])]
+def role_programs(link_parent: np.ndarray, foot_links, roles: int = LANES_PER_ENV) -> np.ndarray:
+    """Static partition of the links 1..nl-1 into `roles` programs for the warp-specialised physics kernel.
 
-    def rec(k):
-        if k == len(links):
-            return True
-        l = links[k]
-        order = [0, 1, 2, 3] if l == 0 else [slot_of[l][1] % 4] + [r for r in range(4) if r != slot_of[l][1] % 4]
-        for r in order:
-            if cnt[r] >= cap[r] or (l > 0 and r in used[slot_of[l][0]]):
-                continue
-            res[l] = r
-            cnt[r] += 1
-            if l > 0:
-                used[slot_of[l][0]].add(r)
-            if rec(k + 1):
-                return True
-            cnt[r] -= 1
-            if l > 0:
-                used[slot_of[l][0]].discard(r)
-            del res[l]
-        return False
-
-    if lanes > 4 or not rec(0):
-        return np.arange(nl, dtype=np.int32)
-    free = {r: list(range(r, nl, 4)) for r in range(4)}
-    return np.array([free[res[l]].pop(0) for l in range(nl)], dtype=np.int32)
+    The tree is cut into chains (a link's tallest child continues its chain, the other children start new ones);
+    chains are dealt to the roles longest-first onto the least loaded role, with every chain that ends in a foot
+    (solver) link pinned to a role of its own so that the contact stage of the two feet runs in two different warps.
+    Returns prog[T][roles] (-1 padded): column r lists role r's links in ascending (= topological) order. Unlike
+    `branch_schedule` there is no slot synchrony: a role waits on per-link flags for what other roles produce."""
+    nl = len(link_parent)
+    children = [[] for _ in range(nl)]
+    for l in range(1, nl):
+        children[int(link_parent[l])].append(l)
+    height = np.zeros(nl, dtype=np.int64)
+    for l in range(nl - 1, 0, -1):
+        height[l] = 1 + max([height[c] for c in children[l]], default=0)
+    chains, stack = [], list(children[0])
+    while stack:
+        head = stack.pop()
+        chain, l = [], head
+        while True:
+            chain.append(l)
+            if not children[l]:
+                break
+            nxt = max(children[l], key=lambda c: (height[c], -c))
+            stack.extend(c for c in children[l] if c != nxt)
+            l = nxt
+        chains.append(chain)
+    foot_links = [int(f) for f in foot_links]
+    foot_chains = [c for c in chains if any(f in c for f in foot_links)]
+    other = sorted([c for c in chains if c not in foot_chains], key=lambda c: -len(c))
+    if len(foot_chains) > roles:
+        raise ValueError("more foot chains than roles")
+    load = [0] * roles
+    members = [[] for _ in range(roles)]
+    # feet take the last roles; the contact stage is charged as extra load so that long arm chains go elsewhere
+    for k, c in enumerate(foot_chains):
+        r = roles - 1 - k
+        members[r] += c
+        load[r] += len(c) + 8
+    for c in other:
+        r = int(np.argmin(load))
+        members[r] += c
+        load[r] += len(c)
+    T = max(len(mm) for mm in members)
+    prog = -np.ones((T, roles), dtype=np.int32)
+    for r, mm in enumerate(members):
+        for k, l in enumerate(sorted(mm)):
+            prog[k, r] = l
+    return prog
 
 
 def build_tables(model: RobotModel, *, solver_bodies: List[str], vel_limit: float = 4.03,

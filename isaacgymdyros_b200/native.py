@@ -25,7 +25,7 @@ class DyrosModelDesc(C.Structure):
         ("dof_lower", P_f64), ("dof_upper", P_f64), ("dof_vel_limit", P_f64), ("dof_effort", P_f64),
         ("pt_link", P_i32), ("pt_body", P_i32), ("pt_pos", P_f64), ("pt_radius", P_f64), ("pt_solver", P_i32),
         ("cyl_link", P_i32), ("cyl_body", P_i32), ("cyl_center", P_f64), ("cyl_axis", P_f64), ("cyl_size", P_f64),
-        ("sched", P_i32), ("link_pos", P_i32)]
+        ("sched", P_i32)]
 
 
 class DyrosSimDesc(C.Structure):

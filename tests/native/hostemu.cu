@@ -1,22 +1,25 @@
-// TEST INFRASTRUCTURE ONLY. CPU emulation of the CUDA physics kernel's lane program: the very same source
-// (isaacgymdyros_b200/csrc/physics_core.cuh) compiled for the host, DYROS_LANES threads per env meeting at a
-// barrier where the GPU lanes meet at __syncwarp(). Lets the CPU test suite compare the kernel's O(n)
-// recursions with the dense fp64 oracle (oracle/physics_oracle.py) without a GPU. Never linked into the product.
+// TEST INFRASTRUCTURE ONLY. CPU emulation of the CUDA physics kernel's role programs: the very same source
+// (isaacgymdyros_b200/csrc/physics_roles.cuh) compiled for the host, one thread per role with atomic stage flags
+// where the GPU uses release/acquire on shared memory. Lets the CPU test suite compare the kernel's O(n) recursions
+// and its dataflow synchronisation with the dense fp64 oracle (oracle/physics_oracle.py) without a GPU.
+// Never linked into the product.
 #include <barrier>
 #include <thread>
 #include <vector>
 
 #include "host_model.h"
-#include "physics_core.cuh"
+#include "physics_roles.cuh"
 
 namespace dyros {
 void set_error(const char*, ...) {}
 }  // namespace dyros
 using namespace dyros;
 
-struct BarrierSync {
-  std::barrier<>* b;
-  void operator()() const { b->arrive_and_wait(); }
+struct HostRoleSync {
+  void signal(int* f, int v) const { __atomic_store_n(f, v, __ATOMIC_RELEASE); }
+  void wait(const int* f, int v) const {
+    while (__atomic_load_n(f, __ATOMIC_ACQUIRE) < v) std::this_thread::yield();
+  }
 };
 
 extern "C" int dyros_hostemu_simulate(const DyrosSimDesc* d, const DyrosModelDesc* md, float* root, float* dof_state,
@@ -34,9 +37,8 @@ extern "C" int dyros_hostemu_simulate(const DyrosSimDesc* d, const DyrosModelDes
   resolve_model(m, off, bl.host.data());
   SimParams p;
   fill_sim_params(d, p);
-  const int es = env_scratch_floats(m.nl);
-  std::vector<real> scratch(es);
-  std::barrier<> bar(DYROS_LANES);
+  const float* hot = reinterpret_cast<const float*>(bl.host.data());
+  std::vector<real> scratch(env_scratch_floats(m.nl));
   for (int env = 0; env < p.N; ++env) {
     EnvIO io;
     io.root = root + (size_t)env * 13;
@@ -50,18 +52,24 @@ extern "C" int dyros_hostemu_simulate(const DyrosSimDesc* d, const DyrosModelDes
     io.rb_force = rb_force ? rb_force + (size_t)env * m.nb * 3 : nullptr;
     io.rb_torque = rb_torque ? rb_torque + (size_t)env * m.nb * 3 : nullptr;
     io.live = true;
-    for (int s = 0; s < p.substeps; ++s) {
-      std::vector<std::thread> th;
-      for (int g = 0; g < DYROS_LANES; ++g)
-        th.emplace_back([&, g]() {
-          BarrierSync sync{&bar};
-          env_substep(io, scratch.data(), reinterpret_cast<const float*>(bl.host.data()), m, p, g, sync);
-        });
-      for (auto& t : th) t.join();
-      io.push = nullptr;
-      io.rb_force = nullptr;
-      io.rb_torque = nullptr;
-    }
+    std::vector<int> flags(F_COUNT, 0);
+    std::barrier<> bar(DYROS_LANES);
+    std::vector<std::thread> th;
+    for (int role = 0; role < DYROS_LANES; ++role)
+      th.emplace_back([&, role]() {
+        EnvIO mine = io;
+        HostRoleSync sync;
+        for (int s = 0; s < p.substeps; ++s) {
+          env_stage_inputs(mine, scratch.data(), hot, m, p, role, DYROS_LANES);
+          bar.arrive_and_wait();
+          env_substep_role(mine, scratch.data(), flags.data(), s, hot, m, p, role, sync);
+          bar.arrive_and_wait();
+          mine.push = nullptr;
+          mine.rb_force = nullptr;
+          mine.rb_torque = nullptr;
+        }
+      });
+    for (auto& t : th) t.join();
   }
   return 0;
 }

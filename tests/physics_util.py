@@ -73,7 +73,7 @@ def hostemu():
     if _EMU is None:
         so = os.path.join(HERE, "native", "libdyros_hostemu.so")
         src = os.path.join(HERE, "native", "hostemu.cu")
-        deps = [src] + [os.path.join(CSRC, f) for f in ("physics_core.cuh", "phys_math.cuh", "host_model.h", "internal.h")]
+        deps = [src] + [os.path.join(CSRC, f) for f in ("physics_roles.cuh", "phys_math.cuh", "host_model.h", "internal.h")]
         if not os.path.isfile(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             subprocess.check_call(["nvcc", "-O2", "-std=c++20", "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "20014",
                                    "-Wno-deprecated-gpu-targets", "-I", CSRC, "-o", so, src])
