@@ -36,7 +36,7 @@ static const T* at(void* base, size_t off) {
 }
 
 struct ModelOffsets {
-  size_t parent, dof, E, r, ax, cs, ch, bs, bd, bl, bp, br, bi, lo, up, vl, ef, ps, pb, pp, pr, ys, yb, yc, ya, yz, sc, rc, ro;
+  size_t parent, dof, E, r, ax, cs, ch, bs, bd, bl, bp, br, bi, lo, up, vl, ef, ps, pb, pp, pr, ys, yb, yc, ya, yz, sc, rc, ro, dl;
 };
 
 // Fills `dm` (counts, foot tables) and appends every table to `bl`. Returns "" or an error message.
@@ -205,6 +205,9 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
   o.sc = bl.add_i(m->sched, (size_t)m->sched_slots * DYROS_LANES);
   o.rc = bl.add_f32(reach.data(), nl);
   o.ro = bl.add_i(role_of.data(), nl);
+  std::vector<int> dof_link(nd, 0);
+  for (int l = 1; l < nl; ++l) dof_link[m->link_dof[l]] = l;
+  o.dl = bl.add_i(dof_link.data(), nd);
   dm.hot_bytes = (int)((bl.host.size() + 15) & ~size_t(15));
   // cold tables (global memory, read only when a link is near the ground or for rigid_body_state)
   o.bl = bl.add_i(m->body_link, nb); o.bp = bl.add_f(m->body_pos, nb * 3); o.br = bl.add_f(m->body_rot, nb * 9);
@@ -220,7 +223,7 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
   dm.o_body_start = (int)(o.bs / 4); dm.o_bodies = (int)(o.bd / 4); dm.o_body_inertia = (int)(o.bi / 4);
   dm.o_lower = (int)(o.lo / 4); dm.o_upper = (int)(o.up / 4); dm.o_vel_limit = (int)(o.vl / 4);
   dm.o_effort = (int)(o.ef / 4); dm.o_pt_start = (int)(o.ps / 4); dm.o_cyl_start = (int)(o.ys / 4);
-  dm.o_sched = (int)(o.sc / 4); dm.o_reach = (int)(o.rc / 4); dm.o_role_of = (int)(o.ro / 4);
+  dm.o_sched = (int)(o.sc / 4); dm.o_reach = (int)(o.rc / 4); dm.o_role_of = (int)(o.ro / 4); dm.o_dof_link = (int)(o.dl / 4);
 
   return std::string();
 #undef MFAIL

@@ -48,7 +48,7 @@ struct DevModel {
   int hot_bytes;
   // word offsets of the hot tables inside the staged prefix (same order as the pointers above)
   int o_parent, o_dof, o_E, o_r, o_axis, o_child_start, o_children, o_body_start, o_bodies, o_body_inertia, o_lower,
-      o_upper, o_vel_limit, o_effort, o_pt_start, o_cyl_start, o_sched, o_reach, o_role_of;
+      o_upper, o_vel_limit, o_effort, o_pt_start, o_cyl_start, o_sched, o_reach, o_role_of, o_dof_link;
   int base_role, foot_role[MAX_FEET], role_len[DYROS_LANES];
   int num_feet;
   int foot_link[MAX_FEET];
@@ -131,7 +131,7 @@ int launch_post_fused(Task* t, cudaStream_t s);
 int physics_configure(Sim* sim);  // chooses envs_per_block / shared memory, sets the kernel attributes
 int launch_simulate(Sim* sim, int apply_wrench, const float* push_force, cudaStream_t s);
 int launch_refresh_rigid_body_state(Sim* sim, cudaStream_t s);
-int launch_task_physics(Task* t, cudaStream_t s);  // skipframe x (torque, simulate, sensor noise) in one launch
+int launch_task_physics(Task* t, cudaStream_t s, long long* trace = nullptr);  // skipframe x (torque, simulate, sensor noise) in one launch
 int measure_fp32_peak(int device, int iters, double* tflops_out);
 
 }  // namespace dyros

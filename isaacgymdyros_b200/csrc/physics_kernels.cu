@@ -19,6 +19,10 @@ __device__ __forceinline__ void st_release_shared(int* p, int v) {
 // the consumer's lane 0 spins with acquire, then the warp re-converges.
 struct RoleSync {
   int lane;
+  long long* trace;  // profiling aid: clock64() at the phase boundaries of one CTA (NULL in production)
+  __device__ __forceinline__ void mark(int id) const {
+    if (trace && lane == 0) trace[id] = clock64();
+  }
   __device__ __forceinline__ void signal(int* f, int v) const {
     __syncwarp();
     if (lane == 0) st_release_shared(f, v);
@@ -84,19 +88,98 @@ __device__ __forceinline__ EnvIO env_io(const DevModel& m, const DyrosSimBuffers
   return io;
 }
 
+// ---- CTA-cooperative, coalesced slab copies between the API tensors and the env scratch blocks. The envs of a CTA
+//      are contiguous in every tensor, so thread t handles words t, t + 128, ... of each slab.
+template <class Dst>
+__device__ __forceinline__ void slab_load(const float* __restrict__ src, int n, Dst dst) {
+  for (int base = 0; base < n; base += 4 * kPhysThreads) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int i = base + u * kPhysThreads + threadIdx.x;
+      v[u] = i < n ? src[i] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      int i = base + u * kPhysThreads + threadIdx.x;
+      if (i < n) dst(i, v[u]);
+    }
+  }
+}
+
+__device__ __forceinline__ void slab_stage_inputs(const DevModel& m, const SimParams& p, const DyrosSimBuffers& b,
+                                                  const float* push, const float* hot, float* envs, int es, int e0, int nenv) {
+  const int nd = m.nd, nb = m.nb, xoff = m.nl * LS;
+  const int* dof_link = reinterpret_cast<const int*>(hot) + m.o_dof_link;
+  slab_load(b.dof_state + (size_t)e0 * nd * 2, nenv * nd * 2, [&](int i, float v) {
+    int le = i / (2 * nd), w = i - le * 2 * nd;
+    envs[le * es + dof_link[w >> 1] * LS + ((w & 1) ? LS_SC : LS_Q)] = v;
+  });
+  slab_load(b.dof_actuation_force + (size_t)e0 * nd, nenv * nd, [&](int i, float v) {
+    int le = i / nd, d = i - le * nd;
+    if (p.clamp_effort) {
+      float lim = hot[m.o_effort + d];
+      v = v > lim ? lim : (v < -lim ? -lim : v);
+    }
+    envs[le * es + dof_link[d] * LS + LS_SC + 1] = v;
+  });
+  slab_load(b.dof_damping + (size_t)e0 * nd, nenv * nd, [&](int i, float v) {
+    int le = i / nd, d = i - le * nd;
+    envs[le * es + dof_link[d] * LS + LS_SC + 2] = v;
+  });
+  slab_load(b.dof_armature + (size_t)e0 * nd, nenv * nd, [&](int i, float v) {
+    int le = i / nd, d = i - le * nd;
+    envs[le * es + dof_link[d] * LS + LS_SC + 3] = v;
+  });
+  slab_load(b.body_mass_scale + (size_t)e0 * nb, nenv * nb, [&](int i, float v) {
+    int le = i / nb;
+    envs[le * es + xoff + X_MASS + (i - le * nb)] = v;
+  });
+  slab_load(b.root_states + (size_t)e0 * 13, nenv * 13, [&](int i, float v) {
+    int le = i / 13;
+    envs[le * es + xoff + X_ROOT + (i - le * 13)] = v;
+  });
+  for (int i = threadIdx.x; i < nenv * 3; i += kPhysThreads) {
+    int le = i / 3;
+    envs[le * es + xoff + X_PUSH + (i - le * 3)] = push ? push[(size_t)e0 * 3 + i] : 0.f;
+  }
+  float* cf = b.net_contact_force + (size_t)e0 * nb * 3;  // net contact force of THIS sub-step only
+  for (int i = threadIdx.x; i < nenv * nb * 3; i += kPhysThreads) cf[i] = 0.f;
+}
+
+__device__ __forceinline__ void slab_store_outputs(const DevModel& m, const DyrosSimBuffers& b, const float* hot,
+                                                   const float* envs, int es, int e0, int nenv) {
+  const int nd = m.nd, xoff = m.nl * LS;
+  const int* dof_link = reinterpret_cast<const int*>(hot) + m.o_dof_link;
+  float* ds = b.dof_state + (size_t)e0 * nd * 2;
+  for (int i = threadIdx.x; i < nenv * nd * 2; i += kPhysThreads) {
+    int le = i / (2 * nd), w = i - le * 2 * nd;
+    ds[i] = envs[le * es + dof_link[w >> 1] * LS + ((w & 1) ? LS_SC : LS_Q)];
+  }
+  float* rs = b.root_states + (size_t)e0 * 13;
+  for (int i = threadIdx.x; i < nenv * 13; i += kPhysThreads) {
+    int le = i / 13;
+    rs[i] = envs[le * es + xoff + X_ROOT + (i - le * 13)];
+  }
+}
+
 __global__ void __launch_bounds__(kPhysThreads) k_simulate(DevModel m, SimParams p, DyrosSimBuffers b, const float* __restrict__ push,
                                                            int apply_wrench, int epb, int es) {
   extern __shared__ __align__(16) float smem[];
   PhysCta c = phys_cta_setup(m, p, smem, epb, es);
+  const int e0 = blockIdx.x * epb, nenv = min(epb, p.N - e0);
+  float* envs = smem + m.hot_bytes / 4 + ((F_COUNT + 3) & ~3);
   EnvIO io = env_io(m, b, c.e, c.live);
   io.push = push ? push + (size_t)c.e * 3 : nullptr;
   io.rb_force = apply_wrench ? b.rb_force + (size_t)c.e * m.nb * 3 : nullptr;
   io.rb_torque = apply_wrench ? b.rb_torque + (size_t)c.e * m.nb * 3 : nullptr;
-  RoleSync sync{c.lane};
+  RoleSync sync{c.lane, nullptr};
   for (int s = 0; s < p.substeps; ++s) {
-    env_stage_inputs(io, c.sm, c.hot, m, p, c.role, DYROS_LANES);
+    slab_stage_inputs(m, p, b, s == 0 ? push : nullptr, c.hot, envs, es, e0, nenv);
     __syncthreads();
     env_substep_role(io, c.sm, c.flags, s, c.hot, m, p, c.role, sync);
+    __syncthreads();
+    slab_store_outputs(m, b, c.hot, envs, es, e0, nenv);
     __syncthreads();
     io.push = nullptr;  // applied wrenches act "for the immediate timestep" (gym_py.html apply_rigid_body_force_tensors)
     io.rb_force = nullptr;
@@ -106,26 +189,40 @@ __global__ void __launch_bounds__(kPhysThreads) k_simulate(DevModel m, SimParams
 
 // The physics part of one policy step in ONE launch: skipframe x (PD + delay torque, gym.simulate, sensor noise),
 // i.e. the loop body of T:504-530 with the three gym calls of T:520-526 folded in.
-__global__ void __launch_bounds__(kPhysThreads) k_step_physics(DevModel m, SimParams p, TK k, int epb, int es) {
+__global__ void __launch_bounds__(kPhysThreads) k_step_physics(DevModel m, SimParams p, TK k, int epb, int es, long long* trace) {
   extern __shared__ __align__(16) float smem[];
   PhysCta c = phys_cta_setup(m, p, smem, epb, es);
+  const int e0 = blockIdx.x * epb, nenv = min(epb, p.N - e0);
+  float* envs = smem + m.hot_bytes / 4 + ((F_COUNT + 3) & ~3);
   EnvIO io = env_io(m, k.s, c.e, c.live);
-  RoleSync sync{c.lane};
+  // trace layout: [sub-step][role][16 marks]; mark 13/14/15 = before torque stage, after staging, after noise
+  RoleSync sync{c.lane, (trace && blockIdx.x == 0) ? trace + c.role * 16 : nullptr};
   CtaSync cta;
+  const int* dof_link = reinterpret_cast<const int*>(c.hot) + m.o_dof_link;
   int epoch = 0;
   for (int s = 0; s < k.p.skipframe; ++s) {
-    stage_substep_torque<DYROS_LANES>(k, c.e, c.role, cta, c.live);
+    sync.mark(13);
+    stage_substep_torque_cta(k, e0, nenv, threadIdx.x, kPhysThreads, cta);
     __syncthreads();
-    io.push = s == 0 ? k.b.push_force + (size_t)c.e * 3 : nullptr;  // the push acts on the first sub-step only (T:502 vs T:504)
+    const float* push = s == 0 ? k.b.push_force : nullptr;  // the push acts on the first sub-step only (T:502 vs T:504)
+    io.push = push;
     for (int ss = 0; ss < p.substeps; ++ss) {
-      env_stage_inputs(io, c.sm, c.hot, m, p, c.role, DYROS_LANES);
+      slab_stage_inputs(m, p, k.s, push, c.hot, envs, es, e0, nenv);
       __syncthreads();
+      sync.mark(14);
       env_substep_role(io, c.sm, c.flags, epoch++, c.hot, m, p, c.role, sync);
       __syncthreads();
+      slab_store_outputs(m, k.s, c.hot, envs, es, e0, nenv);
+      push = nullptr;
       io.push = nullptr;
+      if (ss + 1 < p.substeps) __syncthreads();
     }
-    stage_sensor_noise<DYROS_LANES>(k, s, c.e, c.role, c.live);
+    // sensor noise reads the fresh joint angles from the scratch blocks (the slab store above runs concurrently)
+    stage_sensor_noise_cta(k, s, e0, nenv, threadIdx.x, kPhysThreads,
+                           [&](int le, int d) { return envs[le * es + dof_link[d] * LS + LS_Q]; });
     __syncthreads();
+    sync.mark(15);
+    if (sync.trace) sync.trace += DYROS_LANES * 16;
   }
 }
 
@@ -158,7 +255,7 @@ int launch_simulate(Sim* sim, int apply_wrench, const float* push, cudaStream_t 
   return 0;
 }
 
-int launch_task_physics(Task* t, cudaStream_t s) {
+int launch_task_physics(Task* t, cudaStream_t s, long long* trace) {
   Sim* sim = t->sim;
   const int epb = sim->envs_per_block;
   const int grid = (sim->p.N + epb - 1) / epb;
@@ -167,7 +264,7 @@ int launch_task_physics(Task* t, cudaStream_t s) {
   k.b = t->b;
   k.s = sim->b;
   k.j = t->inj;
-  k_step_physics<<<grid, kPhysThreads, sim->phys_smem, s>>>(sim->m, sim->p, k, epb, env_scratch_floats(sim->m.nl));
+  k_step_physics<<<grid, kPhysThreads, sim->phys_smem, s>>>(sim->m, sim->p, k, epb, env_scratch_floats(sim->m.nl), trace);
   DY_LAUNCH_CHECK();
   return 0;
 }

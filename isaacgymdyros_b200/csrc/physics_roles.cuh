@@ -37,7 +37,9 @@ constexpr int X_FOOTPOSE = 0;                        // MAX_FEET * 12
 constexpr int X_Z = X_FOOTPOSE + MAX_FEET * 12;      // 2 (double buffer) * MAX_FEET * 6: base velocity change of a sweep
 constexpr int X_PD = X_Z + 2 * MAX_FEET * 6;         // MAX_FEET * 6  impulse arriving at the base from a foot
 constexpr int X_G = X_PD + MAX_FEET * 6;             // MAX_FEET * MAX_CHAIN * 6  g_j = S_j^T G_j of the leg-chain links
-constexpr int X_MASS = X_G + MAX_FEET * MAX_CHAIN * 6;  // DYROS_MAX_BODIES per-body mass scale
+constexpr int X_ROOT = X_G + MAX_FEET * MAX_CHAIN * 6;  // 13 (+3 pad): root state in, root state out
+constexpr int X_PUSH = X_ROOT + 13;                  // 3  world force at the base body's COM for this sub-step
+constexpr int X_MASS = X_ROOT + 16;                  // DYROS_MAX_BODIES per-body mass scale
 constexpr int X_SIZE = X_MASS + DYROS_MAX_BODIES;
 
 HD int env_scratch_floats(int nl) {
@@ -114,15 +116,10 @@ HD void link_forces(const EnvIO& io, real* L, const real* X, const float* hot, c
   V3 nrm = v3(Rw.a[6], Rw.a[7], Rw.a[8]);  // world z in link coordinates
   for (int bi = HI(body_start, i); bi < HI(body_start, i + 1); ++bi) {
     int b = HI(bodies, bi);
-    if (io.live) {
-      io.contact[3 * b] = 0.f;
-      io.contact[3 * b + 1] = 0.f;
-      io.contact[3 * b + 2] = 0.f;
-    }
     bool has_push = io.push && b == 0;
     if (has_push || io.rb_force) {  // world wrench at the body's centre of mass (tensors.rst.txt:322-335)
       V3 F = v3(0, 0, 0), T = v3(0, 0, 0);
-      if (has_push) F = ld3_f(io.push);
+      if (has_push) F = ld3(X + X_PUSH);
       if (io.rb_force) {
         F = F + ld3_f(io.rb_force + 3 * b);
         T = ld3_f(io.rb_torque + 3 * b);
@@ -162,9 +159,14 @@ HD void link_forces(const EnvIO& io, real* L, const real* X, const float* hot, c
 }
 
 // Inputs of one env -> its scratch block: thread `tid` of `nthreads` cooperating threads (P0).
+// (The CUDA kernels do the same with CTA-wide coalesced slab copies, physics_kernels.cu.)
 HD void env_stage_inputs(const EnvIO& io, real* sm, const float* hot, const DevModel& m, const SimParams& p, int tid, int nthreads) {
   real* X = sm + m.nl * LS;
   for (int b = tid; b < m.nb; b += nthreads) X[X_MASS + b] = io.mass_scale[b];
+  for (int k = tid; k < 13; k += nthreads) X[X_ROOT + k] = io.root[k];
+  for (int k = tid; k < 3; k += nthreads) X[X_PUSH + k] = io.push ? io.push[k] : 0.f;
+  if (io.live)
+    for (int k = tid; k < 3 * m.nb; k += nthreads) io.contact[k] = 0.f;  // net contact force of THIS sub-step only
   for (int i = 1 + tid; i < m.nl; i += nthreads) {
     int d = HI(dof, i);
     real* L = BLK(i);
@@ -181,6 +183,18 @@ HD void env_stage_inputs(const EnvIO& io, real* sm, const float* hot, const DevM
   }
 }
 
+// Results of one env: scratch -> global (after the sub-step, all roles done).
+HD void env_store_outputs(const EnvIO& io, const real* sm, const float* hot, const DevModel& m, int tid, int nthreads) {
+  if (!io.live) return;
+  const real* X = sm + m.nl * LS;
+  for (int k = tid; k < 13; k += nthreads) io.root[k] = (float)X[X_ROOT + k];
+  for (int i = 1 + tid; i < m.nl; i += nthreads) {
+    int d = HI(dof, i);
+    io.dof_state[2 * d] = (float)BLK(i)[LS_Q];
+    io.dof_state[2 * d + 1] = (float)BLK(i)[LS_SC];
+  }
+}
+
 // One sub-step for role `role` of one env. `flags`: the CTA-wide stage flags; `epoch`: sub-steps done so far in this
 // launch (the flags are monotonic). The env's inputs must have been staged (env_stage_inputs) and made visible.
 template <class Sync>
@@ -194,12 +208,14 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
   const bool base_role = role == m.base_role;
   int* fl = flags + F_LINK;
 
+  sync.mark(0);
   // ---- pass 1, root -> leaves: transforms, velocities, world poses, bias forces
   if (base_role) {
     real* L = BLK(0);
-    V3 pw = ld3_f(io.root);
-    M3 R0 = quat_to_mat(io.root[3], io.root[4], io.root[5], io.root[6]);
-    SV v0{mulT(R0, ld3_f(io.root + 10)), mulT(R0, ld3_f(io.root + 7))};
+    const real* rs = X + X_ROOT;
+    V3 pw = ld3(rs);
+    M3 R0 = quat_to_mat(rs[3], rs[4], rs[5], rs[6]);
+    SV v0{mulT(R0, ld3(rs + 10)), mulT(R0, ld3(rs + 7))};
     st_m3(L + LS_E, R0);
     st6(L + LS_V, v0);
     st_m3(L + LS_A + A_POSE, R0);
@@ -233,6 +249,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     link_forces(io, L, X, hot, m, p, i, Rw, pw, v);
     sync.signal(fl + i, base + ST_PASS1);
   }
+  sync.mark(1);
   // Pass 2 overwrites A (pose) of a link with its contribution to the parent: every child of this role's links that
   // lives in another role must have read its parent's pose first.
   for (int k = 0; k < len; ++k) {
@@ -242,6 +259,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
       if (HI(role_of, c) != role) sync.wait(fl + c, base + ST_PASS1);
     }
   }
+  sync.mark(2);
   // ---- pass 2, leaves -> root: articulated inertias and bias forces
   for (int k = len - 1; k >= 0; --k) {
     const int i = HI(sched, k * DYROS_LANES + role);
@@ -276,6 +294,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     L[LS_SC + 3] = 0;
     sync.signal(fl + i, base + ST_PASS2);
   }
+  sync.mark(3);
   // ---- floating base (base role): inverse articulated inertia, base acceleration, predicted base velocity
   if (base_role) {
     real* L = BLK(0);
@@ -304,6 +323,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     st3(L + LS_SC, dt * cross(v0.w, v0.v));  // rotating-frame term of the world-frame linear velocity update
     sync.signal(fl + 0, base + ST_PASS2);
   }
+  sync.mark(4);
   // ---- feet, part 1 (needs pass 2 of the own leg chain only): up the chain, G = map foot force -> force on the
   //      current link; Om = sum_j g_j g_j^T / D_j with g_j = S_j^T G_j (kept per chain link for the impulse pass)
   int foot = -1;
@@ -343,6 +363,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
       for (int c = 0; c < 6; ++c) G[c] = xform_force_T(E, r, G[c] - (Dinv * gj[c]) * U);
     }
   }
+  sync.mark(5);
   // ---- pass 3, root -> leaves: joint accelerations, predicted joint velocities
   for (int k = 0; k < len; ++k) {
     const int i = HI(sched, k * DYROS_LANES + role);
@@ -366,6 +387,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     L[LS_SC] = qd + dt * qdd;
     sync.signal(fl + i, base + ST_PASS3);
   }
+  sync.mark(6);
   // ---- feet, part 2: predicted foot velocity, Om += G^T Om0 G, active sole points and their rows, the sweeps
   if (foot >= 0) {
     const int g = foot;
@@ -436,6 +458,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
         ++nact;
       }
     }
+    sync.mark(7);
     // fixed number of sweeps; Gauss-Seidel inside a foot, Jacobi between the feet (coupled through the base)
     for (int s = 0; s < p.sweeps; ++s) {
       SV dP = sv_zero();
@@ -478,6 +501,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
         V = V + SV{v3(dot(G[0], z), dot(G[1], z), dot(G[2], z)), v3(dot(G[3], z), dot(G[4], z), dot(G[5], z))};
       }
     }
+    sync.mark(8);
     // contact impulse -> joint space: S^T dp on the leg chain, impulse arriving at the base
     for (int k = 0; k < clen; ++k) {
       real* L = BLK(m.chain[g][k]);
@@ -498,6 +522,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
         }
     }
   }
+  sync.mark(9);
   // ---- base response to the contact impulses (base role)
   if (base_role) {
     SV pd = sv_zero();
@@ -508,6 +533,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     st6(BLK(0) + LS_V, (real)-1 * mul(ld_abi(BLK(0) + LS_A + A_OM0), pd));
     sync.signal(fl + 0, base + ST_DOWN);
   }
+  sync.mark(10);
   // ---- down the tree: joint velocity changes, speed cap, integration, limit projection
   for (int k = 0; k < len; ++k) {
     const int i = HI(sched, k * DYROS_LANES + role);
@@ -539,11 +565,10 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
       qn = lo;
       qdn = qdn > 0 ? qdn : 0;
     }
-    if (io.live) {
-      io.dof_state[2 * d] = (float)qn;
-      io.dof_state[2 * d + 1] = (float)qdn;
-    }
+    L[LS_Q] = qn;      // new joint state; env_store_outputs / the slab copy writes it to dof_state
+    L[LS_SC] = qdn;
   }
+  sync.mark(11);
   // ---- base integration (base role)
   if (base_role) {
     const real* L = BLK(0);
@@ -553,25 +578,27 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     V3 ww = mul(R0, vb.w), vw = mul(R0, vb.v);
     real wn = sqrt(dot(ww, ww));
     if (wn > p.max_ang_vel) ww = (p.max_ang_vel / wn) * ww;
-    if (io.live) {
-      real qx = io.root[3], qy = io.root[4], qz = io.root[5], qw = io.root[6];
+    {
+      real* rs = X + X_ROOT;
+      real qx = rs[3], qy = rs[4], qz = rs[5], qw = rs[6];
       real h = (real)0.5 * dt;
       real nx = qx + h * (ww.x * qw + ww.y * qz - ww.z * qy);
       real ny = qy + h * (-ww.x * qz + ww.y * qw + ww.z * qx);
       real nz = qz + h * (ww.x * qy - ww.y * qx + ww.z * qw);
       real nw = qw + h * (-ww.x * qx - ww.y * qy - ww.z * qz);
       real inv = 1 / sqrt(nx * nx + ny * ny + nz * nz + nw * nw);
-      io.root[0] = (float)(io.root[0] + dt * vw.x);
-      io.root[1] = (float)(io.root[1] + dt * vw.y);
-      io.root[2] = (float)(io.root[2] + dt * vw.z);
-      io.root[3] = (float)(nx * inv);
-      io.root[4] = (float)(ny * inv);
-      io.root[5] = (float)(nz * inv);
-      io.root[6] = (float)(nw * inv);
-      io.root[7] = (float)vw.x; io.root[8] = (float)vw.y; io.root[9] = (float)vw.z;
-      io.root[10] = (float)ww.x; io.root[11] = (float)ww.y; io.root[12] = (float)ww.z;
+      rs[0] = rs[0] + dt * vw.x;
+      rs[1] = rs[1] + dt * vw.y;
+      rs[2] = rs[2] + dt * vw.z;
+      rs[3] = nx * inv;
+      rs[4] = ny * inv;
+      rs[5] = nz * inv;
+      rs[6] = nw * inv;
+      rs[7] = vw.x; rs[8] = vw.y; rs[9] = vw.z;
+      rs[10] = ww.x; rs[11] = ww.y; rs[12] = ww.z;
     }
   }
+  sync.mark(12);
 }
 
 }  // namespace dyros

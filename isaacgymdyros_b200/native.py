@@ -103,6 +103,7 @@ SIGNATURES = {
     "dyros_task_set_noise_injection": (_INT, [_VP, C.POINTER(DyrosNoiseInjection)]),
     "dyros_task_prologue": (_INT, [_VP, _VP, _VP]),
     "dyros_task_physics": (_INT, [_VP, _VP]),
+    "dyros_task_physics_trace": (_INT, [_VP, _VP, _VP]),
     "dyros_task_substep_torque": (_INT, [_VP, _VP]),
     "dyros_task_sensor_noise": (_INT, [_VP, _INT, _VP]),
     "dyros_task_epilogue": (_INT, [_VP, _VP]),

@@ -16,6 +16,7 @@ void set_error(const char*, ...) {}
 using namespace dyros;
 
 struct HostRoleSync {
+  void mark(int) const {}
   void signal(int* f, int v) const { __atomic_store_n(f, v, __ATOMIC_RELEASE); }
   void wait(const int* f, int v) const {
     while (__atomic_load_n(f, __ATOMIC_ACQUIRE) < v) std::this_thread::yield();
@@ -63,6 +64,8 @@ extern "C" int dyros_hostemu_simulate(const DyrosSimDesc* d, const DyrosModelDes
           env_stage_inputs(mine, scratch.data(), hot, m, p, role, DYROS_LANES);
           bar.arrive_and_wait();
           env_substep_role(mine, scratch.data(), flags.data(), s, hot, m, p, role, sync);
+          bar.arrive_and_wait();
+          env_store_outputs(mine, scratch.data(), hot, m, role, DYROS_LANES);
           bar.arrive_and_wait();
           mine.push = nullptr;
           mine.rb_force = nullptr;

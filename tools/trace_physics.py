@@ -1,0 +1,22 @@
+"""Phase timeline of the physics kernel (CTA 0) from the clock64() marks of dyros_task_physics_trace.
+    python tools/trace_physics.py  -> table of cycles per phase and role (run on a GPU box)"""
+import sys, os
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import torch
+from isaacgymdyros_b200 import DyrosDynamicWalk, default_cfg
+
+NAMES = ["pass1", "wait-children-pass1", "pass2", "base solve", "foot G-walk", "pass3", "foot V/Om/rows", "sweeps",
+         "impulse", "base response", "down pass", "base integrate"]
+env = DyrosDynamicWalk(default_cfg(4096), "cuda:0", use_cuda_graph=False)
+g = torch.Generator(device="cuda:0"); g.manual_seed(1)
+for _ in range(30):
+    env.step(torch.rand(4096, 13, device="cuda:0", generator=g) * 2 - 1)
+env.core.prologue(torch.rand(4096, 13, device="cuda:0", generator=g) * 2 - 1)
+tr = env.core.task_physics_trace().cpu()
+torch.cuda.synchronize()
+for s in range(tr.shape[0]):
+    t0 = int(tr[s, :, 13].min())
+    print(f"sub-step {s}: torque+staging until {[int(tr[s, r, 14]) - t0 for r in range(4)]}, end {[int(tr[s, r, 15]) - t0 for r in range(4)]}")
+    print(f"{'phase':24s}" + "".join(f"   role{r}: start   dur" for r in range(4)))
+    for i, n in enumerate(NAMES):
+        print(f"{n:24s}" + "".join(f"   {int(tr[s, r, i]) - t0:12d} {int(tr[s, r, i + 1]) - int(tr[s, r, i]):6d}" for r in range(4)))
