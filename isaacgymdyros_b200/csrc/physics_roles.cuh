@@ -25,19 +25,20 @@ namespace dyros {
 constexpr int LS_E = 0;    // 9  parent->link rotation (base: base->world rotation)
 constexpr int LS_V = 9;    // 6  link velocity, later the impulse response dv
 constexpr int LS_A = 15;   // 27 pass1: pA(6) world pose(12) | pass2: contribution to parent IA(21) pA(6) |
-                           //    pass3: a'(6); leg-chain links then also hold contact rows (14)
+                           //    pass3: a'(6); leg-chain links then also hold contact rows (14) and g = S^T G (6);
+                           //    the first chain link keeps g in X_G0 (the base may still be reading its A block)
 constexpr int LS_U = 42;   // 6  U = IA S (base: predicted velocity v0*)
 constexpr int LS_SC = 48;  // 4  [qd -> qd*, tau -> u, damping -> 1/D, armature -> S^T dp]
 constexpr int LS_Q = 52;   // 1  joint angle
 constexpr int LS = 53;
-constexpr int A_PA = 0, A_POSE = 6, A_CIA = 0, A_CPA = 21, A_ACC = 0, A_OM0 = 6, A_ROWS = 6;
+constexpr int A_PA = 0, A_POSE = 6, A_CIA = 0, A_CPA = 21, A_ACC = 0, A_OM0 = 6, A_ROWS = 6, A_G = 21;
 constexpr int ROWS_PER_LINK = 2;  // contact rows (7 floats each) parked in one leg-chain link's block
 // per-env extra scratch
 constexpr int X_FOOTPOSE = 0;                        // MAX_FEET * 12
 constexpr int X_Z = X_FOOTPOSE + MAX_FEET * 12;      // 2 (double buffer) * MAX_FEET * 6: base velocity change of a sweep
 constexpr int X_PD = X_Z + 2 * MAX_FEET * 6;         // MAX_FEET * 6  impulse arriving at the base from a foot
-constexpr int X_G = X_PD + MAX_FEET * 6;             // MAX_FEET * MAX_CHAIN * 6  g_j = S_j^T G_j of the leg-chain links
-constexpr int X_ROOT = X_G + MAX_FEET * MAX_CHAIN * 6;  // 13 (+3 pad): root state in, root state out
+constexpr int X_G0 = X_PD + MAX_FEET * 6;            // MAX_FEET * 6  g = S^T G of the first leg-chain link (see A_G)
+constexpr int X_ROOT = X_G0 + MAX_FEET * 6;          // 13 (+3 pad): root state in, root state out
 constexpr int X_PUSH = X_ROOT + 13;                  // 3  world force at the base body's COM for this sub-step
 constexpr int X_MASS = X_ROOT + 16;                  // DYROS_MAX_BODIES per-body mass scale
 constexpr int X_SIZE = X_MASS + DYROS_MAX_BODIES;
@@ -350,7 +351,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
 #pragma unroll
       for (int c = 0; c < 6; ++c) gj[c] = dot(ax, G[c].w);
 #pragma unroll
-      for (int c = 0; c < 6; ++c) X[X_G + (foot * MAX_CHAIN + k) * 6 + c] = gj[c];  // (the base may still be reading A of chain[0])
+      for (int c = 0; c < 6; ++c) (k == 0 ? X + X_G0 + foot * 6 : L + LS_A + A_G)[c] = gj[c];
       Om.I.xx += Dinv * gj[0] * gj[0]; Om.I.yy += Dinv * gj[1] * gj[1]; Om.I.zz += Dinv * gj[2] * gj[2];
       Om.I.xy += Dinv * gj[0] * gj[1]; Om.I.xz += Dinv * gj[0] * gj[2]; Om.I.yz += Dinv * gj[1] * gj[2];
       Om.M.xx += Dinv * gj[3] * gj[3]; Om.M.yy += Dinv * gj[4] * gj[4]; Om.M.zz += Dinv * gj[5] * gj[5];
@@ -505,7 +506,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     // contact impulse -> joint space: S^T dp on the leg chain, impulse arriving at the base
     for (int k = 0; k < clen; ++k) {
       real* L = BLK(m.chain[g][k]);
-      const real* gj = X + X_G + (g * MAX_CHAIN + k) * 6;
+      const real* gj = k == 0 ? X + X_G0 + g * 6 : L + LS_A + A_G;
       L[LS_SC + 3] = -(gj[0] * P.w.x + gj[1] * P.w.y + gj[2] * P.w.z + gj[3] * P.v.x + gj[4] * P.v.y + gj[5] * P.v.z);
     }
     st6(X + X_PD + 6 * g, (real)-1 * (P.w.x * G[0] + P.w.y * G[1] + P.w.z * G[2] + P.v.x * G[3] + P.v.y * G[4] + P.v.z * G[5]));
