@@ -89,62 +89,60 @@ __device__ __forceinline__ EnvIO env_io(const DevModel& m, const DyrosSimBuffers
 }
 
 // ---- CTA-cooperative, coalesced slab copies between the API tensors and the env scratch blocks. The envs of a CTA
-//      are contiguous in every tensor, so thread t handles words t, t + 128, ... of each slab.
-template <class Dst>
-__device__ __forceinline__ void slab_load(const float* __restrict__ src, int n, Dst dst) {
-  for (int base = 0; base < n; base += 4 * kPhysThreads) {
-    float v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      int i = base + u * kPhysThreads + threadIdx.x;
-      v[u] = i < n ? src[i] : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      int i = base + u * kPhysThreads + threadIdx.x;
-      if (i < n) dst(i, v[u]);
-    }
-  }
+//      are contiguous in every tensor, so thread t handles words t, t + 128, ... of each slab. Inputs go through
+//      cp.async (LDGSTS, 4-byte): every word is copied straight to its scattered place in shared memory without a
+//      register round trip, all copies of all slabs are in flight together and the CTA pays one memory latency.
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ void slab_stage_inputs(const DevModel& m, const SimParams& p, const DyrosSimBuffers& b,
-                                                  const float* push, const float* hot, float* envs, int es, int e0, int nenv) {
+                                                  const float* push, const float* hot, float* envs, int es, int e0, int nenv,
+                                                  bool with_tau) {
   const int nd = m.nd, nb = m.nb, xoff = m.nl * LS;
   const int* dof_link = reinterpret_cast<const int*>(hot) + m.o_dof_link;
-  slab_load(b.dof_state + (size_t)e0 * nd * 2, nenv * nd * 2, [&](int i, float v) {
-    int le = i / (2 * nd), w = i - le * 2 * nd;
-    envs[le * es + dof_link[w >> 1] * LS + ((w & 1) ? LS_SC : LS_Q)] = v;
-  });
-  slab_load(b.dof_actuation_force + (size_t)e0 * nd, nenv * nd, [&](int i, float v) {
-    int le = i / nd, d = i - le * nd;
-    if (p.clamp_effort) {
-      float lim = hot[m.o_effort + d];
-      v = v > lim ? lim : (v < -lim ? -lim : v);
+  {
+    const float* src = b.dof_state + (size_t)e0 * nd * 2;
+    for (int i = threadIdx.x; i < nenv * nd * 2; i += kPhysThreads) {
+      int le = i / (2 * nd), w = i - le * 2 * nd;
+      cp_async4(envs + le * es + dof_link[w >> 1] * LS + ((w & 1) ? LS_SC : LS_Q), src + i);
     }
-    envs[le * es + dof_link[d] * LS + LS_SC + 1] = v;
-  });
-  slab_load(b.dof_damping + (size_t)e0 * nd, nenv * nd, [&](int i, float v) {
-    int le = i / nd, d = i - le * nd;
-    envs[le * es + dof_link[d] * LS + LS_SC + 2] = v;
-  });
-  slab_load(b.dof_armature + (size_t)e0 * nd, nenv * nd, [&](int i, float v) {
-    int le = i / nd, d = i - le * nd;
-    envs[le * es + dof_link[d] * LS + LS_SC + 3] = v;
-  });
-  slab_load(b.body_mass_scale + (size_t)e0 * nb, nenv * nb, [&](int i, float v) {
-    int le = i / nb;
-    envs[le * es + xoff + X_MASS + (i - le * nb)] = v;
-  });
-  slab_load(b.root_states + (size_t)e0 * 13, nenv * 13, [&](int i, float v) {
-    int le = i / 13;
-    envs[le * es + xoff + X_ROOT + (i - le * 13)] = v;
-  });
+  }
+  {
+    const float* tau = b.dof_actuation_force + (size_t)e0 * nd;
+    const float* dmp = b.dof_damping + (size_t)e0 * nd;
+    const float* arm = b.dof_armature + (size_t)e0 * nd;
+    for (int i = threadIdx.x; i < nenv * nd; i += kPhysThreads) {
+      int le = i / nd, d = i - le * nd;
+      float* L = envs + le * es + dof_link[d] * LS + LS_SC;
+      if (with_tau) cp_async4(L + 1, tau + i);
+      cp_async4(L + 2, dmp + i);
+      cp_async4(L + 3, arm + i);
+    }
+  }
+  {
+    const float* src = b.body_mass_scale + (size_t)e0 * nb;
+    for (int i = threadIdx.x; i < nenv * nb; i += kPhysThreads) {
+      int le = i / nb;
+      cp_async4(envs + le * es + xoff + X_MASS + (i - le * nb), src + i);
+    }
+  }
+  {
+    const float* src = b.root_states + (size_t)e0 * 13;
+    for (int i = threadIdx.x; i < nenv * 13; i += kPhysThreads) {
+      int le = i / 13;
+      cp_async4(envs + le * es + xoff + X_ROOT + (i - le * 13), src + i);
+    }
+  }
   for (int i = threadIdx.x; i < nenv * 3; i += kPhysThreads) {
     int le = i / 3;
-    envs[le * es + xoff + X_PUSH + (i - le * 3)] = push ? push[(size_t)e0 * 3 + i] : 0.f;
+    if (push) cp_async4(envs + le * es + xoff + X_PUSH + (i - le * 3), push + (size_t)e0 * 3 + i);
+    else envs[le * es + xoff + X_PUSH + (i - le * 3)] = 0.f;
   }
   float* cf = b.net_contact_force + (size_t)e0 * nb * 3;  // net contact force of THIS sub-step only
   for (int i = threadIdx.x; i < nenv * nb * 3; i += kPhysThreads) cf[i] = 0.f;
+  cp_async_wait_all();
 }
 
 __device__ __forceinline__ void slab_store_outputs(const DevModel& m, const DyrosSimBuffers& b, const float* hot,
@@ -175,7 +173,7 @@ __global__ void __launch_bounds__(kPhysThreads) k_simulate(DevModel m, SimParams
   io.rb_torque = apply_wrench ? b.rb_torque + (size_t)c.e * m.nb * 3 : nullptr;
   RoleSync sync{c.lane, nullptr};
   for (int s = 0; s < p.substeps; ++s) {
-    slab_stage_inputs(m, p, b, s == 0 ? push : nullptr, c.hot, envs, es, e0, nenv);
+    slab_stage_inputs(m, p, b, s == 0 ? push : nullptr, c.hot, envs, es, e0, nenv, true);
     __syncthreads();
     env_substep_role(io, c.sm, c.flags, s, c.hot, m, p, c.role, sync);
     __syncthreads();
@@ -202,12 +200,13 @@ __global__ void __launch_bounds__(kPhysThreads) k_step_physics(DevModel m, SimPa
   int epoch = 0;
   for (int s = 0; s < k.p.skipframe; ++s) {
     sync.mark(13);
-    stage_substep_torque_cta(k, e0, nenv, threadIdx.x, kPhysThreads, cta);
-    __syncthreads();
+    // the torques go to the API tensor and straight into the scratch blocks (no re-read through global memory)
+    stage_substep_torque_cta(k, e0, nenv, threadIdx.x, kPhysThreads, cta,
+                             [&](int le, int d, float v) { envs[le * es + dof_link[d] * LS + LS_SC + 1] = v; });
     const float* push = s == 0 ? k.b.push_force : nullptr;  // the push acts on the first sub-step only (T:502 vs T:504)
     io.push = push;
     for (int ss = 0; ss < p.substeps; ++ss) {
-      slab_stage_inputs(m, p, k.s, push, c.hot, envs, es, e0, nenv);
+      slab_stage_inputs(m, p, k.s, push, c.hot, envs, es, e0, nenv, ss > 0);
       __syncthreads();
       sync.mark(14);
       env_substep_role(io, c.sm, c.flags, epoch++, c.hot, m, p, c.role, sync);

@@ -171,14 +171,9 @@ HD void env_stage_inputs(const EnvIO& io, real* sm, const float* hot, const DevM
   for (int i = 1 + tid; i < m.nl; i += nthreads) {
     int d = HI(dof, i);
     real* L = BLK(i);
-    real tq = io.tau[d];
-    if (p.clamp_effort) {
-      real lim = HF(effort, d);
-      tq = tq > lim ? lim : (tq < -lim ? -lim : tq);
-    }
     L[LS_Q] = io.dof_state[2 * d];
     L[LS_SC + 0] = io.dof_state[2 * d + 1];
-    L[LS_SC + 1] = tq;
+    L[LS_SC + 1] = io.tau[d];
     L[LS_SC + 2] = io.damping[d];
     L[LS_SC + 3] = io.armature[d];
   }
@@ -279,6 +274,10 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     M3 E = ld_m3(L + LS_E);
     SV v = ld6(L + LS_V);
     real qd = L[LS_SC], tq = L[LS_SC + 1], damp = L[LS_SC + 2], arm = L[LS_SC + 3];
+    if (p.clamp_effort) {  // optional clamp of the actuation to the MJCF ctrlrange
+      real lim = HF(effort, HI(dof, i));
+      tq = tq > lim ? lim : (tq < -lim ? -lim : tq);
+    }
     SV U{mul(IA.I, ax), mulT(IA.H, ax)};
     real D = dot(ax, U.w) + arm + dt * damp;
     real Dinv = 1 / D;

@@ -97,63 +97,117 @@ __device__ __forceinline__ void stage_sensor_noise(const TK& k, int substep, int
 }
 
 // ---- CTA-cooperative variants for a contiguous slab of envs [e0, e0 + nenv): thread `tid` of `nthreads`, one
-//      element per thread and iteration, so every global access is coalesced. Same arithmetic, same bits.
-template <class Sync>
-__device__ __forceinline__ void stage_substep_torque_cta(const TK& k, int e0, int nenv, int tid, int nthreads, Sync& cta_sync) {
+//      element per thread and iteration, so every global access is coalesced; the loads of all iterations are issued
+//      before the first use (MAXE bounds the slab). Same arithmetic, same bits as the per-env variants.
+//      `tau_sink(le, d, v)` additionally receives every torque (the fused kernel feeds its scratch blocks with it).
+constexpr int kSlabMaxEnvs = 32;
+template <class Sync, class Sink>
+__device__ __forceinline__ void stage_substep_torque_cta(const TK& k, int e0, int nenv, int tid, int nthreads, Sync& cta_sync,
+                                                         Sink tau_sink) {
   constexpr int NU = ND - 12;
-  for (int idx = tid; idx < nenv * NU; idx += nthreads) {                         // T:506
-    int le = idx / NU, d = 12 + idx - le * NU;
-    size_t e = (size_t)(e0 + le);
-    float pos = k.s.dof_state[(e * ND + d) * 2], vel = k.s.dof_state[(e * ND + d) * 2 + 1];
-    k.s.dof_actuation_force[e * ND + d] =
-        __fadd_rn(__fmul_rn(k.p.kp[d], __fsub_rn(k.b.target_data_qpos[e * ND + d], pos)), __fmul_rn(k.p.kv[d], -vel));
+  constexpr int THREADS = 128;
+  constexpr int IT_PD = (kSlabMaxEnvs * NU + THREADS - 1) / THREADS, IT_RG = (kSlabMaxEnvs * 12 + THREADS - 1) / THREADS;
+  {
+    float pos[IT_PD], vel[IT_PD], tgt[IT_PD], kp[IT_PD], kv[IT_PD];
+#pragma unroll
+    for (int it = 0; it < IT_PD; ++it) {                                          // T:506, loads
+      int idx = tid + it * nthreads;
+      idx = idx < nenv * NU ? idx : 0;
+      int le = idx / NU, d = 12 + idx - le * NU;
+      size_t e = (size_t)(e0 + le);
+      pos[it] = k.s.dof_state[(e * ND + d) * 2];
+      vel[it] = k.s.dof_state[(e * ND + d) * 2 + 1];
+      tgt[it] = k.b.target_data_qpos[e * ND + d];
+      kp[it] = k.p.kp[d];
+      kv[it] = k.p.kv[d];
+    }
+#pragma unroll
+    for (int it = 0; it < IT_PD; ++it) {
+      int idx = tid + it * nthreads;
+      if (idx < nenv * NU) {
+        int le = idx / NU, d = 12 + idx - le * NU;
+        float t = __fadd_rn(__fmul_rn(kp[it], __fsub_rn(tgt[it], pos[it])), __fmul_rn(kv[it], -vel[it]));
+        k.s.dof_actuation_force[(size_t)(e0 + le) * ND + d] = t;
+        tau_sink(le, d, t);
+      }
+    }
   }
-  for (int idx = tid; idx < nenv * 12; idx += nthreads) {
-    int le = idx / 12, j = idx - le * 12;
-    size_t e = (size_t)(e0 + le);
-    int sl = k.b.simul_len[e] + 1;                                                // T:513-514
-    sl = sl > LOG_DEPTH ? LOG_DEPTH : (sl < 0 ? 0 : sl);
-    int dl = k.b.delay_idx[e];
-    float* lg = k.b.action_log + e * LOG_DEPTH * 12 + j;
-    float v[LOG_DEPTH];
+  {
+    float v[IT_RG][LOG_DEPTH];
+    int sl[IT_RG], dl[IT_RG];
 #pragma unroll
-    for (int i = 0; i < LOG_DEPTH - 1; ++i) v[i] = lg[(i + 1) * 12];              // T:511
-    v[LOG_DEPTH - 1] = k.b.action_torque[e * 12 + j];                             // T:512
+    for (int it = 0; it < IT_RG; ++it) {                                          // loads
+      int idx = tid + it * nthreads;
+      idx = idx < nenv * 12 ? idx : 0;
+      int le = idx / 12, j = idx - le * 12;
+      size_t e = (size_t)(e0 + le);
+      sl[it] = k.b.simul_len[e];
+      dl[it] = k.b.delay_idx[e];
+      const float* lg = k.b.action_log + e * LOG_DEPTH * 12 + j;
 #pragma unroll
-    for (int i = 0; i < LOG_DEPTH; ++i) lg[i * 12] = v[i];
-    int pick = (sl > dl) ? dl : (LOG_DEPTH - sl);                                 // T:515-519
-    float r = v[0];
+      for (int i = 0; i < LOG_DEPTH - 1; ++i) v[it][i] = lg[(i + 1) * 12];        // T:511
+      v[it][LOG_DEPTH - 1] = k.b.action_torque[e * 12 + j];                       // T:512
+    }
 #pragma unroll
-    for (int i = 1; i < LOG_DEPTH; ++i) r = (pick == i) ? v[i] : r;
-    k.s.dof_actuation_force[e * ND + j] = r;                                      // T:520
+    for (int it = 0; it < IT_RG; ++it) {
+      int idx = tid + it * nthreads;
+      if (idx < nenv * 12) {
+        int le = idx / 12, j = idx - le * 12;
+        size_t e = (size_t)(e0 + le);
+        int s1 = sl[it] + 1;                                                      // T:513-514
+        s1 = s1 > LOG_DEPTH ? LOG_DEPTH : (s1 < 0 ? 0 : s1);
+        float* lg = k.b.action_log + e * LOG_DEPTH * 12 + j;
+#pragma unroll
+        for (int i = 0; i < LOG_DEPTH; ++i) lg[i * 12] = v[it][i];
+        int pick = (s1 > dl[it]) ? dl[it] : (LOG_DEPTH - s1);                     // T:515-519
+        float r = v[it][0];
+#pragma unroll
+        for (int i = 1; i < LOG_DEPTH; ++i) r = (pick == i) ? v[it][i] : r;
+        k.s.dof_actuation_force[e * ND + j] = r;                                  // T:520
+        tau_sink(le, j, r);
+      }
+    }
   }
-  cta_sync();
+  cta_sync();  // every thread has read simul_len
   for (int le = tid; le < nenv; le += nthreads) {
-    int sl = k.b.simul_len[e0 + le] + 1;
-    k.b.simul_len[e0 + le] = sl > LOG_DEPTH ? LOG_DEPTH : (sl < 0 ? 0 : sl);
+    int s1 = k.b.simul_len[e0 + le] + 1;
+    k.b.simul_len[e0 + le] = s1 > LOG_DEPTH ? LOG_DEPTH : (s1 < 0 ? 0 : s1);
   }
 }
 
-// T:528-530 for a slab; `dof_state_new(le, d)` supplies the fresh joint angle (from shared memory in the fused kernel)
+// T:528-530 for a slab; `pos_of(le, d)` supplies the fresh joint angle (from shared memory in the fused kernel)
 template <class PosFn>
 __device__ __forceinline__ void stage_sensor_noise_cta(const TK& k, int substep, int e0, int nenv, int tid, int nthreads, PosFn pos_of) {
+  constexpr int THREADS = 128;
+  constexpr int IT = (kSlabMaxEnvs * ND + THREADS - 1) / THREADS;
   const bool inject = k.j.qpos_normal != nullptr;
   const uint64_t epoch = inject ? 0 : *k.p.step_counter;
-  for (int idx = tid; idx < nenv * ND; idx += nthreads) {
+  float pre[IT], nz[IT];
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {  // loads
+    int idx = tid + it * nthreads;
+    idx = idx < nenv * ND ? idx : 0;
     int le = idx / ND, d = idx - le * ND;
-    size_t i = (size_t)(e0 + le) * ND + d;
-    float n;
-    if (inject) {
-      n = k.j.qpos_normal[((size_t)substep * k.p.N + e0 + le) * ND + d];
-    } else {
-      uint4 r = draw4(k.p.seed, epoch, e0 + le, kSiteQposNoise, substep * 64 + d);
-      n = __fmul_rn(normal01(r.x, r.y), k.p.noise_std);
+    pre[it] = k.b.qpos_pre[(size_t)(e0 + le) * ND + d];
+    nz[it] = inject ? k.j.qpos_normal[((size_t)substep * k.p.N + e0 + le) * ND + d] : 0.f;
+  }
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    int idx = tid + it * nthreads;
+    if (idx < nenv * ND) {
+      int le = idx / ND, d = idx - le * ND;
+      size_t i = (size_t)(e0 + le) * ND + d;
+      float n = nz[it];
+      if (!inject) {
+        uint4 r = draw4(k.p.seed, epoch, e0 + le, kSiteQposNoise, substep * 64 + d);
+        n = __fmul_rn(normal01(r.x, r.y), k.p.noise_std);
+      }
+      n = (n < -0.00016f) ? -0.00016f : ((n > 0.00016f) ? 0.00016f : n);
+      float qn = __fadd_rn(pos_of(le, d), n);
+      k.b.qvel_noise[i] = __fdiv_rn(__fsub_rn(qn, pre[it]), k.p.dt);
+      k.b.qpos_noise[i] = qn;
+      k.b.qpos_pre[i] = qn;
     }
-    n = (n < -0.00016f) ? -0.00016f : ((n > 0.00016f) ? 0.00016f : n);
-    float qn = __fadd_rn(pos_of(le, d), n);
-    k.b.qvel_noise[i] = __fdiv_rn(__fsub_rn(qn, k.b.qpos_pre[i]), k.p.dt);
-    k.b.qpos_noise[i] = qn;
-    k.b.qpos_pre[i] = qn;
   }
 }
 
