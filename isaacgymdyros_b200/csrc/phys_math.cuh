@@ -48,6 +48,14 @@ template <class F>
 HD V3 ld3_f(const F* p) { return V3{(real)p[0], (real)p[1], (real)p[2]}; }  // from float tables / tensors
 #endif
 HD real fmin_r(real a, real b) { return a < b ? a : b; }
+HD void sincos_r(real x, real* s, real* c) {
+#if defined(__CUDA_ARCH__)
+  sincosf((float)x, s, c);
+#else
+  *s = sin(x);
+  *c = cos(x);
+#endif
+}
 HD void st3(real* p, V3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
 
 HD V3 mul(const M3& m, V3 v) {

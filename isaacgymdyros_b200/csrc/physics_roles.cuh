@@ -40,7 +40,8 @@ constexpr int X_PD = X_Z + 2 * MAX_FEET * 6;         // MAX_FEET * 6  impulse ar
 constexpr int X_G0 = X_PD + MAX_FEET * 6;            // MAX_FEET * 6  g = S^T G of the first leg-chain link (see A_G)
 constexpr int X_ROOT = X_G0 + MAX_FEET * 6;          // 13 (+3 pad): root state in, root state out
 constexpr int X_PUSH = X_ROOT + 13;                  // 3  world force at the base body's COM for this sub-step
-constexpr int X_MASS = X_ROOT + 16;                  // DYROS_MAX_BODIES per-body mass scale
+constexpr int X_Y = X_ROOT + 16;                     // MAX_FEET * 36  Om0 G of each foot (read once per sweep)
+constexpr int X_MASS = X_Y + MAX_FEET * 36;          // DYROS_MAX_BODIES per-body mass scale
 constexpr int X_SIZE = X_MASS + DYROS_MAX_BODIES;
 
 HD int env_scratch_floats(int nl) {
@@ -216,34 +217,47 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     st6(L + LS_V, v0);
     st_m3(L + LS_A + A_POSE, R0);
     st3(L + LS_A + A_POSE + 9, pw);
-    link_forces(io, L, X, hot, m, p, 0, R0, pw, v0);
     sync.signal(fl + 0, base + ST_PASS1);
+    link_forces(io, L, X, hot, m, p, 0, R0, pw, v0);
   }
+  // (a) joint transforms: local to each link, no dependencies
+  for (int k = 0; k < len; ++k) {
+    const int i = HI(sched, k * DYROS_LANES + role);
+    real* L = BLK(i);
+    real sq, cq;
+    sincos_r(L[LS_Q], &sq, &cq);
+    st_m3(L + LS_E, mul(axis_rot_T(HF3(axis, i), sq, cq), ld_m3_f(hot + m.o_E + 9 * i)));
+  }
+  // (b) propagation root -> leaves: velocity and world pose; this is the only chained part and what the children
+  //     in other roles wait for
   for (int k = 0; k < len; ++k) {
     const int i = HI(sched, k * DYROS_LANES + role);
     const int par = HI(parent, i);
     if (HI(role_of, par) != role) sync.wait(fl + par, base + ST_PASS1);
     real* L = BLK(i);
     const real* Lp = BLK(par);
-    real q = L[LS_Q], qd = L[LS_SC];
     V3 ax = HF3(axis, i), r = HF3(r, i);
-    M3 E = mul(axis_rot_T(ax, sin(q), cos(q)), ld_m3_f(hot + m.o_E + 9 * i));
+    M3 E = ld_m3(L + LS_E);
     SV v = xform_motion(E, r, ld6(Lp + LS_V));
-    v.w = v.w + qd * ax;
+    v.w = v.w + L[LS_SC] * ax;
     M3 Rwp = ld_m3(Lp + LS_A + A_POSE);
-    M3 Rw = mulABt(Rwp, E);
-    V3 pw = ld3(Lp + LS_A + A_POSE + 9) + mul(Rwp, r);
-    st_m3(L + LS_E, E);
     st6(L + LS_V, v);
-    st_m3(L + LS_A + A_POSE, Rw);
-    st3(L + LS_A + A_POSE + 9, pw);
+    st_m3(L + LS_A + A_POSE, mulABt(Rwp, E));
+    st3(L + LS_A + A_POSE + 9, ld3(Lp + LS_A + A_POSE + 9) + mul(Rwp, r));
+    sync.signal(fl + i, base + ST_PASS1);
+  }
+  // (c) bias forces and external wrenches: local to each link again
+  for (int k = 0; k < len; ++k) {
+    const int i = HI(sched, k * DYROS_LANES + role);
+    real* L = BLK(i);
+    M3 Rw = ld_m3(L + LS_A + A_POSE);
+    V3 pw = ld3(L + LS_A + A_POSE + 9);
     for (int f = 0; f < m.num_feet; ++f)
       if (m.foot_link[f] == i) {
         st_m3(X + X_FOOTPOSE + 12 * f, Rw);
         st3(X + X_FOOTPOSE + 12 * f + 9, pw);
       }
-    link_forces(io, L, X, hot, m, p, i, Rw, pw, v);
-    sync.signal(fl + i, base + ST_PASS1);
+    link_forces(io, L, X, hot, m, p, i, Rw, pw, ld6(L + LS_V));
   }
   sync.mark(1);
   // Pass 2 overwrites A (pose) of a link with its contribution to the parent: every child of this role's links that
@@ -392,7 +406,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
   if (foot >= 0) {
     const int g = foot;
     const int clen = m.chain_len[g];
-    SV Y[6];              // Om0 G
+    real* Yp = X + X_Y + 36 * g;  // Om0 G, parked in shared memory (register pressure)
     SV V = ld6(BLK(0) + LS_U);  // base role published v0* with ST_PASS2 (waited for in pass 3)
     SV P = sv_zero();     // accumulated contact impulse on the foot (foot coordinates)
     for (int k = 0; k < clen; ++k) {
@@ -403,13 +417,15 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     }
     {
       ABI Om0 = ld_abi(BLK(0) + LS_A + A_OM0);
-#pragma unroll
-      for (int c = 0; c < 6; ++c) Y[c] = mul(Om0, G[c]);
       real w[6][6];
 #pragma unroll
-      for (int a = 0; a < 6; ++a)
+      for (int b = 0; b < 6; ++b) {
+        SV Yb = mul(Om0, G[b]);
+        st6(Yp + 6 * b, Yb);
 #pragma unroll
-        for (int b = a; b < 6; ++b) w[a][b] = dot(G[a], Y[b]);
+        for (int a = 0; a < 6; ++a)
+          if (a <= b) w[a][b] = dot(G[a], Yb);
+      }
       Om.I.xx += w[0][0]; Om.I.yy += w[1][1]; Om.I.zz += w[2][2]; Om.I.xy += w[0][1]; Om.I.xz += w[0][2]; Om.I.yz += w[1][2];
       Om.M.xx += w[3][3]; Om.M.yy += w[4][4]; Om.M.zz += w[5][5]; Om.M.xy += w[3][4]; Om.M.xz += w[3][5]; Om.M.yz += w[4][5];
 #pragma unroll
@@ -494,7 +510,8 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
         // base velocity change caused by this sweep's impulses: Om0 G dP = sum_c dP_c Y_c (double-buffered by sweep parity)
         const int seq = epoch * 64 + s + 1;
         st6(X + X_Z + ((s & 1) * MAX_FEET + g) * 6,
-            dP.w.x * Y[0] + dP.w.y * Y[1] + dP.w.z * Y[2] + dP.v.x * Y[3] + dP.v.y * Y[4] + dP.v.z * Y[5]);
+            dP.w.x * ld6(Yp) + dP.w.y * ld6(Yp + 6) + dP.w.z * ld6(Yp + 12) + dP.v.x * ld6(Yp + 18) + dP.v.y * ld6(Yp + 24) +
+                dP.v.z * ld6(Yp + 30));
         sync.signal(flags + F_Z + g, seq);
         sync.wait(flags + F_Z + (1 - g), seq);
         SV z = ld6(X + X_Z + ((s & 1) * MAX_FEET + (1 - g)) * 6);  // response of this foot: G^T z
