@@ -161,6 +161,20 @@ __device__ __forceinline__ void slab_store_outputs(const DevModel& m, const Dyro
   }
 }
 
+// The slab stages are compiled as separate functions so that their (large, short-lived) register arrays do not raise
+// the register pressure of the role programs.
+__device__ __noinline__ void torque_stage_slab(TorqueSlabArgs k, int e0, int nenv, float* envs, int es, const int* dof_link) {
+  CtaSync cta;
+  // the torques go to the API tensor and straight into the scratch blocks (no re-read through global memory)
+  stage_substep_torque_cta(k, e0, nenv, threadIdx.x, kPhysThreads, cta,
+                           [&](int le, int d, float v) { envs[le * es + dof_link[d] * LS + LS_SC + 1] = v; });
+}
+__device__ __noinline__ void noise_stage_slab(NoiseSlabArgs k, int substep, int e0, int nenv, const float* envs, int es, const int* dof_link) {
+  // sensor noise reads the fresh joint angles from the scratch blocks
+  stage_sensor_noise_cta(k, substep, e0, nenv, threadIdx.x, kPhysThreads,
+                         [&](int le, int d) { return envs[le * es + dof_link[d] * LS + LS_Q]; });
+}
+
 __global__ void __launch_bounds__(kPhysThreads) k_simulate(DevModel m, SimParams p, DyrosSimBuffers b, const float* __restrict__ push,
                                                            int apply_wrench, int epb, int es) {
   extern __shared__ __align__(16) float smem[];
@@ -195,14 +209,11 @@ __global__ void __launch_bounds__(kPhysThreads) k_step_physics(DevModel m, SimPa
   EnvIO io = env_io(m, k.s, c.e, c.live);
   // trace layout: [sub-step][role][16 marks]; mark 13/14/15 = before torque stage, after staging, after noise
   RoleSync sync{c.lane, (trace && blockIdx.x == 0) ? trace + c.role * 16 : nullptr};
-  CtaSync cta;
   const int* dof_link = reinterpret_cast<const int*>(c.hot) + m.o_dof_link;
   int epoch = 0;
   for (int s = 0; s < k.p.skipframe; ++s) {
     sync.mark(13);
-    // the torques go to the API tensor and straight into the scratch blocks (no re-read through global memory)
-    stage_substep_torque_cta(k, e0, nenv, threadIdx.x, kPhysThreads, cta,
-                             [&](int le, int d, float v) { envs[le * es + dof_link[d] * LS + LS_SC + 1] = v; });
+    torque_stage_slab(torque_args(k), e0, nenv, envs, es, dof_link);
     const float* push = s == 0 ? k.b.push_force : nullptr;  // the push acts on the first sub-step only (T:502 vs T:504)
     io.push = push;
     for (int ss = 0; ss < p.substeps; ++ss) {
@@ -216,9 +227,7 @@ __global__ void __launch_bounds__(kPhysThreads) k_step_physics(DevModel m, SimPa
       io.push = nullptr;
       if (ss + 1 < p.substeps) __syncthreads();
     }
-    // sensor noise reads the fresh joint angles from the scratch blocks (the slab store above runs concurrently)
-    stage_sensor_noise_cta(k, s, e0, nenv, threadIdx.x, kPhysThreads,
-                           [&](int le, int d) { return envs[le * es + dof_link[d] * LS + LS_Q]; });
+    noise_stage_slab(noise_args(k), s, e0, nenv, envs, es, dof_link);  // (the slab store above runs concurrently)
     __syncthreads();
     sync.mark(15);
     if (sync.trace) sync.trace += DYROS_LANES * 16;

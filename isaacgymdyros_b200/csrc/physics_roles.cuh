@@ -40,8 +40,7 @@ constexpr int X_PD = X_Z + 2 * MAX_FEET * 6;         // MAX_FEET * 6  impulse ar
 constexpr int X_G0 = X_PD + MAX_FEET * 6;            // MAX_FEET * 6  g = S^T G of the first leg-chain link (see A_G)
 constexpr int X_ROOT = X_G0 + MAX_FEET * 6;          // 13 (+3 pad): root state in, root state out
 constexpr int X_PUSH = X_ROOT + 13;                  // 3  world force at the base body's COM for this sub-step
-constexpr int X_Y = X_ROOT + 16;                     // MAX_FEET * 36  Om0 G of each foot (read once per sweep)
-constexpr int X_MASS = X_Y + MAX_FEET * 36;          // DYROS_MAX_BODIES per-body mass scale
+constexpr int X_MASS = X_ROOT + 16;                  // DYROS_MAX_BODIES per-body mass scale
 constexpr int X_SIZE = X_MASS + DYROS_MAX_BODIES;
 
 HD int env_scratch_floats(int nl) {
@@ -406,7 +405,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
   if (foot >= 0) {
     const int g = foot;
     const int clen = m.chain_len[g];
-    real* Yp = X + X_Y + 36 * g;  // Om0 G, parked in shared memory (register pressure)
+    SV Y[6];              // Om0 G
     SV V = ld6(BLK(0) + LS_U);  // base role published v0* with ST_PASS2 (waited for in pass 3)
     SV P = sv_zero();     // accumulated contact impulse on the foot (foot coordinates)
     for (int k = 0; k < clen; ++k) {
@@ -417,15 +416,13 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     }
     {
       ABI Om0 = ld_abi(BLK(0) + LS_A + A_OM0);
+#pragma unroll
+      for (int c = 0; c < 6; ++c) Y[c] = mul(Om0, G[c]);
       real w[6][6];
 #pragma unroll
-      for (int b = 0; b < 6; ++b) {
-        SV Yb = mul(Om0, G[b]);
-        st6(Yp + 6 * b, Yb);
+      for (int a = 0; a < 6; ++a)
 #pragma unroll
-        for (int a = 0; a < 6; ++a)
-          if (a <= b) w[a][b] = dot(G[a], Yb);
-      }
+        for (int b = a; b < 6; ++b) w[a][b] = dot(G[a], Y[b]);
       Om.I.xx += w[0][0]; Om.I.yy += w[1][1]; Om.I.zz += w[2][2]; Om.I.xy += w[0][1]; Om.I.xz += w[0][2]; Om.I.yz += w[1][2];
       Om.M.xx += w[3][3]; Om.M.yy += w[4][4]; Om.M.zz += w[5][5]; Om.M.xy += w[3][4]; Om.M.xz += w[3][5]; Om.M.yz += w[4][5];
 #pragma unroll
@@ -510,8 +507,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
         // base velocity change caused by this sweep's impulses: Om0 G dP = sum_c dP_c Y_c (double-buffered by sweep parity)
         const int seq = epoch * 64 + s + 1;
         st6(X + X_Z + ((s & 1) * MAX_FEET + g) * 6,
-            dP.w.x * ld6(Yp) + dP.w.y * ld6(Yp + 6) + dP.w.z * ld6(Yp + 12) + dP.v.x * ld6(Yp + 18) + dP.v.y * ld6(Yp + 24) +
-                dP.v.z * ld6(Yp + 30));
+            dP.w.x * Y[0] + dP.w.y * Y[1] + dP.w.z * Y[2] + dP.v.x * Y[3] + dP.v.y * Y[4] + dP.v.z * Y[5]);
         sync.signal(flags + F_Z + g, seq);
         sync.wait(flags + F_Z + (1 - g), seq);
         SV z = ld6(X + X_Z + ((s & 1) * MAX_FEET + (1 - g)) * 6);  // response of this foot: G^T z

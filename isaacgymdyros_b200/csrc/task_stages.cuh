@@ -101,9 +101,38 @@ __device__ __forceinline__ void stage_sensor_noise(const TK& k, int substep, int
 //      before the first use (MAXE bounds the slab). Same arithmetic, same bits as the per-env variants.
 //      `tau_sink(le, d, v)` additionally receives every torque (the fused kernel feeds its scratch blocks with it).
 constexpr int kSlabMaxEnvs = 32;
+struct TorqueSlabArgs {  // the handful of pointers the torque stage touches (passed by value to a non-inlined function)
+  const float* dof_state;
+  float* dof_actuation_force;
+  const float* target_data_qpos;
+  const float* kp;
+  const float* kv;
+  int* simul_len;
+  const int* delay_idx;
+  float* action_log;
+  const float* action_torque;
+};
+struct NoiseSlabArgs {
+  const float* qpos_normal;  // injected draws or NULL
+  float* qpos_pre;
+  float* qvel_noise;
+  float* qpos_noise;
+  const uint64_t* step_counter;
+  uint64_t seed;
+  float noise_std, dt;
+  int N;
+};
+__device__ __forceinline__ TorqueSlabArgs torque_args(const TK& k) {
+  return TorqueSlabArgs{k.s.dof_state, k.s.dof_actuation_force, k.b.target_data_qpos, k.p.kp, k.p.kv, k.b.simul_len,
+                        k.b.delay_idx, k.b.action_log, k.b.action_torque};
+}
+__device__ __forceinline__ NoiseSlabArgs noise_args(const TK& k) {
+  return NoiseSlabArgs{k.j.qpos_normal, k.b.qpos_pre, k.b.qvel_noise, k.b.qpos_noise, k.p.step_counter, k.p.seed,
+                       k.p.noise_std, k.p.dt, k.p.N};
+}
 template <class Sync, class Sink>
-__device__ __forceinline__ void stage_substep_torque_cta(const TK& k, int e0, int nenv, int tid, int nthreads, Sync& cta_sync,
-                                                         Sink tau_sink) {
+__device__ __forceinline__ void stage_substep_torque_cta(const TorqueSlabArgs& k, int e0, int nenv, int tid, int nthreads,
+                                                         Sync& cta_sync, Sink tau_sink) {
   constexpr int NU = ND - 12;
   constexpr int THREADS = 128;
   constexpr int IT_PD = (kSlabMaxEnvs * NU + THREADS - 1) / THREADS, IT_RG = (kSlabMaxEnvs * 12 + THREADS - 1) / THREADS;
@@ -115,11 +144,11 @@ __device__ __forceinline__ void stage_substep_torque_cta(const TK& k, int e0, in
       idx = idx < nenv * NU ? idx : 0;
       int le = idx / NU, d = 12 + idx - le * NU;
       size_t e = (size_t)(e0 + le);
-      pos[it] = k.s.dof_state[(e * ND + d) * 2];
-      vel[it] = k.s.dof_state[(e * ND + d) * 2 + 1];
-      tgt[it] = k.b.target_data_qpos[e * ND + d];
-      kp[it] = k.p.kp[d];
-      kv[it] = k.p.kv[d];
+      pos[it] = k.dof_state[(e * ND + d) * 2];
+      vel[it] = k.dof_state[(e * ND + d) * 2 + 1];
+      tgt[it] = k.target_data_qpos[e * ND + d];
+      kp[it] = k.kp[d];
+      kv[it] = k.kv[d];
     }
 #pragma unroll
     for (int it = 0; it < IT_PD; ++it) {
@@ -127,7 +156,7 @@ __device__ __forceinline__ void stage_substep_torque_cta(const TK& k, int e0, in
       if (idx < nenv * NU) {
         int le = idx / NU, d = 12 + idx - le * NU;
         float t = __fadd_rn(__fmul_rn(kp[it], __fsub_rn(tgt[it], pos[it])), __fmul_rn(kv[it], -vel[it]));
-        k.s.dof_actuation_force[(size_t)(e0 + le) * ND + d] = t;
+        k.dof_actuation_force[(size_t)(e0 + le) * ND + d] = t;
         tau_sink(le, d, t);
       }
     }
@@ -141,12 +170,12 @@ __device__ __forceinline__ void stage_substep_torque_cta(const TK& k, int e0, in
       idx = idx < nenv * 12 ? idx : 0;
       int le = idx / 12, j = idx - le * 12;
       size_t e = (size_t)(e0 + le);
-      sl[it] = k.b.simul_len[e];
-      dl[it] = k.b.delay_idx[e];
-      const float* lg = k.b.action_log + e * LOG_DEPTH * 12 + j;
+      sl[it] = k.simul_len[e];
+      dl[it] = k.delay_idx[e];
+      const float* lg = k.action_log + e * LOG_DEPTH * 12 + j;
 #pragma unroll
       for (int i = 0; i < LOG_DEPTH - 1; ++i) v[it][i] = lg[(i + 1) * 12];        // T:511
-      v[it][LOG_DEPTH - 1] = k.b.action_torque[e * 12 + j];                       // T:512
+      v[it][LOG_DEPTH - 1] = k.action_torque[e * 12 + j];                       // T:512
     }
 #pragma unroll
     for (int it = 0; it < IT_RG; ++it) {
@@ -156,40 +185,40 @@ __device__ __forceinline__ void stage_substep_torque_cta(const TK& k, int e0, in
         size_t e = (size_t)(e0 + le);
         int s1 = sl[it] + 1;                                                      // T:513-514
         s1 = s1 > LOG_DEPTH ? LOG_DEPTH : (s1 < 0 ? 0 : s1);
-        float* lg = k.b.action_log + e * LOG_DEPTH * 12 + j;
+        float* lg = k.action_log + e * LOG_DEPTH * 12 + j;
 #pragma unroll
         for (int i = 0; i < LOG_DEPTH; ++i) lg[i * 12] = v[it][i];
         int pick = (s1 > dl[it]) ? dl[it] : (LOG_DEPTH - s1);                     // T:515-519
         float r = v[it][0];
 #pragma unroll
         for (int i = 1; i < LOG_DEPTH; ++i) r = (pick == i) ? v[it][i] : r;
-        k.s.dof_actuation_force[e * ND + j] = r;                                  // T:520
+        k.dof_actuation_force[e * ND + j] = r;                                  // T:520
         tau_sink(le, j, r);
       }
     }
   }
   cta_sync();  // every thread has read simul_len
   for (int le = tid; le < nenv; le += nthreads) {
-    int s1 = k.b.simul_len[e0 + le] + 1;
-    k.b.simul_len[e0 + le] = s1 > LOG_DEPTH ? LOG_DEPTH : (s1 < 0 ? 0 : s1);
+    int s1 = k.simul_len[e0 + le] + 1;
+    k.simul_len[e0 + le] = s1 > LOG_DEPTH ? LOG_DEPTH : (s1 < 0 ? 0 : s1);
   }
 }
 
 // T:528-530 for a slab; `pos_of(le, d)` supplies the fresh joint angle (from shared memory in the fused kernel)
 template <class PosFn>
-__device__ __forceinline__ void stage_sensor_noise_cta(const TK& k, int substep, int e0, int nenv, int tid, int nthreads, PosFn pos_of) {
+__device__ __forceinline__ void stage_sensor_noise_cta(const NoiseSlabArgs& k, int substep, int e0, int nenv, int tid, int nthreads, PosFn pos_of) {
   constexpr int THREADS = 128;
   constexpr int IT = (kSlabMaxEnvs * ND + THREADS - 1) / THREADS;
-  const bool inject = k.j.qpos_normal != nullptr;
-  const uint64_t epoch = inject ? 0 : *k.p.step_counter;
+  const bool inject = k.qpos_normal != nullptr;
+  const uint64_t epoch = inject ? 0 : *k.step_counter;
   float pre[IT], nz[IT];
 #pragma unroll
   for (int it = 0; it < IT; ++it) {  // loads
     int idx = tid + it * nthreads;
     idx = idx < nenv * ND ? idx : 0;
     int le = idx / ND, d = idx - le * ND;
-    pre[it] = k.b.qpos_pre[(size_t)(e0 + le) * ND + d];
-    nz[it] = inject ? k.j.qpos_normal[((size_t)substep * k.p.N + e0 + le) * ND + d] : 0.f;
+    pre[it] = k.qpos_pre[(size_t)(e0 + le) * ND + d];
+    nz[it] = inject ? k.qpos_normal[((size_t)substep * k.N + e0 + le) * ND + d] : 0.f;
   }
 #pragma unroll
   for (int it = 0; it < IT; ++it) {
@@ -199,14 +228,14 @@ __device__ __forceinline__ void stage_sensor_noise_cta(const TK& k, int substep,
       size_t i = (size_t)(e0 + le) * ND + d;
       float n = nz[it];
       if (!inject) {
-        uint4 r = draw4(k.p.seed, epoch, e0 + le, kSiteQposNoise, substep * 64 + d);
-        n = __fmul_rn(normal01(r.x, r.y), k.p.noise_std);
+        uint4 r = draw4(k.seed, epoch, e0 + le, kSiteQposNoise, substep * 64 + d);
+        n = __fmul_rn(normal01(r.x, r.y), k.noise_std);
       }
       n = (n < -0.00016f) ? -0.00016f : ((n > 0.00016f) ? 0.00016f : n);
       float qn = __fadd_rn(pos_of(le, d), n);
-      k.b.qvel_noise[i] = __fdiv_rn(__fsub_rn(qn, pre[it]), k.p.dt);
-      k.b.qpos_noise[i] = qn;
-      k.b.qpos_pre[i] = qn;
+      k.qvel_noise[i] = __fdiv_rn(__fsub_rn(qn, pre[it]), k.dt);
+      k.qpos_noise[i] = qn;
+      k.qpos_pre[i] = qn;
     }
   }
 }
