@@ -220,7 +220,7 @@ int dyros_task_prologue(DyrosTask* task, const float* actions, void* stream);   
 /* T:504-530 in one launch: skipframe x (substep torque, gym.simulate, sensor noise); what dyros_task_step uses. */
 int dyros_task_physics(DyrosTask* task, void* stream);
 /* Profiling aid: dyros_task_physics that also writes clock64() at the phase boundaries of CTA 0 into `trace`
- * (device buffer of skipframe * DYROS_LANES * 16 int64; see physics_roles.cuh for the mark ids). */
+ * (device buffer of skipframe * DYROS_LANES * 32 int64; see physics_roles.cuh for the mark ids). */
 int dyros_task_physics_trace(DyrosTask* task, int64_t* trace, void* stream);
 int dyros_task_substep_torque(DyrosTask* task, void* stream);                      /* T:505-520 -> dof_actuation_force */
 int dyros_task_sensor_noise(DyrosTask* task, int substep, void* stream);           /* T:528-530 */

@@ -315,8 +315,8 @@ class DyrosCore:
         native.check(self.lib.dyros_task_physics(self.task_handle, self._stream), "task_physics")
 
     def task_physics_trace(self) -> "torch.Tensor":
-        """Profiling aid: runs the fused physics launch and returns clock64() marks of CTA 0, (skipframe, roles, 16)."""
-        buf = torch.zeros(self.cfg.control_freq_inv, native.DYROS_LANES, 16, dtype=torch.int64, device=self.device)
+        """Profiling aid: runs the fused physics launch and returns clock64() marks of CTA 0, (skipframe, roles, 32)."""
+        buf = torch.zeros(self.cfg.control_freq_inv, native.DYROS_LANES, 32, dtype=torch.int64, device=self.device)
         native.check(self.lib.dyros_task_physics_trace(self.task_handle, C.c_void_p(buf.data_ptr()), self._stream), "trace")
         return buf
 

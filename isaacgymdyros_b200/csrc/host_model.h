@@ -36,7 +36,7 @@ static const T* at(void* base, size_t off) {
 }
 
 struct ModelOffsets {
-  size_t parent, dof, E, r, ax, cs, ch, bs, bd, bl, bp, br, bi, lo, up, vl, ef, ps, pb, pp, pr, ys, yb, yc, ya, yz, sc, rc, ro, dl;
+  size_t parent, dof, E, r, ax, cs, ch, bs, bd, bl, bp, br, bi, lo, up, vl, ef, ps, pb, pp, pr, ys, yb, yc, ya, yz, sc, rc, ro, dl, pg;
 };
 
 // Fills `dm` (counts, foot tables) and appends every table to `bl`. Returns "" or an error message.
@@ -194,22 +194,84 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
     }
   }
   // hot tables first: the physics kernel stages the prefix [0, hot_bytes) into shared memory
-  o.parent = bl.add_i(m->link_parent, nl); o.dof = bl.add_i(m->link_dof, nl);
+  o.bi = bl.add_f(m->body_inertia, nb * 10);
+  o.dof = bl.add_i(m->link_dof, nl);
+  {  // flattened role programs
+    std::vector<int> order(1, 0);
+    for (int g = 0; g < DYROS_LANES; ++g) {
+      dm.prog_start[g] = (int)order.size();
+      for (int t = 0; t < role_len[g]; ++t) order.push_back(m->sched[t * DYROS_LANES + g]);
+    }
+    std::vector<int> rec_of(nl, 0);
+    for (size_t k = 0; k < order.size(); ++k) rec_of[order[k]] = (int)k;
+    std::vector<int> prog(order.size() * REC_WORDS, 0);
+    auto F = [&](size_t k, int field) -> float& { return reinterpret_cast<float*>(prog.data())[k * REC_WORDS + field]; };
+    for (size_t k = 0; k < order.size(); ++k) {
+      const int l = order[k];
+      int* R = prog.data() + k * REC_WORDS;
+      const int par = l > 0 ? m->link_parent[l] : 0;
+      R[R_LINK] = l;
+      R[R_PARENT] = par;
+      R[R_FLAGS] = (l > 0 && role_of[par] != role_of[l] ? RF_PARENT_FOREIGN : 0) | (l > 0 && par == 0 ? RF_PARENT_BASE : 0);
+      R[R_DOF] = l > 0 ? m->link_dof[l] : 0;
+      const int nbod = body_start[l + 1] - body_start[l], nch = child_start[l + 1] - child_start[l];
+      if (nbod > MAX_LINK_BODIES) MFAIL("link %d merges %d bodies (max %d)", l, nbod, MAX_LINK_BODIES);
+      if (nch > MAX_LINK_CHILDREN) MFAIL("link %d has %d children (max %d)", l, nch, MAX_LINK_CHILDREN);
+      R[R_NBODY] = nbod;
+      for (int j = 0; j < nbod; ++j) R[R_BODY0 + j] = bodies[body_start[l] + j];
+      R[R_NCHILD] = nch;
+      for (int j = 0; j < nch; ++j) {
+        int c = children[child_start[l] + j];
+        R[R_CHILD0 + j] = c | (role_of[c] != role_of[l] ? REC_FOREIGN : 0);
+      }
+      for (int j = 0; j < 3; ++j) F(k, R_AXIS + j) = (float)m->link_axis[3 * l + j];
+      for (int j = 0; j < 3; ++j) F(k, R_R + j) = (float)m->link_r[3 * l + j];
+      for (int j = 0; j < 9; ++j) F(k, R_E + j) = (float)m->link_E[9 * l + j];
+      F(k, R_REACH) = reach[l];
+      R[R_PT0] = pt_start[l]; R[R_PT1] = pt_start[l + 1];
+      R[R_CYL0] = cyl_start[l]; R[R_CYL1] = cyl_start[l + 1];
+      if (l > 0) {
+        const int d = m->link_dof[l];
+        F(k, R_VLIM) = (float)m->dof_vel_limit[d];
+        F(k, R_LO) = (float)m->dof_lower[d];
+        F(k, R_UP) = (float)m->dof_upper[d];
+        F(k, R_EFF) = (float)m->dof_effort[d];
+      }
+      R[R_FOOT] = -1;
+      for (int f = 0; f < dm.num_feet; ++f)
+        if (dm.foot_link[f] == l) R[R_FOOT] = f;
+    }
+    o.pg = bl.add_i(prog.data(), prog.size());
+    for (int f = 0; f < dm.num_feet; ++f)
+      for (int k = 0; k < dm.chain_len[f]; ++k) dm.chain_rec[f][k] = rec_of[dm.chain[f][k]];
+    for (int g = 0; g < DYROS_LANES; ++g) {
+      dm.n_xchild[g] = 0;
+      for (int t = 0; t < role_len[g]; ++t) {
+        int l = m->sched[t * DYROS_LANES + g];
+        for (int ci = child_start[l]; ci < child_start[l + 1]; ++ci)
+          if (role_of[children[ci]] != g) {
+            if (dm.n_xchild[g] >= 8) MFAIL("role %d has more than 8 children in other roles", g);
+            dm.xchild[g][dm.n_xchild[g]++] = children[ci];
+          }
+      }
+    }
+  }
+  std::vector<int> dof_link(nd, 0);
+  for (int l = 1; l < nl; ++l) dof_link[m->link_dof[l]] = l;
+  o.dl = bl.add_i(dof_link.data(), nd);
+  dm.hot_bytes = (int)((bl.host.size() + 15) & ~size_t(15));
+  // cold tables (global memory): penalty candidates (read only when a link is near the ground), rigid_body_state
+  // kinematics, and the unflattened tree
+  o.parent = bl.add_i(m->link_parent, nl);
   o.E = bl.add_f(m->link_E, nl * 9); o.r = bl.add_f(m->link_r, nl * 3); o.ax = bl.add_f(m->link_axis, nl * 3);
   o.cs = bl.add_i(child_start.data(), nl + 1); o.ch = bl.add_i(children.data(), children.size());
   o.bs = bl.add_i(body_start.data(), nl + 1); o.bd = bl.add_i(bodies.data(), nb);
-  o.bi = bl.add_f(m->body_inertia, nb * 10);
   o.lo = bl.add_f(m->dof_lower, nd); o.up = bl.add_f(m->dof_upper, nd); o.vl = bl.add_f(m->dof_vel_limit, nd);
   o.ef = bl.add_f(m->dof_effort, nd);
   o.ps = bl.add_i(pt_start.data(), nl + 1); o.ys = bl.add_i(cyl_start.data(), nl + 1);
   o.sc = bl.add_i(m->sched, (size_t)m->sched_slots * DYROS_LANES);
   o.rc = bl.add_f32(reach.data(), nl);
   o.ro = bl.add_i(role_of.data(), nl);
-  std::vector<int> dof_link(nd, 0);
-  for (int l = 1; l < nl; ++l) dof_link[m->link_dof[l]] = l;
-  o.dl = bl.add_i(dof_link.data(), nd);
-  dm.hot_bytes = (int)((bl.host.size() + 15) & ~size_t(15));
-  // cold tables (global memory, read only when a link is near the ground or for rigid_body_state)
   o.bl = bl.add_i(m->body_link, nb); o.bp = bl.add_f(m->body_pos, nb * 3); o.br = bl.add_f(m->body_rot, nb * 9);
   o.pb = bl.add_i(ppt_body.data(), ppt_body.size());
   o.pp = bl.add_f32(ppt_pos.data(), ppt_pos.size()); o.pr = bl.add_f32(ppt_rad.data(), ppt_rad.size());
@@ -223,7 +285,7 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
   dm.o_body_start = (int)(o.bs / 4); dm.o_bodies = (int)(o.bd / 4); dm.o_body_inertia = (int)(o.bi / 4);
   dm.o_lower = (int)(o.lo / 4); dm.o_upper = (int)(o.up / 4); dm.o_vel_limit = (int)(o.vl / 4);
   dm.o_effort = (int)(o.ef / 4); dm.o_pt_start = (int)(o.ps / 4); dm.o_cyl_start = (int)(o.ys / 4);
-  dm.o_sched = (int)(o.sc / 4); dm.o_reach = (int)(o.rc / 4); dm.o_role_of = (int)(o.ro / 4); dm.o_dof_link = (int)(o.dl / 4);
+  dm.o_sched = (int)(o.sc / 4); dm.o_reach = (int)(o.rc / 4); dm.o_role_of = (int)(o.ro / 4); dm.o_dof_link = (int)(o.dl / 4); dm.o_prog = (int)(o.pg / 4);
 
   return std::string();
 #undef MFAIL

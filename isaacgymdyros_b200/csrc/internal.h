@@ -14,6 +14,12 @@ constexpr int MAX_CHAIN = 8;   // links between the base and a solver (foot) lin
 constexpr int MAX_FEET = 2;    // solver links
 constexpr int MAX_SOLVER_PTS = 8;  // candidate solver points per foot
 constexpr int MAX_ACTIVE_PTS = 4;  // active (constraint-solved) points per foot and sub-step
+// record of one link in the flattened role programs (word offsets; ints and floats share the table)
+constexpr int REC_WORDS = 40, MAX_LINK_BODIES = 3, MAX_LINK_CHILDREN = 3, REC_FOREIGN = 1 << 30;
+constexpr int R_LINK = 0, R_PARENT = 1, R_FLAGS = 2, R_DOF = 3, R_NBODY = 4, R_BODY0 = 5, R_NCHILD = 8, R_CHILD0 = 9,
+              R_AXIS = 12, R_R = 15, R_E = 18, R_REACH = 27, R_PT0 = 28, R_PT1 = 29, R_CYL0 = 30, R_CYL1 = 31,
+              R_VLIM = 32, R_LO = 33, R_UP = 34, R_EFF = 35, R_FOOT = 36;
+constexpr int RF_PARENT_FOREIGN = 1, RF_PARENT_BASE = 2;
 struct DevModel {
   int nl, nb, nd, np, nc, T;
   const int* link_parent;
@@ -50,6 +56,9 @@ struct DevModel {
   int o_parent, o_dof, o_E, o_r, o_axis, o_child_start, o_children, o_body_start, o_bodies, o_body_inertia, o_lower,
       o_upper, o_vel_limit, o_effort, o_pt_start, o_cyl_start, o_sched, o_reach, o_role_of, o_dof_link;
   int base_role, foot_role[MAX_FEET], role_len[DYROS_LANES];
+  // flattened role programs: one record of REC_WORDS words per link, base first, then role 0's links in order, ...
+  int o_prog, prog_start[DYROS_LANES], chain_rec[MAX_FEET][MAX_CHAIN];
+  int n_xchild[DYROS_LANES], xchild[DYROS_LANES][8];  // children of the role's links that live in other roles
   int num_feet;
   int foot_link[MAX_FEET];
   int chain_len[MAX_FEET];

@@ -207,8 +207,8 @@ __global__ void __launch_bounds__(kPhysThreads) k_step_physics(DevModel m, SimPa
   const int e0 = blockIdx.x * epb, nenv = min(epb, p.N - e0);
   float* envs = smem + m.hot_bytes / 4 + ((F_COUNT + 3) & ~3);
   EnvIO io = env_io(m, k.s, c.e, c.live);
-  // trace layout: [sub-step][role][16 marks]; mark 13/14/15 = before torque stage, after staging, after noise
-  RoleSync sync{c.lane, (trace && blockIdx.x == 0) ? trace + c.role * 16 : nullptr};
+  // trace layout: [sub-step][role][32 marks]; mark 13/14/15 = before torque stage, after staging, after noise
+  RoleSync sync{c.lane, (trace && blockIdx.x == 0) ? trace + c.role * 32 : nullptr};
   const int* dof_link = reinterpret_cast<const int*>(c.hot) + m.o_dof_link;
   int epoch = 0;
   for (int s = 0; s < k.p.skipframe; ++s) {
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kPhysThreads) k_step_physics(DevModel m, SimPa
     noise_stage_slab(noise_args(k), s, e0, nenv, envs, es, dof_link);  // (the slab store above runs concurrently)
     __syncthreads();
     sync.mark(15);
-    if (sync.trace) sync.trace += DYROS_LANES * 16;
+    if (sync.trace) sync.trace += DYROS_LANES * 32;
   }
 }
 

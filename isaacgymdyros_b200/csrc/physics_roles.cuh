@@ -60,6 +60,9 @@ constexpr int ST_PASS1 = 1, ST_PASS2 = 2, ST_PASS3 = 3, ST_DOWN = 4, ST_STRIDE =
 #define HF(field, idx) (hot[m.o_##field + (idx)])
 #define HF3(field, idx) ld3_f(hot + m.o_##field + 3 * (idx))
 #define BLK(link) (sm + (link) * LS)
+// record of a link in the flattened role programs (one base address, constant offsets: no dependent table walks)
+#define REC(idx) (hot + m.o_prog + (idx) * REC_WORDS)
+#define RI(R, field) (reinterpret_cast<const int*>(R)[field])
 
 // global-memory views of one env (all device pointers on the GPU, host pointers in the emulation)
 struct EnvIO {
@@ -96,13 +99,17 @@ HD void penalty_point(const SimParams& p, const M3& Rw, SV v, V3 xs, real depth,
   fext.v = fext.v + fl;
 }
 
-// Rigid inertia of link i from the hot body table and the env's per-body mass scales (X_MASS).
-HD ABI link_inertia(const real* X, const float* hot, const DevModel& m, int i) {
+// Rigid inertia of the link of record R from the hot body table and the env's per-body mass scales (X_MASS).
+HD ABI link_inertia(const real* X, const float* hot, const DevModel& m, const float* R) {
   real par[10];
+  {  // first body (most links have exactly one): straight-line code
+    int b = RI(R, R_BODY0);
+    real sc = X[X_MASS + b];
 #pragma unroll
-  for (int k = 0; k < 10; ++k) par[k] = 0;
-  for (int bi = HI(body_start, i); bi < HI(body_start, i + 1); ++bi) {
-    int b = HI(bodies, bi);
+    for (int k = 0; k < 10; ++k) par[k] = sc * HF(body_inertia, b * 10 + k);
+  }
+  for (int j = 1; j < RI(R, R_NBODY); ++j) {
+    int b = RI(R, R_BODY0 + j);
     real sc = X[X_MASS + b];
 #pragma unroll
     for (int k = 0; k < 10; ++k) par[k] += sc * HF(body_inertia, b * 10 + k);
@@ -110,17 +117,16 @@ HD ABI link_inertia(const real* X, const float* hot, const DevModel& m, int i) {
   return abi_rigid(par[0], v3(par[1], par[2], par[3]), S3{par[4], par[5], par[6], par[7], par[8], par[9]});
 }
 
-// Bias force and external wrench of link i (pass 1). Writes A_PA.
-HD void link_forces(const EnvIO& io, real* L, const real* X, const float* hot, const DevModel& m, const SimParams& p, int i,
-                    const M3& Rw, V3 pw, SV v) {
+// Bias force and external wrench of the link of record R (pass 1). Writes A_PA.
+HD void link_forces(const EnvIO& io, real* L, const real* X, const float* hot, const DevModel& m, const SimParams& p,
+                    const float* R, const M3& Rw, V3 pw, SV v) {
   SV fext = sv_zero();
   V3 nrm = v3(Rw.a[6], Rw.a[7], Rw.a[8]);  // world z in link coordinates
-  for (int bi = HI(body_start, i); bi < HI(body_start, i + 1); ++bi) {
-    int b = HI(bodies, bi);
-    bool has_push = io.push && b == 0;
-    if (has_push || io.rb_force) {  // world wrench at the body's centre of mass (tensors.rst.txt:322-335)
+  if (io.rb_force || (io.push && RI(R, R_LINK) == 0)) {  // applied world wrenches at the bodies' COMs (tensors.rst.txt:322-335)
+    for (int j = 0; j < RI(R, R_NBODY); ++j) {
+      int b = RI(R, R_BODY0 + j);
       V3 F = v3(0, 0, 0), T = v3(0, 0, 0);
-      if (has_push) F = ld3(X + X_PUSH);
+      if (io.push && b == 0) F = ld3(X + X_PUSH);
       if (io.rb_force) {
         F = F + ld3_f(io.rb_force + 3 * b);
         T = ld3_f(io.rb_torque + 3 * b);
@@ -135,14 +141,14 @@ HD void link_forces(const EnvIO& io, real* L, const real* X, const float* hot, c
       fext.v = fext.v + fl;
     }
   }
-  if (pw.z < HF(reach, i)) {  // nothing of this link can reach z = 0 otherwise
-    for (int k = HI(pt_start, i); k < HI(pt_start, i + 1); ++k) {
+  if (pw.z < R[R_REACH]) {  // nothing of this link can reach z = 0 otherwise
+    for (int k = RI(R, R_PT0); k < RI(R, R_PT1); ++k) {
       V3 x = ld3_f(m.pt_pos + 3 * k);
       real rad = m.pt_radius[k];
       real z = pw.z + dot(nrm, x);
       penalty_point(p, Rw, v, x - rad * nrm, rad - z, io.contact + 3 * m.pt_body[k], io.live, fext);
     }
-    for (int k = HI(cyl_start, i); k < HI(cyl_start, i + 1); ++k) {
+    for (int k = RI(R, R_CYL0); k < RI(R, R_CYL1); ++k) {
       V3 c = ld3_f(m.cyl_center + 3 * k), a = ld3_f(m.cyl_axis + 3 * k);
       real rad = m.cyl_size[2 * k], hh = m.cyl_size[2 * k + 1];
       real az = dot(nrm, a);
@@ -155,7 +161,7 @@ HD void link_forces(const EnvIO& io, real* L, const real* X, const float* hot, c
       penalty_point(p, Rw, v, rim, -z, io.contact + 3 * m.cyl_body[k], io.live, fext);
     }
   }
-  SV pA = crf(v, mul(link_inertia(X, hot, m, i), v)) - fext;
+  SV pA = crf(v, mul(link_inertia(X, hot, m, R), v)) - fext;
   st6(L + LS_A + A_PA, pA);
 }
 
@@ -205,6 +211,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
   int* fl = flags + F_LINK;
 
   sync.mark(0);
+  const int rec0 = m.prog_start[role];
   // ---- pass 1, root -> leaves: transforms, velocities, world poses, bias forces
   if (base_role) {
     real* L = BLK(0);
@@ -217,25 +224,26 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     st_m3(L + LS_A + A_POSE, R0);
     st3(L + LS_A + A_POSE + 9, pw);
     sync.signal(fl + 0, base + ST_PASS1);
-    link_forces(io, L, X, hot, m, p, 0, R0, pw, v0);
+    link_forces(io, L, X, hot, m, p, REC(0), R0, pw, v0);
   }
   // (a) joint transforms: local to each link, no dependencies
   for (int k = 0; k < len; ++k) {
-    const int i = HI(sched, k * DYROS_LANES + role);
-    real* L = BLK(i);
+    const float* R = REC(rec0 + k);
+    real* L = BLK(RI(R, R_LINK));
     real sq, cq;
     sincos_r(L[LS_Q], &sq, &cq);
-    st_m3(L + LS_E, mul(axis_rot_T(HF3(axis, i), sq, cq), ld_m3_f(hot + m.o_E + 9 * i)));
+    st_m3(L + LS_E, mul(axis_rot_T(ld3_f(R + R_AXIS), sq, cq), ld_m3_f(R + R_E)));
   }
+  sync.mark(16);
   // (b) propagation root -> leaves: velocity and world pose; this is the only chained part and what the children
   //     in other roles wait for
   for (int k = 0; k < len; ++k) {
-    const int i = HI(sched, k * DYROS_LANES + role);
-    const int par = HI(parent, i);
-    if (HI(role_of, par) != role) sync.wait(fl + par, base + ST_PASS1);
+    const float* R = REC(rec0 + k);
+    const int i = RI(R, R_LINK), par = RI(R, R_PARENT);
+    if (RI(R, R_FLAGS) & RF_PARENT_FOREIGN) sync.wait(fl + par, base + ST_PASS1);
     real* L = BLK(i);
     const real* Lp = BLK(par);
-    V3 ax = HF3(axis, i), r = HF3(r, i);
+    V3 ax = ld3_f(R + R_AXIS), r = ld3_f(R + R_R);
     M3 E = ld_m3(L + LS_E);
     SV v = xform_motion(E, r, ld6(Lp + LS_V));
     v.w = v.w + L[LS_SC] * ax;
@@ -245,50 +253,46 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     st3(L + LS_A + A_POSE + 9, ld3(Lp + LS_A + A_POSE + 9) + mul(Rwp, r));
     sync.signal(fl + i, base + ST_PASS1);
   }
+  sync.mark(17);
   // (c) bias forces and external wrenches: local to each link again
   for (int k = 0; k < len; ++k) {
-    const int i = HI(sched, k * DYROS_LANES + role);
-    real* L = BLK(i);
+    const float* R = REC(rec0 + k);
+    real* L = BLK(RI(R, R_LINK));
     M3 Rw = ld_m3(L + LS_A + A_POSE);
     V3 pw = ld3(L + LS_A + A_POSE + 9);
-    for (int f = 0; f < m.num_feet; ++f)
-      if (m.foot_link[f] == i) {
-        st_m3(X + X_FOOTPOSE + 12 * f, Rw);
-        st3(X + X_FOOTPOSE + 12 * f + 9, pw);
-      }
-    link_forces(io, L, X, hot, m, p, i, Rw, pw, ld6(L + LS_V));
+    const int f = RI(R, R_FOOT);
+    if (f >= 0) {
+      st_m3(X + X_FOOTPOSE + 12 * f, Rw);
+      st3(X + X_FOOTPOSE + 12 * f + 9, pw);
+    }
+    link_forces(io, L, X, hot, m, p, R, Rw, pw, ld6(L + LS_V));
   }
   sync.mark(1);
   // Pass 2 overwrites A (pose) of a link with its contribution to the parent: every child of this role's links that
   // lives in another role must have read its parent's pose first.
-  for (int k = 0; k < len; ++k) {
-    const int i = HI(sched, k * DYROS_LANES + role);
-    for (int ci = HI(child_start, i); ci < HI(child_start, i + 1); ++ci) {
-      const int c = HI(children, ci);
-      if (HI(role_of, c) != role) sync.wait(fl + c, base + ST_PASS1);
-    }
-  }
+  for (int k = 0; k < m.n_xchild[role]; ++k) sync.wait(fl + m.xchild[role][k], base + ST_PASS1);
   sync.mark(2);
   // ---- pass 2, leaves -> root: articulated inertias and bias forces
   for (int k = len - 1; k >= 0; --k) {
-    const int i = HI(sched, k * DYROS_LANES + role);
+    const float* R = REC(rec0 + k);
+    const int i = RI(R, R_LINK);
     real* L = BLK(i);
     real* A = L + LS_A;
-    ABI IA = link_inertia(X, hot, m, i);
+    ABI IA = link_inertia(X, hot, m, R);
     SV pA = ld6(A + A_PA);
-    for (int ci = HI(child_start, i); ci < HI(child_start, i + 1); ++ci) {
-      const int c = HI(children, ci);
-      if (HI(role_of, c) != role) sync.wait(fl + c, base + ST_PASS2);
+    for (int j = 0; j < RI(R, R_NCHILD); ++j) {
+      const int cf = RI(R, R_CHILD0 + j), c = cf & ~REC_FOREIGN;
+      if (cf & REC_FOREIGN) sync.wait(fl + c, base + ST_PASS2);
       const real* Ac = BLK(c) + LS_A;
       IA = IA + ld_abi(Ac + A_CIA);
       pA = pA + ld6(Ac + A_CPA);
     }
-    V3 ax = HF3(axis, i), r = HF3(r, i);
+    V3 ax = ld3_f(R + R_AXIS), r = ld3_f(R + R_R);
     M3 E = ld_m3(L + LS_E);
     SV v = ld6(L + LS_V);
     real qd = L[LS_SC], tq = L[LS_SC + 1], damp = L[LS_SC + 2], arm = L[LS_SC + 3];
     if (p.clamp_effort) {  // optional clamp of the actuation to the MJCF ctrlrange
-      real lim = HF(effort, HI(dof, i));
+      real lim = R[R_EFF];
       tq = tq > lim ? lim : (tq < -lim ? -lim : tq);
     }
     SV U{mul(IA.I, ax), mulT(IA.H, ax)};
@@ -310,13 +314,14 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
   sync.mark(3);
   // ---- floating base (base role): inverse articulated inertia, base acceleration, predicted base velocity
   if (base_role) {
+    const float* R = REC(0);
     real* L = BLK(0);
     real* A = L + LS_A;
-    ABI IA = link_inertia(X, hot, m, 0);
+    ABI IA = link_inertia(X, hot, m, R);
     SV pA = ld6(A + A_PA);
-    for (int ci = HI(child_start, 0); ci < HI(child_start, 1); ++ci) {
-      const int c = HI(children, ci);
-      if (HI(role_of, c) != role) sync.wait(fl + c, base + ST_PASS2);
+    for (int j = 0; j < RI(R, R_NCHILD); ++j) {
+      const int cf = RI(R, R_CHILD0 + j), c = cf & ~REC_FOREIGN;
+      if (cf & REC_FOREIGN) sync.wait(fl + c, base + ST_PASS2);
       const real* Ac = BLK(c) + LS_A;
       IA = IA + ld_abi(Ac + A_CIA);
       pA = pA + ld6(Ac + A_CPA);
@@ -353,9 +358,9 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
 #pragma unroll
     for (int c = 0; c < 9; ++c) Om.H.a[c] = 0;
     for (int k = m.chain_len[foot] - 1; k >= 0; --k) {
-      int j = m.chain[foot][k];
-      real* L = BLK(j);
-      V3 ax = HF3(axis, j), r = HF3(r, j);
+      const float* R = REC(m.chain_rec[foot][k]);
+      real* L = BLK(RI(R, R_LINK));
+      V3 ax = ld3_f(R + R_AXIS), r = ld3_f(R + R_R);
       M3 E = ld_m3(L + LS_E);
       real Dinv = L[LS_SC + 2];
       SV U = ld6(L + LS_U);
@@ -379,16 +384,16 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
   sync.mark(5);
   // ---- pass 3, root -> leaves: joint accelerations, predicted joint velocities
   for (int k = 0; k < len; ++k) {
-    const int i = HI(sched, k * DYROS_LANES + role);
-    const int par = HI(parent, i);
-    if (par == 0) {
+    const float* R = REC(rec0 + k);
+    const int i = RI(R, R_LINK), par = RI(R, R_PARENT), flg = RI(R, R_FLAGS);
+    if (flg & RF_PARENT_BASE) {
       if (!base_role) sync.wait(fl + 0, base + ST_PASS2);
-    } else if (HI(role_of, par) != role) {
+    } else if (flg & RF_PARENT_FOREIGN) {
       sync.wait(fl + par, base + ST_PASS3);
     }
     real* L = BLK(i);
     const real* Lp = BLK(par);
-    V3 ax = HF3(axis, i), r = HF3(r, i);
+    V3 ax = ld3_f(R + R_AXIS), r = ld3_f(R + R_R);
     M3 E = ld_m3(L + LS_E);
     SV v = ld6(L + LS_V);
     real qd = L[LS_SC];
@@ -409,10 +414,10 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     SV V = ld6(BLK(0) + LS_U);  // base role published v0* with ST_PASS2 (waited for in pass 3)
     SV P = sv_zero();     // accumulated contact impulse on the foot (foot coordinates)
     for (int k = 0; k < clen; ++k) {
-      int j = m.chain[g][k];
-      const real* L = BLK(j);
-      V = xform_motion(ld_m3(L + LS_E), HF3(r, j), V);
-      V.w = V.w + L[LS_SC] * HF3(axis, j);
+      const float* R = REC(m.chain_rec[g][k]);
+      const real* L = BLK(RI(R, R_LINK));
+      V = xform_motion(ld_m3(L + LS_E), ld3_f(R + R_R), V);
+      V.w = V.w + L[LS_SC] * ld3_f(R + R_AXIS);
     }
     {
       ABI Om0 = ld_abi(BLK(0) + LS_A + A_OM0);
@@ -549,28 +554,27 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
   sync.mark(10);
   // ---- down the tree: joint velocity changes, speed cap, integration, limit projection
   for (int k = 0; k < len; ++k) {
-    const int i = HI(sched, k * DYROS_LANES + role);
-    const int par = HI(parent, i);
-    if (par == 0) {
+    const float* R = REC(rec0 + k);
+    const int i = RI(R, R_LINK), par = RI(R, R_PARENT), flg = RI(R, R_FLAGS);
+    if (flg & RF_PARENT_BASE) {
       if (!base_role) sync.wait(fl + 0, base + ST_DOWN);
-    } else if (HI(role_of, par) != role) {
+    } else if (flg & RF_PARENT_FOREIGN) {
       sync.wait(fl + par, base + ST_DOWN);
     }
     real* L = BLK(i);
     const real* Lp = BLK(par);
-    int d = HI(dof, i);
-    V3 ax = HF3(axis, i), r = HF3(r, i);
+    V3 ax = ld3_f(R + R_AXIS), r = ld3_f(R + R_R);
     SV dv = xform_motion(ld_m3(L + LS_E), r, ld6(Lp + LS_V));
     real dqd = -L[LS_SC + 2] * (dot(ld6(L + LS_U), dv) + L[LS_SC + 3]);
     dv.w = dv.w + dqd * ax;
     st6(L + LS_V, dv);
     sync.signal(fl + i, base + ST_DOWN);
     // joint velocity cap (dof_prop['velocity'], T:372), explicit Euler on the angle, limit projection
-    real vl = HF(vel_limit, d);
+    real vl = R[R_VLIM];
     real qdn = L[LS_SC] + dqd;
     qdn = qdn > vl ? vl : (qdn < -vl ? -vl : qdn);
     real qn = L[LS_Q] + dt * qdn;
-    real lo = HF(lower, d), up = HF(upper, d);
+    real lo = R[R_LO], up = R[R_UP];
     if (qn > up) {
       qn = up;
       qdn = qdn < 0 ? qdn : 0;
