@@ -51,6 +51,24 @@ __device__ __forceinline__ float normal01(uint32_t a, uint32_t b) {
   return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
 }
 
+// standard normal pair (Box-Muller, both outputs) from two words
+__device__ __forceinline__ float2 normal01_pair(uint32_t a, uint32_t b) {
+  float u1 = ((float)(a >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0,1]
+  float u2 = u01(b);
+  float r = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+// Division of small non-negative ints by a run-time constant: q = (i * mul) >> 20, exact while i * d < 2^20.
+struct FastDiv {
+  unsigned mul;
+  int d;
+  __host__ __device__ explicit FastDiv(int div) : mul(((1u << 20) + (unsigned)div - 1) / (unsigned)div), d(div) {}
+  __device__ __forceinline__ int div(int i) const { return (int)(((unsigned)i * mul) >> 20); }
+};
+
 // ---------------------------------------------------------------- warp helpers
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -102,10 +102,11 @@ __device__ __forceinline__ void slab_stage_inputs(const DevModel& m, const SimPa
                                                   bool with_tau) {
   const int nd = m.nd, nb = m.nb, xoff = m.nl * LS;
   const int* dof_link = reinterpret_cast<const int*>(hot) + m.o_dof_link;
+  const FastDiv d2nd(2 * nd), dnd(nd), dnb(nb), d13(13), d3(3);  // slabs are < 2^20 / divisor words (checked at create)
   {
     const float* src = b.dof_state + (size_t)e0 * nd * 2;
     for (int i = threadIdx.x; i < nenv * nd * 2; i += kPhysThreads) {
-      int le = i / (2 * nd), w = i - le * 2 * nd;
+      int le = d2nd.div(i), w = i - le * 2 * nd;
       cp_async4(envs + le * es + dof_link[w >> 1] * LS + ((w & 1) ? LS_SC : LS_Q), src + i);
     }
   }
@@ -114,7 +115,7 @@ __device__ __forceinline__ void slab_stage_inputs(const DevModel& m, const SimPa
     const float* dmp = b.dof_damping + (size_t)e0 * nd;
     const float* arm = b.dof_armature + (size_t)e0 * nd;
     for (int i = threadIdx.x; i < nenv * nd; i += kPhysThreads) {
-      int le = i / nd, d = i - le * nd;
+      int le = dnd.div(i), d = i - le * nd;
       float* L = envs + le * es + dof_link[d] * LS + LS_SC;
       if (with_tau) cp_async4(L + 1, tau + i);
       cp_async4(L + 2, dmp + i);
@@ -124,19 +125,19 @@ __device__ __forceinline__ void slab_stage_inputs(const DevModel& m, const SimPa
   {
     const float* src = b.body_mass_scale + (size_t)e0 * nb;
     for (int i = threadIdx.x; i < nenv * nb; i += kPhysThreads) {
-      int le = i / nb;
+      int le = dnb.div(i);
       cp_async4(envs + le * es + xoff + X_MASS + (i - le * nb), src + i);
     }
   }
   {
     const float* src = b.root_states + (size_t)e0 * 13;
     for (int i = threadIdx.x; i < nenv * 13; i += kPhysThreads) {
-      int le = i / 13;
+      int le = d13.div(i);
       cp_async4(envs + le * es + xoff + X_ROOT + (i - le * 13), src + i);
     }
   }
   for (int i = threadIdx.x; i < nenv * 3; i += kPhysThreads) {
-    int le = i / 3;
+    int le = d3.div(i);
     if (push) cp_async4(envs + le * es + xoff + X_PUSH + (i - le * 3), push + (size_t)e0 * 3 + i);
     else envs[le * es + xoff + X_PUSH + (i - le * 3)] = 0.f;
   }
@@ -149,14 +150,15 @@ __device__ __forceinline__ void slab_store_outputs(const DevModel& m, const Dyro
                                                    const float* envs, int es, int e0, int nenv) {
   const int nd = m.nd, xoff = m.nl * LS;
   const int* dof_link = reinterpret_cast<const int*>(hot) + m.o_dof_link;
+  const FastDiv d2nd(2 * nd), d13(13);
   float* ds = b.dof_state + (size_t)e0 * nd * 2;
   for (int i = threadIdx.x; i < nenv * nd * 2; i += kPhysThreads) {
-    int le = i / (2 * nd), w = i - le * 2 * nd;
+    int le = d2nd.div(i), w = i - le * 2 * nd;
     ds[i] = envs[le * es + dof_link[w >> 1] * LS + ((w & 1) ? LS_SC : LS_Q)];
   }
   float* rs = b.root_states + (size_t)e0 * 13;
   for (int i = threadIdx.x; i < nenv * 13; i += kPhysThreads) {
-    int le = i / 13;
+    int le = d13.div(i);
     rs[i] = envs[le * es + xoff + X_ROOT + (i - le * 13)];
   }
 }

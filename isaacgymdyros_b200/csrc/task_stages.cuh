@@ -83,8 +83,9 @@ __device__ __forceinline__ void stage_sensor_noise(const TK& k, int substep, int
     if (d < ND && live) {
       float n = nz[it];
       if (!inject) {
-        uint4 r = draw4(k.p.seed, epoch, e, kSiteQposNoise, substep * 64 + d);
-        n = __fmul_rn(normal01(r.x, r.y), k.p.noise_std);
+        uint4 r = draw4(k.p.seed, epoch, e, kSiteQposNoise, substep * 64 + (d >> 1));  // one draw per pair of DOFs
+        float2 nn = normal01_pair(r.x, r.y);
+        n = __fmul_rn((d & 1) ? nn.y : nn.x, k.p.noise_std);
       }
       n = (n < -0.00016f) ? -0.00016f : ((n > 0.00016f) ? 0.00016f : n);
       float qn = __fadd_rn(pos[it], n);
@@ -135,6 +136,7 @@ __device__ __forceinline__ void stage_substep_torque_cta(const TorqueSlabArgs& k
                                                          Sync& cta_sync, Sink tau_sink) {
   constexpr int NU = ND - 12;
   constexpr int THREADS = 128;
+  const FastDiv dNU(NU), d12(12);
   constexpr int IT_PD = (kSlabMaxEnvs * NU + THREADS - 1) / THREADS, IT_RG = (kSlabMaxEnvs * 12 + THREADS - 1) / THREADS;
   {
     float pos[IT_PD], vel[IT_PD], tgt[IT_PD], kp[IT_PD], kv[IT_PD];
@@ -142,7 +144,7 @@ __device__ __forceinline__ void stage_substep_torque_cta(const TorqueSlabArgs& k
     for (int it = 0; it < IT_PD; ++it) {                                          // T:506, loads
       int idx = tid + it * nthreads;
       idx = idx < nenv * NU ? idx : 0;
-      int le = idx / NU, d = 12 + idx - le * NU;
+      int le = dNU.div(idx), d = 12 + idx - le * NU;
       size_t e = (size_t)(e0 + le);
       pos[it] = k.dof_state[(e * ND + d) * 2];
       vel[it] = k.dof_state[(e * ND + d) * 2 + 1];
@@ -154,7 +156,7 @@ __device__ __forceinline__ void stage_substep_torque_cta(const TorqueSlabArgs& k
     for (int it = 0; it < IT_PD; ++it) {
       int idx = tid + it * nthreads;
       if (idx < nenv * NU) {
-        int le = idx / NU, d = 12 + idx - le * NU;
+        int le = dNU.div(idx), d = 12 + idx - le * NU;
         float t = __fadd_rn(__fmul_rn(kp[it], __fsub_rn(tgt[it], pos[it])), __fmul_rn(kv[it], -vel[it]));
         k.dof_actuation_force[(size_t)(e0 + le) * ND + d] = t;
         tau_sink(le, d, t);
@@ -168,7 +170,7 @@ __device__ __forceinline__ void stage_substep_torque_cta(const TorqueSlabArgs& k
     for (int it = 0; it < IT_RG; ++it) {                                          // loads
       int idx = tid + it * nthreads;
       idx = idx < nenv * 12 ? idx : 0;
-      int le = idx / 12, j = idx - le * 12;
+      int le = d12.div(idx), j = idx - le * 12;
       size_t e = (size_t)(e0 + le);
       sl[it] = k.simul_len[e];
       dl[it] = k.delay_idx[e];
@@ -181,7 +183,7 @@ __device__ __forceinline__ void stage_substep_torque_cta(const TorqueSlabArgs& k
     for (int it = 0; it < IT_RG; ++it) {
       int idx = tid + it * nthreads;
       if (idx < nenv * 12) {
-        int le = idx / 12, j = idx - le * 12;
+        int le = d12.div(idx), j = idx - le * 12;
         size_t e = (size_t)(e0 + le);
         int s1 = sl[it] + 1;                                                      // T:513-514
         s1 = s1 > LOG_DEPTH ? LOG_DEPTH : (s1 < 0 ? 0 : s1);
@@ -204,38 +206,53 @@ __device__ __forceinline__ void stage_substep_torque_cta(const TorqueSlabArgs& k
   }
 }
 
-// T:528-530 for a slab; `pos_of(le, d)` supplies the fresh joint angle (from shared memory in the fused kernel)
+// T:528-530 for a slab; `pos_of(le, d)` supplies the fresh joint angle (from shared memory in the fused kernel).
+// One thread handles a pair of DOFs (one Philox draw and one Box-Muller transform per pair).
 template <class PosFn>
 __device__ __forceinline__ void stage_sensor_noise_cta(const NoiseSlabArgs& k, int substep, int e0, int nenv, int tid, int nthreads, PosFn pos_of) {
   constexpr int THREADS = 128;
-  constexpr int IT = (kSlabMaxEnvs * ND + THREADS - 1) / THREADS;
+  constexpr int NP = (ND + 1) / 2;
+  constexpr int IT = (kSlabMaxEnvs * NP + THREADS - 1) / THREADS;
+  const FastDiv dNP(NP);
   const bool inject = k.qpos_normal != nullptr;
   const uint64_t epoch = inject ? 0 : *k.step_counter;
-  float pre[IT], nz[IT];
+  float pre[IT][2], nz[IT][2];
 #pragma unroll
   for (int it = 0; it < IT; ++it) {  // loads
     int idx = tid + it * nthreads;
-    idx = idx < nenv * ND ? idx : 0;
-    int le = idx / ND, d = idx - le * ND;
-    pre[it] = k.qpos_pre[(size_t)(e0 + le) * ND + d];
-    nz[it] = inject ? k.qpos_normal[((size_t)substep * k.N + e0 + le) * ND + d] : 0.f;
+    idx = idx < nenv * NP ? idx : 0;
+    int le = dNP.div(idx), pr = idx - le * NP;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int d = 2 * pr + h;
+      d = d < ND ? d : ND - 1;
+      pre[it][h] = k.qpos_pre[(size_t)(e0 + le) * ND + d];
+      nz[it][h] = inject ? k.qpos_normal[((size_t)substep * k.N + e0 + le) * ND + d] : 0.f;
+    }
   }
 #pragma unroll
   for (int it = 0; it < IT; ++it) {
     int idx = tid + it * nthreads;
-    if (idx < nenv * ND) {
-      int le = idx / ND, d = idx - le * ND;
-      size_t i = (size_t)(e0 + le) * ND + d;
-      float n = nz[it];
+    if (idx < nenv * NP) {
+      int le = dNP.div(idx), pr = idx - le * NP;
+      float2 nn = make_float2(0.f, 0.f);
       if (!inject) {
-        uint4 r = draw4(k.seed, epoch, e0 + le, kSiteQposNoise, substep * 64 + d);
-        n = __fmul_rn(normal01(r.x, r.y), k.noise_std);
+        uint4 r = draw4(k.seed, epoch, e0 + le, kSiteQposNoise, substep * 64 + pr);
+        nn = normal01_pair(r.x, r.y);
       }
-      n = (n < -0.00016f) ? -0.00016f : ((n > 0.00016f) ? 0.00016f : n);
-      float qn = __fadd_rn(pos_of(le, d), n);
-      k.qvel_noise[i] = __fdiv_rn(__fsub_rn(qn, pre[it]), k.dt);
-      k.qpos_noise[i] = qn;
-      k.qpos_pre[i] = qn;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        int d = 2 * pr + h;
+        if (d < ND) {
+          size_t i = (size_t)(e0 + le) * ND + d;
+          float n = inject ? nz[it][h] : __fmul_rn(h ? nn.y : nn.x, k.noise_std);
+          n = (n < -0.00016f) ? -0.00016f : ((n > 0.00016f) ? 0.00016f : n);
+          float qn = __fadd_rn(pos_of(le, d), n);
+          k.qvel_noise[i] = __fdiv_rn(__fsub_rn(qn, pre[it][h]), k.dt);
+          k.qpos_noise[i] = qn;
+          k.qpos_pre[i] = qn;
+        }
+      }
     }
   }
 }
