@@ -374,7 +374,13 @@ __device__ void stage_compute_observations(const TK& k, int e, int lane) {
   float* ob = k.b.obs_buf + (size_t)e * NOBS;
   const float* ah = k.b.action_history + (size_t)e * NSLOT * NA;
   int ahead = k.b.act_hist_head[e];
-  for (int o = lane; o < NOBS; o += kWarp) {
+  // gather: all loads first (the compiler cannot reorder them across the stores itself), then the stores
+  constexpr int IT = (NOBS + kWarp - 1) / kWarp;
+  float vals[IT];
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    int o = lane + it * kWarp;
+    o = o < NOBS ? o : NOBS - 1;
     float v;
     if (o < NOBS1 * NHIS) {                                                                         // T:789-791
       int i = o / NOBS1, j = o - i * NOBS1;
@@ -386,18 +392,44 @@ __device__ void stage_compute_observations(const TK& k, int e, int lane) {
       int pos = NSKIP * (i + 1);
       v = ah[((ahead + 1 + pos) % NSLOT) * NA + j];
     }
-    ob[o] = v;
+    vals[it] = v;
+  }
+#pragma unroll
+  for (int it = 0; it < IT; ++it) {
+    int o = lane + it * kWarp;
+    if (o < NOBS) ob[o] = vals[it];
   }
 }
 
-// T:560-563
+// T:560-563 (loads of all four copies are issued before the first store)
 __device__ void stage_late_update(const TK& k, int e, int lane) {
   const float* ds = k.s.dof_state + (size_t)e * ND * 2;
-  for (int d = lane; d < ND; d += kWarp) k.b.pre_joint_velocity_states[(size_t)e * ND + d] = ds[2 * d + 1];
-  if (lane < 12) k.b.action_torque_pre[(size_t)e * 12 + lane] = k.b.action_torque[(size_t)e * 12 + lane];
-  if (lane < NA) k.b.actions_pre[(size_t)e * NA + lane] = k.b.actions[(size_t)e * NA + lane];
-  for (int i = lane; i < NB * 3; i += kWarp)
-    k.b.contact_forces_pre[(size_t)e * NB * 3 + i] = k.s.net_contact_force[(size_t)e * NB * 3 + i];
+  constexpr int ITC = (NB * 3 + kWarp - 1) / kWarp;
+  float vel[2], cf[ITC], at = 0.f, ac = 0.f;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    int d = lane + it * kWarp;
+    vel[it] = ds[2 * (d < ND ? d : ND - 1) + 1];
+  }
+#pragma unroll
+  for (int it = 0; it < ITC; ++it) {
+    int i = lane + it * kWarp;
+    cf[it] = k.s.net_contact_force[(size_t)e * NB * 3 + (i < NB * 3 ? i : NB * 3 - 1)];
+  }
+  if (lane < 12) at = k.b.action_torque[(size_t)e * 12 + lane];
+  if (lane < NA) ac = k.b.actions[(size_t)e * NA + lane];
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    int d = lane + it * kWarp;
+    if (d < ND) k.b.pre_joint_velocity_states[(size_t)e * ND + d] = vel[it];
+  }
+  if (lane < 12) k.b.action_torque_pre[(size_t)e * 12 + lane] = at;
+  if (lane < NA) k.b.actions_pre[(size_t)e * NA + lane] = ac;
+#pragma unroll
+  for (int it = 0; it < ITC; ++it) {
+    int i = lane + it * kWarp;
+    if (i < NB * 3) k.b.contact_forces_pre[(size_t)e * NB * 3 + i] = cf[it];
+  }
 }
 
 // ------------------------------------------------------------------ kernels
