@@ -19,6 +19,29 @@ void set_error(const char* fmt, ...);
   } while (0)
 #define DY_LAUNCH_CHECK() DY_CUDA(cudaGetLastError())
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// The four kernels of one env-step are launched back to back on one stream. With the programmatic-stream-serialisation
+// attribute a kernel's CTAs may become resident (and run their preamble, e.g. staging the model tables) while the
+// previous kernel drains; griddepcontrol.wait then blocks until the previous grid has completed and flushed.
+// Without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 

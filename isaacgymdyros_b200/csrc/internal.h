@@ -131,16 +131,16 @@ int launch_sensor_noise(Task* t, int substep, cudaStream_t s);
 int launch_epilogue(Task* t, cudaStream_t s);
 int launch_check_termination(Task* t, cudaStream_t s);
 int launch_compute_reward(Task* t, cudaStream_t s);
-int launch_crossenv(Task* t, bool compact, bool gate, bool bump, cudaStream_t s);
+int launch_crossenv(Task* t, bool compact, bool gate, bool bump, cudaStream_t s, bool pdl = false);
 int launch_reset_idx(Task* t, const int64_t* env_ids, int count, cudaStream_t s);
 int launch_compute_observations(Task* t, cudaStream_t s);
 int launch_late_update(Task* t, cudaStream_t s);
-int launch_post_fused(Task* t, cudaStream_t s);
+int launch_post_fused(Task* t, cudaStream_t s, bool pdl = false);
 // launchers (physics_kernels.cu)
 int physics_configure(Sim* sim);  // chooses envs_per_block / shared memory, sets the kernel attributes
 int launch_simulate(Sim* sim, int apply_wrench, const float* push_force, cudaStream_t s);
 int launch_refresh_rigid_body_state(Sim* sim, cudaStream_t s);
-int launch_task_physics(Task* t, cudaStream_t s, long long* trace = nullptr);  // skipframe x (torque, simulate, sensor noise) in one launch
+int launch_task_physics(Task* t, cudaStream_t s, long long* trace = nullptr, bool pdl = false);  // skipframe x (torque, simulate, sensor noise) in one launch
 int measure_fp32_peak(int device, int iters, double* tflops_out);
 
 }  // namespace dyros

@@ -58,6 +58,8 @@ __device__ __forceinline__ PhysCta phys_cta_setup(const DevModel& m, const SimPa
   }
   int* flags = reinterpret_cast<int*>(smem + m.hot_bytes / 4);
   for (int i = threadIdx.x; i < F_COUNT; i += blockDim.x) flags[i] = 0;
+  pdl_launch_dependents();
+  pdl_wait();  // everything above is independent of the previous kernel of the step (model tables only)
   __syncthreads();
   PhysCta c;
   c.hot = smem;
@@ -265,7 +267,7 @@ int launch_simulate(Sim* sim, int apply_wrench, const float* push, cudaStream_t 
   return 0;
 }
 
-int launch_task_physics(Task* t, cudaStream_t s, long long* trace) {
+int launch_task_physics(Task* t, cudaStream_t s, long long* trace, bool pdl) {
   Sim* sim = t->sim;
   const int epb = sim->envs_per_block;
   const int grid = (sim->p.N + epb - 1) / epb;
@@ -274,8 +276,8 @@ int launch_task_physics(Task* t, cudaStream_t s, long long* trace) {
   k.b = t->b;
   k.s = sim->b;
   k.j = t->inj;
-  k_step_physics<<<grid, kPhysThreads, sim->phys_smem, s>>>(sim->m, sim->p, k, epb, env_scratch_floats(sim->m.nl), trace);
-  DY_LAUNCH_CHECK();
+  DY_CUDA(launch_kernel(k_step_physics, dim3(grid), dim3(kPhysThreads), sim->phys_smem, s, pdl, sim->m, sim->p, k, epb,
+                        env_scratch_floats(sim->m.nl), trace));
   return 0;
 }
 

@@ -439,6 +439,7 @@ __device__ void stage_late_update(const TK& k, int e, int lane) {
   if (e >= k.p.N) return;
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_prologue(TK k, const float* __restrict__ actions) {
+  pdl_launch_dependents();
   ENV_LANE();
   stage_prologue(k, actions, e, lane);
 }
@@ -508,6 +509,8 @@ __device__ __forceinline__ void prefetch_post_inputs(const TK& k, int e, int lan
 // post_physics_step in one launch: epilogue, termination, reward, reset, observations, late update.
 // Reward/termination read the pre-reset state, observations the post-reset state.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_post_fused(TK k) {
+  pdl_launch_dependents();
+  pdl_wait();
   ENV_LANE();
   prefetch_post_inputs(k, e, lane);
   stage_epilogue(k, e, lane);
@@ -534,6 +537,7 @@ __global__ void __launch_bounds__(kScanThreads) k_crossenv(TK k, int do_compact,
   __shared__ double red[2][kScanThreads / 32];
   int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   int N = k.p.N;
+  pdl_wait();
   if (do_compact) {
     if (tid == 0) base_sh = 0;
     __syncthreads();
@@ -619,7 +623,10 @@ int launch_check_termination(Task* t, cudaStream_t s) { LAUNCH_ENV(k_check_termi
 int launch_compute_reward(Task* t, cudaStream_t s) { LAUNCH_ENV(k_compute_reward) }
 int launch_compute_observations(Task* t, cudaStream_t s) { LAUNCH_ENV(k_compute_observations) }
 int launch_late_update(Task* t, cudaStream_t s) { LAUNCH_ENV(k_late_update) }
-int launch_post_fused(Task* t, cudaStream_t s) { LAUNCH_ENV(k_post_fused) }
+int launch_post_fused(Task* t, cudaStream_t s, bool pdl) {
+  DY_CUDA(launch_kernel(k_post_fused, dim3(env_grid(t->p.N)), dim3(kWarpsPerBlock * 32), 0, s, pdl, make_tk(t)));
+  return 0;
+}
 int launch_reset_idx(Task* t, const int64_t* env_ids, int count, cudaStream_t s) {
   if (count == 0) return 0;
   const int64_t* ids = env_ids ? env_ids : t->b.reset_env_ids;
@@ -628,9 +635,8 @@ int launch_reset_idx(Task* t, const int64_t* env_ids, int count, cudaStream_t s)
   DY_LAUNCH_CHECK();
   return 0;
 }
-int launch_crossenv(Task* t, bool compact, bool gate, bool bump, cudaStream_t s) {
-  k_crossenv<<<1, kScanThreads, 0, s>>>(make_tk(t), compact, gate, bump);
-  DY_LAUNCH_CHECK();
+int launch_crossenv(Task* t, bool compact, bool gate, bool bump, cudaStream_t s, bool pdl) {
+  DY_CUDA(launch_kernel(k_crossenv, dim3(1), dim3(kScanThreads), 0, s, pdl, make_tk(t), (int)compact, (int)gate, (int)bump));
   return 0;
 }
 
