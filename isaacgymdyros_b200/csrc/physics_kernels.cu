@@ -101,11 +101,11 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 __device__ __forceinline__ void slab_stage_inputs(const DevModel& m, const SimParams& p, const DyrosSimBuffers& b,
                                                   const float* push, const float* hot, float* envs, int es, int e0, int nenv,
-                                                  bool with_tau) {
+                                                  bool with_tau, bool with_state) {
   const int nd = m.nd, nb = m.nb, xoff = m.nl * LS;
   const int* dof_link = reinterpret_cast<const int*>(hot) + m.o_dof_link;
   const FastDiv d2nd(2 * nd), dnd(nd), dnb(nb), d13(13), d3(3);  // slabs are < 2^20 / divisor words (checked at create)
-  {
+  if (with_state) {  // joint state, mass scales and root: only before the first sub-step of a launch (they stay in the scratch)
     const float* src = b.dof_state + (size_t)e0 * nd * 2;
     for (int i = threadIdx.x; i < nenv * nd * 2; i += kPhysThreads) {
       int le = d2nd.div(i), w = i - le * 2 * nd;
@@ -124,14 +124,14 @@ __device__ __forceinline__ void slab_stage_inputs(const DevModel& m, const SimPa
       cp_async4(L + 3, arm + i);
     }
   }
-  {
+  if (with_state) {
     const float* src = b.body_mass_scale + (size_t)e0 * nb;
     for (int i = threadIdx.x; i < nenv * nb; i += kPhysThreads) {
       int le = dnb.div(i);
       cp_async4(envs + le * es + xoff + X_MASS + (i - le * nb), src + i);
     }
   }
-  {
+  if (with_state) {
     const float* src = b.root_states + (size_t)e0 * 13;
     for (int i = threadIdx.x; i < nenv * 13; i += kPhysThreads) {
       int le = d13.div(i);
@@ -169,9 +169,11 @@ __device__ __forceinline__ void slab_store_outputs(const DevModel& m, const Dyro
 // the register pressure of the role programs.
 __device__ __noinline__ void torque_stage_slab(TorqueSlabArgs k, int e0, int nenv, float* envs, int es, const int* dof_link) {
   CtaSync cta;
-  // the torques go to the API tensor and straight into the scratch blocks (no re-read through global memory)
-  stage_substep_torque_cta(k, e0, nenv, threadIdx.x, kPhysThreads, cta,
-                           [&](int le, int d, float v) { envs[le * es + dof_link[d] * LS + LS_SC + 1] = v; });
+  // joint state comes from the scratch blocks; the torques go to the API tensor and straight into the scratch blocks
+  stage_substep_torque_cta(
+      k, e0, nenv, threadIdx.x, kPhysThreads, cta,
+      [&](int le, int d, float v) { envs[le * es + dof_link[d] * LS + LS_SC + 1] = v; },
+      [&](int le, int d, int which) { return envs[le * es + dof_link[d] * LS + (which ? LS_SC : LS_Q)]; });
 }
 __device__ __noinline__ void noise_stage_slab(NoiseSlabArgs k, int substep, int e0, int nenv, const float* envs, int es, const int* dof_link) {
   // sensor noise reads the fresh joint angles from the scratch blocks
@@ -191,12 +193,11 @@ __global__ void __launch_bounds__(kPhysThreads) k_simulate(DevModel m, SimParams
   io.rb_torque = apply_wrench ? b.rb_torque + (size_t)c.e * m.nb * 3 : nullptr;
   RoleSync sync{c.lane, nullptr};
   for (int s = 0; s < p.substeps; ++s) {
-    slab_stage_inputs(m, p, b, s == 0 ? push : nullptr, c.hot, envs, es, e0, nenv, true);
+    slab_stage_inputs(m, p, b, s == 0 ? push : nullptr, c.hot, envs, es, e0, nenv, true, s == 0);
     __syncthreads();
     env_substep_role(io, c.sm, c.flags, s, c.hot, m, p, c.role, sync);
     __syncthreads();
-    slab_store_outputs(m, b, c.hot, envs, es, e0, nenv);
-    __syncthreads();
+    if (s + 1 == p.substeps) slab_store_outputs(m, b, c.hot, envs, es, e0, nenv);
     io.push = nullptr;  // applied wrenches act "for the immediate timestep" (gym_py.html apply_rigid_body_force_tensors)
     io.rb_force = nullptr;
     io.rb_torque = nullptr;
@@ -215,23 +216,27 @@ __global__ void __launch_bounds__(kPhysThreads) k_step_physics(DevModel m, SimPa
   RoleSync sync{c.lane, (trace && blockIdx.x == 0) ? trace + c.role * 32 : nullptr};
   const int* dof_link = reinterpret_cast<const int*>(c.hot) + m.o_dof_link;
   int epoch = 0;
+  // joint state, root and mass scales are staged once and then live in the scratch blocks for the whole launch; the
+  // torque and noise stages read them there, and only the final state is written back
+  slab_stage_inputs(m, p, k.s, nullptr, c.hot, envs, es, e0, nenv, false, true);
+  __syncthreads();
   for (int s = 0; s < k.p.skipframe; ++s) {
     sync.mark(13);
     torque_stage_slab(torque_args(k), e0, nenv, envs, es, dof_link);
     const float* push = s == 0 ? k.b.push_force : nullptr;  // the push acts on the first sub-step only (T:502 vs T:504)
     io.push = push;
     for (int ss = 0; ss < p.substeps; ++ss) {
-      slab_stage_inputs(m, p, k.s, push, c.hot, envs, es, e0, nenv, ss > 0);
+      // per sub-step inputs: damping / armature (their slots are reused by the recursion), push, zeroed contact forces
+      slab_stage_inputs(m, p, k.s, push, c.hot, envs, es, e0, nenv, ss > 0, false);
       __syncthreads();
       sync.mark(14);
       env_substep_role(io, c.sm, c.flags, epoch++, c.hot, m, p, c.role, sync);
       __syncthreads();
-      slab_store_outputs(m, k.s, c.hot, envs, es, e0, nenv);
       push = nullptr;
       io.push = nullptr;
-      if (ss + 1 < p.substeps) __syncthreads();
     }
-    noise_stage_slab(noise_args(k), s, e0, nenv, envs, es, dof_link);  // (the slab store above runs concurrently)
+    noise_stage_slab(noise_args(k), s, e0, nenv, envs, es, dof_link);
+    if (s + 1 == k.p.skipframe) slab_store_outputs(m, k.s, c.hot, envs, es, e0, nenv);
     __syncthreads();
     sync.mark(15);
     if (sync.trace) sync.trace += DYROS_LANES * 32;

@@ -131,9 +131,11 @@ __device__ __forceinline__ NoiseSlabArgs noise_args(const TK& k) {
   return NoiseSlabArgs{k.j.qpos_normal, k.b.qpos_pre, k.b.qvel_noise, k.b.qpos_noise, k.p.step_counter, k.p.seed,
                        k.p.noise_std, k.p.dt, k.p.N};
 }
-template <class Sync, class Sink>
+// `state_of(le, d, which)` supplies the joint angle (which = 0) / velocity (1): global dof_state or the fused kernel's
+// scratch blocks.
+template <class Sync, class Sink, class StateFn>
 __device__ __forceinline__ void stage_substep_torque_cta(const TorqueSlabArgs& k, int e0, int nenv, int tid, int nthreads,
-                                                         Sync& cta_sync, Sink tau_sink) {
+                                                         Sync& cta_sync, Sink tau_sink, StateFn state_of) {
   constexpr int NU = ND - 12;
   constexpr int THREADS = 128;
   const FastDiv dNU(NU), d12(12);
@@ -146,8 +148,8 @@ __device__ __forceinline__ void stage_substep_torque_cta(const TorqueSlabArgs& k
       idx = idx < nenv * NU ? idx : 0;
       int le = dNU.div(idx), d = 12 + idx - le * NU;
       size_t e = (size_t)(e0 + le);
-      pos[it] = k.dof_state[(e * ND + d) * 2];
-      vel[it] = k.dof_state[(e * ND + d) * 2 + 1];
+      pos[it] = state_of(le, d, 0);
+      vel[it] = state_of(le, d, 1);
       tgt[it] = k.target_data_qpos[e * ND + d];
       kp[it] = k.kp[d];
       kv[it] = k.kv[d];
