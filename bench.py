@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--force-perturb", action="store_true", help="pushes forced on (BASELINE configs[3]; T:491)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
 
@@ -182,6 +183,8 @@ def run_ours(a):
     torch.cuda.set_device(dev)
     N, K, W = a.envs, a.steps, max(a.warmup, 3)
     env = DyrosDynamicWalk(default_cfg(N), dev, rank=rank)
+    if a.force_perturb:
+        env.core.task_t["perturb_start"].fill_(1)
     g = torch.Generator(device=dev)
     g.manual_seed(42 + rank)  # reference default seed, cfg/config.yaml:11
     pool = [torch.rand(N, 13, device=dev, generator=g) * 2 - 1 for _ in range(16)]
@@ -279,7 +282,7 @@ def run_ours(a):
             "ms_per_step": cold_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": N, "actions": "torch.rand(N,13)*2-1, seed 42",
-                       "domain_randomisation": True, "perturbation": "gated as in the reference (T:489)",
+                       "domain_randomisation": True, "perturbation": "forced on (T:491)" if a.force_perturb else "gated as in the reference (T:489)",
                        "l2": "flushed between timed steps (256 MiB fill outside the timed intervals)",
                        "timing": "CUDA events per step on the launch stream, summed; max over ranks",
                        "launch_geometry": core.launch_info(), "reset_rate_last_step": reset_rate},

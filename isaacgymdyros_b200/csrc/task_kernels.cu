@@ -481,38 +481,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_late_update(TK k) {
   ENV_LANE();
   stage_late_update(k, e, lane);
 }
-// Touch every cache line an env's warp is going to read, up front: the stages below read ~6 KB per env from a dozen
-// tensors in dependent phases, and with a cold L2 each phase would otherwise pay its own HBM latency.
-__device__ __forceinline__ void prefetch_rows(const void* base, size_t row_bytes, int e, int lane) {
-  const char* p = static_cast<const char*>(base) + (size_t)e * row_bytes;
-  const char* first = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(p) & ~uintptr_t(127));
-  for (const char* q = first + (size_t)lane * 128; q < p + row_bytes; q += 32 * 128)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-}
-__device__ __forceinline__ void prefetch_post_inputs(const TK& k, int e, int lane) {
-  prefetch_rows(k.s.root_states, 13 * 4, e, lane);
-  prefetch_rows(k.s.dof_state, ND * 8, e, lane);
-  prefetch_rows(k.s.net_contact_force, NB * 12, e, lane);
-  prefetch_rows(k.b.contact_forces_pre, NB * 12, e, lane);
-  prefetch_rows(k.b.target_data_qpos, ND * 4, e, lane);
-  prefetch_rows(k.b.pre_joint_velocity_states, ND * 4, e, lane);
-  prefetch_rows(k.b.qpos_noise, ND * 4, e, lane);
-  prefetch_rows(k.b.qvel_noise, ND * 4, e, lane);
-  prefetch_rows(k.b.actions, NA * 4, e, lane);
-  prefetch_rows(k.b.actions_pre, NA * 4, e, lane);
-  prefetch_rows(k.b.obs_history, NSLOT * NOBS1 * 4, e, lane);
-  prefetch_rows(k.b.action_history, NSLOT * NA * 4, e, lane);
-  prefetch_rows(k.b.qpos_bias, 12 * 4, e, lane);
-  prefetch_rows(k.b.action_torque, 12 * 4, e, lane);
-}
-
 // post_physics_step in one launch: epilogue, termination, reward, reset, observations, late update.
 // Reward/termination read the pre-reset state, observations the post-reset state.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_post_fused(TK k) {
   pdl_launch_dependents();
   pdl_wait();
   ENV_LANE();
-  prefetch_post_inputs(k, e, lane);
   stage_epilogue(k, e, lane);
   __syncwarp();
   int reset = stage_check_termination(k, e, lane);
