@@ -97,6 +97,12 @@ __device__ __forceinline__ EnvIO env_io(const DevModel& m, const DyrosSimBuffers
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
+// one L2 prefetch per 128-byte line of a contiguous slab (thread t takes lines t, t + 128, ...)
+__device__ __forceinline__ void slab_prefetch_l2(const void* base, size_t bytes) {
+  const char* p = static_cast<const char*>(base);
+  for (size_t off = (size_t)threadIdx.x * 128; off < bytes; off += (size_t)kPhysThreads * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ void slab_stage_inputs(const DevModel& m, const SimParams& p, const DyrosSimBuffers& b,
@@ -216,6 +222,15 @@ __global__ void __launch_bounds__(kPhysThreads) k_step_physics(DevModel m, SimPa
   RoleSync sync{c.lane, (trace && blockIdx.x == 0) ? trace + c.role * 32 : nullptr};
   const int* dof_link = reinterpret_cast<const int*>(c.hot) + m.o_dof_link;
   int epoch = 0;
+  {  // with a cold L2, pull in what the torque and noise stages will read while the first staging is in flight
+    const size_t e = (size_t)e0;
+    slab_prefetch_l2(k.b.target_data_qpos + e * ND, (size_t)nenv * ND * 4);
+    slab_prefetch_l2(k.b.action_log + e * LOG_DEPTH * 12, (size_t)nenv * LOG_DEPTH * 12 * 4);
+    slab_prefetch_l2(k.b.action_torque + e * 12, (size_t)nenv * 12 * 4);
+    slab_prefetch_l2(k.b.qpos_pre + e * ND, (size_t)nenv * ND * 4);
+    slab_prefetch_l2(k.s.dof_damping + e * ND, (size_t)nenv * ND * 4);
+    slab_prefetch_l2(k.s.dof_armature + e * ND, (size_t)nenv * ND * 4);
+  }
   // joint state, root and mass scales are staged once and then live in the scratch blocks for the whole launch; the
   // torque and noise stages read them there, and only the final state is written back
   slab_stage_inputs(m, p, k.s, nullptr, c.hot, envs, es, e0, nenv, false, true);
