@@ -51,6 +51,7 @@ typedef struct {
   const double* dof_upper;    /* [nd] */
   const double* dof_vel_limit;/* [nd]  dof_prop['velocity'], T:372 */
   const double* dof_effort;   /* [nd]  MJCF ctrlrange; used only if clamp_effort */
+  const double* dof_stiffness;/* [nd]  joint spring about q = 0 (MJCF joint stiffness; NULL = none) */
   const int32_t* pt_link;     /* [np] */
   const int32_t* pt_body;     /* [np] */
   const double* pt_pos;       /* [np*3] */

@@ -107,6 +107,7 @@ def make_model_desc(t: ModelTables, cfg: "CoreConfig"):
                           ("body_inertia", f64(t.body_inertia), C.c_double),
                           ("dof_lower", f64(t.dof_lower), C.c_double), ("dof_upper", f64(t.dof_upper), C.c_double),
                           ("dof_vel_limit", f64(vel_limit), C.c_double), ("dof_effort", f64(t.dof_effort), C.c_double),
+                          ("dof_stiffness", f64(t.dof_stiffness), C.c_double),
                           ("pt_link", i32(t.pt_link), C.c_int32), ("pt_body", i32(t.pt_body), C.c_int32),
                           ("pt_pos", f64(t.pt_pos), C.c_double), ("pt_radius", f64(t.pt_radius), C.c_double),
                           ("pt_solver", i32(pt_solver), C.c_int32),
@@ -143,7 +144,9 @@ def measure_fp32_peak(device_index: int = 0, iters: int = 20000) -> float:
 
 class DyrosCore:
     def __init__(self, num_envs: int, device: str = "cuda:0", cfg: Optional[CoreConfig] = None,
-                 tables: Optional[ModelTables] = None, seed: int = 42, rank: int = 0):
+                 tables: Optional[ModelTables] = None, seed: int = 42, rank: int = 0, with_task: bool = True):
+        """with_task=False builds only the simulator (gym level) and accepts any supported articulation; the
+        DyrosDynamicWalk task state needs the 33-DOF / 38-body TOCABI model."""
         if not torch.cuda.is_available():
             raise native.DyrosError("DyrosCore needs a CUDA device (sm_100a); there is no CPU path")
         self.lib = native.load()
@@ -152,7 +155,9 @@ class DyrosCore:
         self.device = torch.device(device)
         self.tables = tables or ModelTables.load(os.path.join(ASSETS, "tocabi_tables.npz"))
         t = self.tables
-        if t.num_dofs != ND or t.num_bodies != NB:
+        self.with_task = with_task
+        self.nd, self.nb = t.num_dofs, t.num_bodies
+        if with_task and (t.num_dofs != ND or t.num_bodies != NB):
             raise native.DyrosError("DyrosDynamicWalk expects the 33-DOF / 38-body TOCABI model")
         self._keep = []  # host arrays referenced by the descriptors during the create calls
         self.sim_handle = C.c_void_p()
@@ -160,26 +165,36 @@ class DyrosCore:
         torch.cuda.set_device(self.device)
         self._alloc()
         self._create_sim()
-        self._create_task(seed + rank)
+        if with_task:
+            self._create_task(seed + rank)
 
     # ------------------------------------------------------------------ buffers
     def _alloc(self):
         N, dev, cfg = self.N, self.device, self.cfg
+        nd, nb = self.nd, self.nb
         z = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype, device=dev)
         s: Dict[str, torch.Tensor] = {}
         s["root_states"] = z(N, 13)
-        s["dof_state"] = z(N * ND, 2)
-        s["net_contact_force"] = z(N * NB, 3)
-        s["dof_actuation_force"] = z(N * ND)
-        s["dof_damping"] = torch.full((N, ND), cfg.dof_damping, device=dev)
-        s["dof_armature"] = torch.tensor(ARMATURE, device=dev).repeat(N, 1).contiguous()
-        s["body_mass_scale"] = torch.ones(N, NB, device=dev)
+        s["dof_state"] = z(N * nd, 2)
+        s["net_contact_force"] = z(N * nb, 3)
+        s["dof_actuation_force"] = z(N * nd)
+        if self.with_task:
+            s["dof_damping"] = torch.full((N, nd), cfg.dof_damping, device=dev)
+            s["dof_armature"] = torch.tensor(ARMATURE, device=dev).repeat(N, 1).contiguous()
+        else:  # the asset's own joint properties (MJCF damping / armature)
+            s["dof_damping"] = torch.tensor(self.tables.dof_damping, dtype=torch.float32, device=dev).repeat(N, 1).contiguous()
+            s["dof_armature"] = torch.tensor(self.tables.dof_armature, dtype=torch.float32, device=dev).repeat(N, 1).contiguous()
+        s["body_mass_scale"] = torch.ones(N, nb, device=dev)
         if cfg.with_rigid_body_state:
-            s["rigid_body_state"] = z(N * NB, 13)
+            s["rigid_body_state"] = z(N * nb, 13)
         if cfg.with_rb_force_tensors:
-            s["rb_force"] = z(N * NB, 3)
-            s["rb_torque"] = z(N * NB, 3)
+            s["rb_force"] = z(N * nb, 3)
+            s["rb_torque"] = z(N * nb, 3)
         self.sim_t = s
+        s["root_states"][:, 6] = 1.0
+        if not self.with_task:
+            self.task_t = {}
+            return
         tb: Dict[str, torch.Tensor] = {}
         for name, dt, shape in native.TASK_BUFFERS:
             full = tuple(shape[1:]) if (shape and shape[0] is None) else (N,) + tuple(shape)

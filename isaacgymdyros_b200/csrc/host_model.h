@@ -49,7 +49,7 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
   } while (0)
   const int nl = m->num_links, nb = m->num_bodies, nd = m->num_dofs, np = m->num_points, nc = m->num_cyls;
   if (nl < 1 || nl > DYROS_MAX_LINKS) MFAIL("num_links %d outside [1,%d]", nl, DYROS_MAX_LINKS);
-  if (nb < nl || nb > DYROS_MAX_BODIES) MFAIL("num_bodies %d outside [%d,%d]", nb, nl, DYROS_MAX_BODIES);
+  if (nb < 1 || nb > DYROS_MAX_BODIES) MFAIL("num_bodies %d outside [1,%d]", nb, DYROS_MAX_BODIES);
   if (nd != nl - 1) MFAIL("one revolute DOF per non-base link expected (links %d, dofs %d)", nl, nd);
   if (m->sched_slots < 1 || !m->sched) MFAIL("missing branch schedule");
   for (int l = 1; l < nl; ++l) {
@@ -144,16 +144,30 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
       for (int c = 0; c < 3; ++c) std::swap(dm.foot_pt_pos[0][k][c], dm.foot_pt_pos[1][k][c]);
     }
   }
-  for (int f = 0; f < dm.num_feet; ++f) {
-    std::vector<int> path;
-    for (int l = dm.foot_link[f]; l > 0; l = m->link_parent[l]) path.push_back(l);
-    if ((int)path.size() > MAX_CHAIN || path.empty()) MFAIL("solver link %d is %zu joints from the base (max %d)", dm.foot_link[f], path.size(),
-                MAX_CHAIN);
-    if ((int)path.size() * 2 < MAX_ACTIVE_PTS * 3)
-      MFAIL("solver link %d is only %zu joints from the base; the contact rows are parked in the chain's scratch blocks "
-            "(2 per link, %d needed)", dm.foot_link[f], path.size(), MAX_ACTIVE_PTS * 3);
-    dm.chain_len[f] = (int)path.size();
-    for (int k = 0; k < (int)path.size(); ++k) dm.chain[f][k] = path[path.size() - 1 - k];
+  // Leg chains hang off the lowest common ancestor (LCA) of the solver links (the base for TOCABI, the pelvis for the
+  // Humanoid); `shared` = links from the base down to the LCA (exclusive of the base, inclusive of the LCA).
+  {
+    std::vector<std::vector<int>> paths(dm.num_feet);
+    for (int f = 0; f < dm.num_feet; ++f) {
+      for (int l = dm.foot_link[f]; l > 0; l = m->link_parent[l]) paths[f].push_back(l);
+      std::reverse(paths[f].begin(), paths[f].end());
+    }
+    size_t common = 0;
+    if (dm.num_feet == 2)
+      while (common < paths[0].size() && common < paths[1].size() && paths[0][common] == paths[1][common]) ++common;
+    if (common > (size_t)MAX_CHAIN) MFAIL("%zu links between the base and the feet's common ancestor (max %d)", common, MAX_CHAIN);
+    dm.shared_len = (int)common;
+    for (size_t k = 0; k < common; ++k) dm.shared[k] = paths[0][k];
+    dm.lca = common ? paths[0][common - 1] : 0;
+    for (int f = 0; f < dm.num_feet; ++f) {
+      const int len = (int)paths[f].size() - (int)common;
+      if (len > MAX_CHAIN || len < 1) MFAIL("solver link %d is %d joints below the common ancestor (1..%d)", dm.foot_link[f], len, MAX_CHAIN);
+      if (len * 2 < MAX_ACTIVE_PTS * 3)
+        MFAIL("solver link %d is only %d joints below the common ancestor; the contact rows are parked in the chain's "
+              "scratch blocks (2 per link, %d needed)", dm.foot_link[f], len, MAX_ACTIVE_PTS * 3);
+      dm.chain_len[f] = len;
+      for (int k = 0; k < len; ++k) dm.chain[f][k] = paths[f][common + k];
+    }
   }
   for (int f = 0; f < dm.num_feet; ++f) {
     dm.foot_role[f] = role_of[dm.foot_link[f]];
@@ -174,13 +188,6 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
     role_of[0] = best;
     for (int g = 0; g < DYROS_LANES; ++g) dm.role_len[g] = role_len[g];
   }
-  if (dm.num_feet == 2) {  // the two chains must only share the base (block-Jacobi coupling goes through the base)
-    for (int a = 0; a < dm.chain_len[0]; ++a)
-      for (int c = 0; c < dm.chain_len[1]; ++c)
-        if (dm.chain[0][a] == dm.chain[1][c]) MFAIL("solver links %d and %d share link %d below the base", dm.foot_link[0],
-                    dm.foot_link[1], dm.chain[0][a]);
-  }
-
   // per-link bounding radius of the penalty candidates about the link origin (early-out of the contact loops)
   std::vector<float> reach(nl, 0.f);
   for (int l = 0; l < nl; ++l) {
@@ -236,6 +243,7 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
         F(k, R_LO) = (float)m->dof_lower[d];
         F(k, R_UP) = (float)m->dof_upper[d];
         F(k, R_EFF) = (float)m->dof_effort[d];
+        F(k, R_STIFF) = m->dof_stiffness ? (float)m->dof_stiffness[d] : 0.f;
       }
       R[R_FOOT] = -1;
       for (int f = 0; f < dm.num_feet; ++f)
@@ -244,6 +252,7 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
     o.pg = bl.add_i(prog.data(), prog.size());
     for (int f = 0; f < dm.num_feet; ++f)
       for (int k = 0; k < dm.chain_len[f]; ++k) dm.chain_rec[f][k] = rec_of[dm.chain[f][k]];
+    for (int k = 0; k < dm.shared_len; ++k) dm.shared_rec[k] = rec_of[dm.shared[k]];
     for (int g = 0; g < DYROS_LANES; ++g) {
       dm.n_xchild[g] = 0;
       for (int t = 0; t < role_len[g]; ++t) {

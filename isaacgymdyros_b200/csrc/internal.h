@@ -10,7 +10,7 @@ constexpr int LOG_DEPTH = 6;                                                    
 
 // float32 device copies of the model tables (see model/tables.py for the meaning of each array) plus
 // tables derived at create time (children lists, per-link candidate ranges, foot chains)
-constexpr int MAX_CHAIN = 8;   // links between the base and a solver (foot) link
+constexpr int MAX_CHAIN = 8;   // links between the feet's common ancestor and a solver (foot) link / the base and that ancestor
 constexpr int MAX_FEET = 2;    // solver links
 constexpr int MAX_SOLVER_PTS = 8;  // candidate solver points per foot
 constexpr int MAX_ACTIVE_PTS = 4;  // active (constraint-solved) points per foot and sub-step
@@ -18,7 +18,7 @@ constexpr int MAX_ACTIVE_PTS = 4;  // active (constraint-solved) points per foot
 constexpr int REC_WORDS = 40, MAX_LINK_BODIES = 3, MAX_LINK_CHILDREN = 3, REC_FOREIGN = 1 << 30;
 constexpr int R_LINK = 0, R_PARENT = 1, R_FLAGS = 2, R_DOF = 3, R_NBODY = 4, R_BODY0 = 5, R_NCHILD = 8, R_CHILD0 = 9,
               R_AXIS = 12, R_R = 15, R_E = 18, R_REACH = 27, R_PT0 = 28, R_PT1 = 29, R_CYL0 = 30, R_CYL1 = 31,
-              R_VLIM = 32, R_LO = 33, R_UP = 34, R_EFF = 35, R_FOOT = 36;
+              R_VLIM = 32, R_LO = 33, R_UP = 34, R_EFF = 35, R_FOOT = 36, R_STIFF = 37;
 constexpr int RF_PARENT_FOREIGN = 1, RF_PARENT_BASE = 2;
 struct DevModel {
   int nl, nb, nd, np, nc, T;
@@ -58,6 +58,7 @@ struct DevModel {
   int base_role, foot_role[MAX_FEET], role_len[DYROS_LANES];
   // flattened role programs: one record of REC_WORDS words per link, base first, then role 0's links in order, ...
   int o_prog, prog_start[DYROS_LANES], chain_rec[MAX_FEET][MAX_CHAIN];
+  int lca, shared_len, shared[MAX_CHAIN], shared_rec[MAX_CHAIN];  // base -> common ancestor of the feet (0 = the base itself)
   int n_xchild[DYROS_LANES], xchild[DYROS_LANES][8];  // children of the role's links that live in other roles
   int num_feet;
   int foot_link[MAX_FEET];

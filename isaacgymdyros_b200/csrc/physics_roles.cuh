@@ -40,7 +40,8 @@ constexpr int X_PD = X_Z + 2 * MAX_FEET * 6;         // MAX_FEET * 6  impulse ar
 constexpr int X_G0 = X_PD + MAX_FEET * 6;            // MAX_FEET * 6  g = S^T G of the first leg-chain link (see A_G)
 constexpr int X_ROOT = X_G0 + MAX_FEET * 6;          // 13 (+3 pad): root state in, root state out
 constexpr int X_PUSH = X_ROOT + 13;                  // 3  world force at the base body's COM for this sub-step
-constexpr int X_MASS = X_ROOT + 16;                  // DYROS_MAX_BODIES per-body mass scale
+constexpr int X_OML = X_ROOT + 16;                   // 21 (+3 pad): inverse inertia at the feet's common ancestor (LCA)
+constexpr int X_MASS = X_OML + 24;                   // DYROS_MAX_BODIES per-body mass scale
 constexpr int X_SIZE = X_MASS + DYROS_MAX_BODIES;
 
 HD int env_scratch_floats(int nl) {
@@ -52,7 +53,8 @@ HD int env_scratch_floats(int nl) {
 constexpr int F_LINK = 0;                         // [DYROS_MAX_LINKS]
 constexpr int F_Z = DYROS_MAX_LINKS;              // [MAX_FEET] sweeps published
 constexpr int F_PD = F_Z + MAX_FEET;              // [MAX_FEET] base impulse published
-constexpr int F_COUNT = F_PD + MAX_FEET;
+constexpr int F_OML = F_PD + MAX_FEET;            // [1] inverse inertia at the LCA published
+constexpr int F_COUNT = F_OML + 1;
 constexpr int ST_PASS1 = 1, ST_PASS2 = 2, ST_PASS3 = 3, ST_DOWN = 4, ST_STRIDE = 8;
 
 // The hot model tables are read from the staged copy `hot` (shared memory on the GPU) through word offsets.
@@ -102,9 +104,10 @@ HD void penalty_point(const SimParams& p, const M3& Rw, SV v, V3 xs, real depth,
 // Rigid inertia of the link of record R from the hot body table and the env's per-body mass scales (X_MASS).
 HD ABI link_inertia(const real* X, const float* hot, const DevModel& m, const float* R) {
   real par[10];
-  {  // first body (most links have exactly one): straight-line code
-    int b = RI(R, R_BODY0);
-    real sc = X[X_MASS + b];
+  {  // first body (most links have exactly one): straight-line code; massless links (extra hinges of a body) have none
+    const bool any = RI(R, R_NBODY) > 0;
+    int b = any ? RI(R, R_BODY0) : 0;
+    real sc = any ? X[X_MASS + b] : (real)0;
 #pragma unroll
     for (int k = 0; k < 10; ++k) par[k] = sc * HF(body_inertia, b * 10 + k);
   }
@@ -295,10 +298,11 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
       real lim = R[R_EFF];
       tq = tq > lim ? lim : (tq < -lim ? -lim : tq);
     }
+    const real stiff = R[R_STIFF];  // joint spring about q = 0, implicit like the damping
     SV U{mul(IA.I, ax), mulT(IA.H, ax)};
-    real D = dot(ax, U.w) + arm + dt * damp;
+    real D = dot(ax, U.w) + arm + dt * (damp + dt * stiff);
     real Dinv = 1 / D;
-    real u = tq - damp * qd - dot(ax, pA.w);
+    real u = tq - damp * qd - stiff * (L[LS_Q] + dt * qd) - dot(ax, pA.w);
     V3 aq = qd * ax;
     SV c{cross(v.w, aq), cross(v.v, aq)};
     ABI Ia = rank1_sub(IA, U, Dinv);
@@ -340,6 +344,20 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     st6(L + LS_U, vs);
     st3(L + LS_SC, dt * cross(v0.w, v0.v));  // rotating-frame term of the world-frame linear velocity update
     sync.signal(fl + 0, base + ST_PASS2);
+    // inverse inertia at the feet's common ancestor: Om_j = L_j^T Om_parent L_j + S D^-1 S^T down the shared links
+    ABI Oml = Om0;
+    for (int k = 0; k < m.shared_len; ++k) {
+      const float* Rs = REC(m.shared_rec[k]);
+      const real* Ls = BLK(RI(Rs, R_LINK));
+      V3 axs = ld3_f(Rs + R_AXIS), rs = ld3_f(Rs + R_R);
+      M3 Es = ld_m3(Ls + LS_E);
+      real Dinv = Ls[LS_SC + 2];
+      SV w = Dinv * xform_force_T(Es, rs, ld6(Ls + LS_U));
+      SV y = mul(Oml, w);
+      Oml = inv_joint_update(inv_to_child(Es, rs, Oml), axs, xform_motion(Es, rs, y), dot(w, y) + Dinv);
+    }
+    st_abi(X + X_OML, Oml);
+    sync.signal(flags + F_OML, epoch + 1);
   }
   sync.mark(4);
   // ---- feet, part 1 (needs pass 2 of the own leg chain only): up the chain, G = map foot force -> force on the
@@ -410,9 +428,18 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
   if (foot >= 0) {
     const int g = foot;
     const int clen = m.chain_len[g];
-    SV Y[6];              // Om0 G
+    SV Y[6];              // Om_lca G
     SV V = ld6(BLK(0) + LS_U);  // base role published v0* with ST_PASS2 (waited for in pass 3)
     SV P = sv_zero();     // accumulated contact impulse on the foot (foot coordinates)
+    if (m.shared_len > 0) {  // predicted velocity of the common ancestor (needs pass 3 of the shared links)
+      sync.wait(fl + m.lca, base + ST_PASS3);
+      for (int k = 0; k < m.shared_len; ++k) {
+        const float* Rs = REC(m.shared_rec[k]);
+        const real* Ls = BLK(RI(Rs, R_LINK));
+        V = xform_motion(ld_m3(Ls + LS_E), ld3_f(Rs + R_R), V);
+        V.w = V.w + Ls[LS_SC] * ld3_f(Rs + R_AXIS);
+      }
+    }
     for (int k = 0; k < clen; ++k) {
       const float* R = REC(m.chain_rec[g][k]);
       const real* L = BLK(RI(R, R_LINK));
@@ -420,7 +447,8 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
       V.w = V.w + L[LS_SC] * ld3_f(R + R_AXIS);
     }
     {
-      ABI Om0 = ld_abi(BLK(0) + LS_A + A_OM0);
+      sync.wait(flags + F_OML, epoch + 1);
+      ABI Om0 = ld_abi(X + X_OML);  // inverse inertia at the common ancestor (= the base's for TOCABI)
 #pragma unroll
       for (int c = 0; c < 6; ++c) Y[c] = mul(Om0, G[c]);
       real w[6][6];
@@ -546,7 +574,14 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     SV pd = sv_zero();
     for (int f = 0; f < m.num_feet; ++f) {
       sync.wait(flags + F_PD + f, epoch + 1);
-      pd = pd + ld6(X + X_PD + 6 * f);
+      pd = pd + ld6(X + X_PD + 6 * f);  // impulse arriving at the common ancestor
+    }
+    for (int k = m.shared_len - 1; k >= 0; --k) {  // ... and from there up the shared links to the base
+      const float* Rs = REC(m.shared_rec[k]);
+      real* Ls = BLK(RI(Rs, R_LINK));
+      real sd = dot(ld3_f(Rs + R_AXIS), pd.w);
+      Ls[LS_SC + 3] = sd;
+      pd = xform_force_T(ld_m3(Ls + LS_E), ld3_f(Rs + R_R), pd - (Ls[LS_SC + 2] * sd) * ld6(Ls + LS_U));
     }
     st6(BLK(0) + LS_V, (real)-1 * mul(ld_abi(BLK(0) + LS_A + A_OM0), pd));
     sync.signal(fl + 0, base + ST_DOWN);

@@ -225,12 +225,13 @@ class Gym:
     def load_asset(self, sim: Sim, rootpath: str, filename: str, options: Optional[AssetOptions] = None):
         options = options or AssetOptions()
         path = os.path.join(rootpath, filename)
+        bundled = {"dyros_tocabi.xml": "tocabi_tables.npz", "nv_humanoid.xml": "humanoid_tables.npz"}
         if os.path.isfile(path):
-            model = load_mjcf(path)
-            feet = [b.name for b in model.bodies if b.name.endswith("_Foot_Link")]
-            tables = build_tables(model, solver_bodies=feet)
-        elif os.path.basename(filename) == "dyros_tocabi.xml":
-            tables = ModelTables.load(os.path.join(ASSETS, "tocabi_tables.npz"))  # bundled import of the same MJCF
+            model = load_mjcf(path, infer_missing_inertia=os.path.basename(filename) != "dyros_tocabi.xml",
+                              geom_density=options.density)
+            tables = build_tables(model, solver_bodies=[b.name for b in model.bodies if _is_foot(b.name)], vel_limit=1.0e3)
+        elif os.path.basename(filename) in bundled:
+            tables = ModelTables.load(os.path.join(ASSETS, bundled[os.path.basename(filename)]))  # bundled import of the same MJCF
         else:
             print(f"*** Failed to load asset {path}")
             return None
@@ -279,7 +280,7 @@ class Gym:
         props["hasLimits"] = True
         props["lower"], props["upper"] = t.dof_lower, t.dof_upper
         props["driveMode"] = asset.options.default_dof_drive_mode
-        props["velocity"] = 3.4e38
+        props["velocity"] = 1.0e3
         props["effort"] = t.dof_effort
         props["damping"] = t.dof_damping
         props["armature"] = np.maximum(t.dof_armature, asset.options.armature)
@@ -390,10 +391,12 @@ class Gym:
         cfg = _cfg_from_sim(sim)
         vel = np.stack([p["velocity"] for p in sim.dof_props])
         cfg.dof_vel_limit = float(min(vel.min(), 1.0e9))
-        core = DyrosCore(N, f"cuda:{sim.compute_device}", cfg, tables=sim.asset.tables) if _is_tocabi(sim.asset.tables) \
-            else None
-        if core is None:
-            print("*** prepare_sim: only the 33-DOF / 38-body TOCABI tree is wired to the task buffers in this round")
+        t = sim.asset.tables
+        cfg.solver_bodies = tuple(n for n in t.body_names if _is_foot(n))
+        try:  # the DyrosDynamicWalk task buffers exist only for the TOCABI tree; any other articulation is simulator-only
+            core = DyrosCore(N, f"cuda:{sim.compute_device}", cfg, tables=t, with_task=_is_tocabi(t))
+        except native.DyrosError as e:
+            print(f"*** prepare_sim: {e}")
             return False
         dev = core.device
         core.sim_t["dof_damping"].copy_(torch.tensor(np.stack([p["damping"] for p in sim.dof_props]), device=dev))
@@ -531,6 +534,12 @@ class Gym:
 
     def query_viewer_has_closed(self, *a, **k):
         return False
+
+
+def _is_foot(body_name: str) -> bool:
+    """Bodies whose ground contact is constraint-solved: `*_Foot_Link` (TOCABI), `right_foot` / `left_foot` (Humanoid)."""
+    import re
+    return re.search(r"(^|_)foot(_link)?$", body_name, re.IGNORECASE) is not None
 
 
 def _is_tocabi(t: ModelTables) -> bool:

@@ -57,6 +57,11 @@ class ModelTables:
     solver_links: np.ndarray  # links whose ground contacts go through the PGS solver (feet)
     sched: np.ndarray  # (T, G) int32
     meta: dict = field(default_factory=dict)
+    dof_stiffness: np.ndarray = None  # joint spring about q = 0 (MJCF `stiffness`); zeros for TOCABI
+
+    def __post_init__(self):
+        if self.dof_stiffness is None:
+            self.dof_stiffness = np.zeros(len(self.dof_names))
 
     @property
     def num_bodies(self) -> int:
@@ -80,6 +85,7 @@ class ModelTables:
 
     def save(self, path: str) -> None:
         d = {k: getattr(self, k) for k in self._ARRAYS}
+        d["dof_stiffness"] = self.dof_stiffness
         d["names_json"] = np.frombuffer(json.dumps(
             {"body_names": self.body_names, "dof_names": self.dof_names, "meta": self.meta}).encode(), dtype=np.uint8)
         np.savez_compressed(path, **d)
@@ -89,6 +95,7 @@ class ModelTables:
         z = np.load(path)
         names = json.loads(bytes(z["names_json"]).decode())
         return cls(body_names=names["body_names"], dof_names=names["dof_names"], meta=names.get("meta", {}),
+                   dof_stiffness=z["dof_stiffness"] if "dof_stiffness" in z.files else None,
                    **{k: z[k] for k in cls._ARRAYS})
 
 
@@ -197,11 +204,10 @@ def build_tables(model: RobotModel, *, solver_bodies: List[str], vel_limit: floa
     link_body = []  # representative body of each link
     link_parent, link_E, link_r, link_axis, link_dof = [], [], [], [], []
     dof_names, lo, up, arm, damp, eff = [], [], [], [], [], []
+    stiff = []
     for bi, b in enumerate(model.bodies):
         hinges = [j for j in b.joints if j.type == "hinge"]
         frees = [j for j in b.joints if j.type == "free"]
-        if len(hinges) > 1:
-            raise NotImplementedError("multi-hinge bodies (Humanoid-style) are a later row (SURVEY section 8f)")
         if b.parent < 0:
             if not frees:
                 raise NotImplementedError("fixed-base articulations are not on this path")
@@ -221,26 +227,35 @@ def build_tables(model: RobotModel, *, solver_bodies: List[str], vel_limit: floa
         R_rel = Rp @ b.rot
         p_rel = pp + Rp @ b.pos
         if hinges:
-            j = hinges[0]
-            if np.linalg.norm(j.pos) > 0:
-                raise NotImplementedError("joint pos offset inside body")
-            l = len(link_parent)
-            body_link[bi] = l
-            body_pos[bi] = 0.0
+            # One link per hinge. A body with k hinges (MuJoCo applies them in order, each about its anchor) becomes a
+            # chain of k links: the first k-1 are massless, the body itself rides on the last one. Every link frame has
+            # the body's orientation at q = 0 and its origin at the hinge's anchor.
+            prev_anchor = None
+            for t, j in enumerate(hinges):
+                l = len(link_parent)
+                if t == 0:
+                    link_parent.append(int(pl))
+                    link_E.append(R_rel.T)
+                    link_r.append(p_rel + R_rel @ j.pos)
+                else:
+                    link_parent.append(l - 1)
+                    link_E.append(np.eye(3))
+                    link_r.append(j.pos - prev_anchor)
+                prev_anchor = j.pos
+                link_axis.append(j.axis)
+                link_dof.append(len(dof_names))
+                link_body.append(bi)
+                dof_names.append(j.name)
+                lo.append(min(j.range))
+                up.append(max(j.range))
+                arm.append(j.armature)
+                damp.append(j.damping if j.damping else default_damping)
+                stiff.append(j.stiffness)
+                lim = model.actuators.get(j.name, (-np.inf, np.inf, 1.0))
+                eff.append(max(abs(lim[0]), abs(lim[1])) * abs(lim[2]))
+            body_link[bi] = len(link_parent) - 1
+            body_pos[bi] = -prev_anchor
             body_rot[bi] = np.eye(3)
-            link_body.append(bi)
-            link_parent.append(int(pl))
-            link_E.append(R_rel.T)
-            link_r.append(p_rel)
-            link_axis.append(j.axis)
-            link_dof.append(len(dof_names))
-            dof_names.append(j.name)
-            lo.append(min(j.range))
-            up.append(max(j.range))
-            arm.append(j.armature)
-            damp.append(j.damping if j.damping else default_damping)
-            lim = model.actuators.get(j.name, (-np.inf, np.inf, 1.0))
-            eff.append(max(abs(lim[0]), abs(lim[1])))
         else:  # fixed: merge
             body_link[bi] = pl
             body_pos[bi] = p_rel
@@ -289,7 +304,7 @@ def build_tables(model: RobotModel, *, solver_bodies: List[str], vel_limit: floa
         link_E=f64(link_E, (nl, 9)), link_r=f64(link_r, (nl, 3)), link_axis=f64(link_axis, (nl, 3)),
         body_link=body_link, body_pos=body_pos, body_rot=body_rot.reshape(nb, 9), body_inertia=body_inertia,
         dof_lower=f64(lo, -1), dof_upper=f64(up, -1), dof_armature=f64(arm, -1), dof_damping=f64(damp, -1),
-        dof_vel_limit=np.full(len(dof_names), float(vel_limit)), dof_effort=f64(eff, -1),
+        dof_vel_limit=np.full(len(dof_names), float(vel_limit)), dof_effort=f64(eff, -1), dof_stiffness=f64(stiff, -1),
         pt_link=np.array(pt_link, dtype=np.int32), pt_body=np.array(pt_body, dtype=np.int32),
         pt_pos=f64(pt_pos, (-1, 3)), pt_radius=f64(pt_rad, -1),
         cyl_link=np.array(cyl_link, dtype=np.int32), cyl_body=np.array(cyl_body, dtype=np.int32),

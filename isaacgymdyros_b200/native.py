@@ -22,7 +22,7 @@ class DyrosModelDesc(C.Structure):
     _fields_ = [(n, i32) for n in ("num_links", "num_bodies", "num_dofs", "num_points", "num_cyls", "sched_slots")] + [
         ("link_parent", P_i32), ("link_dof", P_i32), ("link_E", P_f64), ("link_r", P_f64), ("link_axis", P_f64),
         ("body_link", P_i32), ("body_pos", P_f64), ("body_rot", P_f64), ("body_inertia", P_f64),
-        ("dof_lower", P_f64), ("dof_upper", P_f64), ("dof_vel_limit", P_f64), ("dof_effort", P_f64),
+        ("dof_lower", P_f64), ("dof_upper", P_f64), ("dof_vel_limit", P_f64), ("dof_effort", P_f64), ("dof_stiffness", P_f64),
         ("pt_link", P_i32), ("pt_body", P_i32), ("pt_pos", P_f64), ("pt_radius", P_f64), ("pt_solver", P_i32),
         ("cyl_link", P_i32), ("cyl_body", P_i32), ("cyl_center", P_f64), ("cyl_axis", P_f64), ("cyl_size", P_f64),
         ("sched", P_i32)]

@@ -178,12 +178,13 @@ class PhysicsOracle:
             fi = fi - self._external_wrench(i, Rw[i], pw[i], v[i], contact, par, push, rb_force, rb_torque)
             h += np.einsum("nji,nj->ni", J[i], fi)
         idx = np.arange(nd)
-        M[:, 6 + idx, 6 + idx] += armature + dt * damping
+        stiff = np.asarray(getattr(t, "dof_stiffness", np.zeros(nd)), float)  # joint spring about q = 0, implicit
+        M[:, 6 + idx, 6 + idx] += armature + dt * damping + dt * dt * stiff
         tq = tau.copy()
         if p.clamp_effort:
             tq = np.clip(tq, -t.dof_effort, t.dof_effort)
         rhs = -h
-        rhs[:, 6:] += tq - damping * qd
+        rhs[:, 6:] += tq - damping * qd - stiff * (q + dt * qd)
         Minv = np.linalg.inv(M)
         acc = np.einsum("nij,nj->ni", Minv, rhs)
         vstar = vgen + dt * acc

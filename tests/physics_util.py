@@ -91,7 +91,7 @@ def emulate_substep(tables, cfg, st, push=None, rb_force=None, rb_torque=None):
     root = f32(st["root"])
     dof = f32(np.stack([st["q"], st["qd"]], -1))
     tau, damp, arm, ms = f32(st["tau"]), f32(st["damping"]), f32(st["armature"]), f32(st["mass_scale"])
-    contact = np.zeros((N, 38, 3), np.float32)
+    contact = np.zeros((N, tables.num_bodies, 3), np.float32)
     P = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
     pf = f32(push) if push is not None else None
     rf = f32(rb_force) if rb_force is not None else None

@@ -98,3 +98,40 @@ def test_create_sim_failure_returns_none():
     from isaacgymdyros_b200 import gymapi
     gym = gymapi.acquire_gym()
     assert gym.create_sim(0, -1, gymapi.SIM_FLEX, gymapi.SimParams()) is None  # caller quits (vec_task.py:270-273)
+
+
+def test_humanoid_through_the_gym_api():
+    """BASELINE configs[2] at the gym level: load_asset / create_actor / prepare_sim / tensor API / simulate on the stock
+    Humanoid MJCF (Humanoid.yaml: dt 1/60 in 2 sub-steps, contact_offset 0.02)."""
+    from isaacgymdyros_b200 import gymapi, gymtorch
+    gym = gymapi.acquire_gym()
+    sp = gymapi.SimParams()
+    sp.dt, sp.substeps, sp.up_axis = 0.0166, 2, gymapi.UP_AXIS_Z
+    sp.gravity = gymapi.Vec3(0.0, 0.0, -9.81)
+    sp.physx.contact_offset, sp.physx.num_position_iterations, sp.physx.num_velocity_iterations = 0.02, 4, 0
+    sim = gym.create_sim(0, -1, gymapi.SIM_PHYSX, sp)
+    pp = gymapi.PlaneParams()
+    pp.normal = gymapi.Vec3(0.0, 0.0, 1.0)
+    gym.add_ground(sim, pp)
+    asset = gym.load_asset(sim, "../../assets", "mjcf/nv_humanoid.xml", gymapi.AssetOptions())
+    assert gym.get_asset_rigid_body_count(asset) == 16 and gym.get_asset_dof_count(asset) == 21
+    N = 64
+    for i in range(N):
+        env = gym.create_env(sim, gymapi.Vec3(0, 0, 0), gymapi.Vec3(0, 0, 0), 8)
+        gym.create_actor(env, asset, gymapi.Transform(gymapi.Vec3(2.0 * i, 0.0, 1.34), gymapi.Quat(0, 0, 0, 1)), "humanoid", i, 0, 0)
+    assert gym.prepare_sim(sim)
+    root = gymtorch.wrap_tensor(gym.acquire_actor_root_state_tensor(sim))
+    dof = gymtorch.wrap_tensor(gym.acquire_dof_state_tensor(sim))
+    contact = gymtorch.wrap_tensor(gym.acquire_net_contact_force_tensor(sim))
+    assert root.shape == (N, 13) and dof.shape == (N * 21, 2) and contact.shape == (N * 16, 3)
+    tau = torch.zeros(N * 21, device=root.device)
+    for _ in range(60):  # one second: the humanoids drop 5 cm onto their feet
+        gym.set_dof_actuation_force_tensor(sim, gymtorch.unwrap_tensor(tau))
+        gym.simulate(sim)
+    gym.fetch_results(sim, True)
+    assert torch.isfinite(root).all() and torch.isfinite(dof).all()
+    feet = [13, 9] if False else [gym.find_asset_rigid_body_index(asset, "right_foot"), gym.find_asset_rigid_body_index(asset, "left_foot")]
+    cf = contact.view(N, 16, 3)
+    assert (cf[:, feet, 2].sum(1) > 50.0).all()  # standing or crouching on the soles
+    assert (root[:, 2] > 0.3).all() and (root[:, 2] < 1.4).all()
+    gym.destroy_sim(sim)
