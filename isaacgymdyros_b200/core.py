@@ -73,6 +73,12 @@ class CoreConfig:
     with_rb_force_tensors: bool = False  # generic apply_rigid_body_force_tensors buffers
 
 
+def stable_penalty(dt_substep: float, m_ref: float = 0.3):
+    """Penalty (non-foot) ground contact is integrated explicitly: stiffness k and damping c are only stable for
+    k dt^2 / m <~ 1 and c dt / m <~ 1. Returns (k, c) for a reference link mass, capped at the TOCABI defaults."""
+    return min(2.0e5, 0.5 * m_ref / dt_substep ** 2), min(2.0e3, 0.5 * m_ref / dt_substep)
+
+
 def _np_ptr(a: np.ndarray, ctype):
     return a.ctypes.data_as(C.POINTER(ctype))
 

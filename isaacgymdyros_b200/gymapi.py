@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import native
-from .core import ARMATURE, ASSETS, CoreConfig, DyrosCore
+from .core import ARMATURE, ASSETS, CoreConfig, DyrosCore, stable_penalty
 from .model.mjcf import load_mjcf
 from .model.tables import ModelTables, build_tables
 
@@ -189,6 +189,7 @@ def _cfg_from_sim(sim: Sim) -> CoreConfig:
                      num_position_iterations=p.physx.num_position_iterations,
                      num_velocity_iterations=p.physx.num_velocity_iterations,
                      with_rigid_body_state=True, with_rb_force_tensors=True)
+    cfg.penalty_stiffness, cfg.penalty_damping = stable_penalty(p.dt / p.substeps)
     if sim.plane is not None:
         cfg.friction = float(sim.plane.dynamic_friction)  # shape friction default 1.0
     if sim.asset is not None:

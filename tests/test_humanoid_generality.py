@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from isaacgymdyros_b200.core import ASSETS, CoreConfig
+from isaacgymdyros_b200.core import ASSETS, CoreConfig, stable_penalty
 from isaacgymdyros_b200.model.tables import ModelTables, role_programs
 from oracle.physics_oracle import PhysicsOracle
 from tests.physics_util import emulate_substep, oracle_params
@@ -127,7 +127,8 @@ def test_humanoid_cuda_simulate_matches_oracle_and_runs_4096():
     core.close()
     # BASELINE configs[2] size: 4096 humanoids, Humanoid.yaml stepping (dt 1/60 in 2 sub-steps), random torques
     N = 4096
-    cfg2 = CoreConfig(**{**HUMANOID_CFG, "substeps": 2})
+    k_pen, c_pen = stable_penalty(0.0166 / 2)
+    cfg2 = CoreConfig(**{**HUMANOID_CFG, "substeps": 2, "penalty_stiffness": k_pen, "penalty_damping": c_pen})
     core = DyrosCore(N, "cuda:0", cfg2, tables=t, with_task=False)
     core.sim_t["root_states"][:, 2] = STAND_Z
     g = torch.Generator(device="cuda:0"); g.manual_seed(0)
