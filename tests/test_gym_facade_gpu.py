@@ -125,13 +125,13 @@ def test_humanoid_through_the_gym_api():
     contact = gymtorch.wrap_tensor(gym.acquire_net_contact_force_tensor(sim))
     assert root.shape == (N, 13) and dof.shape == (N * 21, 2) and contact.shape == (N * 16, 3)
     tau = torch.zeros(N * 21, device=root.device)
-    for _ in range(60):  # one second: the humanoids drop 5 cm onto their feet
+    for _ in range(15):  # a quarter of a second: the humanoids drop 5 cm onto their feet (passive, they collapse later)
         gym.set_dof_actuation_force_tensor(sim, gymtorch.unwrap_tensor(tau))
         gym.simulate(sim)
     gym.fetch_results(sim, True)
     assert torch.isfinite(root).all() and torch.isfinite(dof).all()
-    feet = [13, 9] if False else [gym.find_asset_rigid_body_index(asset, "right_foot"), gym.find_asset_rigid_body_index(asset, "left_foot")]
+    feet = [gym.find_asset_rigid_body_index(asset, "right_foot"), gym.find_asset_rigid_body_index(asset, "left_foot")]
     cf = contact.view(N, 16, 3)
-    assert (cf[:, feet, 2].sum(1) > 50.0).all()  # standing or crouching on the soles
-    assert (root[:, 2] > 0.3).all() and (root[:, 2] < 1.4).all()
+    assert (cf[:, feet, 2].sum(1) > 50.0).all()  # standing on the soles
+    assert (root[:, 2] > 1.0).all() and (root[:, 2] < 1.4).all()
     gym.destroy_sim(sim)
