@@ -125,21 +125,30 @@ def test_humanoid_cuda_simulate_matches_oracle_and_runs_4096():
     got = (f(core.sim_t["root_states"]), f(ds[:, :, 0]), f(ds[:, :, 1]), f(core.sim_t["net_contact_force"].view(N, 16, 3)))
     compare(st, got, want, ctx="humanoid cuda: ")
     core.close()
-    # BASELINE configs[2] size: 4096 humanoids, Humanoid.yaml stepping (dt 1/60 in 2 sub-steps), random torques
+    # BASELINE configs[2] size: 4096 humanoids, Humanoid.yaml stepping (dt 1/60 in 2 sub-steps), held upright by a
+    # joint-space PD with random torque noise for one second. (Only the soles are constraint-solved; other bodies get
+    # the soft, explicitly integrated penalty contact that TOCABI uses to flag a fall, so a rollout of *fallen*
+    # humanoids is out of scope here: DESIGN.md section 8.)
     N = 4096
     k_pen, c_pen = stable_penalty(0.0166 / 2)
     cfg2 = CoreConfig(**{**HUMANOID_CFG, "substeps": 2, "penalty_stiffness": k_pen, "penalty_damping": c_pen})
     core = DyrosCore(N, "cuda:0", cfg2, tables=t, with_task=False)
     core.sim_t["root_states"][:, 2] = STAND_Z
     g = torch.Generator(device="cuda:0"); g.manual_seed(0)
-    for _ in range(120):
-        core.sim_t["dof_actuation_force"].copy_((torch.rand(N * 21, device="cuda:0", generator=g) * 2 - 1) * 40.0)
+    gear = torch.tensor(t.dof_effort, dtype=torch.float32, device="cuda:0")
+    ds = core.sim_t["dof_state"].view(N, 21, 2)
+    for _ in range(60):
+        noise = (torch.rand(N, 21, device="cuda:0", generator=g) * 2 - 1) * 0.05 * gear
+        core.sim_t["dof_actuation_force"].copy_((-300.0 * ds[:, :, 0] - 10.0 * ds[:, :, 1] + noise).reshape(-1))
         core.simulate()
     torch.cuda.synchronize()
     assert torch.isfinite(core.sim_t["root_states"]).all() and torch.isfinite(core.sim_t["dof_state"]).all()
     z = core.sim_t["root_states"][:, 2]
-    # nobody flew away or fell through the ground (non-foot bodies rest on the soft, dt-scaled penalty contact)
-    assert z.min().item() > -0.2 and z.max().item() < 2.0
+    assert z.min().item() > 1.0 and z.max().item() < 1.4  # everybody is still on their feet
     cf = core.sim_t["net_contact_force"].view(N, 16, 3)
-    assert (cf[:, :, 2] >= 0).all() and cf[:, :, 2].sum(1).mean().item() > 100.0  # the ground carries them
+    feet = [t.body_names.index("right_foot"), t.body_names.index("left_foot")]
+    others = [b for b in range(16) if b not in feet]
+    assert cf[:, others].abs().max().item() == 0.0
+    w = 40.844 * 9.81
+    assert (cf[:, feet, 2].sum(1) - w).abs().mean().item() < 0.15 * w  # the soles carry the weight
     core.close()
