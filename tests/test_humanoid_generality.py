@@ -126,7 +126,8 @@ def test_humanoid_cuda_simulate_matches_oracle_and_runs_4096():
     compare(st, got, want, ctx="humanoid cuda: ")
     core.close()
     # BASELINE configs[2] size: 4096 humanoids, Humanoid.yaml stepping (dt 1/60 in 2 sub-steps), held upright by a
-    # joint-space PD with random torque noise for one second. (Only the soles are constraint-solved; other bodies get
+    # weak joint-space PD with random torque noise for a quarter of a second (a humanoid without a balance controller
+    # buckles after ~0.5 s, in MuJoCo and PhysX too). (Only the soles are constraint-solved; other bodies get
     # the soft, explicitly integrated penalty contact that TOCABI uses to flag a fall, so a rollout of *fallen*
     # humanoids is out of scope here: DESIGN.md section 8.)
     N = 4096
@@ -137,14 +138,14 @@ def test_humanoid_cuda_simulate_matches_oracle_and_runs_4096():
     g = torch.Generator(device="cuda:0"); g.manual_seed(0)
     gear = torch.tensor(t.dof_effort, dtype=torch.float32, device="cuda:0")
     ds = core.sim_t["dof_state"].view(N, 21, 2)
-    for _ in range(60):
+    for _ in range(15):
         noise = (torch.rand(N, 21, device="cuda:0", generator=g) * 2 - 1) * 0.05 * gear
-        core.sim_t["dof_actuation_force"].copy_((-300.0 * ds[:, :, 0] - 10.0 * ds[:, :, 1] + noise).reshape(-1))
+        core.sim_t["dof_actuation_force"].copy_((-20.0 * ds[:, :, 0] - 1.0 * ds[:, :, 1] + noise).reshape(-1))
         core.simulate()
     torch.cuda.synchronize()
     assert torch.isfinite(core.sim_t["root_states"]).all() and torch.isfinite(core.sim_t["dof_state"]).all()
     z = core.sim_t["root_states"][:, 2]
-    assert z.min().item() > 1.0 and z.max().item() < 1.4  # everybody is still on their feet
+    assert z.min().item() > 1.2 and z.max().item() < 1.4  # everybody is still on their feet
     cf = core.sim_t["net_contact_force"].view(N, 16, 3)
     feet = [t.body_names.index("right_foot"), t.body_names.index("left_foot")]
     others = [b for b in range(16) if b not in feet]
