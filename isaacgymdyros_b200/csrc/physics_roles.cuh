@@ -463,6 +463,11 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
 #pragma unroll
         for (int b = 0; b < 3; ++b) Om.H.a[3 * a + b] += w[a][3 + b];
     }
+    // blocks of the first chain links park the contact rows (2 per link): resolve their addresses once
+    real* rowblk[MAX_ACTIVE_PTS * 3 / ROWS_PER_LINK];
+#pragma unroll
+    for (int k = 0; k < MAX_ACTIVE_PTS * 3 / ROWS_PER_LINK; ++k) rowblk[k] = BLK(m.chain[g][k]) + LS_A + A_ROWS;
+    const real inv_dt = 1 / dt;
     M3 Rwf = ld_m3(X + X_FOOTPOSE + 12 * g);
     real pz = X[X_FOOTPOSE + 12 * g + 11];
     V3 nrm = v3(Rwf.a[6], Rwf.a[7], Rwf.a[8]);
@@ -482,7 +487,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
       real rad = m.foot_pt_radius[g][k];
       real phi = pz + dot(nrm, x) - rad;
       if (phi < p.contact_offset && nact < MAX_ACTIVE_PTS) {
-        real b = phi >= 0 ? -phi / dt : fmin_r(-p.erp * phi / dt, p.max_depen_vel);
+        real b = phi >= 0 ? -phi * inv_dt : fmin_r(-p.erp * phi * inv_dt, p.max_depen_vel);
         V3 xsk = x - rad * nrm;
 #pragma unroll
         for (int a = 0; a < MAX_ACTIVE_PTS; ++a)
@@ -496,10 +501,14 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
           V3 dir = d == 0 ? nrm : (d == 1 ? v3(Rwf.a[0], Rwf.a[1], Rwf.a[2]) : v3(Rwf.a[3], Rwf.a[4], Rwf.a[5]));
           SV J{cross(xsk, dir), dir};
           SV cv = mul(Om, J);
-          int row = nact * 3 + d;  // parked in the block of chain link row / ROWS_PER_LINK
-          real* rw = BLK(m.chain[g][row / ROWS_PER_LINK]) + LS_A + A_ROWS + (row % ROWS_PER_LINK) * 7;
-          st6(rw, cv);
-          rw[6] = 1 / dot(J, cv);
+          real winv = 1 / dot(J, cv);
+#pragma unroll
+          for (int a = 0; a < MAX_ACTIVE_PTS; ++a)
+            if (a == nact) {  // parked in the block of chain link row / ROWS_PER_LINK (row = 3 a + d, compile-time here)
+              real* rw = rowblk[(a * 3 + d) / ROWS_PER_LINK] + ((a * 3 + d) % ROWS_PER_LINK) * 7;
+              st6(rw, cv);
+              rw[6] = winv;
+            }
         }
         ++nact;
       }
@@ -516,8 +525,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
             V3 dir = d == 0 ? v3(Rwf.a[6], Rwf.a[7], Rwf.a[8])
                             : (d == 1 ? v3(Rwf.a[0], Rwf.a[1], Rwf.a[2]) : v3(Rwf.a[3], Rwf.a[4], Rwf.a[5]));
             SV J{cross(xs[a], dir), dir};
-            const int row = a * 3 + d;
-            const real* rw = BLK(m.chain[g][row / ROWS_PER_LINK]) + LS_A + A_ROWS + (row % ROWS_PER_LINK) * 7;
+            const real* rw = rowblk[(a * 3 + d) / ROWS_PER_LINK] + ((a * 3 + d) % ROWS_PER_LINK) * 7;
             real vrel = dot(J, V);
             real nw;
             if (d == 0) {
@@ -557,7 +565,6 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     st6(X + X_PD + 6 * g, (real)-1 * (P.w.x * G[0] + P.w.y * G[1] + P.w.z * G[2] + P.v.x * G[3] + P.v.y * G[4] + P.v.z * G[5]));
     sync.signal(flags + F_PD + g, epoch + 1);
     if (io.live) {
-      real inv_dt = 1 / dt;
 #pragma unroll
       for (int a = 0; a < MAX_ACTIVE_PTS; ++a)
         if (a < nact) {  // world force over this sub-step: (t1, t2, n) = world (x, y, z)

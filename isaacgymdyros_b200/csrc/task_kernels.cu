@@ -502,76 +502,77 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_post_fused(TK k) {
   stage_late_update(k, e, lane);
 }
 
-// Cross-env pass (one block): (a) reset_buf.nonzero() -> ascending ids by ballot + prefix scan (T:554),
-// (b) the curriculum gate means of T:489, (c) Philox epoch bump.
+// Cross-env pass (one block, one sweep over the envs): (a) reset_buf.nonzero() -> ascending ids (T:554): thread t owns the
+// consecutive envs [t * per, (t + 1) * per), so a block-wide exclusive scan of the per-thread counts (warp shuffle scan,
+// then a scan of the 32 warp totals) gives every thread the output position of its first id; (b) the curriculum gate
+// means of T:489 (fixed summation order: deterministic); (c) Philox epoch bump.
 constexpr int kScanThreads = 1024;
 __global__ void __launch_bounds__(kScanThreads) k_crossenv(TK k, int do_compact, int do_gate, int do_bump) {
   __shared__ int warp_tot[kScanThreads / 32];
-  __shared__ int base_sh;
   __shared__ double red[2][kScanThreads / 32];
-  int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  int N = k.p.N;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int N = k.p.N;
+  const int per = (N + kScanThreads - 1) / kScanThreads;
+  const int e0 = tid * per, e1 = min(N, e0 + per);
   pdl_wait();
-  if (do_compact) {
-    if (tid == 0) base_sh = 0;
-    __syncthreads();
-    for (int start = 0; start < N; start += kScanThreads) {
-      int e = start + tid;
-      bool f = (e < N) && (k.b.reset_buf[e] != 0);
-      unsigned bal = __ballot_sync(kFull, f);
-      int rank = __popc(bal & ((1u << lane) - 1u));
-      if (lane == 0) warp_tot[w] = __popc(bal);
-      __syncthreads();
-      if (w == 0) {
-        int v = warp_tot[lane];
-        int inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          int t = __shfl_up_sync(kFull, inc, o);
-          if (lane >= o) inc += t;
-        }
-        warp_tot[lane] = inc - v;  // exclusive
-        if (lane == 31) red[0][0] = (double)inc;  // chunk total (reuse smem slot)
-      }
-      __syncthreads();
-      int base = base_sh;
-      if (f) {
-        int pos = base + warp_tot[w] + rank;
-        k.b.reset_env_ids[pos] = e;
-        k.b.reset_env_ids32[pos] = e;
-      }
-      __syncthreads();
-      if (tid == 0) base_sh = base + (int)red[0][0];
-      __syncthreads();
-    }
-    if (tid == 0) *k.b.reset_count = base_sh;
-  }
-  if (do_gate && k.p.perturb) {
-    double s0 = 0.0, s1 = 0.0;
-    for (int e = tid; e < N; e += kScanThreads) {
+  int cnt = 0;
+  double s0 = 0.0, s1 = 0.0;
+  const bool gate = do_gate && k.p.perturb;
+  for (int e = e0; e < e1; ++e) {
+    if (do_compact) cnt += k.b.reset_buf[e] != 0;
+    if (gate) {
       s0 += (double)k.b.epi_len_log[e];
       s1 += (double)k.b.contact_reward_mean[e];
     }
-    for (int o = 16; o > 0; o >>= 1) {
-      s0 += __shfl_xor_sync(kFull, s0, o);
-      s1 += __shfl_xor_sync(kFull, s1, o);
-    }
-    __syncthreads();
-    if (lane == 0) {
-      red[0][w] = s0;
-      red[1][w] = s1;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      double a = 0, b = 0;
-      for (int i = 0; i < kScanThreads / 32; ++i) {
-        a += red[0][i];
-        b += red[1][i];
-      }
-      if ((float)(a / N) > k.p.gate_len && (float)(b / N) > 0.165f) *k.b.perturb_start = 1;  // T:489-490 (sticky)
-    }
   }
-  if (do_bump && tid == 0) *k.p.step_counter = *k.p.step_counter + 1;
+  // inclusive scan of cnt inside the warp, warp totals to shared memory
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += t;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(kFull, s0, o);
+    s1 += __shfl_xor_sync(kFull, s1, o);
+  }
+  if (lane == 31) warp_tot[w] = inc;
+  if (lane == 0) {
+    red[0][w] = s0;
+    red[1][w] = s1;
+  }
+  __syncthreads();
+  if (w == 0) {
+    int v = warp_tot[lane], sc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(kFull, sc, o);
+      if (lane >= o) sc += t;
+    }
+    warp_tot[lane] = sc - v;  // exclusive offsets of the warps
+    if (lane == 31 && do_compact) *k.b.reset_count = sc;
+    if (gate) {
+      double a = red[0][lane], b = red[1][lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(kFull, a, o);
+        b += __shfl_xor_sync(kFull, b, o);
+      }
+      if (lane == 0 && (float)(a / N) > k.p.gate_len && (float)(b / N) > 0.165f) *k.b.perturb_start = 1;  // T:489-490 (sticky)
+    }
+    if (do_bump && lane == 0) *k.p.step_counter = *k.p.step_counter + 1;
+  }
+  __syncthreads();
+  if (do_compact && cnt) {
+    int pos = warp_tot[w] + inc - cnt;
+    for (int e = e0; e < e1; ++e)
+      if (k.b.reset_buf[e] != 0) {
+        k.b.reset_env_ids[pos] = e;
+        k.b.reset_env_ids32[pos] = e;
+        ++pos;
+      }
+  }
 }
 
 // ------------------------------------------------------------------ launchers
