@@ -84,6 +84,12 @@ __device__ __forceinline__ float2 normal01_pair(uint32_t a, uint32_t b) {
   return make_float2(r * c, r * s);
 }
 
+// Out-of-line draw + Box-Muller for call sites that are unrolled several times (keeps the instruction footprint small).
+static __device__ __noinline__ float2 draw_normal_pair(uint64_t seed, uint64_t step, uint32_t env, uint32_t site, uint32_t sub) {
+  uint4 r = draw4(seed, step, env, site, sub);
+  return normal01_pair(r.x, r.y);
+}
+
 // Division of small non-negative ints by a run-time constant: q = (i * mul) >> 20, exact while i * d < 2^20.
 struct FastDiv {
   unsigned mul;

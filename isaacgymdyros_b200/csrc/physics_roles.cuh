@@ -111,6 +111,7 @@ HD ABI link_inertia(const real* X, const float* hot, const DevModel& m, const fl
 #pragma unroll
     for (int k = 0; k < 10; ++k) par[k] = sc * HF(body_inertia, b * 10 + k);
   }
+#pragma unroll 1
   for (int j = 1; j < RI(R, R_NBODY); ++j) {
     int b = RI(R, R_BODY0 + j);
     real sc = X[X_MASS + b];
@@ -126,6 +127,7 @@ HD void link_forces(const EnvIO& io, real* L, const real* X, const float* hot, c
   SV fext = sv_zero();
   V3 nrm = v3(Rw.a[6], Rw.a[7], Rw.a[8]);  // world z in link coordinates
   if (io.rb_force || (io.push && RI(R, R_LINK) == 0)) {  // applied world wrenches at the bodies' COMs (tensors.rst.txt:322-335)
+#pragma unroll 1
     for (int j = 0; j < RI(R, R_NBODY); ++j) {
       int b = RI(R, R_BODY0 + j);
       V3 F = v3(0, 0, 0), T = v3(0, 0, 0);
@@ -145,12 +147,14 @@ HD void link_forces(const EnvIO& io, real* L, const real* X, const float* hot, c
     }
   }
   if (pw.z < R[R_REACH]) {  // nothing of this link can reach z = 0 otherwise
+#pragma unroll 1
     for (int k = RI(R, R_PT0); k < RI(R, R_PT1); ++k) {
       V3 x = ld3_f(m.pt_pos + 3 * k);
       real rad = m.pt_radius[k];
       real z = pw.z + dot(nrm, x);
       penalty_point(p, Rw, v, x - rad * nrm, rad - z, io.contact + 3 * m.pt_body[k], io.live, fext);
     }
+#pragma unroll 1
     for (int k = RI(R, R_CYL0); k < RI(R, R_CYL1); ++k) {
       V3 c = ld3_f(m.cyl_center + 3 * k), a = ld3_f(m.cyl_axis + 3 * k);
       real rad = m.cyl_size[2 * k], hh = m.cyl_size[2 * k + 1];

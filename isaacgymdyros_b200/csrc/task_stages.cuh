@@ -239,8 +239,7 @@ __device__ __forceinline__ void stage_sensor_noise_cta(const NoiseSlabArgs& k, i
       int le = dNP.div(idx), pr = idx - le * NP;
       float2 nn = make_float2(0.f, 0.f);
       if (!inject) {
-        uint4 r = draw4(k.seed, epoch, e0 + le, kSiteQposNoise, substep * 64 + pr);
-        nn = normal01_pair(r.x, r.y);
+        nn = draw_normal_pair(k.seed, epoch, e0 + le, kSiteQposNoise, substep * 64 + pr);
       }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
