@@ -97,10 +97,12 @@ __device__ __forceinline__ EnvIO env_io(const DevModel& m, const DyrosSimBuffers
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
-// one L2 prefetch per 128-byte line of a contiguous slab (thread t takes lines t, t + 128, ...)
-__device__ __forceinline__ void slab_prefetch_l2(const void* base, size_t bytes) {
+// one L2 prefetch per 128-byte line of a contiguous slab (thread t takes lines t, t + 128, ...); rolled: this runs once
+// per launch and should cost as few instruction-cache lines as possible
+__device__ __forceinline__ void slab_prefetch_l2(const void* base, unsigned bytes) {
   const char* p = static_cast<const char*>(base);
-  for (size_t off = (size_t)threadIdx.x * 128; off < bytes; off += (size_t)kPhysThreads * 128)
+#pragma unroll 1
+  for (unsigned off = threadIdx.x * 128u; off < bytes; off += kPhysThreads * 128u)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
@@ -113,6 +115,7 @@ __device__ __forceinline__ void slab_stage_inputs(const DevModel& m, const SimPa
   const FastDiv d2nd(2 * nd), dnd(nd), dnb(nb), d13(13), d3(3);  // slabs are < 2^20 / divisor words (checked at create)
   if (with_state) {  // joint state, mass scales and root: only before the first sub-step of a launch (they stay in the scratch)
     const float* src = b.dof_state + (size_t)e0 * nd * 2;
+#pragma unroll 1
     for (int i = threadIdx.x; i < nenv * nd * 2; i += kPhysThreads) {
       int le = d2nd.div(i), w = i - le * 2 * nd;
       cp_async4(envs + le * es + dof_link[w >> 1] * LS + ((w & 1) ? LS_SC : LS_Q), src + i);
@@ -122,6 +125,7 @@ __device__ __forceinline__ void slab_stage_inputs(const DevModel& m, const SimPa
     const float* tau = b.dof_actuation_force + (size_t)e0 * nd;
     const float* dmp = b.dof_damping + (size_t)e0 * nd;
     const float* arm = b.dof_armature + (size_t)e0 * nd;
+#pragma unroll 1
     for (int i = threadIdx.x; i < nenv * nd; i += kPhysThreads) {
       int le = dnd.div(i), d = i - le * nd;
       float* L = envs + le * es + dof_link[d] * LS + LS_SC;
@@ -132,6 +136,7 @@ __device__ __forceinline__ void slab_stage_inputs(const DevModel& m, const SimPa
   }
   if (with_state) {
     const float* src = b.body_mass_scale + (size_t)e0 * nb;
+#pragma unroll 1
     for (int i = threadIdx.x; i < nenv * nb; i += kPhysThreads) {
       int le = dnb.div(i);
       cp_async4(envs + le * es + xoff + X_MASS + (i - le * nb), src + i);
@@ -139,17 +144,20 @@ __device__ __forceinline__ void slab_stage_inputs(const DevModel& m, const SimPa
   }
   if (with_state) {
     const float* src = b.root_states + (size_t)e0 * 13;
+#pragma unroll 1
     for (int i = threadIdx.x; i < nenv * 13; i += kPhysThreads) {
       int le = d13.div(i);
       cp_async4(envs + le * es + xoff + X_ROOT + (i - le * 13), src + i);
     }
   }
+#pragma unroll 1
   for (int i = threadIdx.x; i < nenv * 3; i += kPhysThreads) {
     int le = d3.div(i);
     if (push) cp_async4(envs + le * es + xoff + X_PUSH + (i - le * 3), push + (size_t)e0 * 3 + i);
     else envs[le * es + xoff + X_PUSH + (i - le * 3)] = 0.f;
   }
   float* cf = b.net_contact_force + (size_t)e0 * nb * 3;  // net contact force of THIS sub-step only
+#pragma unroll 1
   for (int i = threadIdx.x; i < nenv * nb * 3; i += kPhysThreads) cf[i] = 0.f;
   cp_async_wait_all();
 }
@@ -160,11 +168,13 @@ __device__ __forceinline__ void slab_store_outputs(const DevModel& m, const Dyro
   const int* dof_link = reinterpret_cast<const int*>(hot) + m.o_dof_link;
   const FastDiv d2nd(2 * nd), d13(13);
   float* ds = b.dof_state + (size_t)e0 * nd * 2;
+#pragma unroll 1
   for (int i = threadIdx.x; i < nenv * nd * 2; i += kPhysThreads) {
     int le = d2nd.div(i), w = i - le * 2 * nd;
     ds[i] = envs[le * es + dof_link[w >> 1] * LS + ((w & 1) ? LS_SC : LS_Q)];
   }
   float* rs = b.root_states + (size_t)e0 * 13;
+#pragma unroll 1
   for (int i = threadIdx.x; i < nenv * 13; i += kPhysThreads) {
     int le = d13.div(i);
     rs[i] = envs[le * es + xoff + X_ROOT + (i - le * 13)];
@@ -224,12 +234,12 @@ __global__ void __launch_bounds__(kPhysThreads) k_step_physics(DevModel m, SimPa
   int epoch = 0;
   {  // with a cold L2, pull in what the torque and noise stages will read while the first staging is in flight
     const size_t e = (size_t)e0;
-    slab_prefetch_l2(k.b.target_data_qpos + e * ND, (size_t)nenv * ND * 4);
-    slab_prefetch_l2(k.b.action_log + e * LOG_DEPTH * 12, (size_t)nenv * LOG_DEPTH * 12 * 4);
-    slab_prefetch_l2(k.b.action_torque + e * 12, (size_t)nenv * 12 * 4);
-    slab_prefetch_l2(k.b.qpos_pre + e * ND, (size_t)nenv * ND * 4);
-    slab_prefetch_l2(k.s.dof_damping + e * ND, (size_t)nenv * ND * 4);
-    slab_prefetch_l2(k.s.dof_armature + e * ND, (size_t)nenv * ND * 4);
+    slab_prefetch_l2(k.b.target_data_qpos + e * ND, (unsigned)nenv * ND * 4);
+    slab_prefetch_l2(k.b.action_log + e * LOG_DEPTH * 12, (unsigned)nenv * LOG_DEPTH * 12 * 4);
+    slab_prefetch_l2(k.b.action_torque + e * 12, (unsigned)nenv * 12 * 4);
+    slab_prefetch_l2(k.b.qpos_pre + e * ND, (unsigned)nenv * ND * 4);
+    slab_prefetch_l2(k.s.dof_damping + e * ND, (unsigned)nenv * ND * 4);
+    slab_prefetch_l2(k.s.dof_armature + e * ND, (unsigned)nenv * ND * 4);
   }
   // joint state, root and mass scales are staged once and then live in the scratch blocks for the whole launch; the
   // torque and noise stages read them there, and only the final state is written back
