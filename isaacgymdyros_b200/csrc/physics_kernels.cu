@@ -16,7 +16,7 @@ __device__ __forceinline__ void st_release_shared(int* p, int v) {
 }
 
 // Flags between role warps: the producer's lanes finish their shared-memory writes, lane 0 publishes with release;
-// the consumer's lane 0 spins with acquire, then the warp re-converges.
+// the consumer's lanes spin with acquire.
 struct RoleSync {
   int lane;
   long long* trace;  // profiling aid: clock64() at the phase boundaries of one CTA (NULL in production)
@@ -27,11 +27,11 @@ struct RoleSync {
     __syncwarp();
     if (lane == 0) st_release_shared(f, v);
   }
+  // every lane polls (one broadcast load per iteration): the loop branch is warp-uniform, so the warp never splits
+  // into a lane-0 group and a rest group that would then run the following phase twice
   __device__ __forceinline__ void wait(const int* f, int v) const {
-    if (lane == 0)
-      while (ld_acquire_shared(f) < v) {
-      }
-    __syncwarp();
+    while (ld_acquire_shared(f) < v) {
+    }
   }
 };
 struct CtaSync {
@@ -97,104 +97,125 @@ __device__ __forceinline__ EnvIO env_io(const DevModel& m, const DyrosSimBuffers
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
-// one L2 prefetch per 128-byte line of a contiguous slab (thread t takes lines t, t + 128, ...); rolled: this runs once
-// per launch and should cost as few instruction-cache lines as possible
-__device__ __forceinline__ void slab_prefetch_l2(const void* base, unsigned bytes) {
+// one L2 prefetch per 128-byte line of a contiguous slab (thread tid takes lines tid, tid + nthreads, ...); rolled: this
+// runs once per launch and should cost as few instruction-cache lines as possible
+__device__ __forceinline__ void slab_prefetch_l2(const void* base, unsigned bytes, int tid, int nthreads) {
   const char* p = static_cast<const char*>(base);
 #pragma unroll 1
-  for (unsigned off = threadIdx.x * 128u; off < bytes; off += kPhysThreads * 128u)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+  for (unsigned off = tid * 128u; off < bytes; off += nthreads * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-__device__ __forceinline__ void slab_stage_inputs(const DevModel& m, const SimParams& p, const DyrosSimBuffers& b,
-                                                  const float* push, const float* hot, float* envs, int es, int e0, int nenv,
-                                                  bool with_tau, bool with_state) {
+// The copies below are issued by thread `tid` of `nthreads` cooperating threads (a CTA's role warps, or one warp);
+// the caller waits with cp_async_wait_all() and then synchronises the cooperating threads.
+// (1) joint state, mass scales and root: once per launch (they stay in the scratch blocks)
+__device__ __forceinline__ void slab_stage_state(const DevModel& m, const DyrosSimBuffers& b, const float* hot, float* envs, int es,
+                                                 int e0, int nenv, int tid, int nthreads) {
   const int nd = m.nd, nb = m.nb, xoff = m.nl * LS;
   const int* dof_link = reinterpret_cast<const int*>(hot) + m.o_dof_link;
-  const FastDiv d2nd(2 * nd), dnd(nd), dnb(nb), d13(13), d3(3);  // slabs are < 2^20 / divisor words (checked at create)
-  if (with_state) {  // joint state, mass scales and root: only before the first sub-step of a launch (they stay in the scratch)
+  const FastDiv d2nd(2 * nd), dnb(nb), d13(13);  // slabs are < 2^20 / divisor words (checked at create)
+  {
     const float* src = b.dof_state + (size_t)e0 * nd * 2;
 #pragma unroll 1
-    for (int i = threadIdx.x; i < nenv * nd * 2; i += kPhysThreads) {
+    for (int i = tid; i < nenv * nd * 2; i += nthreads) {
       int le = d2nd.div(i), w = i - le * 2 * nd;
       cp_async4(envs + le * es + dof_link[w >> 1] * LS + ((w & 1) ? LS_SC : LS_Q), src + i);
     }
   }
   {
-    const float* tau = b.dof_actuation_force + (size_t)e0 * nd;
-    const float* dmp = b.dof_damping + (size_t)e0 * nd;
-    const float* arm = b.dof_armature + (size_t)e0 * nd;
-#pragma unroll 1
-    for (int i = threadIdx.x; i < nenv * nd; i += kPhysThreads) {
-      int le = dnd.div(i), d = i - le * nd;
-      float* L = envs + le * es + dof_link[d] * LS + LS_SC;
-      if (with_tau) cp_async4(L + 1, tau + i);
-      cp_async4(L + 2, dmp + i);
-      cp_async4(L + 3, arm + i);
-    }
-  }
-  if (with_state) {
     const float* src = b.body_mass_scale + (size_t)e0 * nb;
 #pragma unroll 1
-    for (int i = threadIdx.x; i < nenv * nb; i += kPhysThreads) {
+    for (int i = tid; i < nenv * nb; i += nthreads) {
       int le = dnb.div(i);
       cp_async4(envs + le * es + xoff + X_MASS + (i - le * nb), src + i);
     }
   }
-  if (with_state) {
+  {
     const float* src = b.root_states + (size_t)e0 * 13;
 #pragma unroll 1
-    for (int i = threadIdx.x; i < nenv * 13; i += kPhysThreads) {
+    for (int i = tid; i < nenv * 13; i += nthreads) {
       int le = d13.div(i);
       cp_async4(envs + le * es + xoff + X_ROOT + (i - le * 13), src + i);
     }
   }
+}
+// (2) per sub-step, needed by the force loop of pass 1: the push, and the zeroed net contact forces (THIS sub-step only)
+__device__ __forceinline__ void slab_stage_pre(const DevModel& m, const DyrosSimBuffers& b, const float* push, float* envs, int es,
+                                               int e0, int nenv, int tid, int nthreads) {
+  const int nb = m.nb, xoff = m.nl * LS;
+  const FastDiv d3(3);
 #pragma unroll 1
-  for (int i = threadIdx.x; i < nenv * 3; i += kPhysThreads) {
+  for (int i = tid; i < nenv * 3; i += nthreads) {
     int le = d3.div(i);
     if (push) cp_async4(envs + le * es + xoff + X_PUSH + (i - le * 3), push + (size_t)e0 * 3 + i);
     else envs[le * es + xoff + X_PUSH + (i - le * 3)] = 0.f;
   }
-  float* cf = b.net_contact_force + (size_t)e0 * nb * 3;  // net contact force of THIS sub-step only
+  float* cf = b.net_contact_force + (size_t)e0 * nb * 3;
+  const int nw = nenv * nb * 3;
+  if (((reinterpret_cast<uintptr_t>(cf) | (uintptr_t)(nw * 4)) & 15) == 0) {  // the usual case: 16-byte stores
 #pragma unroll 1
-  for (int i = threadIdx.x; i < nenv * nb * 3; i += kPhysThreads) cf[i] = 0.f;
-  cp_async_wait_all();
+    for (int i = tid; i < nw / 4; i += nthreads) reinterpret_cast<float4*>(cf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+#pragma unroll 1
+    for (int i = tid; i < nw; i += nthreads) cf[i] = 0.f;
+  }
+}
+// (3) per sub-step, needed by pass 2: damping and armature (their slots are reused by the recursion) and the torque
+__device__ __forceinline__ void slab_stage_dofpar(const DevModel& m, const DyrosSimBuffers& b, const float* hot, float* envs, int es,
+                                                  int e0, int nenv, bool with_tau, int tid, int nthreads) {
+  const int nd = m.nd;
+  const int* dof_link = reinterpret_cast<const int*>(hot) + m.o_dof_link;
+  const FastDiv dnd(nd);
+  const float* tau = b.dof_actuation_force + (size_t)e0 * nd;
+  const float* dmp = b.dof_damping + (size_t)e0 * nd;
+  const float* arm = b.dof_armature + (size_t)e0 * nd;
+#pragma unroll 1
+  for (int i = tid; i < nenv * nd; i += nthreads) {
+    int le = dnd.div(i), d = i - le * nd;
+    float* L = envs + le * es + dof_link[d] * LS + LS_SC;
+    if (with_tau) cp_async4(L + 1, tau + i);
+    cp_async4(L + 2, dmp + i);
+    cp_async4(L + 3, arm + i);
+  }
 }
 
 __device__ __forceinline__ void slab_store_outputs(const DevModel& m, const DyrosSimBuffers& b, const float* hot,
-                                                   const float* envs, int es, int e0, int nenv) {
+                                                   const float* envs, int es, int e0, int nenv, int tid, int nthreads) {
   const int nd = m.nd, xoff = m.nl * LS;
   const int* dof_link = reinterpret_cast<const int*>(hot) + m.o_dof_link;
   const FastDiv d2nd(2 * nd), d13(13);
   float* ds = b.dof_state + (size_t)e0 * nd * 2;
-#pragma unroll 1
-  for (int i = threadIdx.x; i < nenv * nd * 2; i += kPhysThreads) {
+#pragma unroll 2
+  for (int i = tid; i < nenv * nd * 2; i += nthreads) {
     int le = d2nd.div(i), w = i - le * 2 * nd;
     ds[i] = envs[le * es + dof_link[w >> 1] * LS + ((w & 1) ? LS_SC : LS_Q)];
   }
   float* rs = b.root_states + (size_t)e0 * 13;
 #pragma unroll 1
-  for (int i = threadIdx.x; i < nenv * 13; i += kPhysThreads) {
+  for (int i = tid; i < nenv * 13; i += nthreads) {
     int le = d13.div(i);
     rs[i] = envs[le * es + xoff + X_ROOT + (i - le * 13)];
   }
 }
 
-// The slab stages are compiled as separate functions so that their (large, short-lived) register arrays do not raise
-// the register pressure of the role programs.
-__device__ __noinline__ void torque_stage_slab(TorqueSlabArgs k, int e0, int nenv, float* envs, int es, const int* dof_link) {
-  CtaSync cta;
+// The task's slab stages are compiled as separate functions so that their (large, short-lived) register arrays do not
+// raise the register pressure of the role programs. `tid0` of `nreal` real threads act as 128 virtual threads.
+__device__ __noinline__ void torque_stage_slab(TorqueSlabArgs k, int e0, int nenv, float* envs, int es, const int* dof_link,
+                                               int tid0, int nreal) {
   // joint state comes from the scratch blocks; the torques go to the API tensor and straight into the scratch blocks
-  stage_substep_torque_cta(
-      k, e0, nenv, threadIdx.x, kPhysThreads, cta,
-      [&](int le, int d, float v) { envs[le * es + dof_link[d] * LS + LS_SC + 1] = v; },
-      [&](int le, int d, int which) { return envs[le * es + dof_link[d] * LS + (which ? LS_SC : LS_Q)]; });
+#pragma unroll 1
+  for (int vt = tid0; vt < kPhysThreads; vt += nreal)
+    stage_substep_torque_cta(
+        k, e0, nenv, vt, kPhysThreads, [&](int le, int d, float v) { envs[le * es + dof_link[d] * LS + LS_SC + 1] = v; },
+        [&](int le, int d, int which) { return envs[le * es + dof_link[d] * LS + (which ? LS_SC : LS_Q)]; });
 }
-__device__ __noinline__ void noise_stage_slab(NoiseSlabArgs k, int substep, int e0, int nenv, const float* envs, int es, const int* dof_link) {
+__device__ __noinline__ void noise_stage_slab(NoiseSlabArgs k, int substep, int e0, int nenv, const float* envs, int es,
+                                              const int* dof_link, int tid0, int nreal) {
   // sensor noise reads the fresh joint angles from the scratch blocks
-  stage_sensor_noise_cta(k, substep, e0, nenv, threadIdx.x, kPhysThreads,
-                         [&](int le, int d) { return envs[le * es + dof_link[d] * LS + LS_Q]; });
+#pragma unroll 1
+  for (int vt = tid0; vt < kPhysThreads; vt += nreal)
+    stage_sensor_noise_cta(k, substep, e0, nenv, vt, kPhysThreads,
+                           [&](int le, int d) { return envs[le * es + dof_link[d] * LS + LS_Q]; });
 }
 
 __global__ void __launch_bounds__(kPhysThreads) k_simulate(DevModel m, SimParams p, DyrosSimBuffers b, const float* __restrict__ push,
@@ -209,11 +230,14 @@ __global__ void __launch_bounds__(kPhysThreads) k_simulate(DevModel m, SimParams
   io.rb_torque = apply_wrench ? b.rb_torque + (size_t)c.e * m.nb * 3 : nullptr;
   RoleSync sync{c.lane, nullptr};
   for (int s = 0; s < p.substeps; ++s) {
-    slab_stage_inputs(m, p, b, s == 0 ? push : nullptr, c.hot, envs, es, e0, nenv, true, s == 0);
+    if (s == 0) slab_stage_state(m, b, c.hot, envs, es, e0, nenv, threadIdx.x, kPhysThreads);
+    slab_stage_pre(m, b, s == 0 ? push : nullptr, envs, es, e0, nenv, threadIdx.x, kPhysThreads);
+    slab_stage_dofpar(m, b, c.hot, envs, es, e0, nenv, true, threadIdx.x, kPhysThreads);
+    cp_async_wait_all();
     __syncthreads();
     env_substep_role(io, c.sm, c.flags, s, c.hot, m, p, c.role, sync);
     __syncthreads();
-    if (s + 1 == p.substeps) slab_store_outputs(m, b, c.hot, envs, es, e0, nenv);
+    if (s + 1 == p.substeps) slab_store_outputs(m, b, c.hot, envs, es, e0, nenv, threadIdx.x, kPhysThreads);
     io.push = nullptr;  // applied wrenches act "for the immediate timestep" (gym_py.html apply_rigid_body_force_tensors)
     io.rb_force = nullptr;
     io.rb_torque = nullptr;
@@ -222,47 +246,74 @@ __global__ void __launch_bounds__(kPhysThreads) k_simulate(DevModel m, SimParams
 
 // The physics part of one policy step in ONE launch: skipframe x (PD + delay torque, gym.simulate, sensor noise),
 // i.e. the loop body of T:504-530 with the three gym calls of T:520-526 folded in.
-__global__ void __launch_bounds__(kPhysThreads) k_step_physics(DevModel m, SimParams p, TK k, int epb, int es, long long* trace) {
+// Warps 0-3 run the role programs; warps 4-7 are the I/O group: while the roles are in pass 1 of a sub-step it zeroes
+// the contact forces and stages the push (F_IO_PRE), draws the sensor noise of the PREVIOUS policy sub-step (which only
+// reads the joint angles, untouched until the roles' last pass), evaluates the torque stage and re-stages damping and
+// armature (F_IO_TAU, consumed by pass 2), so none of this sits on the roles' critical path.
+constexpr int kIoThreads = 128;
+constexpr int kStepThreads = kPhysThreads + kIoThreads;
+__device__ __forceinline__ void io_group_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kIoThreads) : "memory"); }
+
+__global__ void __launch_bounds__(kStepThreads) k_step_physics(DevModel m, SimParams p, TK k, int epb, int es, long long* trace) {
   extern __shared__ __align__(16) float smem[];
   PhysCta c = phys_cta_setup(m, p, smem, epb, es);
   const int e0 = blockIdx.x * epb, nenv = min(epb, p.N - e0);
   float* envs = smem + m.hot_bytes / 4 + ((F_COUNT + 3) & ~3);
+  const bool io_group = c.role >= DYROS_LANES;
+  const int role = c.role & (DYROS_LANES - 1);
+  const int it = threadIdx.x - kPhysThreads;  // thread index within the I/O group
   EnvIO io = env_io(m, k.s, c.e, c.live);
-  // trace layout: [sub-step][role][32 marks]; mark 13/14/15 = before torque stage, after staging, after noise
-  RoleSync sync{c.lane, (trace && blockIdx.x == 0) ? trace + c.role * 32 : nullptr};
+  // trace layout: [sub-step][role][32 marks]
+  RoleSync sync{c.lane, (trace && blockIdx.x == 0 && !io_group) ? trace + role * 32 : nullptr};
   const int* dof_link = reinterpret_cast<const int*>(c.hot) + m.o_dof_link;
-  int epoch = 0;
-  {  // with a cold L2, pull in what the torque and noise stages will read while the first staging is in flight
+  if (io_group) {  // with a cold L2, pull in what the torque and noise stages will read while the first staging is in flight
     const size_t e = (size_t)e0;
-    slab_prefetch_l2(k.b.target_data_qpos + e * ND, (unsigned)nenv * ND * 4);
-    slab_prefetch_l2(k.b.action_log + e * LOG_DEPTH * 12, (unsigned)nenv * LOG_DEPTH * 12 * 4);
-    slab_prefetch_l2(k.b.action_torque + e * 12, (unsigned)nenv * 12 * 4);
-    slab_prefetch_l2(k.b.qpos_pre + e * ND, (unsigned)nenv * ND * 4);
-    slab_prefetch_l2(k.s.dof_damping + e * ND, (unsigned)nenv * ND * 4);
-    slab_prefetch_l2(k.s.dof_armature + e * ND, (unsigned)nenv * ND * 4);
+    slab_prefetch_l2(k.b.target_data_qpos + e * ND, (unsigned)nenv * ND * 4, it, kIoThreads);
+    slab_prefetch_l2(k.b.action_log + e * LOG_DEPTH * 12, (unsigned)nenv * LOG_DEPTH * 12 * 4, it, kIoThreads);
+    slab_prefetch_l2(k.b.action_torque + e * 12, (unsigned)nenv * 12 * 4, it, kIoThreads);
+    slab_prefetch_l2(k.b.qpos_pre + e * ND, (unsigned)nenv * ND * 4, it, kIoThreads);
+    slab_prefetch_l2(k.s.dof_damping + e * ND, (unsigned)nenv * ND * 4, it, kIoThreads);
+    slab_prefetch_l2(k.s.dof_armature + e * ND, (unsigned)nenv * ND * 4, it, kIoThreads);
+  } else {
+    // joint state, root and mass scales are staged once and then live in the scratch blocks for the whole launch; the
+    // torque and noise stages read them there, and only the final state is written back
+    slab_stage_state(m, k.s, c.hot, envs, es, e0, nenv, threadIdx.x, kPhysThreads);
+    cp_async_wait_all();
   }
-  // joint state, root and mass scales are staged once and then live in the scratch blocks for the whole launch; the
-  // torque and noise stages read them there, and only the final state is written back
-  slab_stage_inputs(m, p, k.s, nullptr, c.hot, envs, es, e0, nenv, false, true);
   __syncthreads();
+  int epoch = 0;
   for (int s = 0; s < k.p.skipframe; ++s) {
-    sync.mark(13);
-    torque_stage_slab(torque_args(k), e0, nenv, envs, es, dof_link);
-    const float* push = s == 0 ? k.b.push_force : nullptr;  // the push acts on the first sub-step only (T:502 vs T:504)
-    io.push = push;
-    for (int ss = 0; ss < p.substeps; ++ss) {
-      // per sub-step inputs: damping / armature (their slots are reused by the recursion), push, zeroed contact forces
-      slab_stage_inputs(m, p, k.s, push, c.hot, envs, es, e0, nenv, ss > 0, false);
+    for (int ss = 0; ss < p.substeps; ++ss, ++epoch) {
+      if (io_group) {
+        // the push acts on the first sub-step of the policy step only (T:502 vs T:504)
+        slab_stage_pre(m, k.s, (s == 0 && ss == 0) ? k.b.push_force : nullptr, envs, es, e0, nenv, it, kIoThreads);
+        cp_async_wait_all();
+        io_group_sync();
+        if (it == 0) st_release_shared(c.flags + F_IO_PRE, epoch + 1);
+        if (ss == 0) {
+          torque_stage_slab(torque_args(k), e0, nenv, envs, es, dof_link, it, kIoThreads);
+          io_group_sync();  // every thread has read simul_len
+          stage_simul_len_update(torque_args(k), e0, nenv, it, kIoThreads);
+        }
+        slab_stage_dofpar(m, k.s, c.hot, envs, es, e0, nenv, ss > 0, it, kIoThreads);
+        cp_async_wait_all();
+        io_group_sync();
+        if (it == 0) st_release_shared(c.flags + F_IO_TAU, epoch + 1);
+        // off the critical path: the sensor noise of the previous policy sub-step
+        if (ss == 0 && s > 0) noise_stage_slab(noise_args(k), s - 1, e0, nenv, envs, es, dof_link, it, kIoThreads);
+        io_group_sync();
+        if (it == 0) st_release_shared(c.flags + F_IO_DONE, epoch + 1);
+      } else {
+        io.push = (s == 0 && ss == 0) ? k.b.push_force : nullptr;
+        sync.mark(13);
+        env_substep_role(io, c.sm, c.flags, epoch, c.hot, m, p, role, sync, true);
+      }
       __syncthreads();
-      sync.mark(14);
-      env_substep_role(io, c.sm, c.flags, epoch++, c.hot, m, p, c.role, sync);
-      __syncthreads();
-      push = nullptr;
-      io.push = nullptr;
     }
-    noise_stage_slab(noise_args(k), s, e0, nenv, envs, es, dof_link);
-    if (s + 1 == k.p.skipframe) slab_store_outputs(m, k.s, c.hot, envs, es, e0, nenv);
-    __syncthreads();
+    if (s + 1 == k.p.skipframe) {  // last policy sub-step: its noise stage on the I/O group, the state write-back on the role warps
+      if (io_group) noise_stage_slab(noise_args(k), s, e0, nenv, envs, es, dof_link, it, kIoThreads);
+      else slab_store_outputs(m, k.s, c.hot, envs, es, e0, nenv, threadIdx.x, kPhysThreads);
+    }
     sync.mark(15);
     if (sync.trace) sync.trace += DYROS_LANES * 32;
   }
@@ -306,7 +357,7 @@ int launch_task_physics(Task* t, cudaStream_t s, long long* trace, bool pdl) {
   k.b = t->b;
   k.s = sim->b;
   k.j = t->inj;
-  DY_CUDA(launch_kernel(k_step_physics, dim3(grid), dim3(kPhysThreads), sim->phys_smem, s, pdl, sim->m, sim->p, k, epb,
+  DY_CUDA(launch_kernel(k_step_physics, dim3(grid), dim3(kStepThreads), sim->phys_smem, s, pdl, sim->m, sim->p, k, epb,
                         env_scratch_floats(sim->m.nl), trace));
   return 0;
 }

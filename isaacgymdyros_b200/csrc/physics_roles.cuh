@@ -54,7 +54,10 @@ constexpr int F_LINK = 0;                         // [DYROS_MAX_LINKS]
 constexpr int F_Z = DYROS_MAX_LINKS;              // [MAX_FEET] sweeps published
 constexpr int F_PD = F_Z + MAX_FEET;              // [MAX_FEET] base impulse published
 constexpr int F_OML = F_PD + MAX_FEET;            // [1] inverse inertia at the LCA published
-constexpr int F_COUNT = F_OML + 1;
+constexpr int F_IO_PRE = F_OML + 1;               // [1] fused step: push staged, contact forces zeroed (I/O warp)
+constexpr int F_IO_TAU = F_IO_PRE + 1;            // [1] fused step: torque, damping and armature staged (I/O warp)
+constexpr int F_IO_DONE = F_IO_TAU + 1;           // [1] fused step: the I/O group no longer reads the joint angles
+constexpr int F_COUNT = F_IO_DONE + 1;
 constexpr int ST_PASS1 = 1, ST_PASS2 = 2, ST_PASS3 = 3, ST_DOWN = 4, ST_STRIDE = 8;
 
 // The hot model tables are read from the staged copy `hot` (shared memory on the GPU) through word offsets.
@@ -205,10 +208,13 @@ HD void env_store_outputs(const EnvIO& io, const real* sm, const float* hot, con
 }
 
 // One sub-step for role `role` of one env. `flags`: the CTA-wide stage flags; `epoch`: sub-steps done so far in this
-// launch (the flags are monotonic). The env's inputs must have been staged (env_stage_inputs) and made visible.
+// launch (the flags are monotonic). The env's inputs must have been staged (env_stage_inputs) and made visible;
+// with `io_async` the per-sub-step inputs are staged concurrently by another warp, which publishes F_IO_PRE (push,
+// zeroed contact forces: needed by the force loop), F_IO_TAU (torque, damping, armature: needed by pass 2) and
+// F_IO_DONE (it has finished reading the joint angles, which the last pass overwrites).
 template <class Sync>
 HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const float* hot, const DevModel& m,
-                         const SimParams& p, int role, Sync& sync) {
+                         const SimParams& p, int role, Sync& sync, bool io_async = false) {
   const int nl = m.nl;
   real* X = sm + nl * LS;
   const real dt = p.dt;
@@ -231,7 +237,6 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     st_m3(L + LS_A + A_POSE, R0);
     st3(L + LS_A + A_POSE + 9, pw);
     sync.signal(fl + 0, base + ST_PASS1);
-    link_forces(io, L, X, hot, m, p, REC(0), R0, pw, v0);
   }
   // (a) joint transforms: local to each link, no dependencies
   for (int k = 0; k < len; ++k) {
@@ -261,9 +266,10 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     sync.signal(fl + i, base + ST_PASS1);
   }
   sync.mark(17);
-  // (c) bias forces and external wrenches: local to each link again
-  for (int k = 0; k < len; ++k) {
-    const float* R = REC(rec0 + k);
+  // (c) bias forces and external wrenches: local to each link again (k = -1: the base itself, record 0)
+  if (io_async) sync.wait(flags + F_IO_PRE, epoch + 1);
+  for (int k = base_role ? -1 : 0; k < len; ++k) {
+    const float* R = k < 0 ? REC(0) : REC(rec0 + k);
     real* L = BLK(RI(R, R_LINK));
     M3 Rw = ld_m3(L + LS_A + A_POSE);
     V3 pw = ld3(L + LS_A + A_POSE + 9);
@@ -278,10 +284,12 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
   // Pass 2 overwrites A (pose) of a link with its contribution to the parent: every child of this role's links that
   // lives in another role must have read its parent's pose first.
   for (int k = 0; k < m.n_xchild[role]; ++k) sync.wait(fl + m.xchild[role][k], base + ST_PASS1);
+  if (io_async) sync.wait(flags + F_IO_TAU, epoch + 1);
   sync.mark(2);
-  // ---- pass 2, leaves -> root: articulated inertias and bias forces
-  for (int k = len - 1; k >= 0; --k) {
-    const float* R = REC(rec0 + k);
+  // ---- pass 2, leaves -> root: articulated inertias and bias forces; the base role ends with the base itself
+  //      (k = -1, record 0): inverse articulated inertia, base acceleration, predicted base velocity
+  for (int k = len - 1; k >= (base_role ? -1 : 0); --k) {
+    const float* R = k < 0 ? REC(0) : REC(rec0 + k);
     const int i = RI(R, R_LINK);
     real* L = BLK(i);
     real* A = L + LS_A;
@@ -294,46 +302,34 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
       IA = IA + ld_abi(Ac + A_CIA);
       pA = pA + ld6(Ac + A_CPA);
     }
-    V3 ax = ld3_f(R + R_AXIS), r = ld3_f(R + R_R);
-    M3 E = ld_m3(L + LS_E);
-    SV v = ld6(L + LS_V);
-    real qd = L[LS_SC], tq = L[LS_SC + 1], damp = L[LS_SC + 2], arm = L[LS_SC + 3];
-    if (p.clamp_effort) {  // optional clamp of the actuation to the MJCF ctrlrange
-      real lim = R[R_EFF];
-      tq = tq > lim ? lim : (tq < -lim ? -lim : tq);
+    if (k >= 0) {
+      V3 ax = ld3_f(R + R_AXIS), r = ld3_f(R + R_R);
+      M3 E = ld_m3(L + LS_E);
+      SV v = ld6(L + LS_V);
+      real qd = L[LS_SC], tq = L[LS_SC + 1], damp = L[LS_SC + 2], arm = L[LS_SC + 3];
+      if (p.clamp_effort) {  // optional clamp of the actuation to the MJCF ctrlrange
+        real lim = R[R_EFF];
+        tq = tq > lim ? lim : (tq < -lim ? -lim : tq);
+      }
+      const real stiff = R[R_STIFF];  // joint spring about q = 0, implicit like the damping
+      SV U{mul(IA.I, ax), mulT(IA.H, ax)};
+      real D = dot(ax, U.w) + arm + dt * (damp + dt * stiff);
+      real Dinv = 1 / D;
+      real u = tq - damp * qd - stiff * (L[LS_Q] + dt * qd) - dot(ax, pA.w);
+      V3 aq = qd * ax;
+      SV c{cross(v.w, aq), cross(v.v, aq)};
+      ABI Ia = rank1_sub(IA, U, Dinv);
+      SV pa = pA + mul(Ia, c) + (Dinv * u) * U;
+      st_abi(A + A_CIA, abi_to_parent(E, r, Ia));
+      st6(A + A_CPA, xform_force_T(E, r, pa));
+      st6(L + LS_U, U);
+      L[LS_SC + 1] = u;
+      L[LS_SC + 2] = Dinv;
+      L[LS_SC + 3] = 0;
+      sync.signal(fl + i, base + ST_PASS2);
+      continue;
     }
-    const real stiff = R[R_STIFF];  // joint spring about q = 0, implicit like the damping
-    SV U{mul(IA.I, ax), mulT(IA.H, ax)};
-    real D = dot(ax, U.w) + arm + dt * (damp + dt * stiff);
-    real Dinv = 1 / D;
-    real u = tq - damp * qd - stiff * (L[LS_Q] + dt * qd) - dot(ax, pA.w);
-    V3 aq = qd * ax;
-    SV c{cross(v.w, aq), cross(v.v, aq)};
-    ABI Ia = rank1_sub(IA, U, Dinv);
-    SV pa = pA + mul(Ia, c) + (Dinv * u) * U;
-    st_abi(A + A_CIA, abi_to_parent(E, r, Ia));
-    st6(A + A_CPA, xform_force_T(E, r, pa));
-    st6(L + LS_U, U);
-    L[LS_SC + 1] = u;
-    L[LS_SC + 2] = Dinv;
-    L[LS_SC + 3] = 0;
-    sync.signal(fl + i, base + ST_PASS2);
-  }
-  sync.mark(3);
-  // ---- floating base (base role): inverse articulated inertia, base acceleration, predicted base velocity
-  if (base_role) {
-    const float* R = REC(0);
-    real* L = BLK(0);
-    real* A = L + LS_A;
-    ABI IA = link_inertia(X, hot, m, R);
-    SV pA = ld6(A + A_PA);
-    for (int j = 0; j < RI(R, R_NCHILD); ++j) {
-      const int cf = RI(R, R_CHILD0 + j), c = cf & ~REC_FOREIGN;
-      if (cf & REC_FOREIGN) sync.wait(fl + c, base + ST_PASS2);
-      const real* Ac = BLK(c) + LS_A;
-      IA = IA + ld_abi(Ac + A_CIA);
-      pA = pA + ld6(Ac + A_CPA);
-    }
+    sync.mark(3);
     real f[36];
     abi_to_full(IA, f);
     spd6_inverse(f);
@@ -350,6 +346,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     sync.signal(fl + 0, base + ST_PASS2);
     // inverse inertia at the feet's common ancestor: Om_j = L_j^T Om_parent L_j + S D^-1 S^T down the shared links
     ABI Oml = Om0;
+#pragma unroll 1
     for (int k = 0; k < m.shared_len; ++k) {
       const float* Rs = REC(m.shared_rec[k]);
       const real* Ls = BLK(RI(Rs, R_LINK));
@@ -363,6 +360,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     st_abi(X + X_OML, Oml);
     sync.signal(flags + F_OML, epoch + 1);
   }
+  if (!base_role) sync.mark(3);
   sync.mark(4);
   // ---- feet, part 1 (needs pass 2 of the own leg chain only): up the chain, G = map foot force -> force on the
   //      current link; Om = sum_j g_j g_j^T / D_j with g_j = S_j^T G_j (kept per chain link for the impulse pass)
@@ -437,6 +435,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     SV P = sv_zero();     // accumulated contact impulse on the foot (foot coordinates)
     if (m.shared_len > 0) {  // predicted velocity of the common ancestor (needs pass 3 of the shared links)
       sync.wait(fl + m.lca, base + ST_PASS3);
+#pragma unroll 1
       for (int k = 0; k < m.shared_len; ++k) {
         const float* Rs = REC(m.shared_rec[k]);
         const real* Ls = BLK(RI(Rs, R_LINK));
@@ -587,6 +586,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
       sync.wait(flags + F_PD + f, epoch + 1);
       pd = pd + ld6(X + X_PD + 6 * f);  // impulse arriving at the common ancestor
     }
+#pragma unroll 1
     for (int k = m.shared_len - 1; k >= 0; --k) {  // ... and from there up the shared links to the base
       const float* Rs = REC(m.shared_rec[k]);
       real* Ls = BLK(RI(Rs, R_LINK));
@@ -599,6 +599,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
   }
   sync.mark(10);
   // ---- down the tree: joint velocity changes, speed cap, integration, limit projection
+  if (io_async) sync.wait(flags + F_IO_DONE, epoch + 1);
   for (int k = 0; k < len; ++k) {
     const float* R = REC(rec0 + k);
     const int i = RI(R, R_LINK), par = RI(R, R_PARENT), flg = RI(R, R_FLAGS);

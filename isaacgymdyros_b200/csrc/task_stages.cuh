@@ -133,9 +133,11 @@ __device__ __forceinline__ NoiseSlabArgs noise_args(const TK& k) {
 }
 // `state_of(le, d, which)` supplies the joint angle (which = 0) / velocity (1): global dof_state or the fused kernel's
 // scratch blocks.
-template <class Sync, class Sink, class StateFn>
+// Split in two: the part below reads simul_len, stage_simul_len_update (after a barrier of the cooperating threads)
+// advances it. `tid` of `nthreads` = 128 VIRTUAL threads: a single warp runs it as four chunks of 32.
+template <class Sink, class StateFn>
 __device__ __forceinline__ void stage_substep_torque_cta(const TorqueSlabArgs& k, int e0, int nenv, int tid, int nthreads,
-                                                         Sync& cta_sync, Sink tau_sink, StateFn state_of) {
+                                                         Sink tau_sink, StateFn state_of) {
   constexpr int NU = ND - 12;
   constexpr int THREADS = 128;
   const FastDiv dNU(NU), d12(12);
@@ -201,7 +203,9 @@ __device__ __forceinline__ void stage_substep_torque_cta(const TorqueSlabArgs& k
       }
     }
   }
-  cta_sync();  // every thread has read simul_len
+}
+__device__ __forceinline__ void stage_simul_len_update(const TorqueSlabArgs& k, int e0, int nenv, int tid, int nthreads) {
+#pragma unroll 1
   for (int le = tid; le < nenv; le += nthreads) {
     int s1 = k.simul_len[e0 + le] + 1;
     k.simul_len[e0 + le] = s1 > LOG_DEPTH ? LOG_DEPTH : (s1 < 0 ? 0 : s1);

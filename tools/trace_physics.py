@@ -16,7 +16,7 @@ tr = env.core.task_physics_trace().cpu()
 torch.cuda.synchronize()
 for s in range(tr.shape[0]):
     t0 = int(tr[s, :, 13].min())
-    print(f"sub-step {s}: torque+staging until {[int(tr[s, r, 14]) - t0 for r in range(4)]}, end {[int(tr[s, r, 15]) - t0 for r in range(4)]}")
+    print(f"sub-step {s}: roles start at {[int(tr[s, r, 0]) - t0 for r in range(4)]}, end {[int(tr[s, r, 15]) - t0 for r in range(4)]}")
     print(f"{'phase':24s}" + "".join(f"   role{r}: start   dur" for r in range(4)))
     print("pass1 split (E loop | propagation | forces): " + "  ".join(
         f"role{r}: {int(tr[s, r, 16]) - int(tr[s, r, 0])} | {int(tr[s, r, 17]) - int(tr[s, r, 16])} | {int(tr[s, r, 1]) - int(tr[s, r, 17])}" for r in range(4)))
