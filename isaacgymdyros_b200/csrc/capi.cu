@@ -348,16 +348,15 @@ int dyros_task_step(DyrosTask* task, const float* actions, void* stream) {
     return 1;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  // kernels 2-4 use programmatic dependent launch: their CTAs get resident and run their preamble while the previous
+  // the kernels use programmatic dependent launch: their CTAs get resident and run their preamble while the previous
   // kernel drains (common.cuh); the data dependency is enforced by griddepcontrol.wait inside each kernel
-  if (launch_prologue(t, actions, st)) return 1;
-  if (launch_task_physics(t, st, nullptr, true)) return 1;
+  if (launch_task_physics(t, st, nullptr, true, actions)) return 1;  // prologue folded into the physics launch
   if (launch_post_fused(t, st, true)) return 1;
   return launch_crossenv(t, true, true, true, st, true);
 }
 int dyros_task_step_launches(DyrosTask* task) {
   TASK_OR_FAIL("dyros_task_step_launches");
-  return 4;  // prologue, fused physics, fused post-physics, cross-env
+  return 3;  // prologue + fused physics, fused post-physics, cross-env
 }
 
 }  // extern "C"

@@ -141,7 +141,8 @@ int launch_post_fused(Task* t, cudaStream_t s, bool pdl = false);
 int physics_configure(Sim* sim);  // chooses envs_per_block / shared memory, sets the kernel attributes
 int launch_simulate(Sim* sim, int apply_wrench, const float* push_force, cudaStream_t s);
 int launch_refresh_rigid_body_state(Sim* sim, cudaStream_t s);
-int launch_task_physics(Task* t, cudaStream_t s, long long* trace = nullptr, bool pdl = false);  // skipframe x (torque, simulate, sensor noise) in one launch
+// skipframe x (torque, simulate, sensor noise) in one launch; with `actions` the policy-step prologue runs in it too
+int launch_task_physics(Task* t, cudaStream_t s, long long* trace = nullptr, bool pdl = false, const float* actions = nullptr);
 int measure_fp32_peak(int device, int iters, double* tflops_out);
 
 }  // namespace dyros

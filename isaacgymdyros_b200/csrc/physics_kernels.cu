@@ -244,17 +244,20 @@ __global__ void __launch_bounds__(kPhysThreads) k_simulate(DevModel m, SimParams
   }
 }
 
-// The physics part of one policy step in ONE launch: skipframe x (PD + delay torque, gym.simulate, sensor noise),
-// i.e. the loop body of T:504-530 with the three gym calls of T:520-526 folded in.
-// Warps 0-3 run the role programs; warps 4-7 are the I/O group: while the roles are in pass 1 of a sub-step it zeroes
-// the contact forces and stages the push (F_IO_PRE), draws the sensor noise of the PREVIOUS policy sub-step (which only
-// reads the joint angles, untouched until the roles' last pass), evaluates the torque stage and re-stages damping and
-// armature (F_IO_TAU, consumed by pass 2), so none of this sits on the roles' critical path.
 constexpr int kIoThreads = 128;
 constexpr int kStepThreads = kPhysThreads + kIoThreads;
 __device__ __forceinline__ void io_group_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kIoThreads) : "memory"); }
 
-__global__ void __launch_bounds__(kStepThreads) k_step_physics(DevModel m, SimParams p, TK k, int epb, int es, long long* trace) {
+// The physics part of one policy step in ONE launch: skipframe x (PD + delay torque, gym.simulate, sensor noise),
+// i.e. the loop body of T:504-530 with the three gym calls of T:520-526 folded in; with `actions` also the part of
+// pre_physics_step before that loop (T:449-502).
+// Warps 0-3 run the role programs; warps 4-7 are the I/O group: while the roles are in pass 1 of a sub-step it zeroes
+// the contact forces and stages the push (F_IO_PRE), draws the sensor noise of the PREVIOUS policy sub-step (which only
+// reads the joint angles, untouched until the roles' last pass), evaluates the torque stage and re-stages damping and
+// armature (F_IO_TAU, consumed by pass 2), so none of this sits on the roles' critical path.
+
+__global__ void __launch_bounds__(kStepThreads) k_step_physics(DevModel m, SimParams p, TK k, int epb, int es, long long* trace,
+                                                                const float* __restrict__ actions) {
   extern __shared__ __align__(16) float smem[];
   PhysCta c = phys_cta_setup(m, p, smem, epb, es);
   const int e0 = blockIdx.x * epb, nenv = min(epb, p.N - e0);
@@ -285,6 +288,10 @@ __global__ void __launch_bounds__(kStepThreads) k_step_physics(DevModel m, SimPa
   for (int s = 0; s < k.p.skipframe; ++s) {
     for (int ss = 0; ss < p.substeps; ++ss, ++epoch) {
       if (io_group) {
+        if (actions && epoch == 0) {  // the policy-step prologue (T:449-502) of the CTA's envs
+          stage_prologue_slab(k, actions, e0, nenv, it, kIoThreads, [] { io_group_sync(); });
+          io_group_sync();
+        }
         // the push acts on the first sub-step of the policy step only (T:502 vs T:504)
         slab_stage_pre(m, k.s, (s == 0 && ss == 0) ? k.b.push_force : nullptr, envs, es, e0, nenv, it, kIoThreads);
         cp_async_wait_all();
@@ -348,7 +355,7 @@ int launch_simulate(Sim* sim, int apply_wrench, const float* push, cudaStream_t 
   return 0;
 }
 
-int launch_task_physics(Task* t, cudaStream_t s, long long* trace, bool pdl) {
+int launch_task_physics(Task* t, cudaStream_t s, long long* trace, bool pdl, const float* actions) {
   Sim* sim = t->sim;
   const int epb = sim->envs_per_block;
   const int grid = (sim->p.N + epb - 1) / epb;
@@ -358,7 +365,7 @@ int launch_task_physics(Task* t, cudaStream_t s, long long* trace, bool pdl) {
   k.s = sim->b;
   k.j = t->inj;
   DY_CUDA(launch_kernel(k_step_physics, dim3(grid), dim3(kStepThreads), sim->phys_smem, s, pdl, sim->m, sim->p, k, epb,
-                        env_scratch_floats(sim->m.nl), trace));
+                        env_scratch_floats(sim->m.nl), trace, actions));
   return 0;
 }
 

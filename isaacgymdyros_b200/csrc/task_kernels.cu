@@ -11,21 +11,6 @@ namespace dyros {
 constexpr int kWarpsPerBlock = 4;
 
 // ------------------------------------------------------------------ small math (TU / JU restated)
-// JU:374-395 with x_dot_0 = x_dot_f = 0.0 (T:458-461), reference operation order
-__device__ __forceinline__ float cubic0(float time, float t0, float tf, float x0, float xf) {
-  float e = time - t0;
-  float tt = tf - t0;
-  float tt2 = tt * tt;
-  float tt3 = tt2 * tt;
-  float tx = xf - x0;
-  float c = x0 + 0.0f * e;
-  c = c + ((3.0f * tx) / tt2 - 0.0f / tt - 0.0f / tt) * e * e;
-  c = c + ((-2.0f * tx) / tt3 + 0.0f / tt2) * e * e * e;
-  float xt = (time > tf) ? xf : x0;
-  if (t0 <= time && time <= tf) xt = c;
-  return xt;
-}
-
 // JU:142-160 with a = identity: |vec(a (x) conj(q))| through the TU:20-40 product, then 2*asin(min(.,1))
 __device__ __forceinline__ float quat_err_identity(const float* q) {
   float x2 = -q[0], y2 = -q[1], z2 = -q[2], w2 = q[3];
@@ -72,80 +57,6 @@ __device__ __forceinline__ bool collision_true(const TK& k, int e, int lane) {
 }
 
 // ------------------------------------------------------------------ stages (device functions, one warp per env)
-// VT:307 clamp + T:449-468 + push schedule T:489-502, T:438-447
-__device__ void stage_prologue(const TK& k, const float* __restrict__ actions_in, int e, int lane) {
-  const TaskParams& P = k.p;
-  float time = k.b.time[e];
-  int init = k.b.init_mocap_data_idx[e];
-  float local_time = py_fmodf(time, P.period);                                   // T:450
-  float lt_init = py_fmodf(local_time + (float)init * P.cycle_dt, P.period);     // T:451
-  int idx = (int)(((long long)init + (long long)(local_time / P.cycle_dt)) % P.mocap_data_num);  // T:452
-  if (lane == 0) k.b.mocap_data_idx[e] = idx;
-  const float* r0 = k.b.mocap_data + (size_t)idx * 36;
-  const float* r1 = r0 + 36;
-  float t0 = r0[0], tf = r1[0];
-  for (int c = lane; c < 35; c += kWarp) {                                        // T:458-461
-    float v = cubic0(lt_init, t0, tf, r0[1 + c], r1[1 + c]);
-    if (c < ND) k.b.target_data_qpos[(size_t)e * ND + c] = v;
-    else k.b.target_data_force[(size_t)e * 2 + (c - ND)] = v;
-  }
-  if (lane < NA) {
-    float a = actions_in[(size_t)e * NA + lane];
-    a = (a < -1.0f) ? -1.0f : ((a > 1.0f) ? 1.0f : a);                            // VT:307 (NaN passes through)
-    if (lane == NA - 1) a = ((a > 0.0f) ? 1.0f : 0.0f) * a;                       // T:464-465
-    k.b.actions[(size_t)e * NA + lane] = a;
-    int head = (k.b.act_hist_head[e] + 1) % NSLOT;                                // T:466 as a ring push
-    k.b.action_history[((size_t)e * NSLOT + head) * NA + lane] = a;
-    if (lane < 12)                                                                // T:468
-      k.b.action_torque[(size_t)e * 12 + lane] = a * k.b.motor_constant_scale[(size_t)e * 12 + lane] * P.action_high[lane];
-    __syncwarp(0x1fffu);
-    if (lane == 0) k.b.act_hist_head[e] = head;
-  }
-  if (lane == 0) {
-    float fx = 0.f, fy = 0.f;
-    if (*k.b.perturb_start) {                                                     // T:492
-      int on = k.b.pert_on[e], cnt = k.b.perturbation_count[e], dur = k.b.pert_duration[e];
-      float mag = k.b.magnitude[e], ph = k.b.phase[e];
-      if (py_fmodf(k.b.epi_len[e], P.pert_period) == (float)k.b.perturb_timing[e]) {  // T:495
-        int imp;
-        float u;
-        if (k.j.pert_i) {
-          imp = (int)k.j.pert_i[(size_t)e * 2];
-          dur = (int)k.j.pert_i[(size_t)e * 2 + 1];
-          u = k.j.pert_f[e];
-        } else {
-          uint4 r = draw4(P.seed, *P.step_counter, e, kSitePert, 0);
-          int lo = (int)(0.1 / (double)P.dt_policy), hi = (int)(1.0 / (double)P.dt_policy);
-          imp = 50 + (int)(r.x % 200u);                                           // T:440 randint(50,250)
-          dur = lo + (int)(r.y % (uint32_t)(hi - lo));                            // T:441
-          u = u01(r.z);
-        }
-        on = 1;                                                                   // T:439
-        mag = (float)imp / ((float)dur * P.dt_policy);                            // T:442
-        ph = u * 2.0f * 3.14159265358979f;                                        // T:443
-        k.b.impulse[e] = imp;
-        k.b.pert_duration[e] = dur;
-        k.b.magnitude[e] = mag;
-        k.b.phase[e] = ph;
-      }
-      if (on) cnt += 1;                                                           // T:497
-      if (on) {                                                                   // T:498-499
-        fx = mag * cosf(ph);
-        fy = mag * sinf(ph);
-      }
-      if (cnt == dur) {                                                           // T:500-501, T:445-447
-        on = 0;
-        cnt = 0;
-      }
-      k.b.pert_on[e] = on;
-      k.b.perturbation_count[e] = cnt;
-    }
-    k.b.push_force[(size_t)e * 3 + 0] = fx;
-    k.b.push_force[(size_t)e * 3 + 1] = fy;
-    k.b.push_force[(size_t)e * 3 + 2] = 0.f;
-  }
-}
-
 struct WarpSyncT {
   __device__ __forceinline__ void operator()() const { __syncwarp(); }
 };

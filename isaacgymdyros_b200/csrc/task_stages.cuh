@@ -14,6 +14,148 @@ struct TK {
   DyrosNoiseInjection j;
 };
 
+// JU:374-395 with x_dot_0 = x_dot_f = 0.0 (T:458-461), reference operation order
+__device__ __forceinline__ float cubic0(float time, float t0, float tf, float x0, float xf) {
+  float e = __fsub_rn(time, t0);
+  float tt = __fsub_rn(tf, t0);
+  float tt2 = __fmul_rn(tt, tt);
+  float tt3 = __fmul_rn(tt2, tt);
+  float tx = __fsub_rn(xf, x0);
+  float c = __fadd_rn(x0, __fmul_rn(0.0f, e));
+  float a2 = __fsub_rn(__fsub_rn(__fdiv_rn(__fmul_rn(3.0f, tx), tt2), __fdiv_rn(0.0f, tt)), __fdiv_rn(0.0f, tt));
+  c = __fadd_rn(c, __fmul_rn(__fmul_rn(a2, e), e));
+  float a3 = __fadd_rn(__fdiv_rn(__fmul_rn(-2.0f, tx), tt3), __fdiv_rn(0.0f, tt2));
+  c = __fadd_rn(c, __fmul_rn(__fmul_rn(__fmul_rn(a3, e), e), e));
+  float xt = (time > tf) ? xf : x0;
+  if (t0 <= time && time <= tf) xt = c;
+  return xt;
+}
+
+// push schedule of one env (T:489-502, T:438-447): one thread
+__device__ __forceinline__ void stage_push_schedule(const TK& k, int e) {
+  const TaskParams& P = k.p;
+  float fx = 0.f, fy = 0.f;
+  if (*k.b.perturb_start) {                                                     // T:492
+    int on = k.b.pert_on[e], cnt = k.b.perturbation_count[e], dur = k.b.pert_duration[e];
+    float mag = k.b.magnitude[e], ph = k.b.phase[e];
+    if (py_fmodf(k.b.epi_len[e], P.pert_period) == (float)k.b.perturb_timing[e]) {  // T:495
+      int imp;
+      float u;
+      if (k.j.pert_i) {
+        imp = (int)k.j.pert_i[(size_t)e * 2];
+        dur = (int)k.j.pert_i[(size_t)e * 2 + 1];
+        u = k.j.pert_f[e];
+      } else {
+        uint4 r = draw4(P.seed, *P.step_counter, e, kSitePert, 0);
+        int lo = (int)(0.1 / (double)P.dt_policy), hi = (int)(1.0 / (double)P.dt_policy);
+        imp = 50 + (int)(r.x % 200u);                                           // T:440 randint(50,250)
+        dur = lo + (int)(r.y % (uint32_t)(hi - lo));                            // T:441
+        u = u01(r.z);
+      }
+      on = 1;                                                                   // T:439
+      mag = __fdiv_rn((float)imp, __fmul_rn((float)dur, P.dt_policy));          // T:442
+      ph = __fmul_rn(__fmul_rn(u, 2.0f), 3.14159265358979f);                    // T:443
+      k.b.impulse[e] = imp;
+      k.b.pert_duration[e] = dur;
+      k.b.magnitude[e] = mag;
+      k.b.phase[e] = ph;
+    }
+    if (on) cnt += 1;                                                           // T:497
+    if (on) {                                                                   // T:498-499
+      fx = __fmul_rn(mag, cosf(ph));
+      fy = __fmul_rn(mag, sinf(ph));
+    }
+    if (cnt == dur) {                                                           // T:500-501, T:445-447
+      on = 0;
+      cnt = 0;
+    }
+    k.b.pert_on[e] = on;
+    k.b.perturbation_count[e] = cnt;
+  }
+  k.b.push_force[(size_t)e * 3 + 0] = fx;
+  k.b.push_force[(size_t)e * 3 + 1] = fy;
+  k.b.push_force[(size_t)e * 3 + 2] = 0.f;
+}
+
+// VT:307 clamp + T:449-468 + push schedule T:489-502, T:438-447; one warp per env. Runs as its own kernel
+// (k_prologue) and on the I/O warps of the fused physics kernel.
+__device__ __forceinline__ void stage_prologue(const TK& k, const float* __restrict__ actions_in, int e, int lane) {
+  const TaskParams& P = k.p;
+  float time = k.b.time[e];
+  int init = k.b.init_mocap_data_idx[e];
+  float local_time = py_fmodf(time, P.period);                                                          // T:450
+  float lt_init = py_fmodf(__fadd_rn(local_time, __fmul_rn((float)init, P.cycle_dt)), P.period);        // T:451
+  int idx = (int)(((long long)init + (long long)__fdiv_rn(local_time, P.cycle_dt)) % P.mocap_data_num);  // T:452
+  if (lane == 0) k.b.mocap_data_idx[e] = idx;
+  const float* r0 = k.b.mocap_data + (size_t)idx * 36;
+  const float* r1 = r0 + 36;
+  float t0 = r0[0], tf = r1[0];
+  for (int c = lane; c < 35; c += 32) {                                           // T:458-461
+    float v = cubic0(lt_init, t0, tf, r0[1 + c], r1[1 + c]);
+    if (c < ND) k.b.target_data_qpos[(size_t)e * ND + c] = v;
+    else k.b.target_data_force[(size_t)e * 2 + (c - ND)] = v;
+  }
+  if (lane < NA) {
+    float a = actions_in[(size_t)e * NA + lane];
+    a = (a < -1.0f) ? -1.0f : ((a > 1.0f) ? 1.0f : a);                            // VT:307 (NaN passes through)
+    if (lane == NA - 1) a = __fmul_rn((a > 0.0f) ? 1.0f : 0.0f, a);               // T:464-465
+    k.b.actions[(size_t)e * NA + lane] = a;
+    int head = (k.b.act_hist_head[e] + 1) % NSLOT;                                // T:466 as a ring push
+    k.b.action_history[((size_t)e * NSLOT + head) * NA + lane] = a;
+    if (lane < 12)                                                                // T:468
+      k.b.action_torque[(size_t)e * 12 + lane] =
+          __fmul_rn(__fmul_rn(a, k.b.motor_constant_scale[(size_t)e * 12 + lane]), P.action_high[lane]);
+    __syncwarp(0x1fffu);
+    if (lane == 0) k.b.act_hist_head[e] = head;
+  }
+  if (lane == 0) stage_push_schedule(k, e);
+}
+
+// The same stage for a contiguous slab of envs [e0, e0 + nenv), thread `tid` of `nthreads` cooperating threads with one
+// (env, column) item per thread and iteration, so that the items' memory latencies overlap (the warp-per-env form
+// above is a serial chain per env). Same arithmetic, same bits. `group_sync` is a barrier of the cooperating threads.
+template <class GroupSync>
+__device__ __forceinline__ void stage_prologue_slab(const TK& k, const float* __restrict__ actions_in, int e0, int nenv, int tid,
+                                                    int nthreads, GroupSync group_sync) {
+  const TaskParams& P = k.p;
+  const FastDiv d35(35), dNA(NA);
+#pragma unroll 2
+  for (int it = tid; it < nenv * 35; it += nthreads) {                            // T:450-461
+    const int le = d35.div(it), c = it - le * 35, e = e0 + le;
+    float time = k.b.time[e];
+    int init = k.b.init_mocap_data_idx[e];
+    float local_time = py_fmodf(time, P.period);
+    float lt_init = py_fmodf(__fadd_rn(local_time, __fmul_rn((float)init, P.cycle_dt)), P.period);
+    int idx = (int)(((long long)init + (long long)__fdiv_rn(local_time, P.cycle_dt)) % P.mocap_data_num);
+    if (c == 0) k.b.mocap_data_idx[e] = idx;
+    const float* r0 = k.b.mocap_data + (size_t)idx * 36;
+    const float* r1 = r0 + 36;
+    float v = cubic0(lt_init, r0[0], r1[0], r0[1 + c], r1[1 + c]);
+    if (c < ND) k.b.target_data_qpos[(size_t)e * ND + c] = v;
+    else k.b.target_data_force[(size_t)e * 2 + (c - ND)] = v;
+  }
+#pragma unroll 1
+  for (int it = tid; it < nenv * NA; it += nthreads) {                            // VT:307, T:464-468
+    const int le = dNA.div(it), lane = it - le * NA, e = e0 + le;
+    float a = actions_in[(size_t)e * NA + lane];
+    a = (a < -1.0f) ? -1.0f : ((a > 1.0f) ? 1.0f : a);
+    if (lane == NA - 1) a = __fmul_rn((a > 0.0f) ? 1.0f : 0.0f, a);
+    k.b.actions[(size_t)e * NA + lane] = a;
+    int head = (k.b.act_hist_head[e] + 1) % NSLOT;
+    k.b.action_history[((size_t)e * NSLOT + head) * NA + lane] = a;
+    if (lane < 12)
+      k.b.action_torque[(size_t)e * 12 + lane] =
+          __fmul_rn(__fmul_rn(a, k.b.motor_constant_scale[(size_t)e * 12 + lane]), P.action_high[lane]);
+  }
+  group_sync();  // every item has read act_hist_head
+#pragma unroll 1
+  for (int le = tid; le < nenv; le += nthreads) {                                 // ring head, push schedule T:489-502
+    const int e = e0 + le;
+    k.b.act_hist_head[e] = (k.b.act_hist_head[e] + 1) % NSLOT;
+    stage_push_schedule(k, e);
+  }
+}
+
 // T:505-520: upper-body PD, actuation-delay ring, the 33 torques of set_dof_actuation_force_tensor.
 // LANES lanes of one env cooperate; `lane` in [0, LANES). Ends with the lanes in sync.
 template <int LANES, class Sync>
