@@ -262,6 +262,34 @@ HD M3 axis_rot_T(V3 a, real s, real c) {
   return transpose(R);
 }
 
+// Inverse of a symmetric positive definite 3x3 (adjugate / determinant).
+HD S3 spd3_inverse(const S3& s) {
+  real cxx = s.yy * s.zz - s.yz * s.yz, cyy = s.xx * s.zz - s.xz * s.xz, czz = s.xx * s.yy - s.xy * s.xy;
+  real cxy = s.xz * s.yz - s.xy * s.zz, cxz = s.xy * s.yz - s.xz * s.yy, cyz = s.xy * s.xz - s.xx * s.yz;
+  real inv = 1 / (s.xx * cxx + s.xy * cxy + s.xz * cxz);
+  return S3{inv * cxx, inv * cyy, inv * czz, inv * cxy, inv * cxz, inv * cyz};
+}
+// Inverse of a symmetric positive definite [[I, H], [H^T, M]] through the Schur complement of M (M: the
+// articulated mass block, I - H M^-1 H^T: the rotational inertia about the centre of mass; both well conditioned):
+// [[S^-1, -S^-1 P], [-P^T S^-1, M^-1 + P^T S^-1 P]] with P = H M^-1, S = I - P H^T.
+HD ABI abi_inverse_spd(const ABI& a) {
+  const M3 Mi = full(spd3_inverse(a.M));
+  const M3 P = mul(a.H, Mi);
+  const M3 PHt = mulABt(P, a.H);
+  const S3 S{a.I.xx - PHt.a[0], a.I.yy - PHt.a[4], a.I.zz - PHt.a[8],
+             a.I.xy - (real)0.5 * (PHt.a[1] + PHt.a[3]), a.I.xz - (real)0.5 * (PHt.a[2] + PHt.a[6]),
+             a.I.yz - (real)0.5 * (PHt.a[5] + PHt.a[7])};
+  const M3 Si = full(spd3_inverse(S));
+  const M3 Q = mul(Si, P);  // S^-1 P
+  const M3 PtQ = mulAtB(P, Q);
+  ABI o;
+  o.I = sym_of(Si);
+  o.H = M3{{-Q.a[0], -Q.a[1], -Q.a[2], -Q.a[3], -Q.a[4], -Q.a[5], -Q.a[6], -Q.a[7], -Q.a[8]}};
+  o.M = S3{Mi.a[0] + PtQ.a[0], Mi.a[4] + PtQ.a[4], Mi.a[8] + PtQ.a[8], Mi.a[1] + (real)0.5 * (PtQ.a[1] + PtQ.a[3]),
+           Mi.a[2] + (real)0.5 * (PtQ.a[2] + PtQ.a[6]), Mi.a[5] + (real)0.5 * (PtQ.a[5] + PtQ.a[7])};
+  return o;
+}
+
 // In-place inverse of a symmetric positive definite 6x6 (row-major full storage) by Cholesky.
 HD void spd6_inverse(real* a) {
   real L[36];

@@ -330,10 +330,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
       continue;
     }
     sync.mark(3);
-    real f[36];
-    abi_to_full(IA, f);
-    spd6_inverse(f);
-    ABI Om0 = abi_from_full(f);
+    ABI Om0 = abi_inverse_spd(IA);
     SV a0 = (real)-1 * mul(Om0, pA);  // acceleration relative to the gravity field
     M3 R0 = ld_m3(L + LS_E);
     SV v0 = ld6(L + LS_V);
