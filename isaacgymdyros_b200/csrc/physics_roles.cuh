@@ -398,6 +398,48 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
       for (int c = 0; c < 6; ++c) G[c] = xform_force_T(E, r, G[c] - (Dinv * gj[c]) * U);
     }
   }
+  // active sole points of this foot (needs the foot pose of pass 1 only): candidates below the contact offset, at
+  // most MAX_ACTIVE_PTS, with their offsets from the foot origin and the velocity bias of the non-penetration row
+  real* rowblk[MAX_ACTIVE_PTS * 3 / ROWS_PER_LINK];
+  M3 Rwf;
+  V3 nrm = v3(0, 0, 1);
+  V3 xs[MAX_ACTIVE_PTS];
+  real bias[MAX_ACTIVE_PTS], lam[MAX_ACTIVE_PTS][3];
+  int pbody[MAX_ACTIVE_PTS];
+  int nact = 0;
+  const real inv_dt = 1 / dt;
+  if (foot >= 0) {
+    const int g = foot;
+#pragma unroll
+    for (int k = 0; k < MAX_ACTIVE_PTS * 3 / ROWS_PER_LINK; ++k) rowblk[k] = BLK(m.chain[g][k]) + LS_A + A_ROWS;
+    Rwf = ld_m3(X + X_FOOTPOSE + 12 * g);
+    real pz = X[X_FOOTPOSE + 12 * g + 11];
+    nrm = v3(Rwf.a[6], Rwf.a[7], Rwf.a[8]);
+#pragma unroll
+    for (int a = 0; a < MAX_ACTIVE_PTS; ++a) {
+      xs[a] = v3(0, 0, 0);
+      bias[a] = 0;
+      pbody[a] = 0;
+      lam[a][0] = lam[a][1] = lam[a][2] = 0;
+    }
+    for (int k = 0; k < m.foot_npts[g]; ++k) {
+      V3 x = v3(m.foot_pt_pos[g][k][0], m.foot_pt_pos[g][k][1], m.foot_pt_pos[g][k][2]);
+      real rad = m.foot_pt_radius[g][k];
+      real phi = pz + dot(nrm, x) - rad;
+      if (phi < p.contact_offset && nact < MAX_ACTIVE_PTS) {
+        real b = phi >= 0 ? -phi * inv_dt : fmin_r(-p.erp * phi * inv_dt, p.max_depen_vel);
+        V3 xsk = x - rad * nrm;
+#pragma unroll
+        for (int a = 0; a < MAX_ACTIVE_PTS; ++a)
+          if (a == nact) {
+            xs[a] = xsk;
+            bias[a] = b;
+            pbody[a] = m.foot_pt_body[g][k];
+          }
+        ++nact;
+      }
+    }
+  }
   sync.mark(5);
   // ---- pass 3, root -> leaves: joint accelerations, predicted joint velocities
   for (int k = 0; k < len; ++k) {
@@ -463,56 +505,21 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
 #pragma unroll
         for (int b = 0; b < 3; ++b) Om.H.a[3 * a + b] += w[a][3 + b];
     }
-    // blocks of the first chain links park the contact rows (2 per link): resolve their addresses once
-    real* rowblk[MAX_ACTIVE_PTS * 3 / ROWS_PER_LINK];
+    // rows of the active points: response cv = Om J and 1 / (J . cv) per direction (n, t1, t2), parked in the blocks
+    // of the first chain links (2 per link)
 #pragma unroll
-    for (int k = 0; k < MAX_ACTIVE_PTS * 3 / ROWS_PER_LINK; ++k) rowblk[k] = BLK(m.chain[g][k]) + LS_A + A_ROWS;
-    const real inv_dt = 1 / dt;
-    M3 Rwf = ld_m3(X + X_FOOTPOSE + 12 * g);
-    real pz = X[X_FOOTPOSE + 12 * g + 11];
-    V3 nrm = v3(Rwf.a[6], Rwf.a[7], Rwf.a[8]);
-    V3 xs[MAX_ACTIVE_PTS];
-    real bias[MAX_ACTIVE_PTS], lam[MAX_ACTIVE_PTS][3];
-    int pbody[MAX_ACTIVE_PTS];
-    int nact = 0;
-#pragma unroll
-    for (int a = 0; a < MAX_ACTIVE_PTS; ++a) {
-      xs[a] = v3(0, 0, 0);
-      bias[a] = 0;
-      pbody[a] = 0;
-      lam[a][0] = lam[a][1] = lam[a][2] = 0;
-    }
-    for (int k = 0; k < m.foot_npts[g]; ++k) {
-      V3 x = v3(m.foot_pt_pos[g][k][0], m.foot_pt_pos[g][k][1], m.foot_pt_pos[g][k][2]);
-      real rad = m.foot_pt_radius[g][k];
-      real phi = pz + dot(nrm, x) - rad;
-      if (phi < p.contact_offset && nact < MAX_ACTIVE_PTS) {
-        real b = phi >= 0 ? -phi * inv_dt : fmin_r(-p.erp * phi * inv_dt, p.max_depen_vel);
-        V3 xsk = x - rad * nrm;
-#pragma unroll
-        for (int a = 0; a < MAX_ACTIVE_PTS; ++a)
-          if (a == nact) {
-            xs[a] = xsk;
-            bias[a] = b;
-            pbody[a] = m.foot_pt_body[g][k];
-          }
+    for (int a = 0; a < MAX_ACTIVE_PTS; ++a)
+      if (a < nact) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
           V3 dir = d == 0 ? nrm : (d == 1 ? v3(Rwf.a[0], Rwf.a[1], Rwf.a[2]) : v3(Rwf.a[3], Rwf.a[4], Rwf.a[5]));
-          SV J{cross(xsk, dir), dir};
+          SV J{cross(xs[a], dir), dir};
           SV cv = mul(Om, J);
-          real winv = 1 / dot(J, cv);
-#pragma unroll
-          for (int a = 0; a < MAX_ACTIVE_PTS; ++a)
-            if (a == nact) {  // parked in the block of chain link row / ROWS_PER_LINK (row = 3 a + d, compile-time here)
-              real* rw = rowblk[(a * 3 + d) / ROWS_PER_LINK] + ((a * 3 + d) % ROWS_PER_LINK) * 7;
-              st6(rw, cv);
-              rw[6] = winv;
-            }
+          real* rw = rowblk[(a * 3 + d) / ROWS_PER_LINK] + ((a * 3 + d) % ROWS_PER_LINK) * 7;
+          st6(rw, cv);
+          rw[6] = 1 / dot(J, cv);
         }
-        ++nact;
       }
-    }
     sync.mark(7);
     // fixed number of sweeps; Gauss-Seidel inside a foot, Jacobi between the feet (coupled through the base)
     for (int s = 0; s < p.sweeps; ++s) {
