@@ -220,6 +220,8 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
       R[R_LINK] = l;
       R[R_PARENT] = par;
       R[R_FLAGS] = (l > 0 && role_of[par] != role_of[l] ? RF_PARENT_FOREIGN : 0) | (l > 0 && par == 0 ? RF_PARENT_BASE : 0);
+      for (int ci = child_start[l]; ci < child_start[l + 1]; ++ci)
+        if (role_of[children[ci]] != role_of[l]) R[R_FLAGS] |= RF_PUBLISH;
       R[R_DOF] = l > 0 ? m->link_dof[l] : 0;
       const int nbod = body_start[l + 1] - body_start[l], nch = child_start[l + 1] - child_start[l];
       if (nbod > MAX_LINK_BODIES) MFAIL("link %d merges %d bodies (max %d)", l, nbod, MAX_LINK_BODIES);

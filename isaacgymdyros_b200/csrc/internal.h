@@ -20,6 +20,7 @@ constexpr int R_LINK = 0, R_PARENT = 1, R_FLAGS = 2, R_DOF = 3, R_NBODY = 4, R_B
               R_AXIS = 12, R_R = 15, R_E = 18, R_REACH = 27, R_PT0 = 28, R_PT1 = 29, R_CYL0 = 30, R_CYL1 = 31,
               R_VLIM = 32, R_LO = 33, R_UP = 34, R_EFF = 35, R_FOOT = 36, R_STIFF = 37;
 constexpr int RF_PARENT_FOREIGN = 1, RF_PARENT_BASE = 2;
+constexpr int RF_PUBLISH = 4;  // a child of the link lives in another role: its stage flags are read there
 struct DevModel {
   int nl, nb, nd, np, nc, T;
   const int* link_parent;

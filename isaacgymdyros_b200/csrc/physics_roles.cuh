@@ -263,7 +263,9 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     st6(L + LS_V, v);
     st_m3(L + LS_A + A_POSE, mulABt(Rwp, E));
     st3(L + LS_A + A_POSE + 9, ld3(Lp + LS_A + A_POSE + 9) + mul(Rwp, r));
-    sync.signal(fl + i, base + ST_PASS1);
+    // published only where another role reads it: by foreign children (pose, velocity), or by the foreign parent,
+    // which must not overwrite its pose before this link has used it
+    if (RI(R, R_FLAGS) & (RF_PUBLISH | RF_PARENT_FOREIGN)) sync.signal(fl + i, base + ST_PASS1);
   }
   sync.mark(17);
   // (c) bias forces and external wrenches: local to each link again (k = -1: the base itself, record 0)
@@ -326,7 +328,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
       L[LS_SC + 1] = u;
       L[LS_SC + 2] = Dinv;
       L[LS_SC + 3] = 0;
-      sync.signal(fl + i, base + ST_PASS2);
+      if (RI(R, R_FLAGS) & RF_PARENT_FOREIGN) sync.signal(fl + i, base + ST_PASS2);
       continue;
     }
     sync.mark(3);
@@ -462,7 +464,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     a.w = a.w + qdd * ax;
     st6(L + LS_A + A_ACC, a);
     L[LS_SC] = qd + dt * qdd;
-    sync.signal(fl + i, base + ST_PASS3);
+    if (flg & RF_PUBLISH) sync.signal(fl + i, base + ST_PASS3);
   }
   sync.mark(6);
   // ---- feet, part 2: predicted foot velocity, Om += G^T Om0 G, active sole points and their rows, the sweeps
@@ -619,7 +621,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     real dqd = -L[LS_SC + 2] * (dot(ld6(L + LS_U), dv) + L[LS_SC + 3]);
     dv.w = dv.w + dqd * ax;
     st6(L + LS_V, dv);
-    sync.signal(fl + i, base + ST_DOWN);
+    if (flg & RF_PUBLISH) sync.signal(fl + i, base + ST_DOWN);
     // joint velocity cap (dof_prop['velocity'], T:372), explicit Euler on the angle, limit projection
     real vl = R[R_VLIM];
     real qdn = L[LS_SC] + dqd;
