@@ -226,6 +226,12 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
   sync.mark(0);
   const int rec0 = m.prog_start[role];
   // ---- pass 1, root -> leaves: transforms, velocities, world poses, bias forces
+  // Along a chain the parent is the link handled just before: its results are carried in registers (`prev`), the
+  // scratch block is only read for the first link of a chain. The same holds for the other tree passes.
+  int prev = -1;
+  SV v_prev = sv_zero();
+  M3 Rw_prev;
+  V3 pw_prev = v3(0, 0, 0);
   if (base_role) {
     real* L = BLK(0);
     const real* rs = X + X_ROOT;
@@ -237,6 +243,10 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     st_m3(L + LS_A + A_POSE, R0);
     st3(L + LS_A + A_POSE + 9, pw);
     sync.signal(fl + 0, base + ST_PASS1);
+    prev = 0;
+    v_prev = v0;
+    Rw_prev = R0;
+    pw_prev = pw;
   }
   // (a) joint transforms: local to each link, no dependencies
   for (int k = 0; k < len; ++k) {
@@ -252,17 +262,25 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
   for (int k = 0; k < len; ++k) {
     const float* R = REC(rec0 + k);
     const int i = RI(R, R_LINK), par = RI(R, R_PARENT);
-    if (RI(R, R_FLAGS) & RF_PARENT_FOREIGN) sync.wait(fl + par, base + ST_PASS1);
     real* L = BLK(i);
-    const real* Lp = BLK(par);
+    if (par != prev) {
+      if (RI(R, R_FLAGS) & RF_PARENT_FOREIGN) sync.wait(fl + par, base + ST_PASS1);
+      const real* Lp = BLK(par);
+      v_prev = ld6(Lp + LS_V);
+      Rw_prev = ld_m3(Lp + LS_A + A_POSE);
+      pw_prev = ld3(Lp + LS_A + A_POSE + 9);
+    }
     V3 ax = ld3_f(R + R_AXIS), r = ld3_f(R + R_R);
     M3 E = ld_m3(L + LS_E);
-    SV v = xform_motion(E, r, ld6(Lp + LS_V));
+    SV v = xform_motion(E, r, v_prev);
     v.w = v.w + L[LS_SC] * ax;
-    M3 Rwp = ld_m3(Lp + LS_A + A_POSE);
+    pw_prev = pw_prev + mul(Rw_prev, r);
+    Rw_prev = mulABt(Rw_prev, E);
+    v_prev = v;
+    prev = i;
     st6(L + LS_V, v);
-    st_m3(L + LS_A + A_POSE, mulABt(Rwp, E));
-    st3(L + LS_A + A_POSE + 9, ld3(Lp + LS_A + A_POSE + 9) + mul(Rwp, r));
+    st_m3(L + LS_A + A_POSE, Rw_prev);
+    st3(L + LS_A + A_POSE + 9, pw_prev);
     // published only where another role reads it: by foreign children (pose, velocity), or by the foreign parent,
     // which must not overwrite its pose before this link has used it
     if (RI(R, R_FLAGS) & (RF_PUBLISH | RF_PARENT_FOREIGN)) sync.signal(fl + i, base + ST_PASS1);
@@ -290,6 +308,9 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
   sync.mark(2);
   // ---- pass 2, leaves -> root: articulated inertias and bias forces; the base role ends with the base itself
   //      (k = -1, record 0): inverse articulated inertia, base acceleration, predicted base velocity
+  prev = -1;
+  ABI cia_prev;
+  SV cpa_prev = sv_zero();
   for (int k = len - 1; k >= (base_role ? -1 : 0); --k) {
     const float* R = k < 0 ? REC(0) : REC(rec0 + k);
     const int i = RI(R, R_LINK);
@@ -299,10 +320,15 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     SV pA = ld6(A + A_PA);
     for (int j = 0; j < RI(R, R_NCHILD); ++j) {
       const int cf = RI(R, R_CHILD0 + j), c = cf & ~REC_FOREIGN;
-      if (cf & REC_FOREIGN) sync.wait(fl + c, base + ST_PASS2);
-      const real* Ac = BLK(c) + LS_A;
-      IA = IA + ld_abi(Ac + A_CIA);
-      pA = pA + ld6(Ac + A_CPA);
+      if (c == prev) {  // the child handled just before: its contribution is still in registers
+        IA = IA + cia_prev;
+        pA = pA + cpa_prev;
+      } else {
+        if (cf & REC_FOREIGN) sync.wait(fl + c, base + ST_PASS2);
+        const real* Ac = BLK(c) + LS_A;
+        IA = IA + ld_abi(Ac + A_CIA);
+        pA = pA + ld6(Ac + A_CPA);
+      }
     }
     if (k >= 0) {
       V3 ax = ld3_f(R + R_AXIS), r = ld3_f(R + R_R);
@@ -322,8 +348,11 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
       SV c{cross(v.w, aq), cross(v.v, aq)};
       ABI Ia = rank1_sub(IA, U, Dinv);
       SV pa = pA + mul(Ia, c) + (Dinv * u) * U;
-      st_abi(A + A_CIA, abi_to_parent(E, r, Ia));
-      st6(A + A_CPA, xform_force_T(E, r, pa));
+      cia_prev = abi_to_parent(E, r, Ia);
+      cpa_prev = xform_force_T(E, r, pa);
+      prev = i;
+      st_abi(A + A_CIA, cia_prev);
+      st6(A + A_CPA, cpa_prev);
       st6(L + LS_U, U);
       L[LS_SC + 1] = u;
       L[LS_SC + 2] = Dinv;
@@ -444,6 +473,8 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
   }
   sync.mark(5);
   // ---- pass 3, root -> leaves: joint accelerations, predicted joint velocities
+  prev = -1;
+  SV a_prev = sv_zero();
   for (int k = 0; k < len; ++k) {
     const float* R = REC(rec0 + k);
     const int i = RI(R, R_LINK), par = RI(R, R_PARENT), flg = RI(R, R_FLAGS);
@@ -453,15 +484,17 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
       sync.wait(fl + par, base + ST_PASS3);
     }
     real* L = BLK(i);
-    const real* Lp = BLK(par);
+    if (par != prev) a_prev = ld6(BLK(par) + LS_A + A_ACC);
     V3 ax = ld3_f(R + R_AXIS), r = ld3_f(R + R_R);
     M3 E = ld_m3(L + LS_E);
     SV v = ld6(L + LS_V);
     real qd = L[LS_SC];
     V3 aq = qd * ax;
-    SV a = xform_motion(E, r, ld6(Lp + LS_A + A_ACC)) + SV{cross(v.w, aq), cross(v.v, aq)};
+    SV a = xform_motion(E, r, a_prev) + SV{cross(v.w, aq), cross(v.v, aq)};
     real qdd = L[LS_SC + 2] * (L[LS_SC + 1] - dot(ld6(L + LS_U), a));
     a.w = a.w + qdd * ax;
+    a_prev = a;
+    prev = i;
     st6(L + LS_A + A_ACC, a);
     L[LS_SC] = qd + dt * qdd;
     if (flg & RF_PUBLISH) sync.signal(fl + i, base + ST_PASS3);
@@ -605,6 +638,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
   }
   sync.mark(10);
   // ---- down the tree: joint velocity changes, speed cap, integration, limit projection
+  prev = -1;
   if (io_async) sync.wait(flags + F_IO_DONE, epoch + 1);
   for (int k = 0; k < len; ++k) {
     const float* R = REC(rec0 + k);
@@ -615,11 +649,13 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
       sync.wait(fl + par, base + ST_DOWN);
     }
     real* L = BLK(i);
-    const real* Lp = BLK(par);
+    if (par != prev) a_prev = ld6(BLK(par) + LS_V);  // (re-used register set: the parent's velocity change)
     V3 ax = ld3_f(R + R_AXIS), r = ld3_f(R + R_R);
-    SV dv = xform_motion(ld_m3(L + LS_E), r, ld6(Lp + LS_V));
+    SV dv = xform_motion(ld_m3(L + LS_E), r, a_prev);
     real dqd = -L[LS_SC + 2] * (dot(ld6(L + LS_U), dv) + L[LS_SC + 3]);
     dv.w = dv.w + dqd * ax;
+    a_prev = dv;
+    prev = i;
     st6(L + LS_V, dv);
     if (flg & RF_PUBLISH) sync.signal(fl + i, base + ST_DOWN);
     // joint velocity cap (dof_prop['velocity'], T:372), explicit Euler on the angle, limit projection
