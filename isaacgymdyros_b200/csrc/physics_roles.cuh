@@ -24,7 +24,7 @@ namespace dyros {
 // per-link scratch block (floats) of one env
 constexpr int LS_E = 0;    // 9  parent->link rotation (base: base->world rotation)
 constexpr int LS_V = 9;    // 6  link velocity, later the impulse response dv
-constexpr int LS_A = 15;   // 27 pass1: pA(6) world pose(12) | pass2: contribution to parent IA(21) pA(6) |
+constexpr int LS_A = 15;   // 27 pass1: world pose(12) at +6 | pass2: contribution to parent IA(21) pA(6) |
                            //    pass3: a'(6); leg-chain links then also hold contact rows (14) and g = S^T G (6);
                            //    the first chain link keeps g in X_G0 (the base may still be reading its A block)
 constexpr int LS_U = 42;   // 6  U = IA S (base: predicted velocity v0*)
@@ -124,9 +124,9 @@ HD ABI link_inertia(const real* X, const float* hot, const DevModel& m, const fl
   return abi_rigid(par[0], v3(par[1], par[2], par[3]), S3{par[4], par[5], par[6], par[7], par[8], par[9]});
 }
 
-// Bias force and external wrench of the link of record R (pass 1). Writes A_PA.
-HD void link_forces(const EnvIO& io, real* L, const real* X, const float* hot, const DevModel& m, const SimParams& p,
-                    const float* R, const M3& Rw, V3 pw, SV v) {
+// External wrench on the link of record R (link coordinates): applied body wrenches and penalty ground contact.
+HD SV link_ext_wrench(const EnvIO& io, const real* X, const float* hot, const DevModel& m, const SimParams& p,
+                      const float* R, const M3& Rw, V3 pw, SV v) {
   SV fext = sv_zero();
   V3 nrm = v3(Rw.a[6], Rw.a[7], Rw.a[8]);  // world z in link coordinates
   if (io.rb_force || (io.push && RI(R, R_LINK) == 0)) {  // applied world wrenches at the bodies' COMs (tensors.rst.txt:322-335)
@@ -171,8 +171,7 @@ HD void link_forces(const EnvIO& io, real* L, const real* X, const float* hot, c
       penalty_point(p, Rw, v, rim, -z, io.contact + 3 * m.cyl_body[k], io.live, fext);
     }
   }
-  SV pA = crf(v, mul(link_inertia(X, hot, m, R), v)) - fext;
-  st6(L + LS_A + A_PA, pA);
+  return fext;
 }
 
 // Inputs of one env -> its scratch block: thread `tid` of `nthreads` cooperating threads (P0).
@@ -286,25 +285,14 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     if (RI(R, R_FLAGS) & (RF_PUBLISH | RF_PARENT_FOREIGN)) sync.signal(fl + i, base + ST_PASS1);
   }
   sync.mark(17);
-  // (c) bias forces and external wrenches: local to each link again (k = -1: the base itself, record 0)
-  if (io_async) sync.wait(flags + F_IO_PRE, epoch + 1);
-  for (int k = base_role ? -1 : 0; k < len; ++k) {
-    const float* R = k < 0 ? REC(0) : REC(rec0 + k);
-    real* L = BLK(RI(R, R_LINK));
-    M3 Rw = ld_m3(L + LS_A + A_POSE);
-    V3 pw = ld3(L + LS_A + A_POSE + 9);
-    const int f = RI(R, R_FOOT);
-    if (f >= 0) {
-      st_m3(X + X_FOOTPOSE + 12 * f, Rw);
-      st3(X + X_FOOTPOSE + 12 * f + 9, pw);
-    }
-    link_forces(io, L, X, hot, m, p, R, Rw, pw, ld6(L + LS_V));
-  }
   sync.mark(1);
   // Pass 2 overwrites A (pose) of a link with its contribution to the parent: every child of this role's links that
   // lives in another role must have read its parent's pose first.
   for (int k = 0; k < m.n_xchild[role]; ++k) sync.wait(fl + m.xchild[role][k], base + ST_PASS1);
-  if (io_async) sync.wait(flags + F_IO_TAU, epoch + 1);
+  if (io_async) {
+    sync.wait(flags + F_IO_PRE, epoch + 1);
+    sync.wait(flags + F_IO_TAU, epoch + 1);
+  }
   sync.mark(2);
   // ---- pass 2, leaves -> root: articulated inertias and bias forces; the base role ends with the base itself
   //      (k = -1, record 0): inverse articulated inertia, base acceleration, predicted base velocity
@@ -316,8 +304,21 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     const int i = RI(R, R_LINK);
     real* L = BLK(i);
     real* A = L + LS_A;
+    // rigid inertia, bias force and external wrench of the link itself (its world pose is still in A: read it before
+    // the block is overwritten with the contribution to the parent)
     ABI IA = link_inertia(X, hot, m, R);
-    SV pA = ld6(A + A_PA);
+    const SV v = ld6(L + LS_V);
+    SV pA;
+    {
+      M3 Rw = ld_m3(A + A_POSE);
+      V3 pw = ld3(A + A_POSE + 9);
+      const int f = RI(R, R_FOOT);
+      if (f >= 0) {
+        st_m3(X + X_FOOTPOSE + 12 * f, Rw);
+        st3(X + X_FOOTPOSE + 12 * f + 9, pw);
+      }
+      pA = crf(v, mul(IA, v)) - link_ext_wrench(io, X, hot, m, p, R, Rw, pw, v);
+    }
     for (int j = 0; j < RI(R, R_NCHILD); ++j) {
       const int cf = RI(R, R_CHILD0 + j), c = cf & ~REC_FOREIGN;
       if (c == prev) {  // the child handled just before: its contribution is still in registers
@@ -333,7 +334,6 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     if (k >= 0) {
       V3 ax = ld3_f(R + R_AXIS), r = ld3_f(R + R_R);
       M3 E = ld_m3(L + LS_E);
-      SV v = ld6(L + LS_V);
       real qd = L[LS_SC], tq = L[LS_SC + 1], damp = L[LS_SC + 2], arm = L[LS_SC + 3];
       if (p.clamp_effort) {  // optional clamp of the actuation to the MJCF ctrlrange
         real lim = R[R_EFF];
@@ -364,7 +364,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     ABI Om0 = abi_inverse_spd(IA);
     SV a0 = (real)-1 * mul(Om0, pA);  // acceleration relative to the gravity field
     M3 R0 = ld_m3(L + LS_E);
-    SV v0 = ld6(L + LS_V);
+    SV v0 = v;
     st6(A + A_ACC, a0);
     st_abi(A + A_OM0, Om0);
     V3 gl = mulT(R0, v3(p.g[0], p.g[1], p.g[2]));
