@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kStepThreads) k_step_physics(DevModel m, SimPa
 }
 
 static size_t phys_smem_bytes(const Sim* sim, int epb) {
-  return (size_t)sim->m.hot_bytes + (((F_COUNT + 3) & ~3) + (size_t)epb * env_scratch_floats(sim->m.nl)) * sizeof(float);
+  return (size_t)sim->m.hot_bytes + (((F_COUNT + 3) & ~3) + (size_t)epb * env_scratch_floats(sim->m.nl, sim->m.nb)) * sizeof(float);
 }
 
 int physics_configure(Sim* sim) {
@@ -350,7 +350,7 @@ int launch_simulate(Sim* sim, int apply_wrench, const float* push, cudaStream_t 
   const int epb = sim->envs_per_block;
   const int grid = (sim->p.N + epb - 1) / epb;
   k_simulate<<<grid, kPhysThreads, sim->phys_smem, s>>>(sim->m, sim->p, sim->b, push, apply_wrench, epb,
-                                                   env_scratch_floats(sim->m.nl));
+                                                   env_scratch_floats(sim->m.nl, sim->m.nb));
   DY_LAUNCH_CHECK();
   return 0;
 }
@@ -365,7 +365,7 @@ int launch_task_physics(Task* t, cudaStream_t s, long long* trace, bool pdl, con
   k.s = sim->b;
   k.j = t->inj;
   DY_CUDA(launch_kernel(k_step_physics, dim3(grid), dim3(kStepThreads), sim->phys_smem, s, pdl, sim->m, sim->p, k, epb,
-                        env_scratch_floats(sim->m.nl), trace, actions));
+                        env_scratch_floats(sim->m.nl, sim->m.nb), trace, actions));
   return 0;
 }
 

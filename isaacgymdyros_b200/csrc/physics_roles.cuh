@@ -40,12 +40,13 @@ constexpr int X_PD = X_Z + 2 * MAX_FEET * 6;         // MAX_FEET * 6  impulse ar
 constexpr int X_G0 = X_PD + MAX_FEET * 6;            // MAX_FEET * 6  g = S^T G of the first leg-chain link (see A_G)
 constexpr int X_ROOT = X_G0 + MAX_FEET * 6;          // 13 (+3 pad): root state in, root state out
 constexpr int X_PUSH = X_ROOT + 13;                  // 3  world force at the base body's COM for this sub-step
-constexpr int X_OML = X_ROOT + 16;                   // 21 (+3 pad): inverse inertia at the feet's common ancestor (LCA)
-constexpr int X_MASS = X_OML + 24;                   // DYROS_MAX_BODIES per-body mass scale
-constexpr int X_SIZE = X_MASS + DYROS_MAX_BODIES;
+constexpr int X_OML = X_ROOT + 16;                   // 21: inverse inertia at the feet's common ancestor (LCA)
+constexpr int PT_WORDS = 5;                          // active sole point: candidate index (int), bias, impulse lam(3)
+constexpr int X_PTS = X_OML + 21;                    // MAX_FEET * MAX_ACTIVE_PTS * PT_WORDS
+constexpr int X_MASS = X_PTS + MAX_FEET * MAX_ACTIVE_PTS * PT_WORDS;  // nb per-body mass scales (last: sized by the model)
 
-HD int env_scratch_floats(int nl) {
-  int n = nl * LS + X_SIZE;
+HD int env_scratch_floats(int nl, int nb) {
+  int n = nl * LS + X_MASS + nb;
   return n | 1;  // odd stride: the 32 envs of a warp touch 32 different banks for any field
 }
 
@@ -430,43 +431,32 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     }
   }
   // active sole points of this foot (needs the foot pose of pass 1 only): candidates below the contact offset, at
-  // most MAX_ACTIVE_PTS, with their offsets from the foot origin and the velocity bias of the non-penetration row
-  real* rowblk[MAX_ACTIVE_PTS * 3 / ROWS_PER_LINK];
+  // most MAX_ACTIVE_PTS, with their offsets from the foot origin and the velocity bias of the non-penetration row;
+  // kept in the env's scratch (X_PTS) so that the per-point loops below stay rolled (small instruction footprint)
   M3 Rwf;
-  V3 nrm = v3(0, 0, 1);
-  V3 xs[MAX_ACTIVE_PTS];
-  real bias[MAX_ACTIVE_PTS], lam[MAX_ACTIVE_PTS][3];
-  int pbody[MAX_ACTIVE_PTS];
+  // contact location of candidate k of foot g relative to the foot origin (foot coordinates): the sphere's lowest point
+  auto sole_point = [&](int g, int k) {
+    const real rad = m.foot_pt_radius[g][k];
+    return v3(m.foot_pt_pos[g][k][0] - rad * Rwf.a[6], m.foot_pt_pos[g][k][1] - rad * Rwf.a[7], m.foot_pt_pos[g][k][2] - rad * Rwf.a[8]);
+  };
   int nact = 0;
   const real inv_dt = 1 / dt;
+  real* const pts = X + X_PTS + (foot >= 0 ? foot : 0) * MAX_ACTIVE_PTS * PT_WORDS;
   if (foot >= 0) {
     const int g = foot;
-#pragma unroll
-    for (int k = 0; k < MAX_ACTIVE_PTS * 3 / ROWS_PER_LINK; ++k) rowblk[k] = BLK(m.chain[g][k]) + LS_A + A_ROWS;
     Rwf = ld_m3(X + X_FOOTPOSE + 12 * g);
-    real pz = X[X_FOOTPOSE + 12 * g + 11];
-    nrm = v3(Rwf.a[6], Rwf.a[7], Rwf.a[8]);
-#pragma unroll
-    for (int a = 0; a < MAX_ACTIVE_PTS; ++a) {
-      xs[a] = v3(0, 0, 0);
-      bias[a] = 0;
-      pbody[a] = 0;
-      lam[a][0] = lam[a][1] = lam[a][2] = 0;
-    }
+    const real pz = X[X_FOOTPOSE + 12 * g + 11];
+    const V3 nrm = v3(Rwf.a[6], Rwf.a[7], Rwf.a[8]);
+#pragma unroll 1
     for (int k = 0; k < m.foot_npts[g]; ++k) {
       V3 x = v3(m.foot_pt_pos[g][k][0], m.foot_pt_pos[g][k][1], m.foot_pt_pos[g][k][2]);
       real rad = m.foot_pt_radius[g][k];
       real phi = pz + dot(nrm, x) - rad;
       if (phi < p.contact_offset && nact < MAX_ACTIVE_PTS) {
-        real b = phi >= 0 ? -phi * inv_dt : fmin_r(-p.erp * phi * inv_dt, p.max_depen_vel);
-        V3 xsk = x - rad * nrm;
-#pragma unroll
-        for (int a = 0; a < MAX_ACTIVE_PTS; ++a)
-          if (a == nact) {
-            xs[a] = xsk;
-            bias[a] = b;
-            pbody[a] = m.foot_pt_body[g][k];
-          }
+        real* pt = pts + nact * PT_WORDS;
+        reinterpret_cast<int*>(pt)[0] = k;
+        pt[1] = phi >= 0 ? -phi * inv_dt : fmin_r(-p.erp * phi * inv_dt, p.max_depen_vel);
+        pt[2] = pt[3] = pt[4] = 0;
         ++nact;
       }
     }
@@ -541,49 +531,56 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
         for (int b = 0; b < 3; ++b) Om.H.a[3 * a + b] += w[a][3 + b];
     }
     // rows of the active points: response cv = Om J and 1 / (J . cv) per direction (n, t1, t2), parked in the blocks
-    // of the first chain links (2 per link)
+    // of the first chain links (ROWS_PER_LINK per link)
+#pragma unroll 1
+    for (int a = 0; a < nact; ++a) {
+      const V3 xa = sole_point(g, reinterpret_cast<const int*>(pts + a * PT_WORDS)[0]);
 #pragma unroll
-    for (int a = 0; a < MAX_ACTIVE_PTS; ++a)
-      if (a < nact) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          V3 dir = d == 0 ? nrm : (d == 1 ? v3(Rwf.a[0], Rwf.a[1], Rwf.a[2]) : v3(Rwf.a[3], Rwf.a[4], Rwf.a[5]));
-          SV J{cross(xs[a], dir), dir};
-          SV cv = mul(Om, J);
-          real* rw = rowblk[(a * 3 + d) / ROWS_PER_LINK] + ((a * 3 + d) % ROWS_PER_LINK) * 7;
-          st6(rw, cv);
-          rw[6] = 1 / dot(J, cv);
-        }
+      for (int d = 0; d < 3; ++d) {
+        V3 dir = d == 0 ? v3(Rwf.a[6], Rwf.a[7], Rwf.a[8]) : (d == 1 ? v3(Rwf.a[0], Rwf.a[1], Rwf.a[2]) : v3(Rwf.a[3], Rwf.a[4], Rwf.a[5]));
+        SV J{cross(xa, dir), dir};
+        SV cv = mul(Om, J);
+        const int row = a * 3 + d;
+        real* rw = BLK(m.chain[g][row / ROWS_PER_LINK]) + LS_A + A_ROWS + (row % ROWS_PER_LINK) * 7;
+        st6(rw, cv);
+        rw[6] = 1 / dot(J, cv);
       }
+    }
     sync.mark(7);
     // fixed number of sweeps; Gauss-Seidel inside a foot, Jacobi between the feet (coupled through the base)
     for (int s = 0; s < p.sweeps; ++s) {
       SV dP = sv_zero();
+#pragma unroll 1
+      for (int a = 0; a < nact; ++a) {
+        real* pt = pts + a * PT_WORDS;
+        const V3 xa = sole_point(g, reinterpret_cast<const int*>(pt)[0]);
+        const real bias = pt[1];
+        real lam[3] = {pt[2], pt[3], pt[4]};
 #pragma unroll
-      for (int a = 0; a < MAX_ACTIVE_PTS; ++a) {
-        if (a < nact) {
-#pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            V3 dir = d == 0 ? v3(Rwf.a[6], Rwf.a[7], Rwf.a[8])
-                            : (d == 1 ? v3(Rwf.a[0], Rwf.a[1], Rwf.a[2]) : v3(Rwf.a[3], Rwf.a[4], Rwf.a[5]));
-            SV J{cross(xs[a], dir), dir};
-            const real* rw = rowblk[(a * 3 + d) / ROWS_PER_LINK] + ((a * 3 + d) % ROWS_PER_LINK) * 7;
-            real vrel = dot(J, V);
-            real nw;
-            if (d == 0) {
-              nw = lam[a][0] + (bias[a] - vrel) * rw[6];
-              nw = nw > 0 ? nw : 0;
-            } else {
-              real lim = p.mu * lam[a][0];
-              nw = lam[a][d] - vrel * rw[6];
-              nw = nw > lim ? lim : (nw < -lim ? -lim : nw);
-            }
-            real delta = nw - lam[a][d];
-            lam[a][d] = nw;
-            V = V + delta * ld6(rw);
-            dP = dP + delta * J;
+        for (int d = 0; d < 3; ++d) {
+          V3 dir = d == 0 ? v3(Rwf.a[6], Rwf.a[7], Rwf.a[8])
+                          : (d == 1 ? v3(Rwf.a[0], Rwf.a[1], Rwf.a[2]) : v3(Rwf.a[3], Rwf.a[4], Rwf.a[5]));
+          SV J{cross(xa, dir), dir};
+          const int row = a * 3 + d;
+          const real* rw = BLK(m.chain[g][row / ROWS_PER_LINK]) + LS_A + A_ROWS + (row % ROWS_PER_LINK) * 7;
+          real vrel = dot(J, V);
+          real nw;
+          if (d == 0) {
+            nw = lam[0] + (bias - vrel) * rw[6];
+            nw = nw > 0 ? nw : 0;
+          } else {
+            real lim = p.mu * lam[0];
+            nw = lam[d] - vrel * rw[6];
+            nw = nw > lim ? lim : (nw < -lim ? -lim : nw);
           }
+          real delta = nw - lam[d];
+          lam[d] = nw;
+          V = V + delta * ld6(rw);
+          dP = dP + delta * J;
         }
+        pt[2] = lam[0];
+        pt[3] = lam[1];
+        pt[4] = lam[2];
       }
       P = P + dP;
       if (m.num_feet == 2) {
@@ -607,14 +604,14 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     st6(X + X_PD + 6 * g, (real)-1 * (P.w.x * G[0] + P.w.y * G[1] + P.w.z * G[2] + P.v.x * G[3] + P.v.y * G[4] + P.v.z * G[5]));
     sync.signal(flags + F_PD + g, epoch + 1);
     if (io.live) {
-#pragma unroll
-      for (int a = 0; a < MAX_ACTIVE_PTS; ++a)
-        if (a < nact) {  // world force over this sub-step: (t1, t2, n) = world (x, y, z)
-          float* cf = io.contact + 3 * pbody[a];
-          cf[0] += (float)(lam[a][1] * inv_dt);
-          cf[1] += (float)(lam[a][2] * inv_dt);
-          cf[2] += (float)(lam[a][0] * inv_dt);
-        }
+#pragma unroll 1
+      for (int a = 0; a < nact; ++a) {  // world force over this sub-step: (t1, t2, n) = world (x, y, z)
+        const real* pt = pts + a * PT_WORDS;
+        float* cf = io.contact + 3 * m.foot_pt_body[g][reinterpret_cast<const int*>(pt)[0]];
+        cf[0] += (float)(pt[3] * inv_dt);
+        cf[1] += (float)(pt[4] * inv_dt);
+        cf[2] += (float)(pt[2] * inv_dt);
+      }
     }
   }
   sync.mark(9);

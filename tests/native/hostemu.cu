@@ -39,7 +39,7 @@ extern "C" int dyros_hostemu_simulate(const DyrosSimDesc* d, const DyrosModelDes
   SimParams p;
   fill_sim_params(d, p);
   const float* hot = reinterpret_cast<const float*>(bl.host.data());
-  std::vector<real> scratch(env_scratch_floats(m.nl));
+  std::vector<real> scratch(env_scratch_floats(m.nl, m.nb));
   for (int env = 0; env < p.N; ++env) {
     EnvIO io;
     io.root = root + (size_t)env * 13;
@@ -83,6 +83,15 @@ extern "C" int dyros_hostemu_layout(const DyrosModelDesc* md, int* hot_bytes, in
   ModelOffsets off;
   if (!build_model_tables(md, bl, m, off).empty()) return 1;
   *hot_bytes = m.hot_bytes;
-  *env_scratch_bytes = env_scratch_floats(m.nl) * (int)sizeof(real);
+  *env_scratch_bytes = env_scratch_floats(m.nl, m.nb) * (int)sizeof(real);
   return 0;
+}
+
+// Dynamic shared memory of a physics CTA holding `epb` envs (mirrors phys_smem_bytes in physics_kernels.cu).
+extern "C" long dyros_hostemu_cta_smem_bytes(const DyrosModelDesc* md, int epb) {
+  Blob bl;
+  DevModel m;
+  ModelOffsets off;
+  if (!build_model_tables(md, bl, m, off).empty()) return -1;
+  return (long)m.hot_bytes + (((F_COUNT + 3) & ~3) + (long)epb * env_scratch_floats(m.nl, m.nb)) * (long)sizeof(float);
 }

@@ -77,3 +77,15 @@ def test_lane_program_short_rollout_stays_with_oracle():
     assert np.abs(a["q"] - b["q"]).max() < 2e-5 and np.abs(a["qd"] - b["qd"]).max() < 5e-3
     assert np.abs(a["root"][:, :7] - b["root"][:, :7]).max() < 2e-5
     assert np.abs(c - c2).max() < 2e-3 * np.abs(c).max()
+
+
+def test_tocabi_cta_holds_28_envs():
+    """4096 envs on 148 SMs run as ONE wave only if a CTA (one per SM, 227 KiB of shared memory) holds 28 envs."""
+    import ctypes as C
+    from tests.physics_util import hostemu
+    from isaacgymdyros_b200.core import make_model_desc
+    md, keep = make_model_desc(load_assets()[0], CoreConfig())
+    fn = hostemu().dyros_hostemu_cta_smem_bytes
+    fn.restype = C.c_long
+    need = fn(C.byref(md), 28)
+    assert 0 < need <= 227 * 1024, need

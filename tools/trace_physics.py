@@ -12,6 +12,10 @@ g = torch.Generator(device="cuda:0"); g.manual_seed(1)
 for _ in range(30):
     env.step(torch.rand(4096, 13, device="cuda:0", generator=g) * 2 - 1)
 env.core.prologue(torch.rand(4096, 13, device="cuda:0", generator=g) * 2 - 1)
+if "--cold" in sys.argv:  # evict everything from L2 first (what bench.py does between timed steps)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda:0")
+    flush.zero_()
+    torch.cuda.synchronize()
 tr = env.core.task_physics_trace().cpu()
 torch.cuda.synchronize()
 for s in range(tr.shape[0]):
