@@ -39,9 +39,11 @@ __device__ __forceinline__ float quat2euler_comp(const float* q, int which) {
   float m22 = w * w - x * x - y * y + z * z;
   float cy = sqrtf(m00 * m00 + m10 * m10);
   bool cond = cy > (float)(2.220446049250313e-16 * 4);
-  if (which == 2) return cond ? atan2f(m10, m00) : atan2f(-m01, m11);
-  if (which == 1) return atan2f(-m20, cy);
-  return cond ? atan2f(m21, m22) : 0.0f;
+  // one atan2f for whichever component the lane wants (lanes with different `which` do not diverge):
+  // 2: cond ? atan2(m10, m00) : atan2(-m01, m11); 1: atan2(-m20, cy); 0: cond ? atan2(m21, m22) : 0 (= atan2(0, 1))
+  float ay = which == 2 ? (cond ? m10 : -m01) : (which == 1 ? -m20 : (cond ? m21 : 0.0f));
+  float ax = which == 2 ? (cond ? m00 : m11) : (which == 1 ? cy : (cond ? m22 : 1.0f));
+  return atan2f(ay, ax);
 }
 
 __device__ __forceinline__ bool collision_true(const TK& k, int e, int lane) {
@@ -75,17 +77,28 @@ __device__ void stage_epilogue(const TK& k, int e, int lane) {
 }
 
 // T:581-596 ; returns the reset flag (warp-uniform)
-__device__ int stage_check_termination(const TK& k, int e, int lane) {
+// `shared` (fused kernel): hands the collision flag and the orientation error on to the reward stage, which needs
+// the same two quantities of the same (pre-reset) state.
+struct TermShared {
+  bool col;
+  float qe;
+};
+__device__ int stage_check_termination(const TK& k, int e, int lane, TermShared* shared = nullptr) {
   float qe = quat_err_identity(k.s.root_states + (size_t)e * 13 + 3);
   int reset = (fabsf(qe) > 0.5f) ? 1 : 0;
   if ((float)k.b.progress_buf[e] >= k.p.max_len_m1) reset = 1;
-  if (collision_true(k, e, lane)) reset = 1;
+  const bool col = collision_true(k, e, lane);
+  if (shared) {
+    shared->col = col;
+    shared->qe = qe;
+  }
+  if (col) reset = 1;
   if (lane == 0) k.b.reset_buf[e] = reset;
   return reset;
 }
 
 // T:387-428 + T:802-947
-__device__ void stage_compute_reward(const TK& k, int e, int lane) {
+__device__ void stage_compute_reward(const TK& k, int e, int lane, const TermShared* shared = nullptr) {
   const float* root = k.s.root_states + (size_t)e * 13;
   const float* ds = k.s.dof_state + (size_t)e * ND * 2;
   float s_qpos = 0.f, s_qvel = 0.f, s_qacc = 0.f, s_tq = 0.f, s_tqd = 0.f;
@@ -109,9 +122,9 @@ __device__ void stage_compute_reward(const TK& k, int e, int lane) {
   s_qacc = warp_sum(s_qacc);
   s_tq = warp_sum(s_tq);
   s_tqd = warp_sum(s_tqd);
-  bool col = collision_true(k, e, lane);
+  bool col = shared ? shared->col : collision_true(k, e, lane);
   if (lane != 0) return;
-  float qe = quat_err_identity(root + 3);
+  float qe = shared ? shared->qe : quat_err_identity(root + 3);
   float r[14];
   r[0] = 0.3f * expf(-13.2f * fabsf(qe));                                          // T:835
   float n;
@@ -400,9 +413,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_post_fused(TK k) {
   ENV_LANE();
   stage_epilogue(k, e, lane);
   __syncwarp();
-  int reset = stage_check_termination(k, e, lane);
+  TermShared ts;
+  int reset = stage_check_termination(k, e, lane, &ts);
   __syncwarp();
-  stage_compute_reward(k, e, lane);
+  stage_compute_reward(k, e, lane, &ts);
   __syncwarp();
   if (reset) {
     stage_reset_env(k, e, lane);
