@@ -50,7 +50,10 @@ HD V3 ld3_f(const F* p) { return V3{(real)p[0], (real)p[1], (real)p[2]}; }  // f
 HD real fmin_r(real a, real b) { return a < b ? a : b; }
 HD void sincos_r(real x, real* s, real* c) {
 #if defined(__CUDA_ARCH__)
-  sincosf((float)x, s, c);
+  float sf, cf;
+  sincosf((float)x, &sf, &cf);
+  *s = sf;
+  *c = cf;
 #else
   *s = sin(x);
   *c = cos(x);
@@ -213,6 +216,38 @@ HD ABI abi_to_parent(const M3& E, V3 r, const ABI& a) {
   p.I.xz = I1.xz + (real)0.5 * ((A.a[2] - B.a[2]) + (A.a[6] - B.a[6]));
   p.I.yz = I1.yz + (real)0.5 * ((A.a[5] - B.a[5]) + (A.a[7] - B.a[7]));
   return p;
+}
+// ---- the same transforms for a pure translation (all quantities in world axes, reference point moved by r)
+HD SV shift_motion(V3 r, SV m) { return SV{m.w, m.v - cross(r, m.w)}; }   // parent origin -> child origin (r = child - parent)
+HD SV shift_force_T(V3 r, SV f) { return SV{f.w + cross(r, f.v), f.v}; }  // child origin -> parent origin
+HD ABI abi_shift_to_parent(V3 r, const ABI& a) {
+  M3 RM = skew_mul(r, full(a.M));               // r~ M
+  M3 Hp = a.H + RM;                             // H + r~ M
+  M3 A = skew_mul(r, transpose(a.H));           // r~ H^T
+  M3 B = mul_skew(Hp, r);                       // Hp r~
+  ABI p;
+  p.M = a.M;
+  p.H = Hp;
+  p.I.xx = a.I.xx + A.a[0] - B.a[0];
+  p.I.yy = a.I.yy + A.a[4] - B.a[4];
+  p.I.zz = a.I.zz + A.a[8] - B.a[8];
+  p.I.xy = a.I.xy + (real)0.5 * ((A.a[1] - B.a[1]) + (A.a[3] - B.a[3]));
+  p.I.xz = a.I.xz + (real)0.5 * ((A.a[2] - B.a[2]) + (A.a[6] - B.a[6]));
+  p.I.yz = a.I.yz + (real)0.5 * ((A.a[5] - B.a[5]) + (A.a[7] - B.a[7]));
+  return p;
+}
+HD ABI inv_shift_to_child(V3 r, const ABI& o) {
+  M3 A = full(o.I);
+  M3 Bp = o.H + mul_skew(A, r);
+  M3 RB = skew_mul(r, o.H);
+  M3 BtR = mul_skew(transpose(Bp), r);
+  M3 Cp = full(o.M) - RB + BtR;
+  ABI c;
+  c.I = o.I;
+  c.H = Bp;
+  c.M = S3{Cp.a[0], Cp.a[4], Cp.a[8], (real)0.5 * (Cp.a[1] + Cp.a[3]), (real)0.5 * (Cp.a[2] + Cp.a[6]),
+           (real)0.5 * (Cp.a[5] + Cp.a[7])};
+  return c;
 }
 // Inverse inertia (maps force to motion) of the parent expressed at the child: X Om X^T (motion-type congruence)
 HD ABI inv_to_child(const M3& E, V3 r, const ABI& o) {

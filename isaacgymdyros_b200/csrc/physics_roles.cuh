@@ -8,6 +8,12 @@
 // leg chains). The model and every formula are stated independently (dense, fp64) in oracle/physics_oracle.py;
 // see DESIGN.md section 4.
 //
+// Coordinates: every spatial quantity of a link is expressed in WORLD axes with the link's origin as reference point,
+// and accelerations are classical (d/dt of the origin's velocity), as in most production articulation solvers. The
+// transforms between a link and its parent are then pure translations (no 3x3 rotations inside the recursions); the
+// price is one rotation of the link's rigid inertia per sub-step and the classical velocity-product terms
+// c = [w_p x s qd; w_p x (w_p x r)], p = [w x I w; w x (w x h)].
+//
 // Parallel decomposition (GPU): the link tree is cut into DYROS_LANES "roles" (model/tables.py::role_programs: torso
 // + left arm, head + right arm (+ base), left leg, right leg for TOCABI). A CTA holds one warp per role; lane = env,
 // so a warp runs the same link operation on up to 32 envs (no divergence, warp-uniform table reads). Roles exchange
@@ -22,8 +28,9 @@
 namespace dyros {
 
 // per-link scratch block (floats) of one env
-constexpr int LS_E = 0;    // 9  parent->link rotation (base: base->world rotation)
-constexpr int LS_V = 9;    // 6  link velocity, later the impulse response dv
+constexpr int LS_E = 0;    // 9  pass 1a: parent->link rotation; from pass 1b on: joint axis s (3) and offset from the
+                           //    parent's origin r (3), both in world axes (LS_S, LS_R)
+constexpr int LS_V = 9;    // 6  link velocity [w; u], later the impulse response dv
 constexpr int LS_A = 15;   // 27 pass1: world pose(12) at +6 | pass2: contribution to parent IA(21) pA(6) |
                            //    pass3: a'(6); leg-chain links then also hold contact rows (14) and g = S^T G (6);
                            //    the first chain link keeps g in X_G0 (the base may still be reading its A block)
@@ -31,6 +38,7 @@ constexpr int LS_U = 42;   // 6  U = IA S (base: predicted velocity v0*)
 constexpr int LS_SC = 48;  // 4  [qd -> qd*, tau -> u, damping -> 1/D, armature -> S^T dp]
 constexpr int LS_Q = 52;   // 1  joint angle
 constexpr int LS = 53;
+constexpr int LS_S = LS_E, LS_R = LS_E + 3;
 constexpr int A_PA = 0, A_POSE = 6, A_CIA = 0, A_CPA = 21, A_ACC = 0, A_OM0 = 6, A_ROWS = 6, A_G = 21;
 constexpr int ROWS_PER_LINK = 2;  // contact rows (7 floats each) parked in one leg-chain link's block
 // per-env extra scratch
@@ -85,10 +93,11 @@ struct EnvIO {
   bool live;               // false: padding lane, no global writes
 };
 
-// ---- penalty ground contact of one location on a link (oracle: PhysicsOracle._external_wrench.add_point)
-HD void penalty_point(const SimParams& p, const M3& Rw, SV v, V3 xs, real depth, float* cf, bool live, SV& fext) {
+// ---- penalty ground contact of one location on a link (oracle: PhysicsOracle._external_wrench.add_point);
+//      xw = the location relative to the link origin, world axes; v = [w; u] of the link
+HD void penalty_point(const SimParams& p, SV v, V3 xw, real depth, float* cf, bool live, SV& fext) {
   if (!(depth > 0)) return;
-  V3 vel_w = mul(Rw, v.v + cross(v.w, xs));
+  V3 vel_w = v.v + cross(v.w, xw);
   real fn = p.pen_k * depth - p.pen_c * vel_w.z;
   fn = fn < 0 ? 0 : (fn > p.pen_fmax ? p.pen_fmax : fn);
   real speed = sqrt(vel_w.x * vel_w.x + vel_w.y * vel_w.y);
@@ -100,13 +109,13 @@ HD void penalty_point(const SimParams& p, const M3& Rw, SV v, V3 xs, real depth,
     cf[1] += (float)Fw.y;
     cf[2] += (float)Fw.z;
   }
-  V3 fl = mulT(Rw, Fw);
-  fext.w = fext.w + cross(xs, fl);
-  fext.v = fext.v + fl;
+  fext.w = fext.w + cross(xw, Fw);
+  fext.v = fext.v + Fw;
 }
 
-// Rigid inertia of the link of record R from the hot body table and the env's per-body mass scales (X_MASS).
-HD ABI link_inertia(const real* X, const float* hot, const DevModel& m, const float* R) {
+// Rigid inertia of the link of record R about its origin in WORLD axes, from the hot body table (link coordinates),
+// the env's per-body mass scales (X_MASS) and the link's world rotation Rw.
+HD ABI link_inertia(const real* X, const float* hot, const DevModel& m, const float* R, const M3& Rw) {
   real par[10];
   {  // first body (most links have exactly one): straight-line code; massless links (extra hinges of a body) have none
     const bool any = RI(R, R_NBODY) > 0;
@@ -122,10 +131,11 @@ HD ABI link_inertia(const real* X, const float* hot, const DevModel& m, const fl
 #pragma unroll
     for (int k = 0; k < 10; ++k) par[k] += sc * HF(body_inertia, b * 10 + k);
   }
-  return abi_rigid(par[0], v3(par[1], par[2], par[3]), S3{par[4], par[5], par[6], par[7], par[8], par[9]});
+  return abi_rigid(par[0], mul(Rw, v3(par[1], par[2], par[3])), rot_sym(Rw, S3{par[4], par[5], par[6], par[7], par[8], par[9]}));
 }
 
-// External wrench on the link of record R (link coordinates): applied body wrenches and penalty ground contact.
+// External wrench on the link of record R (world axes, about the link origin): applied body wrenches and penalty
+// ground contact.
 HD SV link_ext_wrench(const EnvIO& io, const real* X, const float* hot, const DevModel& m, const SimParams& p,
                       const float* R, const M3& Rw, V3 pw, SV v) {
   SV fext = sv_zero();
@@ -143,11 +153,10 @@ HD SV link_ext_wrench(const EnvIO& io, const real* X, const float* hot, const De
       real sc = X[X_MASS + b];
       real mb = sc * HF(body_inertia, b * 10);
       real inv = 1 / (mb > (real)1e-30 ? mb : (real)1e-30);
-      V3 com = v3(sc * HF(body_inertia, b * 10 + 1) * inv, sc * HF(body_inertia, b * 10 + 2) * inv,
-                  sc * HF(body_inertia, b * 10 + 3) * inv);
-      V3 fl = mulT(Rw, F);
-      fext.w = fext.w + cross(com, fl) + mulT(Rw, T);
-      fext.v = fext.v + fl;
+      V3 com = mul(Rw, v3(sc * HF(body_inertia, b * 10 + 1) * inv, sc * HF(body_inertia, b * 10 + 2) * inv,
+                          sc * HF(body_inertia, b * 10 + 3) * inv));
+      fext.w = fext.w + cross(com, F) + T;
+      fext.v = fext.v + F;
     }
   }
   if (pw.z < R[R_REACH]) {  // nothing of this link can reach z = 0 otherwise
@@ -156,7 +165,7 @@ HD SV link_ext_wrench(const EnvIO& io, const real* X, const float* hot, const De
       V3 x = ld3_f(m.pt_pos + 3 * k);
       real rad = m.pt_radius[k];
       real z = pw.z + dot(nrm, x);
-      penalty_point(p, Rw, v, x - rad * nrm, rad - z, io.contact + 3 * m.pt_body[k], io.live, fext);
+      penalty_point(p, v, mul(Rw, x) - v3(0, 0, rad), rad - z, io.contact + 3 * m.pt_body[k], io.live, fext);
     }
 #pragma unroll 1
     for (int k = RI(R, R_CYL0); k < RI(R, R_CYL1); ++k) {
@@ -169,7 +178,7 @@ HD SV link_ext_wrench(const EnvIO& io, const real* X, const float* hot, const De
       V3 rim = c + (s * hh) * a;
       if (dn > (real)1e-6) rim = rim + (rad / dn) * d;
       real z = pw.z + dot(nrm, rim);
-      penalty_point(p, Rw, v, rim, -z, io.contact + 3 * m.cyl_body[k], io.live, fext);
+      penalty_point(p, v, mul(Rw, rim), -z, io.contact + 3 * m.cyl_body[k], io.live, fext);
     }
   }
   return fext;
@@ -225,7 +234,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
 
   sync.mark(0);
   const int rec0 = m.prog_start[role];
-  // ---- pass 1, root -> leaves: transforms, velocities, world poses, bias forces
+  // ---- pass 1, root -> leaves: world poses, joint axes / offsets in world axes, velocities
   // Along a chain the parent is the link handled just before: its results are carried in registers (`prev`), the
   // scratch block is only read for the first link of a chain. The same holds for the other tree passes.
   int prev = -1;
@@ -237,8 +246,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     const real* rs = X + X_ROOT;
     V3 pw = ld3(rs);
     M3 R0 = quat_to_mat(rs[3], rs[4], rs[5], rs[6]);
-    SV v0{mulT(R0, ld3(rs + 10)), mulT(R0, ld3(rs + 7))};
-    st_m3(L + LS_E, R0);
+    SV v0{ld3(rs + 10), ld3(rs + 7)};  // root state: world angular velocity, world velocity of the base origin
     st6(L + LS_V, v0);
     st_m3(L + LS_A + A_POSE, R0);
     st3(L + LS_A + A_POSE + 9, pw);
@@ -257,8 +265,8 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     st_m3(L + LS_E, mul(axis_rot_T(ld3_f(R + R_AXIS), sq, cq), ld_m3_f(R + R_E)));
   }
   sync.mark(16);
-  // (b) propagation root -> leaves: velocity and world pose; this is the only chained part and what the children
-  //     in other roles wait for
+  // (b) propagation root -> leaves: world pose, axis and offset in world axes, velocity; this is the only chained
+  //     part and what the children in other roles wait for
   for (int k = 0; k < len; ++k) {
     const float* R = REC(rec0 + k);
     const int i = RI(R, R_LINK), par = RI(R, R_PARENT);
@@ -270,15 +278,16 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
       Rw_prev = ld_m3(Lp + LS_A + A_POSE);
       pw_prev = ld3(Lp + LS_A + A_POSE + 9);
     }
-    V3 ax = ld3_f(R + R_AXIS), r = ld3_f(R + R_R);
     M3 E = ld_m3(L + LS_E);
-    SV v = xform_motion(E, r, v_prev);
-    v.w = v.w + L[LS_SC] * ax;
-    pw_prev = pw_prev + mul(Rw_prev, r);
+    const V3 rw = mul(Rw_prev, ld3_f(R + R_R));  // offset of this link's origin from its parent's, world axes
     Rw_prev = mulABt(Rw_prev, E);
-    v_prev = v;
+    const V3 sw = mul(Rw_prev, ld3_f(R + R_AXIS));  // joint axis, world axes
+    pw_prev = pw_prev + rw;
+    v_prev = SV{v_prev.w + L[LS_SC] * sw, v_prev.v + cross(v_prev.w, rw)};
     prev = i;
-    st6(L + LS_V, v);
+    st3(L + LS_S, sw);
+    st3(L + LS_R, rw);
+    st6(L + LS_V, v_prev);
     st_m3(L + LS_A + A_POSE, Rw_prev);
     st3(L + LS_A + A_POSE + 9, pw_prev);
     // published only where another role reads it: by foreign children (pose, velocity), or by the foreign parent,
@@ -305,10 +314,10 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     const int i = RI(R, R_LINK);
     real* L = BLK(i);
     real* A = L + LS_A;
-    // rigid inertia, bias force and external wrench of the link itself (its world pose is still in A: read it before
-    // the block is overwritten with the contribution to the parent)
-    ABI IA = link_inertia(X, hot, m, R);
+    // rigid inertia (rotated to world axes), velocity-product force and external wrench of the link itself (its world
+    // pose is still in A: read it before the block is overwritten with the contribution to the parent)
     const SV v = ld6(L + LS_V);
+    ABI IA;
     SV pA;
     {
       M3 Rw = ld_m3(A + A_POSE);
@@ -318,7 +327,9 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
         st_m3(X + X_FOOTPOSE + 12 * f, Rw);
         st3(X + X_FOOTPOSE + 12 * f + 9, pw);
       }
-      pA = crf(v, mul(IA, v)) - link_ext_wrench(io, X, hot, m, p, R, Rw, pw, v);
+      IA = link_inertia(X, hot, m, R, Rw);
+      const V3 h = v3(IA.H.a[7], IA.H.a[2], IA.H.a[3]);  // m c, world axes
+      pA = SV{cross(v.w, mul(IA.I, v.w)), cross(v.w, cross(v.w, h))} - link_ext_wrench(io, X, hot, m, p, R, Rw, pw, v);
     }
     for (int j = 0; j < RI(R, R_NCHILD); ++j) {
       const int cf = RI(R, R_CHILD0 + j), c = cf & ~REC_FOREIGN;
@@ -333,24 +344,24 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
       }
     }
     if (k >= 0) {
-      V3 ax = ld3_f(R + R_AXIS), r = ld3_f(R + R_R);
-      M3 E = ld_m3(L + LS_E);
+      const V3 sw = ld3(L + LS_S), rw = ld3(L + LS_R);
       real qd = L[LS_SC], tq = L[LS_SC + 1], damp = L[LS_SC + 2], arm = L[LS_SC + 3];
       if (p.clamp_effort) {  // optional clamp of the actuation to the MJCF ctrlrange
         real lim = R[R_EFF];
         tq = tq > lim ? lim : (tq < -lim ? -lim : tq);
       }
       const real stiff = R[R_STIFF];  // joint spring about q = 0, implicit like the damping
-      SV U{mul(IA.I, ax), mulT(IA.H, ax)};
-      real D = dot(ax, U.w) + arm + dt * (damp + dt * stiff);
+      SV U{mul(IA.I, sw), mulT(IA.H, sw)};
+      real D = dot(sw, U.w) + arm + dt * (damp + dt * stiff);
       real Dinv = 1 / D;
-      real u = tq - damp * qd - stiff * (L[LS_Q] + dt * qd) - dot(ax, pA.w);
-      V3 aq = qd * ax;
-      SV c{cross(v.w, aq), cross(v.v, aq)};
+      real u = tq - damp * qd - stiff * (L[LS_Q] + dt * qd) - dot(sw, pA.w);
+      // classical velocity-product acceleration of the joint: [w_p x s qd; w_p x (w_p x r)], w_p = w - s qd
+      const V3 wp = v.w - qd * sw;
+      SV c{cross(wp, qd * sw), cross(wp, cross(wp, rw))};
       ABI Ia = rank1_sub(IA, U, Dinv);
       SV pa = pA + mul(Ia, c) + (Dinv * u) * U;
-      cia_prev = abi_to_parent(E, r, Ia);
-      cpa_prev = xform_force_T(E, r, pa);
+      cia_prev = abi_shift_to_parent(rw, Ia);
+      cpa_prev = shift_force_T(rw, pa);
       prev = i;
       st_abi(A + A_CIA, cia_prev);
       st6(A + A_CPA, cpa_prev);
@@ -363,28 +374,28 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     }
     sync.mark(3);
     ABI Om0 = abi_inverse_spd(IA);
-    SV a0 = (real)-1 * mul(Om0, pA);  // acceleration relative to the gravity field
-    M3 R0 = ld_m3(L + LS_E);
-    SV v0 = v;
+    SV a0 = (real)-1 * mul(Om0, pA);  // [angular acceleration; acceleration of the origin relative to the gravity field]
     st6(A + A_ACC, a0);
     st_abi(A + A_OM0, Om0);
-    V3 gl = mulT(R0, v3(p.g[0], p.g[1], p.g[2]));
-    SV vs{v0.w + dt * a0.w, v0.v + dt * (a0.v + gl)};
+    // Predicted base velocity as the contact stage sees it. The model (oracle/physics_oracle.py) advances the base
+    // twist by its BODY-frame components, i.e. it holds the body frame fixed over the step: in world axes that is the
+    // classical update minus dt w x u; the term is given back when the base is integrated.
+    const V3 rot = dt * cross(v.w, v.v);
+    SV vs{v.w + dt * a0.w, v.v + dt * (a0.v + v3(p.g[0], p.g[1], p.g[2])) - rot};
     st6(L + LS_U, vs);
-    st3(L + LS_SC, dt * cross(v0.w, v0.v));  // rotating-frame term of the world-frame linear velocity update
+    st3(L + LS_SC, rot);
     sync.signal(fl + 0, base + ST_PASS2);
-    // inverse inertia at the feet's common ancestor: Om_j = L_j^T Om_parent L_j + S D^-1 S^T down the shared links
+    // inverse inertia at the feet's common ancestor: Om_j = X Om_parent X^T + S D^-1 S^T down the shared links
     ABI Oml = Om0;
 #pragma unroll 1
-    for (int k = 0; k < m.shared_len; ++k) {
-      const float* Rs = REC(m.shared_rec[k]);
+    for (int k2 = 0; k2 < m.shared_len; ++k2) {
+      const float* Rs = REC(m.shared_rec[k2]);
       const real* Ls = BLK(RI(Rs, R_LINK));
-      V3 axs = ld3_f(Rs + R_AXIS), rs = ld3_f(Rs + R_R);
-      M3 Es = ld_m3(Ls + LS_E);
+      const V3 ss = ld3(Ls + LS_S), rs = ld3(Ls + LS_R);
       real Dinv = Ls[LS_SC + 2];
-      SV w = Dinv * xform_force_T(Es, rs, ld6(Ls + LS_U));
+      SV w = Dinv * shift_force_T(rs, ld6(Ls + LS_U));
       SV y = mul(Oml, w);
-      Oml = inv_joint_update(inv_to_child(Es, rs, Oml), axs, xform_motion(Es, rs, y), dot(w, y) + Dinv);
+      Oml = inv_joint_update(inv_shift_to_child(rs, Oml), ss, shift_motion(rs, y), dot(w, y) + Dinv);
     }
     st_abi(X + X_OML, Oml);
     sync.signal(flags + F_OML, epoch + 1);
@@ -409,13 +420,12 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     for (int k = m.chain_len[foot] - 1; k >= 0; --k) {
       const float* R = REC(m.chain_rec[foot][k]);
       real* L = BLK(RI(R, R_LINK));
-      V3 ax = ld3_f(R + R_AXIS), r = ld3_f(R + R_R);
-      M3 E = ld_m3(L + LS_E);
+      const V3 sw = ld3(L + LS_S), rw = ld3(L + LS_R);
       real Dinv = L[LS_SC + 2];
       SV U = ld6(L + LS_U);
       real gj[6];
 #pragma unroll
-      for (int c = 0; c < 6; ++c) gj[c] = dot(ax, G[c].w);
+      for (int c = 0; c < 6; ++c) gj[c] = dot(sw, G[c].w);
 #pragma unroll
       for (int c = 0; c < 6; ++c) (k == 0 ? X + X_G0 + foot * 6 : L + LS_A + A_G)[c] = gj[c];
       Om.I.xx += Dinv * gj[0] * gj[0]; Om.I.yy += Dinv * gj[1] * gj[1]; Om.I.zz += Dinv * gj[2] * gj[2];
@@ -427,17 +437,16 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
 #pragma unroll
         for (int b = 0; b < 3; ++b) Om.H.a[3 * a + b] += Dinv * gj[a] * gj[3 + b];
 #pragma unroll
-      for (int c = 0; c < 6; ++c) G[c] = xform_force_T(E, r, G[c] - (Dinv * gj[c]) * U);
+      for (int c = 0; c < 6; ++c) G[c] = shift_force_T(rw, G[c] - (Dinv * gj[c]) * U);
     }
   }
   // active sole points of this foot (needs the foot pose of pass 1 only): candidates below the contact offset, at
   // most MAX_ACTIVE_PTS, with their offsets from the foot origin and the velocity bias of the non-penetration row;
   // kept in the env's scratch (X_PTS) so that the per-point loops below stay rolled (small instruction footprint)
   M3 Rwf;
-  // contact location of candidate k of foot g relative to the foot origin (foot coordinates): the sphere's lowest point
+  // contact location of candidate k of foot g relative to the foot origin (world axes): the sphere's lowest point
   auto sole_point = [&](int g, int k) {
-    const real rad = m.foot_pt_radius[g][k];
-    return v3(m.foot_pt_pos[g][k][0] - rad * Rwf.a[6], m.foot_pt_pos[g][k][1] - rad * Rwf.a[7], m.foot_pt_pos[g][k][2] - rad * Rwf.a[8]);
+    return mul(Rwf, v3(m.foot_pt_pos[g][k][0], m.foot_pt_pos[g][k][1], m.foot_pt_pos[g][k][2])) - v3(0, 0, m.foot_pt_radius[g][k]);
   };
   int nact = 0;
   const real inv_dt = 1 / dt;
@@ -465,6 +474,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
   // ---- pass 3, root -> leaves: joint accelerations, predicted joint velocities
   prev = -1;
   SV a_prev = sv_zero();
+  V3 w_prev = v3(0, 0, 0);  // angular velocity of the parent (start-of-step velocities: for the velocity-product term)
   for (int k = 0; k < len; ++k) {
     const float* R = REC(rec0 + k);
     const int i = RI(R, R_LINK), par = RI(R, R_PARENT), flg = RI(R, R_FLAGS);
@@ -474,16 +484,17 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
       sync.wait(fl + par, base + ST_PASS3);
     }
     real* L = BLK(i);
-    if (par != prev) a_prev = ld6(BLK(par) + LS_A + A_ACC);
-    V3 ax = ld3_f(R + R_AXIS), r = ld3_f(R + R_R);
-    M3 E = ld_m3(L + LS_E);
-    SV v = ld6(L + LS_V);
+    if (par != prev) {
+      a_prev = ld6(BLK(par) + LS_A + A_ACC);
+      w_prev = ld3(BLK(par) + LS_V);
+    }
+    const V3 sw = ld3(L + LS_S), rw = ld3(L + LS_R);
     real qd = L[LS_SC];
-    V3 aq = qd * ax;
-    SV a = xform_motion(E, r, a_prev) + SV{cross(v.w, aq), cross(v.v, aq)};
+    SV a = shift_motion(rw, a_prev) + SV{cross(w_prev, qd * sw), cross(w_prev, cross(w_prev, rw))};
     real qdd = L[LS_SC + 2] * (L[LS_SC + 1] - dot(ld6(L + LS_U), a));
-    a.w = a.w + qdd * ax;
+    a.w = a.w + qdd * sw;
     a_prev = a;
+    w_prev = w_prev + qd * sw;
     prev = i;
     st6(L + LS_A + A_ACC, a);
     L[LS_SC] = qd + dt * qdd;
@@ -496,22 +507,20 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     const int clen = m.chain_len[g];
     SV Y[6];              // Om_lca G
     SV V = ld6(BLK(0) + LS_U);  // base role published v0* with ST_PASS2 (waited for in pass 3)
-    SV P = sv_zero();     // accumulated contact impulse on the foot (foot coordinates)
+    SV P = sv_zero();     // accumulated contact impulse on the foot (world axes, about the foot origin)
     if (m.shared_len > 0) {  // predicted velocity of the common ancestor (needs pass 3 of the shared links)
       sync.wait(fl + m.lca, base + ST_PASS3);
 #pragma unroll 1
       for (int k = 0; k < m.shared_len; ++k) {
-        const float* Rs = REC(m.shared_rec[k]);
-        const real* Ls = BLK(RI(Rs, R_LINK));
-        V = xform_motion(ld_m3(Ls + LS_E), ld3_f(Rs + R_R), V);
-        V.w = V.w + Ls[LS_SC] * ld3_f(Rs + R_AXIS);
+        const real* Ls = BLK(RI(REC(m.shared_rec[k]), R_LINK));
+        V = shift_motion(ld3(Ls + LS_R), V);
+        V.w = V.w + Ls[LS_SC] * ld3(Ls + LS_S);
       }
     }
     for (int k = 0; k < clen; ++k) {
-      const float* R = REC(m.chain_rec[g][k]);
-      const real* L = BLK(RI(R, R_LINK));
-      V = xform_motion(ld_m3(L + LS_E), ld3_f(R + R_R), V);
-      V.w = V.w + L[LS_SC] * ld3_f(R + R_AXIS);
+      const real* L = BLK(RI(REC(m.chain_rec[g][k]), R_LINK));
+      V = shift_motion(ld3(L + LS_R), V);
+      V.w = V.w + L[LS_SC] * ld3(L + LS_S);
     }
     {
       sync.wait(flags + F_OML, epoch + 1);
@@ -530,14 +539,14 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
 #pragma unroll
         for (int b = 0; b < 3; ++b) Om.H.a[3 * a + b] += w[a][3 + b];
     }
-    // rows of the active points: response cv = Om J and 1 / (J . cv) per direction (n, t1, t2), parked in the blocks
-    // of the first chain links (ROWS_PER_LINK per link)
+    // rows of the active points: response cv = Om J and 1 / (J . cv) per direction (world z, x, y), parked in the
+    // blocks of the first chain links (ROWS_PER_LINK per link)
 #pragma unroll 1
     for (int a = 0; a < nact; ++a) {
       const V3 xa = sole_point(g, reinterpret_cast<const int*>(pts + a * PT_WORDS)[0]);
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        V3 dir = d == 0 ? v3(Rwf.a[6], Rwf.a[7], Rwf.a[8]) : (d == 1 ? v3(Rwf.a[0], Rwf.a[1], Rwf.a[2]) : v3(Rwf.a[3], Rwf.a[4], Rwf.a[5]));
+        const V3 dir = d == 0 ? v3(0, 0, 1) : (d == 1 ? v3(1, 0, 0) : v3(0, 1, 0));
         SV J{cross(xa, dir), dir};
         SV cv = mul(Om, J);
         const int row = a * 3 + d;
@@ -558,8 +567,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
         real lam[3] = {pt[2], pt[3], pt[4]};
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-          V3 dir = d == 0 ? v3(Rwf.a[6], Rwf.a[7], Rwf.a[8])
-                          : (d == 1 ? v3(Rwf.a[0], Rwf.a[1], Rwf.a[2]) : v3(Rwf.a[3], Rwf.a[4], Rwf.a[5]));
+          const V3 dir = d == 0 ? v3(0, 0, 1) : (d == 1 ? v3(1, 0, 0) : v3(0, 1, 0));
           SV J{cross(xa, dir), dir};
           const int row = a * 3 + d;
           const real* rw = BLK(m.chain[g][row / ROWS_PER_LINK]) + LS_A + A_ROWS + (row % ROWS_PER_LINK) * 7;
@@ -605,7 +613,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     sync.signal(flags + F_PD + g, epoch + 1);
     if (io.live) {
 #pragma unroll 1
-      for (int a = 0; a < nact; ++a) {  // world force over this sub-step: (t1, t2, n) = world (x, y, z)
+      for (int a = 0; a < nact; ++a) {  // world force over this sub-step: rows (n, t1, t2) = world (z, x, y)
         const real* pt = pts + a * PT_WORDS;
         float* cf = io.contact + 3 * m.foot_pt_body[g][reinterpret_cast<const int*>(pt)[0]];
         cf[0] += (float)(pt[3] * inv_dt);
@@ -624,19 +632,18 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     }
 #pragma unroll 1
     for (int k = m.shared_len - 1; k >= 0; --k) {  // ... and from there up the shared links to the base
-      const float* Rs = REC(m.shared_rec[k]);
-      real* Ls = BLK(RI(Rs, R_LINK));
-      real sd = dot(ld3_f(Rs + R_AXIS), pd.w);
+      real* Ls = BLK(RI(REC(m.shared_rec[k]), R_LINK));
+      real sd = dot(ld3(Ls + LS_S), pd.w);
       Ls[LS_SC + 3] = sd;
-      pd = xform_force_T(ld_m3(Ls + LS_E), ld3_f(Rs + R_R), pd - (Ls[LS_SC + 2] * sd) * ld6(Ls + LS_U));
+      pd = shift_force_T(ld3(Ls + LS_R), pd - (Ls[LS_SC + 2] * sd) * ld6(Ls + LS_U));
     }
     st6(BLK(0) + LS_V, (real)-1 * mul(ld_abi(BLK(0) + LS_A + A_OM0), pd));
     sync.signal(fl + 0, base + ST_DOWN);
   }
   sync.mark(10);
   // ---- down the tree: joint velocity changes, speed cap, integration, limit projection
-  prev = -1;
   if (io_async) sync.wait(flags + F_IO_DONE, epoch + 1);
+  prev = -1;
   for (int k = 0; k < len; ++k) {
     const float* R = REC(rec0 + k);
     const int i = RI(R, R_LINK), par = RI(R, R_PARENT), flg = RI(R, R_FLAGS);
@@ -647,10 +654,10 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     }
     real* L = BLK(i);
     if (par != prev) a_prev = ld6(BLK(par) + LS_V);  // (re-used register set: the parent's velocity change)
-    V3 ax = ld3_f(R + R_AXIS), r = ld3_f(R + R_R);
-    SV dv = xform_motion(ld_m3(L + LS_E), r, a_prev);
+    const V3 sw = ld3(L + LS_S);
+    SV dv = shift_motion(ld3(L + LS_R), a_prev);
     real dqd = -L[LS_SC + 2] * (dot(ld6(L + LS_U), dv) + L[LS_SC + 3]);
-    dv.w = dv.w + dqd * ax;
+    dv.w = dv.w + dqd * sw;
     a_prev = dv;
     prev = i;
     st6(L + LS_V, dv);
@@ -672,13 +679,11 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     L[LS_SC] = qdn;
   }
   sync.mark(11);
-  // ---- base integration (base role)
+  // ---- base integration (base role): the base velocity is already in world axes
   if (base_role) {
     const real* L = BLK(0);
-    M3 R0 = ld_m3(L + LS_E);
     SV vb = ld6(L + LS_U) + ld6(L + LS_V);
-    vb.v = vb.v + ld3(L + LS_SC);
-    V3 ww = mul(R0, vb.w), vw = mul(R0, vb.v);
+    V3 ww = vb.w, vw = vb.v + ld3(L + LS_SC);
     real wn = sqrt(dot(ww, ww));
     if (wn > p.max_ang_vel) ww = (p.max_ang_vel / wn) * ww;
     {
