@@ -33,7 +33,8 @@ UNIT = "env-steps/s"
 WORKLOAD = "DyrosDynamicWalk 4096 envs/GPU, random actions, physics + PD + obs/reward/reset kernels (BASELINE configs[1])"
 K1_BYTES_PER_ENV_STEP = 2 * 1648 + 2 * 1296   # per policy step: 2 x K1 sub-step (412 words) + 2 x (torque/delay ring + sensor noise: 324 words), DESIGN.md section 6
 ENV_STEP_BYTES = 7044                # SURVEY 8d canonical bytes per env-step
-K1_FLOP_PER_ENV_STEP = 2 * 62000         # executed FP32 FLOP of 2 sub-steps (ncu r1: ffma*2+fadd+fmul = 62.0e3 per env-sub-step)
+K1_FLOP_PER_ENV_STEP = 2 * 48200         # executed FP32 FLOP of 2 sub-steps (ncu, profiles/r1f_k_step_physics.txt: ffma*2+fadd+fmul = 3.951e8 per 4096-env launch)
+K1_DRAM_BYTES_PER_ENV = 6129152 / 4096   # dram__bytes_read+write of one 4096-env launch (same capture): the state is L2-resident
 
 
 def parse():
@@ -285,7 +286,7 @@ def run_ours(a):
                        "domain_randomisation": True, "perturbation": "forced on (T:491)" if a.force_perturb else "gated as in the reference (T:489)",
                        "l2": "flushed between timed steps (256 MiB fill outside the timed intervals)",
                        "timing": "CUDA events per step on the launch stream, summed; max over ranks",
-                       "launch_geometry": core.launch_info(), "reset_rate_last_step": reset_rate},
+                       "launch_geometry": dict(core.launch_info(), threads_per_cta_fused_step=256), "reset_rate_last_step": reset_rate},
             "clocks": clocks,
             "e2e": {"value": total_envs * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
@@ -293,7 +294,9 @@ def run_ours(a):
             "value_warm_l2": total_envs * K / (warm_ms * 1e-3), "ms_per_step_warm_l2": warm_ms / K,
             "roofline": {"bound": "hbm", "kernel": "k_step_physics (2 x (PD/delay torque, physics sub-step, sensor noise) of all envs, one launch)",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                         "traffic": K1_DRAM_BYTES_PER_ENV * N if N == 4096 else None,
+                         "traffic_source": "profiles/r1f_k_step_physics.txt (ncu --set full, one launch, 4096 envs)",
                          "launch_ms": k1_ms, "algorithmic_bytes_per_launch": k1_bytes,
                          "note": "K1 is FP32-latency bound, not HBM bound (SURVEY 8d): see fp32"},
             "fp32": {"achieved": K1_FLOP_PER_ENV_STEP * N / (k1_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
