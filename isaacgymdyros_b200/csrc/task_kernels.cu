@@ -8,7 +8,7 @@
 
 namespace dyros {
 
-constexpr int kWarpsPerBlock = 4;
+constexpr int kWarpsPerBlock = 8;
 
 // ------------------------------------------------------------------ small math (TU / JU restated)
 // JU:142-160 with a = identity: |vec(a (x) conj(q))| through the TU:20-40 product, then 2*asin(min(.,1))
@@ -97,8 +97,13 @@ __device__ int stage_check_termination(const TK& k, int e, int lane, TermShared*
   return reset;
 }
 
-// T:387-428 + T:802-947
-__device__ void stage_compute_reward(const TK& k, int e, int lane, const TermShared* shared = nullptr) {
+// T:387-428 + T:802-947, in two parts: the warp-wide reductions over the joints, and the scalar terms (one thread per
+// env: the fused kernel runs them for all envs of a CTA side by side in one warp instead of on lane 0 of each).
+struct RewardSums {
+  float s_qpos, s_qvel, s_qacc, s_tq, s_tqd, qe;
+  bool col;
+};
+__device__ RewardSums reward_sums(const TK& k, int e, int lane, const TermShared* shared = nullptr) {
   const float* root = k.s.root_states + (size_t)e * 13;
   const float* ds = k.s.dof_state + (size_t)e * ND * 2;
   float s_qpos = 0.f, s_qvel = 0.f, s_qacc = 0.f, s_tq = 0.f, s_tqd = 0.f;
@@ -117,14 +122,20 @@ __device__ void stage_compute_reward(const TK& k, int e, int lane, const TermSha
     s_tq = t * t;
     s_tqd = td * td;
   }
-  s_qpos = warp_sum(s_qpos);
-  s_qvel = warp_sum(s_qvel);
-  s_qacc = warp_sum(s_qacc);
-  s_tq = warp_sum(s_tq);
-  s_tqd = warp_sum(s_tqd);
-  bool col = shared ? shared->col : collision_true(k, e, lane);
-  if (lane != 0) return;
-  float qe = shared ? shared->qe : quat_err_identity(root + 3);
+  RewardSums o;
+  o.s_qpos = warp_sum(s_qpos);
+  o.s_qvel = warp_sum(s_qvel);
+  o.s_qacc = warp_sum(s_qacc);
+  o.s_tq = warp_sum(s_tq);
+  o.s_tqd = warp_sum(s_tqd);
+  o.col = shared ? shared->col : collision_true(k, e, lane);
+  o.qe = shared ? shared->qe : quat_err_identity(root + 3);
+  return o;
+}
+__device__ void reward_scalar(const TK& k, int e, const RewardSums& in) {
+  const float* root = k.s.root_states + (size_t)e * 13;
+  const float s_qpos = in.s_qpos, s_qvel = in.s_qvel, s_qacc = in.s_qacc, s_tq = in.s_tq, s_tqd = in.s_tqd, qe = in.qe;
+  const bool col = in.col;
   float r[14];
   r[0] = 0.3f * expf(-13.2f * fabsf(qe));                                          // T:835
   float n;
@@ -171,6 +182,10 @@ __device__ void stage_compute_reward(const TK& k, int e, int lane, const TermSha
 #pragma unroll
   for (int i = 0; i < 14; ++i) st[i] = col ? k.p.death_cost : r[i];                // T:945
   st[14] = (*k.b.perturb_start) ? 1.0f : 0.0f;                                     // T:415
+}
+__device__ void stage_compute_reward(const TK& k, int e, int lane, const TermShared* shared = nullptr) {
+  RewardSums sums = reward_sums(k, e, lane, shared);
+  if (lane == 0) reward_scalar(k, e, sums);
 }
 
 // T:598-669, T:720-748 (+ DR re-draw of damping/armature, VT:519-733 / gymutil.py:584-619)
@@ -408,16 +423,29 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_late_update(TK k) {
 // post_physics_step in one launch: epilogue, termination, reward, reset, observations, late update.
 // Reward/termination read the pre-reset state, observations the post-reset state.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_post_fused(TK k) {
+  __shared__ RewardSums sums[kWarpsPerBlock];
   pdl_launch_dependents();
   pdl_wait();
-  ENV_LANE();
-  stage_epilogue(k, e, lane);
-  __syncwarp();
-  TermShared ts;
-  int reset = stage_check_termination(k, e, lane, &ts);
-  __syncwarp();
-  stage_compute_reward(k, e, lane, &ts);
-  __syncwarp();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int e = blockIdx.x * kWarpsPerBlock + w;
+  const bool valid = e < k.p.N;  // (no early return: the CTA meets at two barriers)
+  int reset = 0;
+  if (valid) {
+    stage_epilogue(k, e, lane);
+    __syncwarp();
+    TermShared ts;
+    reset = stage_check_termination(k, e, lane, &ts);
+    __syncwarp();
+    RewardSums rs = reward_sums(k, e, lane, &ts);
+    if (lane == 0) sums[w] = rs;
+  }
+  __syncthreads();
+  if (w == 0 && lane < kWarpsPerBlock) {  // the scalar reward terms of the CTA's envs, one lane per env
+    const int e2 = blockIdx.x * kWarpsPerBlock + lane;
+    if (e2 < k.p.N) reward_scalar(k, e2, sums[lane]);
+  }
+  __syncthreads();
+  if (!valid) return;
   if (reset) {
     stage_reset_env(k, e, lane);
     __syncwarp();
