@@ -223,6 +223,9 @@ int dyros_task_physics(DyrosTask* task, void* stream);
 /* Profiling aid: dyros_task_physics that also writes clock64() at the phase boundaries of CTA 0 into `trace`
  * (device buffer of skipframe * DYROS_LANES * 32 int64; see physics_roles.cuh for the mark ids). */
 int dyros_task_physics_trace(DyrosTask* task, int64_t* trace, void* stream);
+/* The first launch of dyros_task_step on its own: dyros_task_prologue + dyros_task_physics in one kernel (the
+ * prologue runs on the I/O warps while the role warps start the first sub-step). `trace` may be NULL. */
+int dyros_task_prologue_physics(DyrosTask* task, const float* actions, int64_t* trace, void* stream);
 int dyros_task_substep_torque(DyrosTask* task, void* stream);                      /* T:505-520 -> dof_actuation_force */
 int dyros_task_sensor_noise(DyrosTask* task, int substep, void* stream);           /* T:528-530 */
 int dyros_task_epilogue(DyrosTask* task, void* stream);                            /* T:532-541 + VT:325 + T:544-545 */

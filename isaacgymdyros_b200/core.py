@@ -341,6 +341,16 @@ class DyrosCore:
         native.check(self.lib.dyros_task_physics_trace(self.task_handle, C.c_void_p(buf.data_ptr()), self._stream), "trace")
         return buf
 
+    def prologue_physics(self, actions, trace: bool = False):
+        """The first launch of the fused step on its own (prologue + physics); with `trace` returns the clock64() marks."""
+        buf = None
+        if trace:
+            buf = torch.zeros(self.cfg.control_freq_inv, native.DYROS_LANES, 32, dtype=torch.int64, device=self.device)
+        native.check(self.lib.dyros_task_prologue_physics(self.task_handle, self._actions_ptr(actions),
+                                                          C.c_void_p(buf.data_ptr()) if trace else None, self._stream),
+                     "prologue_physics")
+        return buf
+
     def substep_torque(self):
         native.check(self.lib.dyros_task_substep_torque(self.task_handle, self._stream), "substep_torque")
 

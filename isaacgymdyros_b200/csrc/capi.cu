@@ -292,6 +292,14 @@ int dyros_task_physics_trace(DyrosTask* task, int64_t* trace, void* stream) {
   }
   return launch_task_physics(t, (cudaStream_t)stream, reinterpret_cast<long long*>(trace));
 }
+int dyros_task_prologue_physics(DyrosTask* task, const float* actions, int64_t* trace, void* stream) {
+  TASK_OR_FAIL("dyros_task_prologue_physics");
+  if (!actions) {
+    set_error("dyros_task_prologue_physics: actions is NULL");
+    return 1;
+  }
+  return launch_task_physics(t, (cudaStream_t)stream, reinterpret_cast<long long*>(trace), false, actions);
+}
 int dyros_task_substep_torque(DyrosTask* task, void* stream) {
   TASK_OR_FAIL("dyros_task_substep_torque");
   return launch_substep_torque(t, (cudaStream_t)stream);

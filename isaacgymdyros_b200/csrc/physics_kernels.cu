@@ -33,12 +33,17 @@ struct RoleSync {
     while (ld_acquire_shared(f) < v) {
     }
   }
+  // for flags published by the I/O warps, which share the schedulers with the role warps: back off between polls so
+  // that the waiting warp does not take issue slots from the warp it is waiting for
+  __device__ __forceinline__ void wait_io(const int* f, int v) const {
+    while (ld_acquire_shared(f) < v) __nanosleep(100);
+  }
 };
 struct CtaSync {
   __device__ __forceinline__ void operator()() const { __syncthreads(); }
 };
 
-constexpr int kMaxPhysSmem = 227 * 1024;
+constexpr int kMaxPhysSmem = 227 * 1024 - 1024;  // dynamic part; 1 KiB is left for static shared memory (k_step_physics: 1 KiB)
 constexpr int kPhysThreads = DYROS_LANES * 32;
 
 struct PhysCta {
@@ -259,6 +264,7 @@ __device__ __forceinline__ void io_group_sync() { asm volatile("bar.sync 1, %0;"
 __global__ void __launch_bounds__(kStepThreads) k_step_physics(DevModel m, SimParams p, TK k, int epb, int es, long long* trace,
                                                                 const float* __restrict__ actions) {
   extern __shared__ __align__(16) float smem[];
+  __shared__ float pro[kSlabMaxEnvs][8];  // per-env scalars of the prologue (stage_prologue_slab)
   PhysCta c = phys_cta_setup(m, p, smem, epb, es);
   const int e0 = blockIdx.x * epb, nenv = min(epb, p.N - e0);
   float* envs = smem + m.hot_bytes / 4 + ((F_COUNT + 3) & ~3);
@@ -288,24 +294,40 @@ __global__ void __launch_bounds__(kStepThreads) k_step_physics(DevModel m, SimPa
   for (int s = 0; s < k.p.skipframe; ++s) {
     for (int ss = 0; ss < p.substeps; ++ss, ++epoch) {
       if (io_group) {
-        if (actions && epoch == 0) {  // the policy-step prologue (T:449-502) of the CTA's envs
-          stage_prologue_slab(k, actions, e0, nenv, it, kIoThreads, [] { io_group_sync(); });
-          io_group_sync();
-        }
+        // (profiling: marks 18.. of role 0's row are the I/O group's phase boundaries)
+        auto io_mark = [&](int id) {
+          if (trace && blockIdx.x == 0 && it == 0) trace[(size_t)s * DYROS_LANES * 32 + id] = clock64();
+        };
+        io_mark(18);
         // the push acts on the first sub-step of the policy step only (T:502 vs T:504)
-        slab_stage_pre(m, k.s, (s == 0 && ss == 0) ? k.b.push_force : nullptr, envs, es, e0, nenv, it, kIoThreads);
-        cp_async_wait_all();
-        io_group_sync();
-        if (it == 0) st_release_shared(c.flags + F_IO_PRE, epoch + 1);
+        auto stage_pre = [&] {
+          slab_stage_pre(m, k.s, (s == 0 && ss == 0) ? k.b.push_force : nullptr, envs, es, e0, nenv, it, kIoThreads);
+          cp_async_wait_all();
+          io_group_sync();
+          if (it == 0) st_release_shared(c.flags + F_IO_PRE, epoch + 1);
+          io_mark(19);
+        };
+        if (actions && epoch == 0) {  // the policy-step prologue (T:449-502) of the CTA's envs; the push it decides
+                                      // is staged (F_IO_PRE) as soon as the per-env phase is through
+          stage_prologue_slab(k, actions, e0, nenv, it, kIoThreads, pro, [] { io_group_sync(); }, stage_pre);
+          io_group_sync();
+        } else {
+          stage_pre();
+        }
+        io_mark(20);
+        // damping / armature (and, after the first sub-step of a policy step, the unchanged torque) are copied while
+        // the torque stage runs: the copies only touch their own slots
+        slab_stage_dofpar(m, k.s, c.hot, envs, es, e0, nenv, ss > 0, it, kIoThreads);
         if (ss == 0) {
           torque_stage_slab(torque_args(k), e0, nenv, envs, es, dof_link, it, kIoThreads);
           io_group_sync();  // every thread has read simul_len
           stage_simul_len_update(torque_args(k), e0, nenv, it, kIoThreads);
         }
-        slab_stage_dofpar(m, k.s, c.hot, envs, es, e0, nenv, ss > 0, it, kIoThreads);
+        io_mark(21);
         cp_async_wait_all();
         io_group_sync();
         if (it == 0) st_release_shared(c.flags + F_IO_TAU, epoch + 1);
+        io_mark(22);
         // off the critical path: the sensor noise of the previous policy sub-step
         if (ss == 0 && s > 0) noise_stage_slab(noise_args(k), s - 1, e0, nenv, envs, es, dof_link, it, kIoThreads);
         io_group_sync();

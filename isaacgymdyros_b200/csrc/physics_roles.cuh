@@ -300,8 +300,8 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
   // lives in another role must have read its parent's pose first.
   for (int k = 0; k < m.n_xchild[role]; ++k) sync.wait(fl + m.xchild[role][k], base + ST_PASS1);
   if (io_async) {
-    sync.wait(flags + F_IO_PRE, epoch + 1);
-    sync.wait(flags + F_IO_TAU, epoch + 1);
+    sync.wait_io(flags + F_IO_PRE, epoch + 1);
+    sync.wait_io(flags + F_IO_TAU, epoch + 1);
   }
   sync.mark(2);
   // ---- pass 2, leaves -> root: articulated inertias and bias forces; the base role ends with the base itself
@@ -642,7 +642,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
   }
   sync.mark(10);
   // ---- down the tree: joint velocity changes, speed cap, integration, limit projection
-  if (io_async) sync.wait(flags + F_IO_DONE, epoch + 1);
+  if (io_async) sync.wait_io(flags + F_IO_DONE, epoch + 1);
   prev = -1;
   for (int k = 0; k < len; ++k) {
     const float* R = REC(rec0 + k);

@@ -14,20 +14,27 @@ struct TK {
   DyrosNoiseInjection j;
 };
 
-// JU:374-395 with x_dot_0 = x_dot_f = 0.0 (T:458-461), reference operation order
-__device__ __forceinline__ float cubic0(float time, float t0, float tf, float x0, float xf) {
-  float e = __fsub_rn(time, t0);
+// JU:374-395 with x_dot_0 = x_dot_f = 0.0 (T:458-461), reference operation order. The terms that depend on the knot
+// times only (tt^2, tt^3 and the reference's literal 0/tt, 0/tt^2) are computed by cubic_knots once per env: a zero
+// numerator sends the IEEE division down its slow path, which is not something to repeat for each of the 35 columns.
+struct CubicKnots {
+  float t0, tf, tt2, tt3, z1, z2;  // z1 = 0/tt, z2 = 0/tt^2
+};
+__device__ __forceinline__ CubicKnots cubic_knots(float t0, float tf) {
   float tt = __fsub_rn(tf, t0);
   float tt2 = __fmul_rn(tt, tt);
-  float tt3 = __fmul_rn(tt2, tt);
+  return CubicKnots{t0, tf, tt2, __fmul_rn(tt2, tt), __fdiv_rn(0.0f, tt), __fdiv_rn(0.0f, tt2)};
+}
+__device__ __forceinline__ float cubic0(float time, const CubicKnots& kn, float x0, float xf) {
+  float e = __fsub_rn(time, kn.t0);
   float tx = __fsub_rn(xf, x0);
   float c = __fadd_rn(x0, __fmul_rn(0.0f, e));
-  float a2 = __fsub_rn(__fsub_rn(__fdiv_rn(__fmul_rn(3.0f, tx), tt2), __fdiv_rn(0.0f, tt)), __fdiv_rn(0.0f, tt));
+  float a2 = __fsub_rn(__fsub_rn(__fdiv_rn(__fmul_rn(3.0f, tx), kn.tt2), kn.z1), kn.z1);
   c = __fadd_rn(c, __fmul_rn(__fmul_rn(a2, e), e));
-  float a3 = __fadd_rn(__fdiv_rn(__fmul_rn(-2.0f, tx), tt3), __fdiv_rn(0.0f, tt2));
+  float a3 = __fadd_rn(__fdiv_rn(__fmul_rn(-2.0f, tx), kn.tt3), kn.z2);
   c = __fadd_rn(c, __fmul_rn(__fmul_rn(__fmul_rn(a3, e), e), e));
-  float xt = (time > tf) ? xf : x0;
-  if (t0 <= time && time <= tf) xt = c;
+  float xt = (time > kn.tf) ? xf : x0;
+  if (kn.t0 <= time && time <= kn.tf) xt = c;
   return xt;
 }
 
@@ -89,9 +96,9 @@ __device__ __forceinline__ void stage_prologue(const TK& k, const float* __restr
   if (lane == 0) k.b.mocap_data_idx[e] = idx;
   const float* r0 = k.b.mocap_data + (size_t)idx * 36;
   const float* r1 = r0 + 36;
-  float t0 = r0[0], tf = r1[0];
+  const CubicKnots kn = cubic_knots(r0[0], r1[0]);
   for (int c = lane; c < 35; c += 32) {                                           // T:458-461
-    float v = cubic0(lt_init, t0, tf, r0[1 + c], r1[1 + c]);
+    float v = cubic0(lt_init, kn, r0[1 + c], r1[1 + c]);
     if (c < ND) k.b.target_data_qpos[(size_t)e * ND + c] = v;
     else k.b.target_data_force[(size_t)e * 2 + (c - ND)] = v;
   }
@@ -111,48 +118,94 @@ __device__ __forceinline__ void stage_prologue(const TK& k, const float* __restr
   if (lane == 0) stage_push_schedule(k, e);
 }
 
-// The same stage for a contiguous slab of envs [e0, e0 + nenv), thread `tid` of `nthreads` cooperating threads with one
-// (env, column) item per thread and iteration, so that the items' memory latencies overlap (the warp-per-env form
-// above is a serial chain per env). Same arithmetic, same bits. `group_sync` is a barrier of the cooperating threads.
-template <class GroupSync>
+// The same stage for a contiguous slab of envs [e0, e0 + nenv), thread `tid` of `nthreads` cooperating threads. The
+// warp-per-env form above is a serial chain of dependent loads per env; here the per-env scalars (phase time, mocap
+// row, knot times) are computed once by one thread per env and parked in `pro` (shared memory, 8 words per env), and
+// the (env, column) items of the cubic targets and of the action block then need one batch of independent loads each.
+// Same arithmetic, same bits. `group_sync` is a barrier of the cooperating threads; `after_env_phase` runs between
+// the per-env phase (which also holds the push schedule) and the item phases.
+constexpr int kSlabMaxEnvs = 32;
+template <class GroupSync, class AfterEnvPhase>
 __device__ __forceinline__ void stage_prologue_slab(const TK& k, const float* __restrict__ actions_in, int e0, int nenv, int tid,
-                                                    int nthreads, GroupSync group_sync) {
+                                                    int nthreads, float (*pro)[8], GroupSync group_sync,
+                                                    AfterEnvPhase after_env_phase) {
   const TaskParams& P = k.p;
   const FastDiv d35(35), dNA(NA);
-#pragma unroll 2
-  for (int it = tid; it < nenv * 35; it += nthreads) {                            // T:450-461
-    const int le = d35.div(it), c = it - le * 35, e = e0 + le;
-    float time = k.b.time[e];
-    int init = k.b.init_mocap_data_idx[e];
+  constexpr int THREADS = 128;
+  constexpr int IT_A = (kSlabMaxEnvs * NA + THREADS - 1) / THREADS;  // action items per thread
+  // ---- first round trip: everything that depends on nothing is requested at once: the action block of this thread's
+  //      items (VT:307, T:464-468) and, on the per-env threads, the phase time
+  float act[IT_A], mcs[IT_A];
+  int hd[IT_A];
+#pragma unroll
+  for (int j = 0; j < IT_A; ++j) {
+    int it = tid + j * nthreads;
+    it = it < nenv * NA ? it : 0;
+    const int le = dNA.div(it), lane = it - le * NA, e = e0 + le;
+    act[j] = actions_in[(size_t)e * NA + lane];
+    hd[j] = k.b.act_hist_head[e];
+    mcs[j] = k.b.motor_constant_scale[(size_t)e * 12 + (lane < 12 ? lane : 0)];
+  }
+  const bool env_thread = tid < nenv;
+  const int ee = e0 + (env_thread ? tid : 0);
+  const float time = k.b.time[ee];
+  const int init = k.b.init_mocap_data_idx[ee];
+  const int head0 = k.b.act_hist_head[ee];
+  if (env_thread) {                                                               // T:450-452
     float local_time = py_fmodf(time, P.period);
     float lt_init = py_fmodf(__fadd_rn(local_time, __fmul_rn((float)init, P.cycle_dt)), P.period);
     int idx = (int)(((long long)init + (long long)__fdiv_rn(local_time, P.cycle_dt)) % P.mocap_data_num);
-    if (c == 0) k.b.mocap_data_idx[e] = idx;
-    const float* r0 = k.b.mocap_data + (size_t)idx * 36;
-    const float* r1 = r0 + 36;
-    float v = cubic0(lt_init, r0[0], r1[0], r0[1 + c], r1[1 + c]);
-    if (c < ND) k.b.target_data_qpos[(size_t)e * ND + c] = v;
-    else k.b.target_data_force[(size_t)e * 2 + (c - ND)] = v;
+    k.b.mocap_data_idx[ee] = idx;
+    // ---- second round trip (per-env threads): the knot times of the mocap row
+    const float t0 = k.b.mocap_data[(size_t)idx * 36], tf = k.b.mocap_data[(size_t)(idx + 1) * 36];
+    pro[tid][0] = lt_init;
+    pro[tid][1] = __int_as_float(idx);
+    const CubicKnots kn = cubic_knots(t0, tf);
+    pro[tid][2] = kn.t0; pro[tid][3] = kn.tf; pro[tid][4] = kn.tt2; pro[tid][5] = kn.tt3; pro[tid][6] = kn.z1; pro[tid][7] = kn.z2;
+    stage_push_schedule(k, ee);                                                   // T:489-502
   }
-#pragma unroll 1
-  for (int it = tid; it < nenv * NA; it += nthreads) {                            // VT:307, T:464-468
-    const int le = dNA.div(it), lane = it - le * NA, e = e0 + le;
-    float a = actions_in[(size_t)e * NA + lane];
-    a = (a < -1.0f) ? -1.0f : ((a > 1.0f) ? 1.0f : a);
-    if (lane == NA - 1) a = __fmul_rn((a > 0.0f) ? 1.0f : 0.0f, a);
-    k.b.actions[(size_t)e * NA + lane] = a;
-    int head = (k.b.act_hist_head[e] + 1) % NSLOT;
-    k.b.action_history[((size_t)e * NSLOT + head) * NA + lane] = a;
-    if (lane < 12)
-      k.b.action_torque[(size_t)e * 12 + lane] =
-          __fmul_rn(__fmul_rn(a, k.b.motor_constant_scale[(size_t)e * 12 + lane]), P.action_high[lane]);
+#pragma unroll
+  for (int j = 0; j < IT_A; ++j) {
+    const int it = tid + j * nthreads;
+    if (it < nenv * NA) {
+      const int le = dNA.div(it), lane = it - le * NA, e = e0 + le;
+      float a = act[j];
+      a = (a < -1.0f) ? -1.0f : ((a > 1.0f) ? 1.0f : a);
+      if (lane == NA - 1) a = __fmul_rn((a > 0.0f) ? 1.0f : 0.0f, a);
+      k.b.actions[(size_t)e * NA + lane] = a;
+      const int head = (hd[j] + 1) % NSLOT;
+      k.b.action_history[((size_t)e * NSLOT + head) * NA + lane] = a;
+      if (lane < 12) k.b.action_torque[(size_t)e * 12 + lane] = __fmul_rn(__fmul_rn(a, mcs[j]), P.action_high[lane]);
+    }
   }
-  group_sync();  // every item has read act_hist_head
+  group_sync();  // pro[] complete; every action item has read act_hist_head
+  if (env_thread) k.b.act_hist_head[ee] = (head0 + 1) % NSLOT;
+  after_env_phase();
+  // ---- third round trip: the columns of the two mocap rows, B (env, column) items per thread in flight
+  constexpr int B = 4;
 #pragma unroll 1
-  for (int le = tid; le < nenv; le += nthreads) {                                 // ring head, push schedule T:489-502
-    const int e = e0 + le;
-    k.b.act_hist_head[e] = (k.b.act_hist_head[e] + 1) % NSLOT;
-    stage_push_schedule(k, e);
+  for (int it0 = tid; it0 < nenv * 35; it0 += nthreads * B) {                     // T:458-461
+    float x0[B], xf[B];
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      int it = it0 + j * nthreads;
+      it = it < nenv * 35 ? it : 0;
+      const int le = d35.div(it), c = it - le * 35;
+      const float* r0 = k.b.mocap_data + (size_t)__float_as_int(pro[le][1]) * 36;
+      x0[j] = r0[1 + c];
+      xf[j] = r0[36 + 1 + c];
+    }
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      const int it = it0 + j * nthreads;
+      if (it < nenv * 35) {
+        const int le = d35.div(it), c = it - le * 35, e = e0 + le;
+        const CubicKnots kn{pro[le][2], pro[le][3], pro[le][4], pro[le][5], pro[le][6], pro[le][7]};
+        float v = cubic0(pro[le][0], kn, x0[j], xf[j]);
+        if (c < ND) k.b.target_data_qpos[(size_t)e * ND + c] = v;
+        else k.b.target_data_force[(size_t)e * 2 + (c - ND)] = v;
+      }
+    }
   }
 }
 
@@ -243,7 +296,6 @@ __device__ __forceinline__ void stage_sensor_noise(const TK& k, int substep, int
 //      element per thread and iteration, so every global access is coalesced; the loads of all iterations are issued
 //      before the first use (MAXE bounds the slab). Same arithmetic, same bits as the per-env variants.
 //      `tau_sink(le, d, v)` additionally receives every torque (the fused kernel feeds its scratch blocks with it).
-constexpr int kSlabMaxEnvs = 32;
 struct TorqueSlabArgs {  // the handful of pointers the torque stage touches (passed by value to a non-inlined function)
   const float* dof_state;
   float* dof_actuation_force;

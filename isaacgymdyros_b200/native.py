@@ -104,6 +104,7 @@ SIGNATURES = {
     "dyros_task_prologue": (_INT, [_VP, _VP, _VP]),
     "dyros_task_physics": (_INT, [_VP, _VP]),
     "dyros_task_physics_trace": (_INT, [_VP, _VP, _VP]),
+    "dyros_task_prologue_physics": (_INT, [_VP, _VP, _VP, _VP]),
     "dyros_task_substep_torque": (_INT, [_VP, _VP]),
     "dyros_task_sensor_noise": (_INT, [_VP, _INT, _VP]),
     "dyros_task_epilogue": (_INT, [_VP, _VP]),

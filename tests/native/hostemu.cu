@@ -21,6 +21,7 @@ struct HostRoleSync {
   void wait(const int* f, int v) const {
     while (__atomic_load_n(f, __ATOMIC_ACQUIRE) < v) std::this_thread::yield();
   }
+  void wait_io(const int* f, int v) const { wait(f, v); }
 };
 
 extern "C" int dyros_hostemu_simulate(const DyrosSimDesc* d, const DyrosModelDesc* md, float* root, float* dof_state,

@@ -88,4 +88,4 @@ def test_tocabi_cta_holds_28_envs():
     fn = hostemu().dyros_hostemu_cta_smem_bytes
     fn.restype = C.c_long
     need = fn(C.byref(md), 28)
-    assert 0 < need <= 227 * 1024, need
+    assert 0 < need <= 227 * 1024 - 1024, need  # 1 KiB stays free for static shared memory
