@@ -420,6 +420,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_late_update(TK k) {
   ENV_LANE();
   stage_late_update(k, e, lane);
 }
+// one L2 prefetch per 128-byte line of [p, p + bytes), spread over the lanes of a warp
+__device__ __forceinline__ void prefetch_rows_l2(const void* p, int bytes, int lane) {
+  const uintptr_t a0 = reinterpret_cast<uintptr_t>(p) & ~uintptr_t(127);
+  const int lines = (int)((reinterpret_cast<uintptr_t>(p) + bytes + 127 - a0) >> 7);
+  for (int i = lane; i < lines; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(a0 + (uintptr_t)i * 128));
+}
+
 // post_physics_step in one launch: epilogue, termination, reward, reset, observations, late update.
 // Reward/termination read the pre-reset state, observations the post-reset state.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_post_fused(TK k) {
@@ -431,6 +438,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_post_fused(TK k) {
   const bool valid = e < k.p.N;  // (no early return: the CTA meets at two barriers)
   int reset = 0;
   if (valid) {
+    // The stages below are a chain of dependent reads. Once the env state no longer fits L2 (about 10.4 KB per env:
+    // beyond ~8k envs per GPU) the rows the physics launch did not touch (history rings, previous-step copies) are
+    // requested from HBM now, all at once, instead of one miss per stage (+6 % at 16,384 envs; at 4,096 envs they are
+    // L2 hits and the extra instructions only cost).
+    if (k.p.N > 8192) {
+      prefetch_rows_l2(k.b.obs_history + (size_t)e * NSLOT * NOBS1, NSLOT * NOBS1 * 4, lane);
+      prefetch_rows_l2(k.b.action_history + (size_t)e * NSLOT * NA, NSLOT * NA * 4, lane);
+      prefetch_rows_l2(k.b.contact_forces_pre + (size_t)e * NB * 3, NB * 3 * 4, lane);
+      prefetch_rows_l2(k.b.pre_joint_velocity_states + (size_t)e * ND, ND * 4, lane);
+      prefetch_rows_l2(k.b.actions_pre + (size_t)e * NA, NA * 4, lane);
+    }
     stage_epilogue(k, e, lane);
     __syncwarp();
     TermShared ts;
