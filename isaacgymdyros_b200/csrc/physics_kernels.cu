@@ -265,7 +265,9 @@ __global__ void __launch_bounds__(kStepThreads) k_step_physics(DevModel m, SimPa
                                                                 const float* __restrict__ actions) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float pro[kSlabMaxEnvs][8];  // per-env scalars of the prologue (stage_prologue_slab)
+  if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[24] = clock64();  // kernel entry (profiling)
   PhysCta c = phys_cta_setup(m, p, smem, epb, es);
+  if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[25] = clock64();  // tables staged, previous kernel done
   const int e0 = blockIdx.x * epb, nenv = min(epb, p.N - e0);
   float* envs = smem + m.hot_bytes / 4 + ((F_COUNT + 3) & ~3);
   const bool io_group = c.role >= DYROS_LANES;
@@ -346,6 +348,8 @@ __global__ void __launch_bounds__(kStepThreads) k_step_physics(DevModel m, SimPa
     sync.mark(15);
     if (sync.trace) sync.trace += DYROS_LANES * 32;
   }
+  __syncthreads();
+  if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[26] = clock64();  // all outputs written (profiling)
 }
 
 static size_t phys_smem_bytes(const Sim* sim, int epb) {

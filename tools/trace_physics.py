@@ -21,6 +21,9 @@ if "--cold" in sys.argv:  # evict everything from L2 first (what bench.py does b
     torch.cuda.synchronize()
 tr = (env.core.prologue_physics(acts, trace=True) if fused else env.core.task_physics_trace()).cpu()
 torch.cuda.synchronize()
+k0 = int(tr[0, 0, 24])
+print(f"kernel entry 0, tables staged / previous kernel done {int(tr[0, 0, 25]) - k0}, sub-step starts "
+      f"{[int(tr[s, :, 13].min()) - k0 for s in range(tr.shape[0])]}, all outputs written {int(tr[0, 0, 26]) - k0}")
 for s in range(tr.shape[0]):
     t0 = int(tr[s, :, 13].min())
     print(f"sub-step {s}: roles start at {[int(tr[s, r, 0]) - t0 for r in range(4)]}, end {[int(tr[s, r, 15]) - t0 for r in range(4)]}")
