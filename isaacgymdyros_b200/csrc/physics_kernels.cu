@@ -56,16 +56,16 @@ struct PhysCta {
 
 // Common prologue of the physics kernels: stage the hot tables, clear the flags, locate the lane's env.
 __device__ __forceinline__ PhysCta phys_cta_setup(const DevModel& m, const SimParams& p, float* smem, int epb, int es) {
-  {
-    const float4* src = reinterpret_cast<const float4*>(m.blob);
-    float4* dst = reinterpret_cast<float4*>(smem);
-    for (int i = threadIdx.x; i < m.hot_bytes / 16; i += blockDim.x) dst[i] = src[i];
+  {  // 16-byte cp.async: in flight together with the state copies issued after griddepcontrol.wait (the caller waits)
+    const char* src = reinterpret_cast<const char*>(m.blob);
+    for (int i = threadIdx.x; i < m.hot_bytes / 16; i += blockDim.x)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem) + i * 16), "l"(src + (size_t)i * 16)
+                   : "memory");
   }
   int* flags = reinterpret_cast<int*>(smem + m.hot_bytes / 4);
   for (int i = threadIdx.x; i < F_COUNT; i += blockDim.x) flags[i] = 0;
   pdl_launch_dependents();
   pdl_wait();  // everything above is independent of the previous kernel of the step (model tables only)
-  __syncthreads();
   PhysCta c;
   c.hot = smem;
   c.flags = flags;
@@ -235,9 +235,11 @@ __global__ void __launch_bounds__(kPhysThreads) k_simulate(DevModel m, SimParams
   io.rb_torque = apply_wrench ? b.rb_torque + (size_t)c.e * m.nb * 3 : nullptr;
   RoleSync sync{c.lane, nullptr};
   for (int s = 0; s < p.substeps; ++s) {
-    if (s == 0) slab_stage_state(m, b, c.hot, envs, es, e0, nenv, threadIdx.x, kPhysThreads);
+    // (first sub-step: the staged tables are still in flight, dof_link is read from the global copy)
+    const float* tab = s == 0 ? reinterpret_cast<const float*>(m.blob) : c.hot;
+    if (s == 0) slab_stage_state(m, b, tab, envs, es, e0, nenv, threadIdx.x, kPhysThreads);
     slab_stage_pre(m, b, s == 0 ? push : nullptr, envs, es, e0, nenv, threadIdx.x, kPhysThreads);
-    slab_stage_dofpar(m, b, c.hot, envs, es, e0, nenv, true, threadIdx.x, kPhysThreads);
+    slab_stage_dofpar(m, b, tab, envs, es, e0, nenv, true, threadIdx.x, kPhysThreads);
     cp_async_wait_all();
     __syncthreads();
     env_substep_role(io, c.sm, c.flags, s, c.hot, m, p, c.role, sync);
@@ -288,9 +290,10 @@ __global__ void __launch_bounds__(kStepThreads) k_step_physics(DevModel m, SimPa
   } else {
     // joint state, root and mass scales are staged once and then live in the scratch blocks for the whole launch; the
     // torque and noise stages read them there, and only the final state is written back
-    slab_stage_state(m, k.s, c.hot, envs, es, e0, nenv, threadIdx.x, kPhysThreads);
-    cp_async_wait_all();
+    // (the staged tables are still in flight: dof_link is read from the global copy here)
+    slab_stage_state(m, k.s, reinterpret_cast<const float*>(m.blob), envs, es, e0, nenv, threadIdx.x, kPhysThreads);
   }
+  cp_async_wait_all();  // this thread's share of the tables (and of the state)
   __syncthreads();
   int epoch = 0;
   for (int s = 0; s < k.p.skipframe; ++s) {
