@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kStepThreads) k_step_physics(DevModel m, SimPa
           io_mark(19);
         };
         if (actions && epoch == 0) {  // the policy-step prologue (T:449-502) of the CTA's envs; the push it decides
-                                      // is staged (F_IO_PRE) as soon as the per-env phase is through
+                                      // is staged (F_IO_PRE) at its end
           stage_prologue_slab(k, actions, e0, nenv, it, kIoThreads, pro, [] { io_group_sync(); }, stage_pre);
           io_group_sync();
         } else {

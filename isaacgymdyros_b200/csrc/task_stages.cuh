@@ -23,7 +23,9 @@ struct CubicKnots {
 __device__ __forceinline__ CubicKnots cubic_knots(float t0, float tf) {
   float tt = __fsub_rn(tf, t0);
   float tt2 = __fmul_rn(tt, tt);
-  return CubicKnots{t0, tf, tt2, __fmul_rn(tt2, tt), __fdiv_rn(0.0f, tt), __fdiv_rn(0.0f, tt2)};
+  // 0/x in IEEE arithmetic is a zero with the sign of x (NaN for x = 0 or NaN): no need to run a division for it
+  auto zero_over = [](float x) { return (x == 0.0f || x != x) ? __int_as_float(0x7fffffff) : copysignf(0.0f, x); };
+  return CubicKnots{t0, tf, tt2, __fmul_rn(tt2, tt), zero_over(tt), zero_over(tt2)};
 }
 __device__ __forceinline__ float cubic0(float time, const CubicKnots& kn, float x0, float xf) {
   float e = __fsub_rn(time, kn.t0);
@@ -122,8 +124,8 @@ __device__ __forceinline__ void stage_prologue(const TK& k, const float* __restr
 // warp-per-env form above is a serial chain of dependent loads per env; here the per-env scalars (phase time, mocap
 // row, knot times) are computed once by one thread per env and parked in `pro` (shared memory, 8 words per env), and
 // the (env, column) items of the cubic targets and of the action block then need one batch of independent loads each.
-// Same arithmetic, same bits. `group_sync` is a barrier of the cooperating threads; `after_env_phase` runs between
-// the per-env phase (which also holds the push schedule) and the item phases.
+// Same arithmetic, same bits. `group_sync` is a barrier of the cooperating threads; `after_env_phase` runs at the end,
+// after the push schedule (it stages the push).
 constexpr int kSlabMaxEnvs = 32;
 template <class GroupSync, class AfterEnvPhase>
 __device__ __forceinline__ void stage_prologue_slab(const TK& k, const float* __restrict__ actions_in, int e0, int nenv, int tid,
@@ -162,7 +164,6 @@ __device__ __forceinline__ void stage_prologue_slab(const TK& k, const float* __
     pro[tid][1] = __int_as_float(idx);
     const CubicKnots kn = cubic_knots(t0, tf);
     pro[tid][2] = kn.t0; pro[tid][3] = kn.tf; pro[tid][4] = kn.tt2; pro[tid][5] = kn.tt3; pro[tid][6] = kn.z1; pro[tid][7] = kn.z2;
-    stage_push_schedule(k, ee);                                                   // T:489-502
   }
 #pragma unroll
   for (int j = 0; j < IT_A; ++j) {
@@ -180,7 +181,6 @@ __device__ __forceinline__ void stage_prologue_slab(const TK& k, const float* __
   }
   group_sync();  // pro[] complete; every action item has read act_hist_head
   if (env_thread) k.b.act_hist_head[ee] = (head0 + 1) % NSLOT;
-  after_env_phase();
   // ---- third round trip: the columns of the two mocap rows, B (env, column) items per thread in flight
   constexpr int B = 4;
 #pragma unroll 1
@@ -207,6 +207,11 @@ __device__ __forceinline__ void stage_prologue_slab(const TK& k, const float* __
       }
     }
   }
+  // ---- the push schedule (T:489-502) last: nothing in the torque stage depends on it, and the role warps need the
+  //      staged push no earlier than the torques
+  if (env_thread) stage_push_schedule(k, ee);
+  group_sync();
+  after_env_phase();
 }
 
 // T:505-520: upper-body PD, actuation-delay ring, the 33 torques of set_dof_actuation_force_tensor.
