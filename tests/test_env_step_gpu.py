@@ -85,6 +85,38 @@ def test_fused_step_equals_staged_sequence_bitwise():
     a.close(); b.close()
 
 
+def test_prologue_physics_launch_equals_prologue_then_physics_bitwise():
+    """dyros_task_prologue_physics (the first launch of the fused step: the prologue runs on the I/O warps of the physics
+    kernel, restructured per slab) against dyros_task_prologue + dyros_task_physics, at a ragged size (N % 28 != 0)."""
+    N = 999
+    rng = np.random.default_rng(8)
+    a, b = make_core(N), make_core(N)
+    tables, mocap, obs_norm = load_assets()
+    s, _c = O.new_state(N, mocap, obs_norm, np.full(N, np.float32(tables.total_mass())), tables.dof_lower,
+                        tables.dof_upper, O.Params(), rng=rng)
+    s["time"][:] = rng.uniform(0, 30, N).astype(np.float32).reshape(s["time"].shape)  # spread over the mocap cycle
+    s["perturb_start"] = np.ones_like(s["perturb_start"])                            # push schedule active (T:492)
+    s["epi_len"][:] = rng.integers(0, 400, N).astype(np.float32).reshape(s["epi_len"].shape)
+    load_state(a, s)
+    load_state(b, s)
+    for t in range(3):
+        noise = O.draw_noise(N, 2, rng)
+        actions = torch.tensor(rng.uniform(-1.5, 1.5, (N, 13)).astype(np.float32), device=a.device)
+        inject_noise(a, noise)
+        inject_noise(b, noise)
+        a.prologue_physics(actions)
+        b.prologue(actions)
+        b.task_physics()
+        torch.cuda.synchronize()
+        ga, gb = read_state(a), read_state(b)
+        for k in ga:
+            assert np.array_equal(ga[k], gb[k], equal_nan=True), f"step {t}: {k} differs"
+        for x in (a, b):  # finish the step the same way on both
+            x.epilogue(); x.check_termination(); x.compute_reward(); x.compact_resets(); x.reset_idx(None)
+            x.compute_observations(); x.late_update(); x.end_step()
+    a.close(); b.close()
+
+
 def make_core(N, **kw):  # noqa: F811  (rb force tensors needed by the staged push path)
     from isaacgymdyros_b200.core import DyrosCore
     return DyrosCore(N, "cuda:0", CoreConfig(with_rb_force_tensors=True, **kw))
