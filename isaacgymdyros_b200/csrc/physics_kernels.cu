@@ -55,7 +55,10 @@ struct PhysCta {
 };
 
 // Common prologue of the physics kernels: stage the hot tables, clear the flags, locate the lane's env.
-__device__ __forceinline__ PhysCta phys_cta_setup(const DevModel& m, const SimParams& p, float* smem, int epb, int es) {
+// `flag_thread0`: first of the F_COUNT consecutive threads that clear the flags (the fused step lets its I/O group do
+// it, which is also the first to publish one).
+__device__ __forceinline__ PhysCta phys_cta_setup(const DevModel& m, const SimParams& p, float* smem, int epb, int es,
+                                                  int flag_thread0 = 0) {
   {  // 16-byte cp.async: in flight together with the state copies issued after griddepcontrol.wait (the caller waits)
     const char* src = reinterpret_cast<const char*>(m.blob);
     for (int i = threadIdx.x; i < m.hot_bytes / 16; i += blockDim.x)
@@ -63,7 +66,8 @@ __device__ __forceinline__ PhysCta phys_cta_setup(const DevModel& m, const SimPa
                    : "memory");
   }
   int* flags = reinterpret_cast<int*>(smem + m.hot_bytes / 4);
-  for (int i = threadIdx.x; i < F_COUNT; i += blockDim.x) flags[i] = 0;
+  static_assert(F_COUNT <= kPhysThreads, "one thread per flag");
+  if ((int)threadIdx.x >= flag_thread0 && (int)threadIdx.x < flag_thread0 + F_COUNT) flags[threadIdx.x - flag_thread0] = 0;
   pdl_launch_dependents();
   pdl_wait();  // everything above is independent of the previous kernel of the step (model tables only)
   PhysCta c;
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(kStepThreads) k_step_physics(DevModel m, SimPa
   extern __shared__ __align__(16) float smem[];
   __shared__ float pro[kSlabMaxEnvs][8];  // per-env scalars of the prologue (stage_prologue_slab)
   if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[24] = clock64();  // kernel entry (profiling)
-  PhysCta c = phys_cta_setup(m, p, smem, epb, es);
+  PhysCta c = phys_cta_setup(m, p, smem, epb, es, kPhysThreads);
   if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[25] = clock64();  // tables staged, previous kernel done
   const int e0 = blockIdx.x * epb, nenv = min(epb, p.N - e0);
   float* envs = smem + m.hot_bytes / 4 + ((F_COUNT + 3) & ~3);
@@ -279,47 +283,58 @@ __global__ void __launch_bounds__(kStepThreads) k_step_physics(DevModel m, SimPa
   // trace layout: [sub-step][role][32 marks]
   RoleSync sync{c.lane, (trace && blockIdx.x == 0 && !io_group) ? trace + role * 32 : nullptr};
   const int* dof_link = reinterpret_cast<const int*>(c.hot) + m.o_dof_link;
-  if (io_group) {  // with a cold L2, pull in what the torque and noise stages will read while the first staging is in flight
-    const size_t e = (size_t)e0;
-    slab_prefetch_l2(k.b.target_data_qpos + e * ND, (unsigned)nenv * ND * 4, it, kIoThreads);
-    slab_prefetch_l2(k.b.action_log + e * LOG_DEPTH * 12, (unsigned)nenv * LOG_DEPTH * 12 * 4, it, kIoThreads);
-    slab_prefetch_l2(k.b.action_torque + e * 12, (unsigned)nenv * 12 * 4, it, kIoThreads);
-    slab_prefetch_l2(k.b.qpos_pre + e * ND, (unsigned)nenv * ND * 4, it, kIoThreads);
-    slab_prefetch_l2(k.s.dof_damping + e * ND, (unsigned)nenv * ND * 4, it, kIoThreads);
-    slab_prefetch_l2(k.s.dof_armature + e * ND, (unsigned)nenv * ND * 4, it, kIoThreads);
+  // (profiling: marks 18.. of role 0's row are the I/O group's phase boundaries)
+  auto io_mark = [&](int s, int id) {
+    if (trace && blockIdx.x == 0 && it == 0) trace[(size_t)s * DYROS_LANES * 32 + id] = clock64();
+  };
+  // per sub-step, I/O group: the push (first sub-step of the policy step only, T:502 vs T:504) and the zeroed contact forces
+  auto stage_pre = [&](int s, int ss, int epoch) {
+    slab_stage_pre(m, k.s, (s == 0 && ss == 0) ? k.b.push_force : nullptr, envs, es, e0, nenv, it, kIoThreads);
+    cp_async_wait_all();
+    io_group_sync();
+    if (it == 0) st_release_shared(c.flags + F_IO_PRE, epoch + 1);
+    io_mark(s, 19);
+  };
+  // Start-up. The two groups do not meet at a full barrier: the I/O group arrives (non-blocking) at barrier 3 once its
+  // share of the model tables has landed and goes straight on to the prologue, which needs nothing from the role
+  // warps; the role warps stage the state and wait at barrier 3 for the tables; the I/O group waits for the staged
+  // state (barrier 4, where the role warps only arrive) before the first torque stage, which reads it.
+  if (io_group) {
+    {  // with a cold L2, pull in what the torque and noise stages will read
+      const size_t e = (size_t)e0;
+      slab_prefetch_l2(k.b.action_log + e * LOG_DEPTH * 12, (unsigned)nenv * LOG_DEPTH * 12 * 4, it, kIoThreads);
+      slab_prefetch_l2(k.b.qpos_pre + e * ND, (unsigned)nenv * ND * 4, it, kIoThreads);
+      slab_prefetch_l2(k.s.dof_damping + e * ND, (unsigned)nenv * ND * 4, it, kIoThreads);
+      slab_prefetch_l2(k.s.dof_armature + e * ND, (unsigned)nenv * ND * 4, it, kIoThreads);
+      if (!actions) {
+        slab_prefetch_l2(k.b.target_data_qpos + e * ND, (unsigned)nenv * ND * 4, it, kIoThreads);
+        slab_prefetch_l2(k.b.action_torque + e * 12, (unsigned)nenv * 12 * 4, it, kIoThreads);
+      }
+    }
+    cp_async_wait_all();  // this thread's share of the tables
+    asm volatile("bar.arrive 3, %0;" ::"n"(kStepThreads) : "memory");
+    io_mark(0, 18);
+    if (actions) {  // the policy-step prologue (T:449-502) of the CTA's envs; the push it decides is staged at its end
+      stage_prologue_slab(k, actions, e0, nenv, it, kIoThreads, pro, [] { io_group_sync(); }, [&] { stage_pre(0, 0, 0); });
+      io_group_sync();
+    }
+    asm volatile("bar.sync 4, %0;" ::"n"(kStepThreads) : "memory");
   } else {
     // joint state, root and mass scales are staged once and then live in the scratch blocks for the whole launch; the
     // torque and noise stages read them there, and only the final state is written back
     // (the staged tables are still in flight: dof_link is read from the global copy here)
     slab_stage_state(m, k.s, reinterpret_cast<const float*>(m.blob), envs, es, e0, nenv, threadIdx.x, kPhysThreads);
+    cp_async_wait_all();  // this thread's share of the tables and of the state
+    asm volatile("bar.sync 3, %0;" ::"n"(kStepThreads) : "memory");
+    asm volatile("bar.arrive 4, %0;" ::"n"(kStepThreads) : "memory");
   }
-  cp_async_wait_all();  // this thread's share of the tables (and of the state)
-  __syncthreads();
   int epoch = 0;
   for (int s = 0; s < k.p.skipframe; ++s) {
     for (int ss = 0; ss < p.substeps; ++ss, ++epoch) {
       if (io_group) {
-        // (profiling: marks 18.. of role 0's row are the I/O group's phase boundaries)
-        auto io_mark = [&](int id) {
-          if (trace && blockIdx.x == 0 && it == 0) trace[(size_t)s * DYROS_LANES * 32 + id] = clock64();
-        };
-        io_mark(18);
-        // the push acts on the first sub-step of the policy step only (T:502 vs T:504)
-        auto stage_pre = [&] {
-          slab_stage_pre(m, k.s, (s == 0 && ss == 0) ? k.b.push_force : nullptr, envs, es, e0, nenv, it, kIoThreads);
-          cp_async_wait_all();
-          io_group_sync();
-          if (it == 0) st_release_shared(c.flags + F_IO_PRE, epoch + 1);
-          io_mark(19);
-        };
-        if (actions && epoch == 0) {  // the policy-step prologue (T:449-502) of the CTA's envs; the push it decides
-                                      // is staged (F_IO_PRE) at its end
-          stage_prologue_slab(k, actions, e0, nenv, it, kIoThreads, pro, [] { io_group_sync(); }, stage_pre);
-          io_group_sync();
-        } else {
-          stage_pre();
-        }
-        io_mark(20);
+        if (epoch > 0) io_mark(s, 18);
+        if (!(actions && epoch == 0)) stage_pre(s, ss, epoch);  // (epoch 0 with a prologue: done above)
+        io_mark(s, 20);
         // damping / armature (and, after the first sub-step of a policy step, the unchanged torque) are copied while
         // the torque stage runs: the copies only touch their own slots
         slab_stage_dofpar(m, k.s, c.hot, envs, es, e0, nenv, ss > 0, it, kIoThreads);
@@ -328,11 +343,11 @@ __global__ void __launch_bounds__(kStepThreads) k_step_physics(DevModel m, SimPa
           io_group_sync();  // every thread has read simul_len
           stage_simul_len_update(torque_args(k), e0, nenv, it, kIoThreads);
         }
-        io_mark(21);
+        io_mark(s, 21);
         cp_async_wait_all();
         io_group_sync();
         if (it == 0) st_release_shared(c.flags + F_IO_TAU, epoch + 1);
-        io_mark(22);
+        io_mark(s, 22);
         // off the critical path: the sensor noise of the previous policy sub-step
         if (ss == 0 && s > 0) noise_stage_slab(noise_args(k), s - 1, e0, nenv, envs, es, dof_link, it, kIoThreads);
         io_group_sync();
