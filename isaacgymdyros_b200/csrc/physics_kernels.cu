@@ -39,9 +39,6 @@ struct RoleSync {
     while (ld_acquire_shared(f) < v) __nanosleep(100);
   }
 };
-struct CtaSync {
-  __device__ __forceinline__ void operator()() const { __syncthreads(); }
-};
 
 constexpr int kMaxPhysSmem = 227 * 1024 - 1024;  // dynamic part; 1 KiB is left for static shared memory (k_step_physics: 1 KiB)
 constexpr int kPhysThreads = DYROS_LANES * 32;

@@ -39,7 +39,7 @@ constexpr int LS_SC = 48;  // 4  [qd -> qd*, tau -> u, damping -> 1/D, armature 
 constexpr int LS_Q = 52;   // 1  joint angle
 constexpr int LS = 53;
 constexpr int LS_S = LS_E, LS_R = LS_E + 3;
-constexpr int A_PA = 0, A_POSE = 6, A_CIA = 0, A_CPA = 21, A_ACC = 0, A_OM0 = 6, A_ROWS = 6, A_G = 21;
+constexpr int A_POSE = 6, A_CIA = 0, A_CPA = 21, A_ACC = 0, A_OM0 = 6, A_ROWS = 6, A_G = 21;
 constexpr int ROWS_PER_LINK = 2;  // contact rows (7 floats each) parked in one leg-chain link's block
 // per-env extra scratch
 constexpr int X_FOOTPOSE = 0;                        // MAX_FEET * 12

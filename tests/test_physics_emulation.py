@@ -1,4 +1,4 @@
-"""CPU check of the CUDA physics kernel's algorithm: the kernel's lane program (physics_core.cuh, compiled for
+"""CPU check of the CUDA physics kernel's algorithm: the kernel's role program (physics_roles.cuh, compiled for
 the host, float32, O(n) articulated-body recursions) against the dense fp64 oracle (joint-space mass matrix).
 Two independent formulations of the same model must agree to float32 round-off on single-step state deltas."""
 import numpy as np
