@@ -349,6 +349,17 @@ __global__ void __launch_bounds__(kStepThreads) k_step_physics(DevModel m, SimPa
         if (ss == 0 && s > 0) noise_stage_slab(noise_args(k), s - 1, e0, nenv, envs, es, dof_link, it, kIoThreads);
         io_group_sync();
         if (it == 0) st_release_shared(c.flags + F_IO_DONE, epoch + 1);
+        if (s + 1 == k.p.skipframe && ss + 1 == p.substeps) {
+          // idle from here on: request the rows the post-physics launch will read and this launch never touched
+          // (history rings, previous-step copies), so that with a cold L2 it finds them in L2 instead of in HBM
+          const size_t e = (size_t)e0;
+          slab_prefetch_l2(k.b.obs_history + e * NSLOT * NOBS1, (unsigned)nenv * NSLOT * NOBS1 * 4, it, kIoThreads);
+          slab_prefetch_l2(k.b.action_history + e * NSLOT * NA, (unsigned)nenv * NSLOT * NA * 4, it, kIoThreads);
+          slab_prefetch_l2(k.b.contact_forces_pre + e * NB * 3, (unsigned)nenv * NB * 3 * 4, it, kIoThreads);
+          slab_prefetch_l2(k.b.pre_joint_velocity_states + e * ND, (unsigned)nenv * ND * 4, it, kIoThreads);
+          slab_prefetch_l2(k.b.actions_pre + e * NA, (unsigned)nenv * NA * 4, it, kIoThreads);
+          slab_prefetch_l2(k.b.qpos_bias + e * 12, (unsigned)nenv * 12 * 4, it, kIoThreads);
+        }
       } else {
         io.push = (s == 0 && ss == 0) ? k.b.push_force : nullptr;
         sync.mark(13);
