@@ -10,7 +10,8 @@ termination + reward + reset + observations. Envs shard across ranks
 (weak scaling: 4096 envs per GPU); NCCL is used for the barrier, the max-over-ranks timing and the episode statistics.
 
 Prints ONE JSON line (rank 0). `value` is device-resident throughput with the L2 flushed between timed steps;
-`e2e` goes through DyrosDynamicWalk.step with pinned HOST buffers (actions H2D, obs/reward/reset D2H every step).
+`e2e` goes through DyrosDynamicWalk.step with pinned HOST buffers (actions read from pinned host memory by the step's
+first kernel, obs/reward/reset D2H every step).
 `--impl reference` times the CPU oracle port (oracle/env_oracle.py) on the host cores: the reference's own physics
 is closed-source PhysX whose binaries are absent from the checkout, so the "reference arm" is the port.
 """
@@ -235,7 +236,8 @@ def run_ours(a):
         barrier()
         e0.record()
         for i in range(K):
-            obs, rew, rst, _ = env.step(h_act[i % len(h_act)].to(dev, non_blocking=True))
+            # the pinned host tensor goes to the public API as it is: the first kernel of the step reads it over PCIe
+            obs, rew, rst, _ = env.step(h_act[i % len(h_act)])
             h_obs.copy_(obs["obs"], non_blocking=True)
             h_rew.copy_(rew, non_blocking=True)
             h_rst.copy_(rst, non_blocking=True)

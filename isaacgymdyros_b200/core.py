@@ -302,9 +302,11 @@ class DyrosCore:
                      "dyros_task_set_noise_injection")
 
     def _actions_ptr(self, actions: torch.Tensor):
-        if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous() \
-                or tuple(actions.shape) != (self.N, NA):
-            raise native.DyrosError(f"actions must be a contiguous float32 ({self.N},{NA}) tensor on {self.device}")
+        # a pinned host tensor is read by the kernel directly over PCIe (unified addressing: same pointer on the device)
+        on_dev = actions.device == self.device or (actions.device.type == "cpu" and actions.is_pinned())
+        if not on_dev or actions.dtype != torch.float32 or not actions.is_contiguous() or tuple(actions.shape) != (self.N, NA):
+            raise native.DyrosError(f"actions must be a contiguous float32 ({self.N},{NA}) tensor on {self.device} "
+                                    f"or in pinned host memory")
         return C.c_void_p(actions.data_ptr())
 
     def step(self, actions: torch.Tensor):

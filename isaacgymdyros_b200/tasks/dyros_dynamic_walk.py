@@ -182,12 +182,18 @@ class DyrosDynamicWalk:
     # ------------------------------------------------------------------ step / reset (VT:293-374)
     def step(self, actions: torch.Tensor):
         """VT:293-344: returns (obs_dict, rew_buf, reset_buf, extras); tensors are the env's own buffers."""
-        self._actions_static.copy_(actions.to(self.device), non_blocking=True)
-        if self._use_graph:
+        if actions.device.type == "cpu" and actions.is_pinned() and actions.dtype == torch.float32 and actions.is_contiguous():
+            # host-side policy: the first kernel reads the actions straight from the pinned buffer (no staging copy, no
+            # graph: the pointer differs per call); the caller keeps the tensor alive and unchanged until the step has
+            # run, as with every tensor handed to the reference's gym setters (DOCT:348-369)
+            self.core.step(actions)
+        elif self._use_graph:
+            self._actions_static.copy_(actions, non_blocking=True)
             if self._graph is None:
                 self._capture()
             self._graph.replay()
         else:
+            self._actions_static.copy_(actions, non_blocking=True)
             self.core.step(self._actions_static)
         self.extras["time_outs"] = self.timeout_buf.to(self.rl_device)
         self.extras["stacked_rewards"] = self.stacked_rewards

@@ -153,6 +153,23 @@ def test_vectask_api_rollout_properties_full_size():
     env.close()
 
 
+def test_step_reads_pinned_host_actions_like_device_actions():
+    """A pinned host tensor handed to step() is read by the first kernel directly (no staging copy, no graph): same
+    results, bit for bit, as the same actions on the device (CUDA-graph replay path)."""
+    from isaacgymdyros_b200 import DyrosDynamicWalk, default_cfg
+    N = 300
+    a, b = DyrosDynamicWalk(default_cfg(N), "cuda:0"), DyrosDynamicWalk(default_cfg(N), "cuda:0")
+    g = torch.Generator(device="cpu"); g.manual_seed(5)
+    for t in range(6):
+        act = (torch.rand(N, 13, generator=g) * 2 - 1).pin_memory()
+        oa, ra, sa, _ = a.step(act.to("cuda:0"))
+        ob, rb, sb, _ = b.step(act)
+        torch.cuda.synchronize()
+        assert torch.equal(oa["obs"], ob["obs"]) and torch.equal(ra, rb) and torch.equal(sa, sb), f"step {t}"
+    assert torch.equal(a.root_states, b.root_states) and torch.equal(a.dof_state, b.dof_state)
+    a.close(); b.close()
+
+
 def test_domain_randomisation_redraw_on_reset_ranges():
     from isaacgymdyros_b200 import DyrosDynamicWalk, default_cfg
     from isaacgymdyros_b200.core import ARMATURE
