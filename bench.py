@@ -53,13 +53,43 @@ def parse():
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML from a thread every 5 ms (nvidia_ml_py), so
+    that even a 30 ms region gets samples; `nvidia-smi -lms` as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.stop = index, [], None, False
+
+    def _nvml_loop(self):
+        import pynvml as nv
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        bits = [(0x8, 3), (0x40, 4), (0x20, 5), (0x4, 6)]  # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap (NVML reason bits)
+        while not self.stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:  # noqa: BLE001  (older bindings)
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                row = [str(sm), str(mx), "", "", "", "", ""]
+                for bit, col in bits:
+                    row[col] = "Active" if rs & bit else "Not Active"
+                self.rows.append(row)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.005)
 
     def __enter__(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return self
+        except Exception:  # noqa: BLE001
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -74,6 +104,7 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *exc):
+        self.stop = True
         if self.proc:
             self.proc.terminate()
             try:
