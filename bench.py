@@ -10,8 +10,9 @@ termination + reward + reset + observations. Envs shard across ranks
 (weak scaling: 4096 envs per GPU); NCCL is used for the barrier, the max-over-ranks timing and the episode statistics.
 
 Prints ONE JSON line (rank 0). `value` is device-resident throughput with the L2 flushed between timed steps;
-`e2e` goes through DyrosDynamicWalk.step with pinned HOST buffers (actions read from pinned host memory by the step's
-first kernel, obs/reward/reset D2H every step).
+`e2e` goes through DyrosDynamicWalk.step_async / step_wait with pinned HOST buffers (actions read from pinned host memory
+by the step's first kernel; obs / reward / reset / time_outs packed and moved device->host every step on a copy stream,
+overlapping the next step's kernels); `e2e_sync` is DyrosDynamicWalk.step + copies on one stream, nothing overlapped.
 `--impl reference` times the CPU oracle port (oracle/env_oracle.py) on the host cores: the reference's own physics
 is closed-source PhysX whose binaries are absent from the checkout, so the "reference arm" is the port.
 """
@@ -274,9 +275,27 @@ def run_ours(a):
             h_rst.copy_(rst, non_blocking=True)
         e1.record()
         barrier()
+        e2e_sync_ms = e0.elapsed_time(e1)
+        # ---- (3b) the same through step_async / step_wait: results packed into one block by dyros_task_pack_results,
+        #           ONE device->host transfer per step on a copy stream, two steps in flight, the host consumes (waits
+        #           for) the results of step i-1 right after submitting step i
+        tick = env.step_async(h_act[0])
+        env.step_wait(tick)
+        cs = env._pipe.copy_stream
+        barrier()
+        e0.record()
+        for i in range(K):
+            nxt = env.step_async(h_act[i % len(h_act)])
+            if i > 0:
+                env.step_wait(tick)
+            tick = nxt
+        env.step_wait(tick)
+        torch.cuda.current_stream().wait_stream(cs)
+        e1.record()
+        barrier()
         e2e_ms = e0.elapsed_time(e1)
     clocks = clk.summary()
-    h2d, d2h = N * 13 * 4, N * 487 * 4 + N * 4 + N * 8
+    h2d, d2h = N * 13 * 4, env.core.result_bytes()
     # ---- (4) the dominant kernel alone (k_step_physics = 2 x (torque, physics sub-step, noise) in one launch), inside
     #          real staged steps, L2 flushed before each launch
     KS = min(K, 50)
@@ -296,7 +315,7 @@ def run_ours(a):
     reset_rate = float(env.reset_buf.float().mean().item())
 
     from isaacgymdyros_b200.sharding import max_over_ranks, reduce_episode_stats
-    cold_ms, warm_ms, e2e_ms, k1_ms = (max_over_ranks(x, dev) for x in (cold_ms, warm_ms, e2e_ms, k1_ms))
+    cold_ms, warm_ms, e2e_ms, e2e_sync_ms, k1_ms = (max_over_ranks(x, dev) for x in (cold_ms, warm_ms, e2e_ms, e2e_sync_ms, k1_ms))
     # episode statistics across ranks (the only data the env path ever reduces)
     stats = reduce_episode_stats({"epi_len_log": env.epi_len_log, "contact_reward_mean": env.contact_reward_mean})
     if rank == 0:
@@ -322,7 +341,12 @@ def run_ours(a):
                        "launch_geometry": dict(core.launch_info(), threads_per_cta_fused_step=256), "reset_rate_last_step": reset_rate},
             "clocks": clocks,
             "e2e": {"value": total_envs * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K,
+                    "api": "DyrosDynamicWalk.step_async / step_wait: pinned host actions in, one packed pinned host block "
+                           "(obs, rew, reset, time_outs) out per step; the transfer of step k overlaps the kernels of step k+1"},
+            "e2e_sync": {"value": total_envs * K / (e2e_sync_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_sync_ms / K,
+                         "d2h_bytes_per_step": N * 487 * 4 + N * 4 + N * 8,
+                         "api": "DyrosDynamicWalk.step + three device->host copies on the same stream, nothing overlapped"},
             "gpu_launches": K * core.step_launches(),
             "value_warm_l2": total_envs * K / (warm_ms * 1e-3), "ms_per_step_warm_l2": warm_ms / K,
             "roofline": {"bound": "hbm", "kernel": "k_step_physics (2 x (PD/delay torque, physics sub-step, sensor noise) of all envs, one launch)",

@@ -239,8 +239,16 @@ int dyros_task_late_update(DyrosTask* task, void* stream);                      
 int dyros_task_end_step(DyrosTask* task, void* stream);
 /* Whole VecTask.step (VT:293-344) in the fewest launches; same results as the staged calls. */
 int dyros_task_step(DyrosTask* task, const float* actions, void* stream);
+/* The launches of dyros_task_step after dyros_task_prologue_physics, on their own (T:532-563 fused + the cross-env
+ * pass): dyros_task_prologue_physics followed by dyros_task_post_step is dyros_task_step. */
+int dyros_task_post_step(DyrosTask* task, void* stream);
 /* Number of kernel launches dyros_task_step enqueues (for bench.py's gpu_launches). */
 int dyros_task_step_launches(DyrosTask* task);
+/* What VecTask.step returns (VT:336-344: obs_dict["obs"], rew_buf, reset_buf, extras["time_outs"]) gathered into ONE
+ * contiguous device block `dst` of N*(487*4 + 4 + 8 + 8) bytes, 16-byte aligned:
+ * obs (N,487) f32 | rew (N) f32 | reset (N) i64 | time_outs (N) i64. A host-side
+ * caller then moves the block with a single device->host copy on its own stream while the next step runs. */
+int dyros_task_pack_results(DyrosTask* task, void* dst, void* stream);
 
 #ifdef __cplusplus
 }

@@ -313,6 +313,15 @@ class DyrosCore:
         """Whole VecTask.step (VT:293-344) as dyros_task_step."""
         native.check(self.lib.dyros_task_step(self.task_handle, self._actions_ptr(actions), self._stream), "dyros_task_step")
 
+    def pack_results(self, dst: torch.Tensor):
+        """obs | rew | reset | time_outs of the last step into one contiguous device block (dyros_task_pack_results)."""
+        if dst.device != self.device or not dst.is_contiguous() or dst.numel() * dst.element_size() < self.result_bytes():
+            raise native.DyrosError(f"pack_results needs a contiguous block of {self.result_bytes()} bytes on {self.device}")
+        native.check(self.lib.dyros_task_pack_results(self.task_handle, C.c_void_p(dst.data_ptr()), self._stream), "dyros_task_pack_results")
+
+    def result_bytes(self) -> int:
+        return self.N * (487 * 4 + 4 + 8 + 8)
+
     def step_launches(self) -> int:
         return int(self.lib.dyros_task_step_launches(self.task_handle))
 
@@ -352,6 +361,10 @@ class DyrosCore:
                                                           C.c_void_p(buf.data_ptr()) if trace else None, self._stream),
                      "prologue_physics")
         return buf
+
+    def post_step(self):
+        """The launches of `step` after `prologue_physics` (fused post-physics kernel + cross-env pass)."""
+        native.check(self.lib.dyros_task_post_step(self.task_handle, self._stream), "dyros_task_post_step")
 
     def substep_torque(self):
         native.check(self.lib.dyros_task_substep_torque(self.task_handle, self._stream), "substep_torque")

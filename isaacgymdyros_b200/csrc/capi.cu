@@ -362,9 +362,23 @@ int dyros_task_step(DyrosTask* task, const float* actions, void* stream) {
   if (launch_post_fused(t, st, true)) return 1;
   return launch_crossenv(t, true, true, true, st, true);
 }
+int dyros_task_post_step(DyrosTask* task, void* stream) {
+  TASK_OR_FAIL("dyros_task_post_step");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (launch_post_fused(t, st, true)) return 1;
+  return launch_crossenv(t, true, true, true, st, true);
+}
 int dyros_task_step_launches(DyrosTask* task) {
   TASK_OR_FAIL("dyros_task_step_launches");
   return 3;  // prologue + fused physics, fused post-physics, cross-env
+}
+int dyros_task_pack_results(DyrosTask* task, void* dst, void* stream) {
+  TASK_OR_FAIL("dyros_task_pack_results");
+  if (!dst || (reinterpret_cast<uintptr_t>(dst) & 15)) {
+    set_error("dyros_task_pack_results: dst is NULL or not 16-byte aligned");
+    return 1;
+  }
+  return launch_pack_results(t, static_cast<float*>(dst), (cudaStream_t)stream);
 }
 
 }  // extern "C"

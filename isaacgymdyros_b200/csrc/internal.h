@@ -138,6 +138,7 @@ int launch_reset_idx(Task* t, const int64_t* env_ids, int count, cudaStream_t s)
 int launch_compute_observations(Task* t, cudaStream_t s);
 int launch_late_update(Task* t, cudaStream_t s);
 int launch_post_fused(Task* t, cudaStream_t s, bool pdl = false);
+int launch_pack_results(Task* t, float* dst, cudaStream_t s);
 // launchers (physics_kernels.cu)
 int physics_configure(Sim* sim);  // chooses envs_per_block / shared memory, sets the kernel attributes
 int launch_simulate(Sim* sim, int apply_wrench, const float* push_force, cudaStream_t s);

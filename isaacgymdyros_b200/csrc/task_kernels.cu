@@ -546,6 +546,41 @@ __global__ void __launch_bounds__(kScanThreads) k_crossenv(TK k, int do_compact,
   }
 }
 
+
+// ------------------------------------------------------------------ results of a step -> one contiguous block
+// Layout of `dst`: obs (N,487) f32 | rew (N) f32 | reset (N) i64 | time_outs (N) i64 (the i64 part starts at
+// N*488*4, a multiple of 8). The host-facing
+// step (DyrosDynamicWalk.step_async) hands this block to the copy engine as ONE device->host transfer on a second
+// stream, so the next step may overwrite obs_buf / rew_buf / reset_buf / timeout_buf (VT:336-344) while the block is still in flight.
+__global__ void __launch_bounds__(256) k_pack_results(TK k, float* __restrict__ dst) {
+  const int N = k.p.N;
+  const size_t n_obs = (size_t)N * 487;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  const size_t n4 = n_obs / 4;  // obs_buf and dst are 16-byte aligned (torch allocations)
+  const float4* src4 = reinterpret_cast<const float4*>(k.b.obs_buf);
+  float4* dst4 = reinterpret_cast<float4*>(dst);
+  // Both sides of this copy are touched once per step: L2 evict-first, so that the 16 MB streamed here do not push
+  // the env state of the next step's first kernel out of L2 (measured: plain loads / stores cost the next step 75 us,
+  // with the hints 50 us, profiles/r1j_step_async.txt)
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  for (size_t i = tid; i < n4; i += nth) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src4 + i), "l"(pol));
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+                 ::"l"(dst4 + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+  }
+  for (size_t i = n4 * 4 + tid; i < n_obs; i += nth) dst[i] = k.b.obs_buf[i];
+  float* rew = dst + n_obs;
+  long long* rst = reinterpret_cast<long long*>(dst + n_obs + N);
+  for (size_t e = tid; e < (size_t)N; e += nth) {
+    rew[e] = k.b.rew_buf[e];
+    rst[e] = k.b.reset_buf[e];
+    rst[N + e] = k.b.timeout_buf[e];
+  }
+}
+
 // ------------------------------------------------------------------ launchers
 static inline TK make_tk(Task* t) {
   TK k;
@@ -578,6 +613,12 @@ int launch_reset_idx(Task* t, const int64_t* env_ids, int count, cudaStream_t s)
   const int64_t* ids = env_ids ? env_ids : t->b.reset_env_ids;
   int n = count >= 0 ? count : t->p.N;
   k_reset_idx<<<env_grid(n), kWarpsPerBlock * 32, 0, s>>>(make_tk(t), ids, count);
+  DY_LAUNCH_CHECK();
+  return 0;
+}
+int launch_pack_results(Task* t, float* dst, cudaStream_t s) {
+  // a multiple of the SM count; 8 MB at N = 4096: ~13 float4 per thread
+  k_pack_results<<<148 * 4, 256, 0, s>>>(make_tk(t), dst);
   DY_LAUNCH_CHECK();
   return 0;
 }

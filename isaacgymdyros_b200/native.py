@@ -117,6 +117,8 @@ SIGNATURES = {
     "dyros_task_end_step": (_INT, [_VP, _VP]),
     "dyros_task_step": (_INT, [_VP, _VP, _VP]),
     "dyros_task_step_launches": (_INT, [_VP]),
+    "dyros_task_post_step": (_INT, [_VP, _VP]),
+    "dyros_task_pack_results": (_INT, [_VP, _VP, _VP]),
 }
 
 

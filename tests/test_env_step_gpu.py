@@ -170,6 +170,41 @@ def test_step_reads_pinned_host_actions_like_device_actions():
     a.close(); b.close()
 
 
+def test_step_async_pipeline_returns_the_results_of_step_in_host_memory():
+    """step_async / step_wait (two steps in flight, one packed D2H block per step on a copy stream) must hand back,
+    bit for bit and in order, what the synchronous step() of a twin env returns; tickets out of the window raise."""
+    from isaacgymdyros_b200 import DyrosDynamicWalk, default_cfg
+    N = 301  # odd: N*487 is not a multiple of 4 (scalar tail of the pack kernel)
+    a, b = DyrosDynamicWalk(default_cfg(N), "cuda:0"), DyrosDynamicWalk(default_cfg(N), "cuda:0")
+    for e in (a, b):  # episode ends inside the rollout: reset and (progress already at the limit, VT:325) time_outs non-zero
+        e.progress_buf[:4] = 7999
+        e.progress_buf[4:7] = 7996
+    g = torch.Generator(device="cpu"); g.manual_seed(6)
+    acts = [(torch.rand(N, 13, generator=g) * 2 - 1).pin_memory() for _ in range(7)]
+    want = []
+    for act in acts:
+        o, r, s, ex = a.step(act)
+        torch.cuda.synchronize()
+        want.append((o["obs"].cpu().clone(), r.cpu().clone(), s.cpu().clone(), ex["time_outs"].cpu().clone()))
+    assert any(w[3].any() for w in want) and any(w[2].any() for w in want)
+    tickets = []
+    for t, act in enumerate(acts):
+        tickets.append(b.step_async(act if t % 2 == 0 else act.to("cuda:0")))  # pinned-host and device actions alike
+        if t >= 1:
+            o, r, s, ex = b.step_wait(tickets[t - 1])
+            assert not o["obs"].is_cuda and o["obs"].is_pinned()
+            w = want[t - 1]
+            assert torch.equal(o["obs"], w[0]) and torch.equal(r, w[1]) and torch.equal(s, w[2]), f"step {t - 1}"
+            assert torch.equal(ex["time_outs"], w[3]), f"step {t - 1}"
+    o, r, s, ex = b.step_wait(tickets[-1])
+    assert torch.equal(o["obs"], want[-1][0]) and torch.equal(s, want[-1][2])
+    with pytest.raises(RuntimeError):
+        b.step_wait(tickets[0])
+    with pytest.raises(RuntimeError):
+        b.step_wait(len(acts))
+    a.close(); b.close()
+
+
 def test_large_ragged_shard_runs_multi_wave():
     """20,001 envs (715 CTAs of 28 envs: five waves on 148 SMs, last CTA ragged; state beyond the L2): finite outputs and
     exact reset bookkeeping, and env 0 evolves exactly as in a 4096-env shard stepped with the same actions (envs are
