@@ -277,19 +277,20 @@ def run_ours(a):
         barrier()
         e2e_sync_ms = e0.elapsed_time(e1)
         # ---- (3b) the same through step_async / step_wait: results packed into one block by dyros_task_pack_results,
-        #           ONE device->host transfer per step on a copy stream, two steps in flight, the host consumes (waits
-        #           for) the results of step i-1 right after submitting step i
+        #           ONE device->host transfer per step on a copy stream, three steps in flight, the host consumes (waits
+        #           for) the results of step i-2 right after submitting step i
         tick = env.step_async(h_act[0])
         env.step_wait(tick)
         cs = env._pipe.copy_stream
         barrier()
         e0.record()
+        ticks = []
         for i in range(K):
-            nxt = env.step_async(h_act[i % len(h_act)])
-            if i > 0:
-                env.step_wait(tick)
-            tick = nxt
-        env.step_wait(tick)
+            ticks.append(env.step_async(h_act[i % len(h_act)]))
+            if len(ticks) == 3:  # three steps in flight: consume the oldest
+                env.step_wait(ticks.pop(0))
+        for tick in ticks:
+            env.step_wait(tick)
         torch.cuda.current_stream().wait_stream(cs)
         e1.record()
         barrier()

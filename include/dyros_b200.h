@@ -249,6 +249,10 @@ int dyros_task_step_launches(DyrosTask* task);
  * obs (N,487) f32 | rew (N) f32 | reset (N) i64 | time_outs (N) i64. A host-side
  * caller then moves the block with a single device->host copy on its own stream while the next step runs. */
 int dyros_task_pack_results(DyrosTask* task, void* dst, void* stream);
+/* Re-points the observation buffer (DyrosTaskBuffers.obs_buf, (N,487) f32, 16-byte aligned) for the launches enqueued
+ * from now on; launches already enqueued or captured in a CUDA graph keep the pointer they were given. With obs_buf
+ * set to a result block, dyros_task_pack_results on that block only adds rew / reset / time_outs. */
+int dyros_task_set_obs_buf(DyrosTask* task, float* obs_buf);
 
 #ifdef __cplusplus
 }

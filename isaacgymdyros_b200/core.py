@@ -319,6 +319,13 @@ class DyrosCore:
             raise native.DyrosError(f"pack_results needs a contiguous block of {self.result_bytes()} bytes on {self.device}")
         native.check(self.lib.dyros_task_pack_results(self.task_handle, C.c_void_p(dst.data_ptr()), self._stream), "dyros_task_pack_results")
 
+    def set_obs_buf(self, obs: torch.Tensor):
+        """Observation buffer of the launches enqueued from now on (dyros_task_set_obs_buf); `obs` may be the head of a
+        result block, pack_results on that block then only adds rew / reset / time_outs."""
+        if obs.device != self.device or not obs.is_contiguous() or obs.numel() * obs.element_size() < self.N * 487 * 4:
+            raise native.DyrosError(f"set_obs_buf needs a contiguous block of {self.N * 487 * 4} bytes on {self.device}")
+        native.check(self.lib.dyros_task_set_obs_buf(self.task_handle, C.c_void_p(obs.data_ptr())), "dyros_task_set_obs_buf")
+
     def result_bytes(self) -> int:
         return self.N * (487 * 4 + 4 + 8 + 8)
 

@@ -372,6 +372,15 @@ int dyros_task_step_launches(DyrosTask* task) {
   TASK_OR_FAIL("dyros_task_step_launches");
   return 3;  // prologue + fused physics, fused post-physics, cross-env
 }
+int dyros_task_set_obs_buf(DyrosTask* task, float* obs_buf) {
+  TASK_OR_FAIL("dyros_task_set_obs_buf");
+  if (!obs_buf || (reinterpret_cast<uintptr_t>(obs_buf) & 15)) {
+    set_error("dyros_task_set_obs_buf: obs_buf is NULL or not 16-byte aligned");
+    return 1;
+  }
+  t->b.obs_buf = obs_buf;
+  return 0;
+}
 int dyros_task_pack_results(DyrosTask* task, void* dst, void* stream) {
   TASK_OR_FAIL("dyros_task_pack_results");
   if (!dst || (reinterpret_cast<uintptr_t>(dst) & 15)) {

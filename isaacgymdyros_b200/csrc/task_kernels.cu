@@ -559,19 +559,21 @@ __global__ void __launch_bounds__(256) k_pack_results(TK k, float* __restrict__ 
   const size_t n4 = n_obs / 4;  // obs_buf and dst are 16-byte aligned (torch allocations)
   const float4* src4 = reinterpret_cast<const float4*>(k.b.obs_buf);
   float4* dst4 = reinterpret_cast<float4*>(dst);
-  // Both sides of this copy are touched once per step: L2 evict-first, so that the 16 MB streamed here do not push
-  // the env state of the next step's first kernel out of L2 (measured: plain loads / stores cost the next step 75 us,
-  // with the hints 50 us, profiles/r1j_step_async.txt)
-  unsigned long long pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  for (size_t i = tid; i < n4; i += nth) {
-    float4 v;
-    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src4 + i), "l"(pol));
-    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
-                 ::"l"(dst4 + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+  if (k.b.obs_buf != dst) {  // (dyros_task_set_obs_buf(dst): the observation kernel has written the block itself)
+    // Both sides of this copy are touched once per step: L2 evict-first, so that the 16 MB streamed here do not linger
+    // in L2 at the expense of the env state (measured: plain loads / stores cost the next step 75 us, with the hints
+    // 50 us; the pipelined host step therefore avoids this branch altogether, profiles/r1j_step_async.txt)
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    for (size_t i = tid; i < n4; i += nth) {
+      float4 v;
+      asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                   : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src4 + i), "l"(pol));
+      asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+                   ::"l"(dst4 + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+    }
+    for (size_t i = n4 * 4 + tid; i < n_obs; i += nth) dst[i] = k.b.obs_buf[i];
   }
-  for (size_t i = n4 * 4 + tid; i < n_obs; i += nth) dst[i] = k.b.obs_buf[i];
   float* rew = dst + n_obs;
   long long* rst = reinterpret_cast<long long*>(dst + n_obs + N);
   for (size_t e = tid; e < (size_t)N; e += nth) {

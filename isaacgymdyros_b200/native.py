@@ -119,6 +119,7 @@ SIGNATURES = {
     "dyros_task_step_launches": (_INT, [_VP]),
     "dyros_task_post_step": (_INT, [_VP, _VP]),
     "dyros_task_pack_results": (_INT, [_VP, _VP, _VP]),
+    "dyros_task_set_obs_buf": (_INT, [_VP, _VP]),
 }
 
 

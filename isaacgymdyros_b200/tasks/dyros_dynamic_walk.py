@@ -209,16 +209,17 @@ class DyrosDynamicWalk:
         Enqueues VT:293-344 for `actions` (pinned host or device tensor), gathers what `step` returns
         (obs_dict["obs"], rew_buf, reset_buf, extras["time_outs"]: VT:336-344) into one device block (dyros_task_pack_results) and hands that
         block to the copy engine on a second stream as ONE device->host transfer into pinned memory. Returns a ticket
-        for `step_wait`. Two tickets may be in flight: the transfer of step k overlaps the kernels of step k+1, so a
+        for `step_wait`. Three tickets may be in flight: the transfer of step k overlaps the kernels of step k+1, so a
         rollout whose actions do not wait for the newest observation runs at max(kernels, PCIe) instead of their sum.
-        Nothing here synchronises the host."""
+        `self.obs_buf` is not updated by these steps (the observation kernel writes the ticket's block directly); rew_buf,
+        reset_buf and the state tensors are. The only host wait is for the slot of step k-3 to be free again."""
         if self._pipe is None:
             self._pipe = _HostPipe(self)
         return self._pipe.submit(actions)
 
     def step_wait(self, ticket: int):
         """Blocks until the results of `ticket` are in host memory; returns (obs_dict, rew, reset, extras) as pinned
-        host tensors, valid until two further `step_async` calls have been made."""
+        host tensors, valid until three further `step_async` calls have been made."""
         if self._pipe is None:
             raise RuntimeError("step_wait without step_async")
         return self._pipe.wait(ticket)
@@ -310,7 +311,7 @@ class _HostPipe:
     block and ONE CUDA graph (dyros_task_step reading the slot's action buffer + dyros_task_pack_results into the slot's
     block); a copy stream carries the device->host transfers. Launching the step's kernels one by one from Python costs
     more host time (~180 us) than the kernels run (~105 us), hence the graphs."""
-    DEPTH = 2
+    DEPTH = 3
 
     def __init__(self, env: DyrosDynamicWalk):
         self.env, N = env, env.num_envs
@@ -329,9 +330,19 @@ class _HostPipe:
 
     def _run(self, slot: int, src: torch.Tensor, kind: str):
         env = self.env
+
+        def launches():
+            # the observation kernel writes the slot's block itself (no copy of the 8 MB by another kernel, which would
+            # cost the next step's first kernel its L2-resident state); env.obs_buf is not updated by these steps
+            env.core.set_obs_buf(self.dev[slot])
+            try:
+                env.core.step(src)
+                env.core.pack_results(self.dev[slot])
+            finally:
+                env.core.set_obs_buf(env.obs_buf)
+
         if not env._use_graph:
-            env.core.step(src)
-            env.core.pack_results(self.dev[slot])
+            launches()
             return
         g = self.graphs.get((slot, kind))
         if g is None:
@@ -340,8 +351,7 @@ class _HostPipe:
             side.wait_stream(torch.cuda.current_stream(env.device))
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=side):
-                env.core.step(src)
-                env.core.pack_results(self.dev[slot])
+                launches()
             self.graphs[(slot, kind)] = g
         g.replay()
 
@@ -350,7 +360,7 @@ class _HostPipe:
         slot = k % self.DEPTH
         cur = torch.cuda.current_stream(env.device)
         if k >= self.DEPTH:
-            # step k-2 used this slot: its kernels have read h_actions[slot] and its block has left the device
+            # step k-DEPTH used this slot: its kernels have read h_actions[slot] and its block has left the device
             self.landed[slot].synchronize()
         if actions.device.type == "cpu":
             self.h_actions[slot].copy_(actions)  # host memcpy (213 KB at N = 4096); the step's first kernel reads it over PCIe

@@ -171,7 +171,7 @@ def test_step_reads_pinned_host_actions_like_device_actions():
 
 
 def test_step_async_pipeline_returns_the_results_of_step_in_host_memory():
-    """step_async / step_wait (two steps in flight, one packed D2H block per step on a copy stream) must hand back,
+    """step_async / step_wait (up to three steps in flight, one D2H block per step on a copy stream) must hand back,
     bit for bit and in order, what the synchronous step() of a twin env returns; tickets out of the window raise."""
     from isaacgymdyros_b200 import DyrosDynamicWalk, default_cfg
     N = 301  # odd: N*487 is not a multiple of 4 (scalar tail of the pack kernel)
@@ -199,9 +199,9 @@ def test_step_async_pipeline_returns_the_results_of_step_in_host_memory():
     o, r, s, ex = b.step_wait(tickets[-1])
     assert torch.equal(o["obs"], want[-1][0]) and torch.equal(s, want[-1][2])
     with pytest.raises(RuntimeError):
-        b.step_wait(tickets[0])
+        b.step_wait(tickets[0])  # its slot has been reused
     with pytest.raises(RuntimeError):
-        b.step_wait(len(acts))
+        b.step_wait(len(acts))   # not submitted yet
     a.close(); b.close()
 
 
