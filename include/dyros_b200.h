@@ -98,6 +98,8 @@ typedef struct {
   float* dof_damping;        /* (N,nd) per-env dof_prop['damping']  T:365 + DR */
   float* dof_armature;       /* (N,nd) per-env dof_prop['armature'] T:366-371 + DR */
   float* body_mass_scale;    /* (N,nb) per-env rigid_body_properties.mass scaling (setup-only DR) */
+  float* contact_friction;   /* (N) per-env friction coefficient of the ground contacts, replaces DyrosSimDesc.friction
+                                (DR of rigid_shape_properties.friction, DyrosDynamicWalk.yaml:89-96); may be NULL */
 } DyrosSimBuffers;
 
 /* Per-env task state (names = the reference attributes, T:87-195; internal integers are int32). */
@@ -158,6 +160,8 @@ typedef struct {
   const float* mocap_data;   /* (3600,36) T:112-113 */
   const float* obs_mean;     /* (37) */
   const float* obs_var;      /* (37) */
+  float* pd_gain_scale;      /* (N,2) per-env scale of Kp, Kv in the upper-body PD of T:506 (DR of the PD gains,
+                                BASELINE configs[3]; the reference has no such table: NULL = gains as in T:58-70) */
 } DyrosTaskBuffers;
 
 /* Constants of the task. */
@@ -171,6 +175,11 @@ typedef struct {
   float dr_damping_base, dr_damping_lo, dr_damping_hi;  /* 0.1, +U[0,2.9] */
   float dr_armature_lo, dr_armature_hi;                 /* xU[0.8,1.2] of the base table */
   const double* dr_armature_base;                       /* [nd] host pointer, T:366-371 */
+  /* optional DR re-drawn on reset next to damping / armature (lo == hi == 0: leave the table alone):
+   * contact_friction = dr_friction_base * U[lo,hi] (DyrosDynamicWalk.yaml:89-96, "scaling");
+   * pd_gain_scale[:,0] and [:,1] = two independent U[lo,hi] */
+  float dr_friction_base, dr_friction_lo, dr_friction_hi;
+  float dr_pd_gain_lo, dr_pd_gain_hi;
   int32_t mocap_rows;        /* 3600 */
   const float* kp;           /* [33] host, already /9 in float32 (T:58-63) */
   const float* kv;           /* [33] host, already /3 in float32 (T:65-70) */

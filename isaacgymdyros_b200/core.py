@@ -66,6 +66,9 @@ class CoreConfig:
     dr_damping_range: tuple = (0.0, 2.9)   # additive, CFG:103-108
     dr_armature_range: tuple = (0.8, 1.2)  # scaling, CFG:109-115
     dr_mass_range: tuple = (0.8, 1.2)      # scaling, setup only, CFG:81-88
+    # optional per-env tables (BASELINE configs[3] "friction / PD gains"; commented out in the reference, CFG:89-96):
+    dr_friction_range: Optional[tuple] = None  # scaling of `friction` per env -> sim_t["contact_friction"] (N)
+    dr_pd_gain_range: Optional[tuple] = None   # scaling of Kp and of Kv per env -> task_t["pd_gain_scale"] (N,2)
     left_foot: str = "L_Foot_Link"
     right_foot: str = "R_Foot_Link"
     solver_bodies: tuple = ("L_Foot_Link", "R_Foot_Link")
@@ -191,6 +194,8 @@ class DyrosCore:
             s["dof_damping"] = torch.tensor(self.tables.dof_damping, dtype=torch.float32, device=dev).repeat(N, 1).contiguous()
             s["dof_armature"] = torch.tensor(self.tables.dof_armature, dtype=torch.float32, device=dev).repeat(N, 1).contiguous()
         s["body_mass_scale"] = torch.ones(N, nb, device=dev)
+        if cfg.dr_friction_range is not None:
+            s["contact_friction"] = torch.full((N,), cfg.friction, device=dev)
         if cfg.with_rigid_body_state:
             s["rigid_body_state"] = z(N * nb, 13)
         if cfg.with_rb_force_tensors:
@@ -205,6 +210,8 @@ class DyrosCore:
         for name, dt, shape in native.TASK_BUFFERS:
             full = tuple(shape[1:]) if (shape and shape[0] is None) else (N,) + tuple(shape)
             tb[name] = torch.zeros(full, dtype=getattr(torch, dt), device=dev)
+        if cfg.dr_pd_gain_range is not None:
+            tb["pd_gain_scale"] = torch.ones(N, 2, device=dev)
         mocap = np.load(os.path.join(ASSETS, "mocap_walk.npy"))
         obs_norm = np.load(os.path.join(ASSETS, "obs_norm.npy"))
         tb["mocap_data"] = torch.tensor(mocap, device=dev).contiguous()
@@ -251,6 +258,9 @@ class DyrosCore:
         arm = np.ascontiguousarray(ARMATURE, dtype=np.float64)
         keep.append(arm)
         td.dr_armature_base = _np_ptr(arm, C.c_double)
+        td.dr_friction_base = cfg.friction
+        td.dr_friction_lo, td.dr_friction_hi = cfg.dr_friction_range or (0.0, 0.0)
+        td.dr_pd_gain_lo, td.dr_pd_gain_hi = cfg.dr_pd_gain_range or (0.0, 0.0)
         td.mocap_rows = int(self.task_t["mocap_data"].shape[0])
         kp = (torch.tensor(KP, dtype=torch.float32) / 9.0).numpy()  # T:58-63 in float32 as torch does
         kv = (torch.tensor(KV, dtype=torch.float32) / 3.0).numpy()  # T:65-70
@@ -266,6 +276,8 @@ class DyrosCore:
             setattr(tbuf, n, self.task_t[n].data_ptr())
         for n in native.TASK_SHARED:
             setattr(tbuf, n, self.task_t[n].data_ptr())
+        for n, _, _ in native.TASK_OPTIONAL:
+            setattr(tbuf, n, self.task_t[n].data_ptr() if n in self.task_t else None)
         native.check(self.lib.dyros_task_create(self.sim_handle, C.byref(td), C.byref(tbuf), C.byref(self.task_handle)),
                      "dyros_task_create")
 

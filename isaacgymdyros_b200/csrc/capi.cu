@@ -128,6 +128,11 @@ static int build_task(Sim* sim, const DyrosTaskDesc* d, const DyrosTaskBuffers* 
   p.dr_damping_hi = d->dr_damping_hi;
   p.dr_armature_lo = d->dr_armature_lo;
   p.dr_armature_hi = d->dr_armature_hi;
+  p.dr_friction_base = d->dr_friction_base;
+  p.dr_friction_lo = d->dr_friction_lo;
+  p.dr_friction_hi = d->dr_friction_hi;
+  p.dr_pd_gain_lo = d->dr_pd_gain_lo;
+  p.dr_pd_gain_hi = d->dr_pd_gain_hi;
   p.lfoot = d->left_foot_body;
   p.rfoot = d->right_foot_body;
   p.pelvis = d->pelvis_body;

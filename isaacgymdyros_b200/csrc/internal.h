@@ -95,6 +95,7 @@ struct TaskParams {
   float death_cost, initial_height;
   float noise_std;          // float32(0.00016/3.0), T:528
   float dr_damping_base, dr_damping_lo, dr_damping_hi, dr_armature_lo, dr_armature_hi;
+  float dr_friction_base, dr_friction_lo, dr_friction_hi, dr_pd_gain_lo, dr_pd_gain_hi;
   int lfoot, rfoot, pelvis;
   uint64_t seed;
   // small device tables

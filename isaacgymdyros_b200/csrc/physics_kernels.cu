@@ -88,6 +88,7 @@ __device__ __forceinline__ EnvIO env_io(const DevModel& m, const DyrosSimBuffers
   io.damping = b.dof_damping + (size_t)e * m.nd;
   io.armature = b.dof_armature + (size_t)e * m.nd;
   io.mass_scale = b.body_mass_scale + (size_t)e * m.nb;
+  io.friction = b.contact_friction ? b.contact_friction + e : nullptr;
   io.contact = b.net_contact_force + (size_t)e * m.nb * 3;
   io.push = nullptr;
   io.rb_force = nullptr;
@@ -116,8 +117,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // the caller waits with cp_async_wait_all() and then synchronises the cooperating threads.
 // (1) joint state, mass scales and root: once per launch (they stay in the scratch blocks)
 __device__ __forceinline__ void slab_stage_state(const DevModel& m, const DyrosSimBuffers& b, const float* hot, float* envs, int es,
-                                                 int e0, int nenv, int tid, int nthreads) {
+                                                 int e0, int nenv, int tid, int nthreads, float mu) {
   const int nd = m.nd, nb = m.nb, xoff = m.nl * LS;
+#pragma unroll 1
+  for (int le = tid; le < nenv; le += nthreads) {  // per-env friction (DR) or the sim's coefficient
+    if (b.contact_friction) cp_async4(envs + le * es + xoff + X_MU, b.contact_friction + e0 + le);
+    else envs[le * es + xoff + X_MU] = mu;
+  }
   const int* dof_link = reinterpret_cast<const int*>(hot) + m.o_dof_link;
   const FastDiv d2nd(2 * nd), dnb(nb), d13(13);  // slabs are < 2^20 / divisor words (checked at create)
   {
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(kPhysThreads) k_simulate(DevModel m, SimParams
   for (int s = 0; s < p.substeps; ++s) {
     // (first sub-step: the staged tables are still in flight, dof_link is read from the global copy)
     const float* tab = s == 0 ? reinterpret_cast<const float*>(m.blob) : c.hot;
-    if (s == 0) slab_stage_state(m, b, tab, envs, es, e0, nenv, threadIdx.x, kPhysThreads);
+    if (s == 0) slab_stage_state(m, b, tab, envs, es, e0, nenv, threadIdx.x, kPhysThreads, p.mu);
     slab_stage_pre(m, b, s == 0 ? push : nullptr, envs, es, e0, nenv, threadIdx.x, kPhysThreads);
     slab_stage_dofpar(m, b, tab, envs, es, e0, nenv, true, threadIdx.x, kPhysThreads);
     cp_async_wait_all();
@@ -320,7 +326,7 @@ __global__ void __launch_bounds__(kStepThreads) k_step_physics(DevModel m, SimPa
     // joint state, root and mass scales are staged once and then live in the scratch blocks for the whole launch; the
     // torque and noise stages read them there, and only the final state is written back
     // (the staged tables are still in flight: dof_link is read from the global copy here)
-    slab_stage_state(m, k.s, reinterpret_cast<const float*>(m.blob), envs, es, e0, nenv, threadIdx.x, kPhysThreads);
+    slab_stage_state(m, k.s, reinterpret_cast<const float*>(m.blob), envs, es, e0, nenv, threadIdx.x, kPhysThreads, p.mu);
     cp_async_wait_all();  // this thread's share of the tables and of the state
     asm volatile("bar.sync 3, %0;" ::"n"(kStepThreads) : "memory");
     asm volatile("bar.arrive 4, %0;" ::"n"(kStepThreads) : "memory");

@@ -51,7 +51,8 @@ constexpr int X_PUSH = X_ROOT + 13;                  // 3  world force at the ba
 constexpr int X_OML = X_ROOT + 16;                   // 21: inverse inertia at the feet's common ancestor (LCA)
 constexpr int PT_WORDS = 5;                          // active sole point: candidate index (int), bias, impulse lam(3)
 constexpr int X_PTS = X_OML + 21;                    // MAX_FEET * MAX_ACTIVE_PTS * PT_WORDS
-constexpr int X_MASS = X_PTS + MAX_FEET * MAX_ACTIVE_PTS * PT_WORDS;  // nb per-body mass scales (last: sized by the model)
+constexpr int X_MU = X_PTS + MAX_FEET * MAX_ACTIVE_PTS * PT_WORDS;    // 1  friction coefficient of this env's ground contacts
+constexpr int X_MASS = X_MU + 1;                     // nb per-body mass scales (last: sized by the model)
 
 HD int env_scratch_floats(int nl, int nb) {
   int n = nl * LS + X_MASS + nb;
@@ -86,6 +87,7 @@ struct EnvIO {
   const float* damping;    // nd
   const float* armature;   // nd
   const float* mass_scale; // nb
+  const float* friction;   // 1 or NULL (SimParams.mu)
   float* contact;          // nb*3
   const float* push;       // 3 or NULL
   const float* rb_force;   // nb*3 or NULL
@@ -95,13 +97,13 @@ struct EnvIO {
 
 // ---- penalty ground contact of one location on a link (oracle: PhysicsOracle._external_wrench.add_point);
 //      xw = the location relative to the link origin, world axes; v = [w; u] of the link
-HD void penalty_point(const SimParams& p, SV v, V3 xw, real depth, float* cf, bool live, SV& fext) {
+HD void penalty_point(const SimParams& p, real mu, SV v, V3 xw, real depth, float* cf, bool live, SV& fext) {
   if (!(depth > 0)) return;
   V3 vel_w = v.v + cross(v.w, xw);
   real fn = p.pen_k * depth - p.pen_c * vel_w.z;
   fn = fn < 0 ? 0 : (fn > p.pen_fmax ? p.pen_fmax : fn);
   real speed = sqrt(vel_w.x * vel_w.x + vel_w.y * vel_w.y);
-  real lim = p.mu * fn / (speed > (real)1e-6 ? speed : (real)1e-6);
+  real lim = mu * fn / (speed > (real)1e-6 ? speed : (real)1e-6);
   real coef = p.pen_c < lim ? p.pen_c : lim;
   V3 Fw = v3(-coef * vel_w.x, -coef * vel_w.y, fn);
   if (live) {
@@ -160,12 +162,13 @@ HD SV link_ext_wrench(const EnvIO& io, const real* X, const float* hot, const De
     }
   }
   if (pw.z < R[R_REACH]) {  // nothing of this link can reach z = 0 otherwise
+    const real mu = X[X_MU];
 #pragma unroll 1
     for (int k = RI(R, R_PT0); k < RI(R, R_PT1); ++k) {
       V3 x = ld3_f(m.pt_pos + 3 * k);
       real rad = m.pt_radius[k];
       real z = pw.z + dot(nrm, x);
-      penalty_point(p, v, mul(Rw, x) - v3(0, 0, rad), rad - z, io.contact + 3 * m.pt_body[k], io.live, fext);
+      penalty_point(p, mu, v, mul(Rw, x) - v3(0, 0, rad), rad - z, io.contact + 3 * m.pt_body[k], io.live, fext);
     }
 #pragma unroll 1
     for (int k = RI(R, R_CYL0); k < RI(R, R_CYL1); ++k) {
@@ -178,7 +181,7 @@ HD SV link_ext_wrench(const EnvIO& io, const real* X, const float* hot, const De
       V3 rim = c + (s * hh) * a;
       if (dn > (real)1e-6) rim = rim + (rad / dn) * d;
       real z = pw.z + dot(nrm, rim);
-      penalty_point(p, v, mul(Rw, rim), -z, io.contact + 3 * m.cyl_body[k], io.live, fext);
+      penalty_point(p, mu, v, mul(Rw, rim), -z, io.contact + 3 * m.cyl_body[k], io.live, fext);
     }
   }
   return fext;
@@ -191,6 +194,7 @@ HD void env_stage_inputs(const EnvIO& io, real* sm, const float* hot, const DevM
   for (int b = tid; b < m.nb; b += nthreads) X[X_MASS + b] = io.mass_scale[b];
   for (int k = tid; k < 13; k += nthreads) X[X_ROOT + k] = io.root[k];
   for (int k = tid; k < 3; k += nthreads) X[X_PUSH + k] = io.push ? io.push[k] : 0.f;
+  if (tid == 0) X[X_MU] = io.friction ? io.friction[0] : p.mu;
   if (io.live)
     for (int k = tid; k < 3 * m.nb; k += nthreads) io.contact[k] = 0.f;  // net contact force of THIS sub-step only
   for (int i = 1 + tid; i < m.nl; i += nthreads) {
@@ -557,6 +561,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     }
     sync.mark(7);
     // fixed number of sweeps; Gauss-Seidel inside a foot, Jacobi between the feet (coupled through the base)
+    const real mu = X[X_MU];
     for (int s = 0; s < p.sweeps; ++s) {
       SV dP = sv_zero();
 #pragma unroll 1
@@ -577,7 +582,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
             nw = lam[0] + (bias - vrel) * rw[6];
             nw = nw > 0 ? nw : 0;
           } else {
-            real lim = p.mu * lam[0];
+            real lim = mu * lam[0];
             nw = lam[d] - vrel * rw[6];
             nw = nw > lim ? lim : (nw < -lim ? -lim : nw);
           }

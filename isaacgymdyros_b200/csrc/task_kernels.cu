@@ -221,6 +221,17 @@ __device__ void stage_reset_env(const TK& k, int e, int lane) {
       k.s.dof_armature[i] = P.armature_base[d] * (P.dr_armature_lo + u1 * (P.dr_armature_hi - P.dr_armature_lo));
     }
   }
+  // optional tables of the same randomisation pass (DyrosDynamicWalk.yaml:89-96 friction; PD gains: BASELINE configs[3]);
+  // with injected DR draws (tests) they are left alone
+  if (P.randomize && !k.j.dr_u && lane == 0) {
+    uint4 r = draw4(P.seed, step, e, kSiteDR, 64);
+    if (k.s.contact_friction && P.dr_friction_hi > 0.f)
+      k.s.contact_friction[e] = P.dr_friction_base * (P.dr_friction_lo + u01(r.x) * (P.dr_friction_hi - P.dr_friction_lo));
+    if (k.b.pd_gain_scale && P.dr_pd_gain_hi > 0.f) {
+      k.b.pd_gain_scale[(size_t)e * 2] = P.dr_pd_gain_lo + u01(r.y) * (P.dr_pd_gain_hi - P.dr_pd_gain_lo);
+      k.b.pd_gain_scale[(size_t)e * 2 + 1] = P.dr_pd_gain_lo + u01(r.z) * (P.dr_pd_gain_hi - P.dr_pd_gain_lo);
+    }
+  }
   if (lane < 12) {
     k.b.qpos_bias[(size_t)e * 12 + lane] = uf(lane) * 6.28f / 100.f - (float)(3.14 / 100);        // T:615
     k.b.motor_constant_scale[(size_t)e * 12 + lane] = uf(18 + lane) * 0.4f + 0.8f;                // T:645

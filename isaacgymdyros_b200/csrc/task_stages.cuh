@@ -230,8 +230,9 @@ __device__ __forceinline__ void stage_substep_torque(const TK& k, int e, int lan
       pos[it] = ds[2 * dc];
       vel[it] = ds[2 * dc + 1];
       tgt[it] = k.b.target_data_qpos[(size_t)e * ND + dc];
-      kp[it] = k.p.kp[dc];
-      kv[it] = k.p.kv[dc];
+      // optional per-env gain scales (DR of the PD gains); a scale of 1 leaves the reference's product unchanged
+      kp[it] = k.b.pd_gain_scale ? __fmul_rn(k.p.kp[dc], k.b.pd_gain_scale[(size_t)e * 2]) : k.p.kp[dc];
+      kv[it] = k.b.pd_gain_scale ? __fmul_rn(k.p.kv[dc], k.b.pd_gain_scale[(size_t)e * 2 + 1]) : k.p.kv[dc];
     }
 #pragma unroll
     for (int it = 0; it < IT; ++it) {
@@ -311,6 +312,7 @@ struct TorqueSlabArgs {  // the handful of pointers the torque stage touches (pa
   const int* delay_idx;
   float* action_log;
   const float* action_torque;
+  const float* pd_gain_scale;  // (N,2) or NULL
 };
 struct NoiseSlabArgs {
   const float* qpos_normal;  // injected draws or NULL
@@ -324,7 +326,7 @@ struct NoiseSlabArgs {
 };
 __device__ __forceinline__ TorqueSlabArgs torque_args(const TK& k) {
   return TorqueSlabArgs{k.s.dof_state, k.s.dof_actuation_force, k.b.target_data_qpos, k.p.kp, k.p.kv, k.b.simul_len,
-                        k.b.delay_idx, k.b.action_log, k.b.action_torque};
+                        k.b.delay_idx, k.b.action_log, k.b.action_torque, k.b.pd_gain_scale};
 }
 __device__ __forceinline__ NoiseSlabArgs noise_args(const TK& k) {
   return NoiseSlabArgs{k.j.qpos_normal, k.b.qpos_pre, k.b.qvel_noise, k.b.qpos_noise, k.p.step_counter, k.p.seed,
@@ -352,8 +354,8 @@ __device__ __forceinline__ void stage_substep_torque_cta(const TorqueSlabArgs& k
       pos[it] = state_of(le, d, 0);
       vel[it] = state_of(le, d, 1);
       tgt[it] = k.target_data_qpos[e * ND + d];
-      kp[it] = k.kp[d];
-      kv[it] = k.kv[d];
+      kp[it] = k.pd_gain_scale ? __fmul_rn(k.kp[d], k.pd_gain_scale[e * 2]) : k.kp[d];
+      kv[it] = k.pd_gain_scale ? __fmul_rn(k.kv[d], k.pd_gain_scale[e * 2 + 1]) : k.kv[d];
     }
 #pragma unroll
     for (int it = 0; it < IT_PD; ++it) {

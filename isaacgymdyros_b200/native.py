@@ -36,7 +36,7 @@ class DyrosSimDesc(C.Structure):
 
 
 SIM_BUFFERS = ["root_states", "dof_state", "net_contact_force", "rigid_body_state", "dof_actuation_force", "rb_force",
-               "rb_torque", "dof_damping", "dof_armature", "body_mass_scale"]
+               "rb_torque", "dof_damping", "dof_armature", "body_mass_scale", "contact_friction"]
 
 
 class DyrosSimBuffers(C.Structure):
@@ -66,16 +66,20 @@ TASK_BUFFERS = [
     ("obs_hist_head", "int32", ()), ("act_hist_head", "int32", ()),
 ]
 TASK_SHARED = ["mocap_data", "obs_mean", "obs_var"]
+TASK_OPTIONAL = [("pd_gain_scale", "float32", (2,))]  # allocated on request (CoreConfig.dr_pd_gain_range), else NULL
 
 
 class DyrosTaskBuffers(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n, _, _ in TASK_BUFFERS] + [(n, C.c_void_p) for n in TASK_SHARED]
+    _fields_ = ([(n, C.c_void_p) for n, _, _ in TASK_BUFFERS] + [(n, C.c_void_p) for n in TASK_SHARED]
+                + [(n, C.c_void_p) for n, _, _ in TASK_OPTIONAL])
 
 
 class DyrosTaskDesc(C.Structure):
     _fields_ = [("skipframe", i32), ("max_episode_length", f32), ("death_cost", f32), ("initial_height", f32),
                 ("perturb", i32), ("randomize", i32), ("dr_damping_base", f32), ("dr_damping_lo", f32),
                 ("dr_damping_hi", f32), ("dr_armature_lo", f32), ("dr_armature_hi", f32), ("dr_armature_base", P_f64),
+                ("dr_friction_base", f32), ("dr_friction_lo", f32), ("dr_friction_hi", f32),
+                ("dr_pd_gain_lo", f32), ("dr_pd_gain_hi", f32),
                 ("mocap_rows", i32), ("kp", P_f32), ("kv", P_f32), ("action_high", P_f32), ("initial_dof_pos", P_f32),
                 ("left_foot_body", i32), ("right_foot_body", i32), ("pelvis_body", i32), ("seed", u64)]
 

@@ -22,8 +22,21 @@ REWARD_NAMES = ["mimic_body_orientation_reward", "qpos_regulation", "qvel_regula
                 "force_thres_penalty", "force_diff_thres_penalty", "force_ref_reward", "perturbation"]  # T:922-925, T:423
 
 
-def default_cfg(num_envs: int = 4096, randomize: bool = True, perturbation: bool = True) -> Dict[str, Any]:
-    """The values of cfg/task/DyrosDynamicWalk.yaml (+ cfg/config.yaml defaults) as the plain dict VecTask receives."""
+def default_cfg(num_envs: int = 4096, randomize: bool = True, perturbation: bool = True,
+                friction_range=None, pd_gain_range=None) -> Dict[str, Any]:
+    """The values of cfg/task/DyrosDynamicWalk.yaml (+ cfg/config.yaml defaults) as the plain dict VecTask receives.
+    `friction_range` / `pd_gain_range` switch on the optional randomisations of BASELINE configs[3] (friction as in the
+    yaml's commented-out block, CFG:89-96: [0.7, 1.3] scaling)."""
+    cfg = _default_cfg(num_envs, randomize, perturbation)
+    hum = cfg["task"]["randomization_params"]["actor_params"]["humanoid"]
+    if friction_range is not None:
+        hum["rigid_shape_properties"] = {"friction": {"range": list(friction_range), "operation": "scaling", "distribution": "uniform"}}
+    if pd_gain_range is not None:
+        hum["pd_gains"] = {"range": list(pd_gain_range), "operation": "scaling", "distribution": "uniform"}
+    return cfg
+
+
+def _default_cfg(num_envs: int, randomize: bool, perturbation: bool) -> Dict[str, Any]:
     return {
         "name": "DyrosDynamicWalk", "physics_engine": "physx",
         "env": {"numEnvs": num_envs, "envSpacing": 5, "episodeLength": 32, "enableDebugVis": False,
@@ -65,6 +78,14 @@ def core_config_from_cfg(cfg: Dict[str, Any]) -> CoreConfig:
     rb = ap.get("rigid_body_properties", {})
     if "mass" in rb:
         c.dr_mass_range = tuple(rb["mass"]["range"])
+    # optional (commented out in the reference's yaml, CFG:89-96; named by BASELINE configs[3]): per-env friction of the
+    # ground contacts and per-env scales of the upper-body PD gains, re-drawn on reset like damping / armature
+    fr = ap.get("rigid_shape_properties", {}).get("friction")
+    if fr is not None:
+        c.dr_friction_range = tuple(fr["range"])
+    pg = ap.get("pd_gains")
+    if pg is not None:
+        c.dr_pd_gain_range = tuple(pg["range"])
     return c
 
 
@@ -177,6 +198,12 @@ class DyrosDynamicWalk:
             s["dof_damping"].copy_(c.dof_damping + lo + r(N, 33) * (hi - lo))
             lo, hi = c.dr_armature_range
             s["dof_armature"].mul_(lo + r(N, 33) * (hi - lo))
+            if "contact_friction" in s:
+                lo, hi = c.dr_friction_range
+                s["contact_friction"].copy_(c.friction * (lo + r(N) * (hi - lo)))
+            if "pd_gain_scale" in t:
+                lo, hi = c.dr_pd_gain_range
+                t["pd_gain_scale"].copy_(lo + r(N, 2) * (hi - lo))
             masses = torch.tensor(self.core.tables.body_inertia[:, 0], dtype=torch.float32, device=dev)
             t["total_mass"].copy_((s["body_mass_scale"] * masses).sum(1))  # T:221-225
 

@@ -27,7 +27,7 @@ struct HostRoleSync {
 extern "C" int dyros_hostemu_simulate(const DyrosSimDesc* d, const DyrosModelDesc* md, float* root, float* dof_state,
                                       const float* tau, const float* damping, const float* armature,
                                       const float* mass_scale, float* contact, const float* push, const float* rb_force,
-                                      const float* rb_torque, char* err, int errlen) {
+                                      const float* rb_torque, const float* friction, char* err, int errlen) {
   Blob bl;
   DevModel m;
   ModelOffsets off;
@@ -53,6 +53,7 @@ extern "C" int dyros_hostemu_simulate(const DyrosSimDesc* d, const DyrosModelDes
     io.push = push ? push + (size_t)env * 3 : nullptr;
     io.rb_force = rb_force ? rb_force + (size_t)env * m.nb * 3 : nullptr;
     io.rb_torque = rb_torque ? rb_torque + (size_t)env * m.nb * 3 : nullptr;
+    io.friction = friction ? friction + env : nullptr;
     io.live = true;
     std::vector<int> flags(F_COUNT, 0);
     std::barrier<> bar(DYROS_LANES);

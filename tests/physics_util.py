@@ -82,7 +82,7 @@ def hostemu():
     return _EMU
 
 
-def emulate_substep(tables, cfg, st, push=None, rb_force=None, rb_torque=None):
+def emulate_substep(tables, cfg, st, push=None, rb_force=None, rb_torque=None, friction=None):
     """Runs the kernel's lane program on the CPU (float32). Returns root', q', qd', contact like the oracle."""
     N = st["root"].shape[0]
     md, keep = make_model_desc(tables, cfg)
@@ -97,7 +97,8 @@ def emulate_substep(tables, cfg, st, push=None, rb_force=None, rb_torque=None):
     rf = f32(rb_force) if rb_force is not None else None
     rt = f32(rb_torque) if rb_torque is not None else None
     err = C.create_string_buffer(256)
+    mu = f32(friction) if friction is not None else None
     rc = hostemu().dyros_hostemu_simulate(C.byref(sd), C.byref(md), P(root), P(dof), P(tau), P(damp), P(arm), P(ms),
-                                          P(contact), P(pf), P(rf), P(rt), err, 256)
+                                          P(contact), P(pf), P(rf), P(rt), P(mu), err, 256)
     assert rc == 0, err.value
     return root.astype(np.float64), dof[:, :, 0].astype(np.float64), dof[:, :, 1].astype(np.float64), contact.astype(np.float64)

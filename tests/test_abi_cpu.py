@@ -40,7 +40,7 @@ def test_abi_version_and_error_string(lib):
 def test_struct_layouts_match_header_sizes(lib):
     # pointer-only structs: one pointer per declared member
     assert ctypes.sizeof(native.DyrosSimBuffers) == 8 * len(native.SIM_BUFFERS)
-    assert ctypes.sizeof(native.DyrosTaskBuffers) == 8 * (len(native.TASK_BUFFERS) + len(native.TASK_SHARED))
+    assert ctypes.sizeof(native.DyrosTaskBuffers) == 8 * (len(native.TASK_BUFFERS) + len(native.TASK_SHARED) + len(native.TASK_OPTIONAL))
     assert ctypes.sizeof(native.DyrosNoiseInjection) == 8 * len(native.NOISE_FIELDS)
     # compile a tiny C program against the header and compare sizeof() of the mixed structs
     src = r'''

@@ -49,11 +49,20 @@ def test_fused_step_matches_cpu_oracle_rollout():
     core.close()
 
 
-def test_fused_step_equals_staged_sequence_bitwise():
-    """dyros_task_step must give the same bits as the staged calls it fuses (same kernels, same order)."""
+@pytest.mark.parametrize("optional_tables", [False, True])
+def test_fused_step_equals_staged_sequence_bitwise(optional_tables):
+    """dyros_task_step must give the same bits as the staged calls it fuses (same kernels, same order); also with the
+    optional per-env friction and PD-gain tables in use."""
     N = 257
     rng = np.random.default_rng(3)
-    a, b = make_core(N), make_core(N)
+    kw = dict(dr_friction_range=(0.5, 1.2), dr_pd_gain_range=(0.8, 1.2)) if optional_tables else {}
+    a, b = make_core(N, **kw), make_core(N, **kw)
+    if optional_tables:
+        mu = torch.tensor(rng.uniform(0.5, 1.2, N).astype(np.float32), device=a.device)
+        gs = torch.tensor(rng.uniform(0.8, 1.2, (N, 2)).astype(np.float32), device=a.device)
+        for c in (a, b):
+            c.sim_t["contact_friction"].copy_(mu)
+            c.task_t["pd_gain_scale"].copy_(gs)
     tables, mocap, obs_norm = load_assets()
     s, _c = O.new_state(N, mocap, obs_norm, np.full(N, np.float32(tables.total_mass())), tables.dof_lower,
                         tables.dof_upper, O.Params(), rng=rng)
@@ -233,6 +242,35 @@ def test_large_ragged_shard_runs_multi_wave():
     # envs that never reset use no shard-dependent random draws besides their own Philox streams (keyed by env index)
     assert torch.equal(big.root_states[:M], small.root_states) and torch.equal(ob["obs"][:M], os_["obs"])
     big.close(); small.close()
+
+
+def test_optional_friction_and_pd_gain_randomisation():
+    """BASELINE configs[3] names friction and PD-gain randomisation (commented out in the reference's yaml, CFG:89-96):
+    the optional per-env tables are drawn at start, re-drawn for exactly the envs that reset, stay in range, and the
+    rollout with them differs from the one without."""
+    from isaacgymdyros_b200 import DyrosDynamicWalk, default_cfg
+    N = 512
+    env = DyrosDynamicWalk(default_cfg(N, friction_range=(0.7, 1.3), pd_gain_range=(0.9, 1.1)), "cuda:0", use_cuda_graph=False)
+    ref = DyrosDynamicWalk(default_cfg(N), "cuda:0", use_cuda_graph=False)
+    assert "contact_friction" not in ref.core.sim_t and "pd_gain_scale" not in ref.core.task_t
+    mu0, g0 = env.core.sim_t["contact_friction"].clone(), env.core.task_t["pd_gain_scale"].clone()
+    assert mu0.min() >= 0.7 - 1e-6 and mu0.max() <= 1.3 + 1e-6 and mu0.std() > 0.1
+    assert g0.min() >= 0.9 - 1e-6 and g0.max() <= 1.1 + 1e-6 and g0.std() > 0.03
+    ids = torch.arange(0, N, 2, device="cuda:0")
+    env.reset_idx(ids)
+    torch.cuda.synchronize()
+    mu1, g1 = env.core.sim_t["contact_friction"], env.core.task_t["pd_gain_scale"]
+    assert (mu1[1::2] == mu0[1::2]).all() and (mu1[0::2] != mu0[0::2]).float().mean() > 0.99
+    assert (g1[1::2] == g0[1::2]).all() and (g1[0::2] != g0[0::2]).float().mean() > 0.99
+    assert mu1.min() >= 0.7 - 1e-6 and mu1.max() <= 1.3 + 1e-6 and g1.min() >= 0.9 - 1e-6 and g1.max() <= 1.1 + 1e-6
+    g = torch.Generator(device="cuda:0"); g.manual_seed(3)
+    for _ in range(20):
+        act = torch.rand(N, 13, device="cuda:0", generator=g) * 2 - 1
+        env.step(act); ref.step(act)
+    torch.cuda.synchronize()
+    assert torch.isfinite(env.obs_buf).all() and torch.isfinite(env.root_states).all()
+    assert not torch.equal(env.dof_state, ref.dof_state)
+    env.close(); ref.close()
 
 
 def test_domain_randomisation_redraw_on_reset_ranges():

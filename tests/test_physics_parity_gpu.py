@@ -55,6 +55,36 @@ def test_cuda_simulate_matches_dense_oracle(kind, N, seed):
     core.close()
 
 
+@pytest.mark.parametrize("kind", ["stand", "mixed"])
+def test_cuda_simulate_per_env_friction(kind):
+    """DyrosSimBuffers.contact_friction: per-env friction of the sole contacts (sweeps) and of the penalty contacts
+    against the oracle run with the same coefficients, on states that slide sideways."""
+    import dataclasses
+    from isaacgymdyros_b200.core import DyrosCore
+    from tests.test_physics_emulation import SLIDING_SLACK, sliding_states
+    tables = load_assets()[0]
+    N = 96
+    cfg = CoreConfig(dr_friction_range=(0.2, 1.3))
+    rng = np.random.default_rng(33)
+    st = sliding_states(N, rng, tables, kind)
+    mu = rng.uniform(0.2, 1.3, N).astype(np.float32)
+    o = PhysicsOracle(tables, dataclasses.replace(oracle_params(cfg), mu=mu.astype(np.float64)))
+    want = o.substep(st["root"], st["q"], st["qd"], st["tau"], st["damping"], st["armature"], st["mass_scale"])
+    core = DyrosCore(N, "cuda:0", cfg)
+    load_sim_state(core, st)
+    core.sim_t["contact_friction"].copy_(torch.tensor(mu))
+    core.simulate()
+    torch.cuda.synchronize()
+    got = read_sim_state(core)
+    compare(st, got, want, ctx=f"{kind}: ", slack=SLIDING_SLACK)
+    core.sim_t["contact_friction"].fill_(1.0)  # the table is what the kernel uses
+    load_sim_state(core, st)
+    core.simulate()
+    torch.cuda.synchronize()
+    assert np.abs(read_sim_state(core)[3] - got[3]).max() > 1.0
+    core.close()
+
+
 def test_cuda_standing_carries_weight_on_feet_only():
     """Physical invariant on the GPU at the full size: 4096 robots held at the reset pose by a stiff PD settle with
     the ground reaction equal to their weight, on bodies 8 and 16 only."""

@@ -174,6 +174,34 @@ def test_cuda_task_kernels_match_oracle(N, steps, perturb):
     core.close()
 
 
+def test_cuda_substep_torque_with_pd_gain_scale():
+    """DyrosTaskBuffers.pd_gain_scale (optional per-env scales of Kp, Kv in T:506): both torque stages (warp-per-env
+    kernel, slab stage of the fused physics launch) against the oracle, float32 products in the same order: exact."""
+    from oracle import task_oracle as O
+    tables, mocap, obs_norm = load_assets()
+    N = 61
+    rng = np.random.default_rng(77)
+    s, c = O.new_state(N, mocap, obs_norm, np.full(N, np.float32(tables.total_mass())), tables.dof_lower,
+                       tables.dof_upper, O.Params(), rng=rng)
+    s["dof_pos"] = (s["dof_pos"] + rng.normal(0, 0.1, (N, 33))).astype(np.float32)
+    s["dof_vel"] = rng.normal(0, 1, (N, 33)).astype(np.float32)
+    s["target_data_qpos"] = (s["dof_pos"] + rng.normal(0, 0.2, (N, 33))).astype(np.float32)
+    s["action_torque"] = rng.normal(0, 50, (N, 12)).astype(np.float32)
+    s["pd_gain_scale"] = rng.uniform(0.8, 1.2, (N, 2)).astype(np.float32)
+    core = make_core(N, dr_pd_gain_range=(0.8, 1.2))
+    load_state(core, s)
+    core.task_t["pd_gain_scale"].copy_(torch.tensor(s["pd_gain_scale"], device=core.device))
+    want = O.substep_torque(s, c)
+    core.substep_torque()
+    torch.cuda.synchronize()
+    got = core.sim_t["dof_actuation_force"].view(N, 33).cpu().numpy()
+    assert np.array_equal(got, want)
+    unscaled = dict(s)
+    del unscaled["pd_gain_scale"]
+    assert np.abs(O.substep_torque(unscaled, c)[:, 12:] - want[:, 12:]).max() > 1e-3
+    core.close()
+
+
 def test_actions_validation_and_errors():
     from isaacgymdyros_b200 import native
     core = make_core(4)
