@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--force-perturb", action="store_true", help="pushes forced on (BASELINE configs[3]; T:491)")
+    ap.add_argument("--dr-extra", action="store_true",
+                    help="also randomise friction x[0.7,1.3] and the PD gains x[0.9,1.1] per env (BASELINE configs[3])")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
 
@@ -216,7 +218,8 @@ def run_ours(a):
     dev = f"cuda:{local}"
     torch.cuda.set_device(dev)
     N, K, W = a.envs, a.steps, max(a.warmup, 3)
-    env = DyrosDynamicWalk(default_cfg(N), dev, rank=rank)
+    extra = dict(friction_range=(0.7, 1.3), pd_gain_range=(0.9, 1.1)) if a.dr_extra else {}
+    env = DyrosDynamicWalk(default_cfg(N, **extra), dev, rank=rank)
     if a.force_perturb:
         env.core.task_t["perturb_start"].fill_(1)
     g = torch.Generator(device=dev)
@@ -336,7 +339,8 @@ def run_ours(a):
             "ms_per_step": cold_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": N, "actions": "torch.rand(N,13)*2-1, seed 42",
-                       "domain_randomisation": True, "perturbation": "forced on (T:491)" if a.force_perturb else "gated as in the reference (T:489)",
+                       "domain_randomisation": "mass, damping, armature, friction, PD gains" if a.dr_extra else "mass, damping, armature (CFG:81-115)",
+                       "perturbation": "forced on (T:491)" if a.force_perturb else "gated as in the reference (T:489)",
                        "l2": "flushed between timed steps (256 MiB fill outside the timed intervals)",
                        "timing": "CUDA events per step on the launch stream, summed; max over ranks",
                        "launch_geometry": dict(core.launch_info(), threads_per_cta_fused_step=256), "reset_rate_last_step": reset_rate},
