@@ -36,7 +36,7 @@ WORKLOAD = "DyrosDynamicWalk 4096 envs/GPU, random actions, physics + PD + obs/r
 K1_BYTES_PER_ENV_STEP = 2 * 1648 + 2 * 1296   # per policy step: 2 x K1 sub-step (412 words) + 2 x (torque/delay ring + sensor noise: 324 words), DESIGN.md section 6
 ENV_STEP_BYTES = 7044                # SURVEY 8d canonical bytes per env-step
 K1_FLOP_PER_ENV_STEP = 2 * 48200         # executed FP32 FLOP of 2 sub-steps (ncu, profiles/r1f_k_step_physics.txt: ffma*2+fadd+fmul = 3.951e8 per 4096-env launch)
-K1_DRAM_BYTES_PER_ENV = 6129152 / 4096   # dram__bytes_read+write of one 4096-env launch (same capture): the state is L2-resident
+K1_DRAM_BYTES_PER_ENV = 22267136 / 4096  # dram__bytes_read + write of one 4096-env launch, caches flushed by ncu before the launch like the timed launches here (profiles/r1i_k_step_physics.txt; with a warm L2 it is 6.1 MB, profiles/r1f_k_step_physics.txt)
 
 
 def parse():
@@ -358,7 +358,7 @@ def run_ours(a):
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                          "traffic": K1_DRAM_BYTES_PER_ENV * N if N == 4096 else None,
-                         "traffic_source": "profiles/r1f_k_step_physics.txt (ncu --set full, one launch, 4096 envs)",
+                         "traffic_source": "profiles/r1i_k_step_physics.txt (ncu --set full, one launch, 4096 envs, cold caches as in the timed launches)",
                          "launch_ms": k1_ms, "algorithmic_bytes_per_launch": k1_bytes,
                          "note": "K1 is FP32-latency bound, not HBM bound (SURVEY 8d): see fp32"},
             "fp32": {"achieved": K1_FLOP_PER_ENV_STEP * N / (k1_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
