@@ -199,7 +199,7 @@ def run_reference(a):
                              "sample": f"{workers} processes x 64-env shards x {steps_done} steps of the oracle port "
                                        f"(reference PhysX binaries absent: SURVEY fact 2), {el:.1f} s"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -219,7 +219,14 @@ def run_ours(a):
     torch.cuda.set_device(dev)
     N, K, W = a.envs, a.steps, max(a.warmup, 3)
     extra = dict(friction_range=(0.7, 1.3), pd_gain_range=(0.9, 1.1)) if a.dr_extra else {}
-    env = DyrosDynamicWalk(default_cfg(N, **extra), dev, rank=rank)
+    cfg = default_cfg(N, **extra)
+    # tickets in flight for step_async: 3 hides the host's reaction time when the PCIe link of ONE GPU is the limit
+    # (155 vs 172 us per step); with more ranks the host's memory system is the limit (8 ranks: ~112 GB/s of device->host
+    # writes in total) and fewer, cache-resident host blocks do better (8 ranks: 56.9 M with 2, 51.4 M with 3;
+    # profiles/r1j_step_async.txt)
+    depth = 3 if world <= 2 else 2
+    cfg["async_depth"] = depth
+    env = DyrosDynamicWalk(cfg, dev, rank=rank)
     if a.force_perturb:
         env.core.task_t["perturb_start"].fill_(1)
     g = torch.Generator(device=dev)
@@ -280,8 +287,8 @@ def run_ours(a):
         barrier()
         e2e_sync_ms = e0.elapsed_time(e1)
         # ---- (3b) the same through step_async / step_wait: results packed into one block by dyros_task_pack_results,
-        #           ONE device->host transfer per step on a copy stream, three steps in flight, the host consumes (waits
-        #           for) the results of step i-2 right after submitting step i
+        #           ONE device->host transfer per step on a copy stream, `depth` steps in flight, the host consumes (waits
+        #           for) the results of step i-depth+1 right after submitting step i
         tick = env.step_async(h_act[0])
         env.step_wait(tick)
         cs = env._pipe.copy_stream
@@ -290,7 +297,7 @@ def run_ours(a):
         ticks = []
         for i in range(K):
             ticks.append(env.step_async(h_act[i % len(h_act)]))
-            if len(ticks) == 3:  # three steps in flight: consume the oldest
+            if len(ticks) == depth:  # `depth` steps in flight: consume the oldest
                 env.step_wait(ticks.pop(0))
         for tick in ticks:
             env.step_wait(tick)
@@ -348,7 +355,8 @@ def run_ours(a):
             "e2e": {"value": total_envs * K / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K,
                     "api": "DyrosDynamicWalk.step_async / step_wait: pinned host actions in, one packed pinned host block "
-                           "(obs, rew, reset, time_outs) out per step; the transfer of step k overlaps the kernels of step k+1"},
+                           "(obs, rew, reset, time_outs) out per step; the transfer of step k overlaps the kernels of step k+1",
+                    "tickets_in_flight": depth},
             "e2e_sync": {"value": total_envs * K / (e2e_sync_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_sync_ms / K,
                          "d2h_bytes_per_step": N * 487 * 4 + N * 4 + N * 8,
                          "api": "DyrosDynamicWalk.step + three device->host copies on the same stream, nothing overlapped"},
@@ -370,14 +378,28 @@ def run_ours(a):
         }
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(a.cpu_seconds)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line: dict):
+    """The ONE JSON line, on the process's original stdout."""
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    global _JSON_FD
     a = parse()
+    # stdout carries the JSON line and nothing else: whatever libraries print there from C (NCCL prints its version to
+    # stdout when the box sets NCCL_DEBUG) goes to stderr instead
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:

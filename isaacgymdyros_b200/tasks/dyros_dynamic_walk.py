@@ -236,17 +236,17 @@ class DyrosDynamicWalk:
         Enqueues VT:293-344 for `actions` (pinned host or device tensor), gathers what `step` returns
         (obs_dict["obs"], rew_buf, reset_buf, extras["time_outs"]: VT:336-344) into one device block (dyros_task_pack_results) and hands that
         block to the copy engine on a second stream as ONE device->host transfer into pinned memory. Returns a ticket
-        for `step_wait`. Three tickets may be in flight: the transfer of step k overlaps the kernels of step k+1, so a
+        for `step_wait`. Up to cfg["async_depth"] (default 3) tickets may be in flight: the transfer of step k overlaps the kernels of step k+1, so a
         rollout whose actions do not wait for the newest observation runs at max(kernels, PCIe) instead of their sum.
         `self.obs_buf` is not updated by these steps (the observation kernel writes the ticket's block directly); rew_buf,
-        reset_buf and the state tensors are. The only host wait is for the slot of step k-3 to be free again."""
+        reset_buf and the state tensors are. The only host wait is for the slot of step k-async_depth to be free again."""
         if self._pipe is None:
             self._pipe = _HostPipe(self)
         return self._pipe.submit(actions)
 
     def step_wait(self, ticket: int):
         """Blocks until the results of `ticket` are in host memory; returns (obs_dict, rew, reset, extras) as pinned
-        host tensors, valid until three further `step_async` calls have been made."""
+        host tensors, valid until async_depth further `step_async` calls have been made."""
         if self._pipe is None:
             raise RuntimeError("step_wait without step_async")
         return self._pipe.wait(ticket)
@@ -342,6 +342,9 @@ class _HostPipe:
 
     def __init__(self, env: DyrosDynamicWalk):
         self.env, N = env, env.num_envs
+        self.DEPTH = int(env.cfg.get("async_depth", self.DEPTH))
+        if self.DEPTH < 1:
+            raise ValueError("async_depth must be at least 1")
         nbytes = env.core.result_bytes()
         self.copy_stream = torch.cuda.Stream(device=env.device)
         self.h_actions = [torch.zeros(N, env.num_actions).pin_memory() for _ in range(self.DEPTH)]
