@@ -140,6 +140,8 @@ class DyrosDynamicWalk:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._use_graph = use_cuda_graph
         self._pipe: Optional["_HostPipe"] = None
+        self._inplace_graphs: Dict[int, torch.cuda.CUDAGraph] = {}
+        self._seen_action_ptrs: set = set()
         self.first_randomization = True
 
     # ------------------------------------------------------------------ VT:129-152
@@ -216,10 +218,14 @@ class DyrosDynamicWalk:
             # run, as with every tensor handed to the reference's gym setters (DOCT:348-369)
             self.core.step(actions)
         elif self._use_graph:
-            self._actions_static.copy_(actions, non_blocking=True)
-            if self._graph is None:
-                self._capture()
-            self._graph.replay()
+            g = self._graph_reading(actions)
+            if g is not None:
+                g.replay()  # the step's first kernel reads the caller's tensor in place
+            else:
+                self._actions_static.copy_(actions, non_blocking=True)
+                if self._graph is None:
+                    self._capture()
+                self._graph.replay()
         else:
             self._actions_static.copy_(actions, non_blocking=True)
             self.core.step(self._actions_static)
@@ -250,6 +256,33 @@ class DyrosDynamicWalk:
         if self._pipe is None:
             raise RuntimeError("step_wait without step_async")
         return self._pipe.wait(ticket)
+
+    _MAX_INPLACE_GRAPHS = 32
+
+    def _graph_reading(self, actions: torch.Tensor) -> Optional[torch.cuda.CUDAGraph]:
+        """A rollout loop hands `step` the same few action tensors over and over (the policy's output buffer): for a
+        contiguous float32 (N,13) tensor on the env's device, one CUDA graph per storage address whose first kernel
+        reads that address directly, so the step needs no staging copy (a launch and ~5 us). The graph is captured the
+        second time an address is seen; any other tensor, or more than _MAX_INPLACE_GRAPHS distinct addresses, goes
+        through the staging buffer."""
+        if (not actions.is_cuda or actions.dtype != torch.float32 or not actions.is_contiguous()
+                or tuple(actions.shape) != (self.num_envs, self.num_actions) or actions.device != self.core.device):
+            return None
+        key = actions.data_ptr()
+        g = self._inplace_graphs.get(key)
+        if g is None and key not in self._seen_action_ptrs:
+            if len(self._seen_action_ptrs) < 4 * self._MAX_INPLACE_GRAPHS:
+                self._seen_action_ptrs.add(key)
+            return None
+        if g is None and len(self._inplace_graphs) < self._MAX_INPLACE_GRAPHS:
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                self.core.step(actions)
+            self._inplace_graphs[key] = g
+        return g
 
     def _capture(self):
         torch.cuda.synchronize()
@@ -330,6 +363,7 @@ class DyrosDynamicWalk:
     def close(self):
         self._graph = None
         self._pipe = None
+        self._inplace_graphs = {}
         self.core.close()
 
 

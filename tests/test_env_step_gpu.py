@@ -179,6 +179,30 @@ def test_step_reads_pinned_host_actions_like_device_actions():
     a.close(); b.close()
 
 
+def test_step_reads_a_reused_device_tensor_in_place():
+    """A device tensor handed to step() again and again (the policy's output buffer) is read in place by a CUDA graph
+    captured for its address from the second sighting on: same bits as the staging-copy path without graphs."""
+    from isaacgymdyros_b200 import DyrosDynamicWalk, default_cfg
+    N = 130
+    a = DyrosDynamicWalk(default_cfg(N), "cuda:0", use_cuda_graph=False)
+    b = DyrosDynamicWalk(default_cfg(N), "cuda:0")
+    g = torch.Generator(device="cuda:0"); g.manual_seed(8)
+    bufs = [torch.zeros(N, 13, device="cuda:0") for _ in range(2)]
+    for t in range(9):
+        act = torch.rand(N, 13, device="cuda:0", generator=g) * 2 - 1
+        buf = bufs[t % 2]
+        buf.copy_(act)
+        oa, ra, sa, _ = a.step(act)
+        ob, rb, sb, _ = b.step(buf)
+        torch.cuda.synchronize()
+        assert torch.equal(oa["obs"], ob["obs"]) and torch.equal(ra, rb) and torch.equal(sa, sb), f"step {t}"
+    assert len(b._inplace_graphs) == 2
+    assert torch.equal(a.root_states, b.root_states) and torch.equal(a.dof_state, b.dof_state)
+    ob, _, _, _ = b.step(bufs[0][:, :13].t().contiguous().t())  # non-contiguous: staging path, no new graph
+    assert len(b._inplace_graphs) == 2
+    a.close(); b.close()
+
+
 def test_step_async_pipeline_returns_the_results_of_step_in_host_memory():
     """step_async / step_wait (up to three steps in flight, one D2H block per step on a copy stream) must hand back,
     bit for bit and in order, what the synchronous step() of a twin env returns; tickets out of the window raise."""
