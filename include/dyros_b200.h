@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DYROS_ABI_VERSION 1
+#define DYROS_ABI_VERSION 2  /* 2: contact_friction, pd_gain_scale, dr_friction_*, dr_pd_gain_* members; pack_results, set_obs_buf, post_step */
 #define DYROS_MAX_LINKS 40
 #define DYROS_MAX_BODIES 48
 #define DYROS_LANES 4 /* roles (warps) per env group in the physics kernel */

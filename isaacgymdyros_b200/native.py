@@ -10,6 +10,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+ABI_VERSION = 2  # include/dyros_b200.h DYROS_ABI_VERSION: struct layouts below mirror that header
 LIB_PATH = os.environ.get("DYROS_B200_LIB", os.path.join(_HERE, "libdyros_b200.so"))  # override: A/B builds only
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "dyros_b200.h")
 
@@ -153,7 +154,7 @@ def load(path: str = LIB_PATH):
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.dyros_abi_version() != 1:
+    if lib.dyros_abi_version() != ABI_VERSION:
         raise DyrosError("libdyros_b200.so ABI version mismatch")
     _LIB = lib
     return lib
