@@ -326,9 +326,28 @@ def run_ours(a):
     torch.cuda.synchronize()
     k1_ms = statistics.mean(s.elapsed_time(e) for s, e in kev)
     reset_rate = float(env.reset_buf.float().mean().item())
+    # ---- (5) as (1), with the env state pinned in the persisting part of L2 (dyros_sim_set_l2_persistence): the same
+    #          256 MiB fill between the steps no longer evicts it. Reported beside `value`, not as `value`.
+    persist_ms, set_aside = float("nan"), 0
+    try:
+        set_aside = env.set_l2_persistence(True)
+        for i in range(len(pool) + W):
+            device_step(i)
+        barrier()
+        pev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for i in range(K):
+            flush.fill_(i & 0xFF)
+            pev[i][0].record()
+            device_step(W + i)
+            pev[i][1].record()
+        barrier()
+        persist_ms = sum(s.elapsed_time(e) for s, e in pev)
+        env.set_l2_persistence(False)
+    except Exception as exc:  # noqa: BLE001  (an informational extra must not cost the run its JSON line)
+        print(f"l2 persistence measurement skipped: {exc}", file=sys.stderr)
 
     from isaacgymdyros_b200.sharding import max_over_ranks, reduce_episode_stats
-    cold_ms, warm_ms, e2e_ms, e2e_sync_ms, k1_ms = (max_over_ranks(x, dev) for x in (cold_ms, warm_ms, e2e_ms, e2e_sync_ms, k1_ms))
+    cold_ms, warm_ms, e2e_ms, e2e_sync_ms, k1_ms, persist_ms = (max_over_ranks(x, dev) for x in (cold_ms, warm_ms, e2e_ms, e2e_sync_ms, k1_ms, persist_ms))
     # episode statistics across ranks (the only data the env path ever reduces)
     stats = reduce_episode_stats({"epi_len_log": env.epi_len_log, "contact_reward_mean": env.contact_reward_mean})
     if rank == 0:
@@ -364,6 +383,12 @@ def run_ours(a):
                          "api": "DyrosDynamicWalk.step + three device->host copies on the same stream, nothing overlapped"},
             "gpu_launches": K * core.step_launches(),
             "value_warm_l2": total_envs * K / (warm_ms * 1e-3), "ms_per_step_warm_l2": warm_ms / K,
+            "l2_persisting_state": None if persist_ms != persist_ms else {
+                                    "value": total_envs * K / (persist_ms * 1e-3), "unit": UNIT, "ms_per_step": persist_ms / K,
+                                    "set_aside_bytes": set_aside, "state_bytes": int(core.state_arena.numel()),
+                                    "note": "same flushed-L2 loop as `value`, env state pinned in the persisting part of L2 "
+                                            "(DyrosDynamicWalk.set_l2_persistence): an opt-in of the product, not the headline; "
+                                            "it buys ~2 us of the ~24 us a flushed L2 costs: the rest is not env state"},
             "roofline": {"bound": "hbm", "kernel": "k_step_physics (2 x (PD/delay torque, physics sub-step, sensor noise) of all envs, one launch)",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",

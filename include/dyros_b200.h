@@ -219,6 +219,13 @@ int dyros_set_state_indexed(DyrosSim* sim, const int32_t* env_ids, int count, vo
 /* Measurement aid (no reference counterpart): FFMA-saturation micro-benchmark giving the FP32 roofline denominator
  * that MEASURED_PEAKS.json lacks. Synchronous; returns TFLOP/s (FMA = 2 FLOP). */
 int dyros_measure_fp32_peak(int device, int iters, double* tflops_out);
+/* Optional: keep the env state resident in the set-aside (persisting) part of the B200's 126 MB L2. [base, base+bytes)
+ * is the one contiguous range holding the per-env buffers (the caller allocates them from one arena); kernels launched
+ * on `stream` afterwards, and kernel nodes captured from it into CUDA graphs, access that range with the persisting
+ * property, so traffic of other kernels (a policy network between two env steps, an L2 flush) does not evict it.
+ * bytes = 0 switches the window off and resets the persisting lines. *set_aside_out (may be NULL) receives the size of
+ * the set-aside region actually configured (device limit: cudaDevAttrMaxPersistingL2CacheSize). */
+int dyros_sim_set_l2_persistence(DyrosSim* sim, void* base, size_t bytes, void* stream, size_t* set_aside_out);
 /* Physics launch geometry chosen at create time: envs per CTA, CTAs, threads per CTA, dynamic shared memory bytes. */
 int dyros_sim_launch_info(DyrosSim* sim, int32_t out[4]);
 

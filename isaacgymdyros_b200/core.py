@@ -169,10 +169,12 @@ class DyrosCore:
         if with_task and (t.num_dofs != ND or t.num_bodies != NB):
             raise native.DyrosError("DyrosDynamicWalk expects the 33-DOF / 38-body TOCABI model")
         self._keep = []  # host arrays referenced by the descriptors during the create calls
+        self.l2_persist = False
         self.sim_handle = C.c_void_p()
         self.task_handle = C.c_void_p()
         torch.cuda.set_device(self.device)
         self._alloc()
+        self._pack_state_arena()
         self._create_sim()
         if with_task:
             self._create_task(seed + rank)
@@ -231,6 +233,35 @@ class DyrosCore:
         tb["total_mass"].fill_(float(np.float32(self.tables.total_mass())))
         tb["obs_hist_head"].fill_(19)
         tb["act_hist_head"].fill_(19)
+
+    def _pack_state_arena(self):
+        """Moves every per-env buffer except obs_buf (written once per step, never read by the step) into ONE
+        contiguous allocation, 256-byte aligned views: the range dyros_sim_set_l2_persistence can pin in L2."""
+        items = [(d, k) for d in (self.sim_t, self.task_t) for k in d if k != "obs_buf"]
+        al = lambda n: (n + 255) & ~255
+        total = sum(al(d[k].numel() * d[k].element_size()) for d, k in items)
+        self.state_arena = torch.zeros(total, dtype=torch.uint8, device=self.device)
+        off = 0
+        for d, k in items:
+            t = d[k]
+            nbytes = t.numel() * t.element_size()
+            view = self.state_arena[off:off + nbytes].view(t.dtype).view(t.shape)
+            view.copy_(t)
+            d[k] = view
+            off += al(nbytes)
+
+    def set_l2_persistence(self, on: bool = True, stream: Optional["torch.cuda.Stream"] = None) -> int:
+        """Pins the env state (state_arena) in the persisting part of L2 for the kernels launched on `stream` (default:
+        the current stream) from now on, including those captured from it into CUDA graphs; returns the bytes of L2 set
+        aside. Other kernels' traffic between two env steps then no longer evicts the state."""
+        st = stream or torch.cuda.current_stream(self.device)
+        out = C.c_size_t(0)
+        native.check(self.lib.dyros_sim_set_l2_persistence(
+            self.sim_handle, C.c_void_p(self.state_arena.data_ptr() if on else 0),
+            C.c_size_t(self.state_arena.numel() if on else 0), C.c_void_p(st.cuda_stream), C.byref(out)),
+            "dyros_sim_set_l2_persistence")
+        self.l2_persist = bool(on)
+        return int(out.value)
 
     # ------------------------------------------------------------------ native objects
     def _create_sim(self):

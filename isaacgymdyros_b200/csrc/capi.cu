@@ -240,6 +240,39 @@ int dyros_measure_fp32_peak(int device, int iters, double* tflops_out) {
   }
   return measure_fp32_peak(device, iters, tflops_out);
 }
+int dyros_sim_set_l2_persistence(DyrosSim* sim, void* base, size_t bytes, void* stream, size_t* set_aside_out) {
+  SIM_OR_FAIL("dyros_sim_set_l2_persistence");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaStreamAttrValue attr;
+  memset(&attr, 0, sizeof(attr));
+  size_t set_aside = 0;
+  if (base && bytes) {
+    int max_persist = 0, max_window = 0;
+    DY_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, s->device));
+    DY_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, s->device));
+    if (max_persist <= 0 || max_window <= 0) {
+      set_error("dyros_sim_set_l2_persistence: the device has no persisting L2 cache");
+      return 1;
+    }
+    set_aside = std::min(bytes, (size_t)max_persist);
+    DY_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside));
+    const size_t window = std::min(bytes, (size_t)max_window);
+    attr.accessPolicyWindow.base_ptr = base;
+    attr.accessPolicyWindow.num_bytes = window;
+    // fraction of the window that gets the persisting property: what fits the set-aside part of L2
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)set_aside / (double)window);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  } else {
+    attr.accessPolicyWindow.num_bytes = 0;  // window off
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+  }
+  DY_CUDA(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr));
+  if (!(base && bytes)) DY_CUDA(cudaCtxResetPersistingL2Cache());
+  if (set_aside_out) *set_aside_out = set_aside;
+  return 0;
+}
 int dyros_sim_launch_info(DyrosSim* sim, int32_t out[4]) {
   SIM_OR_FAIL("dyros_sim_launch_info");
   if (!out) {

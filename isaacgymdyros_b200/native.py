@@ -96,6 +96,7 @@ _VP, _INT = C.c_void_p, C.c_int
 SIGNATURES = {
     "dyros_last_error": (C.c_char_p, []),
     "dyros_abi_version": (_INT, []),
+    "dyros_sim_set_l2_persistence": (_INT, [_VP, _VP, C.c_size_t, _VP, C.POINTER(C.c_size_t)]),
     "dyros_sim_create": (_INT, [C.POINTER(DyrosSimDesc), C.POINTER(DyrosModelDesc), C.POINTER(DyrosSimBuffers), C.POINTER(_VP)]),
     "dyros_sim_destroy": (_INT, [_VP]),
     "dyros_simulate": (_INT, [_VP, _INT, _VP]),

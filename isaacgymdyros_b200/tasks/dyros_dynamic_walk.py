@@ -276,8 +276,7 @@ class DyrosDynamicWalk:
             return None
         if g is None and len(self._inplace_graphs) < self._MAX_INPLACE_GRAPHS:
             torch.cuda.synchronize()
-            side = torch.cuda.Stream(device=self.device)
-            side.wait_stream(torch.cuda.current_stream(self.device))
+            side = self._capture_stream()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=side):
                 self.core.step(actions)
@@ -286,12 +285,26 @@ class DyrosDynamicWalk:
 
     def _capture(self):
         torch.cuda.synchronize()
-        side = torch.cuda.Stream(device=self.device)
-        side.wait_stream(torch.cuda.current_stream(self.device))
+        side = self._capture_stream()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=side):
             self.core.step(self._actions_static)
         self._graph = g
+
+    def _capture_stream(self) -> "torch.cuda.Stream":
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        if self.core.l2_persist:  # kernel nodes inherit the stream's access-policy window at capture
+            self.core.set_l2_persistence(True, side)
+        return side
+
+    def set_l2_persistence(self, on: bool = True) -> int:
+        """Keep the env state in the persisting part of the 126 MB L2 (dyros_sim_set_l2_persistence): the step then runs
+        at its back-to-back speed even when other kernels (the policy network) stream through L2 between two steps.
+        Drops the CUDA graphs captured so far (their kernel nodes carry the previous setting). Returns the bytes set aside."""
+        n = self.core.set_l2_persistence(on)
+        self._graph, self._inplace_graphs, self._pipe = None, {}, None
+        return n
 
     def zero_actions(self) -> torch.Tensor:
         return torch.zeros(self.num_envs, self.num_actions, dtype=torch.float32, device=self.rl_device)
@@ -411,8 +424,7 @@ class _HostPipe:
         g = self.graphs.get((slot, kind))
         if g is None:
             torch.cuda.synchronize(env.device)
-            side = torch.cuda.Stream(device=env.device)
-            side.wait_stream(torch.cuda.current_stream(env.device))
+            side = env._capture_stream()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=side):
                 launches()
