@@ -253,7 +253,9 @@ int dyros_task_compute_observations(DyrosTask* task, void* stream);             
 int dyros_task_late_update(DyrosTask* task, void* stream);                         /* T:560-563 */
 /* End of a staged step: the cross-env curriculum gate of T:489 (evaluated for the next step) + RNG epoch bump. */
 int dyros_task_end_step(DyrosTask* task, void* stream);
-/* Whole VecTask.step (VT:293-344) in the fewest launches; same results as the staged calls. */
+/* Whole VecTask.step (VT:293-344) in the fewest launches; same results as the staged calls, except that the compacted
+ * id list of T:554 (reset_env_ids / reset_count), which the fused step does not need, is left to
+ * dyros_task_compact_resets. */
 int dyros_task_step(DyrosTask* task, const float* actions, void* stream);
 /* The launches of dyros_task_step after dyros_task_prologue_physics, on their own (T:532-563 fused + the cross-env
  * pass): dyros_task_prologue_physics followed by dyros_task_post_step is dyros_task_step. */

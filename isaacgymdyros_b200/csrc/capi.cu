@@ -156,6 +156,8 @@ static int build_task(Sim* sim, const DyrosTaskDesc* d, const DyrosTaskBuffers* 
   size_t o_rp = bl.add_f32(reset_pos.data(), ND), o_ip = bl.add_f32(d->initial_dof_pos, ND), o_ar = bl.add_f32(arm.data(), ND);
   unsigned long long zero = 0;
   size_t o_ct = bl.add(&zero, sizeof(zero));
+  unsigned long long zeros4[4] = {0, 0, 0, 0};
+  size_t o_tail = bl.add(zeros4, sizeof(zeros4));
   cudaError_t e = cudaMalloc(&t->dev_blob, bl.host.size());
   if (e == cudaSuccess) e = cudaMemcpy(t->dev_blob, bl.host.data(), bl.host.size(), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
@@ -168,6 +170,7 @@ static int build_task(Sim* sim, const DyrosTaskDesc* d, const DyrosTaskBuffers* 
   p.kp = at<float>(base, o_kp); p.kv = at<float>(base, o_kv); p.action_high = at<float>(base, o_ah);
   p.reset_dof_pos = at<float>(base, o_rp); p.init_dof_pos = at<float>(base, o_ip); p.armature_base = at<float>(base, o_ar);
   p.step_counter = const_cast<uint64_t*>(at<uint64_t>(base, o_ct));
+  p.tail = const_cast<unsigned long long*>(at<unsigned long long>(base, o_tail));
   *out = t;
   return 0;
 }
@@ -397,18 +400,18 @@ int dyros_task_step(DyrosTask* task, const float* actions, void* stream) {
   // the kernels use programmatic dependent launch: their CTAs get resident and run their preamble while the previous
   // kernel drains (common.cuh); the data dependency is enforced by griddepcontrol.wait inside each kernel
   if (launch_task_physics(t, st, nullptr, true, actions)) return 1;  // prologue folded into the physics launch
-  if (launch_post_fused(t, st, true)) return 1;
-  return launch_crossenv(t, true, true, true, st, true);
+  // ... and the cross-env pass (gate of T:489, Philox epoch) into the post-physics launch: its last CTA does it. The
+  // compacted id list of T:554 is not needed by the fused step (every env resets itself): dyros_task_compact_resets
+  // produces it on demand.
+  return launch_post_fused(t, st, true, true);
 }
 int dyros_task_post_step(DyrosTask* task, void* stream) {
   TASK_OR_FAIL("dyros_task_post_step");
-  cudaStream_t st = (cudaStream_t)stream;
-  if (launch_post_fused(t, st, true)) return 1;
-  return launch_crossenv(t, true, true, true, st, true);
+  return launch_post_fused(t, (cudaStream_t)stream, true, true);
 }
 int dyros_task_step_launches(DyrosTask* task) {
   TASK_OR_FAIL("dyros_task_step_launches");
-  return 3;  // prologue + fused physics, fused post-physics, cross-env
+  return 2;  // prologue + fused physics, fused post-physics (+ cross-env pass in its last CTA)
 }
 int dyros_task_set_obs_buf(DyrosTask* task, float* obs_buf) {
   TASK_OR_FAIL("dyros_task_set_obs_buf");

@@ -105,7 +105,8 @@ struct TaskParams {
   const float* reset_dof_pos;   // clamp(initial_dof_pos, lower, upper), T:742
   const float* init_dof_pos;
   const float* armature_base;
-  uint64_t* step_counter;       // device, Philox epoch; bumped once per step by the cross-env kernel
+  uint64_t* step_counter;       // device, Philox epoch; bumped once per step by the cross-env pass
+  unsigned long long* tail;     // device [4]: fixed-point sums of the two gate means, CTA ticket of the fused post-physics launch
 };
 
 struct Sim {
@@ -138,7 +139,7 @@ int launch_crossenv(Task* t, bool compact, bool gate, bool bump, cudaStream_t s,
 int launch_reset_idx(Task* t, const int64_t* env_ids, int count, cudaStream_t s);
 int launch_compute_observations(Task* t, cudaStream_t s);
 int launch_late_update(Task* t, cudaStream_t s);
-int launch_post_fused(Task* t, cudaStream_t s, bool pdl = false);
+int launch_post_fused(Task* t, cudaStream_t s, bool pdl = false, bool tail = false);
 int launch_pack_results(Task* t, float* dst, cudaStream_t s);
 // launchers (physics_kernels.cu)
 int physics_configure(Sim* sim);  // chooses envs_per_block / shared memory, sets the kernel attributes

@@ -440,8 +440,19 @@ __device__ __forceinline__ void prefetch_rows_l2(const void* p, int bytes, int l
 
 // post_physics_step in one launch: epilogue, termination, reward, reset, observations, late update.
 // Reward/termination read the pre-reset state, observations the post-reset state.
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_post_fused(TK k) {
+// The two means of the curriculum gate (T:489) are formed from fixed-point terms summed in 64-bit integers, so that the
+// result does not depend on the order of summation: k_crossenv (one CTA, fixed order) and the fused post-physics launch
+// (atomics across CTAs) give the same bits. epi_len_log holds whole numbers (exact at 2^-20), contact_reward_mean lies
+// in [0, 1] (2^-40 is below a float's resolution there).
+__device__ __forceinline__ long long gate_term0(float epi_len_log) { return __double2ll_rn((double)epi_len_log * 1048576.0); }
+__device__ __forceinline__ long long gate_term1(float contact_reward_mean) { return __double2ll_rn((double)contact_reward_mean * 1099511627776.0); }
+__device__ __forceinline__ bool gate_open(const TaskParams& P, long long s0, long long s1) {  // T:489
+  return (float)((double)s0 / 1048576.0 / P.N) > P.gate_len && (float)((double)s1 / 1099511627776.0 / P.N) > 0.165f;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_post_fused(TK k, int tail) {
   __shared__ RewardSums sums[kWarpsPerBlock];
+  __shared__ long long gate_acc[2][kWarpsPerBlock];
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -474,14 +485,48 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_post_fused(TK k) {
     if (e2 < k.p.N) reward_scalar(k, e2, sums[lane]);
   }
   __syncthreads();
-  if (!valid) return;
-  if (reset) {
-    stage_reset_env(k, e, lane);
+  if (valid) {
+    if (reset) {
+      stage_reset_env(k, e, lane);
+      __syncwarp();
+    }
+    stage_compute_observations(k, e, lane);
     __syncwarp();
+    stage_late_update(k, e, lane);
   }
-  stage_compute_observations(k, e, lane);
+  if (!tail) return;
+  // ---- cross-env pass of the fused step (what k_crossenv does for the staged one, minus the id list): gate sums by
+  //      64-bit integer atomics, one pair per CTA; the last CTA to finish decides the gate and bumps the Philox epoch
+  const bool gate = k.p.perturb != 0;
   __syncwarp();
-  stage_late_update(k, e, lane);
+  if (gate && lane == 0) {
+    gate_acc[0][w] = valid ? gate_term0(k.b.epi_len_log[e]) : 0;          // (post-reset values, as k_crossenv reads them)
+    gate_acc[1][w] = valid ? gate_term1(k.b.contact_reward_mean[e]) : 0;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (gate) {
+      long long a = 0, b = 0;
+#pragma unroll
+      for (int i = 0; i < kWarpsPerBlock; ++i) {
+        a += gate_acc[0][i];
+        b += gate_acc[1][i];
+      }
+      atomicAdd(k.p.tail + 0, (unsigned long long)a);
+      atomicAdd(k.p.tail + 1, (unsigned long long)b);
+    }
+    __threadfence();
+    if (atomicAdd(k.p.tail + 2, 1ull) == gridDim.x - 1) {  // every CTA has finished its envs and published its sums
+      __threadfence();
+      if (gate) {
+        const long long s0 = (long long)atomicExch(k.p.tail + 0, 0ull), s1 = (long long)atomicExch(k.p.tail + 1, 0ull);
+        if (gate_open(k.p, s0, s1)) *k.b.perturb_start = 1;  // T:489-490 (sticky)
+      }
+      k.p.tail[2] = 0;
+      *k.p.step_counter = *k.p.step_counter + 1;
+    }
+  }
 }
 
 // Cross-env pass (one block, one sweep over the envs): (a) reset_buf.nonzero() -> ascending ids (T:554): thread t owns the
@@ -491,20 +536,20 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_post_fused(TK k) {
 constexpr int kScanThreads = 1024;
 __global__ void __launch_bounds__(kScanThreads) k_crossenv(TK k, int do_compact, int do_gate, int do_bump) {
   __shared__ int warp_tot[kScanThreads / 32];
-  __shared__ double red[2][kScanThreads / 32];
+  __shared__ long long red[2][kScanThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int N = k.p.N;
   const int per = (N + kScanThreads - 1) / kScanThreads;
   const int e0 = tid * per, e1 = min(N, e0 + per);
   pdl_wait();
   int cnt = 0;
-  double s0 = 0.0, s1 = 0.0;
+  long long s0 = 0, s1 = 0;  // fixed-point terms: see gate_term0 / gate_term1
   const bool gate = do_gate && k.p.perturb;
   for (int e = e0; e < e1; ++e) {
     if (do_compact) cnt += k.b.reset_buf[e] != 0;
     if (gate) {
-      s0 += (double)k.b.epi_len_log[e];
-      s1 += (double)k.b.contact_reward_mean[e];
+      s0 += gate_term0(k.b.epi_len_log[e]);
+      s1 += gate_term1(k.b.contact_reward_mean[e]);
     }
   }
   // inclusive scan of cnt inside the warp, warp totals to shared memory
@@ -535,13 +580,13 @@ __global__ void __launch_bounds__(kScanThreads) k_crossenv(TK k, int do_compact,
     warp_tot[lane] = sc - v;  // exclusive offsets of the warps
     if (lane == 31 && do_compact) *k.b.reset_count = sc;
     if (gate) {
-      double a = red[0][lane], b = red[1][lane];
+      long long a = red[0][lane], b = red[1][lane];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         a += __shfl_xor_sync(kFull, a, o);
         b += __shfl_xor_sync(kFull, b, o);
       }
-      if (lane == 0 && (float)(a / N) > k.p.gate_len && (float)(b / N) > 0.165f) *k.b.perturb_start = 1;  // T:489-490 (sticky)
+      if (lane == 0 && gate_open(k.p, a, b)) *k.b.perturb_start = 1;  // T:489-490 (sticky)
     }
     if (do_bump && lane == 0) *k.p.step_counter = *k.p.step_counter + 1;
   }
@@ -617,8 +662,8 @@ int launch_check_termination(Task* t, cudaStream_t s) { LAUNCH_ENV(k_check_termi
 int launch_compute_reward(Task* t, cudaStream_t s) { LAUNCH_ENV(k_compute_reward) }
 int launch_compute_observations(Task* t, cudaStream_t s) { LAUNCH_ENV(k_compute_observations) }
 int launch_late_update(Task* t, cudaStream_t s) { LAUNCH_ENV(k_late_update) }
-int launch_post_fused(Task* t, cudaStream_t s, bool pdl) {
-  DY_CUDA(launch_kernel(k_post_fused, dim3(env_grid(t->p.N)), dim3(kWarpsPerBlock * 32), 0, s, pdl, make_tk(t)));
+int launch_post_fused(Task* t, cudaStream_t s, bool pdl, bool tail) {
+  DY_CUDA(launch_kernel(k_post_fused, dim3(env_grid(t->p.N)), dim3(kWarpsPerBlock * 32), 0, s, pdl, make_tk(t), (int)tail));
   return 0;
 }
 int launch_reset_idx(Task* t, const int64_t* env_ids, int count, cudaStream_t s) {

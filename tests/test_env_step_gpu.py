@@ -33,6 +33,7 @@ def test_fused_step_matches_cpu_oracle_rollout():
         want_ids = ref.step(actions, noise)
         inject_noise(core, noise)
         core.step(torch.tensor(actions, device=core.device))
+        core.compact_resets()  # the fused step does not need the id list of T:554; it is produced on demand
         torch.cuda.synchronize()
         got = read_state(core)
         n = int(core.task_t["reset_count"].item())
@@ -87,6 +88,7 @@ def test_fused_step_equals_staged_sequence_bitwise(optional_tables):
             b.sensor_noise(k)
         b.epilogue(); b.check_termination(); b.compute_reward(); b.compact_resets(); b.reset_idx(None)
         b.compute_observations(); b.late_update(); b.end_step()
+        a.compact_resets()
         torch.cuda.synchronize()
         ga, gb = read_state(a), read_state(b)
         for k in ga:
@@ -153,6 +155,7 @@ def test_vectask_api_rollout_properties_full_size():
             assert torch.isfinite(obs["obs"]).all() and torch.isfinite(rew).all()
             assert torch.isfinite(env.root_states).all() and torch.isfinite(env.dof_state).all()
             assert ((env.progress_buf == 0) == (rst == 1)).all()
+            env.core.compact_resets()  # id list of T:554, on demand
             n = int(env.core.task_t["reset_count"].item())
             assert torch.equal(env.core.task_t["reset_env_ids"][:n], rst.nonzero().flatten())
             assert rew.max().item() <= 2.5 and rew.min().item() >= -0.3
@@ -260,6 +263,7 @@ def test_large_ragged_shard_runs_multi_wave():
         os_, rs, ss, _ = small.step(act[:M].contiguous())
     torch.cuda.synchronize()
     assert torch.isfinite(ob["obs"]).all() and torch.isfinite(rb).all() and torch.isfinite(big.root_states).all()
+    big.core.compact_resets()  # id list of T:554, on demand
     n = int(big.core.task_t["reset_count"].item())
     assert torch.equal(big.core.task_t["reset_env_ids"][:n], sb.nonzero().flatten())
     assert ((big.progress_buf == 0) == (sb == 1)).all()
