@@ -503,7 +503,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_post_fused(TK k, int ta
     gate_acc[0][w] = valid ? gate_term0(k.b.epi_len_log[e]) : 0;          // (post-reset values, as k_crossenv reads them)
     gate_acc[1][w] = valid ? gate_term1(k.b.contact_reward_mean[e]) : 0;
   }
-  __threadfence();
+  // (no device-wide fence by every thread: nothing written above is read by another CTA of this launch; what the last
+  //  CTA reads are the sums below, and what it overwrites, the Philox epoch, every warp has finished reading before
+  //  the barrier; thread 0's fences order its atomics)
   __syncthreads();
   if (threadIdx.x == 0) {
     if (gate) {
