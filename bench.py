@@ -35,8 +35,20 @@ UNIT = "env-steps/s"
 WORKLOAD = "DyrosDynamicWalk 4096 envs/GPU, random actions, physics + PD + obs/reward/reset kernels (BASELINE configs[1])"
 K1_BYTES_PER_ENV_STEP = 2 * 1648 + 2 * 1296   # per policy step: 2 x K1 sub-step (412 words) + 2 x (torque/delay ring + sensor noise: 324 words), DESIGN.md section 6
 ENV_STEP_BYTES = 7044                # SURVEY 8d canonical bytes per env-step
-K1_FLOP_PER_ENV_STEP = 2 * 48200         # executed FP32 FLOP of 2 sub-steps (ncu, profiles/r1f_k_step_physics.txt: ffma*2+fadd+fmul = 3.951e8 per 4096-env launch)
-K1_DRAM_BYTES_PER_ENV = 22267136 / 4096  # dram__bytes_read + write of one 4096-env launch, caches flushed by ncu before the launch like the timed launches here (profiles/r1i_k_step_physics.txt; with a warm L2 it is 6.1 MB, profiles/r1f_k_step_physics.txt)
+
+
+def k1_profile():
+    """Executed FP32 FLOP and DRAM bytes of ONE k_step_physics launch of the CURRENT build, per env: read from
+    profiles/current.json, which tools/ncu_summary.py --json writes from the ncu --set full capture of this build
+    (ffma*2 + fadd + fmul; dram__bytes_read + write with the caches flushed by ncu before the launch, as in the timed
+    launches here). Returns (flop_per_env, dram_bytes_per_env, source) or (None, None, why)."""
+    path = os.path.join(ROOT, "profiles", "current.json")
+    try:
+        d = json.load(open(path))["k_step_physics"]
+        return d["flop"] / d["envs"], d["dram_bytes"] / d["envs"], f"profiles/{d['source']} ({d['envs']} envs, one launch)"
+    except Exception as exc:  # noqa: BLE001
+        return None, None, f"profiles/current.json unreadable: {exc}"
+
 
 
 def parse():
@@ -184,7 +196,7 @@ def run_reference(a):
     budget = 150.0
     per_step_guess = 0.2
     steps = max(1, min(a.steps, int(budget / per_step_guess)))
-    warm = min(a.warmup, 3)
+    warm = max(a.warmup, 3) if a.warmup <= 5 else 5  # >= 3 as in our arm; capped: a port step costs ~0.1 s
     with mp.get_context("spawn").Pool(workers) as pool:
         res = pool.map(cpu_worker, [(64, steps, warm, budget, 42 + i) for i in range(workers)])
     total = sum(64 * d for d, _ in res)
@@ -194,7 +206,9 @@ def run_reference(a):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps_done,
             "warmup": warm, "ms_per_step": 1e3 * el / max(steps_done, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": a.envs},
+            "config": {"workload": WORKLOAD, "envs_per_gpu": a.envs,
+                       "sample": f"bounded: {workers} host processes x 64-env shards = {workers * 64} envs per step (not "
+                                 f"{a.envs}: a 4096-env port step takes minutes); throughput is per env-step, so comparable"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
                              "sample": f"{workers} processes x 64-env shards x {steps_done} steps of the oracle port "
                                        f"(reference PhysX binaries absent: SURVEY fact 2), {el:.1f} s"},
@@ -291,8 +305,10 @@ def run_ours(a):
         # ---- (3b) the same through step_async / step_wait: results packed into one block by dyros_task_pack_results,
         #           ONE device->host transfer per step on a copy stream, `depth` steps in flight, the host consumes (waits
         #           for) the results of step i-depth+1 right after submitting step i
-        tick = env.step_async(h_act[0])
-        env.step_wait(tick)
+        # every ticket slot captures its CUDA graph on first use: use each slot (twice) BEFORE the timed region, so that
+        # no capture (a device synchronisation + graph instantiation) lands inside it
+        for j in range(2 * depth):
+            env.step_wait(env.step_async(h_act[j % len(h_act)]))
         cs = env._pipe.copy_stream
         barrier()
         e0.record()
@@ -358,6 +374,7 @@ def run_ours(a):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         fp32_peak = measure_fp32_peak(local)
+        k1_flop_env, k1_dram_env, k1_src = k1_profile()
         total_envs = N * world
         value = total_envs * K / (cold_ms * 1e-3)
         k1_bytes = K1_BYTES_PER_ENV_STEP * N
@@ -392,12 +409,14 @@ def run_ours(a):
             "roofline": {"bound": "hbm", "kernel": "k_step_physics (2 x (PD/delay torque, physics sub-step, sensor noise) of all envs, one launch)",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                         "traffic": K1_DRAM_BYTES_PER_ENV * N if N == 4096 else None,
-                         "traffic_source": "profiles/r1i_k_step_physics.txt (ncu --set full, one launch, 4096 envs, cold caches as in the timed launches)",
+                         "traffic": None if k1_dram_env is None else k1_dram_env * N,
+                         "traffic_source": k1_src + "; ncu --set full, cold caches as in the timed launches; scaled per env",
                          "launch_ms": k1_ms, "algorithmic_bytes_per_launch": k1_bytes,
                          "note": "K1 is FP32-latency bound, not HBM bound (SURVEY 8d): see fp32"},
-            "fp32": {"achieved": K1_FLOP_PER_ENV_STEP * N / (k1_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-                     "frac": K1_FLOP_PER_ENV_STEP * N / (k1_ms * 1e-3) / 1e12 / fp32_peak,
+            "fp32": None if k1_flop_env is None else {
+                     "achieved": k1_flop_env * N / (k1_ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": k1_flop_env * N / (k1_ms * 1e-3) / 1e12 / fp32_peak,
+                     "flop_per_launch": k1_flop_env * N, "flop_source": k1_src + ": executed ffma*2 + fadd + fmul",
                      "peak_source": "dyros_measure_fp32_peak (FFMA saturation, this run)"},
             "whole_step_hbm": {"achieved": ENV_STEP_BYTES * N / (cold_ms / K * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"},
             "episode_stats": stats,

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DYROS_ABI_VERSION 2  /* 2: contact_friction, pd_gain_scale, dr_friction_*, dr_pd_gain_* members; pack_results, set_obs_buf, post_step */
+#define DYROS_ABI_VERSION 3  /* 3: DyrosTaskBuffers.reset_seq; 2: contact_friction, pd_gain_scale, dr_friction_*, dr_pd_gain_*, pack_results, set_obs_buf, post_step */
 #define DYROS_MAX_LINKS 40
 #define DYROS_MAX_BODIES 48
 #define DYROS_LANES 4 /* roles (warps) per env group in the physics kernel */
@@ -156,6 +156,8 @@ typedef struct {
   float* action_history;     /* (N,20,13) ring */
   int32_t* obs_hist_head;    /* (N) newest slot */
   int32_t* act_hist_head;    /* (N) newest slot */
+  int32_t* reset_seq;        /* (N) resets of this env so far: part of the Philox counter of reset_idx, so that two resets of
+                                one env inside one step epoch (reset_done() + a termination) draw different values, T:611-665 */
   /* shared tables */
   const float* mocap_data;   /* (3600,36) T:112-113 */
   const float* obs_mean;     /* (37) */

@@ -92,7 +92,7 @@ static int build_task(Sim* sim, const DyrosTaskDesc* d, const DyrosTaskBuffers* 
                        b->total_mass, b->env_origins, b->epi_len, b->epi_len_log, b->contact_reward_sum,
                        b->contact_reward_mean, b->perturbation_count, b->pert_duration, b->pert_on, b->impulse,
                        b->magnitude, b->phase, b->perturb_timing, b->perturb_start, b->push_force, b->obs_history,
-                       b->action_history, b->obs_hist_head, b->act_hist_head};
+                       b->action_history, b->obs_hist_head, b->act_hist_head, b->reset_seq};
   for (size_t i = 0; i < sizeof(req) / sizeof(req[0]); ++i)
     REQUIRE(req[i], "dyros_task_create: DyrosTaskBuffers member #%zu is NULL", i);
   Task* t = new (std::nothrow) Task();
@@ -137,6 +137,20 @@ static int build_task(Sim* sim, const DyrosTaskDesc* d, const DyrosTaskBuffers* 
   p.rfoot = d->right_foot_body;
   p.pelvis = d->pelvis_body;
   p.seed = d->seed;
+  // Python: int() truncates, round() is half-to-even; all on the double dt / dt_policy (never on their float32 casts:
+  // float(0.002) = 0.00200000009 would turn int(0.002/dt) into 0)
+  p.delay_lo = 1 + (int)(0.002 / dt_sim);                 // T:652
+  p.delay_hi = 1 + (int)std::nearbyint(0.01 / dt_sim);    // T:652
+  p.timing_hi = (int)(8.0 / dt_policy);                   // T:665
+  p.dur_lo = (int)(0.1 / dt_policy);                      // T:441
+  p.dur_hi = (int)(1.0 / dt_policy);                      // T:441
+  if (!(p.delay_hi == LOG_DEPTH && p.delay_lo >= 0 && p.delay_lo < p.delay_hi && p.timing_hi > 0 && p.dur_lo < p.dur_hi)) {
+    set_error("dyros_task_create: dt %.6g / skipframe %d unsupported: the actuation-delay ring is compiled for "
+              "round(0.01/dt)+1 == %d (T:166), and the draw ranges of T:441,652,665 must be non-empty", dt_sim,
+              d->skipframe, LOG_DEPTH);
+    delete t;
+    return 1;
+  }
   REQUIRE(p.lfoot >= 0 && p.lfoot < NB && p.rfoot >= 0 && p.rfoot < NB && p.pelvis >= 0 && p.pelvis < NB,
           "dyros_task_create: body index out of range");
 

@@ -97,6 +97,10 @@ struct TaskParams {
   float dr_damping_base, dr_damping_lo, dr_damping_hi, dr_armature_lo, dr_armature_hi;
   float dr_friction_base, dr_friction_lo, dr_friction_hi, dr_pd_gain_lo, dr_pd_gain_hi;
   int lfoot, rfoot, pelvis;
+  // integer bounds of the randint draws, formed on the host in double exactly as Python forms them from dt / dt_policy
+  int delay_lo, delay_hi;   // 1+int(0.002/dt), 1+round(0.01/dt), T:652
+  int timing_hi;            // int(8/dt_policy), T:665
+  int dur_lo, dur_hi;       // int(0.1/dt_policy), int(1/dt_policy), T:441
   uint64_t seed;
   // small device tables
   const float* kp;

@@ -191,7 +191,12 @@ __device__ void stage_compute_reward(const TK& k, int e, int lane, const TermSha
 // T:598-669, T:720-748 (+ DR re-draw of damping/armature, VT:519-733 / gymutil.py:584-619)
 __device__ void stage_reset_env(const TK& k, int e, int lane) {
   const TaskParams& P = k.p;
-  uint64_t step = *P.step_counter;
+  // Philox epoch of this reset: the step epoch, plus the env's own count of explicit resets since the last step so that
+  // an env reset twice within one epoch (reset_done() then a termination; repeated reset_idx calls) draws afresh
+  const uint64_t step = *P.step_counter + ((uint64_t)k.b.reset_seq[e] << 40);
+  // VT:540-544: only envs whose randomize_buf reached the frequency (1) are re-randomised; the buffer is cleared below
+  const bool dr = P.randomize && k.b.randomize_buf[e] >= 1;
+  __syncwarp();
   // --- draws (env-indexed). reset_f columns: see DyrosNoiseInjection
   auto uf = [&](int col) -> float {
     if (k.j.reset_f) return k.j.reset_f[(size_t)e * 32 + col];
@@ -207,7 +212,7 @@ __device__ void stage_reset_env(const TK& k, int e, int lane) {
     k.s.dof_state[2 * i] = P.reset_dof_pos[d];                                     // T:742
     k.s.dof_state[2 * i + 1] = 0.f;                                                // T:743
     k.b.pre_joint_velocity_states[i] = 0.f;                                        // T:635
-    if (P.randomize) {                                                             // CFG:103-115, always re-drawn on reset
+    if (dr) {                                                                      // CFG:103-115, re-drawn on reset
       float u0, u1;
       if (k.j.dr_u) {
         u0 = k.j.dr_u[(size_t)e * 66 + d];
@@ -223,7 +228,7 @@ __device__ void stage_reset_env(const TK& k, int e, int lane) {
   }
   // optional tables of the same randomisation pass (DyrosDynamicWalk.yaml:89-96 friction; PD gains: BASELINE configs[3]);
   // with injected DR draws (tests) they are left alone
-  if (P.randomize && !k.j.dr_u && lane == 0) {
+  if (dr && !k.j.dr_u && lane == 0) {
     uint4 r = draw4(P.seed, step, e, kSiteDR, 64);
     if (k.s.contact_friction && P.dr_friction_hi > 0.f)
       k.s.contact_friction[e] = P.dr_friction_base * (P.dr_friction_lo + u01(r.x) * (P.dr_friction_hi - P.dr_friction_lo));
@@ -265,9 +270,8 @@ __device__ void stage_reset_env(const TK& k, int e, int lane) {
       timing = (int)k.j.reset_i[(size_t)e * 2 + 1];
     } else {
       uint4 r = draw4(P.seed, step, e, kSiteResetI, 0);
-      int lo = 1 + (int)(0.002 / (double)P.dt), hi = 1 + (int)(0.01 / (double)P.dt + 0.5);
-      delay = lo + (int)(r.x % (uint32_t)(hi - lo));                               // T:652
-      timing = (int)(r.y % (uint32_t)(int)(8.0 / (double)P.dt_policy));            // T:665
+      delay = P.delay_lo + (int)(r.x % (uint32_t)(P.delay_hi - P.delay_lo));       // T:652
+      timing = (int)(r.y % (uint32_t)P.timing_hi);                                 // T:665
     }
     k.b.delay_idx[e] = delay;
     float el = k.b.epi_len[e];
@@ -279,7 +283,8 @@ __device__ void stage_reset_env(const TK& k, int e, int lane) {
     k.b.perturbation_count[e] = 0;                                                 // T:663
     k.b.pert_on[e] = 0;                                                            // T:664
     k.b.perturb_timing[e] = timing;                                                // T:665
-    if (P.randomize && k.b.randomize_buf[e] >= 1) k.b.randomize_buf[e] = 0;        // VT:540-544 (frequency 1)
+    if (dr) k.b.randomize_buf[e] = 0;                                              // VT:540-544 (frequency 1)
+    k.b.reset_seq[e] = k.b.reset_seq[e] + 1;
   }
 }
 

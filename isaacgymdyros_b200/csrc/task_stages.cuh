@@ -56,9 +56,8 @@ __device__ __forceinline__ void stage_push_schedule(const TK& k, int e) {
         u = k.j.pert_f[e];
       } else {
         uint4 r = draw4(P.seed, *P.step_counter, e, kSitePert, 0);
-        int lo = (int)(0.1 / (double)P.dt_policy), hi = (int)(1.0 / (double)P.dt_policy);
         imp = 50 + (int)(r.x % 200u);                                           // T:440 randint(50,250)
-        dur = lo + (int)(r.y % (uint32_t)(hi - lo));                            // T:441
+        dur = P.dur_lo + (int)(r.y % (uint32_t)(P.dur_hi - P.dur_lo));          // T:441
         u = u01(r.z);
       }
       on = 1;                                                                   // T:439

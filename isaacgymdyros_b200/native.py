@@ -10,7 +10,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-ABI_VERSION = 2  # include/dyros_b200.h DYROS_ABI_VERSION: struct layouts below mirror that header
+ABI_VERSION = 3  # include/dyros_b200.h DYROS_ABI_VERSION: struct layouts below mirror that header
 LIB_PATH = os.environ.get("DYROS_B200_LIB", os.path.join(_HERE, "libdyros_b200.so"))  # override: A/B builds only
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "dyros_b200.h")
 
@@ -64,7 +64,7 @@ TASK_BUFFERS = [
     ("impulse", "int32", ()), ("magnitude", "float32", ()), ("phase", "float32", ()), ("perturb_timing", "int32", ()),
     ("perturb_start", "int32", (None, 1)), ("push_force", "float32", (3,)),
     ("obs_history", "float32", (20, 37)), ("action_history", "float32", (20, 13)),
-    ("obs_hist_head", "int32", ()), ("act_hist_head", "int32", ()),
+    ("obs_hist_head", "int32", ()), ("act_hist_head", "int32", ()), ("reset_seq", "int32", ()),
 ]
 TASK_SHARED = ["mocap_data", "obs_mean", "obs_var"]
 TASK_OPTIONAL = [("pd_gain_scale", "float32", (2,))]  # allocated on request (CoreConfig.dr_pd_gain_range), else NULL

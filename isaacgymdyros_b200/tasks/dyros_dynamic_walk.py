@@ -232,8 +232,18 @@ class DyrosDynamicWalk:
         self.extras["time_outs"] = self.timeout_buf.to(self.rl_device)
         self.extras["stacked_rewards"] = self.stacked_rewards
         self.extras["reward_names"] = REWARD_NAMES
-        self.obs_dict["obs"] = self.obs_buf.to(self.rl_device)  # clipObservations = inf (VT:97-98): clamp is the identity
+        self.obs_dict["obs"] = self._obs_out()
         return self.obs_dict, self.rew_buf.to(self.rl_device), self.reset_buf.to(self.rl_device), self.extras
+
+    def _obs_out(self) -> torch.Tensor:
+        """VT:338 `torch.clamp(obs_buf, -clip_obs, clip_obs).to(rl_device)`. With a finite clipObservations that is a
+        fresh clamped tensor, as in the reference. With the yaml's default (no clipObservations: inf, VT:97-98) the clamp
+        is the identity and the env's own buffer is returned WITHOUT the copy the reference makes (8 MB per step at 4096
+        envs): the next `step` overwrites it, so a caller that keeps observations across steps must clone them (rl_games
+        copies them into its rollout buffer, a2c_common_dyros.py:641)."""
+        if np.isfinite(self.clip_obs):
+            return torch.clamp(self.obs_buf, -self.clip_obs, self.clip_obs).to(self.rl_device)
+        return self.obs_buf.to(self.rl_device)
 
     # ------------------------------------------------------------------ host-facing pipelined step
     def step_async(self, actions: torch.Tensor) -> int:
@@ -311,7 +321,7 @@ class DyrosDynamicWalk:
 
     def reset(self) -> Dict[str, torch.Tensor]:
         """VT:362-374: returns the observation buffer as is (zeros before the first step); resets nothing."""
-        self.obs_dict["obs"] = self.obs_buf.to(self.rl_device)
+        self.obs_dict["obs"] = self._obs_out()
         return self.obs_dict
 
     def reset_done(self):
@@ -319,7 +329,7 @@ class DyrosDynamicWalk:
         done = self.reset_buf.nonzero(as_tuple=False).squeeze(-1)
         if len(done) > 0:
             self.reset_idx(done)
-        self.obs_dict["obs"] = self.obs_buf.to(self.rl_device)
+        self.obs_dict["obs"] = self._obs_out()
         return self.obs_dict, done
 
     def reset_idx(self, env_ids: torch.Tensor):

@@ -94,6 +94,18 @@ class FakeGym:
         self.calls = []
         self.simulate_hook = None
         self._masses = masses
+        self.actuation = []   # tensors handed to set_dof_actuation_force_tensor (dyros_dynamic_walk.py:520), in call order
+        self.applied = []     # (forces, torques, space) handed to apply_rigid_body_force_tensors (:502)
+
+    def set_dof_actuation_force_tensor(self, sim, tensor):
+        self.calls.append("set_dof_actuation_force_tensor")
+        self.actuation.append(tensor.detach().clone())
+        return True
+
+    def apply_rigid_body_force_tensors(self, sim, forces, torques, space):
+        self.calls.append("apply_rigid_body_force_tensors")
+        self.applied.append((forces.detach().clone(), torques.detach().clone(), space))
+        return True
 
     def get_actor_rigid_body_properties(self, env, handle):
         self.calls.append("get_actor_rigid_body_properties")

@@ -123,6 +123,8 @@ def run_scenario(name, N, steps, seed, *, force_perturb=False, near_timeout=Fals
         sim_out.clear()
         actions = torch.tensor(rng.uniform(-1.2, 1.2, (N, 13)), dtype=torch.float)
         s.gym.calls.clear()
+        s.gym.actuation.clear()
+        s.gym.applied.clear()
         with DrawRecorder() as rec:
             ref_harness.reference_step(s, actions)
         # ---- map the draw log to env-indexed rows (SURVEY A6 order)
@@ -168,6 +170,20 @@ def run_scenario(name, N, steps, seed, *, force_perturb=False, near_timeout=Fals
                 out[f"s{t}/sim{j}/{k}"] = v
         for k, v in noise.items():
             out[f"s{t}/noise/{k}"] = v
+        # the two tensors the reference hands to the simulator (north star: PD torques within 1e-5)
+        assert len(s.gym.actuation) == 2
+        for j, tau in enumerate(s.gym.actuation):
+            out[f"s{t}/tau{j}"] = tau.numpy().reshape(N, 33)        # dyros_dynamic_walk.py:520
+        push = np.zeros((N, 3), np.float32)
+        if s.gym.applied:                                           # dyros_dynamic_walk.py:493-502
+            assert len(s.gym.applied) == 1
+            forces, torques, space = s.gym.applied[0]
+            assert space == 0 and not torques.any()
+            nz = forces.clone()
+            nz[:, s.pelvis_idx] = 0
+            assert not nz.any(), "only the pelvis is pushed"
+            push = forces[:, s.pelvis_idx].numpy().copy()
+        out[f"s{t}/push"] = push
         out[f"s{t}/env_ids"] = ids.astype(np.int64)
         out[f"s{t}/stacked_rewards"] = s.extras["stacked_rewards"].clone().numpy()
         for k, v in snapshot(s).items():

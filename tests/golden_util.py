@@ -34,6 +34,9 @@ class Golden:
             p = f"s{t}/"
             d = {"actions": z[p + "actions"], "env_ids": z[p + "env_ids"], "stacked_rewards": z[p + "stacked_rewards"],
                  "sim": [{k.split("/")[-1]: z[k] for k in z.files if k.startswith(f"{p}sim{j}/")} for j in range(2)],
+                 # what the reference handed to set_dof_actuation_force_tensor (T:520, per substep) and the pelvis row
+                 # of apply_rigid_body_force_tensors (T:498-502)
+                 "tau": [z[f"{p}tau{j}"] for j in range(2)], "push": z[p + "push"],
                  "noise": {k.split("/")[-1]: z[k] for k in z.files if k.startswith(p + "noise/")},
                  "after": {k.split("/")[-1]: z[k] for k in z.files if k.startswith(p + "after/")}}
             self.step.append(d)

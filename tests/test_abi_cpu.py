@@ -28,7 +28,7 @@ def test_header_symbols_all_exported(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.dyros_abi_version() == native.ABI_VERSION == 2
+    assert lib.dyros_abi_version() == native.ABI_VERSION == 3
     # NULL handles are rejected with a message and no CUDA call
     assert lib.dyros_simulate(None, 0, None) != 0
     assert b"sim is NULL" in lib.dyros_last_error()

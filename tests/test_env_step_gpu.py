@@ -285,6 +285,7 @@ def test_optional_friction_and_pd_gain_randomisation():
     assert mu0.min() >= 0.7 - 1e-6 and mu0.max() <= 1.3 + 1e-6 and mu0.std() > 0.1
     assert g0.min() >= 0.9 - 1e-6 and g0.max() <= 1.1 + 1e-6 and g0.std() > 0.03
     ids = torch.arange(0, N, 2, device="cuda:0")
+    env.randomize_buf.fill_(1)  # VT:540-544: only envs whose randomize_buf reached the frequency (1) are re-drawn
     env.reset_idx(ids)
     torch.cuda.synchronize()
     mu1, g1 = env.core.sim_t["contact_friction"], env.core.task_t["pd_gain_scale"]
@@ -308,6 +309,7 @@ def test_domain_randomisation_redraw_on_reset_ranges():
     env = DyrosDynamicWalk(default_cfg(N, randomize=True), "cuda:0", use_cuda_graph=False)
     d0 = env.core.sim_t["dof_damping"].clone()
     ids = torch.arange(0, N, 2, device="cuda:0")
+    env.randomize_buf.fill_(1)  # VT:540-544
     env.reset_idx(ids)
     torch.cuda.synchronize()
     d1, a1 = env.core.sim_t["dof_damping"], env.core.sim_t["dof_armature"]

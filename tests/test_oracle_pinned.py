@@ -17,10 +17,13 @@ def oracle_from_golden(g):
     return s, c
 
 
-def inject_sim(outs):
+def inject_sim(outs, seen=None):
     it = iter(outs)
 
     def simulate(s, tau, ext):
+        if seen is not None:  # what the oracle hands to the simulator
+            seen["tau"].append(tau.copy())
+            seen["ext"].append(None if ext is None else ext.copy())
         o = next(it)
         for k, v in o.items():
             s[k] = v.copy()
@@ -33,8 +36,14 @@ def test_oracle_matches_golden(name):
     s, c = oracle_from_golden(g)
     saw_reset = False
     for t, st in enumerate(g.step):
-        ids = O.step(s, c, st["actions"], st["noise"], inject_sim(st["sim"]))
+        seen = {"tau": [], "ext": []}
+        ids = O.step(s, c, st["actions"], st["noise"], inject_sim(st["sim"], seen))
         assert np.array_equal(ids, st["env_ids"]), f"step {t}: compacted reset ids differ"
+        # the simulator inputs (north star: PD torques within 1e-5): T:520 per substep, T:498-502 push on substep 0 only
+        for j in range(2):
+            assert_field(f"tau{j}", seen["tau"][j], st["tau"][j], "float", ctx=f"{name} step {t} ")
+        assert_field("push", seen["ext"][0], st["push"], "float", ctx=f"{name} step {t} ")
+        assert seen["ext"][1] is None
         saw_reset |= len(ids) > 0
         for k, kind in COMPARE.items():
             assert_field(k, s[k], st["after"][k], kind, ctx=f"{name} step {t} ")
@@ -45,6 +54,7 @@ def test_oracle_matches_golden(name):
 
 def test_golden_perturb_scenario_pushes():
     g = Golden("walk_perturb")
+    assert any(np.abs(st["push"]).max() > 100 for st in g.step), "the golden must hold non-zero pelvis pushes"
     assert any(st["after"]["pert_on"].any() for st in g.step)
     assert any((st["after"]["magnitude"] > 0).any() for st in g.step)
 

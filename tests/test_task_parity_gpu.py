@@ -74,12 +74,19 @@ def inject_noise(core, noise):
         pert_f=torch.tensor(noise["pert_f"], device=dev).contiguous())
 
 
-def staged_step(core, actions, sim_outputs):
-    """VT:293-344 + T:449-563 as the staged C-ABI calls; sim_outputs[k] replaces gym.simulate #k (T:525)."""
+def staged_step(core, actions, sim_outputs, sim_inputs=None):
+    """VT:293-344 + T:449-563 as the staged C-ABI calls; sim_outputs[k] replaces gym.simulate #k (T:525).
+    `sim_inputs` (dict) receives what the kernels hand to the simulator: the actuation forces of each substep (T:520)
+    and the pelvis push (T:498-502)."""
     dev, N = core.device, core.N
     core.prologue(torch.tensor(actions, device=dev).contiguous())
+    if sim_inputs is not None:
+        sim_inputs["push"] = core.task_t["push_force"].cpu().numpy().copy()
+        sim_inputs["tau"] = []
     for k in range(2):
         core.substep_torque()
+        if sim_inputs is not None:
+            sim_inputs["tau"].append(core.sim_t["dof_actuation_force"].view(N, 33).cpu().numpy().copy())
         o = sim_outputs[k]
         core.sim_t["root_states"].copy_(torch.tensor(o["root_states"], device=dev))
         ds = core.sim_t["dof_state"].view(N, 33, 2)
@@ -110,8 +117,12 @@ def test_cuda_task_kernels_match_reference_golden(name):
     load_state(core, g.init)
     for t, st in enumerate(g.step):
         inject_noise(core, st["noise"])
-        ids = staged_step(core, st["actions"], st["sim"])
+        seen = {}
+        ids = staged_step(core, st["actions"], st["sim"], seen)
         assert np.array_equal(ids, st["env_ids"]), f"{name} step {t}: compacted reset ids differ"
+        for j in range(2):  # simulator inputs vs the tensors the reference passed to gym (T:520, T:502)
+            assert_field(f"tau{j}", seen["tau"][j], st["tau"][j], "float", ctx=f"{name} step {t} ")
+        assert_field("push", seen["push"], st["push"], "float", ctx=f"{name} step {t} ")
         got = read_state(core)
         for k, kind in COMPARE.items():
             assert_field(k, got[k], st["after"][k], kind, ctx=f"{name} step {t} ")
@@ -160,13 +171,22 @@ def test_cuda_task_kernels_match_oracle(N, steps, perturb):
         actions = rng.uniform(-1.2, 1.2, (N, 13)).astype(np.float32)
         outs = []
 
+        want_tau, want_push = [], []
+
         def simulate(st, tau, ext):
+            want_tau.append(tau.copy())
+            if ext is not None:
+                want_push.append(ext.copy())
             scripted_sim(rng, st, N)
             outs.append({k: st[k].copy() for k in ("root_states", "dof_pos", "dof_vel", "contact_forces")})
         want_ids = O.step(s, c, actions, noise, simulate)
         inject_noise(core, noise)
-        ids = staged_step(core, actions, outs)
+        seen = {}
+        ids = staged_step(core, actions, outs, seen)
         assert np.array_equal(ids, want_ids), f"step {t}: compacted reset ids differ"
+        for j in range(2):
+            assert_field(f"tau{j}", seen["tau"][j], want_tau[j], "float", ctx=f"N={N} step {t} ")
+        assert_field("push", seen["push"], want_push[0], "float", ctx=f"N={N} step {t} ")
         got = read_state(core)
         for k, kind in COMPARE.items():
             assert_field(k, got[k], s[k], kind, ctx=f"N={N} step {t} ")

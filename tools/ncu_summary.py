@@ -1,5 +1,8 @@
 """Summarise an .ncu-rep (and optionally a launch-list csv) into a small text file for profiles/.
     python tools/ncu_summary.py gpurun_out/prof.ncu-rep [gpurun_out/launches.csv] > profiles/rN_<kernel>.txt
+    python tools/ncu_summary.py --json <envs> <summary-file-name> gpurun_out/prof.ncu-rep   # updates profiles/current.json
+The second form records the executed FLOP and the DRAM bytes of the k_step_physics launch in profiles/current.json,
+which bench.py reads for `fp32` and `roofline.traffic` (so those always describe the build that is benchmarked).
 """
 import collections
 import csv
@@ -19,7 +22,37 @@ KEYS = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_
 STALLS = "smsp__average_warps_issue_stalled_"
 
 
+def write_json(envs, source, rep):
+    import json
+    import os
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    H, units, data = rows[0], rows[1], rows[2:]
+    ki = H.index("Kernel Name")
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "current.json")
+    cur = json.load(open(path)) if os.path.isfile(path) else {}
+
+    def val(r, name):
+        i = H.index(name)
+        x = float(r[i])
+        return x * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}.get(units[i], 1.0)
+
+    for r in data:
+        for kern in ("k_step_physics", "k_post_fused"):
+            if kern in r[ki]:
+                cyc = val(r, "sm__cycles_elapsed.max")
+                fl = sum(val(r, f"smsp__sass_thread_inst_executed_op_{o}_pred_on.sum.per_cycle_elapsed") * w
+                         for o, w in (("ffma", 2), ("fadd", 1), ("fmul", 1))) * cyc
+                cur[kern] = {"envs": int(envs), "flop": fl, "dram_bytes": val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum"),
+                             "duration_us_under_ncu": val(r, "gpu__time_duration.sum") / (1.0 if units[H.index("gpu__time_duration.sum")] == "us" else 1e3),
+                             "source": source}
+    json.dump(cur, open(path, "w"), indent=1)
+    print(json.dumps(cur))
+
+
 def main():
+    if sys.argv[1] == "--json":
+        return write_json(sys.argv[2], sys.argv[3], sys.argv[4])
     rep = sys.argv[1]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
