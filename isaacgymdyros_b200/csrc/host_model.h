@@ -36,7 +36,7 @@ static const T* at(void* base, size_t off) {
 }
 
 struct ModelOffsets {
-  size_t parent, dof, E, r, ax, cs, ch, bs, bd, bl, bp, br, bi, lo, up, vl, ef, ps, pb, pp, pr, ys, yb, yc, ya, yz, sc, rc, ro, dl, pg;
+  size_t parent, dof, E, r, ax, cs, ch, bs, bd, bl, bp, br, bi, lo, up, vl, ef, ps, pb, pp, pr, ys, yb, yc, ya, yz, sc, rc, ro, dl, pg, fp, fb;
 };
 
 // Fills `dm` (counts, foot tables) and appends every table to `bl`. Returns "" or an error message.
@@ -212,6 +212,7 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
     std::vector<int> rec_of(nl, 0);
     for (size_t k = 0; k < order.size(); ++k) rec_of[order[k]] = (int)k;
     std::vector<int> prog(order.size() * REC_WORDS, 0);
+    int n_cslot = 0;
     auto F = [&](size_t k, int field) -> float& { return reinterpret_cast<float*>(prog.data())[k * REC_WORDS + field]; };
     for (size_t k = 0; k < order.size(); ++k) {
       const int l = order[k];
@@ -250,6 +251,23 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
       R[R_FOOT] = -1;
       for (int f = 0; f < dm.num_feet; ++f)
         if (dm.foot_link[f] == l) R[R_FOOT] = f;
+      // multi-lane program: results travel in registers between consecutive links of a role; everything else goes
+      // through the scratch block. R_CSLOT: this link's parent is not the previous link of the role (the base, for the
+      // first link of the base role); RF_KEEP: a same-role child of this link is not the role's next link.
+      R[R_CSLOT] = -1;
+      if (l > 0) {
+        const int g = role_of[l];
+        int t = 0;
+        while (m->sched[t * DYROS_LANES + g] != l) ++t;
+        const int before = t > 0 ? m->sched[(t - 1) * DYROS_LANES + g] : (g == dm.base_role ? 0 : -1);
+        if (par != before) {
+          if (n_cslot >= MAX_CSLOTS) MFAIL("more than %d links whose parent is not their role's previous link", MAX_CSLOTS);
+          R[R_CSLOT] = n_cslot++;
+        }
+        const int after = t + 1 < role_len[g] ? m->sched[(t + 1) * DYROS_LANES + g] : -1;
+        for (int ci = child_start[l]; ci < child_start[l + 1]; ++ci)
+          if (role_of[children[ci]] == g && children[ci] != after) R[R_FLAGS] |= RF_KEEP;
+      }
     }
     o.pg = bl.add_i(prog.data(), prog.size());
     for (int f = 0; f < dm.num_feet; ++f)
@@ -270,6 +288,18 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
   std::vector<int> dof_link(nd, 0);
   for (int l = 1; l < nl; ++l) dof_link[m->link_dof[l]] = l;
   o.dl = bl.add_i(dof_link.data(), nd);
+  {  // solver-point candidates of the feet (read with a per-lane index by the multi-lane kernel: staged, not in DevModel)
+    std::vector<float> fp(MAX_FEET * MAX_SOLVER_PTS * 4, 0.f);
+    std::vector<int> fb(MAX_FEET * MAX_SOLVER_PTS, 0);
+    for (int f = 0; f < dm.num_feet; ++f)
+      for (int k = 0; k < dm.foot_npts[f]; ++k) {
+        for (int c = 0; c < 3; ++c) fp[(f * MAX_SOLVER_PTS + k) * 4 + c] = dm.foot_pt_pos[f][k][c];
+        fp[(f * MAX_SOLVER_PTS + k) * 4 + 3] = dm.foot_pt_radius[f][k];
+        fb[f * MAX_SOLVER_PTS + k] = dm.foot_pt_body[f][k];
+      }
+    o.fp = bl.add_f32(fp.data(), fp.size());
+    o.fb = bl.add_i(fb.data(), fb.size());
+  }
   dm.hot_bytes = (int)((bl.host.size() + 15) & ~size_t(15));
   // cold tables (global memory): penalty candidates (read only when a link is near the ground), rigid_body_state
   // kinematics, and the unflattened tree
@@ -297,6 +327,7 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
   dm.o_lower = (int)(o.lo / 4); dm.o_upper = (int)(o.up / 4); dm.o_vel_limit = (int)(o.vl / 4);
   dm.o_effort = (int)(o.ef / 4); dm.o_pt_start = (int)(o.ps / 4); dm.o_cyl_start = (int)(o.ys / 4);
   dm.o_sched = (int)(o.sc / 4); dm.o_reach = (int)(o.rc / 4); dm.o_role_of = (int)(o.ro / 4); dm.o_dof_link = (int)(o.dl / 4); dm.o_prog = (int)(o.pg / 4);
+  dm.o_foot_pts = (int)(o.fp / 4); dm.o_foot_body = (int)(o.fb / 4);
 
   return std::string();
 #undef MFAIL

@@ -15,12 +15,16 @@ constexpr int MAX_FEET = 2;    // solver links
 constexpr int MAX_SOLVER_PTS = 8;  // candidate solver points per foot
 constexpr int MAX_ACTIVE_PTS = 4;  // active (constraint-solved) points per foot and sub-step
 // record of one link in the flattened role programs (word offsets; ints and floats share the table)
-constexpr int REC_WORDS = 40, MAX_LINK_BODIES = 3, MAX_LINK_CHILDREN = 3, REC_FOREIGN = 1 << 30;
+constexpr int REC_WORDS = 44, MAX_LINK_BODIES = 3, MAX_LINK_CHILDREN = 3, REC_FOREIGN = 1 << 30;
+// (44 words: a multiple of 4 so that the 3-vectors below sit on 16-byte boundaries, and 44 mod 32 = 12 so that the 8
+//  lanes of a group reading 8 consecutive records hit 8 different shared-memory banks)
 constexpr int R_LINK = 0, R_PARENT = 1, R_FLAGS = 2, R_DOF = 3, R_NBODY = 4, R_BODY0 = 5, R_NCHILD = 8, R_CHILD0 = 9,
-              R_AXIS = 12, R_R = 15, R_E = 18, R_REACH = 27, R_PT0 = 28, R_PT1 = 29, R_CYL0 = 30, R_CYL1 = 31,
-              R_VLIM = 32, R_LO = 33, R_UP = 34, R_EFF = 35, R_FOOT = 36, R_STIFF = 37;
+              R_AXIS = 12, R_R = 16, R_E = 20, R_REACH = 32, R_PT0 = 33, R_PT1 = 34, R_CYL0 = 35, R_CYL1 = 36,
+              R_VLIM = 37, R_LO = 38, R_UP = 39, R_EFF = 40, R_FOOT = 41, R_STIFF = 42, R_CSLOT = 43;
 constexpr int RF_PARENT_FOREIGN = 1, RF_PARENT_BASE = 2;
 constexpr int RF_PUBLISH = 4;  // a child of the link lives in another role: its stage flags are read there
+constexpr int RF_KEEP = 8;     // a child of the link in the SAME role is not the role's next link: results go through the block
+constexpr int MAX_CSLOTS = 8;  // links whose parent is not the role's previous link (R_CSLOT: their index, else -1)
 struct DevModel {
   int nl, nb, nd, np, nc, T;
   const int* link_parent;
@@ -56,6 +60,8 @@ struct DevModel {
   // word offsets of the hot tables inside the staged prefix (same order as the pointers above)
   int o_parent, o_dof, o_E, o_r, o_axis, o_child_start, o_children, o_body_start, o_bodies, o_body_inertia, o_lower,
       o_upper, o_vel_limit, o_effort, o_pt_start, o_cyl_start, o_sched, o_reach, o_role_of, o_dof_link;
+  int o_foot_pts;   // hot: [MAX_FEET][MAX_SOLVER_PTS][4] = candidate position (3) and radius of the solver points
+  int o_foot_body;  // hot: [MAX_FEET][MAX_SOLVER_PTS] body index of each candidate
   int base_role, foot_role[MAX_FEET], role_len[DYROS_LANES];
   // flattened role programs: one record of REC_WORDS words per link, base first, then role 0's links in order, ...
   int o_prog, prog_start[DYROS_LANES], chain_rec[MAX_FEET][MAX_CHAIN];

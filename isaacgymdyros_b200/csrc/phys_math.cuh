@@ -4,7 +4,7 @@
 #pragma once
 #include <math.h>
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) && !defined(DYROS_LANE_EMU)
 #define HD __host__ __device__ __forceinline__
 #else
 #define HD inline
@@ -47,7 +47,11 @@ HD V3 ld3(const real* p) { return V3{p[0], p[1], p[2]}; }
 template <class F>
 HD V3 ld3_f(const F* p) { return V3{(real)p[0], (real)p[1], (real)p[2]}; }  // from float tables / tensors
 #endif
+#if defined(DYROS_LANE_EMU)  // host emulation of a lane group (tests/native/lane_emu.h): `real` is a vector of lanes
+HD real fmin_r(real a, real b) { return sel(a < b, a, b); }
+#else
 HD real fmin_r(real a, real b) { return a < b ? a : b; }
+#endif
 HD void sincos_r(real x, real* s, real* c) {
 #if defined(__CUDA_ARCH__)
   float sf, cf;

@@ -82,7 +82,34 @@ def hostemu():
     return _EMU
 
 
-def emulate_substep(tables, cfg, st, push=None, rb_force=None, rb_torque=None, friction=None):
+_EMU_LANES = {}
+
+
+def hostemu_lanes(scalar="float"):
+    """CPU build of the multi-lane program (csrc/physics_lanes.cuh through tests/native/lane_emu.h); scalar = "double"
+    runs the same program in float64."""
+    if scalar not in _EMU_LANES:
+        so = os.path.join(HERE, "native", f"libdyros_hostemu_lanes_{scalar}.so")
+        src = os.path.join(HERE, "native", "hostemu_lanes.cu")
+        deps = [src, os.path.join(HERE, "native", "lane_emu.h")] + [
+            os.path.join(CSRC, f) for f in ("physics_lanes.cuh", "lanes.cuh", "phys_math.cuh", "host_model.h", "internal.h")]
+        if not os.path.isfile(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            subprocess.check_call(["nvcc", "-O1", "-std=c++20", "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "20014",
+                                   "-Wno-deprecated-gpu-targets", f"-DEMU_SCALAR={scalar}", "-I", CSRC, "-o", so, src])
+        lib = C.CDLL(so)
+        lib.dyros_hostemu_lanes_simulate.restype = C.c_int
+        lib.dyros_hostemu_lanes_cta_smem_bytes.restype = C.c_long
+        _EMU_LANES[scalar] = lib
+    return _EMU_LANES[scalar]
+
+
+def emulate_substep_lanes(tables, cfg, st, push=None, rb_force=None, rb_torque=None, friction=None, scalar="float"):
+    """Runs the multi-lane program of the CUDA kernel on the CPU. Returns root', q', qd', contact like the oracle."""
+    return emulate_substep(tables, cfg, st, push, rb_force, rb_torque, friction,
+                           fn=hostemu_lanes(scalar).dyros_hostemu_lanes_simulate)
+
+
+def emulate_substep(tables, cfg, st, push=None, rb_force=None, rb_torque=None, friction=None, fn=None):
     """Runs the kernel's lane program on the CPU (float32). Returns root', q', qd', contact like the oracle."""
     N = st["root"].shape[0]
     md, keep = make_model_desc(tables, cfg)
@@ -98,7 +125,7 @@ def emulate_substep(tables, cfg, st, push=None, rb_force=None, rb_torque=None, f
     rt = f32(rb_torque) if rb_torque is not None else None
     err = C.create_string_buffer(256)
     mu = f32(friction) if friction is not None else None
-    rc = hostemu().dyros_hostemu_simulate(C.byref(sd), C.byref(md), P(root), P(dof), P(tau), P(damp), P(arm), P(ms),
+    rc = (fn or hostemu().dyros_hostemu_simulate)(C.byref(sd), C.byref(md), P(root), P(dof), P(tau), P(damp), P(arm), P(ms),
                                           P(contact), P(pf), P(rf), P(rt), P(mu), err, 256)
     assert rc == 0, err.value
     return root.astype(np.float64), dof[:, :, 0].astype(np.float64), dof[:, :, 1].astype(np.float64), contact.astype(np.float64)
