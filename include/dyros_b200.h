@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DYROS_ABI_VERSION 3  /* 3: DyrosTaskBuffers.reset_seq; 2: contact_friction, pd_gain_scale, dr_friction_*, dr_pd_gain_*, pack_results, set_obs_buf, post_step */
+#define DYROS_ABI_VERSION 3  /* 3: DyrosTaskBuffers.reset_seq, DyrosSimDesc.physics_program; 2: contact_friction, pd_gain_scale, dr_friction_*, dr_pd_gain_*, pack_results, set_obs_buf, post_step */
 #define DYROS_MAX_LINKS 40
 #define DYROS_MAX_BODIES 48
 #define DYROS_LANES 4 /* roles (warps) per env group in the physics kernel */
@@ -84,6 +84,9 @@ typedef struct {
   float penalty_max_force;  /* clamp of one penalty point's normal force (N) */
   float max_angular_velocity; /* AssetOptions.max_angular_velocity T:289 */
   int32_t clamp_effort;     /* clamp actuation to MJCF ctrlrange (default 0) */
+  int32_t physics_program;  /* mapping of gym.simulate to the GPU: 0 = one lane per env, one warp per role (default, the
+                               faster one at <= 28 envs per SM); 1 = 8 lanes per env with column-distributed articulated
+                               inertias. Same model, same results up to float rounding. */
 } DyrosSimDesc;
 
 /* Device buffers behind the gym tensor API (all owned by the caller). */

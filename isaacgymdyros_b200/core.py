@@ -74,6 +74,7 @@ class CoreConfig:
     solver_bodies: tuple = ("L_Foot_Link", "R_Foot_Link")
     with_rigid_body_state: bool = False  # DyrosDynamicWalk never reads it (T:76,85)
     with_rb_force_tensors: bool = False  # generic apply_rigid_body_force_tensors buffers
+    physics_program: str = "roles"       # "roles": one lane per env, warp per role (default); "lanes": 8 lanes per env
 
 
 def stable_penalty(dt_substep: float, m_ref: float = 0.3):
@@ -141,6 +142,7 @@ def make_sim_desc(cfg: "CoreConfig", num_envs: int, device_index: int = 0):
     sd.penalty_max_force = cfg.penalty_max_force
     sd.max_angular_velocity = cfg.max_angular_velocity
     sd.clamp_effort = int(cfg.clamp_effort)
+    sd.physics_program = {"roles": 0, "lanes": 1}[cfg.physics_program]
     return sd
 
 

@@ -36,6 +36,7 @@ static int build_sim(const DyrosSimDesc* d, const DyrosModelDesc* m, const Dyros
   REQUIRE(d && m && b && out, "dyros_sim_create: null argument");
   REQUIRE(d->num_envs > 0, "dyros_sim_create: num_envs must be positive (got %d)", d->num_envs);
   REQUIRE(d->substeps >= 1 && d->dt > 0, "dyros_sim_create: need dt > 0 and substeps >= 1");
+  REQUIRE(d->physics_program == 0 || d->physics_program == 1, "dyros_sim_create: physics_program %d (0 = roles, 1 = lanes)", d->physics_program);
   REQUIRE(d->contact_sweeps >= 0 && d->contact_sweeps <= 64, "dyros_sim_create: contact_sweeps %d", d->contact_sweeps);
   REQUIRE(b->root_states && b->dof_state && b->net_contact_force && b->dof_actuation_force && b->dof_damping &&
               b->dof_armature && b->body_mass_scale,
@@ -43,6 +44,7 @@ static int build_sim(const DyrosSimDesc* d, const DyrosModelDesc* m, const Dyros
   Sim* sim = new (std::nothrow) Sim();
   REQUIRE(sim, "out of host memory");
   sim->device = d->device;
+  sim->program = d->physics_program;
   fill_sim_params(d, sim->p);
   sim->b = *b;
   Blob bl;
@@ -298,7 +300,7 @@ int dyros_sim_launch_info(DyrosSim* sim, int32_t out[4]) {
   }
   out[0] = s->envs_per_block;
   out[1] = (s->p.N + s->envs_per_block - 1) / s->envs_per_block;
-  out[2] = DYROS_LANES * 32;
+  out[2] = physics_step_threads(s);
   out[3] = (int32_t)s->phys_smem;
   return 0;
 }

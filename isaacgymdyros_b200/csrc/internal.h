@@ -126,7 +126,8 @@ struct Sim {
   void* dev_blob = nullptr;  // one allocation holding every model table
   int device = 0;
   int sm_count = 148;
-  int envs_per_block = 0;    // physics kernel: envs per CTA (DYROS_LANES threads each)
+  int program = 0;           // physics program: 0 = one lane per env, warp per role (physics_roles.cuh); 1 = 8 lanes per env (physics_lanes.cuh)
+  int envs_per_block = 0;    // physics kernel: envs per CTA
   size_t phys_smem = 0;      // dynamic shared memory of one physics CTA
 };
 
@@ -158,5 +159,11 @@ int launch_refresh_rigid_body_state(Sim* sim, cudaStream_t s);
 // skipframe x (torque, simulate, sensor noise) in one launch; with `actions` the policy-step prologue runs in it too
 int launch_task_physics(Task* t, cudaStream_t s, long long* trace = nullptr, bool pdl = false, const float* actions = nullptr);
 int measure_fp32_peak(int device, int iters, double* tflops_out);
+int physics_step_threads(const Sim* sim);  // threads of a k_step_physics CTA (role warps + I/O warps)
+// the multi-lane variant (physics_lanes_kernels.cu)
+int physics_configure_lanes(Sim* sim);
+int launch_simulate_lanes(Sim* sim, int apply_wrench, const float* push_force, cudaStream_t s);
+int launch_task_physics_lanes(Task* t, cudaStream_t s, long long* trace, bool pdl, const float* actions);
+int physics_step_threads_lanes(const Sim* sim);
 
 }  // namespace dyros

@@ -33,7 +33,7 @@ class DyrosSimDesc(C.Structure):
     _fields_ = [("num_envs", i32), ("device", i32), ("dt", f64), ("substeps", i32), ("gravity", f32 * 3),
                 ("contact_offset", f32), ("max_depenetration_velocity", f32), ("contact_sweeps", i32),
                 ("contact_erp", f32), ("friction", f32), ("penalty_stiffness", f32), ("penalty_damping", f32),
-                ("penalty_max_force", f32), ("max_angular_velocity", f32), ("clamp_effort", i32)]
+                ("penalty_max_force", f32), ("max_angular_velocity", f32), ("clamp_effort", i32), ("physics_program", i32)]
 
 
 SIM_BUFFERS = ["root_states", "dof_state", "net_contact_force", "rigid_body_state", "dof_actuation_force", "rb_force",

@@ -68,10 +68,7 @@ extern "C" int dyros_hostemu_simulate(const DyrosSimDesc* d, const DyrosModelDes
           env_substep_role(mine, scratch.data(), flags.data(), s, hot, m, p, role, sync);
           bar.arrive_and_wait();
           env_store_outputs(mine, scratch.data(), hot, m, role, DYROS_LANES);
-          bar.arrive_and_wait();
-          mine.push = nullptr;
-          mine.rb_force = nullptr;
-          mine.rb_torque = nullptr;
+          bar.arrive_and_wait();  // (applied wrenches act over the whole simulate() call: all of its sub-steps)
         }
       });
     for (auto& t : th) t.join();

@@ -66,7 +66,7 @@ extern "C" int dyros_hostemu_lanes_simulate(const DyrosSimDesc* d, const DyrosMo
       for (int i = 0; i < es; ++i) sm[i] = 0.f;
       for (int b = 0; b < m.nb; ++b) X[ln::X_MASS + b] = mass_scale[(size_t)env * m.nb + b];
       for (int k = 0; k < 13; ++k) X[ln::X_ROOT + k] = croot[k];
-      for (int k = 0; k < 3; ++k) X[ln::X_PUSH + k] = (push && s == 0) ? push[(size_t)env * 3 + k] : 0.f;
+      for (int k = 0; k < 3; ++k) X[ln::X_PUSH + k] = push ? push[(size_t)env * 3 + k] : 0.f;
       X[ln::X_MU] = friction ? friction[env] : p.mu;
       for (int k = 0; k < 3 * m.nb; ++k) io.contact[k] = 0.f;  // net contact force of THIS sub-step only
       for (int i = 1; i < m.nl; ++i) {
@@ -78,12 +78,7 @@ extern "C" int dyros_hostemu_lanes_simulate(const DyrosSimDesc* d, const DyrosMo
         L[ln::B_SC + 1] = damping[(size_t)env * m.nd + dd];
         L[ln::B_SC + 2] = armature[(size_t)env * m.nd + dd];
       }
-      ln::EnvIO mine = io;
-      if (s > 0) {  // applied wrenches act on the first sub-step only
-        mine.push = false;
-        mine.rb_force = nullptr;
-        mine.rb_torque = nullptr;
-      }
+      ln::EnvIO mine = io;  // applied wrenches act over the whole simulate() call, i.e. all of its sub-steps
       std::vector<std::thread> th;
       for (int role = 0; role < DYROS_LANES; ++role)
         th.emplace_back([&, role]() {

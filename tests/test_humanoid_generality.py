@@ -10,7 +10,7 @@ import pytest
 from isaacgymdyros_b200.core import ASSETS, CoreConfig, stable_penalty
 from isaacgymdyros_b200.model.tables import ModelTables, role_programs
 from oracle.physics_oracle import PhysicsOracle
-from tests.physics_util import emulate_substep, oracle_params
+from tests.physics_util import emulate_substep, emulate_substep_lanes, oracle_params
 from tests.test_physics_emulation import compare
 
 HUMANOID_CFG = dict(dt=0.0166, substeps=1, contact_offset=0.02, num_position_iterations=4, num_velocity_iterations=0,
@@ -71,14 +71,16 @@ def test_humanoid_tables_known_answers():
     assert links == list(range(1, 22))
 
 
+@pytest.mark.parametrize("program", ["roles", "lanes"])
 @pytest.mark.parametrize("kind,seed", [("air", 0), ("stand", 1), ("mixed", 2)])
-def test_humanoid_lane_program_matches_dense_oracle(kind, seed):
+def test_humanoid_lane_program_matches_dense_oracle(kind, seed, program):
+    """`roles`: the single-lane statement of the algorithm; `lanes`: the 8-lanes-per-env program the CUDA kernels run."""
     t = humanoid()
     cfg = CoreConfig(**HUMANOID_CFG)
     o = PhysicsOracle(t, oracle_params(cfg), solver_bodies=cfg.solver_bodies)
     st = humanoid_states(8, np.random.default_rng(seed), t, kind)
     want = o.substep(st["root"], st["q"], st["qd"], st["tau"], st["damping"], st["armature"], st["mass_scale"])
-    got = emulate_substep(t, cfg, st)
+    got = (emulate_substep if program == "roles" else emulate_substep_lanes)(t, cfg, st)
     compare(st, got, want, ctx=f"humanoid {kind}: ")
     if kind == "stand":
         feet = [t.body_names.index("right_foot"), t.body_names.index("left_foot")]

