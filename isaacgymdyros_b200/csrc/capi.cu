@@ -174,6 +174,8 @@ static int build_task(Sim* sim, const DyrosTaskDesc* d, const DyrosTaskBuffers* 
   size_t o_ct = bl.add(&zero, sizeof(zero));
   unsigned long long zeros4[4] = {0, 0, 0, 0};
   size_t o_tail = bl.add(zeros4, sizeof(zeros4));
+  std::vector<unsigned> scan0(2 + (size_t)(sim->p.N + 1023) / 1024, 0u);
+  size_t o_scan = bl.add(scan0.data(), scan0.size() * sizeof(unsigned));
   cudaError_t e = cudaMalloc(&t->dev_blob, bl.host.size());
   if (e == cudaSuccess) e = cudaMemcpy(t->dev_blob, bl.host.data(), bl.host.size(), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
@@ -187,6 +189,7 @@ static int build_task(Sim* sim, const DyrosTaskDesc* d, const DyrosTaskBuffers* 
   p.reset_dof_pos = at<float>(base, o_rp); p.init_dof_pos = at<float>(base, o_ip); p.armature_base = at<float>(base, o_ar);
   p.step_counter = const_cast<uint64_t*>(at<uint64_t>(base, o_ct));
   p.tail = const_cast<unsigned long long*>(at<unsigned long long>(base, o_tail));
+  p.scan_state = const_cast<unsigned*>(at<unsigned>(base, o_scan));
   *out = t;
   return 0;
 }

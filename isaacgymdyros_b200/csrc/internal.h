@@ -117,6 +117,7 @@ struct TaskParams {
   const float* armature_base;
   uint64_t* step_counter;       // device, Philox epoch; bumped once per step by the cross-env pass
   unsigned long long* tail;     // device [4]: fixed-point sums of the two gate means, CTA ticket of the fused post-physics launch
+  unsigned* scan_state;         // device [2 + ceil(N/1024)]: tile ticket, tiles finished, per-tile counts of the id compaction
 };
 
 struct Sim {

@@ -443,149 +443,401 @@ __device__ __forceinline__ void prefetch_rows_l2(const void* p, int bytes, int l
   for (int i = lane; i < lines; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(a0 + (uintptr_t)i * 128));
 }
 
-// post_physics_step in one launch: epilogue, termination, reward, reset, observations, late update.
-// Reward/termination read the pre-reset state, observations the post-reset state.
+// Inputs of the observation / late-update stages of one env, one value per lane (registers). Loaded once up front and,
+// for an env that resets in this step, once more after the reset has rewritten them.
+struct ObsIn {
+  float root;        // lane < 13: root_states[lane]
+  float qn, qv, qb;  // lane < 12: qpos_noise, qvel_noise, qpos_bias
+  float quatb;       // lane < 3
+  float vel0, vel1;  // joint velocity of DOF lane and of DOF 32 (late update)
+  float tv;          // lane < 2: target_vel
+  float time;
+  int init_idx;
+};
+__device__ __forceinline__ ObsIn load_obs_in(const TK& k, int e, int lane) {
+  ObsIn in;
+  in.root = lane < 13 ? k.s.root_states[(size_t)e * 13 + lane] : 0.f;
+  const int l12 = lane < 12 ? lane : 11;
+  in.qn = k.b.qpos_noise[(size_t)e * ND + l12];
+  in.qv = k.b.qvel_noise[(size_t)e * ND + l12];
+  in.qb = k.b.qpos_bias[(size_t)e * 12 + l12];
+  in.quatb = k.b.quat_bias[(size_t)e * 3 + (lane < 3 ? lane : 2)];
+  const float2* ds2 = reinterpret_cast<const float2*>(k.s.dof_state + (size_t)e * ND * 2);
+  in.vel0 = ds2[lane].y;
+  in.vel1 = ds2[32].y;
+  in.tv = k.b.target_vel[(size_t)e * 2 + (lane & 1)];
+  in.time = k.b.time[e];
+  in.init_idx = k.b.init_mocap_data_idx[e];
+  return in;
+}
+
+// post_physics_step in one launch: epilogue, termination, reward, reset, observations, late update (T:532-563), one
+// warp per env, written as ONE stage: every input of every stage is requested up front (one round of independent,
+// coalesced loads; a second one for the history rows, whose addresses depend on the ring heads), all arithmetic then
+// runs on registers, and the results go out at the end. The arithmetic is that of the staged kernels above, operation
+// for operation (tests/test_env_step_gpu.py pins the two bit for bit). The scalar reward terms are computed by every
+// lane of the warp from broadcast values: no regrouping through shared memory, no CTA barrier.
+// Reward/termination read the pre-reset state, observations the post-reset state. Of contact_forces_pre only
+// the two foot rows are maintained here: they are all the reward reads (T:858-859, T:904-907).
 // The two means of the curriculum gate (T:489) are formed from fixed-point terms summed in 64-bit integers, so that the
-// result does not depend on the order of summation: k_crossenv (one CTA, fixed order) and the fused post-physics launch
-// (atomics across CTAs) give the same bits. epi_len_log holds whole numbers (exact at 2^-20), contact_reward_mean lies
-// in [0, 1] (2^-40 is below a float's resolution there).
+// result does not depend on the order of summation: k_crossenv and this launch (atomics across CTAs) give the same
+// bits. epi_len_log holds whole numbers (exact at 2^-20), contact_reward_mean lies in [0, 1].
 __device__ __forceinline__ long long gate_term0(float epi_len_log) { return __double2ll_rn((double)epi_len_log * 1048576.0); }
 __device__ __forceinline__ long long gate_term1(float contact_reward_mean) { return __double2ll_rn((double)contact_reward_mean * 1099511627776.0); }
 __device__ __forceinline__ bool gate_open(const TaskParams& P, long long s0, long long s1) {  // T:489
   return (float)((double)s0 / 1048576.0 / P.N) > P.gate_len && (float)((double)s1 / 1099511627776.0 / P.N) > 0.165f;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_post_fused(TK k, int tail) {
-  __shared__ RewardSums sums[kWarpsPerBlock];
-  __shared__ long long gate_acc[2][kWarpsPerBlock];
+// 4 warps per CTA, 7 CTAs per SM: 4096 envs (1024 CTAs) are resident on 148 SMs in ONE wave at <= 73 registers per thread
+constexpr int kPostWarps = 4;
+__global__ void __launch_bounds__(kPostWarps * 32, 7) k_post_fused(TK k, int tail) {
+  __shared__ long long gate_acc[2][kPostWarps];
   pdl_launch_dependents();
   pdl_wait();
+  const TaskParams& P = k.p;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int e = blockIdx.x * kWarpsPerBlock + w;
-  const bool valid = e < k.p.N;  // (no early return: the CTA meets at two barriers)
-  int reset = 0;
-  if (valid) {
-    // The stages below are a chain of dependent reads. Once the env state no longer fits L2 (about 10.4 KB per env:
-    // beyond ~8k envs per GPU) the rows the physics launch did not touch (history rings, previous-step copies) are
-    // requested from HBM now, all at once, instead of one miss per stage (+6 % at 16,384 envs; at 4,096 envs they are
-    // L2 hits and the extra instructions only cost).
-    if (k.p.N > 8192) {
-      prefetch_rows_l2(k.b.obs_history + (size_t)e * NSLOT * NOBS1, NSLOT * NOBS1 * 4, lane);
-      prefetch_rows_l2(k.b.action_history + (size_t)e * NSLOT * NA, NSLOT * NA * 4, lane);
-      prefetch_rows_l2(k.b.contact_forces_pre + (size_t)e * NB * 3, NB * 3 * 4, lane);
-      prefetch_rows_l2(k.b.pre_joint_velocity_states + (size_t)e * ND, ND * 4, lane);
-      prefetch_rows_l2(k.b.actions_pre + (size_t)e * NA, NA * 4, lane);
+  const int e = blockIdx.x * kPostWarps + w;
+  const int live_warps = min(kPostWarps, P.N - (int)blockIdx.x * kPostWarps);  // warps of this CTA that hold an env
+  if (e >= P.N) return;
+  {
+    const size_t E = (size_t)e;
+    // ================================================================ loads, round 1 (independent of each other)
+    ObsIn in = load_obs_in(k, e, lane);
+    const float2* ds2 = reinterpret_cast<const float2*>(k.s.dof_state + E * ND * 2);
+    const float2 dsA = ds2[lane], dsB = ds2[32];                   // DOF lane, DOF 32
+    const float tqA = k.b.target_data_qpos[E * ND + lane], tqB = k.b.target_data_qpos[E * ND + 32];
+    const float pjA = k.b.pre_joint_velocity_states[E * ND + lane], pjB = k.b.pre_joint_velocity_states[E * ND + 32];
+    const int l13 = lane < NA ? lane : NA - 1, l12 = lane < 12 ? lane : 11;
+    const float act = k.b.actions[E * NA + l13], actp = k.b.actions_pre[E * NA + l13];
+    const float atq = k.b.action_torque[E * 12 + l12];
+    const float* F = k.s.net_contact_force + E * NB * 3;
+    const int bB = lane + 32 < NB ? lane + 32 : NB - 1;            // second body of this lane (lanes 0..5)
+    const float fA0 = F[3 * lane], fA1 = F[3 * lane + 1], fA2 = F[3 * lane + 2];
+    const float fB0 = F[3 * bB], fB1 = F[3 * bB + 1], fB2 = F[3 * bB + 2];
+    const float* Fp = k.b.contact_forces_pre + E * NB * 3;
+    const float lfp0 = Fp[P.lfoot * 3], lfp1 = Fp[P.lfoot * 3 + 1], lfp2 = Fp[P.lfoot * 3 + 2];
+    const float rfp0 = Fp[P.rfoot * 3], rfp1 = Fp[P.rfoot * 3 + 1], rfp2 = Fp[P.rfoot * 3 + 2];
+    const float epi0 = k.b.epi_len[e];
+    const long long pr = k.b.progress_buf[e], rnd = k.b.randomize_buf[e];
+    const float crs = k.b.contact_reward_sum[e], mass = k.b.total_mass[e];
+    const int midx = k.b.mocap_data_idx[e];
+    const float ft0 = k.b.target_data_force[E * 2], ft1 = k.b.target_data_force[E * 2 + 1];
+    const int ohead0 = k.b.obs_hist_head[e], ahead = k.b.act_hist_head[e];
+    const int pstart = *k.b.perturb_start;
+    float ell = k.b.epi_len_log[e], crm = k.b.contact_reward_mean[e];  // terms of the curriculum gate (T:489)
+    const int iA = lane, iB = lane + 32 < NOBS1 ? lane + 32 : NOBS1 - 1;  // observation components of this lane
+    const float meanA = k.b.obs_mean[iA], varA = k.b.obs_var[iA], meanB = k.b.obs_mean[iB], varB = k.b.obs_var[iB];
+    float velu = 0.f;                                               // T:766 draw of component 31 + c (lanes 31 and 0..4)
+    if (k.j.vel_u) velu = k.j.vel_u[E * 6 + (lane == 31 ? 0 : (lane < 5 ? lane + 1 : 0))];
+    // ================================================================ loads, round 2: history rows of the gather
+    // T:789-796 frame by frame: lane j holds component j (and, lanes 0..4, component 32 + j) of each of the 9 older
+    // observation frames and, lanes 0..12, of the 9 older actions; this step's frame (position 19) stays in registers
+    const int head = (ohead0 + 1) % NSLOT;
+    const float* hist = k.b.obs_history + E * NSLOT * NOBS1;
+    const float* ah = k.b.action_history + E * NSLOT * NA;
+    float hA[NHIS - 1], hB[NHIS - 1], hC[NHIS - 1];
+#pragma unroll
+    for (int i = 0; i < NHIS - 1; ++i) {
+      const float* row = hist + ((head + 1 + NSKIP * (i + 1) - 1) % NSLOT) * NOBS1;   // T:789-791, position 2(i+1)-1
+      hA[i] = row[lane];
+      hB[i] = row[iB];
+      hC[i] = ah[((ahead + 1 + NSKIP * (i + 1)) % NSLOT) * NA + l13];                 // T:793-796, position 2(i+1)
     }
-    stage_epilogue(k, e, lane);
-    __syncwarp();
-    TermShared ts;
-    reset = stage_check_termination(k, e, lane, &ts);
-    __syncwarp();
-    RewardSums rs = reward_sums(k, e, lane, &ts);
-    if (lane == 0) sums[w] = rs;
-  }
-  __syncthreads();
-  if (w == 0 && lane < kWarpsPerBlock) {  // the scalar reward terms of the CTA's envs, one lane per env
-    const int e2 = blockIdx.x * kWarpsPerBlock + lane;
-    if (e2 < k.p.N) reward_scalar(k, e2, sums[lane]);
-  }
-  __syncthreads();
-  if (valid) {
+    // ================================================================ epilogue (T:532-541, VT:325, T:544-545)
+    const float a12 = __shfl_sync(kFull, act, NA - 1);
+    float epi = epi0 + 1.0f;
+    float t = in.time + P.dt_policy;
+    t = t + P.time_gain * a12;
+    const int timeout = ((float)pr >= P.max_len_m1) ? 1 : 0;
+    const long long progress = pr + 1;
+    long long randomize = rnd + 1;
+    // ================================================================ termination (T:581-596)
+    float quat[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) quat[i] = __shfl_sync(kFull, in.root, 3 + i);
+    const float qe = quat_err_identity(quat);
+    int reset = (fabsf(qe) > 0.5f) ? 1 : 0;
+    if ((float)progress >= P.max_len_m1) reset = 1;
+    bool hit = false;                                               // T:590 / T:937: any non-foot body with |F| > 1
+    if (lane != P.lfoot && lane != P.rfoot) hit |= sqrtf(fA0 * fA0 + fA1 * fA1 + fA2 * fA2) > 1.0f;
+    if (lane + 32 < NB && lane + 32 != P.lfoot && lane + 32 != P.rfoot) hit |= sqrtf(fB0 * fB0 + fB1 * fB1 + fB2 * fB2) > 1.0f;
+    const bool col = __any_sync(kFull, hit);
+    if (col) reset = 1;
+    // ================================================================ reward (T:387-428, T:802-947)
+    float s_qpos, s_qvel, s_qacc, s_tq = 0.f, s_tqd = 0.f;
+    {
+      float a = tqA - dsA.x, b = 0.0f - dsA.y, c = dsA.y - pjA;
+      s_qpos = a * a; s_qvel = b * b; s_qacc = c * c;
+      if (lane == 0) {                                              // DOF 32 rides on lane 0, after DOF 0
+        a = tqB - dsB.x; b = 0.0f - dsB.y; c = dsB.y - pjB;
+        s_qpos += a * a; s_qvel += b * b; s_qacc += c * c;
+      }
+      if (lane < 12) {
+        const float tt = act * 333.0f, td = (act - actp) * 333.0f;
+        s_tq = tt * tt;
+        s_tqd = td * td;
+      }
+    }
+    s_qpos = warp_sum(s_qpos); s_qvel = warp_sum(s_qvel); s_qacc = warp_sum(s_qacc); s_tq = warp_sum(s_tq); s_tqd = warp_sum(s_tqd);
+    // the scalar terms, by every lane from broadcast values (reward_scalar, operation for operation)
+    const float lf0 = __shfl_sync(kFull, fA0, P.lfoot), lf1 = __shfl_sync(kFull, fA1, P.lfoot), lf2 = __shfl_sync(kFull, fA2, P.lfoot);
+    const float rf0 = __shfl_sync(kFull, fA0, P.rfoot), rf1 = __shfl_sync(kFull, fA1, P.rfoot), rf2 = __shfl_sync(kFull, fA2, P.rfoot);
+    const float rootvx = __shfl_sync(kFull, in.root, 7), rootvy = __shfl_sync(kFull, in.root, 8);
+    const float tvx = __shfl_sync(kFull, in.tv, 0), tvy = __shfl_sync(kFull, in.tv, 1);
+    float r[14];
+    float total;
+    {
+      r[0] = 0.3f * expf(-13.2f * fabsf(qe));                                         // T:835
+      float n;
+      n = sqrtf(s_qpos); r[1] = 0.35f * expf(-2.0f * (n * n));                        // T:837
+      n = sqrtf(s_qvel); r[2] = 0.05f * expf(-0.01f * (n * n));                       // T:839
+      const float dl0 = lf0 - lfp0, dl1 = lf1 - lfp1, dl2 = lf2 - lfp2;
+      const float dr0 = rf0 - rfp0, dr1 = rf1 - rfp1, dr2 = rf2 - rfp2;
+      r[9] = 0.2f * expf(-0.01f * (sqrtf(dl0 * dl0 + dl1 * dl1 + dl2 * dl2) + sqrtf(dr0 * dr0 + dr1 * dr1 + dr2 * dr2)));  // T:858
+      r[4] = 0.05f * expf(-0.01f * sqrtf(s_tq));                                       // T:861
+      r[5] = 0.6f * expf(-0.01f * sqrtf(s_tqd));                                       // T:863
+      n = sqrtf(s_qacc); r[7] = 0.05f * expf(-20.0f * (n * n));                       // T:865
+      const float vx = tvx - rootvx, vy = tvy - rootvy;
+      n = sqrtf(vx * vx + vy * vy); r[6] = 0.3f * expf(-3.0f * (n * n));              // T:867
+      const bool lc = lf2 > 1.0f, rc = rf2 > 1.0f;                                    // T:869-870
+      const bool DSP = ((3300 <= midx) && (midx < 3600)) || (midx < 300) || ((1500 <= midx) && (midx < 2100));
+      const bool RSSP = (300 <= midx) && (midx < 1500);
+      const bool LSSP = (2100 <= midx) && (midx < 3300);
+      const bool sync = (DSP && rc && lc) || (RSSP && rc && !lc) || (LSSP && !rc && lc);  // T:882-889
+      r[8] = sync ? 0.2f : 0.0f;
+      r[10] = 0.0f;                                                                   // T:893
+      const float thr = (float)(1.4 * 9.81) * mass;                                   // T:895
+      const bool thres = (lf2 > thr) || (rf2 > thr);
+      r[11] = thres ? -0.2f : 0.0f;                                                   // T:898
+      const float cl = fmaxf(lf2 - thr, 0.0f), cr = fmaxf(rf2 - thr, 0.0f);
+      const float pen = 0.1f * expf(-0.007f * (sqrtf(cl * cl) + sqrtf(cr * cr)));     // T:900-901
+      r[3] = thres ? pen : 0.1f;                                                      // T:902
+      const float dthr = (float)(0.2 * 9.81) * mass / 1.0f;                           // T:904
+      const bool tdiff = (fabsf(lf2 - lfp2) > dthr) || (fabsf(rf2 - rfp2) > dthr);
+      r[12] = tdiff ? -0.05f : 0.0f;                                                  // T:907
+      const float ws = mass / 104.48f;                                                // T:917
+      r[13] = 0.1f * expf(-0.001f * fabsf(lf2 + ws * ft0)) + 0.1f * expf(-0.001f * fabsf(rf2 + ws * ft1));  // T:918-919
+      total = r[0] + r[1] + r[2] + r[3] + r[4] + r[5] + r[6] + r[7] + r[8] + r[9] + r[10] + r[11] + r[12] + r[13];  // T:932-934
+      if (col) total = P.death_cost;                                                  // T:942
+      if (fabsf(qe) > 0.5f) total = P.death_cost;                                     // T:943
+    }
+    {
+      float stv = col ? P.death_cost : 0.f;                                           // T:945
+#pragma unroll
+      for (int i = 0; i < 14; ++i)
+        if (lane == i && !col) stv = r[i];
+      if (lane == 14) stv = pstart ? 1.0f : 0.0f;                                     // T:415
+      if (lane < 15) k.b.stacked_rewards[E * 15 + lane] = stv;
+    }
+    // ================================================================ stores of the scalar state; reset (T:598-669)
+    if (lane == 0) {
+      k.b.rew_buf[e] = total;
+      k.b.timeout_buf[e] = timeout;
+      k.b.reset_buf[e] = reset;
+      k.b.contact_reward_sum[e] = crs + r[8];                                          // T:891
+    }
     if (reset) {
+      // the reset stage reads what the epilogue wrote: publish it first, then let it rewrite the env (rare: the stage is
+      // the staged kernel's, from and to global memory), then fetch the rewritten inputs of the observation stage again
+      if (lane == 0) {
+        k.b.epi_len[e] = epi;
+        k.b.time[e] = t;
+        k.b.progress_buf[e] = progress;
+        k.b.randomize_buf[e] = randomize;
+      }
+      __syncwarp();
       stage_reset_env(k, e, lane);
       __syncwarp();
-    }
-    stage_compute_observations(k, e, lane);
-    __syncwarp();
-    stage_late_update(k, e, lane);
-  }
-  if (!tail) return;
-  // ---- cross-env pass of the fused step (what k_crossenv does for the staged one, minus the id list): gate sums by
-  //      64-bit integer atomics, one pair per CTA; the last CTA to finish decides the gate and bumps the Philox epoch
-  const bool gate = k.p.perturb != 0;
-  __syncwarp();
-  if (gate && lane == 0) {
-    gate_acc[0][w] = valid ? gate_term0(k.b.epi_len_log[e]) : 0;          // (post-reset values, as k_crossenv reads them)
-    gate_acc[1][w] = valid ? gate_term1(k.b.contact_reward_mean[e]) : 0;
-  }
-  // (no device-wide fence by every thread: nothing written above is read by another CTA of this launch; what the last
-  //  CTA reads are the sums below, and what it overwrites, the Philox epoch, every warp has finished reading before
-  //  the barrier; thread 0's fences order its atomics)
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (gate) {
-      long long a = 0, b = 0;
+      in = load_obs_in(k, e, lane);
+      t = in.time;
+      epi = k.b.epi_len[e];
+      ell = k.b.epi_len_log[e];
+      crm = k.b.contact_reward_mean[e];
 #pragma unroll
-      for (int i = 0; i < kWarpsPerBlock; ++i) {
-        a += gate_acc[0][i];
-        b += gate_acc[1][i];
-      }
-      atomicAdd(k.p.tail + 0, (unsigned long long)a);
-      atomicAdd(k.p.tail + 1, (unsigned long long)b);
+      for (int i = 0; i < NHIS - 1; ++i) hA[i] = hB[i] = hC[i] = 0.f;                  // T:668-669: histories zeroed
+    } else if (lane == 0) {
+      k.b.epi_len[e] = epi;
+      k.b.time[e] = t;
+      k.b.progress_buf[e] = progress;
+      k.b.randomize_buf[e] = randomize;
     }
-    __threadfence();
-    if (atomicAdd(k.p.tail + 2, 1ull) == gridDim.x - 1) {  // every CTA has finished its envs and published its sums
-      __threadfence();
-      if (gate) {
-        const long long s0 = (long long)atomicExch(k.p.tail + 0, 0ull), s1 = (long long)atomicExch(k.p.tail + 1, 0ull);
-        if (gate_open(k.p, s0, s1)) *k.b.perturb_start = 1;  // T:489-490 (sticky)
+    // ================================================================ cross-env pass of the fused step
+    // (what k_crossenv does for the staged one, minus the id list): gate sums by 64-bit integer atomics, one pair per
+    // CTA; the last CTA to take a ticket decides the gate and bumps the Philox epoch. Placed HERE, before the
+    // observation stage and its 2 KB of stores per env, so that the fence below has little to wait for and the ticket
+    // traffic overlaps the rest of the kernel: every draw of this launch that uses the epoch is either behind us (reset)
+    // or uses the copy taken now.
+    const uint64_t epoch = *P.step_counter;
+    if (tail) {
+      const bool gate = P.perturb != 0;
+      if (gate && lane == 0) {
+        gate_acc[0][w] = gate_term0(ell);  // (post-reset values, as k_crossenv reads them)
+        gate_acc[1][w] = gate_term1(crm);
       }
-      k.p.tail[2] = 0;
-      *k.p.step_counter = *k.p.step_counter + 1;
+      asm volatile("bar.sync 1, %0;" ::"r"(live_warps * 32) : "memory");
+      if (threadIdx.x == 0) {
+        if (gate) {
+          long long a = 0, b = 0;
+          for (int i = 0; i < live_warps; ++i) {
+            a += gate_acc[0][i];
+            b += gate_acc[1][i];
+          }
+          atomicAdd(P.tail + 0, (unsigned long long)a);
+          atomicAdd(P.tail + 1, (unsigned long long)b);
+          __threadfence();  // the sums before the ticket
+        }
+        if (atomicAdd(P.tail + 2, 1ull) == gridDim.x - 1) {  // every CTA has published its sums and taken its epoch copy
+          __threadfence();
+          if (gate) {
+            const long long s0 = (long long)atomicExch(P.tail + 0, 0ull), s1 = (long long)atomicExch(P.tail + 1, 0ull);
+            if (gate_open(P, s0, s1)) *k.b.perturb_start = 1;  // T:489-490 (sticky)
+          }
+          P.tail[2] = 0;
+          *P.step_counter = epoch + 1;
+        }
+      }
+    }
+    // ================================================================ observations (T:750-796)
+    const float time2idx = py_fmodf(t, P.period) / P.cycle_dt;                         // T:762
+    const float phase = py_fmodf((float)in.init_idx + time2idx, (float)P.mocap_data_num) / (float)P.mocap_data_num;  // T:763
+    const float ang = (float)(2 * 3.14159265358979) * phase;
+    const bool start = epi == 0.0f;                                                    // T:785
+#pragma unroll
+    for (int i = 0; i < 4; ++i) quat[i] = __shfl_sync(kFull, in.root, 3 + i);
+    // (shuffles are executed by all lanes: gather every lane's sources first, then select)
+    const float tv0n = __shfl_sync(kFull, in.tv, 0), tv1n = __shfl_sync(kFull, in.tv, 1);
+    const float qb_for_A = __shfl_sync(kFull, in.qb, (lane - 3) & 31), qn_for_A = __shfl_sync(kFull, in.qn, (lane - 3) & 31);
+    const float qv_for_A = __shfl_sync(kFull, in.qv, (lane - 15) & 31);
+    const float rootv_for_A = __shfl_sync(kFull, in.root, 7);       // component 31 = root[7] (lane 31)
+    const float rootv_for_B = __shfl_sync(kFull, in.root, (8 + lane) & 31);  // components 32..36 = root[8..12] (lanes 0..4)
+    // T:766: one draw per velocity component c = 0..5, held by lane 31 (component 31) and lanes 0..4 (32..36)
+    const int cdraw = lane == 31 ? 0 : (lane < 5 ? lane + 1 : 0);
+    float vnoise = velu;
+    if (!k.j.vel_u) vnoise = u01(draw4(P.seed, epoch, e, kSiteVelNoise, cdraw).x);
+    vnoise = vnoise * 0.05f - 0.025f;
+    float vA, vB = 0.f;
+    if (iA < 3) vA = quat2euler_comp(quat, iA) + in.quatb;                             // T:753-757 (quat_bias[lane], lane < 3)
+    else if (iA < 15) vA = qn_for_A + qb_for_A;
+    else if (iA < 27) vA = qv_for_A;
+    else if (iA == 27) vA = sinf(ang);                                                 // T:764
+    else if (iA == 28) vA = cosf(ang);                                                 // T:765
+    else if (iA < 31) vA = iA == 29 ? tv0n : tv1n;
+    else vA = rootv_for_A + vnoise;                                                    // T:766,774 (component 31)
+    if (lane < NOBS1 - 32) vB = rootv_for_B + vnoise;                                  // components 32..36
+    const float nvA = (vA - meanA) / sqrtf(varA + 1e-8f * 1.0f);                       // T:776-777
+    const float nvB = (vB - meanB) / sqrtf(varB + 1e-8f * 1.0f);
+    {
+      float* hw = k.b.obs_history + E * NSLOT * NOBS1;
+      if (start) {
+        for (int sl = 0; sl < NSLOT; ++sl) {                                           // T:786-787
+          hw[sl * NOBS1 + iA] = nvA;
+          if (lane < NOBS1 - 32) hw[sl * NOBS1 + lane + 32] = nvB;
+        }
+      } else {
+        hw[head * NOBS1 + iA] = nvA;                                                   // T:783
+        if (lane < NOBS1 - 32) hw[head * NOBS1 + lane + 32] = nvB;
+      }
+      if (lane == 0) k.b.obs_hist_head[e] = head;
+    }
+    {
+      float* ob = k.b.obs_buf + E * NOBS;
+#pragma unroll
+      for (int i = 0; i < NHIS; ++i) {                                                 // T:789-791
+        const bool newest = start || i == NHIS - 1;                                    // (T:786-787: at an episode start every slot holds this frame)
+        ob[NOBS1 * i + lane] = newest ? nvA : hA[i < NHIS - 1 ? i : 0];
+        if (lane < NOBS1 - 32) ob[NOBS1 * i + 32 + lane] = newest ? nvB : hB[i < NHIS - 1 ? i : 0];
+      }
+#pragma unroll
+      for (int i = 0; i < NHIS - 1; ++i)                                               // T:793-796
+        if (lane < NA) ob[NOBS1 * NHIS + NA * i + lane] = hC[i];
+    }
+    // ================================================================ late update (T:560-563)
+    k.b.pre_joint_velocity_states[E * ND + lane] = in.vel0;
+    if (lane == 0) k.b.pre_joint_velocity_states[E * ND + 32] = in.vel1;
+    if (lane < 12) k.b.action_torque_pre[E * 12 + lane] = atq;
+    if (lane < NA) k.b.actions_pre[E * NA + lane] = act;
+    if (lane == P.lfoot || lane == P.rfoot) {                                          // the rows the reward reads
+      float* o = k.b.contact_forces_pre + E * NB * 3 + 3 * lane;
+      o[0] = fA0; o[1] = fA1; o[2] = fA2;
     }
   }
 }
 
-// Cross-env pass (one block, one sweep over the envs): (a) reset_buf.nonzero() -> ascending ids (T:554): thread t owns the
-// consecutive envs [t * per, (t + 1) * per), so a block-wide exclusive scan of the per-thread counts (warp shuffle scan,
-// then a scan of the 32 warp totals) gives every thread the output position of its first id; (b) the curriculum gate
-// means of T:489 (fixed summation order: deterministic); (c) Philox epoch bump.
-constexpr int kScanThreads = 1024;
-__global__ void __launch_bounds__(kScanThreads) k_crossenv(TK k, int do_compact, int do_gate, int do_bump) {
-  __shared__ int warp_tot[kScanThreads / 32];
-  __shared__ long long red[2][kScanThreads / 32];
+// Cross-env pass: (a) reset_buf.nonzero() -> ascending ids (T:554) by warp ballot + prefix scan, multi-CTA;
+// (b) the curriculum gate means of T:489 (order-free fixed-point sums); (c) Philox epoch bump.
+//
+// Compaction: a CTA takes a tile of kScanTile consecutive envs (tile index = an atomic ticket, so a tile only ever waits
+// for tiles whose CTAs are already running); thread t reads reset_buf[tile * kScanTile + t] (coalesced), a warp ballot
+// gives every lane its rank inside the warp (popc of the lower lanes' bits) and the warp its count, a shuffle scan of
+// the 32 warp counts gives the offsets inside the tile, and the tile's offset in the output is the sum of the counts of
+// the tiles before it: every tile publishes its count as soon as it has it (decoupled: nobody waits for a prefix, only
+// for counts), and warp 0 of tile i sums the i counts before it, 32 at a time. ids come out ascending, exactly
+// reset_buf.nonzero(); the int32 copy (T:737,745) is written alongside. The last CTA to finish writes nothing but the
+// clean-up (ticket, status words) for the next launch, decides the gate and bumps the epoch.
+constexpr int kScanTile = 1024;
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(kScanTile) k_crossenv(TK k, int do_compact, int do_gate, int do_bump) {
+  __shared__ int warp_cnt[kScanTile / 32];
+  __shared__ long long red[2][kScanTile / 32];
+  __shared__ int s_tile, s_prefix;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int N = k.p.N;
-  const int per = (N + kScanThreads - 1) / kScanThreads;
-  const int e0 = tid * per, e1 = min(N, e0 + per);
+  const int N = k.p.N, ntiles = (N + kScanTile - 1) / kScanTile;
+  unsigned* ticket = k.p.scan_state;      // [0] next tile, [1] tiles finished, [2 + t] count of tile t, + 1 (0 = not yet)
+  unsigned* status = k.p.scan_state + 2;
   pdl_wait();
-  int cnt = 0;
-  long long s0 = 0, s1 = 0;  // fixed-point terms: see gate_term0 / gate_term1
+  if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
+  __syncthreads();
+  const int tile = s_tile;
+  const int e = tile * kScanTile + tid;
+  const bool valid = e < N;
   const bool gate = do_gate && k.p.perturb;
-  for (int e = e0; e < e1; ++e) {
-    if (do_compact) cnt += k.b.reset_buf[e] != 0;
-    if (gate) {
-      s0 += gate_term0(k.b.epi_len_log[e]);
-      s1 += gate_term1(k.b.contact_reward_mean[e]);
+  const bool flag = do_compact && valid && k.b.reset_buf[e] != 0;
+  const unsigned bal = __ballot_sync(kFull, flag);
+  const int rank = __popc(bal & ((1u << lane) - 1u));
+  long long s0 = (gate && valid) ? gate_term0(k.b.epi_len_log[e]) : 0;  // fixed-point terms: see gate_term0 / gate_term1
+  long long s1 = (gate && valid) ? gate_term1(k.b.contact_reward_mean[e]) : 0;
+  if (gate) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(kFull, s0, o);
+      s1 += __shfl_xor_sync(kFull, s1, o);
     }
   }
-  // inclusive scan of cnt inside the warp, warp totals to shared memory
-  int inc = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(kFull, inc, o);
-    if (lane >= o) inc += t;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    s0 += __shfl_xor_sync(kFull, s0, o);
-    s1 += __shfl_xor_sync(kFull, s1, o);
-  }
-  if (lane == 31) warp_tot[w] = inc;
   if (lane == 0) {
+    warp_cnt[w] = __popc(bal);
     red[0][w] = s0;
     red[1][w] = s1;
   }
   __syncthreads();
   if (w == 0) {
-    int v = warp_tot[lane], sc = v;
+    // exclusive scan of the warp counts; the tile's count goes out at once
+    const int v = warp_cnt[lane];
+    int inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(kFull, sc, o);
-      if (lane >= o) sc += t;
+      const int t = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += t;
     }
-    warp_tot[lane] = sc - v;  // exclusive offsets of the warps
-    if (lane == 31 && do_compact) *k.b.reset_count = sc;
+    warp_cnt[lane] = inc - v;
+    const int total = __shfl_sync(kFull, inc, 31);
+    if (lane == 0) atomicExch(status + tile, (unsigned)total + 1u);
+    // offset of the tile = sum of the counts of the tiles before it
+    int before = 0;
+    for (int t = lane; t < tile; t += 32) {
+      unsigned c;
+      while ((c = ld_acquire_gpu_u32(status + t)) == 0u) __nanosleep(20);
+      before += (int)(c - 1u);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(kFull, before, o);
+    if (lane == 0) {
+      s_prefix = before;
+      if (do_compact && tile == ntiles - 1) *k.b.reset_count = before + total;
+    }
     if (gate) {
       long long a = red[0][lane], b = red[1][lane];
 #pragma unroll
@@ -593,19 +845,32 @@ __global__ void __launch_bounds__(kScanThreads) k_crossenv(TK k, int do_compact,
         a += __shfl_xor_sync(kFull, a, o);
         b += __shfl_xor_sync(kFull, b, o);
       }
-      if (lane == 0 && gate_open(k.p, a, b)) *k.b.perturb_start = 1;  // T:489-490 (sticky)
+      if (lane == 0) {
+        atomicAdd(k.p.tail + 0, (unsigned long long)a);
+        atomicAdd(k.p.tail + 1, (unsigned long long)b);
+      }
     }
-    if (do_bump && lane == 0) *k.p.step_counter = *k.p.step_counter + 1;
   }
   __syncthreads();
-  if (do_compact && cnt) {
-    int pos = warp_tot[w] + inc - cnt;
-    for (int e = e0; e < e1; ++e)
-      if (k.b.reset_buf[e] != 0) {
-        k.b.reset_env_ids[pos] = e;
-        k.b.reset_env_ids32[pos] = e;
-        ++pos;
+  if (flag) {
+    const int pos = s_prefix + warp_cnt[w] + rank;
+    k.b.reset_env_ids[pos] = e;
+    k.b.reset_env_ids32[pos] = e;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(ticket + 1, 1u) == (unsigned)ntiles - 1u) {  // every tile is done: clean up for the next launch
+      __threadfence();
+      for (int t = 0; t < ntiles; ++t) status[t] = 0u;
+      ticket[0] = 0u;
+      ticket[1] = 0u;
+      if (gate) {
+        const long long a = (long long)atomicExch(k.p.tail + 0, 0ull), b = (long long)atomicExch(k.p.tail + 1, 0ull);
+        if (gate_open(k.p, a, b)) *k.b.perturb_start = 1;  // T:489-490 (sticky)
       }
+      if (do_bump) *k.p.step_counter = *k.p.step_counter + 1;
+    }
   }
 }
 
@@ -670,7 +935,7 @@ int launch_compute_reward(Task* t, cudaStream_t s) { LAUNCH_ENV(k_compute_reward
 int launch_compute_observations(Task* t, cudaStream_t s) { LAUNCH_ENV(k_compute_observations) }
 int launch_late_update(Task* t, cudaStream_t s) { LAUNCH_ENV(k_late_update) }
 int launch_post_fused(Task* t, cudaStream_t s, bool pdl, bool tail) {
-  DY_CUDA(launch_kernel(k_post_fused, dim3(env_grid(t->p.N)), dim3(kWarpsPerBlock * 32), 0, s, pdl, make_tk(t), (int)tail));
+  DY_CUDA(launch_kernel(k_post_fused, dim3((t->p.N + kPostWarps - 1) / kPostWarps), dim3(kPostWarps * 32), 0, s, pdl, make_tk(t), (int)tail));
   return 0;
 }
 int launch_reset_idx(Task* t, const int64_t* env_ids, int count, cudaStream_t s) {
@@ -688,7 +953,8 @@ int launch_pack_results(Task* t, float* dst, cudaStream_t s) {
   return 0;
 }
 int launch_crossenv(Task* t, bool compact, bool gate, bool bump, cudaStream_t s, bool pdl) {
-  DY_CUDA(launch_kernel(k_crossenv, dim3(1), dim3(kScanThreads), 0, s, pdl, make_tk(t), (int)compact, (int)gate, (int)bump));
+  const int ntiles = (t->p.N + kScanTile - 1) / kScanTile;
+  DY_CUDA(launch_kernel(k_crossenv, dim3(ntiles), dim3(kScanTile), 0, s, pdl, make_tk(t), (int)compact, (int)gate, (int)bump));
   return 0;
 }
 

@@ -230,3 +230,27 @@ def test_actions_validation_and_errors():
     with pytest.raises(native.DyrosError):
         core.sensor_noise(2)
     core.close()
+
+
+@pytest.mark.parametrize("N", [1, 1023, 1024, 1025, 4096, 70001])
+def test_reset_compaction_is_nonzero_at_tile_boundaries(N):
+    """T:554 `reset_buf.nonzero()` by the multi-CTA ballot / prefix-scan kernel (tiles of 1024 envs): ascending int64
+    ids, their int32 copy (T:737,745) and the count, bit-exact, for empty, full and random masks; two launches in a row
+    (the kernel cleans up its own tile state)."""
+    core = make_core(N)
+    g = torch.Generator(device="cuda:0"); g.manual_seed(N)
+    for mask in (torch.zeros(N, device="cuda:0"), torch.ones(N, device="cuda:0"),
+                 (torch.rand(N, device="cuda:0", generator=g) < 0.3).float(),
+                 (torch.rand(N, device="cuda:0", generator=g) < 0.01).float()):
+        core.task_t["reset_buf"].copy_(mask.long() * 7)  # any non-zero value counts
+        for rep in range(2):
+            core.task_t["reset_env_ids"].fill_(-1)
+            core.compact_resets()
+            torch.cuda.synchronize()
+            want = torch.nonzero(core.task_t["reset_buf"]).flatten()
+            n = int(core.task_t["reset_count"].item())
+            assert n == want.numel()
+            assert torch.equal(core.task_t["reset_env_ids"][:n], want)
+            assert torch.equal(core.task_t["reset_env_ids32"][:n].long(), want)
+            assert core.task_t["reset_env_ids32"].dtype == torch.int32
+    core.close()
