@@ -32,6 +32,24 @@ MESH_NONE, MESH_COLLISION, MESH_VISUAL, MESH_VISUAL_AND_COLLISION = 0, 1, 2, 3
 DTYPE_FLOAT32, DTYPE_UINT32, DTYPE_UINT64, DTYPE_UINT8, DTYPE_INT16 = 0, 1, 2, 3, 4
 CC_NEVER, CC_LAST_SUBSTEP, CC_ALL_SUBSTEPS = 0, 1, 2
 INVALID_HANDLE = -1
+KEY_ESCAPE, KEY_V = 256, 86
+
+
+def ContactCollection(value: int) -> int:
+    """gymapi.ContactCollection(int) as vec_task.py:461 calls it (an enum in the reference; the value is what matters)."""
+    if int(value) not in (CC_NEVER, CC_LAST_SUBSTEP, CC_ALL_SUBSTEPS):
+        raise ValueError(f"ContactCollection({value})")
+    return int(value)
+
+
+class CameraProperties:
+    pass
+
+
+# The native core behind prepare_sim and the test "is a CUDA device there". Tests that exercise only the Python surface
+# of this facade (tests/test_reference_on_facade.py runs the UNMODIFIED reference task on it) substitute both.
+_core_factory = None
+_device_available = torch.cuda.is_available
 
 
 class Vec3:
@@ -124,6 +142,14 @@ class RigidBodyProperties:
         self.flags = 0
 
 
+class RigidShapeProperties:
+    def __init__(self, friction=1.0, rolling_friction=0.0, torsion_friction=0.0, restitution=0.0, compliance=0.0,
+                 thickness=0.0, contact_offset=0.02, rest_offset=0.0, filter=0):
+        self.friction, self.rolling_friction, self.torsion_friction = friction, rolling_friction, torsion_friction
+        self.restitution, self.compliance, self.thickness = restitution, compliance, thickness
+        self.contact_offset, self.rest_offset, self.filter = contact_offset, rest_offset, filter
+
+
 class Tensor:
     """Tensor descriptor (docs/api/python/struct_py.html `Tensor`; GymTensor.h:33-41). `torch_tensor` keeps the
     storage alive; gymtorch.wrap_tensor returns it."""
@@ -176,6 +202,7 @@ class Sim:
         self.start_poses: List[Transform] = []
         self.dof_props: List[np.ndarray] = []
         self.mass_scale: List[np.ndarray] = []
+        self.shape_friction: List[float] = []
         self.core: Optional[DyrosCore] = None
         self.frame_count = 0
         self.pending_wrench = False
@@ -203,7 +230,7 @@ class Gym:
     # ------------------------------------------------------------------ setup (vec_task.py:270, T:199-385)
     def create_sim(self, compute_device: int = 0, graphics_device: int = -1, type: int = SIM_PHYSX,
                    params: Optional[SimParams] = None):
-        if type != SIM_PHYSX or not torch.cuda.is_available():
+        if type != SIM_PHYSX or not _device_available():
             print("*** Failed to create sim: only SIM_PHYSX-style simulation on a CUDA device is implemented")
             return None
         params = params or SimParams()
@@ -305,8 +332,8 @@ class Gym:
                 pass
         if sim.core is not None:  # live update of this env's rows (the DR path of VT:655-721)
             dev = sim.core.device
-            sim.core.sim_t["dof_damping"][env.index] = torch.tensor(cur["damping"], device=dev)
-            sim.core.sim_t["dof_armature"][env.index] = torch.tensor(cur["armature"], device=dev)
+            sim.core.sim_t["dof_damping"][env.index] = torch.tensor(np.ascontiguousarray(cur["damping"]), device=dev)
+            sim.core.sim_t["dof_armature"][env.index] = torch.tensor(np.ascontiguousarray(cur["armature"]), device=dev)
         return True
 
     def get_actor_rigid_body_properties(self, env: Env, handle: int):
@@ -319,10 +346,36 @@ class Gym:
         sim = env.sim
         t = sim.asset.tables
         base = t.body_inertia[:, 0]
-        sc = np.array([props[b].mass / base[b] if base[b] > 0 else 1.0 for b in range(t.num_bodies)], dtype=np.float32)
+        # (gymutil.apply_random_samples leaves a 1-element array in `mass`: gymutil.py:607-619)
+        mass = [float(np.ravel(props[b].mass)[0]) for b in range(t.num_bodies)]
+        sc = np.array([mass[b] / base[b] if base[b] > 0 else 1.0 for b in range(t.num_bodies)], dtype=np.float32)
         sim.mass_scale[env.index] = sc
         if sim.core is not None:
             sim.core.sim_t["body_mass_scale"][env.index] = torch.tensor(sc, device=sim.core.device)
+        return True
+
+    def get_actor_tendon_properties(self, env: Env, handle: int):
+        return []  # no tendons in the supported asset class (gymutil.py:487-503 builds its maps with these names)
+
+    def set_actor_tendon_properties(self, env: Env, handle: int, props) -> bool:
+        return True
+
+    def get_actor_rigid_shape_properties(self, env: Env, handle: int):
+        """One entry per collision shape; `friction` is the coefficient the ground contacts of this env use."""
+        sim = env.sim
+        mu = float(sim.shape_friction[env.index]) if env.index < len(sim.shape_friction) else 1.0
+        return [RigidShapeProperties(friction=mu) for _ in range(self.get_actor_rigid_shape_count(env, handle))]
+
+    def set_actor_rigid_shape_properties(self, env: Env, handle: int, props) -> bool:
+        """The ground contact uses ONE coefficient per env (DyrosSimBuffers.contact_friction): the mean over the shapes."""
+        sim = env.sim
+        mu = float(np.mean([p.friction for p in props])) if len(props) else 1.0
+        while len(sim.shape_friction) <= env.index:
+            sim.shape_friction.append(1.0)
+        sim.shape_friction[env.index] = mu
+        if sim.core is not None and "contact_friction" in sim.core.sim_t:
+            plane = float(sim.plane.dynamic_friction) if sim.plane is not None else 1.0
+            sim.core.sim_t["contact_friction"][env.index] = plane * mu
         return True
 
     def get_actor_count(self, env: Env) -> int:
@@ -395,7 +448,7 @@ class Gym:
         t = sim.asset.tables
         cfg.solver_bodies = tuple(n for n in t.body_names if _is_foot(n))
         try:  # the DyrosDynamicWalk task buffers exist only for the TOCABI tree; any other articulation is simulator-only
-            core = DyrosCore(N, f"cuda:{sim.compute_device}", cfg, tables=t, with_task=_is_tocabi(t))
+            core = (_core_factory or DyrosCore)(N, f"cuda:{sim.compute_device}", cfg, tables=t, with_task=_is_tocabi(t))
         except native.DyrosError as e:
             print(f"*** prepare_sim: {e}")
             return False
@@ -520,7 +573,7 @@ class Gym:
         sim.frame_count += 1
 
     def fetch_results(self, sim: Sim, wait: bool) -> None:
-        if wait and sim.core is not None:
+        if wait and sim.core is not None and sim.core.device.type == "cuda":
             torch.cuda.current_stream(sim.core.device).synchronize()
 
     # ------------------------------------------------------------------ viewer (headless only, vec_task.py:212-231)
