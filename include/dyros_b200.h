@@ -277,6 +277,53 @@ int dyros_task_pack_results(DyrosTask* task, void* dst, void* stream);
  * set to a result block, dyros_task_pack_results on that block only adds rew / reset / time_outs. */
 int dyros_task_set_obs_buf(DyrosTask* task, float* obs_buf);
 
+/* --- on-device PPO around the env step (reference: learning/rl_games_custom/a2c_common_dyros.py = A2C,
+ *     a2c_continuous_seperate.py = AG, models_dyros.py = MD, cfg/train/DyrosDynamicWalkPPO.yaml = PPO) ---
+ * Rollout buffers are ENV-major, (N, H, .): a minibatch of the update (rl_games slices the swap_and_flatten01 layout,
+ * A2C:703) is a contiguous block of rows. All pointers are device pointers owned by the caller. */
+typedef struct {
+  int32_t N, H;               /* envs, horizon_length (PPO:85) */
+  float gamma, tau;           /* PPO:66-67 */
+  float e_clip, critic_coef;  /* PPO:84, PPO:88 */
+  float reward_scale;         /* reward_shaper.scale_value, PPO:64 */
+  int32_t value_bootstrap;    /* PPO:61 */
+  uint64_t seed;              /* Philox key of the action noise */
+  float* obs;                 /* (N,H,487) A2C:639 */
+  float* actions;             /* (N,H,13) */
+  float* mus;                 /* (N,H,13) */
+  float* neglogp;             /* (N,H) */
+  float* values;              /* (N,H) */
+  float* rewards;             /* (N,H) shaped, A2C:654-661 */
+  float* dones;               /* (N,H) 0/1, self.dones before the step, A2C:640 */
+  float* advantages;          /* (N,H) A2C:485-500 */
+  float* returns;             /* (N,H) A2C:692 */
+  float* cur_reward;          /* (N) A2C:663 */
+  float* cur_length;          /* (N) A2C:664 */
+  float* ep_stats;            /* (3) sums over finished episodes: reward, length, count (A2C:676-677) */
+  int32_t* step;              /* (1) slot of the next rollout step, 0..H-1 */
+  uint64_t* global_step;      /* (1) rollout steps so far (Philox counter) */
+} DyrosPpoBuffers;
+/* get_action_values + the experience_buffer updates of one rollout step (A2C:633-647, MD:28-58): samples the actions
+ * from N(mu, exp(logstd)), computes their neglogp (MD:60-63), records obs / done / mu / value / action / neglogp at slot
+ * *step, and hands the actions to the env (`actions_env`, (N,13)). inject_normal (H,N,13) replaces the Philox draws (tests). */
+int dyros_ppo_act(const DyrosPpoBuffers* b, const float* mu, const float* value, const float* logstd, const float* obs,
+                  const int64_t* reset_buf, float* actions_env, const float* inject_normal, void* stream);
+/* after VecTask.step: shaped reward with the time-out bootstrap (A2C:654-661), episode statistics (A2C:663-684); advances *step. */
+int dyros_ppo_reward(const DyrosPpoBuffers* b, const float* rew, const int64_t* timeout, const int64_t* reset_buf, void* stream);
+/* discount_values (A2C:485-500) and returns = advantages + values (A2C:692). */
+int dyros_ppo_gae(const DyrosPpoBuffers* b, const float* last_values, const int64_t* last_reset, void* stream);
+/* calc_gradients up to the network outputs (AG:108-160) for rows [row0, row0+mb): d loss / d mu, d loss / d value, and the
+ * logged means accumulated into stats[4] = {actor loss, critic loss, kl, clip fraction}. adv_norm: normalised advantages (A2C:944). */
+int dyros_ppo_loss_grad(const DyrosPpoBuffers* b, int row0, int mb, const float* mu, const float* value, const float* logstd,
+                        const float* adv_norm, float* dmu, float* dvalue, float* stats, void* stream);
+/* optimizer_actor + optimizer_critic (AG:50-54) on flat buffers, with clip_grad_norm_ of the actor part (AG:179) and the
+ * 1/world averaging of all-reduced gradient sums (AG:161-163). lr_dev[2] = {actor, critic} rates and step_dev live on the
+ * device; after the update the actor's rate follows rl_games' LinearScheduler, stepped per minibatch as the reference
+ * does (A2C:888-892; lr_max_steps = max_epochs, 0 = constant rate). */
+int dyros_ppo_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int n_actor, int n, float grad_scale,
+                   float max_norm, float* norm2_scratch, float* lr_dev, int32_t* step_dev, float beta1, float beta2,
+                   float eps, float lr0, float lr_min, int lr_max_steps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

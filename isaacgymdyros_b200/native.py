@@ -92,8 +92,21 @@ class DyrosNoiseInjection(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in NOISE_FIELDS]
 
 
+class DyrosPpoBuffers(C.Structure):
+    _fields_ = [("N", i32), ("H", i32), ("gamma", f32), ("tau", f32), ("e_clip", f32), ("critic_coef", f32),
+                ("reward_scale", f32), ("value_bootstrap", i32), ("seed", u64)] + [
+        (n, C.c_void_p) for n in ("obs", "actions", "mus", "neglogp", "values", "rewards", "dones", "advantages", "returns",
+                                  "cur_reward", "cur_length", "ep_stats", "step", "global_step")]
+
+
 _VP, _INT = C.c_void_p, C.c_int
+_PB = C.POINTER(DyrosPpoBuffers)
 SIGNATURES = {
+    "dyros_ppo_act": (_INT, [_PB, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "dyros_ppo_reward": (_INT, [_PB, _VP, _VP, _VP, _VP]),
+    "dyros_ppo_gae": (_INT, [_PB, _VP, _VP, _VP]),
+    "dyros_ppo_loss_grad": (_INT, [_PB, _INT, _INT, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "dyros_ppo_adam": (_INT, [_VP, _VP, _VP, _VP, _INT, _INT, f32, f32, _VP, _VP, _VP, f32, f32, f32, f32, f32, _INT, _VP]),
     "dyros_last_error": (C.c_char_p, []),
     "dyros_abi_version": (_INT, []),
     "dyros_sim_set_l2_persistence": (_INT, [_VP, _VP, C.c_size_t, _VP, C.POINTER(C.c_size_t)]),

@@ -1,0 +1,278 @@
+"""On-device PPO around the env step (BASELINE configs[4]): the rollout / update loop of the reference's
+rl_games fork -- learning/rl_games_custom/a2c_common_dyros.py (A2C: play_steps 629-703, discount_values 485-500,
+prepare_dataset 921-969, train_epoch 837-918), a2c_continuous_seperate.py (AG: calc_gradients 108-227, the two Adam
+optimisers 50-54), models_dyros.py (MD), network_builder_dyros.py, cfg/train/DyrosDynamicWalkPPO.yaml (PPO) -- with
+nothing leaving the GPU: the policy reads the env's observation buffer in place, actions go to the env step in place,
+the rollout buffers, GAE, the loss gradient and both optimisers are kernels of libdyros_b200.so (csrc/ppo_kernels.cu),
+one rollout step and one minibatch update are each ONE CUDA graph, and with several ranks the only traffic is one NCCL
+all-reduce of the flat 1.54 MB gradient bucket per minibatch (AG:161-203) plus a few scalars per epoch.
+
+The two 487-256-256-{13,1} MLPs are library GEMMs (torch / cuBLAS, bf16 autocast where the reference uses fp16
+autocast + GradScaler, PPO:59); parameters, gradients and Adam moments live in flat fp32 buffers."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import native
+
+NOBS, NA = 487, 13
+
+
+@dataclass
+class PPOConfig:
+    """cfg/train/DyrosDynamicWalkPPO.yaml (PPO:28-97)."""
+    horizon_length: int = 128
+    minibatch_size: int = 4096
+    mini_epochs: int = 5
+    gamma: float = 0.99
+    tau: float = 0.95
+    learning_rate: float = 1e-5
+    learning_rate_min: float = 3e-6
+    critic_learning_rate: float = 5e-4      # AG:54
+    lr_schedule: str = "linear"
+    max_epochs: int = 5000
+    e_clip: float = 0.2
+    critic_coef: float = 0.5
+    grad_norm: float = 0.5
+    truncate_grads: bool = True
+    normalize_advantage: bool = True
+    value_bootstrap: bool = True
+    reward_scale: float = 1.0
+    units: tuple = (256, 256)
+    init_gain: float = 0.01                 # orthogonal_initializer gain, PPO:37-38
+    sigma_init: float = -2.302585           # PPO:21-23
+    sigma_last: float = -2.9957             # PPO:24-26
+    mixed_precision: str = "bf16"           # "bf16" | "fp32"
+    seed: int = 42
+    use_cuda_graph: bool = True
+
+
+def layer_shapes(units=(256, 256)):
+    """(name, out, in) of the actor and the critic (network_builder_dyros.py:129-216, `separate: True`)."""
+    dims = [NOBS] + list(units)
+    actor = [(f"actor_mlp.{i}", dims[i + 1], dims[i]) for i in range(len(units))] + [("mu", NA, dims[-1])]
+    critic = [(f"critic_mlp.{i}", dims[i + 1], dims[i]) for i in range(len(units))] + [("value", 1, dims[-1])]
+    return actor, critic
+
+
+class FlatActorCritic:
+    """Parameters, gradients and Adam moments of both networks in flat fp32 buffers: [0, n_actor) actor, then critic.
+    The layer tensors are views (the flat gradient buffer is what the all-reduce and the optimiser kernel see)."""
+
+    def __init__(self, device, cfg: PPOConfig):
+        self.cfg, self.device = cfg, torch.device(device)
+        actor, critic = layer_shapes(cfg.units)
+        self.n_actor = sum(o * i + o for _, o, i in actor)
+        self.n = self.n_actor + sum(o * i + o for _, o, i in critic)
+        self.flat = torch.zeros(self.n, device=device)
+        self.grad = torch.zeros(self.n, device=device)
+        self.exp_avg = torch.zeros(self.n, device=device)
+        self.exp_avg_sq = torch.zeros(self.n, device=device)
+        self.layers: Dict[str, tuple] = {}
+        off = 0
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(cfg.seed)
+        for name, o, i in actor + critic:
+            w = torch.nn.Parameter(torch.empty(0, device=device))
+            w.data = self.flat[off:off + o * i].view(o, i)
+            w.grad = self.grad[off:off + o * i].view(o, i)
+            init = torch.empty(o, i)
+            torch.nn.init.orthogonal_(init, gain=cfg.init_gain, generator=gen)  # every nn.Linear, network_builder_dyros.py:113-118
+            w.data.copy_(init)
+            off += o * i
+            b = torch.nn.Parameter(torch.empty(0, device=device))
+            b.data = self.flat[off:off + o]
+            b.grad = self.grad[off:off + o]  # zeros (network_builder_dyros.py:117-118)
+            off += o
+            self.layers[name] = (w, b)
+        assert off == self.n
+        # fixed, non-trainable log-std (network_builder_dyros.py:103; PPO:27 fixed_sigma), scheduled by update_action_noise
+        self.logstd = torch.full((NA,), cfg.sigma_init, device=device)
+        self.n_hidden = len(cfg.units)
+
+    def update_action_noise(self, progress_remaining: float):
+        """MD:64-70."""
+        b = 2 * progress_remaining - 1 if progress_remaining > 0.5 else 0.0
+        self.logstd.fill_(self.cfg.sigma_init * b + self.cfg.sigma_last * (1 - b))
+
+    def _mlp(self, x, prefix, head):
+        for i in range(self.n_hidden):
+            w, b = self.layers[f"{prefix}.{i}"]
+            x = F.relu(F.linear(x, w, b))
+        w, b = self.layers[head]
+        return F.linear(x, w, b)
+
+    def forward(self, obs):
+        """mu (B,13), value (B) -- `mu_activation: None`, value head linear (PPO:17-18)."""
+        amp = self.cfg.mixed_precision == "bf16"
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp and obs.is_cuda):
+            mu = self._mlp(obs, "actor_mlp", "mu")
+            v = self._mlp(obs, "critic_mlp", "value")
+        return mu, v.squeeze(-1)
+
+
+class PPOTrainer:
+    def __init__(self, env, cfg: Optional[PPOConfig] = None, rank: int = 0, world: int = 1):
+        self.env, self.cfg = env, cfg or PPOConfig()
+        self.rank, self.world = rank, world
+        self.lib = native.load()
+        c, dev = self.cfg, env.device
+        N, H = env.num_envs, c.horizon_length
+        self.N, self.H = N, H
+        if (N * H) % c.minibatch_size:
+            raise ValueError("num_envs * horizon_length must be a multiple of minibatch_size (A2C:192)")
+        self.num_minibatches = N * H // c.minibatch_size
+        self.net = FlatActorCritic(dev, c)
+        if world > 1:  # hvd.setup_algo: rank 0's parameters everywhere (A2C:980-981)
+            import torch.distributed as dist
+            dist.broadcast(self.net.flat, 0)
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
+        self.buf = {"obs": z(N, H, NOBS), "actions": z(N, H, NA), "mus": z(N, H, NA), "neglogp": z(N, H), "values": z(N, H),
+                    "rewards": z(N, H), "dones": z(N, H), "advantages": z(N, H), "returns": z(N, H), "cur_reward": z(N),
+                    "cur_length": z(N), "ep_stats": z(3), "step": z(1, dt=torch.int32), "global_step": z(1, dt=torch.int64)}
+        pb = native.DyrosPpoBuffers()
+        pb.N, pb.H, pb.gamma, pb.tau, pb.e_clip, pb.critic_coef = N, H, c.gamma, c.tau, c.e_clip, c.critic_coef
+        pb.reward_scale, pb.value_bootstrap, pb.seed = c.reward_scale, int(c.value_bootstrap), c.seed + 7919 * (rank + 1)
+        for k, t in self.buf.items():
+            setattr(pb, k, t.data_ptr())
+        self.pb = pb
+        self.actions = z(N, NA)
+        self.adv_norm = z(N, H)
+        self.mb_dmu, self.mb_dv = z(c.minibatch_size, NA), z(c.minibatch_size)
+        self.stats = z(4)
+        self.norm2 = z(1)
+        self.lr = torch.tensor([c.learning_rate, c.critic_learning_rate], device=dev)
+        self.opt_step = z(1, dt=torch.int32)
+        self.inject_normal: Optional[torch.Tensor] = None  # (H,N,13) test hook
+        self.epoch = 0
+        self._g_rollout: Optional[torch.cuda.CUDAGraph] = None
+        self._g_update: Dict[int, torch.cuda.CUDAGraph] = {}
+        self._static_out: Dict[int, tuple] = {}
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream)
+
+    def _p(self, t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    # ------------------------------------------------------------------ rollout (A2C:629-703)
+    def _rollout_step(self):
+        env = self.env
+        with torch.no_grad():
+            mu, v = self.net.forward(env.obs_buf)
+            mu, v = mu.float().contiguous(), v.float().contiguous()
+        native.check(self.lib.dyros_ppo_act(C.byref(self.pb), self._p(mu), self._p(v), self._p(self.net.logstd), self._p(env.obs_buf),
+                                            self._p(env.reset_buf), self._p(self.actions), self._p(self.inject_normal),
+                                            self._stream), "dyros_ppo_act")
+        env.core.step(self.actions)  # VecTask.step: 2 launches, reads `actions` in place
+        native.check(self.lib.dyros_ppo_reward(C.byref(self.pb), self._p(env.rew_buf), self._p(env.timeout_buf),
+                                               self._p(env.reset_buf), self._stream), "dyros_ppo_reward")
+
+    def rollout(self):
+        """horizon_length env steps + GAE; everything stays on the device."""
+        if self.cfg.use_cuda_graph and self._g_rollout is None:
+            self._rollout_step()  # warm-up (cuBLAS workspaces, lazy init) outside the capture
+            torch.cuda.synchronize()
+            self.buf["step"].zero_()
+            side = torch.cuda.Stream(device=self.env.device)
+            side.wait_stream(torch.cuda.current_stream())
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                self._rollout_step()
+            self._g_rollout = g
+            self.buf["step"].zero_()  # (capturing executes nothing; the warm-up step is an extra, unrecorded env step)
+        for _ in range(self.H):
+            if self._g_rollout is not None:
+                self._g_rollout.replay()
+            else:
+                self._rollout_step()
+        with torch.no_grad():
+            _, last_v = self.net.forward(self.env.obs_buf)   # get_values(self.obs), A2C:686
+            last_v = last_v.float().contiguous()
+        native.check(self.lib.dyros_ppo_gae(C.byref(self.pb), self._p(last_v), self._p(self.env.reset_buf), self._stream), "dyros_ppo_gae")
+
+    # ------------------------------------------------------------------ update (A2C:921-969, A2C:862-903, AG:108-227)
+    def _prepare(self):
+        adv = self.buf["advantages"]
+        if self.cfg.normalize_advantage:  # A2C:943-944 (torch.std: unbiased)
+            self.adv_norm.copy_((adv - adv.mean()) / (adv.std() + 1e-8))
+        else:
+            self.adv_norm.copy_(adv)
+
+    def _minibatch(self, i: int):
+        c, mb = self.cfg, self.cfg.minibatch_size
+        r0 = i * mb
+        obs = self.buf["obs"].view(self.N * self.H, NOBS)[r0:r0 + mb]
+        mu, v = self.net.forward(obs)
+        mu32, v32 = mu.float().contiguous(), v.float().contiguous()
+        native.check(self.lib.dyros_ppo_loss_grad(C.byref(self.pb), r0, mb, self._p(mu32), self._p(v32), self._p(self.net.logstd),
+                                                  self._p(self.adv_norm), self._p(self.mb_dmu), self._p(self.mb_dv),
+                                                  self._p(self.stats), self._stream), "dyros_ppo_loss_grad")
+        self.net.grad.zero_()
+        torch.autograd.backward([mu, v], [self.mb_dmu.to(mu.dtype), self.mb_dv.to(v.dtype)])
+        if self.world > 1:  # optimizer.synchronize(): one all-reduce of the flat bucket (AG:161-173)
+            import torch.distributed as dist
+            dist.all_reduce(self.net.grad)
+        n = self.net
+        native.check(self.lib.dyros_ppo_adam(self._p(n.flat), self._p(n.grad), self._p(n.exp_avg), self._p(n.exp_avg_sq), n.n_actor, n.n,
+                                             1.0 / self.world, c.grad_norm if c.truncate_grads else 0.0, self._p(self.norm2),
+                                             self._p(self.lr), self._p(self.opt_step), 0.9, 0.999, 1e-8, c.learning_rate,
+                                             c.learning_rate_min, c.max_epochs if c.lr_schedule == "linear" else 0,
+                                             self._stream), "dyros_ppo_adam")
+        # dataset.update_mu_sigma (A2C:884): later mini-epochs measure the KL against this pass
+        self.buf["mus"].view(self.N * self.H, NA)[r0:r0 + mb].copy_(mu32.detach())
+
+    def update(self):
+        self._prepare()
+        self.stats.zero_()
+        for _ in range(self.cfg.mini_epochs):
+            for i in range(self.num_minibatches):
+                if not self.cfg.use_cuda_graph:
+                    self._minibatch(i)
+                    continue
+                g = self._g_update.get(i)
+                if g is None:
+                    if not self._g_update:  # one eager pass first (autograd / cuBLAS / NCCL lazy init), undone below
+                        snap = [t.clone() for t in (self.net.flat, self.net.exp_avg, self.net.exp_avg_sq, self.opt_step, self.lr,
+                                                    self.stats, self.buf["mus"])]
+                        self._minibatch(i)
+                        torch.cuda.synchronize()
+                        for t, s in zip((self.net.flat, self.net.exp_avg, self.net.exp_avg_sq, self.opt_step, self.lr, self.stats,
+                                         self.buf["mus"]), snap):
+                            t.copy_(s)
+                    side = torch.cuda.Stream(device=self.env.device)
+                    side.wait_stream(torch.cuda.current_stream())
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        self._minibatch(i)
+                    self._g_update[i] = g
+                g.replay()
+
+    def train_epoch(self) -> Dict[str, float]:
+        """One epoch of ContinuousA2CBase.train (A2C:983-1008): noise schedule, rollout, update. One device->host read."""
+        c = self.cfg
+        self.epoch += 1
+        self.net.update_action_noise((c.max_epochs - self.epoch) / c.max_epochs)  # A2C:985
+        self.buf["ep_stats"].zero_()
+        self.rollout()
+        self.update()
+        k = c.mini_epochs * self.num_minibatches
+        out = torch.cat([self.stats / k, self.buf["ep_stats"], self.lr[:1]])
+        if self.world > 1:
+            import torch.distributed as dist
+            s = out.clone()
+            dist.all_reduce(s)
+            out = s / self.world
+            out[4:7] = s[4:7]
+        a_loss, c_loss, kl, clip_frac, ep_r, ep_l, ep_n, lr = out.tolist()
+        return {"a_loss": a_loss, "c_loss": c_loss, "kl": kl, "clip_frac": clip_frac, "lr": lr,
+                "mean_reward": ep_r / max(ep_n, 1.0), "mean_length": ep_l / max(ep_n, 1.0), "episodes": ep_n,
+                "frames": self.N * self.H * self.world}
