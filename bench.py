@@ -63,6 +63,11 @@ def parse():
     ap.add_argument("--dr-extra", action="store_true",
                     help="also randomise friction x[0.7,1.3] and the PD gains x[0.9,1.1] per env (BASELINE configs[3])")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--workload", default="env", choices=["env", "ppo"],
+                    help="env: the env-step hot path (BASELINE configs[1], the default and the driver's line); ppo: end-to-end "
+                         "on-device PPO training (BASELINE configs[4]): --steps / --warmup count EPOCHS of 128 env steps + 640 updates")
+    ap.add_argument("--horizon", type=int, default=128)
+    ap.add_argument("--ppo-dtype", default="bf16", choices=["bf16", "fp32"])
     return ap.parse_args()
 
 
@@ -323,6 +328,20 @@ def run_ours(a):
         e1.record()
         barrier()
         e2e_ms = e0.elapsed_time(e1)
+        # ---- (3c) what the host link gives at this rank count, same run: the same packed block (obs | rew | reset |
+        #           time_outs) copied device -> pinned host back to back on the copy stream, nothing else running, all
+        #           ranks at once. e2e cannot beat it; the fraction says how well the pipelined step hides its kernels.
+        pipe = env._pipe
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(cs):
+            c0.record(cs)
+            for i in range(K):
+                pipe.host[i % depth].copy_(pipe.dev[i % depth], non_blocking=True)
+            c1.record(cs)
+        c1.synchronize()
+        barrier()
+        d2h_ms = c0.elapsed_time(c1)
     clocks = clk.summary()
     h2d, d2h = N * 13 * 4, env.core.result_bytes()
     # ---- (4) the dominant kernel alone (k_step_physics = 2 x (torque, physics sub-step, noise) in one launch), inside
@@ -363,7 +382,7 @@ def run_ours(a):
         print(f"l2 persistence measurement skipped: {exc}", file=sys.stderr)
 
     from isaacgymdyros_b200.sharding import max_over_ranks, reduce_episode_stats
-    cold_ms, warm_ms, e2e_ms, e2e_sync_ms, k1_ms, persist_ms = (max_over_ranks(x, dev) for x in (cold_ms, warm_ms, e2e_ms, e2e_sync_ms, k1_ms, persist_ms))
+    cold_ms, warm_ms, e2e_ms, e2e_sync_ms, k1_ms, persist_ms, d2h_ms = (max_over_ranks(x, dev) for x in (cold_ms, warm_ms, e2e_ms, e2e_sync_ms, k1_ms, persist_ms, d2h_ms))
     # episode statistics across ranks (the only data the env path ever reduces)
     stats = reduce_episode_stats({"epi_len_log": env.epi_len_log, "contact_reward_mean": env.contact_reward_mean})
     if rank == 0:
@@ -394,7 +413,11 @@ def run_ours(a):
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K,
                     "api": "DyrosDynamicWalk.step_async / step_wait: pinned host actions in, one packed pinned host block "
                            "(obs, rew, reset, time_outs) out per step; the transfer of step k overlaps the kernels of step k+1",
-                    "tickets_in_flight": depth},
+                    "tickets_in_flight": depth,
+                    "d2h_ceiling": {"value": total_envs * K / (d2h_ms * 1e-3), "unit": UNIT, "ms_per_step": d2h_ms / K,
+                                    "gb_per_s_per_rank": d2h / (d2h_ms / K * 1e-3) / 1e9,
+                                    "what": "the same result block copied device -> pinned host back to back, all ranks at once, no kernels"},
+                    "frac_of_d2h_ceiling": d2h_ms / e2e_ms},
             "e2e_sync": {"value": total_envs * K / (e2e_sync_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_sync_ms / K,
                          "d2h_bytes_per_step": N * 487 * 4 + N * 4 + N * 8,
                          "api": "DyrosDynamicWalk.step + three device->host copies on the same stream, nothing overlapped"},
@@ -430,6 +453,96 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ PPO (configs[4])
+def run_ppo(a):
+    """End-to-end PPO training on the device (isaacgymdyros_b200/ppo.py): per epoch horizon x envs env-steps (policy
+    forward on the GPU reading obs_buf in place) + mini_epochs x minibatches updates, each with one NCCL all-reduce of
+    the flat 1.54 MB gradient bucket when world > 1. Times K epochs after W warm-up epochs (graph captures land there)."""
+    import torch
+    import torch.distributed as dist
+    from isaacgymdyros_b200 import DyrosDynamicWalk, default_cfg
+    from isaacgymdyros_b200.ppo import PPOConfig, PPOTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = f"cuda:{local}"
+    torch.cuda.set_device(dev)
+    N, K, W = a.envs, a.steps, max(a.warmup, 1)
+    env = DyrosDynamicWalk(default_cfg(N), dev, rank=rank, use_cuda_graph=False)
+    cfg = PPOConfig(horizon_length=a.horizon, mixed_precision=a.ppo_dtype)
+    tr = PPOTrainer(env, cfg, rank=rank, world=world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        out = tr.train_epoch()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    t_roll = t_upd = 0.0
+    with ClockSampler(local) as clk:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            tr.epoch += 1
+            tr.net.update_action_noise((cfg.max_epochs - tr.epoch) / cfg.max_epochs)
+            tr.buf["ep_stats"].zero_()
+            ev[0].record(); tr.rollout(); ev[1].record(); tr.update(); ev[2].record()
+            ev[2].synchronize()
+            t_roll += ev[0].elapsed_time(ev[1]); t_upd += ev[1].elapsed_time(ev[2])
+        e1.record()
+        barrier()
+        total_ms = e0.elapsed_time(e1)
+        # the collective alone: the same flat bucket, all-reduced back to back
+        ar_ms = 0.0
+        if world > 1:
+            reps = 200
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(reps):
+                dist.all_reduce(tr.net.grad)
+            a1.record()
+            barrier()
+            ar_ms = a0.elapsed_time(a1) / reps
+    from isaacgymdyros_b200.sharding import max_over_ranks
+    total_ms, t_roll, t_upd, ar_ms = (max_over_ranks(x, dev) for x in (total_ms, t_roll, t_upd, ar_ms))
+    out = tr.train_epoch()
+    if rank == 0:
+        frames = N * a.horizon * world * K
+        updates = cfg.mini_epochs * tr.num_minibatches
+        line = {"metric": "env-steps/s, end-to-end on-device PPO training (BASELINE configs[4])", "value": frames / (total_ms * 1e-3),
+                "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": a.ppo_dtype, "data": "synthetic",
+                "config": {"workload": "DyrosDynamicWalk PPO (DyrosDynamicWalkPPO.yaml): per epoch horizon x envs env-steps with the "
+                                       "policy on the GPU + mini_epochs x minibatches updates; one step = one epoch",
+                           "envs_per_gpu": N, "horizon_length": a.horizon, "minibatch_size": cfg.minibatch_size,
+                           "mini_epochs": cfg.mini_epochs, "updates_per_epoch": updates, "parameters": tr.net.n,
+                           "gradient_bucket_bytes": tr.net.n * 4},
+                "clocks": clk.summary(),
+                "breakdown_ms_per_epoch": {"rollout_and_gae": t_roll / K, "update": t_upd / K,
+                                           "update_per_minibatch": t_upd / K / updates,
+                                           "allreduce_alone_per_call": ar_ms, "allreduce_alone_per_epoch": ar_ms * updates},
+                "gpu_launches": None, "last_epoch": out}
+        emit(line)
+    if world > 1:
+        # the CUDA graphs hold captured NCCL work: drop them before the communicator goes, and do not wait on a
+        # destroy_process_group that was seen to hang behind them (the JSON line is out; nothing is left to flush)
+        tr._g_update.clear()
+        tr._g_rollout = None
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 _JSON_FD = None
 
 
@@ -448,6 +561,8 @@ def main():
     os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "ppo":
+        run_ppo(a)
     else:
         run_ours(a)
 
