@@ -217,6 +217,15 @@ int dyros_sim_destroy(DyrosSim* sim);
 int dyros_simulate(DyrosSim* sim, int apply_wrench, void* stream);
 /* gym.refresh_rigid_body_state_tensor: forward kinematics into rigid_body_state (DOCT:193-207). */
 int dyros_refresh_rigid_body_state(DyrosSim* sim, void* stream);
+/* gym.refresh_dof_force_tensor (tasks/humanoid.py:85,245; DOCT "DOF forces"): (N*nd) generalised force at every DOF =
+ * applied actuation + passive joint spring and damper on the current state, into the caller's buffer. */
+int dyros_refresh_dof_force(DyrosSim* sim, float* dof_force, void* stream);
+/* gym.refresh_force_sensor_tensor (tasks/humanoid.py:80,167-168,243): per env and sensor [force 3, torque 3] in the sensor
+ * frame: the net contact force on the sensor's body (torque entries zero: the contact model keeps no line of action).
+ * sensor_body (ns) int32 and sensor_pose (ns,7) [pos3, quat xyzw] are device arrays describing the asset's sensors;
+ * refreshes rigid_body_state first (the sensor frames come from it). */
+int dyros_refresh_force_sensors(DyrosSim* sim, const int32_t* sensor_body, const float* sensor_pose, int num_sensors,
+                                float* sensor_out, void* stream);
 /* gym.set_dof_state_tensor_indexed / set_actor_root_state_tensor_indexed (T:738,746): buffers are the live state
  * already (immediate CPU-pipeline semantics); validates the ids and returns. */
 int dyros_set_state_indexed(DyrosSim* sim, const int32_t* env_ids, int count, void* stream);

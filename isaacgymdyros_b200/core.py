@@ -385,6 +385,14 @@ class DyrosCore:
         native.check(self.lib.dyros_sim_launch_info(self.sim_handle, C.byref(out)), "dyros_sim_launch_info")
         return {"envs_per_cta": out[0], "ctas": out[1], "threads_per_cta": out[2], "smem_bytes": out[3]}
 
+    def refresh_dof_force(self, out: torch.Tensor):
+        native.check(self.lib.dyros_refresh_dof_force(self.sim_handle, C.c_void_p(out.data_ptr()), self._stream), "dyros_refresh_dof_force")
+
+    def refresh_force_sensors(self, sensor_body: torch.Tensor, sensor_pose: torch.Tensor, out: torch.Tensor):
+        native.check(self.lib.dyros_refresh_force_sensors(self.sim_handle, C.c_void_p(sensor_body.data_ptr()),
+                                                          C.c_void_p(sensor_pose.data_ptr()), int(sensor_body.numel()),
+                                                          C.c_void_p(out.data_ptr()), self._stream), "dyros_refresh_force_sensors")
+
     def refresh_rigid_body_state(self):
         native.check(self.lib.dyros_refresh_rigid_body_state(self.sim_handle, self._stream), "dyros_refresh_rigid_body_state")
 

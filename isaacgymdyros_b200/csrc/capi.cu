@@ -245,6 +245,28 @@ int dyros_refresh_rigid_body_state(DyrosSim* sim, void* stream) {
   }
   return launch_refresh_rigid_body_state(s, (cudaStream_t)stream);
 }
+int dyros_refresh_dof_force(DyrosSim* sim, float* dof_force, void* stream) {
+  SIM_OR_FAIL("dyros_refresh_dof_force");
+  if (!dof_force) {
+    set_error("dyros_refresh_dof_force: output buffer is NULL");
+    return 1;
+  }
+  return launch_refresh_dof_force(s, dof_force, (cudaStream_t)stream);
+}
+int dyros_refresh_force_sensors(DyrosSim* sim, const int32_t* sensor_body, const float* sensor_pose, int num_sensors,
+                                float* sensor_out, void* stream) {
+  SIM_OR_FAIL("dyros_refresh_force_sensors");
+  if (!sensor_body || !sensor_pose || !sensor_out || num_sensors < 1) {
+    set_error("dyros_refresh_force_sensors: null argument or no sensors");
+    return 1;
+  }
+  if (!s->b.rigid_body_state) {
+    set_error("dyros_refresh_force_sensors: the sim was created without a rigid_body_state buffer (sensor frames come from it)");
+    return 1;
+  }
+  if (launch_refresh_rigid_body_state(s, (cudaStream_t)stream)) return 1;
+  return launch_refresh_force_sensors(s, sensor_body, sensor_pose, num_sensors, sensor_out, (cudaStream_t)stream);
+}
 int dyros_set_state_indexed(DyrosSim* sim, const int32_t* env_ids, int count, void* stream) {
   SIM_OR_FAIL("dyros_set_state_indexed");
   (void)stream;

@@ -36,7 +36,7 @@ static const T* at(void* base, size_t off) {
 }
 
 struct ModelOffsets {
-  size_t parent, dof, E, r, ax, cs, ch, bs, bd, bl, bp, br, bi, lo, up, vl, ef, ps, pb, pp, pr, ys, yb, yc, ya, yz, sc, rc, ro, dl, pg, fp, fb;
+  size_t parent, dof, E, r, ax, cs, ch, bs, bd, bl, bp, br, bi, lo, up, vl, ef, ps, pb, pp, pr, ys, yb, yc, ya, yz, sc, rc, ro, dl, pg, fp, fb, st;
 };
 
 // Fills `dm` (counts, foot tables) and appends every table to `bl`. Returns "" or an error message.
@@ -309,6 +309,12 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
   o.bs = bl.add_i(body_start.data(), nl + 1); o.bd = bl.add_i(bodies.data(), nb);
   o.lo = bl.add_f(m->dof_lower, nd); o.up = bl.add_f(m->dof_upper, nd); o.vl = bl.add_f(m->dof_vel_limit, nd);
   o.ef = bl.add_f(m->dof_effort, nd);
+  {
+    std::vector<double> st(nd, 0.0);
+    if (m->dof_stiffness)
+      for (int d = 0; d < nd; ++d) st[d] = m->dof_stiffness[d];
+    o.st = bl.add_f(st.data(), nd);
+  }
   o.ps = bl.add_i(pt_start.data(), nl + 1); o.ys = bl.add_i(cyl_start.data(), nl + 1);
   o.sc = bl.add_i(m->sched, (size_t)m->sched_slots * DYROS_LANES);
   o.rc = bl.add_f32(reach.data(), nl);
@@ -342,6 +348,7 @@ static void resolve_model(DevModel& dm, const ModelOffsets& o, void* base) {
   dm.body_inertia = at<float>(base, o.bi);
   dm.dof_lower = at<float>(base, o.lo); dm.dof_upper = at<float>(base, o.up); dm.dof_vel_limit = at<float>(base, o.vl);
   dm.dof_effort = at<float>(base, o.ef);
+  dm.dof_stiffness = at<float>(base, o.st);
   dm.link_pt_start = at<int>(base, o.ps); dm.pt_body = at<int>(base, o.pb); dm.pt_pos = at<float>(base, o.pp);
   dm.pt_radius = at<float>(base, o.pr);
   dm.link_cyl_start = at<int>(base, o.ys); dm.cyl_body = at<int>(base, o.yb); dm.cyl_center = at<float>(base, o.yc);

@@ -44,6 +44,7 @@ struct DevModel {
   const float* dof_upper;
   const float* dof_vel_limit;
   const float* dof_effort;
+  const float* dof_stiffness;   // [nd] joint spring about q = 0
   const int* link_pt_start;     // [nl+1] penalty points grouped by link
   const int* pt_body;           // [npp]
   const float* pt_pos;          // [npp*3]
@@ -157,6 +158,8 @@ int launch_pack_results(Task* t, float* dst, cudaStream_t s);
 int physics_configure(Sim* sim);  // chooses envs_per_block / shared memory, sets the kernel attributes
 int launch_simulate(Sim* sim, int apply_wrench, const float* push_force, cudaStream_t s);
 int launch_refresh_rigid_body_state(Sim* sim, cudaStream_t s);
+int launch_refresh_dof_force(Sim* sim, float* out, cudaStream_t s);
+int launch_refresh_force_sensors(Sim* sim, const int32_t* sensor_body, const float* sensor_pose, int ns, float* out, cudaStream_t s);
 // skipframe x (torque, simulate, sensor noise) in one launch; with `actions` the policy-step prologue runs in it too
 int launch_task_physics(Task* t, cudaStream_t s, long long* trace = nullptr, bool pdl = false, const float* actions = nullptr);
 int measure_fp32_peak(int device, int iters, double* tflops_out);

@@ -526,6 +526,52 @@ __global__ void __launch_bounds__(64) k_rigid_body_state(DevModel m, SimParams p
   }
 }
 
+// gym.refresh_dof_force_tensor (tensors.rst.txt "DOF force tensor", used by tasks/humanoid.py:85,245): the generalised force
+// at every DOF = applied actuation (clamped to the ctrlrange when clamp_effort is set) plus the joint's passive spring and
+// damper, evaluated on the current state. One thread per DOF.
+__global__ void __launch_bounds__(256) k_dof_force(DevModel m, SimParams p, DyrosSimBuffers b, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.N * m.nd) return;
+  const int d = i % m.nd;
+  float tq = b.dof_actuation_force[i];
+  if (p.clamp_effort) {
+    const float lim = m.dof_effort[d];
+    tq = tq > lim ? lim : (tq < -lim ? -lim : tq);
+  }
+  out[i] = tq - b.dof_damping[i] * b.dof_state[2 * i + 1] - m.dof_stiffness[d] * b.dof_state[2 * i];
+}
+int launch_refresh_dof_force(Sim* sim, float* out, cudaStream_t s) {
+  const int n = sim->p.N * sim->m.nd;
+  k_dof_force<<<(n + 255) / 256, 256, 0, s>>>(sim->m, sim->p, sim->b, out);
+  DY_LAUNCH_CHECK();
+  return 0;
+}
+
+// gym.refresh_force_sensor_tensor (tasks/humanoid.py:80,243; create_asset_force_sensor :167-168): per sensor the net contact
+// force on its body over the last sub-step, expressed in the sensor frame (body rotation x sensor rotation), as
+// [force 3, torque 3]. The contact model keeps one net force per body (net_contact_force), not its line of action: the
+// torque entries are zero. Needs rigid_body_state to be current (the caller refreshes it first). One thread per sensor.
+__global__ void __launch_bounds__(128) k_force_sensors(DevModel m, SimParams p, DyrosSimBuffers b, const int32_t* __restrict__ sensor_body,
+                                                       const float* __restrict__ sensor_pose, int ns, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.N * ns) return;
+  const int e = i / ns, s = i - e * ns, body = sensor_body[s];
+  const float* rb = b.rigid_body_state + ((size_t)e * m.nb + body) * 13;
+  const M3 Rb = quat_to_mat(rb[3], rb[4], rb[5], rb[6]);
+  const float* sp = sensor_pose + 7 * s;
+  const M3 Rs = quat_to_mat(sp[3], sp[4], sp[5], sp[6]);
+  const V3 F = ld3_f(b.net_contact_force + ((size_t)e * m.nb + body) * 3);
+  const V3 f = mulT(Rs, mulT(Rb, F));
+  float* o = out + (size_t)i * 6;
+  o[0] = f.x; o[1] = f.y; o[2] = f.z; o[3] = 0.f; o[4] = 0.f; o[5] = 0.f;
+}
+int launch_refresh_force_sensors(Sim* sim, const int32_t* sensor_body, const float* sensor_pose, int ns, float* out, cudaStream_t s) {
+  const int n = sim->p.N * ns;
+  k_force_sensors<<<(n + 127) / 128, 128, 0, s>>>(sim->m, sim->p, sim->b, sensor_body, sensor_pose, ns, out);
+  DY_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_refresh_rigid_body_state(Sim* sim, cudaStream_t s) {
   k_rigid_body_state<<<(sim->p.N + 63) / 64, 64, 0, s>>>(sim->m, sim->p, sim->b);
   DY_LAUNCH_CHECK();

@@ -176,9 +176,25 @@ DOF_PROPS_DTYPE = np.dtype([("hasLimits", "?"), ("lower", "f4"), ("upper", "f4")
                             ("effort", "f4"), ("stiffness", "f4"), ("damping", "f4"), ("friction", "f4"), ("armature", "f4")])
 
 
+class ActuatorProperties:
+    """get_asset_actuator_properties (tasks/humanoid.py:159-160): the MJCF motors; `motor_effort` = gear / ctrlrange bound."""
+
+    def __init__(self, motor_effort: float, name: str = ""):
+        self.motor_effort, self.name = float(motor_effort), name
+        self.lower_control_limit, self.upper_control_limit = -1.0, 1.0
+
+
+class ForceSensorProperties:
+    def __init__(self):
+        self.enable_forward_dynamics_forces = True
+        self.enable_constraint_solver_forces = True
+        self.use_world_frame = False
+
+
 class Asset:
     def __init__(self, tables: ModelTables, options: AssetOptions, name: str):
         self.tables, self.options, self.name = tables, options, name
+        self.force_sensors: List[tuple] = []  # (body index, Transform), create_asset_force_sensor
 
 
 class Env:
@@ -288,6 +304,26 @@ class Gym:
 
     def find_asset_dof_index(self, asset: Asset, name: str) -> int:
         return asset.tables.dof_names.index(name) if name in asset.tables.dof_names else INVALID_HANDLE
+
+    def get_asset_actuator_properties(self, asset: Asset):
+        t = asset.tables
+        return [ActuatorProperties(float(t.dof_effort[d]), t.dof_names[d]) for d in range(t.num_dofs)]
+
+    def get_asset_actuator_count(self, asset: Asset) -> int:
+        return asset.tables.num_dofs
+
+    def create_asset_force_sensor(self, asset: Asset, body_idx: int, local_pose: Optional[Transform] = None, props=None) -> int:
+        """tasks/humanoid.py:163-168. Returns the sensor index."""
+        if not (0 <= int(body_idx) < asset.tables.num_bodies):
+            return INVALID_HANDLE
+        asset.force_sensors.append((int(body_idx), local_pose or Transform()))
+        return len(asset.force_sensors) - 1
+
+    def get_asset_force_sensor_count(self, asset: Asset) -> int:
+        return len(asset.force_sensors)
+
+    def enable_actor_dof_force_sensors(self, env: Env, handle: int) -> bool:
+        return True  # the DOF force tensor is always available (tasks/humanoid.py:196)
 
     def create_env(self, sim: Sim, lower: Vec3, upper: Vec3, num_per_row: int) -> Env:
         if sim.core is not None:
@@ -485,6 +521,42 @@ class Gym:
     def acquire_net_contact_force_tensor(self, sim: Sim) -> Tensor:
         return self._desc(sim, "net_contact_force")
 
+    def acquire_dof_force_tensor(self, sim: Sim) -> Tensor:
+        """(num_dofs,) generalised force at every DOF (tasks/humanoid.py:85); filled by refresh_dof_force_tensor."""
+        if sim.core is None:
+            raise native.DyrosError("acquire_dof_force_tensor: call prepare_sim first (DOCT:30-44)")
+        if "dof_force" not in sim.core.sim_t:
+            sim.core.sim_t["dof_force"] = torch.zeros(len(sim.envs) * sim.asset.tables.num_dofs, device=sim.core.device)
+        return self._desc(sim, "dof_force")
+
+    def refresh_dof_force_tensor(self, sim: Sim) -> bool:
+        if sim.core is None or "dof_force" not in sim.core.sim_t:
+            return False
+        sim.core.refresh_dof_force(sim.core.sim_t["dof_force"])
+        return True
+
+    def acquire_force_sensor_tensor(self, sim: Sim) -> Tensor:
+        """(num_envs * sensors_per_env, 6) [force, torque] in the sensor frames (tasks/humanoid.py:80-83)."""
+        if sim.core is None:
+            raise native.DyrosError("acquire_force_sensor_tensor: call prepare_sim first (DOCT:30-44)")
+        ns = len(sim.asset.force_sensors)
+        if ns == 0:
+            return Tensor(torch.zeros(0, 6, device=sim.core.device))  # wrap_tensor prints "Can't create empty tensor" (GTC:40-45)
+        if "force_sensor" not in sim.core.sim_t:
+            dev = sim.core.device
+            sim.core.sim_t["force_sensor"] = torch.zeros(len(sim.envs) * ns, 6, device=dev)
+            sim.core.sim_t["sensor_body"] = torch.tensor([b for b, _ in sim.asset.force_sensors], dtype=torch.int32, device=dev)
+            sim.core.sim_t["sensor_pose"] = torch.tensor([[tf.p.x, tf.p.y, tf.p.z, tf.r.x, tf.r.y, tf.r.z, tf.r.w]
+                                                          for _, tf in sim.asset.force_sensors], dtype=torch.float32, device=dev)
+        return self._desc(sim, "force_sensor")
+
+    def refresh_force_sensor_tensor(self, sim: Sim) -> bool:
+        if sim.core is None or "force_sensor" not in sim.core.sim_t:
+            return False
+        t = sim.core.sim_t
+        sim.core.refresh_force_sensors(t["sensor_body"], t["sensor_pose"], t["force_sensor"])
+        return True
+
     def refresh_actor_root_state_tensor(self, sim: Sim) -> bool:
         return sim.core is not None
 
@@ -578,6 +650,12 @@ class Gym:
 
     # ------------------------------------------------------------------ viewer (headless only, vec_task.py:212-231)
     def create_viewer(self, *a, **k):
+        return None
+
+    def viewer_camera_look_at(self, *a, **k):
+        return None
+
+    def subscribe_viewer_keyboard_event(self, *a, **k):
         return None
 
     def step_graphics(self, *a, **k):

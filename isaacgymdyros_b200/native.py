@@ -115,6 +115,8 @@ SIGNATURES = {
     "dyros_simulate": (_INT, [_VP, _INT, _VP]),
     "dyros_refresh_rigid_body_state": (_INT, [_VP, _VP]),
     "dyros_set_state_indexed": (_INT, [_VP, _VP, _INT, _VP]),
+    "dyros_refresh_dof_force": (_INT, [_VP, _VP, _VP]),
+    "dyros_refresh_force_sensors": (_INT, [_VP, _VP, _VP, _INT, _VP, _VP]),
     "dyros_measure_fp32_peak": (_INT, [_INT, _INT, C.POINTER(C.c_double)]),
     "dyros_sim_launch_info": (_INT, [_VP, C.POINTER(C.c_int32 * 4)]),
     "dyros_task_create": (_INT, [_VP, C.POINTER(DyrosTaskDesc), C.POINTER(DyrosTaskBuffers), C.POINTER(_VP)]),

@@ -47,6 +47,18 @@ class OracleCore:
     def refresh_rigid_body_state(self):
         pass
 
+    def refresh_dof_force(self, out):
+        s, N = self.sim_t, self.N
+        ds = s["dof_state"].view(N, self.nd, 2)
+        stiff = torch.tensor(self.tables.dof_stiffness, dtype=torch.float32)
+        out.copy_((s["dof_actuation_force"].view(N, self.nd) - s["dof_damping"] * ds[:, :, 1] - stiff * ds[:, :, 0]).reshape(-1))
+
+    def refresh_force_sensors(self, sensor_body, sensor_pose, out):
+        # (sensor frames: the stand-in keeps no body rotations; world-frame forces are enough for the API surface)
+        cf = self.sim_t["net_contact_force"].view(self.N, self.nb, 3)
+        out.view(self.N, -1, 6)[:, :, 0:3] = cf[:, sensor_body.long()]
+        out.view(self.N, -1, 6)[:, :, 3:6] = 0
+
     def set_state_indexed(self, ids32, count):
         assert ids32.dtype == torch.int32 and 0 <= count <= ids32.numel()
 

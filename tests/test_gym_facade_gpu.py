@@ -115,11 +115,20 @@ def test_humanoid_through_the_gym_api():
     gym.add_ground(sim, pp)
     asset = gym.load_asset(sim, "../../assets", "mjcf/nv_humanoid.xml", gymapi.AssetOptions())
     assert gym.get_asset_rigid_body_count(asset) == 16 and gym.get_asset_dof_count(asset) == 21
+    # force sensors at the feet and the actuator list, as tasks/humanoid.py:159-168 sets them up
+    feet_idx = [gym.find_asset_rigid_body_index(asset, "right_foot"), gym.find_asset_rigid_body_index(asset, "left_foot")]
+    for b in feet_idx:
+        gym.create_asset_force_sensor(asset, b, gymapi.Transform())
+    assert len(gym.get_asset_actuator_properties(asset)) == 21
     N = 64
     for i in range(N):
         env = gym.create_env(sim, gymapi.Vec3(0, 0, 0), gymapi.Vec3(0, 0, 0), 8)
-        gym.create_actor(env, asset, gymapi.Transform(gymapi.Vec3(2.0 * i, 0.0, 1.34), gymapi.Quat(0, 0, 0, 1)), "humanoid", i, 0, 0)
+        h = gym.create_actor(env, asset, gymapi.Transform(gymapi.Vec3(2.0 * i, 0.0, 1.34), gymapi.Quat(0, 0, 0, 1)), "humanoid", i, 0, 0)
+        gym.enable_actor_dof_force_sensors(env, h)
     assert gym.prepare_sim(sim)
+    sensors = gymtorch.wrap_tensor(gym.acquire_force_sensor_tensor(sim))
+    dof_force = gymtorch.wrap_tensor(gym.acquire_dof_force_tensor(sim))
+    assert sensors.shape == (N * 2, 6) and dof_force.shape == (N * 21,)
     root = gymtorch.wrap_tensor(gym.acquire_actor_root_state_tensor(sim))
     dof = gymtorch.wrap_tensor(gym.acquire_dof_state_tensor(sim))
     contact = gymtorch.wrap_tensor(gym.acquire_net_contact_force_tensor(sim))
@@ -134,4 +143,22 @@ def test_humanoid_through_the_gym_api():
     cf = contact.view(N, 16, 3)
     assert (cf[:, feet, 2].sum(1) > 50.0).all()  # standing on the soles
     assert (root[:, 2] > 1.0).all() and (root[:, 2] < 1.4).all()
+    # refresh_dof_force_tensor / refresh_force_sensor_tensor (tasks/humanoid.py:243-245) against their definitions
+    tau = torch.randn(N * 21, device=root.device)
+    gym.set_dof_actuation_force_tensor(sim, gymtorch.unwrap_tensor(tau))
+    assert gym.refresh_dof_force_tensor(sim) and gym.refresh_force_sensor_tensor(sim) and gym.refresh_rigid_body_state_tensor(sim)
+    torch.cuda.synchronize()
+    t = sim.asset.tables
+    damp = sim.core.sim_t["dof_damping"].reshape(-1)
+    stiff = torch.tensor(t.dof_stiffness, dtype=torch.float32, device=root.device).repeat(N)
+    assert torch.allclose(dof_force, tau - damp * dof[:, 1] - stiff * dof[:, 0], rtol=1e-5, atol=1e-5)
+    rb = gymtorch.wrap_tensor(gym.acquire_rigid_body_state_tensor(sim)).view(N, 16, 13)
+    q = rb[:, feet_idx, 3:7]                                          # xyzw of the two feet
+    F = cf[:, feet_idx, :]
+    qv, qw = q[..., :3], q[..., 3:4]                                  # rotate F by the inverse of q
+    tq = 2.0 * torch.cross(-qv, F, dim=-1)
+    want = F + qw * tq + torch.cross(-qv, tq, dim=-1)
+    got = sensors.view(N, 2, 6)
+    assert torch.allclose(got[..., :3], want, rtol=1e-4, atol=1e-3) and float(got[..., 3:].abs().max()) == 0.0
+    assert float(got[..., 2].min()) > 10.0                            # the soles are flat on the ground: local z carries the weight
     gym.destroy_sim(sim)

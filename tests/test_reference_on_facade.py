@@ -139,3 +139,39 @@ def test_unmodified_reference_task_runs_on_the_facade(reference_task_class):
     still = [i for i in range(N) if int(reset[i]) == 0]
     assert still and all(torch.equal(d1[i], d0[i]) for i in still)
     assert int(env.progress_buf[1]) == 0 and float(env.root_states[1, 2]) == pytest.approx(0.93)
+
+
+def test_unmodified_reference_humanoid_task_runs_on_the_facade(reference_task_class):
+    """BASELINE configs[2] (generality): the stock IsaacGymEnvs Humanoid task (tasks/humanoid.py:41), unmodified, on the
+    facade: nv_humanoid.xml through the MJCF importer, get_asset_actuator_properties, create_asset_force_sensor,
+    acquire_force_sensor_tensor / acquire_dof_force_tensor and their refreshes (humanoid.py:80-86,159-168,196,243-245).
+    (In this fork VecTask.step never calls gym.simulate for stock tasks -- VT:313-319 is commented out, T:1-6 -- so the
+    test steps the simulator itself between two task steps.)"""
+    H = _load("isaacgymenvs.tasks.humanoid", os.path.join(ENVS, "tasks", "humanoid.py"))
+    cfg = yaml.safe_load(open(os.path.join(ENVS, "cfg", "task", "Humanoid.yaml")))
+    N = 3
+    cfg["env"]["numEnvs"] = N
+    cfg["physics_engine"] = "physx"
+    cfg["sim"]["use_gpu_pipeline"] = False
+    cfg["sim"]["physx"]["use_gpu"] = False
+    cfg["sim"]["physx"]["num_threads"] = 4
+    cfg["sim"]["physx"]["num_subscenes"] = 0
+    cfg["sim"]["physx"]["max_gpu_contact_pairs"] = 1024
+    cfg["task"]["randomize"] = False
+    cfg["rl_device"] = "cpu"
+    for k, v in list(cfg["sim"].items()):  # the yaml carries hydra interpolations for values config.yaml supplies
+        if isinstance(v, str) and v.startswith("${"):
+            cfg["sim"][k] = {"use_gpu_pipeline": False}.get(k, 0)
+    cfg["sim"]["dt"], cfg["sim"]["substeps"] = 0.0166, 2
+    env = H.Humanoid(cfg, "cpu", -1, True)
+    core = env.sim.core
+    assert env.num_dof == 21 and env.num_bodies == 16 and env.num_obs == 108 and env.num_acts == 21
+    assert env.vec_sensor_tensor.shape == (N, 12) and env.dof_force_tensor.shape == (N, 21)
+    assert len(env.motor_efforts) == 21 and float(env.max_motor_effort) > 0
+    obs, rew, reset, extras = env.step(torch.zeros(N, 21))          # stock task step: no simulate in this fork
+    assert obs["obs"].shape == (N, 108) and torch.isfinite(obs["obs"]).all()
+    for _ in range(3):                                               # ... so drive the simulator, then step the task again
+        env.gym.simulate(env.sim)
+    obs, rew, reset, extras = env.step(torch.zeros(N, 21))
+    assert core.simulate_calls == 3 and torch.isfinite(obs["obs"]).all() and torch.isfinite(rew).all()
+    assert torch.isfinite(env.vec_sensor_tensor).all() and torch.isfinite(env.dof_force_tensor).all()
