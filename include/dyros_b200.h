@@ -64,6 +64,20 @@ typedef struct {
   const double* cyl_size;     /* [nc*2] radius, half height */
   const int32_t* sched;       /* [sched_slots*DYROS_LANES] role programs: column r = links of role r, ascending, -1 padded
                                  (model/tables.py::role_programs) */
+  /* self-collision tables (model/selfcollision.py; all NULL / 0 = no self-collision): exact shapes + sample spheres per
+   * link, bounding spheres of the links, candidate link pairs. Reference: create_actor(..., group i, filter 0), T:354. */
+  int32_t sc_num_shapes, sc_num_samples, sc_num_pairs;
+  const int32_t* sc_shape_kind;    /* [ns] 0 = box, 1 = cylinder */
+  const int32_t* sc_shape_link;    /* [ns] shapes are grouped by link */
+  const int32_t* sc_shape_body;    /* [ns] */
+  const int32_t* sc_shape_sample0; /* [ns+1] sample range of each shape */
+  const double* sc_shape_center;   /* [ns*3] link frame */
+  const double* sc_shape_rot;      /* [ns*9] row-major, columns = shape axes in the link frame (cylinder: column 2 = axis) */
+  const double* sc_shape_size;     /* [ns*3] box half extents | cylinder radius, half height, 0 */
+  const double* sc_sample;         /* [nsamp*4] link-frame position, radius */
+  const int32_t* sc_link_shape0;   /* [nl+1] */
+  const double* sc_link_sphere;    /* [nl*4] link-frame centre, radius */
+  const int32_t* sc_pairs;         /* [np*2] candidate link pairs i < j */
 } DyrosModelDesc;
 
 /* gymapi.SimParams / PhysXParams subset that reaches the solver (VT:423-471, DyrosDynamicWalk.yaml:37-56)
@@ -103,6 +117,11 @@ typedef struct {
   float* body_mass_scale;    /* (N,nb) per-env rigid_body_properties.mass scaling (setup-only DR) */
   float* contact_friction;   /* (N) per-env friction coefficient of the ground contacts, replaces DyrosSimDesc.friction
                                 (DR of rigid_shape_properties.friction, DyrosDynamicWalk.yaml:89-96); may be NULL */
+  float* link_pose;          /* (N,nl,12) world rotation (row-major) and origin of every link at the start of the LAST
+                                sub-step of a simulate call: what the contact forces of that sub-step are computed from;
+                                written by the physics kernels for the self-collision pass; may be NULL (no self-collision) */
+  float* self_contact_force; /* (N*nb,3) net self-contact force per body of the last sub-step (also added into
+                                net_contact_force); may be NULL */
 } DyrosSimBuffers;
 
 /* Per-env task state (names = the reference attributes, T:87-195; internal integers are int32). */
@@ -215,6 +234,11 @@ int dyros_sim_destroy(DyrosSim* sim);
 /* gym.simulate: one time step dt (in `substeps` sub-steps) from dof_actuation_force (+ pending rb_force/torque
  * when apply_wrench != 0, consumed by the first sub-step, DOCT:322-335). */
 int dyros_simulate(DyrosSim* sim, int apply_wrench, void* stream);
+/* Self-collision pass (actor created with collision filter 0, T:354): detects contacts between the shapes of
+ * non-adjacent links from link_pose, writes self_contact_force and adds it into net_contact_force, so that
+ * collision_true (T:590, T:937) sees them. dyros_simulate and dyros_task_step run it themselves when the model carries
+ * self-collision tables and both buffers are given; exported for callers that stage the step. */
+int dyros_self_collision(DyrosSim* sim, void* stream);
 /* gym.refresh_rigid_body_state_tensor: forward kinematics into rigid_body_state (DOCT:193-207). */
 int dyros_refresh_rigid_body_state(DyrosSim* sim, void* stream);
 /* gym.refresh_dof_force_tensor (tasks/humanoid.py:85,245; DOCT "DOF forces"): (N*nd) generalised force at every DOF =

@@ -75,6 +75,7 @@ class CoreConfig:
     with_rigid_body_state: bool = False  # DyrosDynamicWalk never reads it (T:76,85)
     with_rb_force_tensors: bool = False  # generic apply_rigid_body_force_tensors buffers
     physics_program: str = "roles"       # "roles": one lane per env, warp per role (default); "lanes": 8 lanes per env
+    self_collision: bool = True          # create_actor(..., filter 0), T:354: the actor's shapes collide with each other
 
 
 def stable_penalty(dt_substep: float, m_ref: float = 0.3):
@@ -96,6 +97,23 @@ def env_origins(n: int, spacing: float) -> np.ndarray:
     o[:, 0] = (spacing * xx.flatten()[:n]).astype(np.float32)
     o[:, 1] = (spacing * yy.flatten()[:n]).astype(np.float32)
     return o
+
+
+_SC_CACHE: dict = {}
+
+
+def self_collision_tables(t: ModelTables):
+    """model/selfcollision.py tables of an articulation, built once per model (rest poses: zero and, for TOCABI, the
+    task's initial pose T:95-100)."""
+    from .model import selfcollision
+    key = (tuple(t.body_names), t.pt_pos.tobytes(), t.cyl_center.tobytes())
+    if key not in _SC_CACHE:
+        rest = [np.array(INIT_DOF_POS)] if t.num_dofs == ND else []
+        try:
+            _SC_CACHE[key] = selfcollision.build(t, rest)
+        except ValueError:  # primitives this module does not describe (capsules / spheres of the stock Humanoid)
+            _SC_CACHE[key] = None
+    return _SC_CACHE[key]
 
 
 def make_model_desc(t: ModelTables, cfg: "CoreConfig"):
@@ -125,6 +143,16 @@ def make_model_desc(t: ModelTables, cfg: "CoreConfig"):
                           ("cyl_center", f64(t.cyl_center), C.c_double), ("cyl_axis", f64(t.cyl_axis), C.c_double),
                           ("cyl_size", f64(t.cyl_size), C.c_double), ("sched", i32(prog), C.c_int32)]:
         setattr(md, name, _np_ptr(arr, ct))
+    sc = self_collision_tables(t) if cfg.self_collision else None
+    if sc is not None and len(sc.pairs):
+        md.sc_num_shapes, md.sc_num_samples, md.sc_num_pairs = sc.num_shapes, len(sc.sample), len(sc.pairs)
+        for name, arr, ct in [("sc_shape_kind", i32(sc.shape_kind), C.c_int32), ("sc_shape_link", i32(sc.shape_link), C.c_int32),
+                              ("sc_shape_body", i32(sc.shape_body), C.c_int32), ("sc_shape_sample0", i32(sc.shape_sample0), C.c_int32),
+                              ("sc_shape_center", f64(sc.shape_center), C.c_double), ("sc_shape_rot", f64(sc.shape_rot), C.c_double),
+                              ("sc_shape_size", f64(sc.shape_size), C.c_double), ("sc_sample", f64(sc.sample), C.c_double),
+                              ("sc_link_shape0", i32(sc.link_shape0), C.c_int32), ("sc_link_sphere", f64(sc.link_sphere), C.c_double),
+                              ("sc_pairs", i32(sc.pairs), C.c_int32)]:
+            setattr(md, name, _np_ptr(arr, ct))
     return md, keep
 
 
@@ -205,6 +233,10 @@ class DyrosCore:
         if cfg.with_rb_force_tensors:
             s["rb_force"] = z(N * nb, 3)
             s["rb_torque"] = z(N * nb, 3)
+        sc = self_collision_tables(self.tables) if cfg.self_collision else None
+        if sc is not None and len(sc.pairs):
+            s["link_pose"] = z(N, self.tables.num_links, 12)
+            s["self_contact_force"] = z(N * nb, 3)
         self.sim_t = s
         s["root_states"][:, 6] = 1.0
         if not self.with_task:
@@ -384,6 +416,9 @@ class DyrosCore:
         out = (C.c_int32 * 4)()
         native.check(self.lib.dyros_sim_launch_info(self.sim_handle, C.byref(out)), "dyros_sim_launch_info")
         return {"envs_per_cta": out[0], "ctas": out[1], "threads_per_cta": out[2], "smem_bytes": out[3]}
+
+    def self_collision(self):
+        native.check(self.lib.dyros_self_collision(self.sim_handle, self._stream), "dyros_self_collision")
 
     def refresh_dof_force(self, out: torch.Tensor):
         native.check(self.lib.dyros_refresh_dof_force(self.sim_handle, C.c_void_p(out.data_ptr()), self._stream), "dyros_refresh_dof_force")

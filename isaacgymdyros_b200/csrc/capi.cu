@@ -235,7 +235,16 @@ int dyros_simulate(DyrosSim* sim, int apply_wrench, void* stream) {
     set_error("dyros_simulate: apply_wrench set but rb_force / rb_torque buffers are NULL");
     return 1;
   }
-  return launch_simulate(s, apply_wrench, nullptr, (cudaStream_t)stream);
+  if (launch_simulate(s, apply_wrench, nullptr, (cudaStream_t)stream)) return 1;
+  return launch_self_collision(s, (cudaStream_t)stream);
+}
+int dyros_self_collision(DyrosSim* sim, void* stream) {
+  SIM_OR_FAIL("dyros_self_collision");
+  if (!has_self_collision(s)) {
+    set_error("dyros_self_collision: the model has no self-collision tables, or link_pose / self_contact_force is NULL");
+    return 1;
+  }
+  return launch_self_collision(s, (cudaStream_t)stream);
 }
 int dyros_refresh_rigid_body_state(DyrosSim* sim, void* stream) {
   SIM_OR_FAIL("dyros_refresh_rigid_body_state");
@@ -364,7 +373,8 @@ int dyros_task_prologue(DyrosTask* task, const float* actions, void* stream) {
 }
 int dyros_task_physics(DyrosTask* task, void* stream) {
   TASK_OR_FAIL("dyros_task_physics");
-  return launch_task_physics(t, (cudaStream_t)stream);
+  if (launch_task_physics(t, (cudaStream_t)stream)) return 1;
+  return launch_self_collision(t->sim, (cudaStream_t)stream);
 }
 int dyros_task_physics_trace(DyrosTask* task, int64_t* trace, void* stream) {
   TASK_OR_FAIL("dyros_task_physics_trace");
@@ -372,7 +382,8 @@ int dyros_task_physics_trace(DyrosTask* task, int64_t* trace, void* stream) {
     set_error("dyros_task_physics_trace: trace buffer is NULL");
     return 1;
   }
-  return launch_task_physics(t, (cudaStream_t)stream, reinterpret_cast<long long*>(trace));
+  if (launch_task_physics(t, (cudaStream_t)stream, reinterpret_cast<long long*>(trace))) return 1;
+  return launch_self_collision(t->sim, (cudaStream_t)stream);
 }
 int dyros_task_prologue_physics(DyrosTask* task, const float* actions, int64_t* trace, void* stream) {
   TASK_OR_FAIL("dyros_task_prologue_physics");
@@ -380,7 +391,8 @@ int dyros_task_prologue_physics(DyrosTask* task, const float* actions, int64_t* 
     set_error("dyros_task_prologue_physics: actions is NULL");
     return 1;
   }
-  return launch_task_physics(t, (cudaStream_t)stream, reinterpret_cast<long long*>(trace), false, actions);
+  if (launch_task_physics(t, (cudaStream_t)stream, reinterpret_cast<long long*>(trace), false, actions)) return 1;
+  return launch_self_collision(t->sim, (cudaStream_t)stream);
 }
 int dyros_task_substep_torque(DyrosTask* task, void* stream) {
   TASK_OR_FAIL("dyros_task_substep_torque");
@@ -441,6 +453,7 @@ int dyros_task_step(DyrosTask* task, const float* actions, void* stream) {
   // the kernels use programmatic dependent launch: their CTAs get resident and run their preamble while the previous
   // kernel drains (common.cuh); the data dependency is enforced by griddepcontrol.wait inside each kernel
   if (launch_task_physics(t, st, nullptr, true, actions)) return 1;  // prologue folded into the physics launch
+  if (launch_self_collision(t->sim, st, true)) return 1;             // (no launch unless the model carries the tables)
   // ... and the cross-env pass (gate of T:489, Philox epoch) into the post-physics launch: its last CTA does it. The
   // compacted id list of T:554 is not needed by the fused step (every env resets itself): dyros_task_compact_resets
   // produces it on demand.
@@ -452,7 +465,7 @@ int dyros_task_post_step(DyrosTask* task, void* stream) {
 }
 int dyros_task_step_launches(DyrosTask* task) {
   TASK_OR_FAIL("dyros_task_step_launches");
-  return 2;  // prologue + fused physics, fused post-physics (+ cross-env pass in its last CTA)
+  return has_self_collision(t->sim) ? 3 : 2;  // prologue + fused physics, [self-collision], fused post-physics (+ cross-env pass)
 }
 int dyros_task_set_obs_buf(DyrosTask* task, float* obs_buf) {
   TASK_OR_FAIL("dyros_task_set_obs_buf");

@@ -93,6 +93,7 @@ __device__ __forceinline__ EnvIO env_io(const DevModel& m, const DyrosSimBuffers
   io.push = nullptr;
   io.rb_force = nullptr;
   io.rb_torque = nullptr;
+  io.link_pose = nullptr;
   io.live = live;
   return io;
 }
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(kPhysThreads) k_simulate(DevModel m, SimParams
     slab_stage_dofpar(m, b, tab, envs, es, e0, nenv, true, threadIdx.x, kPhysThreads);
     cp_async_wait_all();
     __syncthreads();
+    io.link_pose = (s + 1 == p.substeps && b.link_pose) ? b.link_pose + (size_t)c.e * m.nl * 12 : nullptr;
     env_substep_role(io, c.sm, c.flags, s, c.hot, m, p, c.role, sync);
     __syncthreads();
     // (applied wrenches act over the whole simulate() call, i.e. all of its sub-steps: gym_py.html apply_rigid_body_force_tensors)
@@ -366,6 +368,7 @@ __global__ void __launch_bounds__(kStepThreads) k_step_physics(DevModel m, SimPa
         }
       } else {
         io.push = s == 0 ? k.b.push_force : nullptr;  // every sub-step of the first simulate of the policy step (T:502 vs T:504)
+        io.link_pose = (s + 1 == k.p.skipframe && ss + 1 == p.substeps && k.s.link_pose) ? k.s.link_pose + (size_t)c.e * m.nl * 12 : nullptr;
         sync.mark(13);
         env_substep_role(io, c.sm, c.flags, epoch, c.hot, m, p, role, sync, true);
       }
@@ -524,6 +527,242 @@ __global__ void __launch_bounds__(64) k_rigid_body_state(DevModel m, SimParams p
     o[0] = pos.x; o[1] = pos.y; o[2] = pos.z; o[3] = qx; o[4] = qy; o[5] = qz; o[6] = qw;
     o[7] = lin.x; o[8] = lin.y; o[9] = lin.z; o[10] = ang.x; o[11] = ang.y; o[12] = ang.z;
   }
+}
+
+// ---------------------------------------------------------------- self-collision (model/selfcollision.py, T:354 filter 0)
+// One warp per env, every level of the hierarchy spread over the lanes and compacted with ballots:
+//   0. the env's link poses -> shared memory (coalesced); world centres of the link and shape bounding spheres;
+//   1. candidate link pairs, one per lane and round: two link spheres overlap -> list of link pairs (standing: ~40 of 497);
+//   2. their shape pairs, 8 lanes per link pair: two shape spheres overlap -> hit list (standing: ~20 of ~250);
+//   2b. hit list, one per lane: face-axis separating-axis test of the two oriented bounding boxes (a box is its own, a
+//      cylinder's is r x r x h) -> what stays is really close (standing: a few);
+//   3. hit list, half a warp per shape pair: lane = one sample sphere of one shape against the exact box / cylinder of
+//      the other (both ways); a penetrating sample pushes the two bodies apart along the gradient of the signed
+//      distance with the penalty stiffness of the ground contacts, accumulated per body in shared memory.
+// Every cull is conservative, so the result is that of the plain double loop restated in oracle/selfcollision_oracle.py
+// (up to the order of the sums); lists that overflow fall back to the unculled work, never to dropped contacts.
+constexpr int kScWarps = 4;
+constexpr int kScPairs = 128;  // link pairs whose spheres overlap
+constexpr int kScHits = 64;    // shape pairs whose spheres overlap
+__device__ __forceinline__ float sc_sdf(int kind, V3 size, V3 x, V3& g) {
+  if (kind == 0) {  // box: half extents
+    const V3 q = v3(fabsf(x.x) - size.x, fabsf(x.y) - size.y, fabsf(x.z) - size.z);
+    const V3 o = v3(fmaxf(q.x, 0.f), fmaxf(q.y, 0.f), fmaxf(q.z, 0.f));
+    const float n = sqrtf(dot(o, o));
+    const V3 sg = v3(x.x < 0 ? -1.f : 1.f, x.y < 0 ? -1.f : 1.f, x.z < 0 ? -1.f : 1.f);
+    if (n > 0.f) {
+      g = v3(o.x / n * sg.x, o.y / n * sg.y, o.z / n * sg.z);
+      return n;
+    }
+    // inside: the face that is nearest (first of the largest components, as numpy's argmax)
+    if (q.x >= q.y && q.x >= q.z) { g = v3(sg.x, 0, 0); return q.x; }
+    if (q.y >= q.z) { g = v3(0, sg.y, 0); return q.y; }
+    g = v3(0, 0, sg.z);
+    return q.z;
+  }
+  const float r = size.x, h = size.y;  // cylinder about its z axis
+  const float rho = sqrtf(x.x * x.x + x.y * x.y);
+  const float inv = 1.f / fmaxf(rho, 1e-30f);
+  const V3 er = v3(x.x * inv, x.y * inv, 0.f), ez = v3(0.f, 0.f, x.z < 0 ? -1.f : 1.f);
+  const float qr = rho - r, qz = fabsf(x.z) - h;
+  const float o0 = fmaxf(qr, 0.f), o1 = fmaxf(qz, 0.f);
+  const float n = sqrtf(o0 * o0 + o1 * o1);
+  if (n > 0.f) {
+    g = (o0 / n) * er + (o1 / n) * ez;
+    return n;
+  }
+  if (qr > qz) { g = er; return qr; }
+  g = ez;
+  return qz;
+}
+struct ScWarp {
+  float pose[DYROS_MAX_LINKS * 12];
+  float4 link_c[DYROS_MAX_LINKS];
+  float4 shape_c[SC_MAX_SHAPES];
+  float force[DYROS_MAX_BODIES * 3];
+  int pairs[kScPairs];
+  int hits[kScHits];
+  int any_hit;
+};
+// sample sphere k (of shape sa) against shape sb
+__device__ __forceinline__ void sc_item(const DevModel& m, const SimParams& p, ScWarp& W, int sa, int sb, int k) {
+  const int la = m.sc_shape_link[sa], lb = m.sc_shape_link[sb];
+  const float4 smp = *reinterpret_cast<const float4*>(m.sc_sample + 4 * k);
+  const V3 c = mul(ld_m3_f(W.pose + 12 * la), v3(smp.x, smp.y, smp.z)) + ld3_f(W.pose + 12 * la + 9);
+  const float rho = smp.w;
+  const float4 sc = W.shape_c[sb];
+  const V3 dc = c - v3(sc.x, sc.y, sc.z);
+  const float reach = rho + sc.w;
+  if (dot(dc, dc) >= reach * reach) return;
+  const M3 Rb = ld_m3_f(W.pose + 12 * lb);
+  const V3 cl = mulT(Rb, c - ld3_f(W.pose + 12 * lb + 9));  // in link lb's frame
+  const float* S = m.sc_shape_f + 16 * sb;
+  const M3 Rs = ld_m3_f(S + 3);
+  V3 g;
+  const float d = sc_sdf(m.sc_shape_kind[sb], ld3_f(S + 12), mulT(Rs, cl - ld3_f(S)), g);
+  const float depth = rho - d;
+  if (depth > 0.f) {
+    const V3 f = fminf(p.pen_k * depth, p.pen_fmax) * mul(Rb, mul(Rs, g));  // pushes the sample's body out
+    const int ba = m.sc_shape_body[sa], bb = m.sc_shape_body[sb];
+    atomicAdd(&W.force[3 * ba], f.x); atomicAdd(&W.force[3 * ba + 1], f.y); atomicAdd(&W.force[3 * ba + 2], f.z);
+    atomicAdd(&W.force[3 * bb], -f.x); atomicAdd(&W.force[3 * bb + 1], -f.y); atomicAdd(&W.force[3 * bb + 2], -f.z);
+    W.any_hit = 1;
+  }
+}
+__device__ __forceinline__ bool sc_spheres_overlap(float4 a, float4 b) {
+  const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, rs = a.w + b.w;
+  return dx * dx + dy * dy + dz * dz < rs * rs;
+}
+// World frame (columns = axes) and half extents of shape s's oriented bounding box.
+__device__ __forceinline__ void sc_obb(const DevModel& m, const ScWarp& W, int s, M3& R, V3& half) {
+  const float* S = m.sc_shape_f + 16 * s;
+  R = mul(ld_m3_f(W.pose + 12 * m.sc_shape_link[s]), ld_m3_f(S + 3));
+  half = m.sc_shape_kind[s] == 0 ? ld3_f(S + 12) : v3(S[12], S[12], S[13]);
+}
+// true when one of the 6 face normals separates the two boxes (with a margin for rounding): certainly no contact
+__device__ __forceinline__ bool sc_obb_separated(const DevModel& m, const ScWarp& W, int sa, int sb) {
+  M3 A, B;
+  V3 ha, hb;
+  sc_obb(m, W, sa, A, ha);
+  sc_obb(m, W, sb, B, hb);
+  const float4 ca = W.shape_c[sa], cb = W.shape_c[sb];
+  const V3 t = mulT(A, v3(cb.x - ca.x, cb.y - ca.y, cb.z - ca.z));  // in A's frame
+  const M3 C = mulAtB(A, B);                                        // B's axes in A's frame
+  const float eps = 1e-5f;
+  float c[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) c[i] = fabsf(C.a[i]) + 1e-6f;
+  const float ta[3] = {t.x, t.y, t.z}, hA[3] = {ha.x, ha.y, ha.z}, hB[3] = {hb.x, hb.y, hb.z};
+  bool sep = false;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) sep |= fabsf(ta[i]) > hA[i] + c[3 * i] * hB[0] + c[3 * i + 1] * hB[1] + c[3 * i + 2] * hB[2] + eps;
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    sep |= fabsf(ta[0] * C.a[j] + ta[1] * C.a[3 + j] + ta[2] * C.a[6 + j]) > hB[j] + c[j] * hA[0] + c[3 + j] * hA[1] + c[6 + j] * hA[2] + eps;
+  return sep;
+}
+__global__ void __launch_bounds__(kScWarps * 32) k_self_collision(DevModel m, SimParams p, DyrosSimBuffers b) {
+  __shared__ ScWarp sw[kScWarps];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const int e = blockIdx.x * kScWarps + w;
+  if (e >= p.N) return;
+  ScWarp& W = sw[w];
+  const float* pose = b.link_pose + (size_t)e * m.nl * 12;
+  for (int i = lane; i < m.nl * 12; i += 32) W.pose[i] = pose[i];
+  for (int i = lane; i < m.nb * 3; i += 32) W.force[i] = 0.f;
+  if (lane == 0) W.any_hit = 0;
+  __syncwarp();
+  for (int l = lane; l < m.nl; l += 32) {
+    const V3 c = mul(ld_m3_f(W.pose + 12 * l), ld3_f(m.sc_link_sphere + 4 * l)) + ld3_f(W.pose + 12 * l + 9);
+    W.link_c[l] = make_float4(c.x, c.y, c.z, m.sc_link_sphere[4 * l + 3]);
+  }
+  for (int s = lane; s < m.sc_ns; s += 32) {
+    const int l = m.sc_shape_link[s];
+    const V3 c = mul(ld_m3_f(W.pose + 12 * l), ld3_f(m.sc_shape_f + 16 * s)) + ld3_f(W.pose + 12 * l + 9);
+    W.shape_c[s] = make_float4(c.x, c.y, c.z, m.sc_shape_f[16 * s + 15]);
+  }
+  __syncwarp();
+  int n1 = 0;  // 1. link spheres
+  const int2* link_pairs = reinterpret_cast<const int2*>(m.sc_pairs);
+#pragma unroll 2
+  for (int base = 0; base < m.sc_np; base += 32) {
+    const int pi = base + lane;
+    bool hit = false;
+    if (pi < m.sc_np) {
+      const int2 lp = link_pairs[pi];
+      hit = sc_spheres_overlap(W.link_c[lp.x], W.link_c[lp.y]);
+    }
+    const unsigned bal = __ballot_sync(kFull, hit);
+    const int slot = n1 + __popc(bal & lt);
+    if (hit && slot < p.sc_pairs_cap) W.pairs[slot] = pi;
+    n1 += __popc(bal);
+  }
+  __syncwarp();
+  int n2 = 0;  // 2. shape spheres
+  auto shape_pair = [&](int q, bool valid) {
+    int sp = 0;
+    bool hit = false;
+    if (valid) {
+      sp = m.sc_shape_pairs[q];
+      hit = sc_spheres_overlap(W.shape_c[sp & 0xffff], W.shape_c[sp >> 16]);
+    }
+    const unsigned bal = __ballot_sync(kFull, hit);
+    const int slot = n2 + __popc(bal & lt);
+    n2 += __popc(bal);
+    if (!hit) return;
+    if (slot < p.sc_hits_cap) {
+      W.hits[slot] = sp;
+      return;
+    }
+    const int sa = sp & 0xffff, sb = sp >> 16;  // (list full: the lane runs the pair's narrow phase itself)
+#pragma unroll 1
+    for (int k = m.sc_shape_sample0[sa]; k < m.sc_shape_sample0[sa + 1]; ++k) sc_item(m, p, W, sa, sb, k);
+#pragma unroll 1
+    for (int k = m.sc_shape_sample0[sb]; k < m.sc_shape_sample0[sb + 1]; ++k) sc_item(m, p, W, sb, sa, k);
+  };
+  if (n1 <= p.sc_pairs_cap) {
+    for (int h0 = 0; h0 < n1; h0 += 4) {  // 8 lanes per link pair
+      const int h = h0 + (lane >> 3);
+      int q0 = 0, n = 0;
+      if (h < n1) {
+        const int pi = W.pairs[h];
+        q0 = m.sc_pair_sq0[pi];
+        n = m.sc_pair_sq0[pi + 1] - q0;
+      }
+      for (int t = lane & 7; __any_sync(kFull, t < n); t += 8) shape_pair(q0 + t, t < n);
+    }
+  } else {
+    const int nq = m.sc_pair_sq0[m.sc_np];
+    for (int base = 0; base < nq; base += 32) shape_pair(base + lane, base + lane < nq);
+  }
+  __syncwarp();
+  int nh = 0;  // 2b. oriented boxes; the survivors are compacted in place
+  n2 = min(n2, p.sc_hits_cap);
+  for (int base = 0; base < n2; base += 32) {
+    const int h = base + lane;
+    int sp = 0;
+    bool keep = false;
+    if (h < n2) {
+      sp = W.hits[h];
+      keep = !sc_obb_separated(m, W, sp & 0xffff, sp >> 16);
+    }
+    const unsigned bal = __ballot_sync(kFull, keep);  // (also orders this round's reads before its writes)
+    if (keep) W.hits[nh + __popc(bal & lt)] = sp;
+    nh += __popc(bal);
+  }
+  __syncwarp();
+  for (int h = lane >> 4; h < nh; h += 2) {  // 3. samples against exact shapes, 16 lanes per shape pair
+    const int sp = W.hits[h], sa = sp & 0xffff, sb = sp >> 16;
+    const int ka = m.sc_shape_sample0[sa], na = m.sc_shape_sample0[sa + 1] - ka;
+    const int kb = m.sc_shape_sample0[sb], nb = m.sc_shape_sample0[sb + 1] - kb;
+    const int t = lane & 15;
+    if (t < na) sc_item(m, p, W, sa, sb, ka + t);
+    else if (t - na < nb) sc_item(m, p, W, sb, sa, kb + t - na);
+  }
+  __syncwarp();
+  const bool any_hit = W.any_hit != 0;
+  float* out = b.self_contact_force + (size_t)e * m.nb * 3;
+  float* net = b.net_contact_force + (size_t)e * m.nb * 3;
+  for (int i = lane; i < m.nb * 3; i += 32) {
+    const float f = any_hit ? W.force[i] : 0.f;
+    out[i] = f;
+    if (any_hit) net[i] += f;
+  }
+}
+int launch_self_collision(Sim* sim, cudaStream_t s, bool pdl) {
+  if (!has_self_collision(sim)) return 0;
+  if (sim->p.sc_pairs_cap == 0) {
+    // DYROS_SC_TEST_CAPS="pairs,hits": shrinks the two lists so that tests reach the overflow paths on ordinary poses
+    int a = kScPairs, h = kScHits;
+    if (const char* v = getenv("DYROS_SC_TEST_CAPS")) sscanf(v, "%d,%d", &a, &h);
+    sim->p.sc_pairs_cap = std::max(1, std::min(a, kScPairs));
+    sim->p.sc_hits_cap = std::max(1, std::min(h, kScHits));
+  }
+  DY_CUDA(launch_kernel(k_self_collision, dim3((sim->p.N + kScWarps - 1) / kScWarps), dim3(kScWarps * 32), 0, s, pdl, sim->m, sim->p, sim->b));
+  return 0;
 }
 
 // gym.refresh_dof_force_tensor (tensors.rst.txt "DOF force tensor", used by tasks/humanoid.py:85,245): the generalised force

@@ -97,9 +97,16 @@ struct EnvIO {
   float* contact;          // nb*3 net contact force of this sub-step (zeroed before the sub-step)
   const float* rb_force;   // nb*3 or NULL
   const float* rb_torque;  // nb*3 or NULL
+  float* link_pose;        // nl*12 or NULL: world pose of every link as pass 1 finds it (for the self-collision pass)
   bool push;               // X_PUSH holds a force for the base body
   bool live;               // false: padding lanes, no global writes
 };
+HDL void export_pose(const EnvIO& io, int link, const M3& Rw, V3 pw) {
+  if (!io.link_pose || !io.live) return;
+  float* o = io.link_pose + 12 * link;
+  for (int c = 0; c < 9; ++c) st(o + c, Rw.a[c]);
+  st(o + 9, pw.x); st(o + 10, pw.y); st(o + 11, pw.z);
+}
 
 HDL V3 ldv3(const float* p) { return V3{ld(p), ld(p + 1), ld(p + 2)}; }
 HDL void stv3(float* p, V3 a) { st(p, a.x); st(p + 1, a.y); st(p + 2, a.z); }
@@ -270,6 +277,7 @@ HDL void env_substep_lanes(const EnvIO& io, float* sm, int* qflags, const int* i
     st4(A + A_W, v0.w.x, v0.w.y, v0.w.z, real(0));
     st4(A + A_V, v0.v.x, v0.v.y, v0.v.z, real(0));
     st_pose(A + A_POSE, R0, pw);
+    export_pose(io, 0, R0, pw);
     sync.signal(fl + 0, base + ST_PASS1);
     prev = 0;
     v_prev = v0;
@@ -303,6 +311,7 @@ HDL void env_substep_lanes(const EnvIO& io, float* sm, int* qflags, const int* i
     st4(A + A_W, v_prev.w.x, v_prev.w.y, v_prev.w.z, real(0));
     st4(A + A_V, v_prev.v.x, v_prev.v.y, v_prev.v.z, real(0));
     st_pose(A + A_POSE, Rw_prev, pw_prev);
+    export_pose(io, i, Rw_prev, pw_prev);
     // published only where another role reads it: by foreign children (pose, velocity), or by the foreign parent,
     // which must not overwrite its pose before this link has used it
     if (flg & (RF_PUBLISH | RF_PARENT_FOREIGN)) sync.signal(fl + i, base + ST_PASS1);

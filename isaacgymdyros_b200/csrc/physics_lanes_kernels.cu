@@ -111,6 +111,7 @@ __device__ __forceinline__ EnvIO env_io(const DevModel& m, const DyrosSimBuffers
   io.rb_force = nullptr;
   io.rb_torque = nullptr;
   io.push = false;
+  io.link_pose = nullptr;
   io.live = live;
   return io;
 }
@@ -268,6 +269,7 @@ __global__ void __launch_bounds__(kMaxQuads * DYROS_LANES * 32) k_simulate_lanes
     slab_stage_dofpar(m, b, tab, envs, es, e0, nenv, true, threadIdx.x, blockDim.x);
     cp_async_wait_all();
     __syncthreads();
+    io.link_pose = (s + 1 == p.substeps && b.link_pose) ? b.link_pose + (size_t)c.e * m.nl * 12 : nullptr;
     if (c.active) env_substep_lanes(io, c.sm, c.qflags, c.ioflags, s, c.hot, m, p, c.role, sync, c.g, false);
     __syncthreads();
     if (s + 1 == p.substeps) slab_store_outputs(m, b, c.hot, envs, es, e0, nenv, threadIdx.x, blockDim.x);
@@ -383,6 +385,7 @@ __global__ void __launch_bounds__(kStepThreadsMax) k_step_physics_lanes(DevModel
         }
       } else {
         io.push = s == 0;
+        io.link_pose = (s + 1 == k.p.skipframe && ss + 1 == p.substeps && k.s.link_pose) ? k.s.link_pose + (size_t)c.e * m.nl * 12 : nullptr;
         sync.mark(13);
         if (c.active) env_substep_lanes(io, c.sm, c.qflags, c.ioflags, epoch, c.hot, m, p, c.role, sync, c.g, true);
       }

@@ -92,8 +92,15 @@ struct EnvIO {
   const float* push;       // 3 or NULL
   const float* rb_force;   // nb*3 or NULL
   const float* rb_torque;  // nb*3 or NULL
+  float* link_pose;        // nl*12 or NULL: world pose of every link as pass 1 finds it (for the self-collision pass)
   bool live;               // false: padding lane, no global writes
 };
+HD void export_pose(const EnvIO& io, int link, const M3& Rw, V3 pw) {
+  if (!io.link_pose || !io.live) return;
+  float* o = io.link_pose + 12 * link;
+  for (int c = 0; c < 9; ++c) o[c] = (float)Rw.a[c];
+  o[9] = (float)pw.x; o[10] = (float)pw.y; o[11] = (float)pw.z;
+}
 
 // ---- penalty ground contact of one location on a link (oracle: PhysicsOracle._external_wrench.add_point);
 //      xw = the location relative to the link origin, world axes; v = [w; u] of the link
@@ -254,6 +261,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     st6(L + LS_V, v0);
     st_m3(L + LS_A + A_POSE, R0);
     st3(L + LS_A + A_POSE + 9, pw);
+    export_pose(io, 0, R0, pw);
     sync.signal(fl + 0, base + ST_PASS1);
     prev = 0;
     v_prev = v0;
@@ -294,6 +302,7 @@ HD void env_substep_role(const EnvIO& io, real* sm, int* flags, int epoch, const
     st6(L + LS_V, v_prev);
     st_m3(L + LS_A + A_POSE, Rw_prev);
     st3(L + LS_A + A_POSE + 9, pw_prev);
+    export_pose(io, i, Rw_prev, pw_prev);
     // published only where another role reads it: by foreign children (pose, velocity), or by the foreign parent,
     // which must not overwrite its pose before this link has used it
     if (RI(R, R_FLAGS) & (RF_PUBLISH | RF_PARENT_FOREIGN)) sync.signal(fl + i, base + ST_PASS1);

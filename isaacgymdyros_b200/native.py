@@ -26,7 +26,11 @@ class DyrosModelDesc(C.Structure):
         ("dof_lower", P_f64), ("dof_upper", P_f64), ("dof_vel_limit", P_f64), ("dof_effort", P_f64), ("dof_stiffness", P_f64),
         ("pt_link", P_i32), ("pt_body", P_i32), ("pt_pos", P_f64), ("pt_radius", P_f64), ("pt_solver", P_i32),
         ("cyl_link", P_i32), ("cyl_body", P_i32), ("cyl_center", P_f64), ("cyl_axis", P_f64), ("cyl_size", P_f64),
-        ("sched", P_i32)]
+        ("sched", P_i32),
+        ("sc_num_shapes", i32), ("sc_num_samples", i32), ("sc_num_pairs", i32),
+        ("sc_shape_kind", P_i32), ("sc_shape_link", P_i32), ("sc_shape_body", P_i32), ("sc_shape_sample0", P_i32),
+        ("sc_shape_center", P_f64), ("sc_shape_rot", P_f64), ("sc_shape_size", P_f64), ("sc_sample", P_f64),
+        ("sc_link_shape0", P_i32), ("sc_link_sphere", P_f64), ("sc_pairs", P_i32)]
 
 
 class DyrosSimDesc(C.Structure):
@@ -37,7 +41,7 @@ class DyrosSimDesc(C.Structure):
 
 
 SIM_BUFFERS = ["root_states", "dof_state", "net_contact_force", "rigid_body_state", "dof_actuation_force", "rb_force",
-               "rb_torque", "dof_damping", "dof_armature", "body_mass_scale", "contact_friction"]
+               "rb_torque", "dof_damping", "dof_armature", "body_mass_scale", "contact_friction", "link_pose", "self_contact_force"]
 
 
 class DyrosSimBuffers(C.Structure):
@@ -114,6 +118,7 @@ SIGNATURES = {
     "dyros_sim_destroy": (_INT, [_VP]),
     "dyros_simulate": (_INT, [_VP, _INT, _VP]),
     "dyros_refresh_rigid_body_state": (_INT, [_VP, _VP]),
+    "dyros_self_collision": (_INT, [_VP, _VP]),
     "dyros_set_state_indexed": (_INT, [_VP, _VP, _INT, _VP]),
     "dyros_refresh_dof_force": (_INT, [_VP, _VP, _VP]),
     "dyros_refresh_force_sensors": (_INT, [_VP, _VP, _VP, _INT, _VP, _VP]),

@@ -15,11 +15,15 @@ f32 = np.float32
 
 class EnvOracle:
     def __init__(self, N, tables, mocap, obs_norm, phys_params: PhysParams = None, task_params: O.Params = None,
-                 damping=None, armature=None, mass_scale=None, rng=None):
+                 damping=None, armature=None, mass_scale=None, rng=None, self_collision=True):
         from isaacgymdyros_b200.core import ARMATURE  # constants only
         self.N = N
         self.tables = tables
         self.phys = PhysicsOracle(tables, phys_params or PhysParams())
+        self.sc = None
+        if self_collision:  # the actor's shapes collide with each other (create_actor filter 0, T:354)
+            from isaacgymdyros_b200.core import self_collision_tables  # tables only
+            self.sc = self_collision_tables(tables)
         self.damping = np.full((N, 33), 0.1) if damping is None else np.asarray(damping, float)
         self.armature = np.tile(np.array(ARMATURE), (N, 1)) if armature is None else np.asarray(armature, float)
         self.mass_scale = np.ones((N, 38)) if mass_scale is None else np.asarray(mass_scale, float)
@@ -29,11 +33,18 @@ class EnvOracle:
 
     def simulate(self, s, tau, ext):
         """gym.set_dof_actuation_force_tensor + gym.simulate + refresh (T:520-526) on the oracle state dict."""
+        if self.sc is not None:  # from the poses the sub-step starts from, as its ground contact forces are
+            from .selfcollision_oracle import self_contact_forces
+            _, Rw, pw = self.phys.kinematics(s["root_states"].astype(float), s["dof_pos"].astype(float))
+            sc_f = np.stack([self_contact_forces(self.sc, [R[n] for R in Rw], [p_[n] for p_ in pw], self.phys.p.pen_k,
+                                                 self.phys.p.pen_fmax) for n in range(self.N)])
         root, q, qd, cf, _ = self.phys.substep(s["root_states"].astype(float), s["dof_pos"].astype(float),
                                                s["dof_vel"].astype(float), tau.astype(float), self.damping,
                                                self.armature, self.mass_scale,
                                                push=None if ext is None else ext.astype(float))
         s["root_states"], s["dof_pos"], s["dof_vel"] = root.astype(f32), q.astype(f32), qd.astype(f32)
+        if self.sc is not None:
+            cf = cf + sc_f[:, :cf.shape[1]]
         s["contact_forces"] = cf.astype(f32)
 
     def step(self, actions, noise):

@@ -54,6 +54,7 @@ extern "C" int dyros_hostemu_simulate(const DyrosSimDesc* d, const DyrosModelDes
     io.rb_force = rb_force ? rb_force + (size_t)env * m.nb * 3 : nullptr;
     io.rb_torque = rb_torque ? rb_torque + (size_t)env * m.nb * 3 : nullptr;
     io.friction = friction ? friction + env : nullptr;
+    io.link_pose = nullptr;
     io.live = true;
     std::vector<int> flags(F_COUNT, 0);
     std::barrier<> bar(DYROS_LANES);

@@ -59,6 +59,7 @@ extern "C" int dyros_hostemu_lanes_simulate(const DyrosSimDesc* d, const DyrosMo
     io.rb_force = rb_force ? rb_force + (size_t)env * m.nb * 3 : nullptr;
     io.rb_torque = rb_torque ? rb_torque + (size_t)env * m.nb * 3 : nullptr;
     io.push = push != nullptr;
+    io.link_pose = nullptr;
     io.live = true;
     std::vector<int> flags(ln::QF_COUNT, 0);
     for (int s = 0; s < p.substeps; ++s) {
