@@ -274,7 +274,7 @@ def run_ours(a):
         barrier()
         t_wall0 = time.perf_counter()
         for i in range(K):
-            flush.fill_(i & 0xFF)
+            env.core.flush_l2(flush, i)
             ev[i][0].record()
             device_step(W + i)
             ev[i][1].record()
@@ -347,19 +347,26 @@ def run_ours(a):
     # ---- (4) the dominant kernel alone (k_step_physics = 2 x (torque, physics sub-step, noise) in one launch), inside
     #          real staged steps, L2 flushed before each launch
     KS = min(K, 50)
-    kev = []
+    kev, scev = [], []
     core = env.core
     for i in range(KS):
         core.prologue(pool[i % len(pool)])
-        flush.fill_(i & 0xFF)
+        core.flush_l2(flush, i)
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
-        core.task_physics()
+        core.task_physics_kernel()
         a1.record()
         kev.append((a0, a1))
+        if core.step_launches() == 3:
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            core.self_collision()
+            b1.record()
+            scev.append((b0, b1))
         env.post_physics_step()
     torch.cuda.synchronize()
     k1_ms = statistics.mean(s.elapsed_time(e) for s, e in kev)
+    sc_ms = statistics.mean(s.elapsed_time(e) for s, e in scev) if scev else 0.0
     reset_rate = float(env.reset_buf.float().mean().item())
     # ---- (5) as (1), with the env state pinned in the persisting part of L2 (dyros_sim_set_l2_persistence): the same
     #          256 MiB fill between the steps no longer evicts it. Reported beside `value`, not as `value`.
@@ -371,7 +378,7 @@ def run_ours(a):
         barrier()
         pev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         for i in range(K):
-            flush.fill_(i & 0xFF)
+            env.core.flush_l2(flush, i)
             pev[i][0].record()
             device_step(W + i)
             pev[i][1].record()
@@ -405,7 +412,7 @@ def run_ours(a):
             "config": {"workload": WORKLOAD, "envs_per_gpu": N, "actions": "torch.rand(N,13)*2-1, seed 42",
                        "domain_randomisation": "mass, damping, armature, friction, PD gains" if a.dr_extra else "mass, damping, armature (CFG:81-115)",
                        "perturbation": "forced on (T:491)" if a.force_perturb else "gated as in the reference (T:489)",
-                       "l2": "flushed between timed steps (256 MiB fill outside the timed intervals)",
+                       "l2": "flushed between timed steps (256 MiB fill outside the timed intervals, by a kernel with the step kernels' L1 / shared-memory split: dyros_flush_l2)",
                        "timing": "CUDA events per step on the launch stream, summed; max over ranks",
                        "launch_geometry": dict(core.launch_info(), threads_per_cta_fused_step=256), "reset_rate_last_step": reset_rate},
             "clocks": clocks,
@@ -441,6 +448,10 @@ def run_ours(a):
                      "frac": k1_flop_env * N / (k1_ms * 1e-3) / 1e12 / fp32_peak,
                      "flop_per_launch": k1_flop_env * N, "flop_source": k1_src + ": executed ffma*2 + fadd + fmul",
                      "peak_source": "dyros_measure_fp32_peak (FFMA saturation, this run)"},
+            "step_kernels": {"k_step_physics_ms": k1_ms, "k_self_collision_ms": sc_ms,
+                             "note": "CUDA events around each launch inside staged steps, L2 flushed before the physics launch "
+                                     "(k_self_collision then finds the link poses in L2, as in the fused step); the rest of "
+                                     "ms_per_step is k_post_fused and launch gaps"},
             "whole_step_hbm": {"achieved": ENV_STEP_BYTES * N / (cold_ms / K * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s"},
             "episode_stats": stats,
             "wall_s_flush_loop": t_wall_flush,

@@ -257,6 +257,10 @@ int dyros_set_state_indexed(DyrosSim* sim, const int32_t* env_ids, int count, vo
 /* Measurement aid (no reference counterpart): FFMA-saturation micro-benchmark giving the FP32 roofline denominator
  * that MEASURED_PEAKS.json lacks. Synchronous; returns TFLOP/s (FMA = 2 FLOP). */
 int dyros_measure_fp32_peak(int device, int iters, double* tflops_out);
+/* Measurement aid (no reference counterpart): overwrites [buf, buf+bytes) on `stream`, to evict the L2 between timed
+ * steps with a kernel that keeps the SMs' L1 / shared-memory split of the step kernels (a fill launched by another
+ * library reconfigures the SMs, and the ~25 us of the switch back would land inside the next timed step). */
+int dyros_flush_l2(void* buf, size_t bytes, int value, void* stream);
 /* Optional: keep the env state resident in the set-aside (persisting) part of the B200's 126 MB L2. [base, base+bytes)
  * is the one contiguous range holding the per-env buffers (the caller allocates them from one arena); kernels launched
  * on `stream` afterwards, and kernel nodes captured from it into CUDA graphs, access that range with the persisting
@@ -274,6 +278,9 @@ int dyros_task_set_noise_injection(DyrosTask* task, const DyrosNoiseInjection* i
 int dyros_task_prologue(DyrosTask* task, const float* actions, void* stream);      /* VT:307 + T:449-502 */
 /* T:504-530 in one launch: skipframe x (substep torque, gym.simulate, sensor noise); what dyros_task_step uses. */
 int dyros_task_physics(DyrosTask* task, void* stream);
+/* Measurement aid: the physics launch of dyros_task_physics alone (without the self-collision pass that follows it;
+ * dyros_self_collision completes the step), so that the dominant kernel can be timed by itself. */
+int dyros_task_physics_kernel(DyrosTask* task, void* stream);
 /* Profiling aid: dyros_task_physics that also writes clock64() at the phase boundaries of CTA 0 into `trace`
  * (device buffer of skipframe * DYROS_LANES * 32 int64; see physics_roles.cuh for the mark ids). */
 int dyros_task_physics_trace(DyrosTask* task, int64_t* trace, void* stream);

@@ -441,6 +441,16 @@ class DyrosCore:
     def task_physics(self):
         native.check(self.lib.dyros_task_physics(self.task_handle, self._stream), "task_physics")
 
+    def task_physics_kernel(self):
+        """Measurement aid: the physics launch alone; `self_collision()` completes what `task_physics()` does."""
+        native.check(self.lib.dyros_task_physics_kernel(self.task_handle, self._stream), "task_physics_kernel")
+
+    def flush_l2(self, buf: "torch.Tensor", value: int = 0):
+        """Measurement aid: overwrites `buf` (larger than the L2) with a kernel that keeps the step kernels' L1 / shared
+        memory split (dyros_flush_l2)."""
+        native.check(self.lib.dyros_flush_l2(C.c_void_p(buf.data_ptr()), C.c_size_t(buf.numel() * buf.element_size()),
+                                            int(value) & 0xFF, self._stream), "flush_l2")
+
     def task_physics_trace(self) -> "torch.Tensor":
         """Profiling aid: runs the fused physics launch and returns clock64() marks of CTA 0, (skipframe, roles, 32)."""
         buf = torch.zeros(self.cfg.control_freq_inv, native.DYROS_LANES, 32, dtype=torch.int64, device=self.device)

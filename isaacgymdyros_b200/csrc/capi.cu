@@ -68,7 +68,7 @@ static int build_sim(const DyrosSimDesc* d, const DyrosModelDesc* m, const Dyros
   int dev_sms = 0;
   if (cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, d->device) == cudaSuccess && dev_sms > 0)
     sim->sm_count = dev_sms;
-  if (physics_configure(sim)) {
+  if (physics_configure(sim) || configure_physics_aux_kernels()) {
     cudaFree(sim->dev_blob);
     delete sim;
     return 1;
@@ -190,6 +190,10 @@ static int build_task(Sim* sim, const DyrosTaskDesc* d, const DyrosTaskBuffers* 
   p.step_counter = const_cast<uint64_t*>(at<uint64_t>(base, o_ct));
   p.tail = const_cast<unsigned long long*>(at<unsigned long long>(base, o_tail));
   p.scan_state = const_cast<unsigned*>(at<unsigned>(base, o_scan));
+  if (configure_task_kernels()) {
+    delete t;
+    return 1;
+  }
   *out = t;
   return 0;
 }
@@ -293,6 +297,13 @@ int dyros_measure_fp32_peak(int device, int iters, double* tflops_out) {
   }
   return measure_fp32_peak(device, iters, tflops_out);
 }
+int dyros_flush_l2(void* buf, size_t bytes, int value, void* stream) {
+  if (!buf || (reinterpret_cast<uintptr_t>(buf) & 15)) {
+    set_error("dyros_flush_l2: NULL or unaligned buffer");
+    return 1;
+  }
+  return launch_fill(buf, bytes, value, (cudaStream_t)stream);
+}
 int dyros_sim_set_l2_persistence(DyrosSim* sim, void* base, size_t bytes, void* stream, size_t* set_aside_out) {
   SIM_OR_FAIL("dyros_sim_set_l2_persistence");
   cudaStream_t st = (cudaStream_t)stream;
@@ -375,6 +386,10 @@ int dyros_task_physics(DyrosTask* task, void* stream) {
   TASK_OR_FAIL("dyros_task_physics");
   if (launch_task_physics(t, (cudaStream_t)stream)) return 1;
   return launch_self_collision(t->sim, (cudaStream_t)stream);
+}
+int dyros_task_physics_kernel(DyrosTask* task, void* stream) {
+  TASK_OR_FAIL("dyros_task_physics_kernel");
+  return launch_task_physics(t, (cudaStream_t)stream);
 }
 int dyros_task_physics_trace(DyrosTask* task, int64_t* trace, void* stream) {
   TASK_OR_FAIL("dyros_task_physics_trace");

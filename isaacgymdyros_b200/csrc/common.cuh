@@ -1,5 +1,6 @@
 // Shared device helpers: error plumbing, Philox4x32-10 counter RNG, warp utilities.
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -38,8 +39,18 @@ inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  static const bool no_pdl = getenv("DYROS_NO_PDL") != nullptr;  // (diagnostics: every launch fully serialised)
+  cfg.numAttrs = pdl && !no_pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+// Every kernel of the library asks for the same L1 / shared-memory split as the physics kernels, which need all of the
+// shared memory of an SM (226 KB). Measured on B200 (profiles/r2_carveout.md): a stream that alternates between kernels
+// with different preferred carve-outs pays ~25 us per switch (the SMs drain and reconfigure), which was ~50 us of a
+// ~147 us fused step; with one carve-out everywhere the same launches take the sum of their kernels (~96 us).
+template <class K>
+inline cudaError_t prefer_max_smem_carveout(K kern) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 constexpr int kWarp = 32;

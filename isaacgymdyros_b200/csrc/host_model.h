@@ -36,7 +36,7 @@ static const T* at(void* base, size_t off) {
 }
 
 struct ModelOffsets {
-  size_t parent, dof, E, r, ax, cs, ch, bs, bd, bl, bp, br, bi, lo, up, vl, ef, ps, pb, pp, pr, ys, yb, yc, ya, yz, sc, rc, ro, dl, pg, fp, fb, st, sk, sl, sb, s0, sf, ss, ls, lp, sp, sq, sq0;
+  size_t parent, dof, E, r, ax, cs, ch, bs, bd, bl, bp, br, bi, lo, up, vl, ef, ps, pb, pp, pr, ys, yb, yc, ya, yz, sc, rc, ro, dl, pg, fp, fb, st, sk;
 };
 
 // Fills `dm` (counts, foot tables) and appends every table to `bl`. Returns "" or an error message.
@@ -325,51 +325,53 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
   o.yb = bl.add_i(ccyl_body.data(), ccyl_body.size());
   o.yc = bl.add_f32(ccyl_center.data(), ccyl_center.size()); o.ya = bl.add_f32(ccyl_axis.data(), ccyl_axis.size());
   o.yz = bl.add_f32(ccyl_size.data(), ccyl_size.size());
-  {  // self-collision tables
+  {  // self-collision tables: one packed block (layout in internal.h)
     const int ns = m->sc_shape_kind ? m->sc_num_shapes : 0, nsm = ns ? m->sc_num_samples : 0, npair = ns ? m->sc_num_pairs : 0;
     dm.sc_ns = ns; dm.sc_nsamp = nsm; dm.sc_np = npair;
-    std::vector<int> zi(1, 0);
-    std::vector<float> sf((size_t)std::max(ns, 1) * 16, 0.f);
-    for (int k = 0; k < ns; ++k) {
-      for (int c = 0; c < 3; ++c) sf[16 * k + c] = (float)m->sc_shape_center[3 * k + c];
-      for (int c = 0; c < 9; ++c) sf[16 * k + 3 + c] = (float)m->sc_shape_rot[9 * k + c];
-      for (int c = 0; c < 3; ++c) sf[16 * k + 12 + c] = (float)m->sc_shape_size[3 * k + c];
-      {  // bounding radius about the centre (rounded up): box |half extents|, cylinder hypot(radius, half height)
-        const double* z = m->sc_shape_size + 3 * k;
-        const double R = m->sc_shape_kind[k] == 0 ? std::sqrt(z[0] * z[0] + z[1] * z[1] + z[2] * z[2]) : std::hypot(z[0], z[1]);
-        sf[16 * k + 15] = std::nextafter((float)(R * (1.0 + 1e-6)), INFINITY);
-      }
-      if (m->sc_shape_link[k] < 0 || m->sc_shape_link[k] >= nl || m->sc_shape_body[k] < 0 || m->sc_shape_body[k] >= nb)
-        MFAIL("self-collision shape %d: link / body out of range", k);
-    }
-    for (int k = 0; k < npair; ++k)
-      if (m->sc_pairs[2 * k] < 0 || m->sc_pairs[2 * k] >= nl || m->sc_pairs[2 * k + 1] < 0 || m->sc_pairs[2 * k + 1] >= nl)
-        MFAIL("self-collision pair %d: link out of range", k);
-    o.sk = ns ? bl.add_i(m->sc_shape_kind, ns) : bl.add_i(zi.data(), 1);
-    o.sl = ns ? bl.add_i(m->sc_shape_link, ns) : bl.add_i(zi.data(), 1);
-    o.sb = ns ? bl.add_i(m->sc_shape_body, ns) : bl.add_i(zi.data(), 1);
-    o.s0 = ns ? bl.add_i(m->sc_shape_sample0, ns + 1) : bl.add_i(zi.data(), 1);
-    o.sf = bl.add_f32(sf.data(), sf.size());
-    o.ss = nsm ? bl.add_f(m->sc_sample, (size_t)nsm * 4) : bl.add_i(zi.data(), 1);
-    o.ls = ns ? bl.add_i(m->sc_link_shape0, nl + 1) : bl.add_i(zi.data(), 1);
-    o.lp = ns ? bl.add_f(m->sc_link_sphere, (size_t)nl * 4) : bl.add_i(zi.data(), 1);
-    o.sp = npair ? bl.add_i(m->sc_pairs, (size_t)npair * 2) : bl.add_i(zi.data(), 1);
-    // shape pairs of every candidate link pair, flattened: [sq0[pi], sq0[pi+1]) = (shape of link i) | (shape of link j) << 16
     if (ns > SC_MAX_SHAPES) MFAIL("self-collision: %d shapes, at most %d", ns, SC_MAX_SHAPES);
-    std::vector<int> sq, sq0(npair + 1, 0);
+    if (ns && (nl > 255 || nb > 255 || nsm > 65535)) MFAIL("self-collision: the model is too large for the packed tables");
+    std::vector<int> hot;
+    auto section = [&]() { hot.resize((hot.size() + 3) & ~size_t(3)); return (int)hot.size(); };
+    auto f2i = [](float f) { int i; memcpy(&i, &f, 4); return i; };
+    std::vector<unsigned short> sp;
     for (int k = 0; k < npair; ++k) {
       const int li = m->sc_pairs[2 * k], lj = m->sc_pairs[2 * k + 1];
+      if (li < 0 || li >= nl || lj < 0 || lj >= nl) MFAIL("self-collision pair %d: link out of range", k);
       for (int a = m->sc_link_shape0[li]; a < m->sc_link_shape0[li + 1]; ++a)
-        for (int b = m->sc_link_shape0[lj]; b < m->sc_link_shape0[lj + 1]; ++b) {
-          if (m->sc_shape_sample0[a + 1] - m->sc_shape_sample0[a] > SC_MAX_SHAPE_SAMPLES || m->sc_shape_sample0[b + 1] - m->sc_shape_sample0[b] > SC_MAX_SHAPE_SAMPLES)
-            MFAIL("self-collision: a shape with more than %d sample spheres", SC_MAX_SHAPE_SAMPLES);
-          sq.push_back(a | (b << 16));
-        }
-      sq0[k + 1] = (int)sq.size();
+        for (int b = m->sc_link_shape0[lj]; b < m->sc_link_shape0[lj + 1]; ++b) sp.push_back((unsigned short)(a | b << 8));
     }
-    if (sq.empty()) sq.push_back(0);
-    o.sq = bl.add_i(sq.data(), sq.size());
-    o.sq0 = bl.add_i(sq0.data(), sq0.size());
+    dm.sc_nq = (int)sp.size();
+    // padded to whole batches of the kernel's sweep with a pair of two far-apart dummy shapes (ns, ns + 1)
+    while (sp.size() % SC_SWEEP_BATCH) sp.push_back((unsigned short)(ns | (ns + 1) << 8));
+    dm.sc_nq_padded = (int)sp.size();
+    dm.sc_o_sp = section();
+    for (size_t k = 0; k < sp.size(); k += 2) hot.push_back((int)(sp[k] | (unsigned)sp[k + 1] << 16));
+    dm.sc_o_shape = section();
+    for (int k = 0; k < ns; ++k) {
+      if (m->sc_shape_link[k] < 0 || m->sc_shape_link[k] >= nl || m->sc_shape_body[k] < 0 || m->sc_shape_body[k] >= nb)
+        MFAIL("self-collision shape %d: link / body out of range", k);
+      for (int c = 0; c < 3; ++c) hot.push_back(f2i((float)m->sc_shape_center[3 * k + c]));
+      for (int c = 0; c < 9; ++c) hot.push_back(f2i((float)m->sc_shape_rot[9 * k + c]));
+      for (int c = 0; c < 3; ++c) hot.push_back(f2i((float)m->sc_shape_size[3 * k + c]));
+      // bounding radius about the centre (rounded up): box |half extents|, cylinder hypot(radius, half height)
+      const double* z = m->sc_shape_size + 3 * k;
+      const double R = m->sc_shape_kind[k] == 0 ? std::sqrt(z[0] * z[0] + z[1] * z[1] + z[2] * z[2]) : std::hypot(z[0], z[1]);
+      hot.push_back(f2i(std::nextafter((float)(R * (1.0 + 1e-6)), INFINITY)));
+    }
+    dm.sc_o_meta = section();
+    for (int k = 0; k < ns; ++k) {
+      const int s0 = m->sc_shape_sample0[k], n = m->sc_shape_sample0[k + 1] - s0;
+      if (n < 0 || n > SC_MAX_SHAPE_SAMPLES || s0 < 0 || s0 + n > nsm)
+        MFAIL("self-collision shape %d: %d sample spheres (at most %d)", k, n, SC_MAX_SHAPE_SAMPLES);
+      hot.push_back(m->sc_shape_link[k] | m->sc_shape_body[k] << 8 | m->sc_shape_kind[k] << 16);
+      hot.push_back(s0 | n << 16);
+    }
+    dm.sc_o_sample = section();
+    for (int k = 0; k < nsm * 4; ++k) hot.push_back(f2i((float)m->sc_sample[k]));
+    section();
+    if (hot.empty()) hot.resize(4, 0);
+    dm.sc_hot_words = (int)hot.size();
+    o.sk = bl.add_i(hot.data(), hot.size());
   }
   bl.host.resize((bl.host.size() + 15) & ~size_t(15));
   // word offsets of the hot tables inside the staged prefix
@@ -400,10 +402,7 @@ static void resolve_model(DevModel& dm, const ModelOffsets& o, void* base) {
   dm.link_cyl_start = at<int>(base, o.ys); dm.cyl_body = at<int>(base, o.yb); dm.cyl_center = at<float>(base, o.yc);
   dm.cyl_axis = at<float>(base, o.ya); dm.cyl_size = at<float>(base, o.yz);
   dm.sched = at<int>(base, o.sc);
-  dm.sc_shape_kind = at<int>(base, o.sk); dm.sc_shape_link = at<int>(base, o.sl); dm.sc_shape_body = at<int>(base, o.sb);
-  dm.sc_shape_sample0 = at<int>(base, o.s0); dm.sc_shape_f = at<float>(base, o.sf); dm.sc_sample = at<float>(base, o.ss);
-  dm.sc_link_shape0 = at<int>(base, o.ls); dm.sc_link_sphere = at<float>(base, o.lp); dm.sc_pairs = at<int>(base, o.sp);
-  dm.sc_shape_pairs = at<int>(base, o.sq); dm.sc_pair_sq0 = at<int>(base, o.sq0);
+  dm.sc_hot = at<int>(base, o.sk);
   dm.link_reach = at<float>(base, o.rc);
   dm.blob = base;
 }
@@ -423,7 +422,7 @@ static void fill_sim_params(const DyrosSimDesc* d, SimParams& p) {
   p.max_ang_vel = d->max_angular_velocity;
   p.sweeps = d->contact_sweeps;
   p.clamp_effort = d->clamp_effort;
-  p.sc_pairs_cap = p.sc_hits_cap = 0;  // set at the first launch_self_collision
+  p.sc_hits_cap = 0;  // set at the first launch_self_collision
 }
 
 }  // namespace dyros

@@ -25,7 +25,8 @@ constexpr int RF_PARENT_FOREIGN = 1, RF_PARENT_BASE = 2;
 constexpr int RF_PUBLISH = 4;  // a child of the link lives in another role: its stage flags are read there
 constexpr int RF_KEEP = 8;     // a child of the link in the SAME role is not the role's next link: results go through the block
 constexpr int SC_MAX_SHAPES = 96;         // self-collision: collision primitives of one articulation
-constexpr int SC_MAX_SHAPE_SAMPLES = 8;   // sample spheres of one primitive (a box has its 8 corners)
+constexpr int SC_MAX_SHAPE_SAMPLES = 8;
+constexpr int SC_SWEEP_BATCH = 128;       // k_self_collision tests shape pairs in batches of 4 rounds x 32 lanes   // sample spheres of one primitive (a box has its 8 corners)
 constexpr int MAX_CSLOTS = 8;  // links whose parent is not the role's previous link (R_CSLOT: their index, else -1)
 struct DevModel {
   int nl, nb, nd, np, nc, T;
@@ -58,19 +59,14 @@ struct DevModel {
   const float* cyl_size;
   const int* sched;             // [T*DYROS_LANES]
   const float* link_reach;      // [nl] bounding radius of the link's penalty candidates about its origin
-  // self-collision tables (cold), see DyrosModelDesc
-  int sc_ns, sc_nsamp, sc_np;
-  const int* sc_shape_kind;
-  const int* sc_shape_link;
-  const int* sc_shape_body;
-  const int* sc_shape_sample0;
-  const float* sc_shape_f;      // [ns*16]: centre 3, rot 9, size 3, bounding radius about the centre
-  const float* sc_sample;       // [nsamp*4]
-  const int* sc_link_shape0;
-  const float* sc_link_sphere;  // [nl*4]
-  const int* sc_pairs;          // [np*2]
-  const int* sc_shape_pairs;    // flattened shape pairs of the link pairs: shape a | shape b << 16
-  const int* sc_pair_sq0;       // [np+1] link pair pi owns sc_shape_pairs[sq0[pi] .. sq0[pi+1])
+  // self-collision tables (see DyrosModelDesc), packed for k_self_collision, which stages all of them in shared memory:
+  //   sp     [nq_padded] uint16: shape a | shape b << 8: the shape pairs of every candidate link pair, flattened
+  //   shape  [ns*16] float: centre 3, rot 9 (row-major, columns = axes), size 3, bounding radius about the centre
+  //   meta   [ns*2] link | body << 8 | kind << 16, first sample | number of samples << 16
+  //   sample [nsamp*4] float: position in the link frame, radius
+  int sc_ns, sc_nsamp, sc_np, sc_nq, sc_nq_padded;
+  const int* sc_hot;
+  int sc_hot_words, sc_o_sp, sc_o_shape, sc_o_meta, sc_o_sample;
   const void* blob;             // base of the packed tables; [blob, blob + hot_bytes) is what the kernel stages in smem
   int hot_bytes;
   // word offsets of the hot tables inside the staged prefix (same order as the pointers above)
@@ -100,7 +96,7 @@ struct SimParams {
   float g[3];
   float contact_offset, max_depen_vel, erp, mu, pen_k, pen_c, pen_fmax, max_ang_vel;
   int sweeps, clamp_effort;
-  int sc_pairs_cap, sc_hits_cap;  // capacities of k_self_collision's lists (<= kScPairs / kScHits; smaller only in tests)
+  int sc_hits_cap;  // capacity of k_self_collision's hit list (smaller than the array only in tests)
 };
 
 // task constants; every derived value is formed in double on the host the way Python forms it, then cast once
@@ -175,6 +171,9 @@ int physics_configure(Sim* sim);  // chooses envs_per_block / shared memory, set
 int launch_simulate(Sim* sim, int apply_wrench, const float* push_force, cudaStream_t s);
 int launch_refresh_rigid_body_state(Sim* sim, cudaStream_t s);
 int launch_refresh_dof_force(Sim* sim, float* out, cudaStream_t s);
+int configure_physics_aux_kernels();
+int launch_fill(void* buf, size_t bytes, int value, cudaStream_t s);
+int configure_task_kernels();
 int launch_self_collision(Sim* sim, cudaStream_t s, bool pdl = false);
 inline bool has_self_collision(const Sim* sim) { return sim->m.sc_np > 0 && sim->b.link_pose && sim->b.self_contact_force; }
 int launch_refresh_force_sensors(Sim* sim, const int32_t* sensor_body, const float* sensor_pose, int ns, float* out, cudaStream_t s);

@@ -530,20 +530,22 @@ __global__ void __launch_bounds__(64) k_rigid_body_state(DevModel m, SimParams p
 }
 
 // ---------------------------------------------------------------- self-collision (model/selfcollision.py, T:354 filter 0)
-// One warp per env, every level of the hierarchy spread over the lanes and compacted with ballots:
-//   0. the env's link poses -> shared memory (coalesced); world centres of the link and shape bounding spheres;
-//   1. candidate link pairs, one per lane and round: two link spheres overlap -> list of link pairs (standing: ~40 of 497);
-//   2. their shape pairs, 8 lanes per link pair: two shape spheres overlap -> hit list (standing: ~20 of ~250);
-//   2b. hit list, one per lane: face-axis separating-axis test of the two oriented bounding boxes (a box is its own, a
-//      cylinder's is r x r x h) -> what stays is really close (standing: a few);
-//   3. hit list, half a warp per shape pair: lane = one sample sphere of one shape against the exact box / cylinder of
+// One warp per env, 16 envs per CTA; the CTA stages the packed tables (DevModel::sc_hot, ~13 KB for TOCABI) in shared
+// memory while the physics kernel before it drains (PDL).
+//   0. the env's link poses -> shared memory (coalesced); world centres of the shapes' bounding spheres;
+//   1. sweep over the shape pairs of all candidate link pairs (1656 for TOCABI), one per lane, 4 rounds in flight: two
+//      bounding spheres overlap -> hit list (standing: ~20);
+//   2. hit list, one per lane: face-axis separating-axis test of the two oriented bounding boxes (a box is its own, a
+//      cylinder's is r x r x h) -> what stays is really close (standing: a few), compacted with a ballot;
+//   3. half a warp per surviving shape pair: lane = one sample sphere of one shape against the exact box / cylinder of
 //      the other (both ways); a penetrating sample pushes the two bodies apart along the gradient of the signed
 //      distance with the penalty stiffness of the ground contacts, accumulated per body in shared memory.
 // Every cull is conservative, so the result is that of the plain double loop restated in oracle/selfcollision_oracle.py
-// (up to the order of the sums); lists that overflow fall back to the unculled work, never to dropped contacts.
-constexpr int kScWarps = 4;
-constexpr int kScPairs = 128;  // link pairs whose spheres overlap
-constexpr int kScHits = 64;    // shape pairs whose spheres overlap
+// (up to the order of the sums); an env that overflows the hit list is swept again without it, never dropping a contact.
+// (Measured dead ends, profiles/r2_self_collision.md: a link-sphere level above the shape spheres costs more in list
+// handling than the 1200 sphere tests it saves; two warps per env only fit one wave at 32 registers.)
+constexpr int kScEnvs = 16;    // envs (warps) per CTA
+constexpr int kScHits = 128;   // shape pairs whose spheres overlap
 __device__ __forceinline__ float sc_sdf(int kind, V3 size, V3 x, V3& g) {
   if (kind == 0) {  // box: half extents
     const V3 q = v3(fabsf(x.x) - size.x, fabsf(x.y) - size.y, fabsf(x.z) - size.z);
@@ -575,56 +577,87 @@ __device__ __forceinline__ float sc_sdf(int kind, V3 size, V3 x, V3& g) {
   g = ez;
   return qz;
 }
-struct ScWarp {
-  float pose[DYROS_MAX_LINKS * 12];
-  float4 link_c[DYROS_MAX_LINKS];
-  float4 shape_c[SC_MAX_SHAPES];
-  float force[DYROS_MAX_BODIES * 3];
-  int pairs[kScPairs];
-  int hits[kScHits];
-  int any_hit;
+struct ScEnv {  // views into the env's block of shared memory (sized by the model: sc_env_bytes)
+  float* pose;                // [nl*12]
+  float4* shape_c;            // [ns+2]: world centre and radius of each shape's bounding sphere; two far-apart dummies
+  float* force;               // [nb*3]
+  int* count;                 // [0] hits, [1] any contact
+  unsigned short* hits;       // [kScHits] shape a | shape b << 8
 };
+__host__ __device__ inline int sc_align4(int words) { return (words + 3) & ~3; }
+__host__ __device__ inline int sc_env_bytes(int nl, int ns, int nb) {
+  return 4 * (sc_align4(nl * 12) + (ns + 2) * 4 + sc_align4(nb * 3) + 4) + 2 * kScHits;
+}
+__device__ __forceinline__ ScEnv sc_env_views(void* base, int nl, int ns, int nb) {
+  ScEnv E;
+  float* f = static_cast<float*>(base);
+  E.pose = f; f += sc_align4(nl * 12);
+  E.shape_c = reinterpret_cast<float4*>(f); f += (ns + 2) * 4;
+  E.force = f; f += sc_align4(nb * 3);
+  E.count = reinterpret_cast<int*>(f); f += 4;
+  E.hits = reinterpret_cast<unsigned short*>(f);
+  return E;
+}
+struct ScTab {  // the staged tables
+  const unsigned short* sp;
+  const float* shape;
+  const int* meta;
+  const float* sample;
+};
+__device__ __forceinline__ bool sc_spheres_overlap(float4 a, float4 b) {
+  const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, rs = a.w + b.w;
+  return dx * dx + dy * dy + dz * dz < rs * rs;
+}
+__device__ __forceinline__ void sc_pose(const float* pose, int l, M3& R, V3& t) {
+  const float4* q = reinterpret_cast<const float4*>(pose + 12 * l);
+  const float4 a = q[0], b = q[1], c = q[2];
+  R = M3{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x}};
+  t = v3(c.y, c.z, c.w);
+}
 // sample sphere k (of shape sa) against shape sb
-__device__ __forceinline__ void sc_item(const DevModel& m, const SimParams& p, ScWarp& W, int sa, int sb, int k) {
-  const int la = m.sc_shape_link[sa], lb = m.sc_shape_link[sb];
-  const float4 smp = *reinterpret_cast<const float4*>(m.sc_sample + 4 * k);
-  const V3 c = mul(ld_m3_f(W.pose + 12 * la), v3(smp.x, smp.y, smp.z)) + ld3_f(W.pose + 12 * la + 9);
+__device__ __forceinline__ void sc_item(const ScTab& T, const SimParams& p, const ScEnv& W, int sa, int sb, int k) {
+  const int ma = T.meta[2 * sa], mb = T.meta[2 * sb];
+  const float4 smp = *reinterpret_cast<const float4*>(T.sample + 4 * k);
+  M3 Ra, Rb;
+  V3 pa, pb;
+  sc_pose(W.pose, ma & 0xff, Ra, pa);
+  const V3 c = mul(Ra, v3(smp.x, smp.y, smp.z)) + pa;
   const float rho = smp.w;
   const float4 sc = W.shape_c[sb];
   const V3 dc = c - v3(sc.x, sc.y, sc.z);
   const float reach = rho + sc.w;
   if (dot(dc, dc) >= reach * reach) return;
-  const M3 Rb = ld_m3_f(W.pose + 12 * lb);
-  const V3 cl = mulT(Rb, c - ld3_f(W.pose + 12 * lb + 9));  // in link lb's frame
-  const float* S = m.sc_shape_f + 16 * sb;
+  sc_pose(W.pose, mb & 0xff, Rb, pb);
+  const V3 cl = mulT(Rb, c - pb);  // in link lb's frame
+  const float* S = T.shape + 16 * sb;
   const M3 Rs = ld_m3_f(S + 3);
   V3 g;
-  const float d = sc_sdf(m.sc_shape_kind[sb], ld3_f(S + 12), mulT(Rs, cl - ld3_f(S)), g);
+  const float d = sc_sdf((mb >> 16) & 0xff, ld3_f(S + 12), mulT(Rs, cl - ld3_f(S)), g);
   const float depth = rho - d;
   if (depth > 0.f) {
     const V3 f = fminf(p.pen_k * depth, p.pen_fmax) * mul(Rb, mul(Rs, g));  // pushes the sample's body out
-    const int ba = m.sc_shape_body[sa], bb = m.sc_shape_body[sb];
+    const int ba = (ma >> 8) & 0xff, bb = (mb >> 8) & 0xff;
     atomicAdd(&W.force[3 * ba], f.x); atomicAdd(&W.force[3 * ba + 1], f.y); atomicAdd(&W.force[3 * ba + 2], f.z);
     atomicAdd(&W.force[3 * bb], -f.x); atomicAdd(&W.force[3 * bb + 1], -f.y); atomicAdd(&W.force[3 * bb + 2], -f.z);
-    W.any_hit = 1;
+    W.count[1] = 1;
   }
 }
-__device__ __forceinline__ bool sc_spheres_overlap(float4 a, float4 b) {
-  const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, rs = a.w + b.w;
-  return dx * dx + dy * dy + dz * dz < rs * rs;
-}
 // World frame (columns = axes) and half extents of shape s's oriented bounding box.
-__device__ __forceinline__ void sc_obb(const DevModel& m, const ScWarp& W, int s, M3& R, V3& half) {
-  const float* S = m.sc_shape_f + 16 * s;
-  R = mul(ld_m3_f(W.pose + 12 * m.sc_shape_link[s]), ld_m3_f(S + 3));
-  half = m.sc_shape_kind[s] == 0 ? ld3_f(S + 12) : v3(S[12], S[12], S[13]);
+__device__ __forceinline__ void sc_obb(const ScTab& T, const ScEnv& W, int s, M3& R, V3& half) {
+  const float* S = T.shape + 16 * s;
+  const int ms = T.meta[2 * s];
+  M3 Rl;
+  V3 pl;
+  sc_pose(W.pose, ms & 0xff, Rl, pl);
+  R = mul(Rl, ld_m3_f(S + 3));
+  half = ((ms >> 16) & 0xff) == 0 ? ld3_f(S + 12) : v3(S[12], S[12], S[13]);
 }
 // true when one of the 6 face normals separates the two boxes (with a margin for rounding): certainly no contact
-__device__ __forceinline__ bool sc_obb_separated(const DevModel& m, const ScWarp& W, int sa, int sb) {
+__device__ __forceinline__ bool sc_obb_separated(const ScTab& T, const ScEnv& W, int sa, int sb) {
   M3 A, B;
   V3 ha, hb;
-  sc_obb(m, W, sa, A, ha);
-  sc_obb(m, W, sb, B, hb);
+  sc_obb(T, W, sa, A, ha);
+  sc_obb(T, W, sb, B, hb);
   const float4 ca = W.shape_c[sa], cb = W.shape_c[sb];
   const V3 t = mulT(A, v3(cb.x - ca.x, cb.y - ca.y, cb.z - ca.z));  // in A's frame
   const M3 C = mulAtB(A, B);                                        // B's axes in A's frame
@@ -641,109 +674,107 @@ __device__ __forceinline__ bool sc_obb_separated(const DevModel& m, const ScWarp
     sep |= fabsf(ta[0] * C.a[j] + ta[1] * C.a[3 + j] + ta[2] * C.a[6 + j]) > hB[j] + c[j] * hA[0] + c[3 + j] * hA[1] + c[6 + j] * hA[2] + eps;
   return sep;
 }
-__global__ void __launch_bounds__(kScWarps * 32) k_self_collision(DevModel m, SimParams p, DyrosSimBuffers b) {
-  __shared__ ScWarp sw[kScWarps];
+__global__ void __launch_bounds__(kScEnvs * 32, 2) k_self_collision(DevModel m, SimParams p, DyrosSimBuffers b) {
+  extern __shared__ float4 sc_smem[];
+  int* tab = reinterpret_cast<int*>(sc_smem);
   pdl_launch_dependents();
+  for (int i = threadIdx.x; i < m.sc_hot_words / 4; i += blockDim.x)  // (constant tables: before the wait)
+    reinterpret_cast<int4*>(tab)[i] = reinterpret_cast<const int4*>(m.sc_hot)[i];
   pdl_wait();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  const int e = blockIdx.x * kScWarps + w;
-  if (e >= p.N) return;
-  ScWarp& W = sw[w];
-  const float* pose = b.link_pose + (size_t)e * m.nl * 12;
-  for (int i = lane; i < m.nl * 12; i += 32) W.pose[i] = pose[i];
-  for (int i = lane; i < m.nb * 3; i += 32) W.force[i] = 0.f;
-  if (lane == 0) W.any_hit = 0;
-  __syncwarp();
-  for (int l = lane; l < m.nl; l += 32) {
-    const V3 c = mul(ld_m3_f(W.pose + 12 * l), ld3_f(m.sc_link_sphere + 4 * l)) + ld3_f(W.pose + 12 * l + 9);
-    W.link_c[l] = make_float4(c.x, c.y, c.z, m.sc_link_sphere[4 * l + 3]);
+  const int e = blockIdx.x * kScEnvs + slot;
+  const bool live = e < p.N;
+  const ScEnv W = sc_env_views(reinterpret_cast<char*>(tab + m.sc_hot_words) + (size_t)slot * sc_env_bytes(m.nl, m.sc_ns, m.nb),
+                               m.nl, m.sc_ns, m.nb);
+  if (live) {
+    const float* pose = b.link_pose + (size_t)e * m.nl * 12;
+    for (int i = lane; i < m.nl * 3; i += 32)  // (12 floats per link: the env's block is 16-byte aligned)
+      reinterpret_cast<float4*>(W.pose)[i] = reinterpret_cast<const float4*>(pose)[i];
+    for (int i = lane; i < m.nb * 3; i += 32) W.force[i] = 0.f;
+    if (lane < 2) W.count[lane] = 0;
   }
+  __syncthreads();
+  if (!live) return;
+  ScTab T;
+  T.sp = reinterpret_cast<const unsigned short*>(tab + m.sc_o_sp);
+  T.shape = reinterpret_cast<const float*>(tab + m.sc_o_shape);
+  T.meta = tab + m.sc_o_meta;
+  T.sample = reinterpret_cast<const float*>(tab + m.sc_o_sample);
   for (int s = lane; s < m.sc_ns; s += 32) {
-    const int l = m.sc_shape_link[s];
-    const V3 c = mul(ld_m3_f(W.pose + 12 * l), ld3_f(m.sc_shape_f + 16 * s)) + ld3_f(W.pose + 12 * l + 9);
-    W.shape_c[s] = make_float4(c.x, c.y, c.z, m.sc_shape_f[16 * s + 15]);
+    const float4 s0 = *reinterpret_cast<const float4*>(T.shape + 16 * s);
+    M3 R;
+    V3 t;
+    sc_pose(W.pose, T.meta[2 * s] & 0xff, R, t);
+    const V3 c = mul(R, v3(s0.x, s0.y, s0.z)) + t;
+    W.shape_c[s] = make_float4(c.x, c.y, c.z, T.shape[16 * s + 15]);
   }
+  if (lane < 2) W.shape_c[m.sc_ns + lane] = make_float4(lane ? -1e18f : 1e18f, 0.f, 0.f, 0.f);
   __syncwarp();
-  int n1 = 0;  // 1. link spheres
-  const int2* link_pairs = reinterpret_cast<const int2*>(m.sc_pairs);
-#pragma unroll 2
-  for (int base = 0; base < m.sc_np; base += 32) {
-    const int pi = base + lane;
-    bool hit = false;
-    if (pi < m.sc_np) {
-      const int2 lp = link_pairs[pi];
-      hit = sc_spheres_overlap(W.link_c[lp.x], W.link_c[lp.y]);
+  // 1. bounding spheres of every candidate shape pair (the list is padded to whole batches with a far-apart dummy pair)
+  const char* centres = reinterpret_cast<const char*>(W.shape_c);
+  for (int base = lane; base < m.sc_nq_padded; base += SC_SWEEP_BATCH) {
+    unsigned sp[4];
+    float4 ca[4], cb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sp[u] = T.sp[base + 32 * u];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ca[u] = *reinterpret_cast<const float4*>(centres + ((sp[u] & 0xffu) << 4));
+      cb[u] = *reinterpret_cast<const float4*>(centres + ((sp[u] >> 4) & 0xff0u));
     }
-    const unsigned bal = __ballot_sync(kFull, hit);
-    const int slot = n1 + __popc(bal & lt);
-    if (hit && slot < p.sc_pairs_cap) W.pairs[slot] = pi;
-    n1 += __popc(bal);
-  }
-  __syncwarp();
-  int n2 = 0;  // 2. shape spheres
-  auto shape_pair = [&](int q, bool valid) {
-    int sp = 0;
-    bool hit = false;
-    if (valid) {
-      sp = m.sc_shape_pairs[q];
-      hit = sc_spheres_overlap(W.shape_c[sp & 0xffff], W.shape_c[sp >> 16]);
-    }
-    const unsigned bal = __ballot_sync(kFull, hit);
-    const int slot = n2 + __popc(bal & lt);
-    n2 += __popc(bal);
-    if (!hit) return;
-    if (slot < p.sc_hits_cap) {
-      W.hits[slot] = sp;
-      return;
-    }
-    const int sa = sp & 0xffff, sb = sp >> 16;  // (list full: the lane runs the pair's narrow phase itself)
-#pragma unroll 1
-    for (int k = m.sc_shape_sample0[sa]; k < m.sc_shape_sample0[sa + 1]; ++k) sc_item(m, p, W, sa, sb, k);
-#pragma unroll 1
-    for (int k = m.sc_shape_sample0[sb]; k < m.sc_shape_sample0[sb + 1]; ++k) sc_item(m, p, W, sb, sa, k);
-  };
-  if (n1 <= p.sc_pairs_cap) {
-    for (int h0 = 0; h0 < n1; h0 += 4) {  // 8 lanes per link pair
-      const int h = h0 + (lane >> 3);
-      int q0 = 0, n = 0;
-      if (h < n1) {
-        const int pi = W.pairs[h];
-        q0 = m.sc_pair_sq0[pi];
-        n = m.sc_pair_sq0[pi + 1] - q0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (sc_spheres_overlap(ca[u], cb[u])) {
+        const int at = atomicAdd(&W.count[0], 1);
+        if (at < p.sc_hits_cap) W.hits[at] = (unsigned short)sp[u];
       }
-      for (int t = lane & 7; __any_sync(kFull, t < n); t += 8) shape_pair(q0 + t, t < n);
     }
-  } else {
-    const int nq = m.sc_pair_sq0[m.sc_np];
-    for (int base = 0; base < nq; base += 32) shape_pair(base + lane, base + lane < nq);
   }
   __syncwarp();
-  int nh = 0;  // 2b. oriented boxes; the survivors are compacted in place
-  n2 = min(n2, p.sc_hits_cap);
+  if (W.count[0] > p.sc_hits_cap) {
+    // more overlapping spheres than the list holds (a badly contorted robot): sweep again, plainly, and let every lane
+    // run the narrow phase of its own hits (both ways, all samples); the list is not used
+#pragma unroll 1
+    for (int q = lane; q < m.sc_nq; q += 32) {
+      const int sp = T.sp[q], sa = sp & 0xff, sb = sp >> 8;
+      if (!sc_spheres_overlap(W.shape_c[sa], W.shape_c[sb])) continue;
+      const int xa = T.meta[2 * sa + 1], xb = T.meta[2 * sb + 1];
+#pragma unroll 1
+      for (int k = 0; k < (xa >> 16) + (xb >> 16); ++k) {
+        const bool fwd = k < (xa >> 16);
+        sc_item(T, p, W, fwd ? sa : sb, fwd ? sb : sa, fwd ? (xa & 0xffff) + k : (xb & 0xffff) + k - (xa >> 16));
+      }
+    }
+    __syncwarp();
+    if (lane == 0) W.count[0] = 0;
+  }
+  __syncwarp();
+  const int n2 = min(W.count[0], p.sc_hits_cap);
+  int nh = 0;  // 2. oriented boxes; the survivors are compacted in place
   for (int base = 0; base < n2; base += 32) {
     const int h = base + lane;
     int sp = 0;
     bool keep = false;
     if (h < n2) {
       sp = W.hits[h];
-      keep = !sc_obb_separated(m, W, sp & 0xffff, sp >> 16);
+      keep = !sc_obb_separated(T, W, sp & 0xff, sp >> 8);
     }
     const unsigned bal = __ballot_sync(kFull, keep);  // (also orders this round's reads before its writes)
-    if (keep) W.hits[nh + __popc(bal & lt)] = sp;
+    if (keep) W.hits[nh + __popc(bal & lt)] = (unsigned short)sp;
     nh += __popc(bal);
   }
   __syncwarp();
   for (int h = lane >> 4; h < nh; h += 2) {  // 3. samples against exact shapes, 16 lanes per shape pair
-    const int sp = W.hits[h], sa = sp & 0xffff, sb = sp >> 16;
-    const int ka = m.sc_shape_sample0[sa], na = m.sc_shape_sample0[sa + 1] - ka;
-    const int kb = m.sc_shape_sample0[sb], nb = m.sc_shape_sample0[sb + 1] - kb;
+    const int sp = W.hits[h], sa = sp & 0xff, sb = sp >> 8;
+    const int xa = T.meta[2 * sa + 1], xb = T.meta[2 * sb + 1];
+    const int na = xa >> 16, nb = xb >> 16;
     const int t = lane & 15;
-    if (t < na) sc_item(m, p, W, sa, sb, ka + t);
-    else if (t - na < nb) sc_item(m, p, W, sb, sa, kb + t - na);
+    if (t < na) sc_item(T, p, W, sa, sb, (xa & 0xffff) + t);
+    else if (t - na < nb) sc_item(T, p, W, sb, sa, (xb & 0xffff) + t - na);
   }
   __syncwarp();
-  const bool any_hit = W.any_hit != 0;
+  const bool any_hit = W.count[1] != 0;
   float* out = b.self_contact_force + (size_t)e * m.nb * 3;
   float* net = b.net_contact_force + (size_t)e * m.nb * 3;
   for (int i = lane; i < m.nb * 3; i += 32) {
@@ -752,16 +783,23 @@ __global__ void __launch_bounds__(kScWarps * 32) k_self_collision(DevModel m, Si
     if (any_hit) net[i] += f;
   }
 }
+static size_t sc_smem_bytes(const Sim* sim) {
+  return (size_t)sim->m.sc_hot_words * 4 + (size_t)kScEnvs * sc_env_bytes(sim->m.nl, sim->m.sc_ns, sim->m.nb);
+}
 int launch_self_collision(Sim* sim, cudaStream_t s, bool pdl) {
   if (!has_self_collision(sim)) return 0;
-  if (sim->p.sc_pairs_cap == 0) {
-    // DYROS_SC_TEST_CAPS="pairs,hits": shrinks the two lists so that tests reach the overflow paths on ordinary poses
-    int a = kScPairs, h = kScHits;
-    if (const char* v = getenv("DYROS_SC_TEST_CAPS")) sscanf(v, "%d,%d", &a, &h);
-    sim->p.sc_pairs_cap = std::max(1, std::min(a, kScPairs));
+  if (sim->p.sc_hits_cap == 0) {
+    // DYROS_SC_TEST_CAPS=<hits>: shrinks the hit list so that tests reach the overflow path on ordinary poses
+    int h = kScHits;
+    if (const char* v = getenv("DYROS_SC_TEST_CAPS")) sscanf(v, "%d", &h);
     sim->p.sc_hits_cap = std::max(1, std::min(h, kScHits));
+    DY_CUDA(cudaFuncSetAttribute(k_self_collision, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem_bytes(sim)));
   }
-  DY_CUDA(launch_kernel(k_self_collision, dim3((sim->p.N + kScWarps - 1) / kScWarps), dim3(kScWarps * 32), 0, s, pdl, sim->m, sim->p, sim->b));
+  // (launched WITHOUT the programmatic-serialisation attribute whatever `pdl` says: as a programmatic dependent of the
+  // physics kernel, whose CTAs own whole SMs, this kernel measured ~50 us slower per step; profiles/r2_carveout.md)
+  (void)pdl;
+  DY_CUDA(launch_kernel(k_self_collision, dim3((sim->p.N + kScEnvs - 1) / kScEnvs), dim3(kScEnvs * 32), sc_smem_bytes(sim), s, false,
+                        sim->m, sim->p, sim->b));
   return 0;
 }
 
@@ -814,6 +852,26 @@ int launch_refresh_force_sensors(Sim* sim, const int32_t* sensor_body, const flo
 int launch_refresh_rigid_body_state(Sim* sim, cudaStream_t s) {
   k_rigid_body_state<<<(sim->p.N + 63) / 64, 64, 0, s>>>(sim->m, sim->p, sim->b);
   DY_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) k_fill(uint4* __restrict__ p, size_t n16, unsigned v) {
+  const uint4 x = make_uint4(v, v, v, v);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) p[i] = x;
+}
+int launch_fill(void* buf, size_t bytes, int value, cudaStream_t s) {
+  static bool once = false;
+  if (!once) {
+    DY_CUDA(prefer_max_smem_carveout(k_fill));
+    once = true;
+  }
+  k_fill<<<148 * 8, 256, 0, s>>>(static_cast<uint4*>(buf), bytes / 16, 0x01010101u * (unsigned)(value & 0xff));
+  DY_LAUNCH_CHECK();
+  return 0;
+}
+int configure_physics_aux_kernels() {  // (k_simulate / k_step_physics already take all of the shared memory)
+  DY_CUDA(prefer_max_smem_carveout(k_rigid_body_state)); DY_CUDA(prefer_max_smem_carveout(k_self_collision));
+  DY_CUDA(prefer_max_smem_carveout(k_dof_force)); DY_CUDA(prefer_max_smem_carveout(k_force_sensors));
   return 0;
 }
 

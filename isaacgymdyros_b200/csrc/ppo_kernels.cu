@@ -234,11 +234,25 @@ void dyros_set_error_ppo(const char* msg) { dyros::set_error("%s", msg); }
     }                          \
   } while (0)
 
+namespace dyros {
+static int configure_ppo_kernels() {  // (common.cuh: one carve-out for every kernel of the library)
+  static bool done = false;
+  if (done) return 0;
+  DY_CUDA(prefer_max_smem_carveout(k_ppo_act)); DY_CUDA(prefer_max_smem_carveout(k_ppo_reward));
+  DY_CUDA(prefer_max_smem_carveout(k_ppo_advance)); DY_CUDA(prefer_max_smem_carveout(k_ppo_gae));
+  DY_CUDA(prefer_max_smem_carveout(k_ppo_loss_grad)); DY_CUDA(prefer_max_smem_carveout(k_ppo_gradnorm));
+  DY_CUDA(prefer_max_smem_carveout(k_ppo_adam)); DY_CUDA(prefer_max_smem_carveout(k_ppo_adam_finish));
+  done = true;
+  return 0;
+}
+}  // namespace dyros
+
 extern "C" {
 
 int dyros_ppo_act(const DyrosPpoBuffers* b, const float* mu, const float* value, const float* logstd, const float* obs,
                   const int64_t* reset_buf, float* actions_env, const float* inject_normal, void* stream) {
   PPO_CHECK(b && mu && value && logstd && obs && reset_buf && actions_env, "dyros_ppo_act: null argument");
+  if (configure_ppo_kernels()) return 1;
   k_ppo_act<<<(b->N + 7) / 8, 256, 0, (cudaStream_t)stream>>>(*b, mu, value, logstd, obs, reinterpret_cast<const long long*>(reset_buf),
                                                               actions_env, inject_normal);
   DY_LAUNCH_CHECK();
@@ -246,6 +260,7 @@ int dyros_ppo_act(const DyrosPpoBuffers* b, const float* mu, const float* value,
 }
 int dyros_ppo_reward(const DyrosPpoBuffers* b, const float* rew, const int64_t* timeout, const int64_t* reset_buf, void* stream) {
   PPO_CHECK(b && rew && timeout && reset_buf, "dyros_ppo_reward: null argument");
+  if (configure_ppo_kernels()) return 1;
   k_ppo_reward<<<(b->N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(*b, rew, reinterpret_cast<const long long*>(timeout),
                                                                     reinterpret_cast<const long long*>(reset_buf));
   k_ppo_advance<<<1, 1, 0, (cudaStream_t)stream>>>(*b);
@@ -254,6 +269,7 @@ int dyros_ppo_reward(const DyrosPpoBuffers* b, const float* rew, const int64_t* 
 }
 int dyros_ppo_gae(const DyrosPpoBuffers* b, const float* last_values, const int64_t* last_reset, void* stream) {
   PPO_CHECK(b && last_values && last_reset, "dyros_ppo_gae: null argument");
+  if (configure_ppo_kernels()) return 1;
   k_ppo_gae<<<(b->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*b, last_values, reinterpret_cast<const long long*>(last_reset));
   DY_LAUNCH_CHECK();
   return 0;
@@ -261,6 +277,7 @@ int dyros_ppo_gae(const DyrosPpoBuffers* b, const float* last_values, const int6
 int dyros_ppo_loss_grad(const DyrosPpoBuffers* b, int row0, int mb, const float* mu, const float* value, const float* logstd,
                         const float* adv_norm, float* dmu, float* dvalue, float* stats, void* stream) {
   PPO_CHECK(b && mu && value && logstd && adv_norm && dmu && dvalue && stats, "dyros_ppo_loss_grad: null argument");
+  if (configure_ppo_kernels()) return 1;
   PPO_CHECK(row0 >= 0 && mb > 0 && (long long)row0 + mb <= (long long)b->N * b->H, "dyros_ppo_loss_grad: rows outside the rollout");
   k_ppo_loss_grad<<<(mb + 7) / 8, 256, 0, (cudaStream_t)stream>>>(*b, row0, mb, mu, value, logstd, adv_norm, dmu, dvalue, stats);
   DY_LAUNCH_CHECK();
@@ -270,6 +287,7 @@ int dyros_ppo_adam(float* params, const float* grads, float* exp_avg, float* exp
                    float max_norm, float* norm2_scratch, float* lr_dev, int32_t* step_dev, float beta1, float beta2,
                    float eps, float lr0, float lr_min, int lr_max_steps, void* stream) {
   PPO_CHECK(params && grads && exp_avg && exp_avg_sq && norm2_scratch && lr_dev && step_dev, "dyros_ppo_adam: null argument");
+  if (configure_ppo_kernels()) return 1;
   PPO_CHECK(n_actor >= 0 && n_actor <= n, "dyros_ppo_adam: n_actor outside [0, n]");
   cudaStream_t s = (cudaStream_t)stream;
   if (max_norm > 0.f && n_actor > 0) k_ppo_gradnorm<<<148, 256, 0, s>>>(grads, n_actor, grad_scale, norm2_scratch);

@@ -934,6 +934,15 @@ int launch_check_termination(Task* t, cudaStream_t s) { LAUNCH_ENV(k_check_termi
 int launch_compute_reward(Task* t, cudaStream_t s) { LAUNCH_ENV(k_compute_reward) }
 int launch_compute_observations(Task* t, cudaStream_t s) { LAUNCH_ENV(k_compute_observations) }
 int launch_late_update(Task* t, cudaStream_t s) { LAUNCH_ENV(k_late_update) }
+int configure_task_kernels() {
+  DY_CUDA(prefer_max_smem_carveout(k_prologue)); DY_CUDA(prefer_max_smem_carveout(k_substep_torque));
+  DY_CUDA(prefer_max_smem_carveout(k_sensor_noise)); DY_CUDA(prefer_max_smem_carveout(k_epilogue));
+  DY_CUDA(prefer_max_smem_carveout(k_check_termination)); DY_CUDA(prefer_max_smem_carveout(k_compute_reward));
+  DY_CUDA(prefer_max_smem_carveout(k_compute_observations)); DY_CUDA(prefer_max_smem_carveout(k_late_update));
+  DY_CUDA(prefer_max_smem_carveout(k_reset_idx)); DY_CUDA(prefer_max_smem_carveout(k_pack_results));
+  DY_CUDA(prefer_max_smem_carveout(k_post_fused)); DY_CUDA(prefer_max_smem_carveout(k_crossenv));
+  return 0;
+}
 int launch_post_fused(Task* t, cudaStream_t s, bool pdl, bool tail) {
   DY_CUDA(launch_kernel(k_post_fused, dim3((t->p.N + kPostWarps - 1) / kPostWarps), dim3(kPostWarps * 32), 0, s, pdl, make_tk(t), (int)tail));
   return 0;

@@ -123,12 +123,14 @@ SIGNATURES = {
     "dyros_refresh_dof_force": (_INT, [_VP, _VP, _VP]),
     "dyros_refresh_force_sensors": (_INT, [_VP, _VP, _VP, _INT, _VP, _VP]),
     "dyros_measure_fp32_peak": (_INT, [_INT, _INT, C.POINTER(C.c_double)]),
+    "dyros_flush_l2": (_INT, [C.c_void_p, C.c_size_t, _INT, C.c_void_p]),
     "dyros_sim_launch_info": (_INT, [_VP, C.POINTER(C.c_int32 * 4)]),
     "dyros_task_create": (_INT, [_VP, C.POINTER(DyrosTaskDesc), C.POINTER(DyrosTaskBuffers), C.POINTER(_VP)]),
     "dyros_task_destroy": (_INT, [_VP]),
     "dyros_task_set_noise_injection": (_INT, [_VP, C.POINTER(DyrosNoiseInjection)]),
     "dyros_task_prologue": (_INT, [_VP, _VP, _VP]),
     "dyros_task_physics": (_INT, [_VP, _VP]),
+    "dyros_task_physics_kernel": (_INT, [_VP, _VP]),
     "dyros_task_physics_trace": (_INT, [_VP, _VP, _VP]),
     "dyros_task_prologue_physics": (_INT, [_VP, _VP, _VP, _VP]),
     "dyros_task_substep_torque": (_INT, [_VP, _VP]),

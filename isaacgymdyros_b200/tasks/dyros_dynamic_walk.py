@@ -68,7 +68,10 @@ def core_config_from_cfg(cfg: Dict[str, Any]) -> CoreConfig:
                    num_velocity_iterations=px.get("num_velocity_iterations", 1),
                    death_cost=env.get("deathCost", 0.0), initial_height=env.get("initialHieght", 0.93),
                    env_spacing=env.get("envSpacing", 5), perturb=env.get("perturbation", False),
-                   randomize=task.get("randomize", False))
+                   randomize=task.get("randomize", False),
+                   # (not a key of the reference's yaml: the reference always creates the actor with collision filter 0,
+                   # T:354; `selfCollision: False` drops the self-collision pass, e.g. to time the step without it)
+                   self_collision=env.get("selfCollision", True))
     ap = task.get("randomization_params", {}).get("actor_params", {}).get("humanoid", {})
     dp = ap.get("dof_properties", {})
     if "damping" in dp:
