@@ -62,6 +62,10 @@ def parse():
     ap.add_argument("--force-perturb", action="store_true", help="pushes forced on (BASELINE configs[3]; T:491)")
     ap.add_argument("--dr-extra", action="store_true",
                     help="also randomise friction x[0.7,1.3] and the PD gains x[0.9,1.1] per env (BASELINE configs[3])")
+    ap.add_argument("--physics-program", default="roles", choices=["roles", "lanes"],
+                    help="roles: one lane per env (default); lanes: 8 lanes per env (DESIGN.md section 4, the measured negative result)")
+    ap.add_argument("--no-self-collision", action="store_true",
+                    help="drop k_self_collision (the reference always has it: create_actor filter 0, T:354)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--workload", default="env", choices=["env", "ppo"],
                     help="env: the env-step hot path (BASELINE configs[1], the default and the driver's line); ppo: end-to-end "
@@ -239,6 +243,8 @@ def run_ours(a):
     N, K, W = a.envs, a.steps, max(a.warmup, 3)
     extra = dict(friction_range=(0.7, 1.3), pd_gain_range=(0.9, 1.1)) if a.dr_extra else {}
     cfg = default_cfg(N, **extra)
+    cfg["env"]["physicsProgram"] = a.physics_program
+    cfg["env"]["selfCollision"] = not a.no_self_collision
     # tickets in flight for step_async: 3 hides the host's reaction time when the PCIe link of ONE GPU is the limit
     # (155 vs 172 us per step); with more ranks the host's memory system is the limit (8 ranks: ~112 GB/s of device->host
     # writes in total) and fewer, cache-resident host blocks do better (8 ranks: 56.9 M with 2, 51.4 M with 3;
@@ -412,6 +418,7 @@ def run_ours(a):
             "config": {"workload": WORKLOAD, "envs_per_gpu": N, "actions": "torch.rand(N,13)*2-1, seed 42",
                        "domain_randomisation": "mass, damping, armature, friction, PD gains" if a.dr_extra else "mass, damping, armature (CFG:81-115)",
                        "perturbation": "forced on (T:491)" if a.force_perturb else "gated as in the reference (T:489)",
+                       "self_collision": not a.no_self_collision, "physics_program": a.physics_program,
                        "l2": "flushed between timed steps (256 MiB fill outside the timed intervals, by a kernel with the step kernels' L1 / shared-memory split: dyros_flush_l2)",
                        "timing": "CUDA events per step on the launch stream, summed; max over ranks",
                        "launch_geometry": dict(core.launch_info(), threads_per_cta_fused_step=256), "reset_rate_last_step": reset_rate},

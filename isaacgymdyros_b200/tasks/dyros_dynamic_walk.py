@@ -71,7 +71,8 @@ def core_config_from_cfg(cfg: Dict[str, Any]) -> CoreConfig:
                    randomize=task.get("randomize", False),
                    # (not a key of the reference's yaml: the reference always creates the actor with collision filter 0,
                    # T:354; `selfCollision: False` drops the self-collision pass, e.g. to time the step without it)
-                   self_collision=env.get("selfCollision", True))
+                   self_collision=env.get("selfCollision", True),
+                   physics_program=env.get("physicsProgram", "roles"))  # (ours too: DESIGN.md section 4, "Two programs")
     ap = task.get("randomization_params", {}).get("actor_params", {}).get("humanoid", {})
     dp = ap.get("dof_properties", {})
     if "damping" in dp:
