@@ -364,6 +364,54 @@ int dyros_ppo_adam(float* params, const float* grads, float* exp_avg, float* exp
                    float max_norm, float* norm2_scratch, float* lr_dev, int32_t* step_dev, float beta1, float beta2,
                    float eps, float lr0, float lr_min, int lr_max_steps, void* stream);
 
+
+/* ---- packed bf16 path of the two MLPs (network_builder_dyros.py:129-216: separate 487-H-H actor and critic): one batch-2
+ * problem in GEMM layout, net 0 = actor, net 1 = critic. The caller runs the 8 batched GEMMs of a minibatch with a
+ * library (3 forward: x W0^T, h0 W1^T, h1 Wh^T; 5 backward); these entry points are everything between them. Weights
+ * and activations bf16 (where the reference trains under fp16 autocast + GradScaler, PPO:59), biases, bias gradients,
+ * master parameters, Adam moments fp32. The flat master layout (dyros_ppo_adam's buffers) is, per net,
+ * [W0 (H x 487), b0 (H), W1 (H x H), b1 (H), Wh (nout x H), bh (nout)], nout = 13 (actor) then 1 (critic). */
+typedef struct DyrosPpoNet {
+  int32_t hidden;        /* H, a multiple of 8 (256: PPO:28-35) */
+  void* w0;              /* bf16 [2][H][488]: 487 inputs padded to 488 (column 487 is zero) */
+  float* b0;             /* [2][H] */
+  void* w1;              /* bf16 [2][H][H] */
+  float* b1;             /* [2][H] */
+  void* wh;              /* bf16 [2][16][H]: rows 0..12 of net 0 = mu, row 0 of net 1 = value, the rest zero */
+  float* bh;             /* [2][16] */
+  void* gw0;             /* bf16 gradients in the same layouts (GEMM outputs) */
+  void* gw1;
+  void* gwh;
+  float* gb0;            /* fp32 bias gradients, accumulated by dyros_ppo_relu_bwd / dyros_ppo_loss_grad_packed, */
+  float* gb1;            /* zeroed by dyros_ppo_unpack_grads */
+  float* gbh;
+} DyrosPpoNet;
+/* obs (N,487) fp32 -> bf16 rows of width 488: x_step (N,488) for this step's policy forward and, if x_roll is given,
+ * row e*H + *step of the env-major rollout store (N*H,488). */
+int dyros_ppo_cast_obs(const DyrosPpoBuffers* b, const float* obs, void* x_step, void* x_roll, void* stream);
+/* t [2][rows][H] bf16 = relu(t + bias [2][H]) in place (the hidden layers' activation, network_builder_dyros.py:132-146). */
+int dyros_ppo_bias_relu(void* t, const float* bias, int rows, int hidden, void* stream);
+/* g [2][rows][H] bf16 = (h > 0 ? g : 0) in place; gbias [2][H] += column sums of the result. */
+int dyros_ppo_relu_bwd(void* g, const void* h, float* gbias, int rows, int hidden, void* stream);
+/* dyros_ppo_act on the packed head output out [2][N][16] bf16 (without bias) and bh [2][16]; does not store obs. */
+int dyros_ppo_act_packed(const DyrosPpoBuffers* b, const void* out, const float* bh, const float* logstd, const int64_t* reset_buf,
+                         float* actions_env, const float* inject_normal, void* stream);
+/* dyros_ppo_loss_grad on the packed head output of rows [row0, row0+mb): writes dout [2][mb][16] bf16, accumulates gbh,
+ * refreshes the rows' stored mu (dataset.update_mu_sigma, A2C:884) and stats[4]. */
+int dyros_ppo_loss_grad_packed(const DyrosPpoBuffers* b, int row0, int mb, const void* out, const float* bh, const float* logstd,
+                               const float* adv_norm, void* dout, float* gbh, float* stats, void* stream);
+/* flat fp32 master parameters -> packed weights / biases (after every optimiser step). */
+int dyros_ppo_pack_params(const DyrosPpoNet* net, const float* flat, void* stream);
+/* packed gradients -> flat fp32 master gradient (what the all-reduce and the optimiser see); zeroes gb0 / gb1 / gbh.
+ * norm2_accum (optional): += squared norm of the actor's gradients (the clip_grad_norm_ reduction of AG:179 folded in;
+ * only meaningful when no all-reduce follows, i.e. on a single rank). */
+int dyros_ppo_unpack_grads(const DyrosPpoNet* net, float* flat_grad, float* norm2_accum, void* stream);
+/* dyros_ppo_adam that also refreshes the packed copy of every parameter it updates (dyros_ppo_pack_params folded in).
+ * norm_done != 0: norm2_scratch already holds the squared norm of the actor's (unscaled) gradients. */
+int dyros_ppo_adam_packed(const DyrosPpoNet* net, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float grad_scale,
+                          float max_norm, int norm_done, float* norm2_scratch, float* lr_dev, int32_t* step_dev, float beta1, float beta2,
+                          float eps, float lr0, float lr_min, int lr_max_steps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,14 +103,27 @@ class DyrosPpoBuffers(C.Structure):
                                   "cur_reward", "cur_length", "ep_stats", "step", "global_step")]
 
 
+class DyrosPpoNet(C.Structure):
+    _fields_ = [("hidden", i32)] + [(n, C.c_void_p) for n in ("w0", "b0", "w1", "b1", "wh", "bh", "gw0", "gw1", "gwh", "gb0", "gb1", "gbh")]
+
+
 _VP, _INT = C.c_void_p, C.c_int
 _PB = C.POINTER(DyrosPpoBuffers)
+_PN = C.POINTER(DyrosPpoNet)
 SIGNATURES = {
     "dyros_ppo_act": (_INT, [_PB, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "dyros_ppo_reward": (_INT, [_PB, _VP, _VP, _VP, _VP]),
     "dyros_ppo_gae": (_INT, [_PB, _VP, _VP, _VP]),
     "dyros_ppo_loss_grad": (_INT, [_PB, _INT, _INT, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "dyros_ppo_adam": (_INT, [_VP, _VP, _VP, _VP, _INT, _INT, f32, f32, _VP, _VP, _VP, f32, f32, f32, f32, f32, _INT, _VP]),
+    "dyros_ppo_cast_obs": (_INT, [_PB, _VP, _VP, _VP, _VP]),
+    "dyros_ppo_bias_relu": (_INT, [_VP, _VP, _INT, _INT, _VP]),
+    "dyros_ppo_relu_bwd": (_INT, [_VP, _VP, _VP, _INT, _INT, _VP]),
+    "dyros_ppo_act_packed": (_INT, [_PB, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "dyros_ppo_loss_grad_packed": (_INT, [_PB, _INT, _INT, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "dyros_ppo_pack_params": (_INT, [_PN, _VP, _VP]),
+    "dyros_ppo_unpack_grads": (_INT, [_PN, _VP, _VP, _VP]),
+    "dyros_ppo_adam_packed": (_INT, [_PN, _VP, _VP, _VP, _VP, f32, f32, _INT, _VP, _VP, _VP, f32, f32, f32, f32, f32, _INT, _VP]),
     "dyros_last_error": (C.c_char_p, []),
     "dyros_abi_version": (_INT, []),
     "dyros_sim_set_l2_persistence": (_INT, [_VP, _VP, C.c_size_t, _VP, C.POINTER(C.c_size_t)]),

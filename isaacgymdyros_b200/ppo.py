@@ -7,8 +7,13 @@ the rollout buffers, GAE, the loss gradient and both optimisers are kernels of l
 one rollout step and one minibatch update are each ONE CUDA graph, and with several ranks the only traffic is one NCCL
 all-reduce of the flat 1.54 MB gradient bucket per minibatch (AG:161-203) plus a few scalars per epoch.
 
-The two 487-256-256-{13,1} MLPs are library GEMMs (torch / cuBLAS, bf16 autocast where the reference uses fp16
-autocast + GradScaler, PPO:59); parameters, gradients and Adam moments live in flat fp32 buffers."""
+The two 487-256-256-{13,1} MLPs are library GEMMs (torch / cuBLAS); parameters, gradients and Adam moments live in flat
+fp32 buffers. Two network paths:
+  * `mixed_precision="bf16"` (default; the reference trains under fp16 autocast + GradScaler, PPO:59): `PackedNets` --
+    actor and critic as ONE batch-2 problem in GEMM layout (bf16 weights, input width padded 487 -> 488), 8 batched
+    GEMMs per minibatch with hand-written backward and the library's own kernels in between (csrc/ppo_kernels.cu,
+    "packed bf16 path"): 21 launches per minibatch instead of 79;
+  * `mixed_precision="fp32"`: torch autograd on views of the flat buffers (what the tests pin against the oracle)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -117,6 +122,84 @@ class FlatActorCritic:
         return mu, v.squeeze(-1)
 
 
+class PackedNets:
+    """bf16 compute copies of the flat master parameters in GEMM layout (include/dyros_b200.h DyrosPpoNet) and the
+    forward / backward of both networks as batch-2 GEMMs. Activations of the last `forward` are kept for `backward`."""
+    K0, HEAD = 488, 16
+
+    def __init__(self, net: FlatActorCritic, lib):
+        if len(net.cfg.units) != 2 or net.cfg.units[0] != net.cfg.units[1] or net.cfg.units[0] % 8:
+            raise ValueError("the packed path holds two hidden layers of equal width (a multiple of 8), PPO:28-35")
+        self.net, self.lib, dev = net, lib, net.device
+        Hd = self.hidden = net.cfg.units[0]
+        zb = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)
+        zf = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        self.w0, self.w1, self.wh = zb(2, Hd, self.K0), zb(2, Hd, Hd), zb(2, self.HEAD, Hd)
+        self.b0, self.b1, self.bh = zf(2, Hd), zf(2, Hd), zf(2, self.HEAD)
+        self.gw0, self.gw1, self.gwh = zb(2, Hd, self.K0), zb(2, Hd, Hd), zb(2, self.HEAD, Hd)
+        self.gb0, self.gb1, self.gbh = zf(2, Hd), zf(2, Hd), zf(2, self.HEAD)
+        d = native.DyrosPpoNet()
+        d.hidden = Hd
+        for k in ("w0", "b0", "w1", "b1", "wh", "bh", "gw0", "gw1", "gwh", "gb0", "gb1", "gbh"):
+            setattr(d, k, getattr(self, k).data_ptr())
+        self.desc = d
+        self._act = {}   # rows -> (h0, h1, out, dout, t1, t0) work buffers
+        self.pack()
+
+    @property
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.net.device).cuda_stream)
+
+    def pack(self):
+        native.check(self.lib.dyros_ppo_pack_params(C.byref(self.desc), C.c_void_p(self.net.flat.data_ptr()), self._stream), "pack")
+
+    def unpack_grads(self, norm2: Optional[torch.Tensor] = None):
+        native.check(self.lib.dyros_ppo_unpack_grads(C.byref(self.desc), C.c_void_p(self.net.grad.data_ptr()),
+                                                     C.c_void_p(norm2.data_ptr()) if norm2 is not None else None, self._stream), "unpack")
+
+    def _buffers(self, rows: int):
+        b = self._act.get(rows)
+        if b is None:
+            dev, Hd = self.net.device, self.hidden
+            zb = lambda *s: torch.empty(*s, dtype=torch.bfloat16, device=dev)
+            b = {"h0": zb(2, rows, Hd), "h1": zb(2, rows, Hd), "out": zb(2, rows, self.HEAD), "dout": zb(2, rows, self.HEAD),
+                 "d1": zb(2, rows, Hd), "d0": zb(2, rows, Hd)}
+            self._act[rows] = b
+        return b
+
+    def forward(self, x: torch.Tensor):
+        """x (rows, 488) bf16 -> head output (2, rows, 16) bf16 WITHOUT the head bias (the consumers add `bh`)."""
+        rows = x.shape[0]
+        b, s, lib = self._buffers(rows), self._stream, self.lib
+        xe = x.unsqueeze(0).expand(2, rows, self.K0)
+        torch.bmm(xe, self.w0.transpose(1, 2), out=b["h0"])
+        native.check(lib.dyros_ppo_bias_relu(C.c_void_p(b["h0"].data_ptr()), C.c_void_p(self.b0.data_ptr()), rows, self.hidden, s), "bias_relu")
+        torch.bmm(b["h0"], self.w1.transpose(1, 2), out=b["h1"])
+        native.check(lib.dyros_ppo_bias_relu(C.c_void_p(b["h1"].data_ptr()), C.c_void_p(self.b1.data_ptr()), rows, self.hidden, s), "bias_relu")
+        torch.bmm(b["h1"], self.wh.transpose(1, 2), out=b["out"])
+        return b["out"]
+
+    def backward(self, x: torch.Tensor):
+        """Given `dout` (filled by dyros_ppo_loss_grad_packed for the rows of the last forward): all weight gradients
+        (bf16, GEMM layout) and bias gradients (fp32, accumulated)."""
+        rows = x.shape[0]
+        b, s, lib = self._buffers(rows), self._stream, self.lib
+        xe = x.unsqueeze(0).expand(2, rows, self.K0)
+        torch.bmm(b["dout"].transpose(1, 2), b["h1"], out=self.gwh)                       # (2,16,H)
+        torch.bmm(b["dout"], self.wh, out=b["d1"])                                        # (2,rows,H)
+        native.check(lib.dyros_ppo_relu_bwd(C.c_void_p(b["d1"].data_ptr()), C.c_void_p(b["h1"].data_ptr()),
+                                            C.c_void_p(self.gb1.data_ptr()), rows, self.hidden, s), "relu_bwd")
+        torch.bmm(b["d1"].transpose(1, 2), b["h0"], out=self.gw1)                         # (2,H,H)
+        torch.bmm(b["d1"], self.w1, out=b["d0"])
+        native.check(lib.dyros_ppo_relu_bwd(C.c_void_p(b["d0"].data_ptr()), C.c_void_p(b["h0"].data_ptr()),
+                                            C.c_void_p(self.gb0.data_ptr()), rows, self.hidden, s), "relu_bwd")
+        torch.bmm(b["d0"].transpose(1, 2), xe, out=self.gw0)                              # (2,H,488)
+
+    def mu_value(self, out: torch.Tensor):
+        """fp32 (rows,13) mu and (rows) value of a head output (tests, the bootstrap value of the last observation)."""
+        return out[0, :, :NA].float() + self.bh[0, :NA], out[1, :, 0].float() + self.bh[1, 0]
+
+
 class PPOTrainer:
     def __init__(self, env, cfg: Optional[PPOConfig] = None, rank: int = 0, world: int = 1):
         self.env, self.cfg = env, cfg or PPOConfig()
@@ -133,7 +216,11 @@ class PPOTrainer:
             import torch.distributed as dist
             dist.broadcast(self.net.flat, 0)
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
-        self.buf = {"obs": z(N, H, NOBS), "actions": z(N, H, NA), "mus": z(N, H, NA), "neglogp": z(N, H), "values": z(N, H),
+        self.packed: Optional[PackedNets] = PackedNets(self.net, self.lib) if c.mixed_precision == "bf16" else None
+        if self.packed is not None:  # the rollout's observations are kept as the bf16 rows the GEMMs read (N*H x 488)
+            self.x_step = z(N, PackedNets.K0, dt=torch.bfloat16)
+            self.x_roll = z(N * H, PackedNets.K0, dt=torch.bfloat16)
+        self.buf = {"obs": z(N, H, NOBS) if self.packed is None else z(1), "actions": z(N, H, NA), "mus": z(N, H, NA), "neglogp": z(N, H), "values": z(N, H),
                     "rewards": z(N, H), "dones": z(N, H), "advantages": z(N, H), "returns": z(N, H), "cur_reward": z(N),
                     "cur_length": z(N), "ep_stats": z(3), "step": z(1, dt=torch.int32), "global_step": z(1, dt=torch.int64)}
         pb = native.DyrosPpoBuffers()
@@ -164,7 +251,24 @@ class PPOTrainer:
         return C.c_void_p(t.data_ptr()) if t is not None else None
 
     # ------------------------------------------------------------------ rollout (A2C:629-703)
+    def _cast_obs(self, into_rollout: bool):
+        native.check(self.lib.dyros_ppo_cast_obs(C.byref(self.pb), self._p(self.env.obs_buf), self._p(self.x_step),
+                                                 self._p(self.x_roll) if into_rollout else None, self._stream), "dyros_ppo_cast_obs")
+
+    def _rollout_step_packed(self):
+        env, pk = self.env, self.packed
+        self._cast_obs(True)
+        out = pk.forward(self.x_step)
+        native.check(self.lib.dyros_ppo_act_packed(C.byref(self.pb), self._p(out), self._p(pk.bh), self._p(self.net.logstd),
+                                                   self._p(env.reset_buf), self._p(self.actions), self._p(self.inject_normal),
+                                                   self._stream), "dyros_ppo_act_packed")
+        env.core.step(self.actions)
+        native.check(self.lib.dyros_ppo_reward(C.byref(self.pb), self._p(env.rew_buf), self._p(env.timeout_buf),
+                                               self._p(env.reset_buf), self._stream), "dyros_ppo_reward")
+
     def _rollout_step(self):
+        if self.packed is not None:
+            return self._rollout_step_packed()
         env = self.env
         with torch.no_grad():
             mu, v = self.net.forward(env.obs_buf)
@@ -194,9 +298,13 @@ class PPOTrainer:
                 self._g_rollout.replay()
             else:
                 self._rollout_step()
-        with torch.no_grad():
-            _, last_v = self.net.forward(self.env.obs_buf)   # get_values(self.obs), A2C:686
-            last_v = last_v.float().contiguous()
+        with torch.no_grad():                                # get_values(self.obs), A2C:686
+            if self.packed is not None:
+                self._cast_obs(False)
+                last_v = self.packed.mu_value(self.packed.forward(self.x_step))[1].contiguous()
+            else:
+                _, last_v = self.net.forward(self.env.obs_buf)
+                last_v = last_v.float().contiguous()
         native.check(self.lib.dyros_ppo_gae(C.byref(self.pb), self._p(last_v), self._p(self.env.reset_buf), self._stream), "dyros_ppo_gae")
 
     # ------------------------------------------------------------------ update (A2C:921-969, A2C:862-903, AG:108-227)
@@ -207,7 +315,41 @@ class PPOTrainer:
         else:
             self.adv_norm.copy_(adv)
 
+    def _optimiser_step(self):
+        c, n = self.cfg, self.net
+        if self.world > 1:  # optimizer.synchronize(): one all-reduce of the flat bucket (AG:161-173)
+            import torch.distributed as dist
+            dist.all_reduce(n.grad)
+        native.check(self.lib.dyros_ppo_adam(self._p(n.flat), self._p(n.grad), self._p(n.exp_avg), self._p(n.exp_avg_sq), n.n_actor, n.n,
+                                             1.0 / self.world, c.grad_norm if c.truncate_grads else 0.0, self._p(self.norm2),
+                                             self._p(self.lr), self._p(self.opt_step), 0.9, 0.999, 1e-8, c.learning_rate,
+                                             c.learning_rate_min, c.max_epochs if c.lr_schedule == "linear" else 0,
+                                             self._stream), "dyros_ppo_adam")
+
+    def _minibatch_packed(self, i: int):
+        pk, mb = self.packed, self.cfg.minibatch_size
+        r0 = i * mb
+        x = self.x_roll[r0:r0 + mb]
+        out = pk.forward(x)
+        native.check(self.lib.dyros_ppo_loss_grad_packed(C.byref(self.pb), r0, mb, self._p(out), self._p(pk.bh), self._p(self.net.logstd),
+                                                         self._p(self.adv_norm), self._p(pk._buffers(mb)["dout"]), self._p(pk.gbh),
+                                                         self._p(self.stats), self._stream), "dyros_ppo_loss_grad_packed")
+        pk.backward(x)
+        c, n, single = self.cfg, self.net, self.world == 1
+        clip = c.grad_norm if c.truncate_grads else 0.0
+        pk.unpack_grads(self.norm2 if single and clip > 0 else None)   # (single rank: the norm reduction rides along)
+        if not single:  # optimizer.synchronize(): one all-reduce of the flat bucket (AG:161-173)
+            import torch.distributed as dist
+            dist.all_reduce(n.grad)
+        native.check(self.lib.dyros_ppo_adam_packed(C.byref(pk.desc), self._p(n.flat), self._p(n.grad), self._p(n.exp_avg),
+                                                    self._p(n.exp_avg_sq), 1.0 / self.world, clip, int(single), self._p(self.norm2),
+                                                    self._p(self.lr), self._p(self.opt_step), 0.9, 0.999, 1e-8, c.learning_rate,
+                                                    c.learning_rate_min, c.max_epochs if c.lr_schedule == "linear" else 0,
+                                                    self._stream), "dyros_ppo_adam_packed")
+
     def _minibatch(self, i: int):
+        if self.packed is not None:
+            return self._minibatch_packed(i)
         c, mb = self.cfg, self.cfg.minibatch_size
         r0 = i * mb
         obs = self.buf["obs"].view(self.N * self.H, NOBS)[r0:r0 + mb]
@@ -218,15 +360,7 @@ class PPOTrainer:
                                                   self._p(self.stats), self._stream), "dyros_ppo_loss_grad")
         self.net.grad.zero_()
         torch.autograd.backward([mu, v], [self.mb_dmu.to(mu.dtype), self.mb_dv.to(v.dtype)])
-        if self.world > 1:  # optimizer.synchronize(): one all-reduce of the flat bucket (AG:161-173)
-            import torch.distributed as dist
-            dist.all_reduce(self.net.grad)
-        n = self.net
-        native.check(self.lib.dyros_ppo_adam(self._p(n.flat), self._p(n.grad), self._p(n.exp_avg), self._p(n.exp_avg_sq), n.n_actor, n.n,
-                                             1.0 / self.world, c.grad_norm if c.truncate_grads else 0.0, self._p(self.norm2),
-                                             self._p(self.lr), self._p(self.opt_step), 0.9, 0.999, 1e-8, c.learning_rate,
-                                             c.learning_rate_min, c.max_epochs if c.lr_schedule == "linear" else 0,
-                                             self._stream), "dyros_ppo_adam")
+        self._optimiser_step()
         # dataset.update_mu_sigma (A2C:884): later mini-epochs measure the KL against this pass
         self.buf["mus"].view(self.N * self.H, NA)[r0:r0 + mb].copy_(mu32.detach())
 
@@ -248,6 +382,8 @@ class PPOTrainer:
                         for t, s in zip((self.net.flat, self.net.exp_avg, self.net.exp_avg_sq, self.opt_step, self.lr, self.stats,
                                          self.buf["mus"]), snap):
                             t.copy_(s)
+                        if self.packed is not None:
+                            self.packed.pack()
                     side = torch.cuda.Stream(device=self.env.device)
                     side.wait_stream(torch.cuda.current_stream())
                     g = torch.cuda.CUDAGraph()

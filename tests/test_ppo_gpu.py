@@ -223,3 +223,84 @@ def test_training_epochs_run_on_device_bf16():
     assert episodes > 0
     assert out["lr"] < 1e-5                                          # the per-minibatch linear schedule moved
     env.close()
+
+
+def test_packed_bf16_networks_match_the_fp32_networks():
+    """The packed bf16 path (PackedNets + csrc 'packed bf16 path': batch-2 GEMMs, hand-written backward) against torch
+    autograd on the fp32 master parameters, same minibatch: head outputs, loss gradients of every parameter, logged
+    losses. Both hold identical (bf16-representable) weights, so what differs is the bf16 rounding of the activations:
+    0.4 % per value, and ReLU masks that flip where a pre-activation is within that of zero (measured: 0.1 % of the
+    critic's hidden units x rows, which alone costs 1e-3 of cosine); hence cosine > 0.997 and max error < 0.2 x the
+    largest entry for the gradients, 2 % of the largest entry for the outputs."""
+    import ctypes as C
+    from isaacgymdyros_b200 import native
+    from isaacgymdyros_b200.ppo import FlatActorCritic
+    env, tr = make_trainer(N=64, H=16, mb=256)                       # mixed_precision defaults to bf16 -> packed
+    assert tr.packed is not None
+    pk = tr.packed
+    g = torch.Generator(device=DEV); g.manual_seed(9)
+    r = lambda *s: torch.randn(*s, device=DEV, generator=g)
+    # larger-than-init weights so that every layer matters, non-zero biases
+    # (rounded to bf16 so that both paths hold identical weights: what is compared is the arithmetic, not the cast)
+    tr.net.flat.copy_((tr.net.flat * 30 + 0.02 * r(tr.net.n)).to(torch.bfloat16).float())
+    pk.pack()
+    N, H, mb, r0 = tr.N, tr.H, 256, 512
+    obs = r(N * H, 487)
+    tr.x_roll[:, :487] = obs.to(torch.bfloat16); tr.x_roll[:, 487] = 0
+    b = tr.buf
+    b["mus"].copy_(0.3 * r(N, H, 13)); b["actions"].copy_(b["mus"] + 0.12 * r(N, H, 13))
+    b["neglogp"].copy_(PO.neglogp(b["actions"], b["mus"], tr.net.logstd) + 0.3 * r(N, H))
+    b["values"].copy_(r(N, H)); b["returns"].copy_(b["values"] + r(N, H)); b["advantages"].copy_(b["returns"] - b["values"])
+    tr._prepare()
+    batch = oracle_batch(tr, r0, mb)
+    # ---- fp32 autograd on the same (bf16-rounded) inputs
+    import dataclasses
+    onet = FlatActorCritic(DEV, dataclasses.replace(tr.cfg, mixed_precision="fp32"))
+    onet.flat.copy_(tr.net.flat)
+    x32 = tr.x_roll[r0:r0 + mb, :487].float()
+    mu, v = onet.forward(x32)
+    loss, a_loss, c_loss, kl, cf = PO.total_loss(mu, v, onet.logstd, batch, 0.2, 0.5)
+    onet.grad.zero_()
+    loss.backward()
+    # ---- packed
+    x = tr.x_roll[r0:r0 + mb]
+    out = pk.forward(x)
+    mu_p, v_p = pk.mu_value(out)
+    scale = lambda t: float(t.abs().max())
+    assert float((mu_p - mu).abs().max()) < 2e-2 * scale(mu) and float((v_p - v).abs().max()) < 2e-2 * scale(v)
+    tr.stats.zero_()
+    native.check(tr.lib.dyros_ppo_loss_grad_packed(C.byref(tr.pb), r0, mb, tr._p(out), tr._p(pk.bh), tr._p(tr.net.logstd), tr._p(tr.adv_norm),
+                                                   tr._p(pk._buffers(mb)["dout"]), tr._p(pk.gbh), tr._p(tr.stats), tr._stream), "loss_grad_packed")
+    pk.backward(x)
+    pk.unpack_grads()
+    torch.cuda.synchronize()
+    assert float(pk.gb0.abs().max()) == 0.0 and float(pk.gbh.abs().max()) == 0.0      # accumulators are left zeroed
+    assert torch.allclose(b["mus"].reshape(-1, 13)[r0:r0 + mb], mu_p, atol=1e-6)      # dataset.update_mu_sigma
+    for name, (w, bias) in onet.layers.items():
+        gw, gb = tr.net.layers[name][0].grad, tr.net.layers[name][1].grad
+        for got, want, what in ((gw, w.grad, "weight"), (gb, bias.grad, "bias")):
+            err = float((got - want).abs().max())
+            cos = float((got * want).sum() / (got.norm() * want.norm() + 1e-30))
+            assert err < 0.2 * scale(want) + 1e-12, (name, what, err, scale(want))
+            assert cos > 0.997, (name, what, cos)
+    for x_, y_ in zip(tr.stats.tolist(), (a_loss.item(), c_loss.item(), kl.item(), cf.item())):
+        assert x_ == pytest.approx(y_, rel=5e-2, abs=2e-3)
+    # ---- the optimiser on the packed path (norm folded into the unpack, pack folded into Adam) against dyros_ppo_adam
+    grad = tr.net.grad.clone()
+    ref = {k: t.clone() for k, t in (("p", tr.net.flat), ("m", tr.net.exp_avg), ("v", tr.net.exp_avg_sq))}
+    lr2, st2, n2 = tr.lr.clone(), tr.opt_step.clone(), torch.zeros(1, device=DEV)
+    grad.mul_(100.0)                                                 # large enough for the actor clip (0.5) to bite
+    native.check(tr.lib.dyros_ppo_adam(tr._p(ref["p"]), tr._p(grad), tr._p(ref["m"]), tr._p(ref["v"]), tr.net.n_actor, tr.net.n, 0.5, 0.5,
+                                       tr._p(n2), tr._p(lr2), tr._p(st2), 0.9, 0.999, 1e-8, 1e-5, 3e-6, 5000, tr._stream), "adam")
+    tr.net.grad.copy_(grad)
+    tr.norm2.copy_((grad[:tr.net.n_actor] ** 2).sum().reshape(1))    # what dyros_ppo_unpack_grads(norm2_accum) leaves
+    native.check(tr.lib.dyros_ppo_adam_packed(C.byref(pk.desc), tr._p(tr.net.flat), tr._p(tr.net.grad), tr._p(tr.net.exp_avg),
+                                              tr._p(tr.net.exp_avg_sq), 0.5, 0.5, 1, tr._p(tr.norm2), tr._p(tr.lr), tr._p(tr.opt_step),
+                                              0.9, 0.999, 1e-8, 1e-5, 3e-6, 5000, tr._stream), "adam_packed")
+    torch.cuda.synchronize()
+    assert torch.allclose(tr.net.flat, ref["p"], rtol=1e-6, atol=1e-9) and torch.allclose(tr.net.exp_avg_sq, ref["v"], rtol=1e-5, atol=1e-12)
+    assert float((tr.net.flat - ref["p"]).abs().max()) < 1e-8 and tr.lr[0].item() == pytest.approx(lr2[0].item(), rel=1e-6)
+    w0 = tr.net.layers["critic_mlp.0"][0]
+    assert torch.equal(pk.w0[1, :, :487].float(), w0.detach().to(torch.bfloat16).float()) and float(pk.w0[:, :, 487].abs().max()) == 0.0
+    assert torch.equal(pk.bh[0, :13], tr.net.layers["mu"][1].detach()) and float(pk.wh[0, 13:].abs().max()) == 0.0
+    env.close()

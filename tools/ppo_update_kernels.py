@@ -8,6 +8,7 @@ N = 4096
 env = DyrosDynamicWalk(default_cfg(N), "cuda:0", use_cuda_graph=False)
 tr = PPOTrainer(env, PPOConfig(horizon_length=8, minibatch_size=4096, use_cuda_graph=False))
 tr.rollout(); tr._prepare()
+print('packed' if tr.packed is not None else 'autograd')
 for i in range(3):
     tr._minibatch(i)
 torch.cuda.synchronize()
