@@ -72,6 +72,8 @@ def parse():
                          "on-device PPO training (BASELINE configs[4]): --steps / --warmup count EPOCHS of 128 env steps + 640 updates")
     ap.add_argument("--horizon", type=int, default=128)
     ap.add_argument("--ppo-dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--grad-sync", default="peer", choices=["peer", "nccl"],
+                    help="PPO gradient exchange at N > 1: sum over peer-mapped buffers inside the optimiser's kernels, or one NCCL all-reduce")
     return ap.parse_args()
 
 
@@ -491,7 +493,7 @@ def run_ppo(a):
     torch.cuda.set_device(dev)
     N, K, W = a.envs, a.steps, max(a.warmup, 1)
     env = DyrosDynamicWalk(default_cfg(N), dev, rank=rank, use_cuda_graph=False)
-    cfg = PPOConfig(horizon_length=a.horizon, mixed_precision=a.ppo_dtype)
+    cfg = PPOConfig(horizon_length=a.horizon, mixed_precision=a.ppo_dtype, grad_sync=a.grad_sync)
     tr = PPOTrainer(env, cfg, rank=rank, world=world)
 
     def barrier():
@@ -543,7 +545,9 @@ def run_ppo(a):
                                        "policy on the GPU + mini_epochs x minibatches updates; one step = one epoch",
                            "envs_per_gpu": N, "horizon_length": a.horizon, "minibatch_size": cfg.minibatch_size,
                            "mini_epochs": cfg.mini_epochs, "updates_per_epoch": updates, "parameters": tr.net.n,
-                           "gradient_bucket_bytes": tr.net.n * 4},
+                           "gradient_bucket_bytes": tr.net.n * 4,
+                           "networks": "packed bf16 (batch-2 GEMMs)" if tr.packed is not None else "fp32 autograd",
+                           "grad_sync": ("peer memory (dyros_ppo_reduce_peers)" if tr.peers is not None else "nccl all_reduce") if world > 1 else "none"},
                 "clocks": clk.summary(),
                 "breakdown_ms_per_epoch": {"rollout_and_gae": t_roll / K, "update": t_upd / K,
                                            "update_per_minibatch": t_upd / K / updates,

@@ -412,6 +412,33 @@ int dyros_ppo_adam_packed(const DyrosPpoNet* net, float* params, const float* gr
                           float max_norm, int norm_done, float* norm2_scratch, float* lr_dev, int32_t* step_dev, float beta1, float beta2,
                           float eps, float lr0, float lr_min, int lr_max_steps, void* stream);
 
+/* ---- gradient exchange over peer memory (NVLink / NVSwitch): the Horovod all-reduce of AG:161-173 folded into the
+ * optimiser's kernels. Every rank allocates two flat gradient buffers of `stride` floats (stride >= n, a multiple of 4,
+ * the second right after the first) and 8 flag words, zero-initialised, and maps its peers' allocations into its own
+ * address space (CUDA IPC); `grad[r][p]` / `flags[r]` are those addresses as seen from THIS process. One process per GPU,
+ * one node, at most 8 ranks. */
+typedef struct DyrosPpoPeers {
+  int32_t world, rank;
+  int32_t stride;            /* floats between a rank's two gradient buffers */
+  float* grad[8][2];         /* [rank][parity of the minibatch counter] */
+  uint32_t* flags[8];        /* [rank] -> that rank's 8 flag words: flags[r][q] = minibatches rank q has published to rank r */
+  uint32_t* epoch;           /* local (1): minibatches finished; advanced by dyros_ppo_reduce_peers */
+  uint32_t* ticket;          /* local (1): zero-initialised scratch */
+} DyrosPpoPeers;
+/* Peer-shareable device memory for the exchange (cudaMalloc + CUDA IPC). dyros_peer_alloc: `bytes` of zeroed memory on
+ * the current device and its 64-byte IPC handle (to be sent to the other ranks of the node by any host channel).
+ * dyros_peer_open: maps another rank's allocation for kernels of the CURRENT device (enables the NVLink peer path).
+ * dyros_peer_close / dyros_peer_free undo them. */
+int dyros_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int dyros_peer_open(const unsigned char* handle64, void** ptr);
+int dyros_peer_close(void* ptr);
+int dyros_peer_free(void* ptr);
+/* dyros_ppo_unpack_grads into this rank's buffer of the current parity. */
+int dyros_ppo_unpack_grads_peers(const DyrosPpoNet* net, const DyrosPpoPeers* peers, void* stream);
+/* Publishes this rank's buffer, waits for every rank's, and writes the SUM over ranks (in rank order: bit-identical on
+ * every rank) to flat_grad_sum (local, n floats); norm2_accum += squared norm of its first n_actor entries. */
+int dyros_ppo_reduce_peers(const DyrosPpoPeers* peers, float* flat_grad_sum, int n, int n_actor, float* norm2_accum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,7 @@
 // plain-torch restatement the tests compare with.
 #include <cuda_bf16.h>
 #include <math.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -481,8 +482,12 @@ __global__ void __launch_bounds__(256) k_ppo_pack(PpoSegs S, DyrosPpoNet net, co
 // packed gradients (bf16 GEMM outputs, fp32 bias accumulators) -> flat fp32 master gradient; zeroes the accumulators
 // norm2 (optional): += sum of squares of the actor's gradients (net 0), i.e. k_ppo_gradnorm folded in (single rank: no
 // all-reduce sits between the two)
-__global__ void __launch_bounds__(256) k_ppo_unpack(PpoSegs S, DyrosPpoNet net, float* __restrict__ flat_grad, float* __restrict__ norm2) {
+// epoch (optional): flat_grad points at TWO buffers of `stride` floats, the one of parity *epoch & 1 is written (the
+// peer-memory exchange below)
+__global__ void __launch_bounds__(256) k_ppo_unpack(PpoSegs S, DyrosPpoNet net, float* __restrict__ flat_grad, float* __restrict__ norm2,
+                                                    const unsigned* __restrict__ epoch, size_t stride) {
   const PpoSeg g = S.s[blockIdx.y];
+  if (epoch) flat_grad += (size_t)(*epoch & 1u) * stride;
   float sq = 0.f;
   const int n = g.rows * g.cols;
   const bf16* wsrc = reinterpret_cast<const bf16*>(g.which == 0 ? net.gw0 : (g.which == 2 ? net.gw1 : net.gwh));
@@ -540,6 +545,72 @@ __global__ void __launch_bounds__(256) k_ppo_adam_pack(PpoSegs S, DyrosPpoNet ne
     else bdst[d] = x;
   }
 }
+
+// ================================================================ gradient exchange over peer memory (NVLink / NVSwitch)
+// What the reference does with Horovod's all-reduce between backward and optimizer.step (AG:161-173), as part of the
+// optimiser's own kernels: every rank's flat gradient buffer is mapped into every other rank (CUDA IPC), a rank
+// publishes "minibatch e written" in its peers' flag words (st.release.sys), waits for the same word from everybody
+// (ld.acquire.sys) and then sums all ranks' buffers itself, reading the remote ones through NVLink, in rank order
+// (so every rank forms bit-identical sums), folding in the squared norm for the actor's clip. Two buffers per rank,
+// alternating with the minibatch counter: a rank can be at most one minibatch ahead of the slowest one, so the buffer
+// it overwrites is never one a peer still reads.
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__global__ void __launch_bounds__(256) k_ppo_reduce_peers(DyrosPpoPeers P, float* __restrict__ out, int n, int n_actor,
+                                                          float* __restrict__ norm2, unsigned* __restrict__ ticket) {
+  const unsigned e = *P.epoch;  // minibatches finished so far; this one publishes e + 1
+  const int par = (int)(e & 1u);
+  if (blockIdx.x == 0 && (int)threadIdx.x < P.world) {
+    __threadfence_system();
+    st_release_sys(P.flags[threadIdx.x] + P.rank, e + 1u);
+  }
+  if ((int)threadIdx.x < P.world)
+    while (ld_acquire_sys(P.flags[P.rank] + threadIdx.x) < e + 1u) __nanosleep(64);
+  __syncthreads();
+  float sq = 0.f;
+  const int n4 = n / 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < P.world; ++r) {
+      const float4 x = ld_cg4(P.grad[r][par] + 4 * i);
+      s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = s;
+    const int j = 4 * i;
+    if (j + 3 < n_actor) sq += s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;
+    else {
+      if (j < n_actor) sq += s.x * s.x;
+      if (j + 1 < n_actor) sq += s.y * s.y;
+      if (j + 2 < n_actor) sq += s.z * s.z;
+    }
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < n - 4 * n4) {  // the tail (n is not a multiple of 4)
+    const int j = 4 * n4 + threadIdx.x;
+    float s = 0.f;
+    for (int r = 0; r < P.world; ++r) s += __ldcg(P.grad[r][par] + j);
+    out[j] = s;
+    if (j < n_actor) sq += s * s;
+  }
+  sq = warp_sum(sq);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += part[k];
+    if (norm2) atomicAdd(norm2, t);
+    __threadfence();
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {  // the last block closes the minibatch
+      *ticket = 0u;
+      *P.epoch = e + 1u;
+    }
+  }
+}
 }  // namespace dyros
 
 using namespace dyros;
@@ -564,6 +635,7 @@ static int configure_ppo_kernels() {  // (common.cuh: one carve-out for every ke
   DY_CUDA(prefer_max_smem_carveout(k_ppo_relu_bwd)); DY_CUDA(prefer_max_smem_carveout(k_ppo_act_packed));
   DY_CUDA(prefer_max_smem_carveout(k_ppo_loss_grad_packed)); DY_CUDA(prefer_max_smem_carveout(k_ppo_pack));
   DY_CUDA(prefer_max_smem_carveout(k_ppo_unpack)); DY_CUDA(prefer_max_smem_carveout(k_ppo_adam_pack));
+  DY_CUDA(prefer_max_smem_carveout(k_ppo_reduce_peers));
   done = true;
   return 0;
 }
@@ -678,7 +750,7 @@ int dyros_ppo_unpack_grads(const DyrosPpoNet* net, float* flat_grad, float* norm
   PPO_CHECK(ppo_net_ok(net) && net->gw0 && net->gw1 && net->gwh && net->gb0 && net->gb1 && net->gbh && flat_grad,
             "dyros_ppo_unpack_grads: bad argument");
   if (configure_ppo_kernels()) return 1;
-  k_ppo_unpack<<<dim3(64, 12), 256, 0, (cudaStream_t)stream>>>(ppo_segments(net->hidden), *net, flat_grad, norm2_accum);
+  k_ppo_unpack<<<dim3(64, 12), 256, 0, (cudaStream_t)stream>>>(ppo_segments(net->hidden), *net, flat_grad, norm2_accum, nullptr, 0);
   DY_LAUNCH_CHECK();
   return 0;
 }
@@ -696,6 +768,61 @@ int dyros_ppo_adam_packed(const DyrosPpoNet* net, float* params, const float* gr
                                               lr_dev, step_dev, beta1, beta2, eps);
   k_ppo_adam_finish<<<1, 1, 0, s>>>(norm2_scratch, step_dev, lr_dev, lr0, lr_min, lr_max_steps);
   DY_LAUNCH_CHECK();
+  return 0;
+}
+
+static bool ppo_peers_ok(const DyrosPpoPeers* p) {
+  if (!p || p->world < 2 || p->world > 8 || p->rank < 0 || p->rank >= p->world || !p->epoch || !p->ticket || p->stride < 4 || p->stride % 4) return false;
+  for (int r = 0; r < p->world; ++r)
+    if (!p->grad[r][0] || !p->grad[r][1] || !p->flags[r]) return false;
+  return true;
+}
+int dyros_ppo_unpack_grads_peers(const DyrosPpoNet* net, const DyrosPpoPeers* peers, void* stream) {
+  PPO_CHECK(ppo_net_ok(net) && net->gw0 && net->gw1 && net->gwh && net->gb0 && net->gb1 && net->gbh && ppo_peers_ok(peers),
+            "dyros_ppo_unpack_grads_peers: bad argument");
+  PPO_CHECK(peers->grad[peers->rank][1] == peers->grad[peers->rank][0] + peers->stride, "dyros_ppo_unpack_grads_peers: the rank's two buffers must be `stride` apart");
+  if (configure_ppo_kernels()) return 1;
+  k_ppo_unpack<<<dim3(64, 12), 256, 0, (cudaStream_t)stream>>>(ppo_segments(net->hidden), *net, peers->grad[peers->rank][0], nullptr, peers->epoch,
+                                                               (size_t)peers->stride);
+  DY_LAUNCH_CHECK();
+  return 0;
+}
+int dyros_ppo_reduce_peers(const DyrosPpoPeers* peers, float* flat_grad_sum, int n, int n_actor, float* norm2_accum, void* stream) {
+  PPO_CHECK(ppo_peers_ok(peers) && flat_grad_sum && n > 0 && n <= peers->stride && n_actor >= 0 && n_actor <= n, "dyros_ppo_reduce_peers: bad argument");
+  PPO_CHECK((reinterpret_cast<uintptr_t>(flat_grad_sum) & 15) == 0, "dyros_ppo_reduce_peers: the output must be 16-byte aligned");
+  if (configure_ppo_kernels()) return 1;
+  k_ppo_reduce_peers<<<148, 256, 0, (cudaStream_t)stream>>>(*peers, flat_grad_sum, n, n_actor, norm2_accum, peers->ticket);
+  DY_LAUNCH_CHECK();
+  return 0;
+}
+
+// Peer-shareable device memory (plain cudaMalloc + CUDA IPC): allocated and zeroed by its owner, opened by the other
+// ranks of the node IN THE CONTEXT OF THE DEVICE THAT WILL DEREFERENCE IT (the current device), which is what makes
+// cudaIpcMemLazyEnablePeerAccess enable the peer path (a mapping opened under the owner's device does not).
+int dyros_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64) {
+  PPO_CHECK(bytes > 0 && ptr && handle64, "dyros_peer_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t");
+  DY_CUDA(cudaMalloc(ptr, bytes));
+  DY_CUDA(cudaMemset(*ptr, 0, bytes));
+  DY_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  DY_CUDA(cudaIpcGetMemHandle(&h, *ptr));
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+int dyros_peer_open(const unsigned char* handle64, void** ptr) {
+  PPO_CHECK(handle64 && ptr, "dyros_peer_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  DY_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int dyros_peer_close(void* ptr) {
+  if (ptr) DY_CUDA(cudaIpcCloseMemHandle(ptr));
+  return 0;
+}
+int dyros_peer_free(void* ptr) {
+  if (ptr) DY_CUDA(cudaFree(ptr));
   return 0;
 }
 

@@ -107,6 +107,11 @@ class DyrosPpoNet(C.Structure):
     _fields_ = [("hidden", i32)] + [(n, C.c_void_p) for n in ("w0", "b0", "w1", "b1", "wh", "bh", "gw0", "gw1", "gwh", "gb0", "gb1", "gbh")]
 
 
+class DyrosPpoPeers(C.Structure):
+    _fields_ = [("world", i32), ("rank", i32), ("stride", i32), ("grad", (C.c_void_p * 2) * 8), ("flags", C.c_void_p * 8),
+                ("epoch", C.c_void_p), ("ticket", C.c_void_p)]
+
+
 _VP, _INT = C.c_void_p, C.c_int
 _PB = C.POINTER(DyrosPpoBuffers)
 _PN = C.POINTER(DyrosPpoNet)
@@ -123,6 +128,12 @@ SIGNATURES = {
     "dyros_ppo_loss_grad_packed": (_INT, [_PB, _INT, _INT, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "dyros_ppo_pack_params": (_INT, [_PN, _VP, _VP]),
     "dyros_ppo_unpack_grads": (_INT, [_PN, _VP, _VP, _VP]),
+    "dyros_peer_alloc": (_INT, [C.c_size_t, C.POINTER(_VP), C.c_char_p]),
+    "dyros_peer_open": (_INT, [C.c_char_p, C.POINTER(_VP)]),
+    "dyros_peer_close": (_INT, [_VP]),
+    "dyros_peer_free": (_INT, [_VP]),
+    "dyros_ppo_unpack_grads_peers": (_INT, [_PN, C.POINTER(DyrosPpoPeers), _VP]),
+    "dyros_ppo_reduce_peers": (_INT, [C.POINTER(DyrosPpoPeers), _VP, _INT, _INT, _VP, _VP]),
     "dyros_ppo_adam_packed": (_INT, [_PN, _VP, _VP, _VP, _VP, f32, f32, _INT, _VP, _VP, _VP, f32, f32, f32, f32, f32, _INT, _VP]),
     "dyros_last_error": (C.c_char_p, []),
     "dyros_abi_version": (_INT, []),

@@ -54,6 +54,8 @@ class PPOConfig:
     sigma_init: float = -2.302585           # PPO:21-23
     sigma_last: float = -2.9957             # PPO:24-26
     mixed_precision: str = "bf16"           # "bf16" | "fp32"
+    grad_sync: str = "peer"                 # world > 1, bf16 path: "peer" = sum over peer-mapped buffers inside the optimiser's
+                                            # kernels (NVLink), "nccl" = one all-reduce call per minibatch (AG:161-173)
     seed: int = 42
     use_cuda_graph: bool = True
 
@@ -200,6 +202,61 @@ class PackedNets:
         return out[0, :, :NA].float() + self.bh[0, :NA], out[1, :, 0].float() + self.bh[1, 0]
 
 
+class _DevMem:
+    """A raw device allocation seen by torch (CUDA array interface)."""
+
+    def __init__(self, ptr: int, nfloats: int):
+        self.__cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+
+class PeerGrads:
+    """Every rank's two flat gradient buffers and flag words mapped into every rank (CUDA IPC, one node): the plumbing of
+    include/dyros_b200.h DyrosPpoPeers. The exchange itself is dyros_ppo_reduce_peers."""
+
+    def __init__(self, n: int, device, rank: int, world: int):
+        import torch.distributed as dist
+        if not 2 <= world <= 8:
+            raise ValueError("peer-memory gradient exchange: 2..8 ranks on one node")
+        self.lib = native.load()
+        self.stride = (n + 3) // 4 * 4
+        nfl = 2 * self.stride + 16                                   # [G0 | G1 | 8 flag words + pad]
+        with torch.cuda.device(device):
+            ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+            native.check(self.lib.dyros_peer_alloc(C.c_size_t(4 * nfl), C.byref(ptr), handle), "dyros_peer_alloc")
+            self._own = ptr.value
+            handles = [None] * world
+            dist.all_gather_object(handles, handle.raw)
+            self.ptrs, self._opened = [], []
+            for r in range(world):
+                if r == rank:
+                    self.ptrs.append(self._own)
+                    continue
+                p = C.c_void_p()
+                native.check(self.lib.dyros_peer_open(handles[r], C.byref(p)), "dyros_peer_open")
+                self._opened.append(p.value)
+                self.ptrs.append(p.value)
+            self.local = torch.as_tensor(_DevMem(self._own, nfl), device=device)   # this rank's block, for tests and tools
+        self.epoch = torch.zeros(2, dtype=torch.int32, device=device)              # [epoch, ticket]
+        d = native.DyrosPpoPeers()
+        d.world, d.rank, d.stride = world, rank, self.stride
+        for r, base in enumerate(self.ptrs):
+            d.grad[r][0], d.grad[r][1] = base, base + 4 * self.stride
+            d.flags[r] = base + 8 * self.stride
+        d.epoch, d.ticket = self.epoch.data_ptr(), self.epoch.data_ptr() + 4
+        self.desc = d
+        torch.cuda.synchronize(device)
+        dist.barrier()   # every rank has mapped every (zeroed) buffer before anybody publishes
+
+    def close(self):
+        """After a barrier of the caller's: unmaps the peers' blocks and frees this rank's."""
+        for p in self._opened:
+            self.lib.dyros_peer_close(C.c_void_p(p))
+        self._opened = []
+        if self._own:
+            self.lib.dyros_peer_free(C.c_void_p(self._own))
+            self._own = 0
+
+
 class PPOTrainer:
     def __init__(self, env, cfg: Optional[PPOConfig] = None, rank: int = 0, world: int = 1):
         self.env, self.cfg = env, cfg or PPOConfig()
@@ -217,6 +274,10 @@ class PPOTrainer:
             dist.broadcast(self.net.flat, 0)
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
         self.packed: Optional[PackedNets] = PackedNets(self.net, self.lib) if c.mixed_precision == "bf16" else None
+        if c.grad_sync not in ("peer", "nccl"):
+            raise ValueError("grad_sync: 'peer' or 'nccl'")
+        self.peers: Optional[PeerGrads] = (PeerGrads(self.net.n, dev, rank, world)
+                                           if world > 1 and self.packed is not None and c.grad_sync == "peer" else None)
         if self.packed is not None:  # the rollout's observations are kept as the bf16 rows the GEMMs read (N*H x 488)
             self.x_step = z(N, PackedNets.K0, dt=torch.bfloat16)
             self.x_roll = z(N * H, PackedNets.K0, dt=torch.bfloat16)
@@ -337,12 +398,20 @@ class PPOTrainer:
         pk.backward(x)
         c, n, single = self.cfg, self.net, self.world == 1
         clip = c.grad_norm if c.truncate_grads else 0.0
-        pk.unpack_grads(self.norm2 if single and clip > 0 else None)   # (single rank: the norm reduction rides along)
-        if not single:  # optimizer.synchronize(): one all-reduce of the flat bucket (AG:161-173)
+        norm_done = True
+        if single:
+            pk.unpack_grads(self.norm2 if clip > 0 else None)   # (the norm reduction rides along)
+        elif self.peers is not None:  # optimizer.synchronize() (AG:161-173) over peer memory: publish, wait, sum in rank order
+            native.check(self.lib.dyros_ppo_unpack_grads_peers(C.byref(pk.desc), C.byref(self.peers.desc), self._stream), "unpack_peers")
+            native.check(self.lib.dyros_ppo_reduce_peers(C.byref(self.peers.desc), self._p(n.grad), n.n, n.n_actor,
+                                                         self._p(self.norm2) if clip > 0 else None, self._stream), "reduce_peers")
+        else:  # ... or as one NCCL all-reduce of the flat bucket
             import torch.distributed as dist
+            pk.unpack_grads(None)
             dist.all_reduce(n.grad)
+            norm_done = False
         native.check(self.lib.dyros_ppo_adam_packed(C.byref(pk.desc), self._p(n.flat), self._p(n.grad), self._p(n.exp_avg),
-                                                    self._p(n.exp_avg_sq), 1.0 / self.world, clip, int(single), self._p(self.norm2),
+                                                    self._p(n.exp_avg_sq), 1.0 / self.world, clip, int(norm_done), self._p(self.norm2),
                                                     self._p(self.lr), self._p(self.opt_step), 0.9, 0.999, 1e-8, c.learning_rate,
                                                     c.learning_rate_min, c.max_epochs if c.lr_schedule == "linear" else 0,
                                                     self._stream), "dyros_ppo_adam_packed")
