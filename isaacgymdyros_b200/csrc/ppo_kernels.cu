@@ -575,11 +575,16 @@ __global__ void __launch_bounds__(256) k_ppo_reduce_peers(DyrosPpoPeers P, float
   float sq = 0.f;
   const int n4 = n / 4;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    float4 x[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)  // all ranks' loads in flight before the first add (remote ones cross NVLink)
+      if (r < P.world) x[r] = ld_cg4(P.grad[r][par] + 4 * i);
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < P.world; ++r) {
-      const float4 x = ld_cg4(P.grad[r][par] + 4 * i);
-      s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
-    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < P.world) {
+        s.x += x[r].x; s.y += x[r].y; s.z += x[r].z; s.w += x[r].w;
+      }
     reinterpret_cast<float4*>(out)[i] = s;
     const int j = 4 * i;
     if (j + 3 < n_actor) sq += s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;
@@ -791,7 +796,7 @@ int dyros_ppo_reduce_peers(const DyrosPpoPeers* peers, float* flat_grad_sum, int
   PPO_CHECK(ppo_peers_ok(peers) && flat_grad_sum && n > 0 && n <= peers->stride && n_actor >= 0 && n_actor <= n, "dyros_ppo_reduce_peers: bad argument");
   PPO_CHECK((reinterpret_cast<uintptr_t>(flat_grad_sum) & 15) == 0, "dyros_ppo_reduce_peers: the output must be 16-byte aligned");
   if (configure_ppo_kernels()) return 1;
-  k_ppo_reduce_peers<<<148, 256, 0, (cudaStream_t)stream>>>(*peers, flat_grad_sum, n, n_actor, norm2_accum, peers->ticket);
+  k_ppo_reduce_peers<<<148 * 2, 256, 0, (cudaStream_t)stream>>>(*peers, flat_grad_sum, n, n_actor, norm2_accum, peers->ticket);
   DY_LAUNCH_CHECK();
   return 0;
 }
