@@ -237,7 +237,8 @@ int dyros_simulate(DyrosSim* sim, int apply_wrench, void* stream);
 /* Self-collision pass (actor created with collision filter 0, T:354): detects contacts between the shapes of
  * non-adjacent links from link_pose, writes self_contact_force and adds it into net_contact_force, so that
  * collision_true (T:590, T:937) sees them. dyros_simulate and dyros_task_step run it themselves when the model carries
- * self-collision tables and both buffers are given; exported for callers that stage the step. */
+ * self-collision tables and both buffers are given; exported for callers that stage the step (after
+ * dyros_task_physics_kernel). It ADDS into net_contact_force: once per physics launch. */
 int dyros_self_collision(DyrosSim* sim, void* stream);
 /* gym.refresh_rigid_body_state_tensor: forward kinematics into rigid_body_state (DOCT:193-207). */
 int dyros_refresh_rigid_body_state(DyrosSim* sim, void* stream);

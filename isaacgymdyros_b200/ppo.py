@@ -337,7 +337,7 @@ class PPOTrainer:
         native.check(self.lib.dyros_ppo_act(C.byref(self.pb), self._p(mu), self._p(v), self._p(self.net.logstd), self._p(env.obs_buf),
                                             self._p(env.reset_buf), self._p(self.actions), self._p(self.inject_normal),
                                             self._stream), "dyros_ppo_act")
-        env.core.step(self.actions)  # VecTask.step: 2 launches, reads `actions` in place
+        env.core.step(self.actions)  # VecTask.step: 3 launches, reads `actions` in place
         native.check(self.lib.dyros_ppo_reward(C.byref(self.pb), self._p(env.rew_buf), self._p(env.timeout_buf),
                                                self._p(env.reset_buf), self._stream), "dyros_ppo_reward")
 
