@@ -67,16 +67,16 @@ typedef struct {
   /* self-collision tables (model/selfcollision.py; all NULL / 0 = no self-collision): exact shapes + sample spheres per
    * link, bounding spheres of the links, candidate link pairs. Reference: create_actor(..., group i, filter 0), T:354. */
   int32_t sc_num_shapes, sc_num_samples, sc_num_pairs;
-  const int32_t* sc_shape_kind;    /* [ns] 0 = box, 1 = cylinder */
+  const int32_t* sc_shape_kind;    /* [ns] 0 = box, 1 = cylinder, 2 = capsule (a sphere when its half height is 0) */
   const int32_t* sc_shape_link;    /* [ns] shapes are grouped by link */
   const int32_t* sc_shape_body;    /* [ns] */
   const int32_t* sc_shape_sample0; /* [ns+1] sample range of each shape */
   const double* sc_shape_center;   /* [ns*3] link frame */
   const double* sc_shape_rot;      /* [ns*9] row-major, columns = shape axes in the link frame (cylinder: column 2 = axis) */
-  const double* sc_shape_size;     /* [ns*3] box half extents | cylinder radius, half height, 0 */
+  const double* sc_shape_size;     /* [ns*3] box half extents | cylinder / capsule radius, half height, 0 */
   const double* sc_sample;         /* [nsamp*4] link-frame position, radius */
   const int32_t* sc_link_shape0;   /* [nl+1] */
-  const double* sc_link_sphere;    /* [nl*4] link-frame centre, radius */
+  const double* sc_link_sphere;    /* [nl*4] link-frame centre, radius (broad phase of the oracle; the kernel uses the shapes' own spheres) */
   const int32_t* sc_pairs;         /* [np*2] candidate link pairs i < j */
 } DyrosModelDesc;
 

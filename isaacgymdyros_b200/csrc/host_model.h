@@ -353,9 +353,12 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
       for (int c = 0; c < 3; ++c) hot.push_back(f2i((float)m->sc_shape_center[3 * k + c]));
       for (int c = 0; c < 9; ++c) hot.push_back(f2i((float)m->sc_shape_rot[9 * k + c]));
       for (int c = 0; c < 3; ++c) hot.push_back(f2i((float)m->sc_shape_size[3 * k + c]));
-      // bounding radius about the centre (rounded up): box |half extents|, cylinder hypot(radius, half height)
+      // bounding radius about the centre (rounded up): box |half extents|, cylinder hypot(radius, half height),
+      // capsule radius + half height
       const double* z = m->sc_shape_size + 3 * k;
-      const double R = m->sc_shape_kind[k] == 0 ? std::sqrt(z[0] * z[0] + z[1] * z[1] + z[2] * z[2]) : std::hypot(z[0], z[1]);
+      if (m->sc_shape_kind[k] < 0 || m->sc_shape_kind[k] > 2) MFAIL("self-collision shape %d: kind %d", k, m->sc_shape_kind[k]);
+      const double R = m->sc_shape_kind[k] == 0 ? std::sqrt(z[0] * z[0] + z[1] * z[1] + z[2] * z[2])
+                       : (m->sc_shape_kind[k] == 1 ? std::hypot(z[0], z[1]) : z[0] + z[1]);
       hot.push_back(f2i(std::nextafter((float)(R * (1.0 + 1e-6)), INFINITY)));
     }
     dm.sc_o_meta = section();

@@ -562,6 +562,12 @@ __device__ __forceinline__ float sc_sdf(int kind, V3 size, V3 x, V3& g) {
     g = v3(0, 0, sg.z);
     return q.z;
   }
+  if (kind == 2) {  // capsule about its z axis (a sphere when the half height is 0): distance to the segment, minus r
+    const V3 q = v3(x.x, x.y, x.z - fminf(fmaxf(x.z, -size.y), size.y));
+    const float n = sqrtf(dot(q, q));
+    g = n > 0.f ? (1.f / n) * q : v3(1.f, 0.f, 0.f);
+    return n - size.x;
+  }
   const float r = size.x, h = size.y;  // cylinder about its z axis
   const float rho = sqrtf(x.x * x.x + x.y * x.y);
   const float inv = 1.f / fmaxf(rho, 1e-30f);
@@ -650,7 +656,8 @@ __device__ __forceinline__ void sc_obb(const ScTab& T, const ScEnv& W, int s, M3
   V3 pl;
   sc_pose(W.pose, ms & 0xff, Rl, pl);
   R = mul(Rl, ld_m3_f(S + 3));
-  half = ((ms >> 16) & 0xff) == 0 ? ld3_f(S + 12) : v3(S[12], S[12], S[13]);
+  const int kind = (ms >> 16) & 0xff;  // box: its half extents; cylinder r x r x h; capsule r x r x (h + r)
+  half = kind == 0 ? ld3_f(S + 12) : v3(S[12], S[12], kind == 2 ? S[13] + S[12] : S[13]);
 }
 // true when one of the 6 face normals separates the two boxes (with a margin for rounding): certainly no contact
 __device__ __forceinline__ bool sc_obb_separated(const ScTab& T, const ScEnv& W, int sa, int sb) {

@@ -4,9 +4,11 @@ docs/_sources/programming/assets.rst.txt:107-109: filter 0 = all shapes of the a
 makes `collision_true` (T:590, T:937) fire when an arm hits the torso or a knee hits the other leg.
 
 Model (stated once more, independently, in oracle/selfcollision_oracle.py):
-  * every collision primitive of the MJCF (box or cylinder; XML:99-353) is kept as an EXACT shape in its link's frame
-    (box: centre, axes, half extents; cylinder: centre, axis, radius, half height) plus a few SAMPLE SPHERES (box: its 8
-    corners, radius 0; cylinder: 3 spheres of radius min(r, h) on its axis);
+  * every collision primitive of the MJCF (box or cylinder; XML:99-353; capsules and spheres for the stock Humanoid,
+    assets/mjcf/nv_humanoid.xml) is kept as an EXACT shape in its link's frame (box: centre, axes, half extents;
+    cylinder / capsule: centre, axis, radius, half height; a sphere is a capsule of half height 0) plus a few SAMPLE
+    SPHERES (box: its 8 corners, radius 0; cylinder: 3 spheres of radius min(r, h) on its axis; capsule: spheres of its
+    own radius on its axis, at most one radius apart, at most 8);
   * two shapes A, B touch when a sample sphere of one penetrates the exact shape of the other: depth = rho - sdf_B(c) > 0;
     the contact pushes the bodies apart along the gradient of sdf_B with the penalty stiffness of the ground contacts, and
     both directions (samples of A in B, samples of B in A) are evaluated;
@@ -24,7 +26,8 @@ from typing import List, Sequence
 
 import numpy as np
 
-KIND_BOX, KIND_CYL = 0, 1
+KIND_BOX, KIND_CYL, KIND_CAP = 0, 1, 2
+MAX_SHAPE_SAMPLES = 8   # csrc/internal.h SC_MAX_SHAPE_SAMPLES
 
 
 @dataclass
@@ -98,6 +101,17 @@ def shapes_from_tables(t) -> List[dict]:
         samples = np.array([[*(c + s * (h - rho) * a), rho] for s in (-1.0, 0.0, 1.0)])
         shapes.append(dict(kind=KIND_CYL, link=int(t.cyl_link[k]), body=int(t.cyl_body[k]), center=c, rot=R,
                            size=np.array([r, h, 0.0]), samples=samples))
+    for k in range(len(getattr(t, "cap_link", []))):
+        a, b = np.asarray(t.cap_ends[k][:3], float), np.asarray(t.cap_ends[k][3:], float)
+        r, c, h = float(t.cap_radius[k]), (a + b) / 2, float(np.linalg.norm(b - a)) / 2
+        ax = (b - a) / (2 * h) if h > 0 else np.array([0.0, 0, 1.0])
+        u = np.cross(ax, [1.0, 0, 0]) if abs(ax[0]) < 0.9 else np.cross(ax, [0, 1.0, 0])
+        u /= np.linalg.norm(u)
+        R = np.stack([u, np.cross(ax, u), ax], 1)
+        n = min(MAX_SHAPE_SAMPLES, 1 + 2 * int(np.ceil(h / r))) if h > 0 else 1
+        samples = np.array([[*(c + z * ax), r] for z in (np.linspace(-h, h, n) if n > 1 else [0.0])])
+        shapes.append(dict(kind=KIND_CAP, link=int(t.cap_link[k]), body=int(t.cap_body[k]), center=c, rot=R,
+                           size=np.array([r, h, 0.0]), samples=samples))
     shapes.sort(key=lambda s: (s["link"], s["kind"], s["body"]))
     return shapes
 
@@ -117,6 +131,11 @@ def sdf(kind: int, size: np.ndarray, x: np.ndarray):
         g = np.where((dist_out > 0)[..., None], g_out, g_in) * np.where(x < 0, -1.0, 1.0)
         return d, g
     r, h = size[0], size[1]
+    if kind == KIND_CAP:  # distance to the segment [-h, h] on z, minus the radius
+        q = x - np.concatenate([np.zeros_like(x[..., :2]), np.clip(x[..., 2:], -h, h)], -1)
+        n = np.linalg.norm(q, axis=-1)
+        g = np.where((n > 0)[..., None], q / np.maximum(n, 1e-30)[..., None], np.array([1.0, 0, 0]))
+        return n - r, g
     rho = np.linalg.norm(x[..., :2], axis=-1)
     qr, qz = rho - r, np.abs(x[..., 2]) - h
     outside = np.stack([np.maximum(qr, 0.0), np.maximum(qz, 0.0)], -1)

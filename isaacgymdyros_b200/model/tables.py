@@ -58,10 +58,19 @@ class ModelTables:
     sched: np.ndarray  # (T, G) int32
     meta: dict = field(default_factory=dict)
     dof_stiffness: np.ndarray = None  # joint spring about q = 0 (MJCF `stiffness`); zeros for TOCABI
+    # sphere / capsule primitives as shapes (their end points are also in pt_*): link, body, the two end centres in the
+    # link frame (equal for a sphere), radius. Used by the self-collision tables (model/selfcollision.py).
+    cap_link: np.ndarray = None
+    cap_body: np.ndarray = None
+    cap_ends: np.ndarray = None    # (ncap, 6)
+    cap_radius: np.ndarray = None
 
     def __post_init__(self):
         if self.dof_stiffness is None:
             self.dof_stiffness = np.zeros(len(self.dof_names))
+        if self.cap_link is None:
+            self.cap_link, self.cap_body = np.zeros(0, np.int32), np.zeros(0, np.int32)
+            self.cap_ends, self.cap_radius = np.zeros((0, 6)), np.zeros(0)
 
     @property
     def num_bodies(self) -> int:
@@ -83,9 +92,13 @@ class ModelTables:
                "dof_effort", "pt_link", "pt_body", "pt_pos", "pt_radius", "cyl_link", "cyl_body", "cyl_center",
                "cyl_axis", "cyl_size", "solver_links", "sched"]
 
+    _OPTIONAL = ["cap_link", "cap_body", "cap_ends", "cap_radius"]
+
     def save(self, path: str) -> None:
         d = {k: getattr(self, k) for k in self._ARRAYS}
         d["dof_stiffness"] = self.dof_stiffness
+        for k in self._OPTIONAL:
+            d[k] = getattr(self, k)
         d["names_json"] = np.frombuffer(json.dumps(
             {"body_names": self.body_names, "dof_names": self.dof_names, "meta": self.meta}).encode(), dtype=np.uint8)
         np.savez_compressed(path, **d)
@@ -96,6 +109,7 @@ class ModelTables:
         names = json.loads(bytes(z["names_json"]).decode())
         return cls(body_names=names["body_names"], dof_names=names["dof_names"], meta=names.get("meta", {}),
                    dof_stiffness=z["dof_stiffness"] if "dof_stiffness" in z.files else None,
+                   **{k: z[k] for k in cls._OPTIONAL if k in z.files},
                    **{k: z[k] for k in cls._ARRAYS})
 
 
@@ -270,6 +284,7 @@ def build_tables(model: RobotModel, *, solver_bodies: List[str], vel_limit: floa
         body_inertia[bi] = [b.mass, *(b.mass * c), Io[0, 0], Io[1, 1], Io[2, 2], Io[0, 1], Io[0, 2], Io[1, 2]]
     pt_link, pt_body, pt_pos, pt_rad = [], [], [], []
     cyl_link, cyl_body, cyl_c, cyl_a, cyl_s = [], [], [], [], []
+    cap_link, cap_body, cap_ends, cap_rad = [], [], [], []
     for bi, b in enumerate(model.bodies):
         R, p = body_rot[bi], body_pos[bi]
         for g in b.geoms:
@@ -283,7 +298,10 @@ def build_tables(model: RobotModel, *, solver_bodies: List[str], vel_limit: floa
                             pt_pos.append(cg + Rg @ (np.array([sx, sy, sz]) * g.size[:3])); pt_rad.append(0.0)
             elif g.type == "sphere":
                 pt_link.append(body_link[bi]); pt_body.append(bi); pt_pos.append(cg); pt_rad.append(g.size[0])
+                cap_link.append(body_link[bi]); cap_body.append(bi); cap_ends.append([*cg, *cg]); cap_rad.append(g.size[0])
             elif g.type == "capsule":
+                ends = [cg + Rg @ np.array([0, 0, s * g.size[1]]) for s in (-1, 1)]
+                cap_link.append(body_link[bi]); cap_body.append(bi); cap_ends.append([*ends[0], *ends[1]]); cap_rad.append(g.size[0])
                 for s in (-1, 1):
                     pt_link.append(body_link[bi]); pt_body.append(bi)
                     pt_pos.append(cg + Rg @ np.array([0, 0, s * g.size[1]])); pt_rad.append(g.size[0])
@@ -309,5 +327,7 @@ def build_tables(model: RobotModel, *, solver_bodies: List[str], vel_limit: floa
         pt_pos=f64(pt_pos, (-1, 3)), pt_radius=f64(pt_rad, -1),
         cyl_link=np.array(cyl_link, dtype=np.int32), cyl_body=np.array(cyl_body, dtype=np.int32),
         cyl_center=f64(cyl_c, (-1, 3)), cyl_axis=f64(cyl_a, (-1, 3)), cyl_size=f64(cyl_s, (-1, 2)),
+        cap_link=np.array(cap_link, dtype=np.int32), cap_body=np.array(cap_body, dtype=np.int32),
+        cap_ends=f64(cap_ends, (-1, 6)), cap_radius=f64(cap_rad, -1),
         solver_links=np.array(sl, dtype=np.int32), sched=branch_schedule(link_parent, lanes),
         meta={"model": model.name, "lanes": lanes})

@@ -9,7 +9,7 @@ Written shape by shape with explicit loops (no shared code with the product's ve
 tables themselves)."""
 import numpy as np
 
-KIND_BOX, KIND_CYL = 0, 1
+KIND_BOX, KIND_CYL, KIND_CAP = 0, 1, 2
 
 
 def sdf_point(kind, size, x):
@@ -25,6 +25,10 @@ def sdf_point(kind, size, x):
         g[k] = -1.0 if x[k] < 0 else 1.0
         return float(q[k]), g
     r, h = size[0], size[1]
+    if kind == KIND_CAP:                                       # capsule (sphere when h = 0): segment [-h, h] on z
+        q = np.array([x[0], x[1], x[2] - min(max(x[2], -h), h)])
+        n = np.linalg.norm(q)
+        return n - r, (q / n if n > 0 else np.array([1.0, 0.0, 0.0]))
     rho = np.hypot(x[0], x[1])
     er = np.array([x[0], x[1], 0.0]) / max(rho, 1e-30)
     ez = np.array([0.0, 0.0, -1.0 if x[2] < 0 else 1.0])

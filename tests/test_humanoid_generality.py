@@ -109,8 +109,8 @@ def test_humanoid_cuda_simulate_matches_oracle_and_runs_4096():
     import torch
     from isaacgymdyros_b200.core import DyrosCore
     t = humanoid()
-    cfg = CoreConfig(**HUMANOID_CFG)
-    o = PhysicsOracle(t, oracle_params(cfg), solver_bodies=cfg.solver_bodies)
+    cfg = CoreConfig(**HUMANOID_CFG, self_collision=False)   # (PhysicsOracle.substep has no self-collision pass; its own
+    o = PhysicsOracle(t, oracle_params(cfg), solver_bodies=cfg.solver_bodies)   # test: tests/test_self_collision.py)
     N = 40
     st = humanoid_states(N, np.random.default_rng(5), t, "mixed")
     want = o.substep(st["root"], st["q"], st["qd"], st["tau"], st["damping"], st["armature"], st["mass_scale"])

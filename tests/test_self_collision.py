@@ -101,6 +101,63 @@ def test_cuda_self_collision_matches_oracle(program, caps, monkeypatch):
     core.close()
 
 
+def test_humanoid_capsule_tables_known_answers():
+    """The stock Humanoid (assets/mjcf/nv_humanoid.xml; tasks/humanoid.py creates its actor with filter 0 as well): capsules
+    and spheres as shape kind 2."""
+    from tests.test_humanoid_generality import humanoid
+    t = humanoid()
+    sc = self_collision_tables(t)
+    assert sc.num_shapes == 19 and (sc.shape_kind == SC.KIND_CAP).all() and np.diff(sc.shape_sample0).max() <= 8
+    head = [k for k in range(19) if t.body_names[sc.shape_body[k]] == "head"][0]          # <geom name="head" type="sphere" size=".09">
+    assert sc.shape_size[head][0] == pytest.approx(0.09) and sc.shape_size[head][1] == 0.0 and sc.shape_sample0[head + 1] - sc.shape_sample0[head] == 1
+    d, g = SC.sdf(SC.KIND_CAP, np.array([0.05, 0.2, 0.0]), np.array([[0.1, 0, 0.1], [0, 0, 0.3], [0.03, 0, -0.5]]))
+    assert np.allclose(d, [0.05, 0.05, np.hypot(0.03, 0.3) - 0.05]) and np.allclose(g[0], [1, 0, 0]) and np.allclose(g[1], [0, 0, 1])
+    Rw, pw = SC.link_fk(t, np.zeros(t.num_dofs))
+    assert np.abs(self_contact_forces(sc, Rw, pw, 2e5, 2e4)).max() == 0.0                   # the zero pose is collision-free
+    rng = np.random.default_rng(1)
+    hit = 0
+    for _ in range(20):
+        Rw, pw = SC.link_fk(t, rng.uniform(t.dof_lower, t.dof_upper))
+        F = self_contact_forces(sc, Rw, pw, 2e5, 2e4)
+        assert np.abs(F.sum(0)).max() < 1e-6
+        hit += np.linalg.norm(F, axis=1).max() > 1.0
+    assert 5 <= hit <= 19                                                                  # poses anywhere in the limits often self-intersect
+
+
+@pytest.mark.gpu
+def test_cuda_humanoid_self_collision_matches_oracle():
+    import torch
+    from isaacgymdyros_b200.core import CoreConfig, DyrosCore
+    from oracle.physics_oracle import PhysicsOracle
+    from tests.physics_util import oracle_params
+    from tests.test_humanoid_generality import HUMANOID_CFG, humanoid
+    t = humanoid()
+    sc = self_collision_tables(t)
+    N = 48
+    rng = np.random.default_rng(3)
+    cfg = CoreConfig(**HUMANOID_CFG)
+    core = DyrosCore(N, "cuda:0", cfg, tables=t, with_task=False)
+    q = rng.uniform(t.dof_lower, t.dof_upper, (N, t.num_dofs)).astype(np.float32)
+    q[: N // 4] = 0.0
+    root = np.zeros((N, 13), np.float32)
+    root[:, 2] = 4.0
+    quat = rng.normal(0, 1, (N, 4)); root[:, 3:7] = quat / np.linalg.norm(quat, axis=1, keepdims=True)
+    core.sim_t["root_states"].copy_(torch.tensor(root))
+    ds = core.sim_t["dof_state"].view(N, t.num_dofs, 2)
+    ds[:, :, 0] = torch.tensor(q); ds[:, :, 1] = 0
+    core.simulate()
+    torch.cuda.synchronize()
+    got = core.sim_t["self_contact_force"].view(N, t.num_bodies, 3).cpu().numpy().astype(np.float64)
+    o = PhysicsOracle(t, oracle_params(cfg), solver_bodies=cfg.solver_bodies)
+    _, Rw, pw = o.kinematics(root.astype(np.float64), q.astype(np.float64))
+    want = np.stack([self_contact_forces(sc, [R[n] for R in Rw], [p[n] for p in pw], cfg.penalty_stiffness, cfg.penalty_max_force)
+                     for n in range(N)])
+    hit = np.linalg.norm(want, axis=2).max(1) > 1.0
+    assert 0.2 < hit.mean() < 1.0 and not hit[: N // 4].any()
+    assert np.abs(got - want).max() < 2e-3 * np.abs(want).max() + 0.5
+    core.close()
+
+
 @pytest.mark.gpu
 def test_self_collision_terminates_the_episode_in_the_fused_step():
     """T:590: a non-foot body in (self-)contact resets the env in the same step; without the tables it does not."""
