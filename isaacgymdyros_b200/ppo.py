@@ -108,6 +108,79 @@ class FlatActorCritic:
         b = 2 * progress_remaining - 1 if progress_remaining > 0.5 else 0.0
         self.logstd.fill_(self.cfg.sigma_init * b + self.cfg.sigma_last * (1 - b))
 
+    # ------------------------------------------------------------------ on-disk formats of the reference
+    # model.state_dict() of ModelA2CContinuousLogStdDYROS.Network (models_dyros.py:17-20) around the A2CBuilder network
+    # (network_builder_dyros.py:78-97): `a2c_network.sigma`, then the Linear layers of the two nn.Sequential MLPs
+    # (Linear, activation, Linear, activation: indices 0 and 2), then `value`, then `mu`.
+    def _named(self):
+        out = []
+        for prefix, head in (("actor_mlp", None), ("critic_mlp", None), (None, "value"), (None, "mu")):
+            if prefix:
+                for i in range(self.n_hidden):
+                    out.append((f"a2c_network.{prefix}.{2 * i}", self.layers[f"{prefix}.{i}"]))
+            else:
+                out.append((f"a2c_network.{head}", self.layers[head]))
+        return out
+
+    def model_state_dict(self) -> "collections.OrderedDict":
+        import collections
+        sd = collections.OrderedDict()
+        sd["a2c_network.sigma"] = self.logstd.detach().clone().cpu()
+        for name, (w, b) in self._named():
+            sd[name + ".weight"] = w.detach().clone().cpu()
+            sd[name + ".bias"] = b.detach().clone().cpu()
+        return sd
+
+    def load_model_state_dict(self, sd) -> None:
+        want = self.model_state_dict()
+        if set(sd.keys()) != set(want.keys()):
+            raise KeyError(f"model state dict: unexpected {sorted(set(sd) - set(want))}, missing {sorted(set(want) - set(sd))}")
+        for k, v in sd.items():
+            if tuple(v.shape) != tuple(want[k].shape):
+                raise ValueError(f"{k}: shape {tuple(v.shape)}, expected {tuple(want[k].shape)}")
+        with torch.no_grad():
+            self.logstd.copy_(sd["a2c_network.sigma"])
+            for name, (w, b) in self._named():
+                w.copy_(sd[name + ".weight"])
+                b.copy_(sd[name + ".bias"])
+
+    def _optimizer_params(self, actor: bool):
+        """Parameter order of optimizer_actor / optimizer_critic (AG:50-54): the MLP's parameters, then the head's."""
+        names = ([f"actor_mlp.{i}" for i in range(self.n_hidden)] + ["mu"]) if actor else \
+                ([f"critic_mlp.{i}" for i in range(self.n_hidden)] + ["value"])
+        return [p for n in names for p in self.layers[n]]
+
+    def _moment_views(self, p: torch.Tensor):
+        off = (p.data_ptr() - self.flat.data_ptr()) // 4
+        return self.exp_avg[off:off + p.numel()].view(p.shape), self.exp_avg_sq[off:off + p.numel()].view(p.shape)
+
+    def optimizer_state_dict(self, actor: bool, step: int, lr: float) -> dict:
+        """torch.optim.Adam.state_dict() of the fork's optimizer_actor / optimizer_critic."""
+        params = self._optimizer_params(actor)
+        state = {}
+        for i, p in enumerate(params):
+            m, v = self._moment_views(p)
+            if step > 0:
+                state[i] = {"step": torch.tensor(float(step)), "exp_avg": m.detach().clone().cpu(), "exp_avg_sq": v.detach().clone().cpu()}
+        group = {"lr": lr, "betas": (0.9, 0.999), "eps": 1e-08, "weight_decay": 0.0, "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": False,
+                 "params": list(range(len(params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, actor: bool, sd: dict) -> int:
+        params = self._optimizer_params(actor)
+        step = 0
+        with torch.no_grad():
+            for i, p in enumerate(params):
+                m, v = self._moment_views(p)
+                st = sd["state"].get(i)
+                if st is None:
+                    m.zero_(); v.zero_()
+                    continue
+                m.copy_(st["exp_avg"]); v.copy_(st["exp_avg_sq"])
+                step = int(float(st["step"]))
+        return step
+
     def _mlp(self, x, prefix, head):
         for i in range(self.n_hidden):
             w, b = self.layers[f"{prefix}.{i}"]
@@ -460,6 +533,49 @@ class PPOTrainer:
                         self._minibatch(i)
                     self._g_update[i] = g
                 g.replay()
+
+    # ------------------------------------------------------------------ checkpoints (A2C:550-585, AG:97-103) and the
+    # deployment weight dump of the play path (torch_runner_dyros.py:140-150)
+    def state_dict(self) -> dict:
+        n = self.net
+        step = int(self.opt_step.item())
+        return {"model": n.model_state_dict(), "epoch": self.epoch,
+                "optimizer_actor": n.optimizer_state_dict(True, step, float(self.lr[0].item())),
+                "optimizer_critic": n.optimizer_state_dict(False, step, float(self.lr[1].item())),
+                "frame": self.epoch * self.N * self.H * self.world, "last_mean_rewards": -100500, "env_state": None}
+
+    def load_state_dict(self, state: dict) -> None:
+        n = self.net
+        n.load_model_state_dict(state["model"])
+        step = max(n.load_optimizer_state_dict(True, state["optimizer_actor"]), n.load_optimizer_state_dict(False, state["optimizer_critic"]))
+        self.opt_step.fill_(step)
+        self.lr[0] = float(state["optimizer_actor"]["param_groups"][0]["lr"])
+        self.lr[1] = float(state["optimizer_critic"]["param_groups"][0]["lr"])
+        self.epoch = int(state.get("epoch", 0))
+        if self.packed is not None:
+            self.packed.pack()
+
+    def save(self, fn: str) -> str:
+        """agent.save(fn) (AG:97-99): rl_games' torch_ext.save_checkpoint appends '.pth'."""
+        path = fn + ".pth"
+        torch.save(self.state_dict(), path)
+        return path
+
+    def restore(self, fn: str) -> None:
+        self.load_state_dict(torch.load(fn if fn.endswith(".pth") else fn + ".pth", map_location="cpu", weights_only=False))
+
+    def dump_weights_txt(self, out_dir: str = "./result") -> list:
+        """torch_runner_dyros.py:143-147: one np.savetxt file per entry of model.state_dict(), dots replaced by underscores
+        (what the robot-side controller reads)."""
+        import os
+        import numpy as np
+        os.makedirs(out_dir, exist_ok=True)
+        files = []
+        for name, param in self.net.model_state_dict().items():
+            path = os.path.join(out_dir, name.replace(".", "_") + ".txt")
+            np.savetxt(path, param.numpy())
+            files.append(path)
+        return files
 
     def train_epoch(self) -> Dict[str, float]:
         """One epoch of ContinuousA2CBase.train (A2C:983-1008): noise schedule, rollout, update. One device->host read."""

@@ -304,3 +304,25 @@ def test_packed_bf16_networks_match_the_fp32_networks():
     assert torch.equal(pk.w0[1, :, :487].float(), w0.detach().to(torch.bfloat16).float()) and float(pk.w0[:, :, 487].abs().max()) == 0.0
     assert torch.equal(pk.bh[0, :13], tr.net.layers["mu"][1].detach()) and float(pk.wh[0, 13:].abs().max()) == 0.0
     env.close()
+
+
+def test_checkpoint_round_trip_and_weight_dump(tmp_path):
+    """PPOTrainer.save / restore (the fork's agent.save / restore, AG:97-103; format pinned in tests/test_ppo_formats.py) and
+    the ./result weight dump of the play path."""
+    env, tr = make_trainer(N=64, H=8, mb=256)
+    tr.train_epoch()
+    path = tr.save(str(tmp_path / "ckpt"))
+    assert path.endswith("ckpt.pth")
+    env2, tr2 = make_trainer(N=64, H=8, mb=256)
+    assert float((tr2.net.flat - tr.net.flat).abs().max()) > 0
+    tr2.restore(path)
+    for a, b in ((tr.net.flat, tr2.net.flat), (tr.net.exp_avg, tr2.net.exp_avg), (tr.net.exp_avg_sq, tr2.net.exp_avg_sq),
+                 (tr.net.logstd, tr2.net.logstd), (tr.packed.w0, tr2.packed.w0), (tr.packed.bh, tr2.packed.bh)):
+        assert torch.equal(a, b)
+    assert int(tr2.opt_step.item()) == int(tr.opt_step.item()) > 0 and tr2.epoch == 1
+    assert tr2.lr[0].item() == pytest.approx(tr.lr[0].item(), rel=1e-6)
+    files = tr.dump_weights_txt(str(tmp_path / "result"))
+    assert len(files) == 13 and files[0].endswith("a2c_network_sigma.txt")
+    w = np.loadtxt(str(tmp_path / "result" / "a2c_network_mu_weight.txt"))
+    assert np.allclose(w, tr.net.layers["mu"][0].detach().cpu().numpy())
+    env.close(); env2.close()
