@@ -16,9 +16,10 @@ pytestmark = pytest.mark.gpu
 
 
 def test_fused_step_matches_cpu_oracle_rollout():
-    """6 policy steps from the reset pose: physics + PD + noise + reward + reset + obs against the oracle.
-    Integer outputs exact; float tolerances account for fp32 vs fp64 physics over the rollout."""
-    N = 16
+    """8 policy steps of 48 envs from the reset pose: physics + self-collision + PD + noise + reward + reset + obs against
+    the oracle (about a minute of CPU: the oracle is dense fp64 numpy). Integer outputs exact; float tolerances account for
+    fp32 vs fp64 physics over the rollout."""
+    N = 48
     tables, mocap, obs_norm = load_assets()
     cfg = CoreConfig()
     rng = np.random.default_rng(11)
@@ -27,7 +28,7 @@ def test_fused_step_matches_cpu_oracle_rollout():
     ref.s["epi_len"][:4] = 7997
     core = make_core(N)
     load_state(core, ref.s)
-    for t in range(6):
+    for t in range(8):
         noise = O.draw_noise(N, 2, rng)
         actions = rng.uniform(-1, 1, (N, 13)).astype(np.float32)
         want_ids = ref.step(actions, noise)
@@ -40,10 +41,11 @@ def test_fused_step_matches_cpu_oracle_rollout():
         assert np.array_equal(core.task_t["reset_env_ids"][:n].cpu().numpy(), want_ids), f"step {t}"
         for k in ("reset_buf", "timeout_buf", "progress_buf", "mocap_data_idx", "delay_idx", "simul_len"):
             assert np.array_equal(got[k].reshape(-1), np.asarray(ref.s[k]).reshape(-1)), f"step {t} {k}"
-        # fp32 kernel vs fp64 oracle over a 12-sub-step rollout with contact: positions 2e-5, velocities 2e-3
+        # fp32 kernel vs fp64 oracle over a 16-sub-step rollout with contact: positions 2e-5, velocities 2e-3; the reward
+        # (14 exponential terms of those states) reaches 1.2e-3 by the 8th step (5e-4 through the 7th)
         got["root_pose"], got["root_vel"] = got["root_states"][:, :7], got["root_states"][:, 7:]
         ref.s["root_pose"], ref.s["root_vel"] = ref.s["root_states"][:, :7], ref.s["root_states"][:, 7:]
-        for k, tol in (("dof_pos", 2e-5), ("dof_vel", 2e-3), ("root_pose", 2e-5), ("root_vel", 2e-3), ("rew_buf", 5e-4),
+        for k, tol in (("dof_pos", 2e-5), ("dof_vel", 2e-3), ("root_pose", 2e-5), ("root_vel", 2e-3), ("rew_buf", 2e-3),
                        ("obs_buf", 1e-2)):
             err = np.abs(got[k].reshape(ref.s[k].shape) - ref.s[k]).max()
             assert err < tol, f"step {t}: {k} differs by {err}"
