@@ -58,6 +58,7 @@ class PPOConfig:
                                             # kernels (NVLink), "nccl" = one all-reduce call per minibatch (AG:161-173)
     seed: int = 42
     use_cuda_graph: bool = True
+    graph_span: str = "mini_epoch"          # one CUDA graph per "minibatch" update, or one for all minibatches of a "mini_epoch"
 
 
 def layer_shapes(units=(256, 256)):
@@ -423,14 +424,17 @@ class PPOTrainer:
             side = torch.cuda.Stream(device=self.env.device)
             side.wait_stream(torch.cuda.current_stream())
             g = torch.cuda.CUDAGraph()
+            self._rollout_span = self.H if self.cfg.graph_span == "mini_epoch" else 1   # steps per replay
             with torch.cuda.graph(g, stream=side):
-                self._rollout_step()
+                for _ in range(self._rollout_span):
+                    self._rollout_step()
             self._g_rollout = g
             self.buf["step"].zero_()  # (capturing executes nothing; the warm-up step is an extra, unrecorded env step)
-        for _ in range(self.H):
-            if self._g_rollout is not None:
+        if self._g_rollout is not None:
+            for _ in range(self.H // self._rollout_span):
                 self._g_rollout.replay()
-            else:
+        else:
+            for _ in range(self.H):
                 self._rollout_step()
         with torch.no_grad():                                # get_values(self.obs), A2C:686
             if self.packed is not None:
@@ -509,17 +513,19 @@ class PPOTrainer:
     def update(self):
         self._prepare()
         self.stats.zero_()
+        whole = self.cfg.use_cuda_graph and self.cfg.graph_span == "mini_epoch"
         for _ in range(self.cfg.mini_epochs):
-            for i in range(self.num_minibatches):
+            for i in ([-1] if whole else range(self.num_minibatches)):
                 if not self.cfg.use_cuda_graph:
                     self._minibatch(i)
                     continue
                 g = self._g_update.get(i)
                 if g is None:
                     if not self._g_update:  # one eager pass first (autograd / cuBLAS / NCCL lazy init), undone below
+                        i0 = max(i, 0)
                         snap = [t.clone() for t in (self.net.flat, self.net.exp_avg, self.net.exp_avg_sq, self.opt_step, self.lr,
                                                     self.stats, self.buf["mus"])]
-                        self._minibatch(i)
+                        self._minibatch(i0)
                         torch.cuda.synchronize()
                         for t, s in zip((self.net.flat, self.net.exp_avg, self.net.exp_avg_sq, self.opt_step, self.lr, self.stats,
                                          self.buf["mus"]), snap):
@@ -530,7 +536,8 @@ class PPOTrainer:
                     side.wait_stream(torch.cuda.current_stream())
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=side):
-                        self._minibatch(i)
+                        for k in (range(self.num_minibatches) if whole else [i]):
+                            self._minibatch(k)
                     self._g_update[i] = g
                 g.replay()
 
