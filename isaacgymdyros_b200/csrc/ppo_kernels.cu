@@ -569,8 +569,17 @@ __global__ void __launch_bounds__(256) k_ppo_reduce_peers(DyrosPpoPeers P, float
     __threadfence_system();
     st_release_sys(P.flags[threadIdx.x] + P.rank, e + 1u);
   }
-  if ((int)threadIdx.x < P.world)
-    while (ld_acquire_sys(P.flags[P.rank] + threadIdx.x) < e + 1u) __nanosleep(64);
+  if ((int)threadIdx.x < P.world) {
+    // (a rank that never arrives -- a crashed peer -- must not hang the device for ever: after 20 s the kernel traps and
+    // the next CUDA call of the host reports it)
+    unsigned long long t0 = 0, now = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (ld_acquire_sys(P.flags[P.rank] + threadIdx.x) < e + 1u) {
+      __nanosleep(64);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (now - t0 > 20000000000ull) __trap();
+    }
+  }
   __syncthreads();
   float sq = 0.f;
   const int n4 = n / 4;
