@@ -334,16 +334,32 @@ static std::string build_model_tables(const DyrosModelDesc* m, Blob& bl, DevMode
     auto section = [&]() { hot.resize((hot.size() + 3) & ~size_t(3)); return (int)hot.size(); };
     auto f2i = [](float f) { int i; memcpy(&i, &f, 4); return i; };
     std::vector<unsigned short> sp;
+    std::vector<int> q0(npair + 1, 0);
     for (int k = 0; k < npair; ++k) {
       const int li = m->sc_pairs[2 * k], lj = m->sc_pairs[2 * k + 1];
       if (li < 0 || li >= nl || lj < 0 || lj >= nl) MFAIL("self-collision pair %d: link out of range", k);
       for (int a = m->sc_link_shape0[li]; a < m->sc_link_shape0[li + 1]; ++a)
         for (int b = m->sc_link_shape0[lj]; b < m->sc_link_shape0[lj + 1]; ++b) sp.push_back((unsigned short)(a | b << 8));
+      q0[k + 1] = (int)sp.size();
     }
     dm.sc_nq = (int)sp.size();
-    // padded to whole batches of the kernel's sweep with a pair of two far-apart dummy shapes (ns, ns + 1)
+    // padded to whole batches of the kernel's sweep with a pair of two far-apart dummy shapes (ns, ns + 1); at most 16
+    // chunks (the kernel keeps one bit per chunk), each a whole number of batches
     while (sp.size() % SC_SWEEP_BATCH) sp.push_back((unsigned short)(ns | (ns + 1) << 8));
+    {
+      const int nbatch = (int)sp.size() / SC_SWEEP_BATCH;
+      dm.sc_chunk = SC_SWEEP_BATCH * std::max(1, (nbatch + 15) / 16);
+      while (sp.size() % dm.sc_chunk) sp.push_back((unsigned short)(ns | (ns + 1) << 8));
+    }
     dm.sc_nq_padded = (int)sp.size();
+    dm.sc_o_pair = section();
+    for (int k = 0; k < npair; ++k) {
+      unsigned mask = 0;
+      for (int c = q0[k] / dm.sc_chunk; c <= (q0[k + 1] - 1) / dm.sc_chunk && q0[k + 1] > q0[k]; ++c) mask |= 1u << c;
+      hot.push_back((int)((unsigned)m->sc_pairs[2 * k] | (unsigned)m->sc_pairs[2 * k + 1] << 8 | mask << 16));
+    }
+    dm.sc_o_lsph = section();
+    for (int k = 0; k < (ns ? nl * 4 : 0); ++k) hot.push_back(f2i((float)m->sc_link_sphere[k]));
     dm.sc_o_sp = section();
     for (size_t k = 0; k < sp.size(); k += 2) hot.push_back((int)(sp[k] | (unsigned)sp[k + 1] << 16));
     dm.sc_o_shape = section();

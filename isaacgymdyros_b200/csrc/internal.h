@@ -60,13 +60,16 @@ struct DevModel {
   const int* sched;             // [T*DYROS_LANES]
   const float* link_reach;      // [nl] bounding radius of the link's penalty candidates about its origin
   // self-collision tables (see DyrosModelDesc), packed for k_self_collision, which stages all of them in shared memory:
-  //   sp     [nq_padded] uint16: shape a | shape b << 8: the shape pairs of every candidate link pair, flattened
+  //   pair   [np] link i | link j << 8 | (bit c set: chunk c of `sp` holds shape pairs of this link pair) << 16
+  //   lsph   [nl*4] float: bounding sphere of the link's shapes (link frame)
+  //   sp     [nq_padded] uint16: shape a | shape b << 8: the shape pairs of every candidate link pair, flattened in the
+  //          order of `pair`, cut into at most 16 chunks of sc_chunk pairs (a multiple of SC_SWEEP_BATCH)
   //   shape  [ns*16] float: centre 3, rot 9 (row-major, columns = axes), size 3, bounding radius about the centre
   //   meta   [ns*2] link | body << 8 | kind << 16, first sample | number of samples << 16
   //   sample [nsamp*4] float: position in the link frame, radius
-  int sc_ns, sc_nsamp, sc_np, sc_nq, sc_nq_padded;
+  int sc_ns, sc_nsamp, sc_np, sc_nq, sc_nq_padded, sc_chunk;
   const int* sc_hot;
-  int sc_hot_words, sc_o_sp, sc_o_shape, sc_o_meta, sc_o_sample;
+  int sc_hot_words, sc_o_pair, sc_o_lsph, sc_o_sp, sc_o_shape, sc_o_meta, sc_o_sample;
   const void* blob;             // base of the packed tables; [blob, blob + hot_bytes) is what the kernel stages in smem
   int hot_bytes;
   // word offsets of the hot tables inside the staged prefix (same order as the pointers above)

@@ -533,8 +533,11 @@ __global__ void __launch_bounds__(64) k_rigid_body_state(DevModel m, SimParams p
 // One warp per env, 16 envs per CTA; the CTA stages the packed tables (DevModel::sc_hot, ~13 KB for TOCABI) in shared
 // memory while the physics kernel before it drains (PDL).
 //   0. the env's link poses -> shared memory (coalesced); world centres of the shapes' bounding spheres;
-//   1. sweep over the shape pairs of all candidate link pairs (1656 for TOCABI), one per lane, 4 rounds in flight: two
-//      bounding spheres overlap -> hit list (standing: ~20);
+//   1. (a) the 497 candidate link pairs, one per lane, 4 rounds in flight: overlapping link spheres mark, warp
+//      uniformly (redux.or), the chunks of the shape-pair list that hold their shape pairs -- the link pairs are ordered
+//      by how often they are near each other, so a standing / walking robot marks 3-5 of 13 chunks; (b) sweep over the
+//      shape pairs of the marked chunks (1656 in all for TOCABI), one per lane, 4 rounds in flight: two bounding spheres
+//      overlap -> hit list (standing: ~20);
 //   2. hit list, one per lane: face-axis separating-axis test of the two oriented bounding boxes (a box is its own, a
 //      cylinder's is r x r x h) -> what stays is really close (standing: a few), compacted with a ballot;
 //   3. half a warp per surviving shape pair: lane = one sample sphere of one shape against the exact box / cylinder of
@@ -585,6 +588,7 @@ __device__ __forceinline__ float sc_sdf(int kind, V3 size, V3 x, V3& g) {
 }
 struct ScEnv {  // views into the env's block of shared memory (sized by the model: sc_env_bytes)
   float* pose;                // [nl*12]
+  float4* link_c;             // [nl]: world centre and radius of each link's bounding sphere
   float4* shape_c;            // [ns+2]: world centre and radius of each shape's bounding sphere; two far-apart dummies
   float* force;               // [nb*3]
   int* count;                 // [0] hits, [1] any contact
@@ -592,12 +596,13 @@ struct ScEnv {  // views into the env's block of shared memory (sized by the mod
 };
 __host__ __device__ inline int sc_align4(int words) { return (words + 3) & ~3; }
 __host__ __device__ inline int sc_env_bytes(int nl, int ns, int nb) {
-  return 4 * (sc_align4(nl * 12) + (ns + 2) * 4 + sc_align4(nb * 3) + 4) + 2 * kScHits;
+  return 4 * (sc_align4(nl * 12) + nl * 4 + (ns + 2) * 4 + sc_align4(nb * 3) + 4) + 2 * kScHits;
 }
 __device__ __forceinline__ ScEnv sc_env_views(void* base, int nl, int ns, int nb) {
   ScEnv E;
   float* f = static_cast<float*>(base);
   E.pose = f; f += sc_align4(nl * 12);
+  E.link_c = reinterpret_cast<float4*>(f); f += nl * 4;
   E.shape_c = reinterpret_cast<float4*>(f); f += (ns + 2) * 4;
   E.force = f; f += sc_align4(nb * 3);
   E.count = reinterpret_cast<int*>(f); f += 4;
@@ -605,6 +610,8 @@ __device__ __forceinline__ ScEnv sc_env_views(void* base, int nl, int ns, int nb
   return E;
 }
 struct ScTab {  // the staged tables
+  const unsigned* pair;
+  const float* lsph;
   const unsigned short* sp;
   const float* shape;
   const int* meta;
@@ -704,10 +711,20 @@ __global__ void __launch_bounds__(kScEnvs * 32, 2) k_self_collision(DevModel m, 
   __syncthreads();
   if (!live) return;
   ScTab T;
+  T.pair = reinterpret_cast<const unsigned*>(tab + m.sc_o_pair);
+  T.lsph = reinterpret_cast<const float*>(tab + m.sc_o_lsph);
   T.sp = reinterpret_cast<const unsigned short*>(tab + m.sc_o_sp);
   T.shape = reinterpret_cast<const float*>(tab + m.sc_o_shape);
   T.meta = tab + m.sc_o_meta;
   T.sample = reinterpret_cast<const float*>(tab + m.sc_o_sample);
+  for (int l = lane; l < m.nl; l += 32) {
+    const float4 ls = *reinterpret_cast<const float4*>(T.lsph + 4 * l);
+    M3 R;
+    V3 t;
+    sc_pose(W.pose, l, R, t);
+    const V3 c = mul(R, v3(ls.x, ls.y, ls.z)) + t;
+    W.link_c[l] = make_float4(c.x, c.y, c.z, ls.w);
+  }
   for (int s = lane; s < m.sc_ns; s += 32) {
     const float4 s0 = *reinterpret_cast<const float4*>(T.shape + 16 * s);
     M3 R;
@@ -718,23 +735,44 @@ __global__ void __launch_bounds__(kScEnvs * 32, 2) k_self_collision(DevModel m, 
   }
   if (lane < 2) W.shape_c[m.sc_ns + lane] = make_float4(lane ? -1e18f : 1e18f, 0.f, 0.f, 0.f);
   __syncwarp();
-  // 1. bounding spheres of every candidate shape pair (the list is padded to whole batches with a far-apart dummy pair)
-  const char* centres = reinterpret_cast<const char*>(W.shape_c);
-  for (int base = lane; base < m.sc_nq_padded; base += SC_SWEEP_BATCH) {
-    unsigned sp[4];
-    float4 ca[4], cb[4];
+  // 1a. link spheres: which chunks of the shape-pair list hold pairs of links that are near each other at all
+  unsigned active = 0;
+  {
+    const char* lcs = reinterpret_cast<const char*>(W.link_c);
+    for (int base = lane; base < m.sc_np; base += 128) {
+      unsigned pt[4], mk = 0;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) sp[u] = T.sp[base + 32 * u];
+      for (int u = 0; u < 4; ++u) pt[u] = base + 32 * u < m.sc_np ? T.pair[base + 32 * u] : 0u;  // (0: link 0 against itself, no chunk)
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      ca[u] = *reinterpret_cast<const float4*>(centres + ((sp[u] & 0xffu) << 4));
-      cb[u] = *reinterpret_cast<const float4*>(centres + ((sp[u] >> 4) & 0xff0u));
+      for (int u = 0; u < 4; ++u) {
+        const float4 a = *reinterpret_cast<const float4*>(lcs + ((pt[u] & 0xffu) << 4));
+        const float4 c = *reinterpret_cast<const float4*>(lcs + ((pt[u] >> 4) & 0xff0u));
+        if (sc_spheres_overlap(a, c)) mk |= pt[u] >> 16;
+      }
+      active |= __reduce_or_sync(kFull, mk);
     }
+  }
+  // 1b. bounding spheres of the candidate shape pairs in the active chunks (the list is padded to whole chunks with a
+  //     far-apart dummy pair)
+  const char* centres = reinterpret_cast<const char*>(W.shape_c);
+  for (int c0 = 0; c0 < m.sc_nq_padded; c0 += m.sc_chunk, active >>= 1) {
+    if (!(active & 1u)) continue;
+    for (int base = c0 + lane; base < c0 + m.sc_chunk; base += SC_SWEEP_BATCH) {
+      unsigned sp[4];
+      float4 ca[4], cb[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (sc_spheres_overlap(ca[u], cb[u])) {
-        const int at = atomicAdd(&W.count[0], 1);
-        if (at < p.sc_hits_cap) W.hits[at] = (unsigned short)sp[u];
+      for (int u = 0; u < 4; ++u) sp[u] = T.sp[base + 32 * u];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ca[u] = *reinterpret_cast<const float4*>(centres + ((sp[u] & 0xffu) << 4));
+        cb[u] = *reinterpret_cast<const float4*>(centres + ((sp[u] >> 4) & 0xff0u));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (sc_spheres_overlap(ca[u], cb[u])) {
+          const int at = atomicAdd(&W.count[0], 1);
+          if (at < p.sc_hits_cap) W.hits[at] = (unsigned short)sp[u];
+        }
       }
     }
   }
