@@ -545,8 +545,9 @@ __global__ void __launch_bounds__(64) k_rigid_body_state(DevModel m, SimParams p
 //      distance with the penalty stiffness of the ground contacts, accumulated per body in shared memory.
 // Every cull is conservative, so the result is that of the plain double loop restated in oracle/selfcollision_oracle.py
 // (up to the order of the sums); an env that overflows the hit list is swept again without it, never dropping a contact.
-// (Measured dead ends, profiles/r2_self_collision.md: a link-sphere level above the shape spheres costs more in list
-// handling than the 1200 sphere tests it saves; two warps per env only fit one wave at 32 registers.)
+// (Measured dead ends, profiles/r2_self_collision.md: link-level culls that build LISTS of link pairs cost more in list
+// handling -- compaction, prefix sums, mapping lanes to shape pairs -- than the sphere tests they save; two warps per env
+// only fit one wave at 32 registers; a lane-chunked sweep doubles the shared-memory bank conflicts.)
 constexpr int kScEnvs = 16;    // envs (warps) per CTA
 constexpr int kScHits = 128;   // shape pairs whose spheres overlap
 __device__ __forceinline__ float sc_sdf(int kind, V3 size, V3 x, V3& g) {
