@@ -72,7 +72,7 @@ def parse():
                          "on-device PPO training (BASELINE configs[4]): --steps / --warmup count EPOCHS of 128 env steps + 640 updates")
     ap.add_argument("--horizon", type=int, default=128)
     ap.add_argument("--ppo-dtype", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--grad-sync", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--grad-sync", default="peer", choices=["peer", "peer2", "nccl"],
                     help="PPO gradient exchange at N > 1: sum over peer-mapped buffers inside the optimiser's kernels, or one NCCL all-reduce")
     return ap.parse_args()
 
@@ -547,7 +547,8 @@ def run_ppo(a):
                            "mini_epochs": cfg.mini_epochs, "updates_per_epoch": updates, "parameters": tr.net.n,
                            "gradient_bucket_bytes": tr.net.n * 4,
                            "networks": "packed bf16 (batch-2 GEMMs)" if tr.packed is not None else "fp32 autograd",
-                           "grad_sync": ("peer memory (dyros_ppo_reduce_peers)" if tr.peers is not None else "nccl all_reduce") if world > 1 else "none"},
+                           "grad_sync": (("peer memory, two-phase (reduce-scatter + all-gather)" if cfg.grad_sync == "peer2" else "peer memory (dyros_ppo_reduce_peers)")
+                                         if tr.peers is not None else "nccl all_reduce") if world > 1 else "none"},
                 "clocks": clk.summary(),
                 "breakdown_ms_per_epoch": {"rollout_and_gae": t_roll / K, "update": t_upd / K,
                                            "update_per_minibatch": t_upd / K / updates,

@@ -423,8 +423,12 @@ typedef struct DyrosPpoPeers {
   int32_t stride;            /* floats between a rank's two gradient buffers */
   float* grad[8][2];         /* [rank][parity of the minibatch counter] */
   uint32_t* flags[8];        /* [rank] -> that rank's 8 flag words: flags[r][q] = minibatches rank q has published to rank r */
-  uint32_t* epoch;           /* local (1): minibatches finished; advanced by dyros_ppo_reduce_peers */
-  uint32_t* ticket;          /* local (1): zero-initialised scratch */
+  uint32_t* epoch;           /* local (1): minibatches finished; advanced by dyros_ppo_reduce_peers / dyros_ppo_all_gather_peers */
+  uint32_t* ticket;          /* local (4): zero-initialised scratch */
+  /* two-phase exchange only (dyros_ppo_reduce_scatter_peers + dyros_ppo_all_gather_peers); may be NULL otherwise */
+  float* sum[8][2];          /* [rank][parity]: `stride` floats, of which the rank writes ITS slice of the summed gradient */
+  uint32_t* flags2[8];       /* [rank] -> 8 more flag words: "rank q has published its summed slice" */
+  float* pnorm[8];           /* [rank] -> 2 floats [parity]: squared norm of the actor entries of the rank's slice */
 } DyrosPpoPeers;
 /* Peer-shareable device memory for the exchange (cudaMalloc + CUDA IPC). dyros_peer_alloc: `bytes` of zeroed memory on
  * the current device and its 64-byte IPC handle (to be sent to the other ranks of the node by any host channel).
@@ -439,6 +443,12 @@ int dyros_ppo_unpack_grads_peers(const DyrosPpoNet* net, const DyrosPpoPeers* pe
 /* Publishes this rank's buffer, waits for every rank's, and writes the SUM over ranks (in rank order: bit-identical on
  * every rank) to flat_grad_sum (local, n floats); norm2_accum += squared norm of its first n_actor entries. */
 int dyros_ppo_reduce_peers(const DyrosPpoPeers* peers, float* flat_grad_sum, int n, int n_actor, float* norm2_accum, void* stream);
+/* The same exchange in two phases, each rank reading 2 x (world-1)/world of a buffer instead of (world-1) buffers:
+ * reduce-scatter (rank r sums slice r of all ranks' buffers, in rank order, into flat_grad_sum and its published `sum`
+ * buffer) and all-gather (every rank copies the other ranks' summed slices; norm2_accum += the slices' partial norms in
+ * rank order). Call one after the other on the same stream. */
+int dyros_ppo_reduce_scatter_peers(const DyrosPpoPeers* peers, float* flat_grad_sum, int n, int n_actor, void* stream);
+int dyros_ppo_all_gather_peers(const DyrosPpoPeers* peers, float* flat_grad_sum, int n, float* norm2_accum, void* stream);
 
 #ifdef __cplusplus
 }

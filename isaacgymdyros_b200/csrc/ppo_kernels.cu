@@ -625,6 +625,103 @@ __global__ void __launch_bounds__(256) k_ppo_reduce_peers(DyrosPpoPeers P, float
     }
   }
 }
+
+// ---- the same exchange in two phases (reduce-scatter, all-gather): at 8 ranks a rank reads 2 x 7/8 of a buffer over
+// NVLink instead of 7 whole buffers. Slice r = floats [r * len, (r + 1) * len), len = stride / world rounded up to 4.
+__device__ __forceinline__ void peers_wait(const unsigned* flags, int world, unsigned want) {
+  if ((int)threadIdx.x < world) {
+    unsigned long long t0 = 0, now = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (ld_acquire_sys(flags + threadIdx.x) < want) {
+      __nanosleep(64);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (now - t0 > 20000000000ull) __trap();
+    }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ int peers_slice_len(const DyrosPpoPeers& P) { return ((P.stride + P.world - 1) / P.world + 3) & ~3; }
+__global__ void __launch_bounds__(256) k_ppo_reduce_scatter_peers(DyrosPpoPeers P, float* __restrict__ out, int n, int n_actor) {
+  const unsigned e = *P.epoch;
+  const int par = (int)(e & 1u);
+  if (blockIdx.x == 0 && (int)threadIdx.x < P.world) {
+    __threadfence_system();
+    st_release_sys(P.flags[threadIdx.x] + P.rank, e + 1u);
+  }
+  peers_wait(P.flags[P.rank], P.world, e + 1u);
+  const int len = peers_slice_len(P), lo = P.rank * len, hi = min(P.stride, lo + len);
+  float* mine = P.sum[P.rank][par];
+  float sq = 0.f;
+  for (int j = lo + 4 * (blockIdx.x * blockDim.x + threadIdx.x); j < hi; j += 4 * gridDim.x * blockDim.x) {
+    float4 x[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < P.world) x[r] = ld_cg4(P.grad[r][par] + j);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < P.world) {
+        s.x += x[r].x; s.y += x[r].y; s.z += x[r].z; s.w += x[r].w;
+      }
+    *reinterpret_cast<float4*>(mine + j) = s;
+    const float v[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (j + c < n) {
+        out[j + c] = v[c];
+        if (j + c < n_actor) sq += v[c] * v[c];
+      }
+  }
+  sq = warp_sum(sq);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += part[k];
+    float* acc = reinterpret_cast<float*>(P.ticket + 2);
+    atomicAdd(acc, t);
+    __threadfence();
+    if (atomicAdd(P.ticket, 1u) == gridDim.x - 1) {  // the last block publishes the slice and its partial norm
+      *P.ticket = 0u;
+      P.pnorm[P.rank][par] = *reinterpret_cast<volatile float*>(acc);
+      *acc = 0.f;
+      __threadfence_system();
+      for (int q = 0; q < P.world; ++q) st_release_sys(P.flags2[q] + P.rank, e + 1u);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_ppo_all_gather_peers(DyrosPpoPeers P, float* __restrict__ out, int n, float* __restrict__ norm2) {
+  const unsigned e = *P.epoch;
+  const int par = (int)(e & 1u);
+  peers_wait(P.flags2[P.rank], P.world, e + 1u);
+  const int len = peers_slice_len(P);
+  // the other ranks' slices, one after the other: element index over (world - 1) * len / 4 float4s
+  const int per4 = len / 4, total4 = (P.world - 1) * per4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+    int q = i / per4;
+    q += q >= P.rank;
+    const int j = q * len + 4 * (i % per4);
+    if (j >= P.stride) continue;
+    const float4 s = ld_cg4(P.sum[q][par] + j);
+    const float v[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (j + c < n) out[j + c] = v[c];
+  }
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0 && norm2) {
+      float t = 0.f;
+      for (int q = 0; q < P.world; ++q) t += __ldcg(P.pnorm[q] + par);  // rank order: the same bits on every rank
+      atomicAdd(norm2, t);
+    }
+    __threadfence();
+    if (atomicAdd(P.ticket + 1, 1u) == gridDim.x - 1) {
+      P.ticket[1] = 0u;
+      *P.epoch = e + 1u;
+    }
+  }
+}
 }  // namespace dyros
 
 using namespace dyros;
@@ -649,7 +746,8 @@ static int configure_ppo_kernels() {  // (common.cuh: one carve-out for every ke
   DY_CUDA(prefer_max_smem_carveout(k_ppo_relu_bwd)); DY_CUDA(prefer_max_smem_carveout(k_ppo_act_packed));
   DY_CUDA(prefer_max_smem_carveout(k_ppo_loss_grad_packed)); DY_CUDA(prefer_max_smem_carveout(k_ppo_pack));
   DY_CUDA(prefer_max_smem_carveout(k_ppo_unpack)); DY_CUDA(prefer_max_smem_carveout(k_ppo_adam_pack));
-  DY_CUDA(prefer_max_smem_carveout(k_ppo_reduce_peers));
+  DY_CUDA(prefer_max_smem_carveout(k_ppo_reduce_peers)); DY_CUDA(prefer_max_smem_carveout(k_ppo_reduce_scatter_peers));
+  DY_CUDA(prefer_max_smem_carveout(k_ppo_all_gather_peers));
   done = true;
   return 0;
 }
@@ -806,6 +904,27 @@ int dyros_ppo_reduce_peers(const DyrosPpoPeers* peers, float* flat_grad_sum, int
   PPO_CHECK((reinterpret_cast<uintptr_t>(flat_grad_sum) & 15) == 0, "dyros_ppo_reduce_peers: the output must be 16-byte aligned");
   if (configure_ppo_kernels()) return 1;
   k_ppo_reduce_peers<<<148 * 2, 256, 0, (cudaStream_t)stream>>>(*peers, flat_grad_sum, n, n_actor, norm2_accum, peers->ticket);
+  DY_LAUNCH_CHECK();
+  return 0;
+}
+static bool ppo_peers2_ok(const DyrosPpoPeers* p) {
+  if (!ppo_peers_ok(p)) return false;
+  for (int r = 0; r < p->world; ++r)
+    if (!p->sum[r][0] || !p->sum[r][1] || !p->flags2[r] || !p->pnorm[r]) return false;
+  return true;
+}
+int dyros_ppo_reduce_scatter_peers(const DyrosPpoPeers* peers, float* flat_grad_sum, int n, int n_actor, void* stream) {
+  PPO_CHECK(ppo_peers2_ok(peers) && flat_grad_sum && n > 0 && n <= peers->stride && n_actor >= 0 && n_actor <= n,
+            "dyros_ppo_reduce_scatter_peers: bad argument");
+  if (configure_ppo_kernels()) return 1;
+  k_ppo_reduce_scatter_peers<<<48, 256, 0, (cudaStream_t)stream>>>(*peers, flat_grad_sum, n, n_actor);
+  DY_LAUNCH_CHECK();
+  return 0;
+}
+int dyros_ppo_all_gather_peers(const DyrosPpoPeers* peers, float* flat_grad_sum, int n, float* norm2_accum, void* stream) {
+  PPO_CHECK(ppo_peers2_ok(peers) && flat_grad_sum && n > 0 && n <= peers->stride, "dyros_ppo_all_gather_peers: bad argument");
+  if (configure_ppo_kernels()) return 1;
+  k_ppo_all_gather_peers<<<148, 256, 0, (cudaStream_t)stream>>>(*peers, flat_grad_sum, n, norm2_accum);
   DY_LAUNCH_CHECK();
   return 0;
 }

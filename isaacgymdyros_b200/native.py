@@ -109,7 +109,8 @@ class DyrosPpoNet(C.Structure):
 
 class DyrosPpoPeers(C.Structure):
     _fields_ = [("world", i32), ("rank", i32), ("stride", i32), ("grad", (C.c_void_p * 2) * 8), ("flags", C.c_void_p * 8),
-                ("epoch", C.c_void_p), ("ticket", C.c_void_p)]
+                ("epoch", C.c_void_p), ("ticket", C.c_void_p), ("sum", (C.c_void_p * 2) * 8), ("flags2", C.c_void_p * 8),
+                ("pnorm", C.c_void_p * 8)]
 
 
 _VP, _INT = C.c_void_p, C.c_int
@@ -134,6 +135,8 @@ SIGNATURES = {
     "dyros_peer_free": (_INT, [_VP]),
     "dyros_ppo_unpack_grads_peers": (_INT, [_PN, C.POINTER(DyrosPpoPeers), _VP]),
     "dyros_ppo_reduce_peers": (_INT, [C.POINTER(DyrosPpoPeers), _VP, _INT, _INT, _VP, _VP]),
+    "dyros_ppo_reduce_scatter_peers": (_INT, [C.POINTER(DyrosPpoPeers), _VP, _INT, _INT, _VP]),
+    "dyros_ppo_all_gather_peers": (_INT, [C.POINTER(DyrosPpoPeers), _VP, _INT, _VP, _VP]),
     "dyros_ppo_adam_packed": (_INT, [_PN, _VP, _VP, _VP, _VP, f32, f32, _INT, _VP, _VP, _VP, f32, f32, f32, f32, f32, _INT, _VP]),
     "dyros_last_error": (C.c_char_p, []),
     "dyros_abi_version": (_INT, []),

@@ -55,7 +55,8 @@ class PPOConfig:
     sigma_last: float = -2.9957             # PPO:24-26
     mixed_precision: str = "bf16"           # "bf16" | "fp32"
     grad_sync: str = "peer"                 # world > 1, bf16 path: "peer" = sum over peer-mapped buffers inside the optimiser's
-                                            # kernels (NVLink), "nccl" = one all-reduce call per minibatch (AG:161-173)
+                                            # kernels (NVLink); "peer2" = the same as reduce-scatter + all-gather;
+                                            # "nccl" = one all-reduce call per minibatch (AG:161-173)
     seed: int = 42
     use_cuda_graph: bool = True
     graph_span: str = "mini_epoch"          # one CUDA graph per "minibatch" update, or one for all minibatches of a "mini_epoch"
@@ -293,7 +294,7 @@ class PeerGrads:
             raise ValueError("peer-memory gradient exchange: 2..8 ranks on one node")
         self.lib = native.load()
         self.stride = (n + 3) // 4 * 4
-        nfl = 2 * self.stride + 16                                   # [G0 | G1 | 8 flag words + pad]
+        nfl = 4 * self.stride + 32                                   # [G0 | G1 | S0 | S1 | 8 + 8 flag words | 2 partial norms + pad]
         with torch.cuda.device(device):
             ptr, handle = C.c_void_p(), C.create_string_buffer(64)
             native.check(self.lib.dyros_peer_alloc(C.c_size_t(4 * nfl), C.byref(ptr), handle), "dyros_peer_alloc")
@@ -310,13 +311,16 @@ class PeerGrads:
                 self._opened.append(p.value)
                 self.ptrs.append(p.value)
             self.local = torch.as_tensor(_DevMem(self._own, nfl), device=device)   # this rank's block, for tests and tools
-        self.epoch = torch.zeros(2, dtype=torch.int32, device=device)              # [epoch, ticket]
+        self.epoch = torch.zeros(8, dtype=torch.int32, device=device)              # [epoch, pad, pad, pad | 4 scratch words]
         d = native.DyrosPpoPeers()
         d.world, d.rank, d.stride = world, rank, self.stride
         for r, base in enumerate(self.ptrs):
             d.grad[r][0], d.grad[r][1] = base, base + 4 * self.stride
-            d.flags[r] = base + 8 * self.stride
-        d.epoch, d.ticket = self.epoch.data_ptr(), self.epoch.data_ptr() + 4
+            d.sum[r][0], d.sum[r][1] = base + 8 * self.stride, base + 12 * self.stride
+            d.flags[r] = base + 16 * self.stride
+            d.flags2[r] = base + 16 * self.stride + 32
+            d.pnorm[r] = base + 16 * self.stride + 64
+        d.epoch, d.ticket = self.epoch.data_ptr(), self.epoch.data_ptr() + 16
         self.desc = d
         torch.cuda.synchronize(device)
         dist.barrier()   # every rank has mapped every (zeroed) buffer before anybody publishes
@@ -348,10 +352,10 @@ class PPOTrainer:
             dist.broadcast(self.net.flat, 0)
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
         self.packed: Optional[PackedNets] = PackedNets(self.net, self.lib) if c.mixed_precision == "bf16" else None
-        if c.grad_sync not in ("peer", "nccl"):
-            raise ValueError("grad_sync: 'peer' or 'nccl'")
+        if c.grad_sync not in ("peer", "peer2", "nccl"):
+            raise ValueError("grad_sync: 'peer', 'peer2' or 'nccl'")
         self.peers: Optional[PeerGrads] = (PeerGrads(self.net.n, dev, rank, world)
-                                           if world > 1 and self.packed is not None and c.grad_sync == "peer" else None)
+                                           if world > 1 and self.packed is not None and c.grad_sync in ("peer", "peer2") else None)
         if self.packed is not None:  # the rollout's observations are kept as the bf16 rows the GEMMs read (N*H x 488)
             self.x_step = z(N, PackedNets.K0, dt=torch.bfloat16)
             self.x_roll = z(N * H, PackedNets.K0, dt=torch.bfloat16)
@@ -480,8 +484,14 @@ class PPOTrainer:
             pk.unpack_grads(self.norm2 if clip > 0 else None)   # (the norm reduction rides along)
         elif self.peers is not None:  # optimizer.synchronize() (AG:161-173) over peer memory: publish, wait, sum in rank order
             native.check(self.lib.dyros_ppo_unpack_grads_peers(C.byref(pk.desc), C.byref(self.peers.desc), self._stream), "unpack_peers")
-            native.check(self.lib.dyros_ppo_reduce_peers(C.byref(self.peers.desc), self._p(n.grad), n.n, n.n_actor,
-                                                         self._p(self.norm2) if clip > 0 else None, self._stream), "reduce_peers")
+            if c.grad_sync == "peer2":
+                native.check(self.lib.dyros_ppo_reduce_scatter_peers(C.byref(self.peers.desc), self._p(n.grad), n.n, n.n_actor,
+                                                                     self._stream), "reduce_scatter_peers")
+                native.check(self.lib.dyros_ppo_all_gather_peers(C.byref(self.peers.desc), self._p(n.grad), n.n,
+                                                                 self._p(self.norm2) if clip > 0 else None, self._stream), "all_gather_peers")
+            else:
+                native.check(self.lib.dyros_ppo_reduce_peers(C.byref(self.peers.desc), self._p(n.grad), n.n, n.n_actor,
+                                                             self._p(self.norm2) if clip > 0 else None, self._stream), "reduce_peers")
         else:  # ... or as one NCCL all-reduce of the flat bucket
             import torch.distributed as dist
             pk.unpack_grads(None)

@@ -24,5 +24,6 @@ def test_peer_memory_exchange_equals_nccl_allreduce():
     assert out.returncode == 0, text[-3000:]
     assert len(re.findall(r"nccl steps 20 identical across ranks True", text)) == 2, text[-3000:]
     assert len(re.findall(r"peer steps 20 identical across ranks True", text)) == 2, text[-3000:]
-    rels = [float(x) for x in re.findall(r"peer vs nccl max \|diff\| \S+ rel (\S+)", text)]
-    assert len(rels) == 2 and max(rels) < 1e-6, text[-3000:]
+    assert len(re.findall(r"peer2 steps 20 identical across ranks True", text)) == 2, text[-3000:]   # reduce-scatter + all-gather
+    rels = [float(x) for x in re.findall(r"peer2? vs nccl max \|diff\| \S+ rel (\S+)", text)]
+    assert len(rels) == 4 and max(rels) < 1e-6, text[-3000:]

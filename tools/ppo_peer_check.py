@@ -9,9 +9,9 @@ dist.init_process_group("nccl", device_id=torch.device(dev))
 from isaacgymdyros_b200 import DyrosDynamicWalk, default_cfg
 from isaacgymdyros_b200.ppo import PPOConfig, PPOTrainer
 res = {}
-for mode in ("nccl", "peer"):
+for mode in ("nccl", "peer", "peer2"):
     env = DyrosDynamicWalk(default_cfg(256), dev, rank=rank, use_cuda_graph=False)
-    tr = PPOTrainer(env, PPOConfig(horizon_length=8, minibatch_size=512, grad_sync=mode, use_cuda_graph=(mode == "peer")), rank=rank, world=world)
+    tr = PPOTrainer(env, PPOConfig(horizon_length=8, minibatch_size=512, grad_sync=mode, use_cuda_graph=(mode != "nccl")), rank=rank, world=world)
     g = torch.Generator(device=dev); g.manual_seed(100 + rank)       # different data per rank, same in both modes
     r = lambda *s: torch.randn(*s, device=dev, generator=g)
     N, H = tr.N, tr.H
@@ -33,7 +33,8 @@ for mode in ("nccl", "peer"):
     if tr.peers is not None:
         tr.peers.close()
     env.close()
-d = (res["peer"] - res["nccl"]).abs().max().item()
-print(f"{rank} peer vs nccl max |diff| {d} rel {d / res['nccl'].abs().max().item()}\n", end="", flush=True)
+for mode in ("peer", "peer2"):
+    d = (res[mode] - res["nccl"]).abs().max().item()
+    print(f"{rank} {mode} vs nccl max |diff| {d} rel {d / res['nccl'].abs().max().item()}\n", end="", flush=True)
 dist.barrier(); torch.cuda.synchronize()
 os._exit(0)
