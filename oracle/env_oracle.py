@@ -34,10 +34,9 @@ class EnvOracle:
     def simulate(self, s, tau, ext):
         """gym.set_dof_actuation_force_tensor + gym.simulate + refresh (T:520-526) on the oracle state dict."""
         if self.sc is not None:  # from the poses the sub-step starts from, as its ground contact forces are
-            from .selfcollision_oracle import self_contact_forces
+            from .selfcollision_oracle import self_contact_forces_batch
             _, Rw, pw = self.phys.kinematics(s["root_states"].astype(float), s["dof_pos"].astype(float))
-            sc_f = np.stack([self_contact_forces(self.sc, [R[n] for R in Rw], [p_[n] for p_ in pw], self.phys.p.pen_k,
-                                                 self.phys.p.pen_fmax) for n in range(self.N)])
+            sc_f = self_contact_forces_batch(self.sc, Rw, pw, self.phys.p.pen_k, self.phys.p.pen_fmax)
         root, q, qd, cf, _ = self.phys.substep(s["root_states"].astype(float), s["dof_pos"].astype(float),
                                                s["dof_vel"].astype(float), tau.astype(float), self.damping,
                                                self.armature, self.mass_scale,

@@ -101,6 +101,25 @@ def test_cuda_self_collision_matches_oracle(program, caps, monkeypatch):
     core.close()
 
 
+def test_batched_oracle_equals_the_loop_oracle():
+    """oracle/selfcollision_oracle.py states the computation twice: per env with explicit loops (the restatement the
+    kernel is compared with) and vectorised over envs (what EnvOracle and bench.py's CPU arms run). Same forces."""
+    from oracle.selfcollision_oracle import self_contact_forces_batch
+    from tests.test_humanoid_generality import humanoid
+    rng = np.random.default_rng(5)
+    for t, q0, sig in ((tocabi()[0], np.array(INIT_DOF_POS), 0.5), (humanoid(), None, None)):
+        sc = self_collision_tables(t)
+        N = 12
+        qs = [np.clip(q0 + rng.normal(0, sig, len(q0)), t.dof_lower, t.dof_upper) if q0 is not None
+              else rng.uniform(t.dof_lower, t.dof_upper) for _ in range(N)]
+        fks = [SC.link_fk(t, q) for q in qs]
+        want = np.stack([self_contact_forces(sc, Rw, pw, 2e5, 2e4) for Rw, pw in fks])
+        Rw = [np.stack([fk[0][l] for fk in fks]) for l in range(t.num_links)]
+        pw = [np.stack([fk[1][l] for fk in fks]) for l in range(t.num_links)]
+        got = self_contact_forces_batch(sc, Rw, pw, 2e5, 2e4)
+        assert np.abs(want).max() > 100.0 and np.allclose(got[:, : want.shape[1]], want, rtol=1e-9, atol=1e-6)
+
+
 def test_humanoid_capsule_tables_known_answers():
     """The stock Humanoid (assets/mjcf/nv_humanoid.xml; tasks/humanoid.py creates its actor with filter 0 as well): capsules
     and spheres as shape kind 2."""
