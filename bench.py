@@ -553,7 +553,12 @@ def run_ppo(a):
                 "breakdown_ms_per_epoch": {"rollout_and_gae": t_roll / K, "update": t_upd / K,
                                            "update_per_minibatch": t_upd / K / updates,
                                            "allreduce_alone_per_call": ar_ms, "allreduce_alone_per_epoch": ar_ms * updates},
-                "gpu_launches": None, "last_epoch": out}
+                # this library's kernels per epoch (the cuBLAS GEMMs between them are not counted): per rollout step
+                # cast_obs, 2 x bias_relu, act, the env step's launches, reward, advance; GAE; per update 2 x bias_relu,
+                # loss_grad, 2 x relu_bwd, unpack (+ reduce_peers at N > 1), adam_pack, adam_finish
+                "gpu_launches": (K * (tr.H * (6 + env.core.step_launches()) + 1 + tr.cfg.mini_epochs * tr.num_minibatches * (8 + (world > 1)))
+                                 if tr.packed is not None else None),
+                "last_epoch": out}
         emit(line)
     if world > 1:
         # the CUDA graphs hold captured NCCL work: drop them before the communicator goes, and do not wait on a
