@@ -223,6 +223,11 @@ class Sim:
         self.frame_count = 0
         self.pending_wrench = False
         self._descs = {}
+        # collision filter of create_actor (docs/_sources/programming/assets.rst.txt:107-109: two shapes collide unless
+        # their filter masks share a bit; 0 = the actor's shapes collide with each other, as T:354 asks; a non-zero mask
+        # on every shape, e.g. 1, switches self-collision off). -1 (filters from the asset file) is read as 0: the MJCF
+        # files of this path carry none.
+        self.self_collision = True
 
 
 def _cfg_from_sim(sim: Sim) -> CoreConfig:
@@ -231,7 +236,7 @@ def _cfg_from_sim(sim: Sim) -> CoreConfig:
                      contact_offset=p.physx.contact_offset, max_depenetration_velocity=p.physx.max_depenetration_velocity,
                      num_position_iterations=p.physx.num_position_iterations,
                      num_velocity_iterations=p.physx.num_velocity_iterations,
-                     with_rigid_body_state=True, with_rb_force_tensors=True)
+                     with_rigid_body_state=True, with_rb_force_tensors=True, self_collision=sim.self_collision)
     cfg.penalty_stiffness, cfg.penalty_damping = stable_penalty(p.dt / p.substeps)
     if sim.plane is not None:
         cfg.friction = float(sim.plane.dynamic_friction)  # shape friction default 1.0
@@ -338,6 +343,8 @@ class Gym:
         if env.actor_names:
             raise native.DyrosError("create_actor: one actor per env is implemented (T:354)")
         env.actor_names.append(name)
+        if filter > 0:
+            sim.self_collision = False
         t = asset.tables
         sim.start_poses.append(pose)
         props = np.zeros(t.num_dofs, dtype=DOF_PROPS_DTYPE)

@@ -94,6 +94,30 @@ def test_gym_tensor_api_loop_matches_core_and_indexed_reset():
     gym.destroy_sim(sim)
 
 
+def test_collision_filter_of_create_actor_switches_self_collision():
+    """create_actor(..., group, filter, seg): filter 0 = the actor's shapes collide with each other (T:354), a non-zero mask
+    shared by all its shapes switches that off (assets.rst.txt:107-109). Seen at the API: two launches per simulate vs one."""
+    from isaacgymdyros_b200 import gymapi
+    out = {}
+    for flt in (0, 1):
+        gym = gymapi.acquire_gym()
+        sp = gymapi.SimParams()
+        sp.dt, sp.substeps, sp.up_axis, sp.gravity = 0.002, 1, gymapi.UP_AXIS_Z, gymapi.Vec3(0.0, 0.0, -9.81)
+        sp.use_gpu_pipeline = True
+        sim = gym.create_sim(0, -1, gymapi.SIM_PHYSX, sp)
+        pp = gymapi.PlaneParams()
+        pp.normal = gymapi.Vec3(0.0, 0.0, 1.0)
+        gym.add_ground(sim, pp)
+        asset = gym.load_asset(sim, "../assets", "mjcf/dyros_tocabi/xml/dyros_tocabi.xml", gymapi.AssetOptions())
+        for i in range(4):
+            env = gym.create_env(sim, gymapi.Vec3(0, 0, 0), gymapi.Vec3(0, 0, 0), 2)
+            gym.create_actor(env, asset, gymapi.Transform(gymapi.Vec3(5.0 * i, 0.0, 0.93), gymapi.Quat(0, 0, 0, 1)), "humanoid", i, flt, 0)
+        assert gym.prepare_sim(sim)
+        out[flt] = sim.core.cfg.self_collision
+        sim.core.close()
+    assert out == {0: True, 1: False}
+
+
 def test_create_sim_failure_returns_none():
     from isaacgymdyros_b200 import gymapi
     gym = gymapi.acquire_gym()
