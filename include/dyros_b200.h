@@ -20,6 +20,7 @@
 #ifndef DYROS_B200_H
 #define DYROS_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus

@@ -66,3 +66,18 @@ def test_core_refuses_to_run_without_gpu():
     from isaacgymdyros_b200.core import DyrosCore
     with pytest.raises(native.DyrosError):
         DyrosCore(4)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/dyros_b200.h is the drop-in boundary for C callers (cgo / JNI / ctypes generators): it must compile as C11 by
+    itself, with nothing but its own includes."""
+    import os
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "dyros_b200.h"\nint main(void) { return sizeof(DyrosPpoPeers) > 0 && sizeof(DyrosModelDesc) > 0 ? 0 : 1; }\n')
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"), "-fsyntax-only", str(src)])
