@@ -326,3 +326,22 @@ def test_checkpoint_round_trip_and_weight_dump(tmp_path):
     w = np.loadtxt(str(tmp_path / "result" / "a2c_network_mu_weight.txt"))
     assert np.allclose(w, tr.net.layers["mu"][0].detach().cpu().numpy())
     env.close(); env2.close()
+
+
+def test_on_device_ppo_learns_to_stay_up():
+    """The whole stack end to end (fused env step with self-collision, packed bf16 networks, CUDA-graphed rollout and
+    mini-epochs, the reference's hyper-parameters) at the benchmark's size: 60 epochs = 31 M env-steps, a few seconds.
+    Episodes must get longer (profiles/r2_ppo_learning_curve.md: 108 -> ~380 policy steps by epoch 60)."""
+    from isaacgymdyros_b200 import DyrosDynamicWalk, default_cfg
+    from isaacgymdyros_b200.ppo import PPOConfig, PPOTrainer
+    env = DyrosDynamicWalk(default_cfg(4096), DEV, use_cuda_graph=False)
+    tr = PPOTrainer(env, PPOConfig())
+    first = tr.train_epoch()
+    for _ in range(58):
+        tr.train_epoch()
+    last = tr.train_epoch()
+    assert all(math.isfinite(v) for v in last.values()), last
+    assert first["episodes"] > 1000 and 60 < first["mean_length"] < 200, first
+    assert last["mean_length"] > 2.0 * first["mean_length"] and last["mean_reward"] > 2.0 * first["mean_reward"], (first, last)
+    assert bool(torch.isfinite(env.obs_buf).all())
+    env.close()
